@@ -1,0 +1,301 @@
+"""ctypes binding of include/bpt_c_api.h. Arrays are numpy; nothing here computes anything."""
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG = Path(__file__).resolve().parent
+_LIB = None
+
+
+class BptError(RuntimeError):
+    pass
+
+
+def library_path() -> Path:
+    return _PKG / "libbpt.so"
+
+
+class Material(C.Structure):  # Types.h:353-416
+    _fields_ = [("flags", C.c_uint16), ("shading_model", C.c_uint16), ("tint", C.c_float * 3), ("roughness", C.c_float),
+                ("tint_roughness_texture_id", C.c_int32), ("roughness_texture_id", C.c_int32), ("specularity", C.c_float),
+                ("metallic", C.c_float), ("metallic_texture_id", C.c_int32), ("coverage", C.c_float),
+                ("coverage_texture_id", C.c_int32), ("emission", C.c_float * 3), ("coat", C.c_uint16), ("coat_roughness", C.c_uint16)]
+
+
+class Light(C.Structure):  # Types.h:290-312
+    _fields_ = [("data", C.c_float * 11), ("flags", C.c_uint32)]
+
+
+class LightSample(C.Structure):  # Types.h:210-222
+    _fields_ = [("radiance", C.c_float * 3), ("pdf", C.c_float), ("direction_to_light", C.c_float * 3), ("distance", C.c_float)]
+
+
+class Instance(C.Structure):
+    _fields_ = [("mesh_id", C.c_int32), ("material_id", C.c_int32), ("to_world", C.c_float * 12)]
+
+
+class Camera(C.Structure):
+    _fields_ = [("view_to_world_rotation", C.c_float * 9), ("inverse_projection", C.c_float * 16), ("inverse_view_projection", C.c_float * 16)]
+
+
+class Settings(C.Structure):
+    _fields_ = [("max_bounce_count", C.c_uint32), ("next_event_sample_count", C.c_int32), ("path_regularization_pdf_scale", C.c_float), ("reserved", C.c_uint32)]
+
+
+class Counters(C.Structure):
+    _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("extend_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float)]
+
+
+assert C.sizeof(Material) == 64 and C.sizeof(Light) == 48 and C.sizeof(LightSample) == 32
+
+MATERIAL_DTYPE = np.dtype([("flags", "<u2"), ("shading_model", "<u2"), ("tint", "<f4", 3), ("roughness", "<f4"),
+                           ("tint_roughness_texture_id", "<i4"), ("roughness_texture_id", "<i4"), ("specularity", "<f4"),
+                           ("metallic", "<f4"), ("metallic_texture_id", "<i4"), ("coverage", "<f4"), ("coverage_texture_id", "<i4"),
+                           ("emission", "<f4", 3), ("coat", "<u2"), ("coat_roughness", "<u2")])
+LIGHT_DTYPE = np.dtype([("data", "<f4", 11), ("flags", "<u4")])
+LIGHT_SAMPLE_DTYPE = np.dtype([("radiance", "<f4", 3), ("pdf", "<f4"), ("direction_to_light", "<f4", 3), ("distance", "<f4")])
+INSTANCE_DTYPE = np.dtype([("mesh_id", "<i4"), ("material_id", "<i4"), ("to_world", "<f4", 12)])
+assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SAMPLE_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 56
+
+LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
+
+EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_upload_mesh", "bpt_set_instances",
+           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render",
+           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_get_counters",
+           "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
+           "bpt_intersect"]
+
+
+def load_library():
+    """Loads libbpt.so. Fails loudly if the CUDA extension has not been built: there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not path.exists():
+        raise BptError(f"{path} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(path))
+    vp, i32, i64, u32 = C.c_void_p, C.c_int, C.c_int64, C.c_uint32
+    lib.bpt_create.argtypes = [i32, C.POINTER(vp)]
+    lib.bpt_destroy.argtypes = [vp]; lib.bpt_destroy.restype = None
+    lib.bpt_last_error.argtypes = [vp]; lib.bpt_last_error.restype = C.c_char_p
+    lib.bpt_stream.argtypes = [vp]; lib.bpt_stream.restype = vp
+    lib.bpt_set_tables.argtypes = [vp, vp, vp, vp]
+    lib.bpt_upload_mesh.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
+    lib.bpt_set_instances.argtypes = [vp, vp, i32]
+    lib.bpt_set_materials.argtypes = [vp, vp, i32]
+    lib.bpt_set_lights.argtypes = [vp, vp, i32]
+    lib.bpt_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]
+    lib.bpt_build_accel.argtypes = [vp]
+    lib.bpt_accel_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
+    lib.bpt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), i32, i32, u32, u32, i32]
+    lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
+    lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
+    lib.bpt_resolve_float4.argtypes = [vp, vp]
+    lib.bpt_synchronize.argtypes = [vp]
+    lib.bpt_get_counters.argtypes = [vp, C.POINTER(Counters), i32]
+    lib.bpt_bsdf_eval_sample_pdf.argtypes = [vp, i32, i64] + [vp] * 11 + [i32]
+    lib.bpt_default_shading_regularized.argtypes = [vp, i64] + [vp] * 11
+    lib.bpt_light_sample_pdf_evaluate.argtypes = [vp, i64, vp, i32, vp, vp, vp, vp, vp, vp]
+    lib.bpt_rng_sample4.argtypes = [vp, i64, vp, vp, vp, vp, vp]
+    lib.bpt_intersect.argtypes = [vp, i64] + [vp] * 8
+    for name in EXPORTS:
+        if getattr(lib, name).restype is C.c_int:
+            pass
+    _LIB = lib
+    return lib
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_tables():
+    t = np.fromfile(_PKG / "data" / "shading_tables.bin", dtype="<f4")
+    assert t.size == 3 * 1024
+    return t[:1024].copy(), t[1024:2048].copy(), t[2048:].copy()
+
+
+class Bpt:
+    """One path tracer context on one CUDA device (mirrors OptiXRenderer::Renderer::initialize)."""
+
+    def __init__(self, device: int = 0, tables=True):
+        self.lib = load_library()
+        handle = C.c_void_p()
+        status = self.lib.bpt_create(device, C.byref(handle))
+        if status != 0:
+            raise BptError(f"bpt_create(device={device}) failed with status {status}: no usable CUDA device. There is no CPU fallback.")
+        self.h = handle
+        if tables:
+            self.set_tables(*default_tables())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bpt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, status):
+        if status != 0:
+            raise BptError(f"status {status}: {self.lib.bpt_last_error(self.h).decode()}")
+
+    @property
+    def stream(self):
+        return self.lib.bpt_stream(self.h)
+
+    def synchronize(self):
+        self._check(self.lib.bpt_synchronize(self.h))
+
+    def set_tables(self, ggx_with_fresnel, ggx, alpha):
+        a, b, c = _f32(ggx_with_fresnel), _f32(ggx), _f32(alpha)
+        assert a.size == b.size == c.size == 1024
+        self._check(self.lib.bpt_set_tables(self.h, _ptr(a), _ptr(b), _ptr(c)))
+
+    # ---- scene ----
+    def upload_mesh(self, mesh_id, indices, positions, normals=None, texcoords=None, tint_roughness=None):
+        idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1, 3)
+        pos = _f32(positions).reshape(-1, 3)
+        nrm = None if normals is None else _f32(normals).reshape(-1, 3)
+        uv = None if texcoords is None else _f32(texcoords).reshape(-1, 2)
+        tr = None if tint_roughness is None else np.ascontiguousarray(tint_roughness, dtype=np.uint8).reshape(-1, 4)
+        for a in (nrm, uv, tr):
+            assert a is None or a.shape[0] == pos.shape[0]
+        self._check(self.lib.bpt_upload_mesh(self.h, mesh_id, _ptr(idx), idx.shape[0], _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(tr), pos.shape[0]))
+
+    def set_instances(self, instances):
+        inst = np.ascontiguousarray(instances, dtype=INSTANCE_DTYPE)
+        self._check(self.lib.bpt_set_instances(self.h, _ptr(inst), inst.shape[0]))
+
+    def set_materials(self, materials):
+        m = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
+        self._check(self.lib.bpt_set_materials(self.h, _ptr(m), m.shape[0]))
+
+    def set_lights(self, lights):
+        l = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE)
+        self._check(self.lib.bpt_set_lights(self.h, _ptr(l) if l.size else None, l.shape[0]))
+
+    def set_environment(self, tint, texels=None, per_pixel_pdf=None, samples=None):
+        t = _f32(tint, (3,))
+        if texels is None:
+            self._check(self.lib.bpt_set_environment(self.h, _ptr(t), None, 0, 0, None, 0, 0, None, 0))
+            return
+        tex = _f32(texels); assert tex.ndim == 3 and tex.shape[2] == 4
+        pdf = _f32(per_pixel_pdf); assert pdf.ndim == 2
+        s = np.ascontiguousarray(samples, dtype=LIGHT_SAMPLE_DTYPE)
+        self._check(self.lib.bpt_set_environment(self.h, _ptr(t), _ptr(tex), tex.shape[1], tex.shape[0], _ptr(pdf), pdf.shape[1], pdf.shape[0], _ptr(s), s.shape[0]))
+
+    def build_accel(self):
+        self._check(self.lib.bpt_build_accel(self.h))
+
+    def accel_info(self):
+        t, n, ms = C.c_int64(), C.c_int64(), C.c_float()
+        self._check(self.lib.bpt_accel_info(self.h, C.byref(t), C.byref(n), C.byref(ms)))
+        return {"triangles": t.value, "nodes": n.value, "build_ms": ms.value}
+
+    # ---- rendering ----
+    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, reset=False):
+        cam = camera if isinstance(camera, Camera) else make_camera(*camera)
+        s = Settings(max_bounces, nee_samples, pdf_scale, 0)
+        self._check(self.lib.bpt_render(self.h, C.byref(cam), C.byref(s), width, height, first_sample, sample_count, int(reset)))
+        self._size = (width, height)
+
+    def accumulation_device_ptr(self):
+        return self.lib.bpt_accumulation_device_ptr(self.h)
+
+    def resolve_float4(self):
+        w, h = self._size
+        out = np.empty((h, w, 4), np.float32)
+        self._check(self.lib.bpt_resolve_float4(self.h, _ptr(out)))
+        return out
+
+    def resolve_half4(self):
+        w, h = self._size
+        out = np.empty((h, w, 4), np.uint16)
+        self._check(self.lib.bpt_resolve_half4(self.h, _ptr(out), 0))
+        return out.view(np.float16)
+
+    def counters(self, reset=False):
+        c = Counters()
+        self._check(self.lib.bpt_get_counters(self.h, C.byref(c), int(reset)))
+        return {k: getattr(c, k) for k, _ in Counters._fields_}
+
+    # ---- batched unit entry points (host arrays) ----
+    def bsdf_eval_sample_pdf(self, kind, wo, wi, tint, rms, u, coat=None):
+        wo, wi, tint, rms, u = (_f32(a).reshape(-1, 3) for a in (wo, wi, tint, rms, u))
+        n = wo.shape[0]
+        coat = None if coat is None else _f32(coat).reshape(-1, 2)
+        ef, sf, sd = (np.empty((n, 3), np.float32) for _ in range(3))
+        ep, sp = (np.empty(n, np.float32) for _ in range(2))
+        self._check(self.lib.bpt_bsdf_eval_sample_pdf(self.h, kind, n, _ptr(wo), _ptr(wi), _ptr(tint), _ptr(rms), _ptr(coat), _ptr(u),
+                                                      _ptr(ef), _ptr(ep), _ptr(sf), _ptr(sp), _ptr(sd), 0))
+        return {"eval_f": ef, "eval_pdf": ep, "sample_f": sf, "sample_pdf": sp, "sample_dir": sd}
+
+    def bsdf_eval_sample_pdf_device(self, kind, n, ptrs):
+        """ptrs: dict of raw device pointers (ints) with the argument names of bpt_bsdf_eval_sample_pdf."""
+        order = ["wo", "wi", "tint", "rms", "coat", "u", "eval_f", "eval_pdf", "sample_f", "sample_pdf", "sample_dir"]
+        args = [C.c_void_p(ptrs.get(k) or None) for k in order]
+        self._check(self.lib.bpt_bsdf_eval_sample_pdf(self.h, kind, n, *args, 1))
+
+    def default_shading_regularized(self, materials, max_pdf_hint, wo, wi, u, tint_roughness_scale=None):
+        m = np.ascontiguousarray(materials, dtype=MATERIAL_DTYPE)
+        n = m.shape[0]
+        hint = _f32(max_pdf_hint, (n,)); wo, wi, u = (_f32(a).reshape(n, 3) for a in (wo, wi, u))
+        sc = None if tint_roughness_scale is None else _f32(tint_roughness_scale).reshape(n, 4)
+        ef, sf, sd = (np.empty((n, 3), np.float32) for _ in range(3))
+        ep, sp = (np.empty(n, np.float32) for _ in range(2))
+        self._check(self.lib.bpt_default_shading_regularized(self.h, n, _ptr(m), _ptr(sc), _ptr(hint), _ptr(wo), _ptr(wi), _ptr(u),
+                                                             _ptr(ef), _ptr(ep), _ptr(sf), _ptr(sp), _ptr(sd)))
+        return {"eval_f": ef, "eval_pdf": ep, "sample_f": sf, "sample_pdf": sp, "sample_dir": sd}
+
+    def light_sample_pdf_evaluate(self, lights, position, u2, query_direction):
+        l = np.ascontiguousarray(lights, dtype=LIGHT_DTYPE).reshape(-1)
+        position, query_direction = _f32(position).reshape(-1, 3), _f32(query_direction).reshape(-1, 3)
+        u2 = _f32(u2).reshape(-1, 2)
+        n = position.shape[0]
+        stride = 0 if l.shape[0] == 1 and n != 1 else 1
+        assert stride == 0 or l.shape[0] == n
+        samples = np.empty(n, LIGHT_SAMPLE_DTYPE); pdf = np.empty(n, np.float32); rad = np.empty((n, 3), np.float32)
+        self._check(self.lib.bpt_light_sample_pdf_evaluate(self.h, n, _ptr(l), stride, _ptr(position), _ptr(u2), _ptr(query_direction),
+                                                           _ptr(samples), _ptr(pdf), _ptr(rad)))
+        return samples, pdf, rad
+
+    def rng_sample4(self, accumulation, pixel_hash, dimension):
+        a, h, d = (np.ascontiguousarray(x, dtype=np.uint32).reshape(-1) for x in (accumulation, pixel_hash, dimension))
+        n = a.shape[0]
+        ui = np.empty((n, 4), np.uint32); f = np.empty((n, 4), np.float32)
+        self._check(self.lib.bpt_rng_sample4(self.h, n, _ptr(a), _ptr(h), _ptr(d), _ptr(ui), _ptr(f)))
+        return ui, f
+
+    def intersect(self, origins, directions, tmin=None, tmax=None, want_occluded=True):
+        o, d = _f32(origins).reshape(-1, 3), _f32(directions).reshape(-1, 3)
+        n = o.shape[0]
+        tmin = np.zeros(n, np.float32) if tmin is None else _f32(np.broadcast_to(tmin, (n,)))
+        tmax = np.full(n, 1e30, np.float32) if tmax is None else _f32(np.broadcast_to(tmax, (n,)))
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32); uv = np.empty((n, 2), np.float32)
+        occ = np.empty(n, np.uint8) if want_occluded else None
+        self._check(self.lib.bpt_intersect(self.h, n, _ptr(o), _ptr(d), _ptr(tmin), _ptr(tmax), _ptr(prim), _ptr(t), _ptr(uv), _ptr(occ)))
+        return prim, t, uv, occ
+
+
+def make_camera(view_to_world_rotation, inverse_projection, inverse_view_projection):
+    cam = Camera()
+    cam.view_to_world_rotation[:] = [float(x) for x in np.asarray(view_to_world_rotation, np.float32).reshape(9)]
+    cam.inverse_projection[:] = [float(x) for x in np.asarray(inverse_projection, np.float32).reshape(16)]
+    cam.inverse_view_projection[:] = [float(x) for x in np.asarray(inverse_view_projection, np.float32).reshape(16)]
+    return cam

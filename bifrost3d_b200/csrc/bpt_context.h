@@ -1,0 +1,146 @@
+// Host-side context of the path tracer: owns every device allocation.
+// Data layout in HBM is described in DESIGN.md ("Data layout").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "bpt_types.h"
+
+namespace bpt {
+
+// Growable device buffer.
+template <typename T>
+struct DeviceBuffer {
+    T* ptr = nullptr;
+    size_t capacity = 0; // elements
+    size_t size = 0;
+
+    cudaError_t reserve(size_t n) {
+        if (n <= capacity) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr; capacity = 0;
+        cudaError_t e = cudaMalloc((void**)&ptr, n * sizeof(T));
+        if (e == cudaSuccess) capacity = n;
+        return e;
+    }
+    cudaError_t resize(size_t n) { cudaError_t e = reserve(n); if (e == cudaSuccess) size = n; return e; }
+    void release() { if (ptr) cudaFree(ptr); ptr = nullptr; capacity = size = 0; }
+    size_t bytes() const { return size * sizeof(T); }
+};
+
+struct HostMesh {
+    std::vector<uint32_t> indices;   // 3 per primitive
+    std::vector<float> positions;    // 3 per vertex
+    std::vector<int16_t> normals;    // 2 per vertex (octahedral), empty if the mesh has none
+    std::vector<float> texcoords;    // 2 per vertex or empty
+    std::vector<uint8_t> tints;      // 4 per vertex or empty
+    int primitive_count = 0;
+    int vertex_count = 0;
+};
+
+// BVH node, 64 bytes, two children per node: child AABBs are stored in the parent so one 64 byte
+// (4 x 128-bit) load decides both children. A negative child index c encodes a leaf: ~c = first
+// triangle slot; leaf triangle counts are in `counts` (0 for inner children).
+struct __align__(16) BvhNode {
+    float4 lo_l_hi_l_x;   // left.lo.x, left.lo.y, left.lo.z, left.hi.x
+    float4 hi_l_lo_r;     // left.hi.y, left.hi.z, right.lo.x, right.lo.y
+    float4 lo_r_hi_r;     // right.lo.z, right.hi.x, right.hi.y, right.hi.z
+    int left, right;      // child node index, or ~first_triangle for leaves
+    int left_count, right_count;
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+// World-space triangle in traversal order: three float4 loads. The w lanes carry the global primitive
+// index (bits of v0.w), the material index (v1.w) and the cull/coverage flags (v2.w).
+struct __align__(16) TraceTriangle {
+    float4 v0, v1, v2;
+};
+static_assert(sizeof(TraceTriangle) == 48, "TraceTriangle must be 48 bytes");
+
+// Per-primitive shading attributes, indexed by global primitive index (instance-major order).
+struct __align__(16) ShadeTriangle {
+    // Octahedral vertex normals (3 x short2), per-vertex tint/roughness (3 x uchar4), material index, flags.
+    int16_t n0[2], n1[2], n2[2];
+    uint8_t t0[4], t1[4], t2[4];
+    int32_t material_index;
+    uint32_t flags; // bit0 has normals, bit1 has tints
+};
+static_assert(sizeof(ShadeTriangle) == 32, "ShadeTriangle must be 32 bytes");
+
+struct Accel {
+    DeviceBuffer<BvhNode> nodes;
+    DeviceBuffer<TraceTriangle> triangles;      // traversal order (Morton sorted)
+    DeviceBuffer<float4> world_vertices;        // 3 per primitive, instance-major order: position.xyz, w unused
+    DeviceBuffer<ShadeTriangle> shade;          // instance-major order
+    int64_t triangle_count = 0;
+    int64_t node_count = 0;
+    float build_ms = 0.0f;
+    float3 scene_lo, scene_hi;
+    bool valid = false;
+};
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string last_error;
+    int sm_count = 148;
+
+    // Tables: [ggx_with_fresnel_rho | ggx_rho | estimate_alpha], 3 x 1024 floats.
+    DeviceBuffer<float> tables;
+    bool has_tables = false;
+    DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
+
+    std::map<int, HostMesh> meshes;
+    std::vector<bpt_instance> instances;
+    DeviceBuffer<Material> materials;
+    std::vector<Material> host_materials;
+    DeviceBuffer<Light> lights;
+    int light_count = 0;
+
+    // Environment
+    DeviceBuffer<float4> env_texels;
+    DeviceBuffer<float> env_pdf;
+    DeviceBuffer<bpt_light_sample> env_samples;
+    int env_width = 0, env_height = 0, env_pdf_width = 0, env_pdf_height = 0, env_sample_count = 0;
+    float env_tint[3] = {0.0f, 0.0f, 0.0f};
+
+    Accel accel;
+
+    // Render state
+    int width = 0, height = 0;
+    DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
+    void* wavefront = nullptr;         // integrator-owned state (bpt_render.cu)
+
+    bpt_counters counters = {};
+    uint64_t* device_counters = nullptr; // [extend, shadow]
+
+    cudaEvent_t ev[8] = {};
+
+    int fail(int status, const std::string& msg) { last_error = msg; return status; }
+    int cuda_fail(cudaError_t e, const char* what) {
+        last_error = std::string(what) + ": " + cudaGetErrorString(e);
+        return e == cudaErrorMemoryAllocation ? BPT_ERROR_OUT_OF_MEMORY : BPT_ERROR_CUDA;
+    }
+};
+
+#define BPT_CUDA_CHECK(ctx, expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return (ctx)->cuda_fail(_e, #expr); } while (0)
+
+inline Context* as_context(bpt_ctx* c) { return reinterpret_cast<Context*>(c); }
+inline const Context* as_context(const bpt_ctx* c) { return reinterpret_cast<const Context*>(c); }
+
+// Implemented in bpt_bvh.cu
+int build_accel(Context* ctx);
+int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* directions, const float* tmin, const float* tmax,
+                    int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded);
+// Implemented in bpt_render.cu
+int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
+           uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
+int resolve_half4(Context* ctx, uint16_t* out, int on_device);
+int resolve_float4(Context* ctx, float* out);
+void release_wavefront(Context* ctx);
+
+} // namespace bpt

@@ -1,0 +1,352 @@
+// Light sources: sampling, PDF and evaluation.
+//   Sphere       extensions/OptiXRenderer/OptiXRenderer/Shading/LightSources/SphereLightImpl.h:22-103
+//   Spot         .../SpotLightImpl.h:22-130
+//   Directional  .../DirectionalLightImpl.h:17-52
+//   dispatch     .../LightImpl.h:23-108
+//   ray/sphere, ray/plane, ray/disk  .../Intersect.h:23-67
+//   TBN          .../TBN.h:27-58, compute_tangents Utils.h:347-356
+//   environment  .../PresampledEnvironmentLightImpl.h:17-55, latlong mapping Utils.h:288-301
+#pragma once
+#include "bpt_shading.cuh"
+
+namespace bpt {
+
+struct LightSample {
+    float3 radiance;
+    Pdf pdf;
+    float3 direction_to_light;
+    float distance;
+};
+
+BPT_D LightSample light_sample_none() {
+    LightSample s;
+    s.radiance = f3(0.0f);
+    s.pdf = Pdf::delta_dirac(0.0f);
+    s.direction_to_light = f3(0.0f, 1.0f, 0.0f);
+    s.distance = 0.0f;
+    return s;
+}
+
+// Orthonormal basis (Duff et al.), Utils.h:347-356.
+struct Tbn {
+    float3 tangent, bitangent, normal;
+    BPT_D explicit Tbn(float3 n) : normal(n) {
+        float sign = copysignf(1.0f, n.z);
+        const float a = -1.0f / (sign + n.z);
+        const float b = n.x * n.y * a;
+        tangent = f3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+        bitangent = f3(b, sign + n.y * n.y * a, -n.y);
+    }
+    // world -> local
+    BPT_D float3 to_local(float3 v) const { return f3(dot(tangent, v), dot(bitangent, v), dot(normal, v)); }
+    // local -> world
+    BPT_D float3 to_world(float3 v) const { return v.x * tangent + v.y * bitangent + v.z * normal; }
+};
+
+namespace isect {
+BPT_D float ray_sphere(float3 ray_origin, float3 ray_direction, float3 sphere_center, float sphere_radius) {
+    float3 direction_to_sphere = ray_origin - sphere_center;
+    float b = dot(direction_to_sphere, ray_direction);
+    float radius_squared = sphere_radius * sphere_radius;
+    float3 fbd = direction_to_sphere - b * ray_direction;
+    float d = radius_squared - dot(fbd, fbd);
+    if (d > 0.0f)
+        return -b - sqrtf(d);
+    return nanf("");
+}
+BPT_D float ray_plane(float3 ray_origin, float3 ray_direction, float3 plane_point, float3 plane_normal) {
+    float d = dot(plane_normal, plane_point);
+    float n_dot_o = dot(plane_normal, ray_origin);
+    float n_dot_d = dot(plane_normal, ray_direction);
+    return (d - n_dot_o) / n_dot_d;
+}
+BPT_D float ray_disk(float3 ray_origin, float3 ray_direction, float3 disk_center, float3 disk_normal, float disk_radius) {
+    float distance_to_plane = ray_plane(ray_origin, ray_direction, disk_center, disk_normal);
+    float3 plane_intersection = ray_origin + ray_direction * distance_to_plane;
+    float3 v = plane_intersection - disk_center;
+    float distance_squared = dot(v, v);
+    if (distance_squared <= disk_radius * disk_radius && distance_to_plane >= 0.0f)
+        return distance_to_plane;
+    return nanf("");
+}
+BPT_D float point_distance_to_plane(float3 point, float3 plane_point, float3 plane_normal) {
+    return dot(plane_normal, plane_point) - dot(plane_normal, point);
+}
+} // namespace isect
+
+// ---- typed views on the 48 byte Light POD -------------------------------------------------------
+struct SphereLight { float3 power, position; float radius; };
+struct SpotLight { float3 power, position; float radius; float3 direction; float cos_angle; };
+struct DirectionalLight { float3 radiance, direction; };
+
+BPT_D uint32_t light_type(const Light& l) { return l.flags & BPT_LIGHT_TYPE_MASK; }
+BPT_D SphereLight as_sphere(const Light& l) {
+    SphereLight s; s.power = f3(l.data[0], l.data[1], l.data[2]); s.position = f3(l.data[3], l.data[4], l.data[5]); s.radius = l.data[6]; return s;
+}
+BPT_D SpotLight as_spot(const Light& l) {
+    SpotLight s; s.power = f3(l.data[0], l.data[1], l.data[2]); s.position = f3(l.data[3], l.data[4], l.data[5]); s.radius = l.data[6];
+    s.direction = f3(l.data[7], l.data[8], l.data[9]); s.cos_angle = l.data[10]; return s;
+}
+BPT_D DirectionalLight as_directional(const Light& l) {
+    DirectionalLight d; d.radiance = f3(l.data[0], l.data[1], l.data[2]); d.direction = f3(l.data[3], l.data[4], l.data[5]); return d;
+}
+
+// ---- sphere light ------------------------------------------------------------------------------
+namespace sphere_light {
+constexpr float small_sin_theta_squared = 0.0f;
+
+BPT_D float surface_area(const SphereLight& l) { return 4.0f * PI_F * l.radius * l.radius; }
+
+BPT_D bool is_delta(const SphereLight& l, float3 position) {
+    float3 v = l.position - position;
+    float sin_theta_squared = l.radius * l.radius / dot(v, v);
+    return sin_theta_squared <= small_sin_theta_squared;
+}
+
+BPT_D LightSample sample_radiance(const SphereLight& l, float3 position, float2 u) {
+    float3 vector_to_light = l.position - position;
+    float sin_theta_squared = l.radius * l.radius / dot(vector_to_light, vector_to_light);
+
+    LightSample s;
+    if (sin_theta_squared <= small_sin_theta_squared) {
+        s.direction_to_light = vector_to_light;
+        s.distance = length(s.direction_to_light);
+        s.direction_to_light /= s.distance;
+        s.radiance = l.power / (4.0f * PI_F * s.distance * s.distance);
+        s.distance -= l.radius;
+        s.pdf = Pdf::delta_dirac(1.0f);
+    } else {
+        float cos_theta = sqrtf(1.0f - sin_theta_squared);
+        DirectionalSample cone = dist::cone_sample(cos_theta, u);
+        const Tbn tbn(normalize(vector_to_light));
+        s.direction_to_light = tbn.to_world(cone.direction);
+        s.pdf = Pdf(cone.pdf);
+        s.distance = isect::ray_sphere(position, s.direction_to_light, l.position, l.radius);
+        if (s.distance <= 0.0f)
+            s.distance = dot(vector_to_light, s.direction_to_light);
+        float inv_divisor = 1.0f / (PI_F * surface_area(l));
+        s.radiance = l.power * inv_divisor;
+    }
+    s.distance = nextafterf(s.distance, 0.0f);
+    return s;
+}
+
+BPT_D Pdf pdf(const SphereLight& l, float3 lit_position, float3 direction_to_light) {
+    float3 v = l.position - lit_position;
+    float sin_theta_squared = l.radius * l.radius / dot(v, v);
+    if (sin_theta_squared < small_sin_theta_squared)
+        return Pdf::delta_dirac(0.0f);
+    float cos_theta_max = sqrtf(1.0f - sin_theta_squared);
+    float cos_theta = dot(direction_to_light, normalize(v));
+    float valid_direction = cos_theta >= cos_theta_max ? 1.0f : 0.0f;
+    return Pdf(dist::cone_pdf(cos_theta_max) * valid_direction);
+}
+
+BPT_D float3 evaluate(const SphereLight& l, float3 position) {
+    float inv_divisor = 1.0f / (is_delta(l, position) ? (4.0f * PI_F) : (PI_F * surface_area(l)));
+    return l.power * inv_divisor;
+}
+} // namespace sphere_light
+
+// ---- spot light --------------------------------------------------------------------------------
+namespace spot_light {
+constexpr float min_cone_angle_to_sample = 1e-5f;
+
+BPT_D float surface_area(const SpotLight& l) { return PI_F * pow2(l.radius); }
+BPT_D bool is_delta(const SpotLight& l) { return l.radius == 0.0f; }
+
+BPT_D Pdf pdf(const SpotLight& l, float3 lit_position, float3 direction_to_light) {
+    float cos_theta = -dot(l.direction, direction_to_light);
+    if (cos_theta > 0.0f && !is_delta(l)) {
+        float t = isect::ray_plane(lit_position, -l.direction, l.position, l.direction);
+        float cone_radius_at_intersection = t * sqrtf(1.0f - pow2(l.cos_angle)) / l.cos_angle;
+        if (l.radius > cone_radius_at_intersection && l.cos_angle > min_cone_angle_to_sample)
+            return Pdf(dist::cone_pdf(l.cos_angle));
+        float td = isect::ray_disk(lit_position, direction_to_light, l.position, l.direction, l.radius);
+        if (td >= 0.0f) {
+            float area_PDF_to_solid_angle_PDF = (td * td) / cos_theta;
+            return Pdf(dist::disk_pdf(l.radius) * area_PDF_to_solid_angle_PDF);
+        }
+    }
+    return Pdf::delta_dirac(0.0f);
+}
+
+BPT_D float3 evaluate(const SpotLight& l, float3 lit_position, float3 direction_to_light) {
+    float cos_theta = -dot(l.direction, direction_to_light);
+    float normalization = TWO_PI_F * (1.0f - l.cos_angle);
+    if (is_delta(l)) {
+        float3 d = l.position - lit_position;
+        normalization *= dot(d, d);
+    } else
+        normalization *= surface_area(l) * cos_theta;
+    float3 radiance = l.power / normalization;
+    return (cos_theta > l.cos_angle) ? radiance : f3(0.0f);
+}
+
+BPT_D LightSample sample_radiance(const SpotLight& l, float3 lit_position, float2 u) {
+    LightSample s;
+    if (is_delta(l)) {
+        s.direction_to_light = l.position - lit_position;
+        s.distance = length(s.direction_to_light);
+        s.direction_to_light /= s.distance;
+        s.pdf = Pdf(1.0f); // the reference leaves this positive (SpotLightImpl.h:84)
+        s.radiance = evaluate(l, lit_position, s.direction_to_light);
+        return s;
+    }
+    const Tbn light_to_world(l.direction);
+
+    float t = isect::ray_plane(lit_position, -l.direction, l.position, l.direction);
+    float cone_radius_at_intersection = t * sqrtf(1.0f - pow2(l.cos_angle)) / l.cos_angle;
+    if (l.radius > cone_radius_at_intersection && l.cos_angle > min_cone_angle_to_sample) {
+        DirectionalSample cone = dist::cone_sample(l.cos_angle, u);
+        s.direction_to_light = light_to_world.to_world(-cone.direction);
+        s.distance = isect::ray_plane(lit_position, s.direction_to_light, l.position, l.direction);
+        s.pdf = Pdf(cone.pdf);
+        s.radiance = f3(0.0f);
+        float3 sample_position_on_light = lit_position + s.direction_to_light * s.distance;
+        float3 light_pos_to_sample_pos = sample_position_on_light - l.position;
+        if (dot(light_pos_to_sample_pos, light_pos_to_sample_pos) < pow2(l.radius))
+            s.radiance = evaluate(l, lit_position, s.direction_to_light);
+    } else {
+        float2 disk_position = dist::disk_sample(l.radius, u);
+        float3 sampled_position = l.position + light_to_world.to_world(f3(disk_position.x, disk_position.y, 0.0f));
+        s.direction_to_light = sampled_position - lit_position;
+        s.distance = length(s.direction_to_light);
+        s.direction_to_light /= s.distance;
+        float cos_theta = -dot(l.direction, s.direction_to_light);
+        float area_PDF_to_solid_angle_PDF = pow2(s.distance) / cos_theta;
+        s.pdf = Pdf(dist::disk_pdf(l.radius) * area_PDF_to_solid_angle_PDF);
+        s.radiance = evaluate(l, lit_position, s.direction_to_light);
+    }
+    s.distance = nextafterf(s.distance, 0.0f);
+    return s;
+}
+} // namespace spot_light
+
+// ---- directional light -------------------------------------------------------------------------
+namespace directional_light {
+BPT_D LightSample sample_radiance(const DirectionalLight& l) {
+    LightSample s;
+    s.radiance = l.radiance;
+    s.pdf = Pdf::delta_dirac(1.0f);
+    s.direction_to_light = -l.direction;
+    s.distance = 1e30f;
+    return s;
+}
+} // namespace directional_light
+
+// ---- environment (presampled) ------------------------------------------------------------------
+// Device view of the scene environment. `texels` is a latlong RGBA float image sampled bilinearly with
+// wrap in u and clamp in v, matching the sampler the reference creates (EnvironmentMap.cpp). `per_pixel_pdf`
+// is sampled with nearest lookup (PresampledEnvironmentMap.cpp:98-100).
+struct EnvironmentView {
+    const float4* texels;
+    int width, height;
+    const float* per_pixel_pdf;
+    int pdf_width, pdf_height;
+    const bpt_light_sample* samples;
+    int sample_count;
+    float3 tint;
+};
+
+BPT_D float2 direction_to_latlong_texcoord(float3 direction) {
+    float u = (atan2f(direction.z, direction.x) + PI_F) * 0.5f / PI_F;
+    float v = (asinf(direction.y) + PI_F * 0.5f) / PI_F;
+    return f2(u, v);
+}
+
+namespace environment_light {
+
+BPT_D float3 fetch_bilinear(const EnvironmentView& e, float2 uv) {
+    // CUDA linear filtering convention: texel centres at (i + 0.5) / N.
+    float x = uv.x * e.width - 0.5f;
+    float y = uv.y * e.height - 0.5f;
+    float fx = floorf(x), fy = floorf(y);
+    float tx = x - fx, ty = y - fy;
+    int x0 = int(fx), y0 = int(fy);
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = ((x0 % e.width) + e.width) % e.width;
+    x1 = ((x1 % e.width) + e.width) % e.width;
+    y0 = max(0, min(e.height - 1, y0));
+    y1 = max(0, min(e.height - 1, y1));
+    float4 p00 = e.texels[y0 * e.width + x0], p10 = e.texels[y0 * e.width + x1];
+    float4 p01 = e.texels[y1 * e.width + x0], p11 = e.texels[y1 * e.width + x1];
+    float3 a = lerp(f3(p00), f3(p10), tx);
+    float3 b = lerp(f3(p01), f3(p11), tx);
+    return lerp(a, b, ty);
+}
+
+BPT_D float fetch_pdf_nearest(const EnvironmentView& e, float2 uv) {
+    int x = int(floorf(uv.x * e.pdf_width));
+    int y = int(floorf(uv.y * e.pdf_height));
+    x = ((x % e.pdf_width) + e.pdf_width) % e.pdf_width;
+    y = max(0, min(e.pdf_height - 1, y));
+    return e.per_pixel_pdf[y * e.pdf_width + x];
+}
+
+BPT_D LightSample sample_radiance(const EnvironmentView& e, float2 u) {
+    int index = int(u.x * e.sample_count);
+    bpt_light_sample raw = e.samples[index];
+    LightSample s;
+    s.radiance = f3(raw.radiance[0], raw.radiance[1], raw.radiance[2]) * e.tint;
+    s.pdf = Pdf(raw.pdf);
+    s.direction_to_light = f3(raw.direction_to_light[0], raw.direction_to_light[1], raw.direction_to_light[2]);
+    s.distance = raw.distance;
+    return s;
+}
+
+BPT_D Pdf pdf(const EnvironmentView& e, float3 direction_to_light) {
+    float2 uv = direction_to_latlong_texcoord(direction_to_light);
+    float sin_theta = sqrtf(1.0f - direction_to_light.y * direction_to_light.y);
+    float p = fetch_pdf_nearest(e, uv) / sin_theta;
+    return sin_theta == 0.0f ? Pdf::delta_dirac(0.0f) : Pdf(p);
+}
+
+BPT_D float3 evaluate(const EnvironmentView& e, float3 direction_to_light) {
+    float2 uv = direction_to_latlong_texcoord(direction_to_light);
+    return e.tint * fetch_bilinear(e, uv);
+}
+
+} // namespace environment_light
+
+// ---- dispatch (LightImpl.h:38-108) -------------------------------------------------------------
+BPT_D LightSample light_sample_radiance(const Light& light, const EnvironmentView& env, float3 position, float2 u) {
+    switch (light_type(light)) {
+    case BPT_LIGHT_SPHERE: return sphere_light::sample_radiance(as_sphere(light), position, u);
+    case BPT_LIGHT_DIRECTIONAL: return directional_light::sample_radiance(as_directional(light));
+    case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::sample_radiance(env, u);
+    case BPT_LIGHT_SPOT: return spot_light::sample_radiance(as_spot(light), position, u);
+    }
+    return light_sample_none();
+}
+
+BPT_D Pdf light_pdf(const Light& light, const EnvironmentView& env, float3 lit_position, float3 direction_to_light) {
+    switch (light_type(light)) {
+    case BPT_LIGHT_SPHERE: return sphere_light::pdf(as_sphere(light), lit_position, direction_to_light);
+    case BPT_LIGHT_DIRECTIONAL: return Pdf::delta_dirac(0.0f);
+    case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::pdf(env, direction_to_light);
+    case BPT_LIGHT_SPOT: return spot_light::pdf(as_spot(light), lit_position, direction_to_light);
+    }
+    return Pdf::invalid();
+}
+
+BPT_D float3 light_evaluate(const Light& light, const EnvironmentView& env, float3 position, float3 direction_to_light) {
+    switch (light_type(light)) {
+    case BPT_LIGHT_SPHERE: return sphere_light::evaluate(as_sphere(light), position);
+    case BPT_LIGHT_DIRECTIONAL: return f3(0.0f);
+    case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::evaluate(env, direction_to_light);
+    case BPT_LIGHT_SPOT: return spot_light::evaluate(as_spot(light), position, direction_to_light);
+    }
+    return f3(0.0f);
+}
+
+// MonteCarlo.h:20-35
+BPT_D float balance_heuristic(float pdf1, float pdf2) {
+    float divisor = pdf1 + pdf2;
+    float result = pdf1 / divisor;
+    bool result_is_invalid = isinf(divisor) || isnan(result);
+    return result_is_invalid ? (pdf1 <= pdf2 ? 0.0f : 1.0f) : result;
+}
+BPT_D float mis_weight(Pdf pdf1, Pdf pdf2) { return balance_heuristic(pdf1.value(), pdf2.value()); }
+
+} // namespace bpt

@@ -1,0 +1,707 @@
+// BSDFs and the default shading model, restated for sm_100a.
+//
+// Arithmetic follows the reference's host-compilable headers so results agree with the
+// host-compiled oracle to ~1e-5 relative (IEEE div/sqrt, no fast-math; see DESIGN.md "FP contract"):
+//   PDF wrapper            extensions/OptiXRenderer/OptiXRenderer/Types.h:155-204
+//   Cosine / Uniform / Cone / Disk / OrenNayar clipped-LTC / GGX (bounded) VNDF
+//                          .../Distributions.h:34-98,135-181,186-260,304-461
+//   GGX_R                  .../Shading/BSDFs/GGX.h:33-133
+//   OrenNayar (EON)        .../Shading/BSDFs/OrenNayar.h:30-127
+//   Burley                 .../Shading/BSDFs/Burley.h:29-71
+//   SpecularRho / GGXMinimumRoughness   .../Shading/ShadingModels/Utils.h:27-57,104-130
+//   DefaultShading         .../Shading/ShadingModels/DefaultShading.h:41-298
+//   fresnel / coat helpers .../Utils.h:129-190,363-367
+// The rho / alpha tables are sampled like the reference's HOST branch: float tables with the
+// software bilinear of core/Bifrost/Bifrost/Math/ImageSampling.h:18-41 (not unorm16 textures).
+#pragma once
+#include "bpt_math.cuh"
+#include "bpt_types.h"
+
+namespace bpt {
+
+// ------------------------------------------------------------------------------------------------
+// PDF wrapper: negative = delta dirac / MIS disabled, NaN = invalid.
+// ------------------------------------------------------------------------------------------------
+constexpr float MIN_VALID_PDF = 0.000001f;
+
+struct Pdf {
+    float v;
+    BPT_HD Pdf() {}
+    BPT_HD Pdf(float pdf) : v(pdf) {}
+    BPT_HD static Pdf invalid() { return Pdf(nanf("")); }
+    BPT_HD static Pdf delta_dirac(float pdf = 1.0f) { return Pdf(-pdf); }
+    BPT_HD float value() const { return fabsf(v); }
+    BPT_HD bool is_valid() const { return value() > MIN_VALID_PDF; }
+    BPT_HD bool is_delta_dirac() const { return !(v >= 0.0f); }
+    BPT_HD void disable_MIS() { if (v >= 0.0f) v = -v; }
+    BPT_HD bool is_valid_and_not_delta_dirac() const { return v > MIN_VALID_PDF; }
+    BPT_HD bool invalid_or_delta_dirac() const { return !(v > MIN_VALID_PDF); }
+    BPT_HD bool use_for_MIS() const { return is_valid_and_not_delta_dirac(); }
+};
+
+struct BsdfResponse { float3 reflectance; Pdf pdf; };
+struct BsdfSample { float3 reflectance; Pdf pdf; float3 direction; };
+
+BPT_HD BsdfResponse bsdf_response_none() { BsdfResponse r; r.reflectance = f3(0.0f); r.pdf = Pdf(0.0f); return r; }
+BPT_HD BsdfSample bsdf_sample_none() { BsdfSample s; s.reflectance = f3(0.0f); s.pdf = Pdf(0.0f); s.direction = f3(0.0f); return s; }
+
+struct DirectionalSample { float3 direction; float pdf; };
+
+// The reference's host build calls sin() and cos() separately; sincosf() returns the same values.
+BPT_D void sincos_(float theta, float& s, float& c) { sincosf(theta, &s, &c); }
+
+// ------------------------------------------------------------------------------------------------
+// Table sampling (ImageSampling.h:18-41). `pixels` is row-major [height][width].
+// ------------------------------------------------------------------------------------------------
+BPT_D float bilinear(const float* __restrict__ pixels, int width, int height, float u, float v) {
+    u = clampf(u, 0.0f, 1.0f); // Bifrost clamp: min(max(v, lo), hi); identical for non-NaN input
+    float u_coord = u * (width - 1);
+    int lower_u = int(u_coord);
+    int upper_u = min(lower_u + 1, width - 1);
+
+    v = clampf(v, 0.0f, 1.0f);
+    float v_coord = v * (height - 1);
+    int lower_v = int(v_coord);
+    int upper_v = min(lower_v + 1, height - 1);
+
+    float u_t = u_coord - lower_u;
+    const float* lower_row = pixels + lower_v * width;
+    float a0 = lower_row[lower_u], a1 = lower_row[upper_u];
+    float lower_pixel = a0 + (a1 - a0) * u_t;
+    const float* upper_row = pixels + upper_v * width;
+    float b0 = upper_row[lower_u], b1 = upper_row[upper_u];
+    float upper_pixel = b0 + (b1 - b0) * u_t;
+
+    float v_t = v_coord - lower_v;
+    return lower_pixel + (upper_pixel - lower_pixel) * v_t;
+}
+
+// Pointers to the three 32x32 float tables; they may live in shared or global memory.
+struct ShadingTables {
+    const float* ggx_with_fresnel_rho; // [roughness][cos_theta]
+    const float* ggx_rho;              // [roughness][cos_theta]
+    const float* estimate_alpha;       // [cos_theta][encoded max PDF]
+};
+constexpr int RHO_TABLE_DIM = 32;
+constexpr int TABLE_FLOATS = RHO_TABLE_DIM * RHO_TABLE_DIM;
+
+struct SpecularRho {
+    float base, full;
+    BPT_D float rho(float specularity) const { return lerp(base, full, specularity); }
+    BPT_D float3 rho(float3 s) const { return f3(rho(s.x), rho(s.y), rho(s.z)); }
+    BPT_D float energy_loss_adjustment() const { return 1.0f / full; }
+    BPT_D static SpecularRho fetch(const ShadingTables& t, float abs_cos_theta, float roughness) {
+        SpecularRho r;
+        r.base = bilinear(t.ggx_with_fresnel_rho, RHO_TABLE_DIM, RHO_TABLE_DIM, abs_cos_theta, roughness);
+        r.full = bilinear(t.ggx_rho, RHO_TABLE_DIM, RHO_TABLE_DIM, abs_cos_theta, roughness);
+        return r;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Distributions
+// ------------------------------------------------------------------------------------------------
+namespace dist {
+
+BPT_D float cone_pdf(float cos_theta_max) { return 1.0f / (2.0f * PI_F * (1.0f - cos_theta_max)); }
+
+BPT_D DirectionalSample cone_sample(float cos_theta_max, float2 u) {
+    float cos_theta = (1.0f - u.x) + u.x * cos_theta_max;
+    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    float phi = 2.0f * PI_F * u.y;
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    DirectionalSample res;
+    res.direction = f3(cos_phi * sin_theta, sin_phi * sin_theta, cos_theta);
+    res.pdf = cone_pdf(cos_theta_max);
+    return res;
+}
+
+BPT_D float disk_pdf(float radius) { return 1.0f / (PI_F * pow2(radius)); }
+
+BPT_D float2 disk_sample(float radius, float2 u) {
+    float r = sqrtf(u.x) * radius;
+    float phi = 2.0f * PI_F * u.y;
+    return f2(r * cosf(phi), r * sinf(phi));
+}
+
+BPT_D float uniform_hemisphere_pdf() { return 0.5f * RECIP_PI_F; }
+
+BPT_D DirectionalSample uniform_hemisphere_sample(float2 u) {
+    float z = u.x;
+    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float phi = TWO_PI_F * u.y;
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    DirectionalSample res;
+    res.direction = f3(r * cos_phi, r * sin_phi, z);
+    res.pdf = uniform_hemisphere_pdf();
+    return res;
+}
+
+BPT_D float cosine_pdf(float abs_cos_theta) { return abs_cos_theta * RECIP_PI_F; }
+
+BPT_D DirectionalSample cosine_sample(float2 u) {
+    float r2 = u.x;
+    float r = sqrtf(1.0f - r2);
+    float z = sqrtf(r2);
+    float phi = 2.0f * PI_F * u.y;
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    DirectionalSample res;
+    res.direction = f3(r * cos_phi, r * sin_phi, z);
+    res.pdf = z * RECIP_PI_F;
+    return res;
+}
+
+// --- Clipped linearly transformed cosine for Oren-Nayar (Distributions.h:186-260) ---------------
+// The 2x2 tangent basis has columns X and Y = (-X.y, X.x).
+BPT_D float2 ltc_tangent_x(float3 w) {
+    float2 wh = f2(w.x, w.y);
+    float len_sqr = dot(wh, wh);
+    return len_sqr > 0.0f ? wh / sqrtf(len_sqr) : f2(1.0f, 0.0f);
+}
+
+BPT_D void oren_nayar_ltc_coefficients(float cos_theta, float roughness, float& a, float& b, float& c, float& d) {
+    a = 1.0f + roughness * (0.303392f + (-0.518982f + 0.111709f * cos_theta) * cos_theta + (-0.276266f + 0.335918f * cos_theta) * roughness);
+    b = roughness * (-1.16407f + 1.15859f * cos_theta + (0.150815f - 0.150105f * cos_theta) * roughness) / (cos_theta * cos_theta * cos_theta - 1.43545f);
+    c = 1.0f + (0.20013f + (-0.506373f + 0.261777f * cos_theta) * cos_theta) * roughness;
+    d = ((0.540852f + (-1.01625f + 0.475392f * cos_theta) * cos_theta) * roughness) / (-1.0743f + cos_theta * (0.0725628f + cos_theta));
+}
+
+BPT_D DirectionalSample oren_nayar_cltc_sample(float roughness, float3 wo, float2 u) {
+    float a, b, c, d;
+    oren_nayar_ltc_coefficients(wo.z, roughness, a, b, c, d);
+
+    float radius = sqrtf(u.x);
+    float phi = 2.0f * PI_F * u.y;
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    float x = radius * cos_phi;
+    float y = radius * sin_phi;
+
+    float vz = 1.0f / sqrtf(d * d + 1.0f);
+    float s = 0.5f * (1.0f + vz);
+    x = -lerp(sqrtf(1.0f - y * y), x, s);
+    float3 wh = f3(x, y, sqrtf(fmaxf(1.0f - (x * x + y * y), 0.0f)));
+    float pdf_wh = wh.z / (PI_F * s);
+    float3 wi = f3(a * wh.x + b * wh.z, c * wh.y, d * wh.x + wh.z);
+    float wi_magnitude = length(wi);
+    float determinant_M = c * (a - b * d);
+    float pdf_wi = pdf_wh * wi_magnitude * wi_magnitude * wi_magnitude / determinant_M;
+    // wi -> local space: [X Y] * wi.xy
+    float2 X = ltc_tangent_x(wo);
+    float2 Y = f2(-X.y, X.x);
+    float2 xy = f2(X.x * wi.x + Y.x * wi.y, X.y * wi.x + Y.y * wi.y);
+    wi = normalize(f3(xy.x, xy.y, wi.z));
+
+    DirectionalSample res;
+    res.direction = wi;
+    res.pdf = pdf_wi;
+    return res;
+}
+
+BPT_D float oren_nayar_cltc_pdf(float roughness, float3 wo, float3 wi_shading) {
+    // wi -> LTC space: transpose([X Y]) * wi.xy
+    float2 X = ltc_tangent_x(wo);
+    float2 Y = f2(-X.y, X.x);
+    float3 wi = f3(X.x * wi_shading.x + X.y * wi_shading.y, Y.x * wi_shading.x + Y.y * wi_shading.y, wi_shading.z);
+
+    float a, b, c, d;
+    oren_nayar_ltc_coefficients(wo.z, roughness, a, b, c, d);
+
+    float determinant_M = c * (a - b * d);
+    float3 wh = f3(c * (wi.x - b * wi.z), (a - b * d) * wi.y, -c * (d * wi.x - a * wi.z));
+    float wh_magnitude_squared = dot(wh, wh);
+    float vz = 1.0f / sqrtf(d * d + 1.0f);
+    float s = 0.5f * (1.0f + vz);
+    return determinant_M * determinant_M / pow2(wh_magnitude_squared) * fmaxf(wh.z, 0.0f) / (PI_F * s);
+}
+
+// --- GGX visible normals (Distributions.h:304-461) -----------------------------------------------
+BPT_D float ggx_D(float alpha, float3 halfway) {
+    float m = pow2(halfway.x / alpha) + pow2(halfway.y / alpha) + pow2(halfway.z);
+    return 1.0f / (PI_F * alpha * alpha * pow2(m));
+}
+
+BPT_D float ggx_lambda(float alpha, float3 w) {
+    return 0.5f * (-1.0f + sqrtf(1.0f + (pow2(alpha * w.x) + pow2(alpha * w.y)) / pow2(w.z)));
+}
+
+// Bounded VNDF (Eto et al. 2023), isotropic alpha.
+BPT_D float3 ggx_bounded_vndf_sample_reflection(float alpha, float3 wo, float2 u) {
+    float3 wo_std = normalize(f3(wo.x * alpha, wo.y * alpha, wo.z));
+
+    float phi = 2.0f * PI_F * u.y;
+    float a = fminf(alpha, alpha);
+    float s = 1.0f + length(f2(wo.x, wo.y));
+    float a2 = a * a; float s2 = s * s;
+    float k = (1.0f - a2) * s2 / (s2 + a2 * wo.z * wo.z);
+    float b = wo.z >= 0.0f ? k * wo_std.z : wo_std.z;
+    float z = fmaf(1.0f - u.x, 1.0f + b, -b);
+    float sin_theta = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    float3 o_std = f3(sin_theta * cos_phi, sin_theta * sin_phi, z);
+
+    float3 halfway_std = wo_std + o_std;
+    float3 halfway = normalize(f3(halfway_std.x * alpha, halfway_std.y * alpha, halfway_std.z));
+    return reflect(-wo, halfway);
+}
+
+BPT_D float ggx_bounded_vndf_reflection_pdf(float alpha, float3 wo, float3 wi) {
+    float3 halfway = normalize(wo + wi);
+    float ndf = ggx_D(alpha, halfway);
+    float2 ao = f2(alpha * wo.x, alpha * wo.y);
+    float len2 = dot(ao, ao);
+    float t = sqrtf(len2 + wo.z * wo.z);
+    if (wo.z >= 0.0f) {
+        float min_alpha = fminf(alpha, alpha);
+        float s = 1.0f + length(f2(wo.x, wo.y));
+        float min_alpha_squared = min_alpha * min_alpha; float s2 = s * s;
+        float k = (1.0f - min_alpha_squared) * s2 / (s2 + min_alpha_squared * wo.z * wo.z);
+        return ndf / (2.0f * (k * wo.z + t));
+    }
+    return ndf * (t - wo.z) / (2.0f * len2);
+}
+
+} // namespace dist
+
+// ------------------------------------------------------------------------------------------------
+// Fresnel and specularity helpers (Utils.h:129-190)
+// ------------------------------------------------------------------------------------------------
+constexpr float COAT_SPECULARITY = 0.04f;
+constexpr float COAT_IOR = 1.5f;
+constexpr float AIR_IOR = 1.0f;
+
+BPT_D float3 schlick_fresnel(float3 incident_specular, float abs_cos_theta) {
+    float t = pow5(1.0f - abs_cos_theta);
+    return (1.0f - t) * incident_specular + t;
+}
+
+BPT_D float dielectric_specularity(float ior_o, float ior_i) { return pow2((ior_o - ior_i) / (ior_o + ior_i)); }
+BPT_D float dielectric_ior_from_specularity(float specularity) { return 2.0f / (1.0f - sqrtf(specularity)) - 1.0f; }
+BPT_D float adjust_dielectric_specularity_to_exterior_medium(float exterior_ior, float specularity_through_air) {
+    float base_ior = dielectric_ior_from_specularity(specularity_through_air);
+    return dielectric_specularity(exterior_ior, base_ior);
+}
+
+// Conductor variants with the extinction coefficient fixed to zero by the only caller
+// (DefaultShading.h:98-100); the general expressions are kept so the rounding is the same.
+BPT_D float3 conductor_ior_from_specularity(float3 specularity, float3 ext_i) {
+    float3 a = specularity - 1.0f;
+    float3 b = 2.0f * specularity + 2.0f;
+    float3 c = a + (specularity - 1.0f) * (ext_i * ext_i);
+    float3 d = b * b - 4.0f * a * c;
+    float3 sqrt_d = f3(sqrtf(d.x), sqrtf(d.y), sqrtf(d.z));
+    return (-b + sqrt_d) / (2.0f * a);
+}
+BPT_D float3 conductor_specularity(float3 ior_o, float3 ior_i, float3 ext_i) {
+    float3 ext_i_sqrd = ext_i * ext_i;
+    float3 dm = ior_o - ior_i, dp = ior_o + ior_i;
+    return (dm * dm + ext_i_sqrd) / (dp * dp + ext_i_sqrd);
+}
+BPT_D float3 adjust_conductor_specularity_to_exterior_medium(float3 exterior_ior, float3 specularity_through_air, float3 extinction) {
+    float3 base_ior = conductor_ior_from_specularity(specularity_through_air, extinction);
+    return conductor_specularity(exterior_ior, base_ior, extinction);
+}
+
+BPT_D float modulate_roughness_under_coat(float base_roughness, float coat_roughness) {
+    float x_coat = 1.0f - AIR_IOR / COAT_IOR;
+    float adjusted_roughness4 = fminf(1.0f, pow4(base_roughness) + 2.0f * x_coat * pow4(coat_roughness));
+    return powf(adjusted_roughness4, 0.25f);
+}
+
+// ------------------------------------------------------------------------------------------------
+// GGX reflection (GGX.h:33-133)
+// ------------------------------------------------------------------------------------------------
+namespace ggx {
+constexpr float MIN_ALPHA = 1e-4f;
+BPT_D float alpha_from_roughness(float roughness) { return fmaxf(MIN_ALPHA, roughness * roughness); }
+BPT_D float roughness_from_alpha(float alpha) { return sqrtf(alpha); }
+BPT_D bool effectively_smooth(float alpha) { return alpha <= MIN_ALPHA; }
+BPT_D float height_correlated_G(float alpha, float3 wo, float3 wi) {
+    return 1.0f / (1.0f + dist::ggx_lambda(alpha, wo) + dist::ggx_lambda(alpha, wi));
+}
+} // namespace ggx
+
+namespace ggx_r {
+
+BPT_D float3 evaluate(float alpha, float3 specularity, float3 wo, float3 wi) {
+    if (ggx::effectively_smooth(alpha))
+        return f3(0.0f);
+    if (wo.z * wi.z <= 0.0f)
+        return f3(0.0f);
+
+    float3 halfway = normalize(wo + wi);
+    float G = ggx::height_correlated_G(alpha, wo, wi);
+    float D = dist::ggx_D(alpha, halfway);
+    float3 F = schlick_fresnel(specularity, dot(wo, halfway));
+    return F * (D * G / (4.0f * wo.z * wi.z));
+}
+
+BPT_D Pdf pdf(float alpha, float3 wo, float3 wi) {
+    if (ggx::effectively_smooth(alpha))
+        return Pdf::invalid();
+    return Pdf(dist::ggx_bounded_vndf_reflection_pdf(alpha, wo, wi));
+}
+
+BPT_D BsdfResponse evaluate_with_pdf(float alpha, float3 specularity, float3 wo, float3 wi) {
+    BsdfResponse r;
+    r.reflectance = evaluate(alpha, specularity, wo, wi);
+    r.pdf = pdf(alpha, wo, wi);
+    return r;
+}
+
+BPT_D BsdfSample sample(float alpha, float3 specularity, float3 wo, float2 u) {
+    BsdfSample s;
+    if (ggx::effectively_smooth(alpha)) {
+        s.direction = f3(-wo.x, -wo.y, wo.z);
+        s.pdf = Pdf::delta_dirac(1.0f);
+        s.reflectance = schlick_fresnel(specularity, fabsf(wo.z)) / fabsf(s.direction.z);
+        return s;
+    }
+    s.direction = dist::ggx_bounded_vndf_sample_reflection(alpha, wo, u);
+    s.pdf = Pdf(dist::ggx_bounded_vndf_reflection_pdf(alpha, wo, s.direction));
+    s.reflectance = evaluate(alpha, specularity, wo, s.direction);
+    bool energyloss = s.direction.z < 0.0f;
+    return energyloss ? bsdf_sample_none() : s;
+}
+
+} // namespace ggx_r
+
+// ------------------------------------------------------------------------------------------------
+// Energy-preserving Oren-Nayar (OrenNayar.h:30-127), approximate E_FON.
+// ------------------------------------------------------------------------------------------------
+namespace oren_nayar {
+
+BPT_D float E_FON_approx(float cos_theta, float A, float B) {
+    float mucomp = 1.0f - cos_theta;
+    float GoverPi = 0.0f;
+    GoverPi = mucomp * (0.0714429953f + GoverPi);
+    GoverPi = mucomp * (-0.332181442f + GoverPi);
+    GoverPi = mucomp * (0.491881867f + GoverPi);
+    GoverPi = mucomp * (0.0571085289f + GoverPi);
+    return A + B * GoverPi;
+}
+
+BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
+    const float constant1_FON = 0.5f - 2.0f / (3.0f * PI_F);
+    const float constant2_FON = 2.0f / 3.0f - 28.0f / (15.0f * PI_F);
+
+    float cos_theta_i = wi.z;
+    float cos_theta_o = wo.z;
+    float s = dot(wi, wo) - cos_theta_i * cos_theta_o;
+    float s_over_t = s > 0.0f ? s / fmaxf(cos_theta_i, cos_theta_o) : s;
+    float A = 1.0f / (1.0f + constant1_FON * roughness);
+    float B = roughness * A;
+
+    float f_single_scatter = RECIP_PI_F * A * (1.0f + roughness * s_over_t);
+
+    float EF_o = E_FON_approx(cos_theta_o, A, B);
+    float EF_i = E_FON_approx(cos_theta_i, A, B);
+    float average_EF = A * (1.0f + constant2_FON * roughness);
+    float multi_scatter_rho = average_EF / (1.0f - (1.0f - average_EF));
+    float f_multi_scatter = (multi_scatter_rho * RECIP_PI_F) * fabsf(1.0f - EF_o) * fabsf(1.0f - EF_i)
+        / fmaxf(1.0e-7f, 1.0f - average_EF);
+    return f_single_scatter + f_multi_scatter;
+}
+
+BPT_D float uniform_lobe_probability(float roughness, float cos_theta) {
+    return powf(roughness, 0.1f) * (0.162925f + cos_theta * (-0.372058f + (0.538233f - 0.290822f * cos_theta) * cos_theta));
+}
+
+BPT_D Pdf pdf(float roughness, float3 wo, float3 wi) {
+    float uniform_probability = uniform_lobe_probability(roughness, wo.z);
+    float cltc_probability = 1.0f - uniform_probability;
+    float cltc_PDF = dist::oren_nayar_cltc_pdf(roughness, wo, wi);
+    float uniform_PDF = dist::uniform_hemisphere_pdf();
+    return Pdf(uniform_probability * uniform_PDF + cltc_probability * cltc_PDF);
+}
+
+BPT_D BsdfResponse evaluate_with_pdf(float3 albedo, float roughness, float3 wo, float3 wi) {
+    BsdfResponse r;
+    r.reflectance = albedo * evaluate(roughness, wo, wi);
+    r.pdf = pdf(roughness, wo, wi);
+    return r;
+}
+
+BPT_D BsdfSample sample(float3 albedo, float roughness, float3 wo, float2 u) {
+    float uniform_probability = uniform_lobe_probability(roughness, wo.z);
+    float cltc_probability = 1.0f - uniform_probability;
+
+    DirectionalSample ds;
+    float cltc_PDF;
+    if (u.x <= uniform_probability) {
+        u.x = u.x / uniform_probability;
+        ds = dist::uniform_hemisphere_sample(u);
+        cltc_PDF = dist::oren_nayar_cltc_pdf(roughness, wo, ds.direction);
+    } else {
+        u.x = (u.x - uniform_probability) / cltc_probability;
+        ds = dist::oren_nayar_cltc_sample(roughness, wo, u);
+        cltc_PDF = ds.pdf;
+    }
+    float uniform_PDF = dist::uniform_hemisphere_pdf();
+
+    BsdfSample s;
+    s.direction = ds.direction;
+    s.pdf = Pdf(uniform_probability * uniform_PDF + cltc_probability * cltc_PDF);
+    s.reflectance = albedo * evaluate(roughness, wo, s.direction);
+    return s;
+}
+
+} // namespace oren_nayar
+
+// ------------------------------------------------------------------------------------------------
+// Burley diffuse (Burley.h:29-71). Not used by the renderer; part of the C1 workload.
+// ------------------------------------------------------------------------------------------------
+namespace burley {
+
+BPT_D float schlick(float abs_cos_theta) { return pow5(fmaxf(1.0f - abs_cos_theta, 0.0f)); }
+
+BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
+    float3 halfway = normalize(wi + wo);
+    float wi_dot_halfway = dot(wi, halfway);
+    float fd90 = 0.5f + 2.0f * wi_dot_halfway * wi_dot_halfway * roughness;
+    float fresnel_wo = schlick(wo.z);
+    float fresnel_wi = schlick(wi.z);
+    float normalizer = 1.0f / lerp(0.969371021f, 1.04337633f, roughness);
+    return lerp(1.0f, fd90, fresnel_wo) * lerp(1.0f, fd90, fresnel_wi) * RECIP_PI_F * normalizer;
+}
+
+BPT_D BsdfResponse evaluate_with_pdf(float3 tint, float roughness, float3 wo, float3 wi) {
+    BsdfResponse r;
+    r.reflectance = tint * evaluate(roughness, wo, wi);
+    r.pdf = Pdf(dist::cosine_pdf(wi.z));
+    return r;
+}
+
+BPT_D BsdfSample sample(float3 tint, float roughness, float3 wo, float2 u) {
+    DirectionalSample ds = dist::cosine_sample(u);
+    BsdfSample s;
+    s.direction = ds.direction;
+    s.pdf = Pdf(ds.pdf);
+    s.reflectance = tint * evaluate(roughness, wo, s.direction);
+    return s;
+}
+
+} // namespace burley
+
+// ------------------------------------------------------------------------------------------------
+// Path regularisation: smallest GGX roughness whose bounded-VNDF peak PDF stays below a hint
+// (ShadingModels/Utils.h:104-130, host branch; EstimateGGXBoundedVNDFAlpha.cpp encode_PDF / estimate_alpha).
+// ------------------------------------------------------------------------------------------------
+BPT_D float ggx_min_roughness_from_pdf(const ShadingTables& t, float abs_cos_theta, Pdf max_pdf) {
+    if (max_pdf.is_delta_dirac())
+        return 0.0f;
+    float pdf = max_pdf.value();
+    float non_linear_PDF = pdf / (1.0f + pdf);
+    float encoded_PDF = (non_linear_PDF - 0.13f) / 0.87f;
+    if (isnan(encoded_PDF))
+        encoded_PDF = 1.0f;
+    float min_alpha = bilinear(t.estimate_alpha, RHO_TABLE_DIM, RHO_TABLE_DIM, encoded_PDF, abs_cos_theta);
+    return ggx::roughness_from_alpha(min_alpha);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Default shading: EON diffuse + GGX specular (+ optional GGX coat). DefaultShading.h:41-298
+// ------------------------------------------------------------------------------------------------
+struct DefaultShading {
+    float3 diffuse_tint;
+    float roughness;
+    float3 specularity;
+    float specular_scale;
+    float coat_scale;
+    float coat_alpha;
+    unsigned short specular_probability_q; // quantised to 16 bit exactly like the reference
+    unsigned short coat_probability_q;
+
+    BPT_D static float compute_specular_properties(const ShadingTables& t, float roughness, float specularity, float scale, float abs_cos_theta_o,
+                                                   float& alpha, float& reflection_scale, float& transmission_scale) {
+        alpha = ggx::alpha_from_roughness(roughness);
+        SpecularRho rho_computation = SpecularRho::fetch(t, abs_cos_theta_o, roughness);
+        reflection_scale = scale * rho_computation.energy_loss_adjustment();
+        float specular_rho = rho_computation.rho(specularity) * reflection_scale;
+        transmission_scale = 1.0f - specular_rho;
+        return specular_rho;
+    }
+
+    BPT_D void setup_shading(const ShadingTables& t, float3 tint, float roughness_in, float dielectric_spec, float metallic,
+                             float coat_scale_in, float coat_roughness, float cos_theta_o, float& coat_rho) {
+        float abs_cos_theta_o = fabsf(cos_theta_o);
+
+        roughness = roughness_in;
+        float3 conductor_spec = tint;
+
+        if (coat_scale_in > 0.0f) {
+            float coat_modulated_roughness = modulate_roughness_under_coat(roughness_in, coat_roughness);
+            roughness = lerp(roughness_in, coat_modulated_roughness, coat_scale_in);
+
+            if (dielectric_spec < 1.0f) {
+                float coated = adjust_dielectric_specularity_to_exterior_medium(COAT_IOR, dielectric_spec);
+                dielectric_spec = lerp(dielectric_spec, coated, coat_scale_in);
+            }
+
+            if (metallic > 0.0f) {
+                float3 coated = adjust_conductor_specularity_to_exterior_medium(f3(COAT_IOR), conductor_spec, f3(0.0f));
+                conductor_spec = lerp(conductor_spec, coated, coat_scale_in);
+                conductor_spec.x = isnan(conductor_spec.x) ? 1.0f : conductor_spec.x;
+                conductor_spec.y = isnan(conductor_spec.y) ? 1.0f : conductor_spec.y;
+                conductor_spec.z = isnan(conductor_spec.z) ? 1.0f : conductor_spec.z;
+            }
+        }
+
+        float specular_alpha, dielectric_specular_transmission;
+        compute_specular_properties(t, roughness, dielectric_spec, 1.0f, abs_cos_theta_o,
+                                    specular_alpha, specular_scale, dielectric_specular_transmission);
+        float3 dielectric_tint = tint * dielectric_specular_transmission;
+
+        specularity = lerp(f3(dielectric_spec), conductor_spec, metallic);
+        diffuse_tint = dielectric_tint * (1.0f - metallic);
+
+        if (coat_scale_in > 0.0f) {
+            float coat_transmission;
+            coat_rho = compute_specular_properties(t, coat_roughness, COAT_SPECULARITY, coat_scale_in, abs_cos_theta_o,
+                                                   coat_alpha, coat_scale, coat_transmission);
+            specular_scale *= coat_transmission;
+            diffuse_tint *= coat_transmission;
+        } else {
+            coat_rho = 0.0f;
+            coat_scale = 0.0f;
+            coat_alpha = 0.0f;
+        }
+    }
+
+    BPT_D float3 specular_rho(const ShadingTables& t, float abs_cos_theta) const {
+        return SpecularRho::fetch(t, abs_cos_theta, roughness).rho(specularity) * specular_scale;
+    }
+    BPT_D float coat_rho_at(const ShadingTables& t, float abs_cos_theta) const {
+        float coat_roughness = ggx::roughness_from_alpha(coat_alpha);
+        return SpecularRho::fetch(t, abs_cos_theta, coat_roughness).rho(COAT_SPECULARITY) * coat_scale;
+    }
+    BPT_D float3 rho(const ShadingTables& t, float abs_cos_theta) const {
+        float3 r = diffuse_tint + specular_rho(t, abs_cos_theta);
+        if (coat_scale > 0.0f)
+            r = r + coat_rho_at(t, abs_cos_theta);
+        return r;
+    }
+
+    BPT_D void setup_sampling_probabilities(const ShadingTables& t, float abs_cos_theta_o, float coat_rho) {
+        const float USHORT_MAX_F = 65535.0f;
+        float diffuse_rho_sum = sum(diffuse_tint);
+        float specular_rho_sum = sum(specular_rho(t, abs_cos_theta_o));
+        float coat_rho_sum = 3.0f * coat_rho;
+        float recip_total_rho = 1.0f / (diffuse_rho_sum + specular_rho_sum + coat_rho_sum);
+
+        float specular_probability = specular_rho_sum * recip_total_rho;
+        specular_probability_q = (unsigned short)(specular_probability * USHORT_MAX_F + 0.5f);
+        float coat_probability = coat_rho_sum * recip_total_rho;
+        coat_probability_q = (unsigned short)(coat_probability * USHORT_MAX_F + 0.5f);
+    }
+
+    // Host constructor equivalent (DefaultShading.h:149-153).
+    BPT_D static DefaultShading create(const ShadingTables& t, float3 tint, float roughness, float specularity, float metallic,
+                                       float coat, float coat_roughness, float abs_cos_theta_o) {
+        DefaultShading s;
+        float coat_rho;
+        s.setup_shading(t, tint, roughness, specularity, metallic, coat, coat_roughness, abs_cos_theta_o, coat_rho);
+        s.setup_sampling_probabilities(t, abs_cos_theta_o, coat_rho);
+        return s;
+    }
+
+    // Renderer constructor (DefaultShading.h:155-179) for untextured materials: per-vertex tint/roughness
+    // scale, roughness floor from the previous bounce's BSDF PDF.
+    BPT_D static DefaultShading create_regularized(const ShadingTables& t, const Material& m, float4 tint_and_roughness_scale,
+                                                   float abs_cos_theta_o, Pdf max_pdf_hint) {
+        float min_roughness = ggx_min_roughness_from_pdf(t, abs_cos_theta_o, max_pdf_hint);
+        float coat_roughness = fmaxf(unorm16_to_float(m.coat_roughness), min_roughness);
+        float metallic = m.metallic;
+        float3 tint = f3(m.tint[0] * tint_and_roughness_scale.x, m.tint[1] * tint_and_roughness_scale.y, m.tint[2] * tint_and_roughness_scale.z);
+        float roughness = fmaxf(m.roughness * tint_and_roughness_scale.w, min_roughness);
+        return create(t, tint, roughness, m.specularity, metallic, unorm16_to_float(m.coat), coat_roughness, abs_cos_theta_o);
+    }
+
+    BPT_D float get_specular_alpha() const { return ggx::alpha_from_roughness(roughness); }
+    BPT_D float get_diffuse_probability() const { return 1.0f - (specular_probability_q + coat_probability_q) / 65535.0f; }
+    BPT_D float get_specular_probability() const { return specular_probability_q / 65535.0f; }
+    BPT_D float get_coat_probability() const { return coat_probability_q / 65535.0f; }
+
+    BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
+        if (wo.z < 0.000001f || wi.z < 0.000001f)
+            return bsdf_response_none();
+
+        BsdfResponse diffuse_response = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, wo, wi);
+        BsdfResponse specular_response = ggx_r::evaluate_with_pdf(get_specular_alpha(), specularity, wo, wi);
+        specular_response.reflectance *= specular_scale;
+
+        BsdfResponse response;
+        response.reflectance = diffuse_response.reflectance + specular_response.reflectance;
+
+        float diffuse_probability = get_diffuse_probability();
+        float specular_probability = get_specular_probability();
+        response.pdf = Pdf(diffuse_response.pdf.v * diffuse_probability + specular_response.pdf.v * specular_probability);
+
+        if (coat_scale > 0.0f) {
+            float coat_probability = get_coat_probability();
+            BsdfResponse coat_response = ggx_r::evaluate_with_pdf(coat_alpha, f3(COAT_SPECULARITY), wo, wi);
+            response.reflectance += coat_scale * coat_response.reflectance;
+            response.pdf.v += coat_response.pdf.v * coat_probability;
+        }
+        return response;
+    }
+
+    BPT_D BsdfSample sample(float3 wo, float3 u) const {
+        if (wo.z < 0.000001f)
+            return bsdf_sample_none();
+
+        float specular_probability = get_specular_probability();
+        float coat_probability = get_coat_probability();
+        float diffuse_probability = 1.0f - coat_probability - specular_probability;
+
+        bool sample_coat = u.z < coat_probability;
+        bool sample_specular = !sample_coat && u.z < (coat_probability + specular_probability);
+        bool sample_diffuse = !sample_coat && !sample_specular;
+
+        BsdfSample s;
+        if (sample_diffuse) {
+            s = oren_nayar::sample(diffuse_tint, roughness, wo, f2(u.x, u.y));
+            s.pdf.v *= diffuse_probability;
+        } else if (sample_specular) {
+            s = ggx_r::sample(get_specular_alpha(), specularity, wo, f2(u.x, u.y));
+            s.reflectance *= specular_scale;
+            s.pdf.v *= specular_probability;
+        } else {
+            s = ggx_r::sample(coat_alpha, f3(COAT_SPECULARITY), wo, f2(u.x, u.y));
+            s.reflectance *= coat_scale;
+            s.pdf.v *= coat_probability;
+        }
+
+        if (s.pdf.invalid_or_delta_dirac())
+            return s;
+
+        if (!sample_diffuse) {
+            BsdfResponse r = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, wo, s.direction);
+            if (r.pdf.is_valid_and_not_delta_dirac()) {
+                s.reflectance += r.reflectance;
+                s.pdf.v += r.pdf.v * diffuse_probability;
+            }
+        }
+        if (!sample_specular) {
+            BsdfResponse r = ggx_r::evaluate_with_pdf(get_specular_alpha(), specularity, wo, s.direction);
+            if (r.pdf.is_valid_and_not_delta_dirac()) {
+                s.reflectance += r.reflectance * specular_scale;
+                s.pdf.v += r.pdf.v * specular_probability;
+            }
+        }
+        if (!sample_coat && coat_scale > 0.0f) {
+            BsdfResponse r = ggx_r::evaluate_with_pdf(coat_alpha, f3(COAT_SPECULARITY), wo, s.direction);
+            if (r.pdf.is_valid_and_not_delta_dirac()) {
+                s.reflectance += coat_scale * r.reflectance;
+                s.pdf.v += r.pdf.v * coat_probability;
+            }
+        }
+        return s;
+    }
+};
+
+} // namespace bpt

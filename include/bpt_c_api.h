@@ -1,0 +1,201 @@
+/* bpt_c_api.h - C ABI of the B200 path tracer that replaces Bifrost3D's OptiXRenderer hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++ or torch types. The host side of
+ * the reference (extensions/OptiXRenderer/OptiXRenderer/Renderer.cpp) flattens the Bifrost core
+ * scene into an OptiX graph and calls `context->launch(...)`; a maintainer swapping in this library
+ * flattens the same scene into the calls below instead (INTEGRATION.md shows the binding).
+ * Every entry point cites the reference interface it replaces.
+ *
+ * Conventions: all functions return 0 on success and a negative bpt_status otherwise;
+ * `bpt_last_error(ctx)` returns a static, human readable message for the last failure.
+ * Unless a parameter says "device", pointers are HOST pointers and are copied during the call.
+ * There is NO CPU fallback: without a CUDA device `bpt_create` fails.
+ */
+#ifndef BPT_C_API_H
+#define BPT_C_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bpt_ctx bpt_ctx;
+
+typedef enum bpt_status {
+    BPT_OK = 0,
+    BPT_ERROR_INVALID_ARGUMENT = -1,
+    BPT_ERROR_CUDA = -2,
+    BPT_ERROR_NO_DEVICE = -3,
+    BPT_ERROR_OUT_OF_MEMORY = -4,
+    BPT_ERROR_NOT_READY = -5
+} bpt_status;
+
+/* ---- PODs, layout identical to extensions/OptiXRenderer/OptiXRenderer/Types.h ------------------ */
+
+/* Types.h:353-416 `Material` (64 bytes). Texture ids must be 0: textures are a "next" row. */
+typedef struct bpt_material {
+    uint16_t flags;              /* 1 = ThinWalled, 2 = Cutout */
+    uint16_t shading_model;      /* 0 = Default (the only model implemented), 1 = Diffuse, 2 = Transmissive */
+    float tint[3];
+    float roughness;
+    int32_t tint_roughness_texture_id;
+    int32_t roughness_texture_id;
+    float specularity;
+    float metallic;
+    int32_t metallic_texture_id;
+    float coverage;
+    int32_t coverage_texture_id;
+    float emission[3];
+    uint16_t coat;               /* UNorm16, Types.h:76-93 */
+    uint16_t coat_roughness;     /* UNorm16 */
+} bpt_material;
+
+/* Types.h:290-312 `Light` (48 bytes): 11 payload floats + flags. */
+enum { BPT_LIGHT_NONE = 0, BPT_LIGHT_SPHERE = 1, BPT_LIGHT_DIRECTIONAL = 2, BPT_LIGHT_ENVIRONMENT = 3,
+       BPT_LIGHT_PRESAMPLED_ENVIRONMENT = 4, BPT_LIGHT_SPOT = 5, BPT_LIGHT_TYPE_MASK = 7 };
+typedef struct bpt_light {
+    /* sphere:      power[3], position[3], radius                       (Types.h:224-228)
+     * spot:        power[3], position[3], radius, direction[3], cos_angle (Types.h:230-236)
+     * directional: radiance[3], direction[3], pad                      (Types.h:238-242) */
+    float data[11];
+    uint32_t flags;
+} bpt_light;
+
+/* Types.h:210-222 `LightSample` (32 bytes). pdf < 0 encodes a delta light (Types.h:155-204). */
+typedef struct bpt_light_sample {
+    float radiance[3];
+    float pdf;
+    float direction_to_light[3];
+    float distance;
+} bpt_light_sample;
+
+/* One MeshModel: mesh + material + world transform. Renderer.cpp:138-182 (one BLAS + Transform per
+ * model there; flattened to world space here). `to_world` is a row-major 3x4 affine matrix; Bifrost
+ * transforms are rigid + uniform scale (core/Bifrost/Bifrost/Math/Transform.h:28-35). */
+typedef struct bpt_instance {
+    int32_t mesh_id;
+    int32_t material_id;
+    float to_world[12];
+} bpt_instance;
+
+/* Types.h:486-501 `CameraStateGPU` minus the buffer ids. Matrices are row-major. */
+typedef struct bpt_camera {
+    float view_to_world_rotation[9];
+    float inverse_projection[16];
+    float inverse_view_projection[16];
+} bpt_camera;
+
+/* Renderer state read by one render call: Renderer.cpp:216 (max_bounce_count, default 4), :479
+ * (next_event_sample_count, default 3), PublicTypes.h:40-45 (path regularisation PDF scale, default 0.5
+ * and already multiplied by (1 + decay * accumulations) by the caller). */
+typedef struct bpt_settings {
+    uint32_t max_bounce_count;
+    int32_t next_event_sample_count;
+    float path_regularization_pdf_scale;
+    uint32_t reserved;
+} bpt_settings;
+
+typedef struct bpt_counters {
+    uint64_t extend_rays;     /* closest-hit traversals            */
+    uint64_t shadow_rays;     /* any-hit (visibility) traversals   */
+    uint64_t samples;         /* pixel samples started             */
+    uint64_t kernel_launches; /* CUDA kernels launched by the library */
+    float extend_ms;          /* CUDA-event time spent in the closest-hit traversal kernel */
+    float shadow_ms;
+    float shade_ms;
+    float other_ms;
+} bpt_counters;
+
+/* ---- context ----------------------------------------------------------------------------------- */
+
+/* Renderer::initialize, Renderer.cpp:1365-1378 / Implementation ctor :273-574. */
+int bpt_create(int cuda_device, bpt_ctx** out_ctx);
+void bpt_destroy(bpt_ctx* ctx);
+const char* bpt_last_error(const bpt_ctx* ctx);
+/* CUDA stream (cudaStream_t) all work of this context is enqueued on; for event timing by callers. */
+void* bpt_stream(bpt_ctx* ctx);
+
+/* Rho / alpha tables that Renderer.cpp:400-466 uploads as textures. 32x32 floats each, row-major, from
+ * Bifrost::Assets::Shading::{Rho::GGX_with_fresnel, Rho::GGX, Estimate_GGX_bounded_VNDF_alpha::alphas}
+ * (core/Bifrost/Bifrost/Assets/Shading/Fittings.h:58-74). */
+int bpt_set_tables(bpt_ctx* ctx, const float* ggx_with_fresnel_rho, const float* ggx_rho, const float* estimate_ggx_alpha);
+
+/* ---- scene upload (Renderer::handle_updates, Renderer.cpp:578-1205) ---------------------------- */
+
+/* load_mesh, Renderer.cpp:92-136. indices: 3*primitive_count uint32; positions: 3*vertex_count floats;
+ * normals (nullable): 3*vertex_count floats, octahedral-encoded to short2 like OctahedralNormal::encode_precise;
+ * texcoords (nullable): 2*vertex_count floats; tint_roughness (nullable): 4*vertex_count bytes. */
+int bpt_upload_mesh(bpt_ctx* ctx, int mesh_id, const uint32_t* indices, int primitive_count,
+                    const float* positions, const float* normals, const float* texcoords,
+                    const uint8_t* tint_roughness, int vertex_count);
+/* Renderer.cpp:1043-1110 (mesh models) + :1010-1041 (transforms). Replaces all instances. */
+int bpt_set_instances(bpt_ctx* ctx, const bpt_instance* instances, int count);
+/* upload_material, Renderer.cpp:753-850. Index = MaterialID; index 0 is the invalid material. */
+int bpt_set_materials(bpt_ctx* ctx, const bpt_material* materials, int count);
+/* Renderer.cpp:852-1008. Sphere, spot and directional lights. */
+int bpt_set_lights(bpt_ctx* ctx, const bpt_light* lights, int count);
+/* Scene root environment, Renderer.cpp:1112-1200, PresampledEnvironmentMap.cpp:19-101.
+ * texels: width*height RGBA float latlong map (nullable -> constant `tint`); per_pixel_pdf: pdf_width*pdf_height
+ * floats (solid angle PDF sans sin theta, InfiniteAreaLight.cpp:140-157); samples: `sample_count` presampled
+ * light samples (PresampledEnvironmentMap.cpp:60-96). */
+int bpt_set_environment(bpt_ctx* ctx, const float tint[3], const float* texels, int width, int height,
+                        const float* per_pixel_pdf, int pdf_width, int pdf_height,
+                        const bpt_light_sample* samples, int sample_count);
+/* Acceleration structure build; replaces OptiX Trbvh (Renderer.cpp:161-182,470-477). Flattens the
+ * instances to world space, builds the LBVH on the device. Must be called after meshes/instances change. */
+int bpt_build_accel(bpt_ctx* ctx);
+/* Number of triangles / BVH nodes of the last build and its device time in ms. */
+int bpt_accel_info(bpt_ctx* ctx, int64_t* triangle_count, int64_t* node_count, float* build_ms);
+
+/* ---- rendering (Renderer::render, Renderer.cpp:1250-1265; SimpleRGPs.cu:74-140) ----------------- */
+
+/* Renders `sample_count` progressive samples with accumulation indices first_sample .. first_sample+sample_count-1
+ * for every pixel of a width x height frame into the context-owned accumulation buffer.
+ * The buffer holds the per-pixel radiance SUM as double4 (w = number of samples); it is reset when
+ * `reset_accumulation` != 0 or the frame size changes (Renderer.cpp:1207-1248). */
+int bpt_render(bpt_ctx* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
+               uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
+/* Device pointer to the double4[width*height] accumulation (sum) buffer, e.g. for an NCCL reduce. */
+void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
+/* mean = sum / w, converted to half4 (alpha 1) exactly like SimpleRGPs.cu:39-42,106; written to `out` which is
+ * a HOST pointer to width*height*4 uint16 (on_device == 0) or a DEVICE pointer (on_device != 0). */
+int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
+/* mean as float4 to a HOST buffer of width*height*4 floats. */
+int bpt_resolve_float4(bpt_ctx* ctx, float* out);
+int bpt_synchronize(bpt_ctx* ctx);
+int bpt_get_counters(bpt_ctx* ctx, bpt_counters* out, int reset);
+
+/* ---- batched unit entry points (parity tests and the C1 workload) ------------------------------ */
+
+enum { BPT_BSDF_DEFAULT_SHADING = 0, BPT_BSDF_GGX_R = 1, BPT_BSDF_OREN_NAYAR = 2, BPT_BSDF_BURLEY = 3 };
+/* evaluate_with_PDF(wo, wi) and sample(wo, u) for n tuples. wo, wi, tint, u: 3n floats; rms: {roughness, metallic,
+ * specularity} 3n floats; coat (nullable): {coat, coat_roughness} 2n floats.
+ * Outputs: eval_f 3n, eval_pdf n, sample_f 3n, sample_pdf n, sample_dir 3n.
+ * on_device != 0: all pointers are device pointers and nothing is copied. */
+int bpt_bsdf_eval_sample_pdf(bpt_ctx* ctx, int kind, int64_t n, const float* wo, const float* wi, const float* tint,
+                             const float* rms, const float* coat, const float* u,
+                             float* eval_f, float* eval_pdf, float* sample_f, float* sample_pdf, float* sample_dir,
+                             int on_device);
+/* DefaultShading as the renderer constructs it (per-vertex scale + path regularisation), for n elements. */
+int bpt_default_shading_regularized(bpt_ctx* ctx, int64_t n, const bpt_material* materials, const float* tint_roughness_scale,
+                                    const float* max_pdf_hint, const float* wo, const float* wi, const float* u,
+                                    float* eval_f, float* eval_pdf, float* sample_f, float* sample_pdf, float* sample_dir);
+/* sample_radiance / pdf / evaluate for n (light, position) pairs; light_stride 0 broadcasts lights[0]. */
+int bpt_light_sample_pdf_evaluate(bpt_ctx* ctx, int64_t n, const bpt_light* lights, int light_stride, const float* position,
+                                  const float* u2, const float* query_direction,
+                                  bpt_light_sample* out_samples, float* out_pdf, float* out_radiance);
+/* PracticalScrambledSobol::sample4ui / sample4f (RNG.h:280-292) for n (accumulation, pixel_hash, dimension) triples. */
+int bpt_rng_sample4(bpt_ctx* ctx, int64_t n, const uint32_t* accumulation, const uint32_t* pixel_hash, const uint32_t* dimension,
+                    uint32_t* out_ui4, float* out_f4);
+/* Closest-hit and any-hit queries against the built acceleration structure for n rays.
+ * origins/directions: 3n floats; tmin/tmax: n floats. out_primitive: global primitive index (instance-major) or -1;
+ * out_t: hit distance; out_uv: barycentrics (2n); out_occluded: n bytes (any hit in [tmin, tmax]). Nullable outputs are skipped. */
+int bpt_intersect(bpt_ctx* ctx, int64_t n, const float* origins, const float* directions, const float* tmin, const float* tmax,
+                  int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* BPT_C_API_H */

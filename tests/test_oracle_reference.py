@@ -1,0 +1,77 @@
+"""CPU tests that pin the oracle to the reference's own golden vectors (no GPU needed)."""
+import subprocess
+
+import numpy as np
+import pytest
+
+from tests import oracle_lib
+
+pytestmark = pytest.mark.skipif(not oracle_lib.available(), reason="oracle/_ref not built")
+
+GTESTS = oracle_lib.REPO / "oracle" / "_ref" / "ref_gtests"
+
+
+def test_reference_gtest_suite_passes():
+    """The reference's own host-compiled OptiXRendererTests cases (85) pass with the oracle toolchain."""
+    out = subprocess.run([str(GTESTS)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-2000:]
+    assert "[  PASSED  ] 85 tests." in out.stdout
+
+
+def test_pod_sizes(ref):
+    # sizes measured from the reference's host build.
+    expected = {"Material": 64, "Light": 48, "LightSample": 32, "BSDFSample": 32, "BSDFResponse": 16,
+                "MonteCarloPayload": 160, "VertexGeometry": 16, "DefaultShading": 44}
+    for name, size in expected.items():
+        assert ref.sizeof(name) == size, name
+
+
+def test_default_shading_regression_vectors(ref):
+    """tests/OptiXRendererTests/ShadingModels/DefaultShadingTest.h:410-447 through the oracle's C API."""
+    golden = np.array([
+        [497358.250000, 380976.437500, 167112.35938, 497357.968750], [124339.296875, 95243.906250, 41778.00000, 124339.195313],
+        [994714.562500, 762453.062500, 335647.75000, 703369.687500], [249080.015625, 190921.531250, 84049.10156, 175985.171875],
+        [4957685248.0, 4900781568.0, 4796215808.0, 49668972.0], [1455754624.0, 1439689728.0, 1410168448.0, 13442245.0],
+        [0.011624, 0.076557, 0.09214, 0.010905], [0.012486, 0.092185, 0.11131, 0.230607],
+        [0.012840, 0.122771, 0.14915, 0.034218], [0.011330, 0.121562, 0.14802, 0.254778],
+        [0.051809, 0.085369, 0.09342, 0.286622], [0.013969, 0.145090, 0.17656, 0.218950],
+        [0.019217, 0.081176, 0.09605, 0.0164565], [0.019548, 0.0975228, 0.116237, 0.228887],
+        [0.017939, 0.128357, 0.15486, 0.0377722], [0.014534, 0.125507, 0.15214, 0.239682],
+        [0.088401, 0.115091, 0.12150, 0.317704], [0.018240, 0.147322, 0.17830, 0.192018]], np.float64)
+    tuples = regression_inputs(ref)
+    out = ref.bsdf_eval_sample_pdf(0, **tuples)
+    got = np.concatenate([out["sample_f"], np.abs(out["sample_pdf"])[:, None]], axis=1).astype(np.float64)
+    assert np.all(np.abs(got - golden) <= golden * 1e-4), np.abs(got - golden) / golden
+
+
+def regression_inputs(ref):
+    """gold / plastic / coated plastic x 3 wo x 2 sample02 points (ShadingModelTestUtils.h:23-47)."""
+    mats = [((1.0, 0.766, 0.336), 0.02, 1.0, 1.0, 0.0, 0.0), ((0.02, 0.27, 0.33), 0.7, 0.0, 0.02, 0.0, 0.0),
+            ((0.02, 0.27, 0.33), 0.7, 0.0, 0.02, 1.0, 0.7)]
+    def normalize(v):
+        v = np.array(v, np.float32); return v * np.float32(1.0 / np.sqrt(np.float32(np.dot(v, v))))
+    wos = [np.array([0, 0, 1], np.float32), normalize([1, 0, 1]), normalize([1, 0, 0.01])]
+    s02 = ref.sample02(2)
+    rows = []
+    for tint, rough, metal, spec, coat, coat_r in mats:
+        for wo in wos:
+            for s in range(2):
+                rows.append((wo, tint, (rough, metal, spec), (s02[s, 0], s02[s, 1], (s + 0.5) / 2), (coat, coat_r)))
+    n = len(rows)
+    return {"wo": np.array([r[0] for r in rows], np.float32), "wi": np.tile(np.array([0, 0, 1], np.float32), (n, 1)),
+            "tint": np.array([r[1] for r in rows], np.float32), "rms": np.array([r[2] for r in rows], np.float32),
+            "u": np.array([r[3] for r in rows], np.float32), "coat": np.array([r[4] for r in rows], np.float32)}
+
+
+def test_tables_match_committed_data(ref):
+    from bifrost3d_b200.capi import default_tables
+    a, b, c, dims = ref.tables()
+    assert list(dims) == [32] * 6
+    ta, tb, tc = default_tables()
+    assert np.array_equal(a, ta) and np.array_equal(b, tb) and np.array_equal(c, tc)
+
+
+def test_golden_fixture_matches_oracle(ref):
+    """tests/golden/bsdf_c1_small.npz was generated from this oracle (tests/golden/make_golden.py)."""
+    from tests.golden import make_golden
+    make_golden.check(ref)
