@@ -111,8 +111,9 @@ __global__ void __launch_bounds__(BSDF_BLOCK) bsdf_batch_kernel(BsdfBatchArgs a)
                 r = ggx_r::evaluate_with_pdf(alpha, tint, wo, wi);
                 s = ggx_r::sample(alpha, tint, wo, f2(u.x, u.y));
             } else if (KIND == BPT_BSDF_OREN_NAYAR) {
-                r = oren_nayar::evaluate_with_pdf(tint, roughness, wo, wi);
-                s = oren_nayar::sample(tint, roughness, wo, f2(u.x, u.y));
+                float roughness_factor = oren_nayar::uniform_lobe_roughness_factor(roughness);
+                r = oren_nayar::evaluate_with_pdf(tint, roughness, roughness_factor, wo, wi);
+                s = oren_nayar::sample(tint, roughness, roughness_factor, wo, f2(u.x, u.y));
             } else {
                 r = burley::evaluate_with_pdf(tint, roughness, wo, wi);
                 s = burley::sample(tint, roughness, wo, f2(u.x, u.y));

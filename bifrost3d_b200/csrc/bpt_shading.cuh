@@ -47,8 +47,22 @@ BPT_HD BsdfSample bsdf_sample_none() { BsdfSample s; s.reflectance = f3(0.0f); s
 
 struct DirectionalSample { float3 direction; float pdf; };
 
-// The reference's host build calls sin() and cos() separately; sincosf() returns the same values.
-BPT_D void sincos_(float theta, float& s, float& c) { sincosf(theta, &s, &c); }
+// powf evaluated through double precision pow: the result is the correctly rounded float in all but
+// vanishingly rare halfway cases, which is what glibc's powf (the oracle's) delivers too. CUDA's native powf
+// is only accurate to a few ulp, and the two call sites (Oren-Nayar lobe selection probability, coat
+// roughness modulation) feed cancellation-prone expressions, so the extra fp64 work buys parity. Both are
+// evaluated once per shading setup, not per BSDF evaluation.
+BPT_D float powf_exact(float x, float y) { return (float)pow((double)x, (double)y); }
+
+// sin/cos of a float angle evaluated in double precision and rounded once: correctly rounded results, which
+// is what the oracle's glibc sinf/cosf deliver in all but ~1e-3 of cases (CUDA's sincosf is 2 ulp). Several
+// samplers square and subtract the results (sqrt(1 - x*x - y*y) in the clipped-LTC and VNDF samplers), which
+// amplifies a 1 ulp difference beyond the 1e-5 parity bound; B200's FP64 rate (half of FP32) makes this cheap.
+BPT_D void sincos_(float theta, float& s, float& c) {
+    double sd, cd;
+    sincos((double)theta, &sd, &cd);
+    s = (float)sd; c = (float)cd;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Table sampling (ImageSampling.h:18-41). `pixels` is row-major [height][width].
@@ -122,7 +136,9 @@ BPT_D float disk_pdf(float radius) { return 1.0f / (PI_F * pow2(radius)); }
 BPT_D float2 disk_sample(float radius, float2 u) {
     float r = sqrtf(u.x) * radius;
     float phi = 2.0f * PI_F * u.y;
-    return f2(r * cosf(phi), r * sinf(phi));
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    return f2(r * cos_phi, r * sin_phi);
 }
 
 BPT_D float uniform_hemisphere_pdf() { return 0.5f * RECIP_PI_F; }
@@ -309,7 +325,7 @@ BPT_D float3 adjust_conductor_specularity_to_exterior_medium(float3 exterior_ior
 BPT_D float modulate_roughness_under_coat(float base_roughness, float coat_roughness) {
     float x_coat = 1.0f - AIR_IOR / COAT_IOR;
     float adjusted_roughness4 = fminf(1.0f, pow4(base_roughness) + 2.0f * x_coat * pow4(coat_roughness));
-    return powf(adjusted_roughness4, 0.25f);
+    return powf_exact(adjusted_roughness4, 0.25f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,27 +423,31 @@ BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
     return f_single_scatter + f_multi_scatter;
 }
 
-BPT_D float uniform_lobe_probability(float roughness, float cos_theta) {
-    return powf(roughness, 0.1f) * (0.162925f + cos_theta * (-0.372058f + (0.538233f - 0.290822f * cos_theta) * cos_theta));
+// pow(roughness, 0.1): the only transcendental in the lobe selection probability; hoisted so that callers
+// that evaluate the BSDF several times for one (roughness, wo) pay for it once.
+BPT_D float uniform_lobe_roughness_factor(float roughness) { return powf_exact(roughness, 0.1f); }
+
+BPT_D float uniform_lobe_probability(float roughness_factor, float cos_theta) {
+    return roughness_factor * (0.162925f + cos_theta * (-0.372058f + (0.538233f - 0.290822f * cos_theta) * cos_theta));
 }
 
-BPT_D Pdf pdf(float roughness, float3 wo, float3 wi) {
-    float uniform_probability = uniform_lobe_probability(roughness, wo.z);
+BPT_D Pdf pdf(float roughness, float roughness_factor, float3 wo, float3 wi) {
+    float uniform_probability = uniform_lobe_probability(roughness_factor, wo.z);
     float cltc_probability = 1.0f - uniform_probability;
     float cltc_PDF = dist::oren_nayar_cltc_pdf(roughness, wo, wi);
     float uniform_PDF = dist::uniform_hemisphere_pdf();
     return Pdf(uniform_probability * uniform_PDF + cltc_probability * cltc_PDF);
 }
 
-BPT_D BsdfResponse evaluate_with_pdf(float3 albedo, float roughness, float3 wo, float3 wi) {
+BPT_D BsdfResponse evaluate_with_pdf(float3 albedo, float roughness, float roughness_factor, float3 wo, float3 wi) {
     BsdfResponse r;
     r.reflectance = albedo * evaluate(roughness, wo, wi);
-    r.pdf = pdf(roughness, wo, wi);
+    r.pdf = pdf(roughness, roughness_factor, wo, wi);
     return r;
 }
 
-BPT_D BsdfSample sample(float3 albedo, float roughness, float3 wo, float2 u) {
-    float uniform_probability = uniform_lobe_probability(roughness, wo.z);
+BPT_D BsdfSample sample(float3 albedo, float roughness, float roughness_factor, float3 wo, float2 u) {
+    float uniform_probability = uniform_lobe_probability(roughness_factor, wo.z);
     float cltc_probability = 1.0f - uniform_probability;
 
     DirectionalSample ds;
@@ -513,6 +533,7 @@ struct DefaultShading {
     float specular_scale;
     float coat_scale;
     float coat_alpha;
+    float diffuse_roughness_factor; // pow(roughness, 0.1), hoisted out of the Oren-Nayar PDF
     unsigned short specular_probability_q; // quantised to 16 bit exactly like the reference
     unsigned short coat_probability_q;
 
@@ -606,6 +627,7 @@ struct DefaultShading {
         float coat_rho;
         s.setup_shading(t, tint, roughness, specularity, metallic, coat, coat_roughness, abs_cos_theta_o, coat_rho);
         s.setup_sampling_probabilities(t, abs_cos_theta_o, coat_rho);
+        s.diffuse_roughness_factor = oren_nayar::uniform_lobe_roughness_factor(s.roughness);
         return s;
     }
 
@@ -630,7 +652,7 @@ struct DefaultShading {
         if (wo.z < 0.000001f || wi.z < 0.000001f)
             return bsdf_response_none();
 
-        BsdfResponse diffuse_response = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, wo, wi);
+        BsdfResponse diffuse_response = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, diffuse_roughness_factor, wo, wi);
         BsdfResponse specular_response = ggx_r::evaluate_with_pdf(get_specular_alpha(), specularity, wo, wi);
         specular_response.reflectance *= specular_scale;
 
@@ -664,7 +686,7 @@ struct DefaultShading {
 
         BsdfSample s;
         if (sample_diffuse) {
-            s = oren_nayar::sample(diffuse_tint, roughness, wo, f2(u.x, u.y));
+            s = oren_nayar::sample(diffuse_tint, roughness, diffuse_roughness_factor, wo, f2(u.x, u.y));
             s.pdf.v *= diffuse_probability;
         } else if (sample_specular) {
             s = ggx_r::sample(get_specular_alpha(), specularity, wo, f2(u.x, u.y));
@@ -680,7 +702,7 @@ struct DefaultShading {
             return s;
 
         if (!sample_diffuse) {
-            BsdfResponse r = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, wo, s.direction);
+            BsdfResponse r = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, diffuse_roughness_factor, wo, s.direction);
             if (r.pdf.is_valid_and_not_delta_dirac()) {
                 s.reflectance += r.reflectance;
                 s.pdf.v += r.pdf.v * diffuse_probability;

@@ -14,10 +14,14 @@ pytestmark = pytest.mark.gpu
 KINDS = {"default": 0, "ggx_r": 1, "oren_nayar": 2, "burley": 3}
 
 # Fraction of tuples allowed to exceed the 1e-5 relative bound. These are ill-conditioned tuples
-# (catastrophic cancellation at grazing angles, tan^2 blow-ups) where 1 ulp of difference in sinf/powf
+# (sqrt(1 - x*x - y*y) near the horizon, rescaled lobe-selection numbers) where the rare 1 ulp difference in sin/cos/pow
 # between glibc and CUDA's libdevice is amplified; see DESIGN.md "FP contract".
-ALLOWED_OUTLIER_FRACTION = 2e-4
-OUTLIER_REL_TOL = 2e-2
+ALLOWED_OUTLIER_FRACTION = 5e-5
+OUTLIER_REL_TOL = 2e-3
+
+
+def allowed_outliers(n):
+    return max(2, int(np.ceil(ALLOWED_OUTLIER_FRACTION * n)))
 
 
 def compare_bsdf(got, want, what):
@@ -27,23 +31,21 @@ def compare_bsdf(got, want, what):
         mismatch = cg != cw
         # a PDF straddling the 1e-6 validity threshold by rounding is a legitimate class flip
         near_threshold = np.abs(np.abs(want[key]) - 1e-6) < 1e-9
-        frac = np.mean(mismatch & ~near_threshold)
-        assert frac <= ALLOWED_OUTLIER_FRACTION, f"{what}.{key}: PDF class mismatch fraction {frac}"
+        count = np.sum(mismatch & ~near_threshold)
+        assert count <= allowed_outliers(mismatch.size), f"{what}.{key}: {count} PDF class mismatches"
     for key, floor in (("eval_f", 1e-6), ("eval_pdf", 1e-6), ("sample_f", 1e-6), ("sample_pdf", 1e-6)):
         # Compare samples only where both agree the sample is usable (the reflectance of an invalid sample is unspecified).
         e = rel_err(got[key], want[key], floor)
         if key.startswith("sample"):
             valid = pdf_class(want["sample_pdf"]) == pdf_class(got["sample_pdf"])
             e = e[valid]
-        frac = np.mean(e > REL_TOL)
         msgs.append(report(f"{what}.{key}", e, REL_TOL))
-        assert frac <= ALLOWED_OUTLIER_FRACTION, msgs[-1]
+        assert np.sum(e > REL_TOL) <= allowed_outliers(e.size), msgs[-1]
         assert np.all(e[np.isfinite(e)] <= OUTLIER_REL_TOL) or np.mean(e > OUTLIER_REL_TOL) < 2e-5, msgs[-1]
     valid = (pdf_class(want["sample_pdf"]) == 3) & (pdf_class(got["sample_pdf"]) == 3)
     d = np.abs(got["sample_dir"][valid].astype(np.float64) - want["sample_dir"][valid])
-    frac = np.mean(d > 1e-5)
-    msgs.append(f"{what}.sample_dir: max abs err {d.max() if d.size else 0:.3e}, fraction above 1e-5: {frac:.2e}")
-    assert frac <= ALLOWED_OUTLIER_FRACTION, msgs[-1]
+    msgs.append(f"{what}.sample_dir: max abs err {d.max() if d.size else 0:.3e}, {int(np.sum(d > 1e-5))}/{d.size} above 1e-5")
+    assert np.sum(d > 1e-5) <= allowed_outliers(d.size), msgs[-1]
     return msgs
 
 
