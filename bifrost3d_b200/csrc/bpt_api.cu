@@ -329,7 +329,7 @@ void bpt_destroy(bpt_ctx* c) {
     release_wavefront(ctx);
     ctx->tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
-    ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release();
+    ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release();
     if (ctx->device_counters) cudaFree(ctx->device_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);

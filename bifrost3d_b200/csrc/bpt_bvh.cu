@@ -1,5 +1,472 @@
+// Acceleration structure build on the device (replaces OptiX "Trbvh", Renderer.cpp:161-182,470-477) and the
+// batched intersection entry point.
+//
+// Build = flatten instances to world space -> centroid bounds -> 63-bit Morton codes -> radix sort ->
+// Karras' parallel radix tree (HPG 2012) -> bottom-up box fit -> emit 64-byte two-child nodes with subtrees
+// of <= LEAF_MAX triangles collapsed into leaves, and the Morton-ordered 48-byte triangle array.
 #include "bpt_context.h"
+#include "bpt_trace.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include <algorithm>
+#include <float.h>
+
 namespace bpt {
-int build_accel(Context* ctx) { return ctx->fail(BPT_ERROR_NOT_READY, "build_accel: not implemented yet"); }
-int intersect_batch(Context* ctx, int64_t, const float*, const float*, const float*, const float*, int32_t*, float*, float*, uint8_t*) { return ctx->fail(BPT_ERROR_NOT_READY, "intersect: not implemented yet"); }
+
+namespace {
+
+constexpr int LEAF_MAX = 4;
+
+struct InstanceRecord {
+    int prim_offset;   // first global primitive index
+    int prim_count;
+    int index_offset;  // first index triple in the concatenated index buffer
+    int vertex_offset; // first vertex in the concatenated vertex buffers
+    int material;
+    uint32_t flags;    // bit0: has normals, bit1: has tints
+    float m[12];       // object -> world, row-major 3x4
+};
+
+struct Aabb { float3 lo, hi; };
+
+__device__ __forceinline__ float3 transform_point(const float* m, float3 p) {
+    // ((m0*x + m1*y) + m2*z) + m3, no contraction: the oracle flattens with the same rounding.
+    return f3(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], p.x), __fmul_rn(m[1], p.y)), __fmul_rn(m[2], p.z)), m[3]),
+              __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], p.x), __fmul_rn(m[5], p.y)), __fmul_rn(m[6], p.z)), m[7]),
+              __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], p.x), __fmul_rn(m[9], p.y)), __fmul_rn(m[10], p.z)), m[11]));
 }
+
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+    if (v >= 0.0f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+// One thread per global primitive: world-space vertices, shading record, centroid bounds.
+__global__ void flatten_kernel(int64_t prim_total, int instance_count, const InstanceRecord* __restrict__ instances,
+                               const uint32_t* __restrict__ indices, const float* __restrict__ positions,
+                               const int16_t* __restrict__ normals, const uint8_t* __restrict__ tints,
+                               float4* __restrict__ world_vertices, ShadeTriangle* __restrict__ shade, float* scene_bounds /*[6]*/) {
+    float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
+    for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < prim_total; gp += (int64_t)gridDim.x * blockDim.x) {
+        // binary search: last instance with prim_offset <= gp
+        int a = 0, b = instance_count - 1;
+        while (a < b) {
+            int mid = (a + b + 1) >> 1;
+            if (instances[mid].prim_offset <= gp) a = mid; else b = mid - 1;
+        }
+        const InstanceRecord& inst = instances[a];
+        int lp = int(gp - inst.prim_offset);
+        const uint32_t* tri = indices + 3ll * (inst.index_offset + lp);
+        uint32_t i0 = tri[0] + inst.vertex_offset, i1 = tri[1] + inst.vertex_offset, i2 = tri[2] + inst.vertex_offset;
+        float3 p0 = transform_point(inst.m, f3(positions[3ll * i0], positions[3ll * i0 + 1], positions[3ll * i0 + 2]));
+        float3 p1 = transform_point(inst.m, f3(positions[3ll * i1], positions[3ll * i1 + 1], positions[3ll * i1 + 2]));
+        float3 p2 = transform_point(inst.m, f3(positions[3ll * i2], positions[3ll * i2 + 1], positions[3ll * i2 + 2]));
+        world_vertices[3 * gp] = f4(p0, 0.0f);
+        world_vertices[3 * gp + 1] = f4(p1, 0.0f);
+        world_vertices[3 * gp + 2] = f4(p2, 0.0f);
+
+        ShadeTriangle s = {};
+        if (inst.flags & 1u) {
+            s.n0[0] = normals[2ll * i0]; s.n0[1] = normals[2ll * i0 + 1];
+            s.n1[0] = normals[2ll * i1]; s.n1[1] = normals[2ll * i1 + 1];
+            s.n2[0] = normals[2ll * i2]; s.n2[1] = normals[2ll * i2 + 1];
+        }
+        if (inst.flags & 2u) {
+            for (int k = 0; k < 4; ++k) { s.t0[k] = tints[4ll * i0 + k]; s.t1[k] = tints[4ll * i1 + k]; s.t2[k] = tints[4ll * i2 + k]; }
+        }
+        s.material_index = inst.material;
+        s.flags = (uint32_t(a) << 2) | (inst.flags & 3u);
+        shade[gp] = s;
+
+        float3 c = (min3(min3(p0, p1), p2) + max3(max3(p0, p1), p2)) * 0.5f;
+        lo = min3(lo, c); hi = max3(hi, c);
+    }
+    // warp reduce, then one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o)); lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o)); hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+    }
+    if ((threadIdx.x & 31) == 0 && lo.x <= hi.x) {
+        atomic_min_float(scene_bounds + 0, lo.x); atomic_min_float(scene_bounds + 1, lo.y); atomic_min_float(scene_bounds + 2, lo.z);
+        atomic_max_float(scene_bounds + 3, hi.x); atomic_max_float(scene_bounds + 4, hi.y); atomic_max_float(scene_bounds + 5, hi.z);
+    }
+}
+
+__device__ __forceinline__ uint64_t expand_bits_21(uint64_t v) {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void morton_kernel(int64_t n, const float4* __restrict__ world_vertices, const float* __restrict__ scene_bounds,
+                              uint64_t* __restrict__ keys, uint32_t* __restrict__ values) {
+    float3 lo = f3(scene_bounds[0], scene_bounds[1], scene_bounds[2]);
+    float3 hi = f3(scene_bounds[3], scene_bounds[4], scene_bounds[5]);
+    float3 extent = max3(hi - lo, f3(1e-30f));
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float3 p0 = f3(world_vertices[3 * i]), p1 = f3(world_vertices[3 * i + 1]), p2 = f3(world_vertices[3 * i + 2]);
+        float3 c = (min3(min3(p0, p1), p2) + max3(max3(p0, p1), p2)) * 0.5f;
+        float3 q = (c - lo) / extent;
+        const float scale = 2097151.0f; // 2^21 - 1
+        uint64_t x = (uint64_t)fminf(fmaxf(q.x * scale, 0.0f), scale);
+        uint64_t y = (uint64_t)fminf(fmaxf(q.y * scale, 0.0f), scale);
+        uint64_t z = (uint64_t)fminf(fmaxf(q.z * scale, 0.0f), scale);
+        keys[i] = (expand_bits_21(x) << 2) | (expand_bits_21(y) << 1) | expand_bits_21(z);
+        values[i] = (uint32_t)i;
+    }
+}
+
+// Karras 2012. Internal node i in [0, n-2]; leaves are sorted positions [0, n-1].
+struct TreeNode {
+    int left, right;   // >= 0: internal node, < 0: ~leaf position
+    int first, last;   // covered range of sorted positions
+};
+
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void hierarchy_kernel(int n, const uint64_t* __restrict__ keys, TreeNode* __restrict__ tree, int* __restrict__ parent_of_internal,
+                                 int* __restrict__ parent_of_leaf) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    int delta_min = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > delta_min) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > delta_min) l += t;
+    int j = i + l * d;
+    int delta_node = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > delta_node) s += t;
+    } while (t > 1);
+    int gamma = i + s * d + min(d, 0);
+    int first = min(i, j), last = max(i, j);
+    TreeNode node;
+    node.first = first; node.last = last;
+    if (first == gamma) { node.left = ~gamma; parent_of_leaf[gamma] = i; } else { node.left = gamma; parent_of_internal[gamma] = i; }
+    if (last == gamma + 1) { node.right = ~(gamma + 1); parent_of_leaf[gamma + 1] = i; } else { node.right = gamma + 1; parent_of_internal[gamma + 1] = i; }
+    tree[i] = node;
+    if (i == 0) parent_of_internal[0] = -1;
+}
+
+__device__ __forceinline__ Aabb load_box_cg(const Aabb* p) {
+    const float* f = reinterpret_cast<const float*>(p);
+    Aabb b;
+    b.lo = f3(__ldcg(f), __ldcg(f + 1), __ldcg(f + 2));
+    b.hi = f3(__ldcg(f + 3), __ldcg(f + 4), __ldcg(f + 5));
+    return b;
+}
+
+// Writes the Morton-ordered triangle array and the leaf boxes, then climbs: the second thread to reach an
+// internal node merges its children's boxes (classic atomic-counter refit).
+__global__ void fit_kernel(int n, const uint32_t* __restrict__ sorted_prims, const float4* __restrict__ world_vertices,
+                           const ShadeTriangle* __restrict__ shade, const uint32_t* __restrict__ material_trace_flags,
+                           TraceTriangle* __restrict__ triangles, Aabb* __restrict__ leaf_boxes, Aabb* __restrict__ node_boxes,
+                           const TreeNode* __restrict__ tree, const int* __restrict__ parent_of_internal, const int* __restrict__ parent_of_leaf,
+                           int* __restrict__ arrival) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t gp = sorted_prims[p];
+    float4 v0 = world_vertices[3ll * gp], v1 = world_vertices[3ll * gp + 1], v2 = world_vertices[3ll * gp + 2];
+    int material = shade[gp].material_index;
+    TraceTriangle t;
+    t.v0 = make_float4(v0.x, v0.y, v0.z, __int_as_float((int)gp));
+    t.v1 = make_float4(v1.x, v1.y, v1.z, __int_as_float(material));
+    t.v2 = make_float4(v2.x, v2.y, v2.z, __uint_as_float(material_trace_flags[material]));
+    triangles[p] = t;
+    Aabb box;
+    box.lo = min3(min3(f3(v0), f3(v1)), f3(v2));
+    box.hi = max3(max3(f3(v0), f3(v1)), f3(v2));
+    leaf_boxes[p] = box;
+    if (n == 1) return;
+
+    int node = parent_of_leaf[p];
+    while (node >= 0) {
+        __threadfence();
+        if (atomicAdd(arrival + node, 1) == 0)
+            return; // first arrival: the sibling subtree is not finished yet
+        TreeNode tn = tree[node];
+        // L1 is not coherent across SMs: read the children's boxes from L2 (ld.global.cg). The sibling published
+        // its box before its atomicAdd (threadfence above).
+        Aabb l = load_box_cg(tn.left < 0 ? leaf_boxes + ~tn.left : node_boxes + tn.left);
+        Aabb r = load_box_cg(tn.right < 0 ? leaf_boxes + ~tn.right : node_boxes + tn.right);
+        Aabb merged;
+        merged.lo = min3(l.lo, r.lo); merged.hi = max3(l.hi, r.hi);
+        node_boxes[node] = merged;
+        node = parent_of_internal[node];
+    }
+}
+
+__global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
+                            BvhNode* __restrict__ nodes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    TreeNode tn = tree[i];
+    int link[2], count[2];
+    Aabb box[2];
+    int child[2] = { tn.left, tn.right };
+    for (int k = 0; k < 2; ++k) {
+        if (child[k] < 0) {
+            link[k] = child[k]; count[k] = 1; box[k] = leaf_boxes[~child[k]];
+        } else {
+            TreeNode c = tree[child[k]];
+            int size = c.last - c.first + 1;
+            box[k] = node_boxes[child[k]];
+            if (size <= LEAF_MAX) { link[k] = ~c.first; count[k] = size; }
+            else { link[k] = child[k]; count[k] = 0; }
+        }
+    }
+    BvhNode out;
+    out.lo_l_hi_l_x = make_float4(box[0].lo.x, box[0].lo.y, box[0].lo.z, box[0].hi.x);
+    out.hi_l_lo_r = make_float4(box[0].hi.y, box[0].hi.z, box[1].lo.x, box[1].lo.y);
+    out.lo_r_hi_r = make_float4(box[1].lo.z, box[1].hi.x, box[1].hi.y, box[1].hi.z);
+    out.left = link[0]; out.right = link[1]; out.left_count = count[0]; out.right_count = count[1];
+    nodes[i] = out;
+}
+
+__global__ void tiny_root_kernel(int n, const Aabb* __restrict__ leaf_boxes, BvhNode* __restrict__ nodes) {
+    // n == 0: both children absent. n == 1: the left child is the only triangle.
+    BvhNode out = {};
+    out.left = out.right = -1; out.left_count = out.right_count = -1;
+    if (n == 1) {
+        Aabb b = leaf_boxes[0];
+        out.lo_l_hi_l_x = make_float4(b.lo.x, b.lo.y, b.lo.z, b.hi.x);
+        out.hi_l_lo_r = make_float4(b.hi.y, b.hi.z, 0.0f, 0.0f);
+        out.left = ~0; out.left_count = 1;
+    }
+    nodes[0] = out;
+}
+
+// ---- batched queries -----------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel, int64_t n, const float* __restrict__ origins,
+                                                                const float* __restrict__ directions, const float* __restrict__ tmin,
+                                                                const float* __restrict__ tmax, const float* __restrict__ coverage,
+                                                                int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        Ray ray;
+        ray.origin = f3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
+        ray.direction = f3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+        ray.tmin = tmin[i]; ray.tmax = tmax[i];
+        float transmission;
+        if (out_primitive || out_t || out_uv) {
+            Hit h = trace<false>(accel, ray, -1, s_stack + threadIdx.x, transmission, coverage);
+            if (out_primitive) out_primitive[i] = h.primitive;
+            if (out_t) out_t[i] = h.primitive >= 0 ? h.t : INFINITY;
+            if (out_uv) { out_uv[2 * i] = h.u; out_uv[2 * i + 1] = h.v; }
+        }
+        if (out_occluded) {
+            trace<true>(accel, ray, -1, s_stack + threadIdx.x, transmission, coverage);
+            out_occluded[i] = transmission < 1.0f ? 1 : 0;
+        }
+    }
+}
+
+} // namespace
+
+// Per-material flags baked into the triangle records (v2.w). bit0: backface culled (not thin walled, not
+// transmissive: MonteCarlo.cu:146-150), bit1: fully opaque (coverage >= 1, not cutout).
+static uint32_t material_trace_flags(const Material& m) {
+    uint32_t f = 0;
+    if (!material_is_thin_walled(m) && !material_is_transmissive(m)) f |= 1u;
+    if (material_coverage(m) >= 1.0f) f |= 2u;
+    return f;
+}
+
+int build_accel(Context* ctx) {
+    Accel& A = ctx->accel;
+    A.valid = false;
+    cudaStream_t st = ctx->stream;
+
+    // ---- concatenate the meshes that are referenced and lay out the instances ----
+    std::map<int, int> mesh_slot; // mesh id -> record index
+    struct MeshSlot { int index_offset, vertex_offset; };
+    std::vector<MeshSlot> slots;
+    std::vector<uint32_t> h_indices; std::vector<float> h_positions; std::vector<int16_t> h_normals; std::vector<uint8_t> h_tints;
+    std::vector<InstanceRecord> records;
+    std::vector<float> h_normal_matrices; // 9 floats per record, row-major
+    int64_t prim_total = 0;
+    for (const bpt_instance& inst : ctx->instances) {
+        const HostMesh& mesh = ctx->meshes[inst.mesh_id];
+        auto it = mesh_slot.find(inst.mesh_id);
+        if (it == mesh_slot.end()) {
+            MeshSlot s = { int(h_indices.size() / 3), int(h_positions.size() / 3) };
+            h_indices.insert(h_indices.end(), mesh.indices.begin(), mesh.indices.end());
+            h_positions.insert(h_positions.end(), mesh.positions.begin(), mesh.positions.end());
+            h_normals.resize(2 * (h_positions.size() / 3), 0);
+            if (!mesh.normals.empty()) std::copy(mesh.normals.begin(), mesh.normals.end(), h_normals.begin() + 2ll * s.vertex_offset);
+            h_tints.resize(4 * (h_positions.size() / 3), 255);
+            if (!mesh.tints.empty()) std::copy(mesh.tints.begin(), mesh.tints.end(), h_tints.begin() + 4ll * s.vertex_offset);
+            slots.push_back(s);
+            it = mesh_slot.emplace(inst.mesh_id, int(slots.size()) - 1).first;
+        }
+        if (inst.material_id < 0 || inst.material_id >= (int)ctx->host_materials.size())
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_build_accel: instance references a material that was not uploaded");
+        if (mesh.primitive_count == 0) continue;
+        InstanceRecord r = {};
+        r.prim_offset = int(prim_total); r.prim_count = mesh.primitive_count;
+        r.index_offset = slots[it->second].index_offset; r.vertex_offset = slots[it->second].vertex_offset;
+        r.material = inst.material_id;
+        r.flags = (mesh.normals.empty() ? 0u : 1u) | (mesh.tints.empty() ? 0u : 2u);
+        memcpy(r.m, inst.to_world, sizeof(r.m));
+        records.push_back(r);
+        { // normal matrix = inverse transpose of the upper 3x3 (rtTransformNormal, MonteCarlo.cu:147,176), in double
+            const float* m = inst.to_world;
+            double a[9] = { m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10] };
+            double c[9] = { a[4] * a[8] - a[5] * a[7], a[5] * a[6] - a[3] * a[8], a[3] * a[7] - a[4] * a[6],
+                            a[2] * a[7] - a[1] * a[8], a[0] * a[8] - a[2] * a[6], a[1] * a[6] - a[0] * a[7],
+                            a[1] * a[5] - a[2] * a[4], a[2] * a[3] - a[0] * a[5], a[0] * a[4] - a[1] * a[3] };
+            double det = a[0] * c[0] + a[1] * c[1] + a[2] * c[2];
+            for (int k = 0; k < 9; ++k) h_normal_matrices.push_back(float(det != 0.0 ? c[k] / det : (k % 4 == 0 ? 1.0 : 0.0)));
+        }
+        prim_total += mesh.primitive_count;
+        if (prim_total > 0x7ffffff0ll)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_build_accel: more than 2^31 triangles");
+    }
+    const int n = int(prim_total);
+
+    std::vector<uint32_t> h_flags(ctx->host_materials.size());
+    for (size_t i = 0; i < h_flags.size(); ++i) h_flags[i] = material_trace_flags(ctx->host_materials[i]);
+
+    DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<uint32_t> d_indices; DeviceBuffer<float> d_positions;
+    DeviceBuffer<int16_t> d_normals; DeviceBuffer<uint8_t> d_tints; DeviceBuffer<uint32_t> d_flags; DeviceBuffer<float> d_bounds;
+    DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<unsigned char> d_temp;
+    DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
+    auto release_all = [&]() {
+        d_records.release(); d_indices.release(); d_positions.release(); d_normals.release(); d_tints.release(); d_flags.release(); d_bounds.release();
+        d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
+        d_tree.release(); d_parent_internal.release(); d_parent_leaf.release(); d_arrival.release(); d_leaf_boxes.release(); d_node_boxes.release();
+    };
+#define BUILD_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { release_all(); return ctx->cuda_fail(_e, #expr); } } while (0)
+
+    auto up = [&](auto& buf, const auto& host) -> cudaError_t {
+        cudaError_t e = buf.resize(std::max<size_t>(host.size(), 1));
+        if (e != cudaSuccess || host.empty()) return e;
+        return cudaMemcpyAsync(buf.ptr, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st);
+    };
+    BUILD_CHECK(up(d_records, records)); BUILD_CHECK(up(d_indices, h_indices)); BUILD_CHECK(up(d_positions, h_positions));
+    BUILD_CHECK(up(d_normals, h_normals)); BUILD_CHECK(up(d_tints, h_tints)); BUILD_CHECK(up(d_flags, h_flags));
+    BUILD_CHECK(up(A.normal_matrices, h_normal_matrices));
+    float init_bounds[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
+    BUILD_CHECK(d_bounds.resize(6));
+    BUILD_CHECK(cudaMemcpyAsync(d_bounds.ptr, init_bounds, sizeof(init_bounds), cudaMemcpyHostToDevice, st));
+
+    BUILD_CHECK(A.world_vertices.resize(std::max<size_t>(3ull * n, 1)));
+    BUILD_CHECK(A.shade.resize(std::max<size_t>(n, 1)));
+    BUILD_CHECK(A.triangles.resize(std::max<size_t>(n, 1)));
+    BUILD_CHECK(A.nodes.resize(std::max<size_t>(n > 1 ? n - 1 : 1, 1)));
+    BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
+
+    BUILD_CHECK(cudaEventRecord(ctx->ev[0], st));
+    const int block = 256;
+    auto grid = [&](int64_t count) { return (int)std::min<int64_t>((count + block - 1) / block, (int64_t)ctx->sm_count * 16); };
+    auto full_grid = [&](int64_t count) { return (int)((count + block - 1) / block); };
+
+    if (n > 0) {
+        flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, d_indices.ptr, d_positions.ptr, d_normals.ptr, d_tints.ptr,
+                                                  A.world_vertices.ptr, A.shade.ptr, d_bounds.ptr);
+        ctx->counters.kernel_launches++;
+        BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
+        morton_kernel<<<grid(n), block, 0, st>>>(n, A.world_vertices.ptr, d_bounds.ptr, d_keys.ptr, d_vals.ptr);
+        ctx->counters.kernel_launches++;
+
+        cub::DoubleBuffer<uint64_t> keys(d_keys.ptr, d_keys_alt.ptr);
+        cub::DoubleBuffer<uint32_t> vals(d_vals.ptr, d_vals_alt.ptr);
+        size_t temp_bytes = 0;
+        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, n, 0, 63, st));
+        BUILD_CHECK(d_temp.resize(std::max<size_t>(temp_bytes, 1)));
+        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.ptr, temp_bytes, keys, vals, n, 0, 63, st));
+        ctx->counters.kernel_launches += 8;
+
+        BUILD_CHECK(d_tree.resize(std::max(n - 1, 1))); BUILD_CHECK(d_parent_internal.resize(std::max(n - 1, 1)));
+        BUILD_CHECK(d_parent_leaf.resize(n)); BUILD_CHECK(d_arrival.resize(std::max(n - 1, 1))); BUILD_CHECK(d_node_boxes.resize(std::max(n - 1, 1)));
+        BUILD_CHECK(cudaMemsetAsync(d_arrival.ptr, 0, sizeof(int) * std::max(n - 1, 1), st));
+        if (n > 1) {
+            hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, keys.Current(), d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
+            ctx->counters.kernel_launches++;
+        }
+        fit_kernel<<<full_grid(n), block, 0, st>>>(n, vals.Current(), A.world_vertices.ptr, A.shade.ptr, d_flags.ptr, A.triangles.ptr,
+                                                   d_leaf_boxes.ptr, d_node_boxes.ptr, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr, d_arrival.ptr);
+        ctx->counters.kernel_launches++;
+        if (n > 1) {
+            emit_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, A.nodes.ptr);
+            ctx->counters.kernel_launches++;
+        }
+    }
+    if (n <= 1) {
+        tiny_root_kernel<<<1, 1, 0, st>>>(n, d_leaf_boxes.ptr, A.nodes.ptr);
+        ctx->counters.kernel_launches++;
+    }
+    BUILD_CHECK(cudaEventRecord(ctx->ev[1], st));
+    BUILD_CHECK(cudaGetLastError());
+    BUILD_CHECK(cudaStreamSynchronize(st));
+    cudaEventElapsedTime(&A.build_ms, ctx->ev[0], ctx->ev[1]);
+    release_all();
+#undef BUILD_CHECK
+
+    A.triangle_count = n;
+    A.node_count = n > 1 ? n - 1 : 1;
+    A.valid = true;
+    return BPT_OK;
+}
+
+int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* directions, const float* tmin, const float* tmax,
+                    int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded) {
+    if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_intersect: call bpt_build_accel first");
+    if (n < 0 || !origins || !directions || !tmin || !tmax) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_intersect: bad arguments");
+    if (n == 0) return BPT_OK;
+    cudaStream_t st = ctx->stream;
+    std::vector<float> h_cov(ctx->host_materials.size());
+    for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
+
+    float *d_o = nullptr, *d_d = nullptr, *d_tmin = nullptr, *d_tmax = nullptr, *d_cov = nullptr, *d_t = nullptr, *d_uv = nullptr;
+    int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
+    auto cleanup = [&]() { for (void* p : { (void*)d_o, (void*)d_d, (void*)d_tmin, (void*)d_tmax, (void*)d_cov, (void*)d_t, (void*)d_uv, (void*)d_prim, (void*)d_occ }) if (p) cudaFree(p); };
+#define Q_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return ctx->cuda_fail(_e, #expr); } } while (0)
+    Q_CHECK(cudaMalloc((void**)&d_o, 3 * n * sizeof(float))); Q_CHECK(cudaMalloc((void**)&d_d, 3 * n * sizeof(float)));
+    Q_CHECK(cudaMalloc((void**)&d_tmin, n * sizeof(float))); Q_CHECK(cudaMalloc((void**)&d_tmax, n * sizeof(float)));
+    Q_CHECK(cudaMalloc((void**)&d_cov, h_cov.size() * sizeof(float)));
+    Q_CHECK(cudaMemcpyAsync(d_o, origins, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    Q_CHECK(cudaMemcpyAsync(d_d, directions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
+    Q_CHECK(cudaMemcpyAsync(d_tmin, tmin, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    Q_CHECK(cudaMemcpyAsync(d_tmax, tmax, n * sizeof(float), cudaMemcpyHostToDevice, st));
+    Q_CHECK(cudaMemcpyAsync(d_cov, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (out_primitive) Q_CHECK(cudaMalloc((void**)&d_prim, n * sizeof(int32_t)));
+    if (out_t) Q_CHECK(cudaMalloc((void**)&d_t, n * sizeof(float)));
+    if (out_uv) Q_CHECK(cudaMalloc((void**)&d_uv, 2 * n * sizeof(float)));
+    if (out_occluded) Q_CHECK(cudaMalloc((void**)&d_occ, n));
+    AccelView view = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr };
+    int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 16);
+    intersect_kernel<<<grid, TRACE_BLOCK, 0, st>>>(view, n, d_o, d_d, d_tmin, d_tmax, d_cov, d_prim, d_t, d_uv, d_occ);
+    ctx->counters.kernel_launches++;
+    Q_CHECK(cudaGetLastError());
+    if (out_primitive) Q_CHECK(cudaMemcpyAsync(out_primitive, d_prim, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (out_t) Q_CHECK(cudaMemcpyAsync(out_t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_uv) Q_CHECK(cudaMemcpyAsync(out_uv, d_uv, 2 * n * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_occluded) Q_CHECK(cudaMemcpyAsync(out_occluded, d_occ, n, cudaMemcpyDeviceToHost, st));
+    Q_CHECK(cudaStreamSynchronize(st));
+#undef Q_CHECK
+    cleanup();
+    return BPT_OK;
+}
+
+} // namespace bpt

@@ -76,6 +76,7 @@ struct Accel {
     DeviceBuffer<TraceTriangle> triangles;      // traversal order (Morton sorted)
     DeviceBuffer<float4> world_vertices;        // 3 per primitive, instance-major order: position.xyz, w unused
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
+    DeviceBuffer<float> normal_matrices;        // 9 floats per instance record: inverse transpose of the upper 3x3
     int64_t triangle_count = 0;
     int64_t node_count = 0;
     float build_ms = 0.0f;

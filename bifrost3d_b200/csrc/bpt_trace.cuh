@@ -1,0 +1,240 @@
+// Ray traversal of the two-wide BVH: closest hit and any hit. Replaces OptiX' proprietary Trbvh/RTX
+// traversal that the reference configures at Renderer.cpp:116-135,161-182,470-477 and queries with rtTrace
+// (SimpleRGPs.cu:114-125).
+//
+// * Nodes are 64 bytes and hold both children's boxes: one node visit = four 128-bit loads.
+// * Triangles are 48 bytes (three float4 world-space vertices) in Morton order: three 128-bit loads.
+// * The ray/triangle test is the watertight test of Woop, Benthin and Wald (JCGT 2013): shear to ray space,
+//   2D edge functions with an fp64 fallback when an edge function is exactly zero. It is evaluated with
+//   explicitly rounded operations (no FMA contraction) so the CPU oracle reproduces t and the barycentrics
+//   bit for bit; shared edges evaluate to exact negations of each other, which is what makes it watertight.
+// * Closest hit is the minimum over (t, global primitive index): ties in t resolve to the lower index so that
+//   the result does not depend on traversal order.
+// * The traversal stack lives in shared memory (STACK_SMEM entries per thread, column layout so that a warp's
+//   accesses hit 32 different banks); deeper paths spill to a per-thread local array.
+#pragma once
+#include "bpt_context.h"
+#include "bpt_math.cuh"
+
+namespace bpt {
+
+struct Ray {
+    float3 origin;
+    float tmin;
+    float3 direction;
+    float tmax;
+};
+
+struct Hit {
+    float t;
+    int primitive; // global primitive index, -1 = miss
+    float u, v;    // barycentric weights of vertex 1 and vertex 2
+};
+
+// Per-ray constants of the watertight test.
+struct RayShear {
+    int kx, ky, kz;
+    float Sx, Sy, Sz;
+};
+
+BPT_D float comp(float3 v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+BPT_D RayShear make_ray_shear(float3 d) {
+    RayShear s;
+    float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    s.kz = (ax > ay) ? ((ax > az) ? 0 : 2) : ((ay > az) ? 1 : 2);
+    s.kx = s.kz + 1; if (s.kx == 3) s.kx = 0;
+    s.ky = s.kx + 1; if (s.ky == 3) s.ky = 0;
+    float dz = comp(d, s.kz);
+    if (dz < 0.0f) { int tmp = s.kx; s.kx = s.ky; s.ky = tmp; }
+    s.Sx = __fdiv_rn(comp(d, s.kx), dz);
+    s.Sy = __fdiv_rn(comp(d, s.ky), dz);
+    s.Sz = __fdiv_rn(1.0f, dz);
+    return s;
+}
+
+// Returns true and fills t, u, v when the ray's supporting line hits the triangle (no interval test).
+BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, float3 p1, float3 p2, float& t, float& u, float& v) {
+    const float3 A = f3(__fsub_rn(p0.x, origin.x), __fsub_rn(p0.y, origin.y), __fsub_rn(p0.z, origin.z));
+    const float3 B = f3(__fsub_rn(p1.x, origin.x), __fsub_rn(p1.y, origin.y), __fsub_rn(p1.z, origin.z));
+    const float3 C = f3(__fsub_rn(p2.x, origin.x), __fsub_rn(p2.y, origin.y), __fsub_rn(p2.z, origin.z));
+
+    const float Akz = comp(A, s.kz), Bkz = comp(B, s.kz), Ckz = comp(C, s.kz);
+    const float Ax = __fsub_rn(comp(A, s.kx), __fmul_rn(s.Sx, Akz));
+    const float Ay = __fsub_rn(comp(A, s.ky), __fmul_rn(s.Sy, Akz));
+    const float Bx = __fsub_rn(comp(B, s.kx), __fmul_rn(s.Sx, Bkz));
+    const float By = __fsub_rn(comp(B, s.ky), __fmul_rn(s.Sy, Bkz));
+    const float Cx = __fsub_rn(comp(C, s.kx), __fmul_rn(s.Sx, Ckz));
+    const float Cy = __fsub_rn(comp(C, s.ky), __fmul_rn(s.Sy, Ckz));
+
+    float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+    float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+    float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+
+    if (U == 0.0f || V == 0.0f || W == 0.0f) {
+        double CxBy = __dmul_rn((double)Cx, (double)By), CyBx = __dmul_rn((double)Cy, (double)Bx);
+        U = (float)__dsub_rn(CxBy, CyBx);
+        double AxCy = __dmul_rn((double)Ax, (double)Cy), AyCx = __dmul_rn((double)Ay, (double)Cx);
+        V = (float)__dsub_rn(AxCy, AyCx);
+        double BxAy = __dmul_rn((double)Bx, (double)Ay), ByAx = __dmul_rn((double)By, (double)Ax);
+        W = (float)__dsub_rn(BxAy, ByAx);
+    }
+
+    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
+        return false;
+
+    const float det = __fadd_rn(__fadd_rn(U, V), W);
+    if (det == 0.0f)
+        return false;
+
+    const float Az = __fmul_rn(s.Sz, Akz);
+    const float Bz = __fmul_rn(s.Sz, Bkz);
+    const float Cz = __fmul_rn(s.Sz, Ckz);
+    const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+
+    const float rcp_det = __fdiv_rn(1.0f, det);
+    t = __fmul_rn(T, rcp_det);
+    u = __fmul_rn(V, rcp_det); // weight of p1
+    v = __fmul_rn(W, rcp_det); // weight of p2
+    return true;
+}
+
+// ---- traversal ---------------------------------------------------------------------------------
+
+constexpr int TRACE_BLOCK = 128;
+constexpr int STACK_SMEM = 24;
+constexpr int STACK_LOCAL = 72;
+
+struct TraversalStack {
+    int* smem;                // [STACK_SMEM][TRACE_BLOCK], this thread's column
+    int local[STACK_LOCAL];
+    int sp;
+    BPT_D void push(int v) {
+        if (sp < STACK_SMEM) smem[sp * TRACE_BLOCK] = v;
+        else if (sp - STACK_SMEM < STACK_LOCAL) local[sp - STACK_SMEM] = v;
+        ++sp;
+    }
+    BPT_D int pop() {
+        --sp;
+        return sp < STACK_SMEM ? smem[sp * TRACE_BLOCK] : local[min(sp - STACK_SMEM, STACK_LOCAL - 1)];
+    }
+};
+
+struct AccelView {
+    const BvhNode* __restrict__ nodes;
+    const TraceTriangle* __restrict__ triangles;
+};
+
+BPT_D float4 ldg4(const float4* p) { return __ldg(p); }
+
+// Slab test against one child box. Conservative: the far distance is padded by a few ulp (Ize, "Robust BVH ray
+// traversal", JCGT 2013) and the near one shrunk, so a triangle the watertight test would accept is never culled.
+BPT_D bool slab(float3 lo, float3 hi, float3 o, float3 inv_d, float tmin, float tmax, float& tnear) {
+    float t0x = (lo.x - o.x) * inv_d.x, t1x = (hi.x - o.x) * inv_d.x;
+    float t0y = (lo.y - o.y) * inv_d.y, t1y = (hi.y - o.y) * inv_d.y;
+    float t0z = (lo.z - o.z) * inv_d.z, t1z = (hi.z - o.z) * inv_d.z;
+    float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+    float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+    tn = fmaxf(tmin, tn * 0.99999905f);
+    tf = fminf(tmax, tf * 1.00000095f);
+    tnear = tn;
+    return tn <= tf;
+}
+
+template <bool ANY_HIT>
+BPT_D void intersect_leaf(const AccelView& a, int first, int count, const RayShear& shear, const Ray& ray, Hit& hit, float& tmax,
+                          int skip_primitive, float& transmission, const float* __restrict__ coverage_by_material) {
+    for (int i = 0; i < count; ++i) {
+        const float4* tri = reinterpret_cast<const float4*>(a.triangles + first + i);
+        float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
+        int primitive = __float_as_int(v0.w);
+        if (primitive == skip_primitive)
+            continue;
+        float t, u, v;
+        if (!watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v))
+            continue;
+        if (ANY_HIT) {
+            if (t > ray.tmin && t < ray.tmax) {
+                // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
+                float coverage = coverage_by_material[__float_as_int(v1.w)];
+                transmission *= 1.0f - coverage;
+                if (transmission < 0.0000001f) { transmission = 0.0f; hit.primitive = primitive; hit.t = t; tmax = -1.0f; return; }
+            }
+        } else {
+            if (t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
+                // NB hit.t starts at ray.tmax and hit.primitive at INT_MAX, so t must be < tmax for a first hit.
+                hit.t = t; hit.primitive = primitive; hit.u = u; hit.v = v;
+                tmax = t;
+            }
+        }
+    }
+}
+
+// Closest hit (ANY_HIT = false) or accumulated transmission along [tmin, tmax] (ANY_HIT = true).
+// `stack_smem` points at this thread's column of a [STACK_SMEM][TRACE_BLOCK] shared array.
+template <bool ANY_HIT>
+BPT_D Hit trace(const AccelView& a, const Ray& ray, int skip_primitive, int* stack_smem, float& transmission,
+                const float* __restrict__ coverage_by_material) {
+    Hit hit;
+    hit.t = ray.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
+    transmission = 1.0f;
+    float tmax = ray.tmax; // shrinks as closer hits are found; ties (t == tmax) must still be visited
+
+    const RayShear shear = make_ray_shear(ray.direction);
+    const float3 inv_d = f3(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
+
+    TraversalStack stack;
+    stack.smem = stack_smem;
+    stack.sp = 0;
+
+    int node_index = 0;
+    while (true) {
+        const float4* n = reinterpret_cast<const float4*>(a.nodes + node_index);
+        float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2);
+        int4 links = __ldg(reinterpret_cast<const int4*>(n + 3));
+
+        float tn_l, tn_r;
+        bool hit_l = slab(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), ray.origin, inv_d, ray.tmin, tmax, tn_l);
+        bool hit_r = slab(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), ray.origin, inv_d, ray.tmin, tmax, tn_r);
+        hit_l = hit_l && links.z >= 0; // count -1 marks an absent child
+        hit_r = hit_r && links.w >= 0;
+
+        // Leaves are intersected on the spot; inner children are descended into, nearest first.
+        if (hit_l && links.z > 0) {
+            intersect_leaf<ANY_HIT>(a, ~links.x, links.z, shear, ray, hit, tmax, skip_primitive, transmission, coverage_by_material);
+            hit_l = false;
+        }
+        if (hit_r && links.w > 0) {
+            if (!ANY_HIT && tn_r > tmax) { /* culled by the hit just found in the left leaf */ }
+            else intersect_leaf<ANY_HIT>(a, ~links.y, links.w, shear, ray, hit, tmax, skip_primitive, transmission, coverage_by_material);
+            hit_r = false;
+        }
+        if (ANY_HIT && tmax < 0.0f)
+            break;
+        if (!ANY_HIT) {
+            // re-test inner children against the possibly shortened interval
+            hit_l = hit_l && tn_l <= tmax;
+            hit_r = hit_r && tn_r <= tmax;
+        }
+
+        if (hit_l && hit_r) {
+            bool left_first = tn_l <= tn_r;
+            node_index = left_first ? links.x : links.y;
+            stack.push(left_first ? links.y : links.x);
+        } else if (hit_l) {
+            node_index = links.x;
+        } else if (hit_r) {
+            node_index = links.y;
+        } else {
+            if (stack.sp == 0)
+                break;
+            node_index = stack.pop();
+        }
+    }
+
+    if (!ANY_HIT && hit.primitive == 0x7fffffff)
+        hit.primitive = -1;
+    return hit;
+}
+
+} // namespace bpt

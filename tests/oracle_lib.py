@@ -121,3 +121,74 @@ def load():
             raise RuntimeError(f"{LIB_PATH} missing: run `make -C oracle` where /root/reference is available")
         _lib = Ref(C.CDLL(str(LIB_PATH)))
     return _lib
+
+
+class OracleScene:
+    """CPU oracle scene (oracle/pt_oracle.cpp): flattening, brute force / BVH intersection and the integrator restatement."""
+
+    def __init__(self, scene):
+        self.ref = load()
+        lib = self.ref.lib
+        vp, i64, i32, u32 = C.c_void_p, C.c_int64, C.c_int, C.c_uint32
+        lib.pto_scene_create.restype = vp
+        lib.pto_scene_destroy.argtypes = [vp]; lib.pto_scene_destroy.restype = None
+        lib.pto_scene_add_mesh.argtypes = [vp, i32, vp, i32, vp, vp, vp, i32]; lib.pto_scene_add_mesh.restype = None
+        for name in ("pto_scene_set_instances", "pto_scene_set_materials", "pto_scene_set_lights"):
+            getattr(lib, name).argtypes = [vp, vp, i32]; getattr(lib, name).restype = None
+        lib.pto_scene_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]; lib.pto_scene_set_environment.restype = None
+        lib.pto_scene_build.argtypes = [vp]; lib.pto_scene_build.restype = None
+        lib.pto_triangle_count.argtypes = [vp]; lib.pto_triangle_count.restype = i64
+        lib.pto_world_vertices.argtypes = [vp, vp]; lib.pto_world_vertices.restype = None
+        lib.pto_intersect.argtypes = [vp, i64, vp, vp, vp, vp, i32, vp, vp, vp, vp]; lib.pto_intersect.restype = None
+        lib.pto_render.argtypes = [vp, vp, vp, i32, i32, u32, u32, i32, i32, vp, vp, i32]; lib.pto_render.restype = None
+        self.lib = lib
+        self.h = C.c_void_p(lib.pto_scene_create())
+        for mesh_id, m in scene["meshes"].items():
+            idx = np.ascontiguousarray(m["indices"], np.uint32); pos = _f32(m["positions"])
+            nrm = None if m.get("normals") is None else _f32(m["normals"])
+            tints = None if m.get("tints") is None else np.ascontiguousarray(m["tints"], np.uint8)
+            lib.pto_scene_add_mesh(self.h, int(mesh_id), _p(idx), idx.shape[0], _p(pos), _p(nrm), _p(tints), pos.shape[0])
+        mats = np.ascontiguousarray(scene["materials"]); inst = np.ascontiguousarray(scene["instances"]); lights = np.ascontiguousarray(scene["lights"])
+        lib.pto_scene_set_materials(self.h, _p(mats), mats.shape[0])
+        lib.pto_scene_set_instances(self.h, _p(inst), inst.shape[0])
+        lib.pto_scene_set_lights(self.h, _p(lights) if lights.size else None, lights.shape[0])
+        env = scene.get("environment", {"tint": (0, 0, 0)})
+        tint = _f32(env["tint"])
+        if env.get("texels") is None:
+            lib.pto_scene_set_environment(self.h, _p(tint), None, 0, 0, None, 0, 0, None, 0)
+        else:
+            tex = _f32(env["texels"]); pdf = _f32(env["per_pixel_pdf"]); s = np.ascontiguousarray(env["samples"])
+            lib.pto_scene_set_environment(self.h, _p(tint), _p(tex), tex.shape[1], tex.shape[0], _p(pdf), pdf.shape[1], pdf.shape[0], _p(s), s.shape[0])
+        lib.pto_scene_build(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.pto_scene_destroy(self.h); self.h = None
+
+    def triangle_count(self):
+        return self.lib.pto_triangle_count(self.h)
+
+    def world_vertices(self):
+        out = np.empty((self.triangle_count(), 3, 3), np.float32)
+        self.lib.pto_world_vertices(self.h, _p(out))
+        return out
+
+    def intersect(self, origins, directions, tmin=None, tmax=None, brute=False):
+        o, d = _f32(origins).reshape(-1, 3), _f32(directions).reshape(-1, 3)
+        n = o.shape[0]
+        tmin = np.zeros(n, np.float32) if tmin is None else _f32(np.broadcast_to(tmin, (n,)))
+        tmax = np.full(n, 1e30, np.float32) if tmax is None else _f32(np.broadcast_to(tmax, (n,)))
+        prim = np.empty(n, np.int32); t = np.empty(n, np.float32); uv = np.empty((n, 2), np.float32); occ = np.empty(n, np.uint8)
+        self.lib.pto_intersect(self.h, n, _p(o), _p(d), _p(tmin), _p(tmax), int(brute), _p(prim), _p(t), _p(uv), _p(occ))
+        return prim, t, uv, occ
+
+    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, rows=None, threads=0, accum=None):
+        from bifrost3d_b200 import capi
+        cam = capi.make_camera(*camera)
+        s = capi.Settings(max_bounces, nee_samples, pdf_scale, 0)
+        if accum is None:
+            accum = np.zeros((height, width, 4), np.float64)
+        counters = np.zeros(2, np.uint64)
+        r0, r1 = (0, height) if rows is None else rows
+        self.lib.pto_render(self.h, C.byref(cam), C.byref(s), width, height, first_sample, sample_count, r0, r1, _p(accum), _p(counters), threads)
+        return accum, counters
