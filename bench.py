@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""Benchmark of the path-tracing hot path (contract: see the task's bench.py section).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cornell|materials|...]
+
+A "step" is ONE progressive sample of every pixel of the frame (one Renderer::render call in the reference,
+Renderer.cpp:1250-1265). Metric: Msamples/s = width * height * steps / seconds (whole job, all GPUs); Mrays/s
+(closest-hit + shadow rays from device counters) is reported next to it.
+  value   : device-timed, scene + BVH resident in HBM, CUDA events on the library's stream.
+  e2e     : through the C ABI with host buffers: every step uploads the camera + settings and reads the resolved
+            half4 frame back to pinned-size host memory (what DX11OptiXAdaptor displays each frame).
+  roofline: closest-hit traversal kernel, algorithmic bytes (48 + 64*ceil(log2(N/4)) + 192 B/ray) over its
+            CUDA-event duration, against the measured HBM copy bandwidth in MEASURED_PEAKS.json.
+  cpu_baseline / --impl reference: the CPU oracle (reference shading headers + restated integrator, OpenMP) on host cores.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def bytes_per_ray(triangles):
+    return 48 + 64 * max(1, math.ceil(math.log2(max(triangles, 8) / 4))) + 192
+
+
+def measured_peak():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback"
+
+
+def build_scene(name):
+    from bifrost3d_b200 import scenes
+    if name == "cornell":
+        return scenes.cornell_box(), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
+    if name == "cornell_small":
+        return scenes.cornell_box(sphere_quads=(24, 12), width=256, height=256), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
+    if hasattr(scenes, name):
+        return getattr(scenes, name)()
+    raise SystemExit(f"unknown workload {name}")
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.stop_flag = device, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=2.0, threads=0):
+    """Times the CPU oracle on a bounded sample of the workload: a band of pixel rows at one sample per pixel per step."""
+    from tests import oracle_lib
+    sc = oracle_lib.OracleScene(scene)
+    w, h = scene["width"], scene["height"]
+    cores = sc.ref.max_threads() if threads <= 0 else threads
+    # calibrate: a few rows around the image centre
+    probe_rows = max(1, min(h, 4))
+    r0 = h // 2 - probe_rows // 2
+    t0 = time.perf_counter()
+    sc.render(scene["camera"], w, h, 1, 1, rows=(r0, r0 + probe_rows), threads=threads, **settings)
+    per_row = (time.perf_counter() - t0) / probe_rows
+    rows = int(max(1, min(h, target_seconds_per_step / max(per_row, 1e-9))))
+    r0 = (h - rows) // 2
+    counters_total = np.zeros(2, np.uint64)
+    times = []
+    for step in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, counters = sc.render(scene["camera"], w, h, step, 1, rows=(r0, r0 + rows), threads=threads, **settings)
+        dt = time.perf_counter() - t0
+        if step >= warmup:
+            times.append(dt); counters_total += counters
+    sc.close()
+    seconds = float(sum(times))
+    samples = rows * w * steps
+    return {"msamples_per_s": samples / seconds / 1e6, "mrays_per_s": float(counters_total.sum()) / seconds / 1e6, "cores": int(cores),
+            "sample": f"rows {r0}..{r0 + rows} of {h} ({rows}x{w} pixels), 1 sample per pixel per step, {steps} steps",
+            "ms_per_step": seconds / steps * 1e3, "rows": rows}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    scene, settings = build_scene(args.workload)
+    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
+    r = cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=max(2.0, 60.0 / (steps + warmup)))
+    line = {"impl": "reference", "metric": "Msamples/s", "value": r["msamples_per_s"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "mrays_per_s": r["mrays_per_s"],
+            "config": workload_config(args, scene, settings),
+            "cpu_baseline": {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["msamples_per_s"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU oracle: the reference's own host-compiled shading/light/RNG headers driven by a restatement of its OptiX integrator over a CPU BVH (the OptiX programs themselves cannot run here); OpenMP, all host cores"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, scene, settings):
+    from bifrost3d_b200 import scenes
+    return {"workload": f"{scene['name']}: {scene['width']}x{scene['height']}, {scenes.triangle_count(scene)} triangles, {len(scene['lights'])} light(s), "
+                        f"max_bounce_count {settings['max_bounces']}, next_event_sample_count {settings['nee_samples']}, 1 sample per pixel per step",
+            "baseline_config": "configs[1] (SmallPT-style Cornell box)" if args.workload == "cornell" else args.workload,
+            "l2_policy": "per-step working set (path state + frame buffers) exceeds L2; no explicit flush",
+            "parallelism": f"sample-index sharding x{args.gpus}, replicated BVH"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cornell")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import bifrost3d_b200 as b
+    from bifrost3d_b200 import scenes, capi
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA extension is the product and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    scene, settings = build_scene(args.workload)
+    W, H = scene["width"], scene["height"]
+    ctx = b.Bpt(local_rank)
+    scenes.upload(ctx, scene)
+    info = ctx.accel_info()
+    ctx.set_profiling(True)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    cam = capi.make_camera(*scene["camera"])
+    K, Wm = args.steps, args.warmup
+
+    def barrier():
+        ctx.synchronize(); torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # Each rank renders its own contiguous range of sample indices (weak scaling: K samples per GPU).
+    first = rank * (K + Wm)
+    # ---- device-timed region -----------------------------------------------------------------------
+    ctx.render(cam, W, H, first, Wm, reset=True, **settings)  # warm-up
+    barrier()
+    ctx.counters(reset=True)
+    sampler = ClockSampler(local_rank); sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    ctx.render(cam, W, H, first + Wm, K, reset=True, **settings)
+    if distributed:
+        # combine the per-GPU radiance sums: one NCCL reduce over NVLink of the double4 accumulation buffer
+        ctx.synchronize()
+        acc = accumulation_tensor(ctx, W, H, local_rank)
+        dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.current_stream().synchronize()
+    e1.record(stream)
+    barrier()
+    device_ms = e0.elapsed_time(e1)
+    clocks = sampler.summary()
+    counters = ctx.counters()
+    t = torch.tensor([device_ms], dtype=torch.float64, device="cuda")
+    rays = torch.tensor([float(counters["extend_rays"]), float(counters["shadow_rays"])], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    device_ms = float(t.item())
+    total_samples = W * H * K * world
+    value = total_samples / (device_ms * 1e-3) / 1e6
+    mrays = float(rays.sum().item()) / (device_ms * 1e-3) / 1e6
+
+    # ---- roofline for the dominant kernel (closest-hit traversal) on this rank ---------------------
+    peak, peak_kind = measured_peak()
+    bpr = bytes_per_ray(info["triangles"])
+    extend_s = counters["extend_ms"] * 1e-3
+    shadow_s = counters["shadow_ms"] * 1e-3
+    launches_per_step = counters["kernel_launches"] / max(K, 1)
+    extend_launches = K * (settings["max_bounces"] + 2)
+    achieved = counters["extend_rays"] * bpr / max(extend_s, 1e-12) / 1e9
+    roofline = {"bound": "hbm", "kernel": "extend_kernel (closest-hit BVH traversal)", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_ray": bpr,
+                "rays_per_launch": counters["extend_rays"] / extend_launches, "avg_launch_ms": counters["extend_ms"] / extend_launches,
+                "share_of_step": {"extend": counters["extend_ms"] / device_ms, "shade": counters["shade_ms"] / device_ms, "shadow": counters["shadow_ms"] / device_ms},
+                "shadow_kernel_achieved": counters["shadow_rays"] * bpr / max(shadow_s, 1e-12) / 1e9,
+                "grays_per_s_extend": counters["extend_rays"] / max(extend_s, 1e-12) / 1e9}
+
+    # ---- end-to-end through the C ABI with host buffers ---------------------------------------------
+    barrier()
+    frame = np.empty((H, W, 4), np.uint16)
+    for k in range(2):
+        ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.lib.bpt_resolve_half4(ctx.h, frame.ctypes.data, 0)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = min(K, 32)
+    for k in range(e2e_steps):
+        cam_k = capi.make_camera(*scene["camera"])  # host-side camera state is rebuilt and uploaded every step
+        ctx.render(cam_k, W, H, first + k, 1, reset=(k == 0), **settings)
+        ctx.lib.bpt_resolve_half4(ctx.h, frame.ctypes.data, 0)  # device -> host read of the displayed frame
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = W * H * e2e_steps * world / float(te.item()) / 1e6
+    assert np.isfinite(frame.view(np.float16).astype(np.float32)).all()
+
+    if rank == 0:
+        line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": device_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "mrays_per_s": mrays, "extend_rays_per_step": counters["extend_rays"] / K, "shadow_rays_per_step": counters["shadow_rays"] / K,
+                "config": workload_config(args, scene, settings),
+                "bvh": {"triangles": info["triangles"], "nodes": info["nodes"], "build_ms": info["build_ms"], "mtris_per_s": info["triangles"] / max(info["build_ms"], 1e-6) / 1e3},
+                "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.Settings)),
+                        "d2h_bytes_per_step": int(frame.nbytes), "steps": e2e_steps},
+                "gpu_launches": int(counters["kernel_launches"]), "gpu_launches_per_step": launches_per_step,
+                "roofline": roofline, "clocks": clocks}
+        if not args.no_cpu_baseline and world == 1 and cpu_baseline_available():
+            r = cpu_oracle_run(scene, settings, steps=3, warmup=1, target_seconds_per_step=4.0)
+            line["cpu_baseline"] = {"value": r["msamples_per_s"], "unit": "Msamples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"],
+                                    "mrays_per_s": r["mrays_per_s"]}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
+def cpu_baseline_available():
+    from tests import oracle_lib
+    return oracle_lib.available()
+
+
+class _CudaArray:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+def accumulation_tensor(ctx, width, height, device):
+    """torch view (no copy) of the context-owned double4 accumulation buffer, for the NCCL reduce."""
+    import torch
+    holder = _CudaArray(ctx.accumulation_device_ptr(), (height, width, 4), "<f8")
+    return torch.as_tensor(holder, device=torch.device("cuda", device))
+
+
+if __name__ == "__main__":
+    sys.exit(main())

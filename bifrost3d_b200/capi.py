@@ -64,7 +64,7 @@ LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_upload_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render",
-           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_get_counters",
+           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
 
@@ -97,6 +97,7 @@ def load_library():
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
     lib.bpt_resolve_float4.argtypes = [vp, vp]
     lib.bpt_synchronize.argtypes = [vp]
+    lib.bpt_set_profiling.argtypes = [vp, i32]
     lib.bpt_get_counters.argtypes = [vp, C.POINTER(Counters), i32]
     lib.bpt_bsdf_eval_sample_pdf.argtypes = [vp, i32, i64] + [vp] * 11 + [i32]
     lib.bpt_default_shading_regularized.argtypes = [vp, i64] + [vp] * 11
@@ -161,6 +162,9 @@ class Bpt:
 
     def synchronize(self):
         self._check(self.lib.bpt_synchronize(self.h))
+
+    def set_profiling(self, enabled):
+        self._check(self.lib.bpt_set_profiling(self.h, int(enabled)))
 
     def set_tables(self, ggx_with_fresnel, ggx, alpha):
         a, b, c = _f32(ggx_with_fresnel), _f32(ggx), _f32(alpha)

@@ -190,8 +190,12 @@ __global__ void rng_batch_kernel(int64_t n, const uint32_t* __restrict__ accumul
 }
 
 // RNG::ReverseHalton(index).sample4f(), RNG.h:196-231: radical inverse with reversed digits in the first four prime bases.
+// NB the reference builds the float4 as make_float4(sample2f(), sample2f()) with sample2f() = make_float2(sample1f(),
+// sample1f()), and every sample1f() advances the prime index. C++ leaves the evaluation order of function arguments
+// unspecified; MSVC (the reference's compiler) and GCC (the oracle's) both evaluate right to left on x86-64, so the
+// components come out as (base 7, base 5, base 3, base 2). The golden fixture tests/golden (halton_offsets) pins this.
 void reverse_halton4(int index, float out[4]) {
-    static const int primes[4] = { 2, 3, 5, 7 };
+    static const int primes[4] = { 7, 5, 3, 2 };
     for (int d = 0; d < 4; ++d) {
         const int prime = primes[d];
         double h = 0.0, f = 1.0 / (double)prime, fct = f;
@@ -333,12 +337,18 @@ void bpt_destroy(bpt_ctx* c) {
     ctx->accumulation.release();
     if (ctx->device_counters) cudaFree(ctx->device_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->stage_events) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 const char* bpt_last_error(const bpt_ctx* c) { return c ? as_context(c)->last_error.c_str() : "null context"; }
 void* bpt_stream(bpt_ctx* c) { return c ? (void*)as_context(c)->stream : nullptr; }
+
+int bpt_set_profiling(bpt_ctx* c, int enabled) {
+    as_context(c)->profiling = enabled != 0;
+    return BPT_OK;
+}
 
 int bpt_synchronize(bpt_ctx* c) {
     Context* ctx = as_context(c);

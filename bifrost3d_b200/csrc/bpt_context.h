@@ -120,6 +120,13 @@ struct Context {
     uint64_t* device_counters = nullptr; // [extend, shadow]
 
     cudaEvent_t ev[8] = {};
+    // Optional per-stage timing (bpt_set_profiling): events recorded around the stage kernels of one sample.
+    bool profiling = false;
+    std::vector<cudaEvent_t> stage_events;
+    size_t stage_event(size_t index) {
+        while (stage_events.size() <= index) { cudaEvent_t e; cudaEventCreate(&e); stage_events.push_back(e); }
+        return index;
+    }
 
     int fail(int status, const std::string& msg) { last_error = msg; return status; }
     int cuda_fail(cudaError_t e, const char* what) {

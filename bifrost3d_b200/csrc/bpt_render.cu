@@ -1,7 +1,676 @@
+// Wavefront path integrator. Replaces the OptiX megakernel launched by Renderer::render
+// (Renderer.cpp:1250-1265 -> context->launch(PathTracing, w, h), IBackend.h:37-39) and its programs:
+//   path_tracing_RPG / accumulate / initialize_monte_carlo_payload   Shading/SimpleRGPs.cu:44-140
+//   miss                                                              Shading/SimpleRGPs.cu:349-362
+//   path_tracing_closest_hit<DefaultMaterialCreator>, NEE + RIS       Shading/MonteCarlo.cu:61-244
+//   shadow_any_hit, light_closest_hit                                 Shading/MonteCarlo.cu:278-302
+//   interpolate_attributes                                            Shading/TriangleAttributes.cu:35-84
+//   analytic light intersect                                          Shading/LightSources/LightSources.cu:31-70
+//
+// One progressive sample of every pixel = generate -> { extend -> shade -> shadow } x bounces -> accumulate.
+// Every stage is a persistent-thread kernel over a queue of pixel indices whose length lives in device memory, so
+// the host never synchronises inside a sample. Queues are compacted with warp ballot + one atomic per warp.
+// Path state is SoA, indexed by pixel, in 16-byte records so every access is a 128-bit transaction.
 #include "bpt_context.h"
+#include "bpt_lights.cuh"
+#include "bpt_rng.cuh"
+#include "bpt_trace.cuh"
+
+#include <cuda_fp16.h>
+#include <algorithm>
+
 namespace bpt {
-int render(Context* ctx, const bpt_camera*, const bpt_settings*, int, int, uint32_t, uint32_t, int) { return ctx->fail(BPT_ERROR_NOT_READY, "render: not implemented yet"); }
-int resolve_half4(Context* ctx, uint16_t*, int) { return ctx->fail(BPT_ERROR_NOT_READY, "resolve: not implemented yet"); }
-int resolve_float4(Context* ctx, float*) { return ctx->fail(BPT_ERROR_NOT_READY, "resolve: not implemented yet"); }
-void release_wavefront(Context*) {}
+
+namespace {
+
+constexpr int SHADE_BLOCK = 128;
+constexpr int LIGHT_HIT_FLAG = 0x40000000; // hit.primitive = LIGHT_HIT_FLAG | light index
+constexpr float RT_DEFAULT_MAX = 1e27f;    // tmax of optix::Ray when none is given (SimpleRGPs.cu:114)
+
+// Queue counters in device memory.
+struct QueueCounters {
+    unsigned int active;       // entries in the current extend/shade queue
+    unsigned int next_active;  // entries appended for the next iteration
+    unsigned int shadow;       // entries in the shadow queue
+    unsigned int pad;
+};
+
+struct Wavefront {
+    int64_t pixel_capacity = 0;
+    // ray_o: origin.xyz, tmin | ray_d: direction.xyz, bsdf_pdf | thr: throughput.xyz, bounces (bits) |
+    // rad: radiance.xyz, previous primitive (bits) | hit: t, primitive (bits), u, v
+    DeviceBuffer<float4> ray_o, ray_d, thr, rad, hit;
+    // shadow rays: origin.xyz + tmax, direction.xyz + pixel (bits), radiance.xyz
+    DeviceBuffer<float4> sh_o, sh_d, sh_rad;
+    DeviceBuffer<unsigned int> queue_a, queue_b;
+    DeviceBuffer<QueueCounters> counters;
+    DeviceBuffer<float> coverage; // per material
+};
+
+struct WavefrontView {
+    float4 *ray_o, *ray_d, *thr, *rad, *hit;
+    float4 *sh_o, *sh_d, *sh_rad;
+    unsigned int *queue_in, *queue_out;
+    QueueCounters* counters;
+    unsigned long long* ray_counters; // [0] extend, [1] shadow
+};
+
+struct SceneView {
+    AccelView accel;
+    const float4* __restrict__ world_vertices;
+    const ShadeTriangle* __restrict__ shade;
+    const float* __restrict__ normal_matrices;
+    const Material* __restrict__ materials;
+    const float* __restrict__ coverage;
+    const Light* __restrict__ lights;
+    int light_count;          // lights sampled by next event estimation (analytic + environment when importance sampled)
+    int analytic_light_count; // lights that rays can hit
+    EnvironmentView env;
+    const float* __restrict__ tables;
+    const float4* __restrict__ nee_offsets;
+};
+
+struct FrameParams {
+    bpt_camera camera;
+    int width, height;
+    unsigned int accumulation_count;
+    unsigned int max_bounce_count;
+    int next_event_sample_count;
+    float path_regularization_pdf_scale;
+};
+
+// Appends `value` to a queue for every lane with `pred` set: one atomicAdd per warp.
+__device__ __forceinline__ void warp_append(bool pred, unsigned int* queue, unsigned int* counter, unsigned int value) {
+    unsigned int mask = __ballot_sync(0xffffffffu, pred);
+    if (mask == 0) return;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = value;
 }
+
+// ---- generate ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float4 mul4x4(const float* m, float4 v) {
+    return make_float4(m[0] * v.x + m[1] * v.y + m[2] * v.z + m[3] * v.w, m[4] * v.x + m[5] * v.y + m[6] * v.z + m[7] * v.w,
+                       m[8] * v.x + m[9] * v.y + m[10] * v.z + m[11] * v.w, m[12] * v.x + m[13] * v.y + m[14] * v.z + m[15] * v.w);
+}
+
+__global__ void generate_kernel(WavefrontView w, FrameParams f) {
+    int64_t pixel_count = (int64_t)f.width * f.height;
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
+        int x = int(p % f.width), y = int(p / f.width);
+        unsigned int pixel_hash = pcg2d((unsigned int)x, (unsigned int)y).x;
+        float2 jitter = f2(0.5f, 0.5f);
+        if (f.accumulation_count != 0) {
+            float4 r = path_rng_sample4f(f.accumulation_count, pixel_hash, 0u, DIM_CAMERA);
+            jitter = f2(r.x, r.y);
+        }
+        float2 screen_pos = f2(float(x) + jitter.x, float(y) + jitter.y);
+        float2 viewport_pos = f2(screen_pos.x / float(f.width), screen_pos.y / float(f.height));
+
+        float4 ndc_near = make_float4(viewport_pos.x * 2.0f - 1.0f, viewport_pos.y * 2.0f - 1.0f, -1.0f, 1.0f);
+        float4 near_world = mul4x4(f.camera.inverse_view_projection, ndc_near);
+        float3 origin = f3(near_world) / near_world.w;
+        float4 ndc_far = make_float4(ndc_near.x, ndc_near.y, 1.0f, 1.0f);
+        float4 far_view = mul4x4(f.camera.inverse_projection, ndc_far);
+        const float* r = f.camera.view_to_world_rotation;
+        float3 v = f3(far_view);
+        float3 direction = normalize(f3(r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z));
+
+        w.ray_o[p] = f4(origin, 0.0f);
+        w.ray_d[p] = f4(direction, Pdf::delta_dirac(1.0f).v);
+        w.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
+        w.rad[p] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
+        w.queue_in[p] = (unsigned int)p;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        w.counters->active = (unsigned int)pixel_count;
+        w.counters->next_active = 0;
+        w.counters->shadow = 0;
+    }
+}
+
+// ---- extend: closest hit over triangles and analytic lights -------------------------------------------------
+
+__global__ void __launch_bounds__(TRACE_BLOCK) extend_kernel(WavefrontView w, SceneView s) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    const unsigned int count = w.counters->active;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        unsigned int pixel = w.queue_in[i];
+        float4 o = w.ray_o[pixel], d = w.ray_d[pixel];
+        int previous_primitive = __float_as_int(w.rad[pixel].w);
+        Ray ray;
+        ray.origin = f3(o); ray.tmin = o.w; ray.direction = f3(d); ray.tmax = RT_DEFAULT_MAX;
+        float transmission;
+        Hit h = trace<false>(s.accel, ray, previous_primitive, s_stack + threadIdx.x, transmission, s.coverage);
+        float t_closest = h.primitive >= 0 ? h.t : RT_DEFAULT_MAX;
+        // Analytic sphere / disk lights (LightSources.cu:31-70): intersectable by MonteCarlo rays only.
+        for (int l = 0; l < s.analytic_light_count; ++l) {
+            Light light = s.lights[l];
+            float t = -1e30f, radius = 0.0f;
+            if (light_type(light) == BPT_LIGHT_SPHERE) {
+                SphereLight sl = as_sphere(light); radius = sl.radius;
+                t = isect::ray_sphere(ray.origin, ray.direction, sl.position, sl.radius);
+            } else if (light_type(light) == BPT_LIGHT_SPOT) {
+                SpotLight sp = as_spot(light); radius = sp.radius;
+                t = isect::ray_disk(ray.origin, ray.direction, sp.position, sp.direction, sp.radius);
+            }
+            if (radius > 0.0f && t > ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
+        }
+        w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
+}
+
+// ---- shadow: accumulated transmission along the light sample's segment ---------------------------------------
+
+__global__ void __launch_bounds__(TRACE_BLOCK) shadow_kernel(WavefrontView w, SceneView s) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    const unsigned int count = w.counters->shadow;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float4 o = w.sh_o[i], d = w.sh_d[i];
+        Ray ray;
+        ray.origin = f3(o); ray.tmin = 0.0f; ray.direction = f3(d); ray.tmax = o.w;
+        float transmission;
+        trace<true>(s.accel, ray, -1, s_stack + threadIdx.x, transmission, s.coverage);
+        if (transmission > 0.0f) {
+            unsigned int pixel = __float_as_uint(d.w);
+            float4 rad = w.rad[pixel];
+            float4 l = w.sh_rad[i];
+            rad.x += l.x * transmission; rad.y += l.y * transmission; rad.z += l.z * transmission;
+            w.rad[pixel] = rad;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
+}
+
+// Swaps the roles of the queues for the next iteration (the pointers are swapped on the host).
+__global__ void advance_kernel(QueueCounters* c) {
+    c->active = c->next_active;
+    c->next_active = 0;
+    c->shadow = 0;
+}
+
+// ---- shade ---------------------------------------------------------------------------------------------
+
+// Utils.h:67-74
+__device__ __forceinline__ float3 fix_backfacing_shading_normal(float3 wdir, float3 n, float target_cos_theta) {
+    float cos_theta = dot(wdir, n);
+    if (cos_theta < target_cos_theta) {
+        float c = cos_theta - target_cos_theta;
+        return normalize(n - c * wdir);
+    }
+    return n;
+}
+
+// Utils.h:372-397 (Ray Tracing Gems ch. 6)
+__device__ __forceinline__ float3 offset_ray_origin(float3 p, float3 n) {
+    const float origin = 1.0f / 32.0f;
+    const float float_scale = 1.0f / 65536.0f;
+    const float int_scale = 256.0f;
+    int3 of_i = make_int3(int(int_scale * n.x), int(int_scale * n.y), int(int_scale * n.z));
+    float3 p_i = f3(__int_as_float(__float_as_int(p.x) + ((p.x < 0) ? -of_i.x : of_i.x)),
+                    __int_as_float(__float_as_int(p.y) + ((p.y < 0) ? -of_i.y : of_i.y)),
+                    __int_as_float(__float_as_int(p.z) + ((p.z < 0) ? -of_i.z : of_i.z)));
+    return f3(fabsf(p.x) < origin ? p.x + float_scale * n.x : p_i.x,
+              fabsf(p.y) < origin ? p.y + float_scale * n.y : p_i.y,
+              fabsf(p.z) < origin ? p.z + float_scale * n.z : p_i.z);
+}
+__device__ __forceinline__ float3 offset_ray_origin(float3 p, float3 direction, float3 geometric_normal) {
+    float cos_theta = dot(geometric_normal, direction);
+    geometric_normal = cos_theta >= 0 ? geometric_normal : -geometric_normal;
+    return offset_ray_origin(p, geometric_normal);
+}
+
+// OctahedralNormal::decode, Types.h:62-69
+__device__ __forceinline__ float3 oct_decode(const int16_t e[2]) {
+    float2 fe = f2(float(e[0]), float(e[1]));
+    float3 n = f3(fe.x, fe.y, 32767 - fabsf(fe.x) - fabsf(fe.y));
+    float t = fmaxf(-n.z, 0.0f);
+    n.x += n.x >= 0 ? -t : t;
+    n.y += n.y >= 0 ? -t : t;
+    return normalize(n);
+}
+
+// Utils.h:286-290
+__device__ __forceinline__ unsigned char unorm8(float v) { return (unsigned char)(saturate(v) * 255.0f + 0.5f); }
+
+// sample_single_light, MonteCarlo.cu:61-87
+__device__ LightSample sample_single_light(const SceneView& s, const ShadingTables& tables, const DefaultShading& material, float3 position,
+                                           float3 wo, const Tbn& tbn, float3 u) {
+    int light_index = min(s.light_count - 1, int(u.z * s.light_count));
+    Light light = s.lights[light_index];
+    LightSample ls = light_sample_radiance(light, s.env, position, f2(u.x, u.y));
+    ls.radiance *= float(s.light_count);
+
+    float N_dot_L = dot(tbn.normal, ls.direction_to_light);
+    ls.radiance *= fabsf(N_dot_L) / ls.pdf.value();
+
+    const float3 shading_light_direction = tbn.to_local(ls.direction_to_light);
+    BsdfResponse response = material.evaluate_with_pdf(wo, shading_light_direction);
+    bool apply_MIS = !ls.pdf.is_delta_dirac();
+    if (apply_MIS)
+        ls.radiance *= mis_weight(ls.pdf, response.pdf);
+    else
+        response.reflectance = min3(response.reflectance, f3(32.0f));
+    ls.radiance *= response.reflectance;
+    return ls;
+}
+
+__global__ void __launch_bounds__(SHADE_BLOCK) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
+    __shared__ __align__(16) float s_tables[3 * TABLE_FLOATS];
+    for (int i = threadIdx.x; i < 3 * TABLE_FLOATS; i += blockDim.x) s_tables[i] = s.tables[i];
+    __syncthreads();
+    const ShadingTables tables = { s_tables, s_tables + TABLE_FLOATS, s_tables + 2 * TABLE_FLOATS };
+
+    const unsigned int count = w.counters->active;
+    const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool valid = i < count;
+        bool continue_path = false, cast_shadow = false;
+        unsigned int pixel = 0;
+        float4 shadow_o = make_float4(0, 0, 0, 0), shadow_d = make_float4(0, 0, 0, 0), shadow_rad = make_float4(0, 0, 0, 0);
+
+        if (valid) {
+            pixel = w.queue_in[i];
+            const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
+            float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
+            const float4 hit4 = w.hit[pixel];
+            const float3 ray_origin = f3(ro), ray_direction = f3(rd);
+            Pdf bsdf_pdf(rd.w);
+            float3 throughput = f3(thr4), radiance = f3(rad4);
+            unsigned int bounces = __float_as_uint(thr4.w);
+            int previous_primitive = __float_as_int(rad4.w);
+            const float t_hit = hit4.x;
+            const int primitive = __float_as_int(hit4.y);
+            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
+
+            float3 next_origin = ray_origin, next_direction = ray_direction;
+            float next_tmin = ro.w;
+
+            if (primitive < 0) {
+                // miss, SimpleRGPs.cu:349-362
+                float3 environment_radiance = s.env.tint;
+                if (s.env.texels != nullptr) {
+                    environment_radiance = environment_light::evaluate(s.env, ray_direction);
+                    if (bsdf_pdf.use_for_MIS())
+                        environment_radiance *= mis_weight(bsdf_pdf, environment_light::pdf(s.env, ray_direction));
+                }
+                radiance += throughput * environment_radiance;
+                throughput = f3(0.0f);
+            } else if (primitive & LIGHT_HIT_FLAG) {
+                // light_closest_hit, MonteCarlo.cu:291-302; evaluate_intersection, LightImpl.h:86-108
+                Light light = s.lights[primitive & ~LIGHT_HIT_FLAG];
+                float3 light_radiance = light_evaluate(light, s.env, ray_origin, ray_direction);
+                if (bsdf_pdf.use_for_MIS())
+                    light_radiance *= mis_weight(bsdf_pdf, light_pdf(light, s.env, ray_origin, ray_direction));
+                throughput = min3(throughput, f3(4.0f));
+                radiance += throughput * light_radiance;
+                throughput = f3(0.0f);
+            } else {
+                // interpolate_attributes, TriangleAttributes.cu:35-84 (geometry is pre-transformed to world space)
+                const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
+                             p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
+                const int4* shade_raw = reinterpret_cast<const int4*>(s.shade + primitive);
+                int4 sr0 = __ldg(shade_raw), sr1 = __ldg(shade_raw + 1);
+                ShadeTriangle st;
+                memcpy(&st, &sr0, 16); memcpy(reinterpret_cast<char*>(&st) + 16, &sr1, 16);
+
+                float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
+                const float bx = hit4.z, by = hit4.w;
+                const float bz = 1.0f - bx - by;
+                const float3 intersection_point = p1 * bx + p2 * by + p0 * bz;
+                const bool has_normals = st.flags & 1u, has_tints = st.flags & 2u;
+                float3 shading_normal;
+                if (has_normals) {
+                    shading_normal = oct_decode(st.n1) * bx + oct_decode(st.n2) * by + oct_decode(st.n0) * bz;
+                    shading_normal = normalize(shading_normal);
+                } else
+                    shading_normal = geometric_normal;
+                float4 tint_and_roughness_scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+                if (has_tints) {
+                    const float n255 = 1.0f / 255.0f;
+                    tint_and_roughness_scale.x = (st.t1[0] * bx + st.t2[0] * by + st.t0[0] * bz) * n255;
+                    tint_and_roughness_scale.y = (st.t1[1] * bx + st.t2[1] * by + st.t0[1] * bz) * n255;
+                    tint_and_roughness_scale.z = (st.t1[2] * bx + st.t2[2] * by + st.t0[2] * bz) * n255;
+                    tint_and_roughness_scale.w = (st.t1[3] * bx + st.t2[3] * by + st.t0[3] * bz) * n255;
+                }
+
+                // path_tracing_closest_hit, MonteCarlo.cu:129-233. The same-primitive test (:137-142) already
+                // happened inside the traversal, which skips `previous_primitive`.
+                const Material material_parameter = s.materials[st.material_index];
+                float3 world_geometric_normal = geometric_normal;
+                bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
+                bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
+                backside_cull &= !material_is_transmissive(material_parameter);
+
+                float4 bsdf_coverage_random = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF);
+                float coverage_cutoff = bsdf_coverage_random.w;
+                float3 bsdf_random_uvs = f3(bsdf_coverage_random);
+                float coverage = material_coverage(material_parameter);
+                bool discard_from_coverage = coverage < coverage_cutoff;
+
+                if (backside_cull || discard_from_coverage) {
+                    next_tmin = nextafterf(t_hit, INFINITY); // same ray, advanced past this surface
+                } else {
+                    previous_primitive = primitive;
+                    world_geometric_normal = hit_from_front ? world_geometric_normal : -world_geometric_normal;
+                    float3 world_shading_normal = shading_normal;
+                    if (has_normals) {
+                        const float* nm = s.normal_matrices + 9 * (st.flags >> 2);
+                        world_shading_normal = normalize(f3(nm[0] * shading_normal.x + nm[1] * shading_normal.y + nm[2] * shading_normal.z,
+                                                            nm[3] * shading_normal.x + nm[4] * shading_normal.y + nm[5] * shading_normal.z,
+                                                            nm[6] * shading_normal.x + nm[7] * shading_normal.y + nm[8] * shading_normal.z));
+                    }
+                    world_shading_normal = hit_from_front ? world_shading_normal : -world_shading_normal;
+                    world_shading_normal = fix_backfacing_shading_normal(-ray_direction, world_shading_normal, 0.002f);
+                    const Tbn tbn(world_shading_normal);
+
+                    const float3 world_intersection_point = intersection_point;
+                    const float3 wo = tbn.to_local(-ray_direction);
+                    float cos_theta = hit_from_front || material_is_thin_walled(material_parameter) ? wo.z : -wo.z;
+
+                    // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
+                    // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
+                    Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
+                    const DefaultShading material = DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+
+                    radiance += throughput * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
+
+                    // reestimated_light_samples, MonteCarlo.cu:91-123
+                    LightSample light_sample = light_sample_none();
+                    if (s.light_count != 0) {
+                        float4 light_random_base = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_NEE);
+                        for (int k = 0; k < f.next_event_sample_count; ++k) {
+                            float4 shift = __ldg(s.nee_offsets + k);
+                            float4 r = light_random_base + shift; // toroidal_shift, Utils.h:46-49
+                            r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
+                            LightSample candidate = sample_single_light(s, tables, material, world_intersection_point, wo, tbn, f3(r));
+                            float light_weight = sum(light_sample.radiance);
+                            float new_light_weight = sum(candidate.radiance);
+                            float new_light_probability = new_light_weight / (light_weight + new_light_weight);
+                            if (r.w < new_light_probability) {
+                                light_sample = candidate;
+                                light_sample.radiance /= new_light_probability;
+                            } else
+                                light_sample.radiance /= 1.0f - new_light_probability;
+                        }
+                        light_sample.radiance /= float(f.next_event_sample_count);
+                    }
+                    float3 light_sample_origin = offset_ray_origin(world_intersection_point, light_sample.direction_to_light, world_geometric_normal);
+                    light_sample.radiance *= throughput;
+
+                    // BSDF sampling
+                    BsdfSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
+                    bool is_reflection = bsdf_sample.direction.z >= 0;
+                    next_direction = tbn.to_world(bsdf_sample.direction);
+                    bsdf_pdf = bsdf_sample.pdf;
+                    if (bsdf_sample.pdf.is_valid())
+                        throughput *= bsdf_sample.reflectance * fabsf(bsdf_sample.direction.z) / bsdf_sample.pdf.value();
+                    else
+                        throughput = f3(0.0f);
+
+                    float cos_geometric_theta_i = dot(next_direction, world_geometric_normal);
+                    if (is_reflection ? cos_geometric_theta_i < 0.0f : cos_geometric_theta_i >= 0.0f)
+                        next_direction = reflect(next_direction, world_geometric_normal);
+
+                    next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
+                    next_tmin = 0.0f;
+                    bounces += 1u;
+                    if (!light_sample.pdf.is_valid())
+                        bsdf_pdf.disable_MIS();
+
+                    // path_trace_single_bounce, SimpleRGPs.cu:117-125
+                    if (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0) {
+                        cast_shadow = true;
+                        shadow_o = f4(light_sample_origin, light_sample.distance);
+                        shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
+                        shadow_rad = f4(light_sample.radiance, 0.0f);
+                    }
+                }
+            }
+
+            continue_path = bounces <= f.max_bounce_count && !is_black(throughput); // SimpleRGPs.cu:136
+            w.rad[pixel] = f4(radiance, __int_as_float(previous_primitive));
+            if (continue_path) {
+                w.ray_o[pixel] = f4(next_origin, next_tmin);
+                w.ray_d[pixel] = f4(next_direction, bsdf_pdf.v);
+                w.thr[pixel] = f4(throughput, __uint_as_float(bounces));
+            }
+        }
+
+        // Queue compaction: ballot + popc inside the warp, one atomic per warp and queue.
+        warp_append(continue_path, w.queue_out, &w.counters->next_active, pixel);
+        {
+            unsigned int mask = __ballot_sync(0xffffffffu, cast_shadow);
+            if (mask) {
+                int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+                unsigned int base = 0;
+                if (lane == leader) base = atomicAdd(&w.counters->shadow, __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (cast_shadow) {
+                    unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
+                    w.sh_o[slot] = shadow_o; w.sh_d[slot] = shadow_d; w.sh_rad[slot] = shadow_rad;
+                }
+            }
+        }
+    }
+}
+
+// ---- accumulate / resolve --------------------------------------------------------------------------------
+
+// accumulate<>, SimpleRGPs.cu:74-107. The reference keeps a running mean in fp64; here the fp64 SUM and the
+// sample count are kept (mean = sum / count on resolve), which lets sample ranges rendered on different GPUs be
+// combined with one sum-reduce.
+__global__ void accumulate_kernel(const float4* __restrict__ rad, double* __restrict__ accum, int64_t pixel_count) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
+        float4 r = rad[p];
+        double2* a = reinterpret_cast<double2*>(accum + 4 * p);
+        double2 rg = a[0], bw = a[1];
+        rg.x += (double)r.x; rg.y += (double)r.y; bw.x += (double)r.z; bw.y += 1.0;
+        a[0] = rg; a[1] = bw;
+    }
+}
+
+__global__ void resolve_half4_kernel(const double* __restrict__ accum, ushort4* __restrict__ out, int64_t pixel_count) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
+        const double2* a = reinterpret_cast<const double2*>(accum + 4 * p);
+        double2 rg = a[0], bw = a[1];
+        double inv = bw.y > 0.0 ? 1.0 / bw.y : 0.0;
+        float3 mean = f3(float(rg.x * inv), float(rg.y * inv), float(bw.x * inv));
+        // float_to_half, SimpleRGPs.cu:39-42
+        out[p] = make_ushort4(__half_as_ushort(__float2half_rn(mean.x)), __half_as_ushort(__float2half_rn(mean.y)),
+                              __half_as_ushort(__float2half_rn(mean.z)), __half_as_ushort(__float2half_rn(1.0f)));
+    }
+}
+
+__global__ void resolve_float4_kernel(const double* __restrict__ accum, float4* __restrict__ out, int64_t pixel_count) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
+        const double2* a = reinterpret_cast<const double2*>(accum + 4 * p);
+        double2 rg = a[0], bw = a[1];
+        double inv = bw.y > 0.0 ? 1.0 / bw.y : 0.0;
+        out[p] = make_float4(float(rg.x * inv), float(rg.y * inv), float(bw.x * inv), 1.0f);
+    }
+}
+
+Wavefront* wavefront(Context* ctx) { return static_cast<Wavefront*>(ctx->wavefront); }
+
+} // namespace
+
+void release_wavefront(Context* ctx) {
+    Wavefront* wf = wavefront(ctx);
+    if (!wf) return;
+    wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
+    wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
+    wf->counters.release(); wf->coverage.release();
+    delete wf;
+    ctx->wavefront = nullptr;
+}
+
+int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
+           uint32_t first_sample, uint32_t sample_count, int reset_accumulation) {
+    if (!camera || !settings || width <= 0 || height <= 0) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: bad arguments");
+    if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_build_accel first");
+    if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_set_tables first");
+    if (settings->next_event_sample_count < 0 || settings->next_event_sample_count > 256)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: next_event_sample_count must be in [0, 256]");
+    cudaStream_t st = ctx->stream;
+    const int64_t pixels = (int64_t)width * height;
+    if (pixels > 0x7fffffffll) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: frame too large");
+
+    if (!ctx->wavefront) ctx->wavefront = new Wavefront();
+    Wavefront* wf = wavefront(ctx);
+    if (wf->pixel_capacity < pixels) {
+        BPT_CUDA_CHECK(ctx, wf->ray_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->ray_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->thr.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->rad.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->hit.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->queue_a.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_b.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->counters.resize(1));
+        wf->pixel_capacity = pixels;
+    }
+    {
+        std::vector<float> h_cov(ctx->host_materials.size());
+        for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
+        BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
+        BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->coverage.ptr, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // h_cov goes out of scope
+    }
+
+    bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
+    if (size_changed) {
+        BPT_CUDA_CHECK(ctx, ctx->accumulation.resize(4 * pixels));
+        ctx->width = width; ctx->height = height;
+    }
+    if (size_changed || reset_accumulation)
+        BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
+
+    SceneView s = {};
+    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr };
+    s.world_vertices = ctx->accel.world_vertices.ptr;
+    s.shade = ctx->accel.shade.ptr;
+    s.normal_matrices = ctx->accel.normal_matrices.ptr;
+    s.materials = ctx->materials.ptr;
+    s.coverage = wf->coverage.ptr;
+    s.lights = ctx->lights.ptr;
+    s.analytic_light_count = ctx->light_count;
+    s.light_count = ctx->light_count;
+    s.env = {};
+    s.env.tint = f3(ctx->env_tint[0], ctx->env_tint[1], ctx->env_tint[2]);
+    if (ctx->env_width > 0) {
+        s.env.texels = ctx->env_texels.ptr; s.env.width = ctx->env_width; s.env.height = ctx->env_height;
+        s.env.per_pixel_pdf = ctx->env_pdf.ptr; s.env.pdf_width = ctx->env_pdf_width; s.env.pdf_height = ctx->env_pdf_height;
+        s.env.samples = ctx->env_samples.ptr; s.env.sample_count = ctx->env_sample_count;
+        if (ctx->env_sample_count > 1) {
+            // next_event_estimation_possible (PresampledEnvironmentMap.h:64): the environment is appended to the light list
+            // (Renderer.cpp:1180-1195). bpt_set_lights reserved the slot.
+            if (!ctx->lights.ptr) { Light none = {}; BPT_CUDA_CHECK(ctx, ctx->lights.resize(1)); (void)none; }
+            Light env_light = {};
+            env_light.flags = BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
+            BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
+            BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            s.lights = ctx->lights.ptr;
+            s.light_count = ctx->light_count + 1;
+        }
+    }
+    s.tables = ctx->tables.ptr;
+    s.nee_offsets = ctx->nee_offsets.ptr;
+
+    WavefrontView w = {};
+    w.ray_o = wf->ray_o.ptr; w.ray_d = wf->ray_d.ptr; w.thr = wf->thr.ptr; w.rad = wf->rad.ptr; w.hit = wf->hit.ptr;
+    w.sh_o = wf->sh_o.ptr; w.sh_d = wf->sh_d.ptr; w.sh_rad = wf->sh_rad.ptr;
+    w.counters = wf->counters.ptr;
+    w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
+
+    FrameParams f = {};
+    f.camera = *camera; f.width = width; f.height = height;
+    f.max_bounce_count = settings->max_bounce_count;
+    f.next_event_sample_count = settings->next_event_sample_count;
+    f.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
+
+    // Persistent grids: a whole number of CTAs per SM.
+    const int trace_grid = ctx->sm_count * 8;
+    const int shade_grid = ctx->sm_count * 4;
+    const int stream_grid = ctx->sm_count * 8;
+
+    for (uint32_t k = 0; k < sample_count; ++k) {
+        f.accumulation_count = first_sample + k;
+        w.queue_in = wf->queue_a.ptr; w.queue_out = wf->queue_b.ptr;
+        generate_kernel<<<stream_grid, 256, 0, st>>>(w, f);
+        ctx->counters.kernel_launches++;
+        // A path shades at most max_bounce_count + 1 surfaces; rejected hits (back faces, coverage) re-trace the same
+        // ray without consuming a bounce, so a few extra iterations run before the queue length is checked on the host.
+        uint32_t planned = settings->max_bounce_count + 2;
+        uint32_t done = 0;
+        while (true) {
+            size_t first_event = 0;
+            for (uint32_t it = 0; it < planned; ++it) {
+                if (ctx->profiling) { first_event = ctx->stage_event(it * 4 + 0); cudaEventRecord(ctx->stage_events[first_event], st); }
+                extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
+                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
+                shade_kernel<<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
+                shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
+                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);
+                advance_kernel<<<1, 1, 0, st>>>(w.counters);
+                std::swap(w.queue_in, w.queue_out);
+                ctx->counters.kernel_launches += 4;
+            }
+            done += planned;
+            QueueCounters h;
+            BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+            BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            if (ctx->profiling)
+                for (uint32_t it = 0; it < planned; ++it) {
+                    float ms = 0.0f;
+                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 0], ctx->stage_events[it * 4 + 1]); ctx->counters.extend_ms += ms;
+                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 1], ctx->stage_events[it * 4 + 2]); ctx->counters.shade_ms += ms;
+                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 2], ctx->stage_events[it * 4 + 3]); ctx->counters.shadow_ms += ms;
+                }
+            if (h.active == 0) break;
+            if (done > 4096) return ctx->fail(BPT_ERROR_CUDA, "bpt_render: path queue did not drain");
+            planned = 2;
+        }
+        accumulate_kernel<<<stream_grid, 256, 0, st>>>(wf->rad.ptr, ctx->accumulation.ptr, pixels);
+        ctx->counters.kernel_launches++;
+        ctx->counters.samples += (uint64_t)pixels;
+    }
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
+int resolve_half4(Context* ctx, uint16_t* out, int on_device) {
+    if (!out || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_half4: nothing rendered");
+    int64_t pixels = (int64_t)ctx->width * ctx->height;
+    cudaStream_t st = ctx->stream;
+    ushort4* d = reinterpret_cast<ushort4*>(out);
+    if (!on_device) BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d, pixels * sizeof(ushort4), st));
+    resolve_half4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels);
+    ctx->counters.kernel_launches++;
+    if (!on_device) {
+        BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, pixels * sizeof(ushort4), cudaMemcpyDeviceToHost, st));
+        BPT_CUDA_CHECK(ctx, cudaFreeAsync(d, st));
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    }
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
+int resolve_float4(Context* ctx, float* out) {
+    if (!out || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_float4: nothing rendered");
+    int64_t pixels = (int64_t)ctx->width * ctx->height;
+    cudaStream_t st = ctx->stream;
+    float4* d = nullptr;
+    BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d, pixels * sizeof(float4), st));
+    resolve_float4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels);
+    ctx->counters.kernel_launches++;
+    BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, pixels * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    BPT_CUDA_CHECK(ctx, cudaFreeAsync(d, st));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
+} // namespace bpt

@@ -164,6 +164,9 @@ int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
 /* mean as float4 to a HOST buffer of width*height*4 floats. */
 int bpt_resolve_float4(bpt_ctx* ctx, float* out);
 int bpt_synchronize(bpt_ctx* ctx);
+/* enabled != 0: bpt_render brackets its stage kernels with CUDA events on the context's stream and accumulates their
+ * durations into bpt_counters.{extend,shade,shadow}_ms (used by bench.py for the roofline figures). */
+int bpt_set_profiling(bpt_ctx* ctx, int enabled);
 int bpt_get_counters(bpt_ctx* ctx, bpt_counters* out, int reset);
 
 /* ---- batched unit entry points (parity tests and the C1 workload) ------------------------------ */
