@@ -57,31 +57,43 @@ def build_scene(name):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi SM clocks and throttle reasons during the timed region."""
-    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """Samples SM clocks and throttle reasons through NVML during the timed region (every 10 ms)."""
 
     def __init__(self, device):
         super().__init__(daemon=True)
-        self.device, self.samples, self.stop_flag = device, [], threading.Event()
+        self.device, self.sm, self.reasons, self.stop_flag, self.max_mhz = device, [], set(), threading.Event(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible and visible.split(",")[device].isdigit() else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        if self.nvml is None:
+            return
+        n = self.nvml
+        names = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-i", str(self.device)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                get = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(get(self.handle))
+                for name, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.01)
 
     def summary(self):
         self.stop_flag.set()
-        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.sm)}
 
 
 def cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=2.0, threads=0):
@@ -232,7 +244,8 @@ def main():
 
     # ---- end-to-end through the C ABI with host buffers ---------------------------------------------
     barrier()
-    frame = np.empty((H, W, 4), np.uint16)
+    frame_t = torch.empty((H, W, 4), dtype=torch.int16).pin_memory()  # pinned host frame, as a display path would use
+    frame = frame_t.numpy().view(np.uint16)
     for k in range(2):
         ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.lib.bpt_resolve_half4(ctx.h, frame.ctypes.data, 0)
     barrier()

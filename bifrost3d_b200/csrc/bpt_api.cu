@@ -306,6 +306,13 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPT_ERROR_CUDA; }
+    { // keep stream-ordered scratch allocations cached instead of returning them to the OS at every synchronise
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, cuda_device) == cudaSuccess) {
+            uint64_t threshold = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+        }
+    }
     for (auto& e : ctx->ev) cudaEventCreate(&e);
     cudaMalloc((void**)&ctx->device_counters, 8 * sizeof(uint64_t));
     cudaMemsetAsync(ctx->device_counters, 0, 8 * sizeof(uint64_t), ctx->stream);
@@ -334,7 +341,7 @@ void bpt_destroy(bpt_ctx* c) {
     ctx->tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
     ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
-    ctx->accumulation.release();
+    ctx->accumulation.release(); ctx->output_half4.release();
     if (ctx->device_counters) cudaFree(ctx->device_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->stage_events) cudaEventDestroy(e);
@@ -417,6 +424,7 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     ctx->host_materials.assign(materials, materials + count);
     BPT_CUDA_CHECK(ctx, upload(ctx, ctx->materials, materials, (size_t)count));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->material_version++;
     ctx->accel.valid = false; // cull / coverage flags are baked into the triangle records
     return BPT_OK;
 }
@@ -437,6 +445,7 @@ int bpt_set_lights(bpt_ctx* c, const bpt_light* lights, int count) {
     BPT_CUDA_CHECK(ctx, upload(ctx, ctx->lights, all.data(), all.size()));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->light_count = count;
+    ctx->env_light_uploaded = false;
     return BPT_OK;
 }
 
@@ -446,6 +455,7 @@ int bpt_set_environment(bpt_ctx* c, const float tint[3], const float* texels, in
     if (!tint) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment: null tint");
     cudaSetDevice(ctx->device);
     memcpy(ctx->env_tint, tint, 3 * sizeof(float));
+    ctx->env_light_uploaded = false;
     if (!texels) {
         ctx->env_width = ctx->env_height = ctx->env_pdf_width = ctx->env_pdf_height = ctx->env_sample_count = 0;
         return BPT_OK;

@@ -114,6 +114,9 @@ struct Context {
     // Render state
     int width = 0, height = 0;
     DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
+    DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
+    uint64_t material_version = 0;
+    bool env_light_uploaded = false;
     void* wavefront = nullptr;         // integrator-owned state (bpt_render.cu)
 
     bpt_counters counters = {};

@@ -45,6 +45,7 @@ struct Wavefront {
     DeviceBuffer<unsigned int> queue_a, queue_b;
     DeviceBuffer<QueueCounters> counters;
     DeviceBuffer<float> coverage; // per material
+    uint64_t coverage_version = ~0ull;
 };
 
 struct WavefrontView {
@@ -531,12 +532,13 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, wf->counters.resize(1));
         wf->pixel_capacity = pixels;
     }
-    {
+    if (wf->coverage_version != ctx->material_version) {
         std::vector<float> h_cov(ctx->host_materials.size());
         for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
         BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->coverage.ptr, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // h_cov goes out of scope
+        wf->coverage_version = ctx->material_version;
     }
 
     bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
@@ -566,11 +568,14 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         if (ctx->env_sample_count > 1) {
             // next_event_estimation_possible (PresampledEnvironmentMap.h:64): the environment is appended to the light list
             // (Renderer.cpp:1180-1195). bpt_set_lights reserved the slot.
-            if (!ctx->lights.ptr) { Light none = {}; BPT_CUDA_CHECK(ctx, ctx->lights.resize(1)); (void)none; }
-            Light env_light = {};
-            env_light.flags = BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
-            BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
-            BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            if (!ctx->lights.ptr) BPT_CUDA_CHECK(ctx, ctx->lights.resize(1));
+            if (!ctx->env_light_uploaded) {
+                Light env_light = {};
+                env_light.flags = BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
+                BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
+                BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+                ctx->env_light_uploaded = true;
+            }
             s.lights = ctx->lights.ptr;
             s.light_count = ctx->light_count + 1;
         }
@@ -646,12 +651,15 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device) {
     int64_t pixels = (int64_t)ctx->width * ctx->height;
     cudaStream_t st = ctx->stream;
     ushort4* d = reinterpret_cast<ushort4*>(out);
-    if (!on_device) BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d, pixels * sizeof(ushort4), st));
+    if (!on_device) {
+        // context-owned staging frame: no allocation on the per-frame path
+        BPT_CUDA_CHECK(ctx, ctx->output_half4.resize(4 * pixels));
+        d = reinterpret_cast<ushort4*>(ctx->output_half4.ptr);
+    }
     resolve_half4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels);
     ctx->counters.kernel_launches++;
     if (!on_device) {
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, pixels * sizeof(ushort4), cudaMemcpyDeviceToHost, st));
-        BPT_CUDA_CHECK(ctx, cudaFreeAsync(d, st));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     }
     BPT_CUDA_CHECK(ctx, cudaGetLastError());

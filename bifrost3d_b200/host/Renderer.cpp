@@ -1,0 +1,348 @@
+// Host side of the drop-in: OptiXRenderer::Renderer over the Bifrost core scene handles, driving libbpt.so through the
+// C ABI (include/bpt_c_api.h). Mirrors the behaviour of the reference's
+// extensions/OptiXRenderer/OptiXRenderer/Renderer.cpp (initialize :1365-1378, handle_updates :578-1205,
+// prepare_camera_state + render :1207-1265, setters :1389-1474) but flattens the scene into device arrays instead of an
+// OptiX scene graph. Scene synchronisation is non-incremental in this revision: any mesh / model / transform / material
+// change re-uploads the flattened scene and rebuilds the BVH (incremental refit is a "next" row).
+#include <OptiXRenderer/Renderer.h>
+
+#include <optixu/optixpp_namespace.h>
+
+#include <Bifrost/Assets/Material.h>
+#include <Bifrost/Assets/Mesh.h>
+#include <Bifrost/Assets/MeshModel.h>
+#include <Bifrost/Assets/Shading/Fittings.h>
+#include <Bifrost/Core/Renderer.h>
+#include <Bifrost/Math/Conversions.h>
+#include <Bifrost/Scene/Camera.h>
+#include <Bifrost/Scene/LightSource.h>
+#include <Bifrost/Scene/SceneNode.h>
+#include <Bifrost/Scene/SceneRoot.h>
+
+#include "../../include/bpt_c_api.h"
+
+#include <cuda_runtime.h>
+
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <vector>
+
+using namespace Bifrost;
+using namespace Bifrost::Assets;
+using namespace Bifrost::Math;
+using namespace Bifrost::Scene;
+
+// ---- optix facade ------------------------------------------------------------------------------------------------
+namespace optix {
+
+static int g_next_buffer_id = 1;
+
+BufferObj::BufferObj(RTformat format, RTsize width, RTsize height)
+    : m_format(format), m_width(width), m_height(height), m_element_size(format == RT_FORMAT_HALF4 ? 8 : 16), m_device(nullptr),
+      m_owns_device(true), m_id(g_next_buffer_id++) {
+    if (cudaMalloc(&m_device, m_width * m_height * m_element_size) != cudaSuccess)
+        throw Exception("optix facade: cudaMalloc failed for a render target");
+}
+BufferObj::~BufferObj() { if (m_owns_device && m_device) cudaFree(m_device); }
+void* BufferObj::map() {
+    m_host.resize(m_width * m_height * m_element_size);
+    cudaMemcpy(m_host.data(), m_device, m_host.size(), cudaMemcpyDeviceToHost);
+    return m_host.data();
+}
+void BufferObj::setDevicePointer(int, void* pointer) {
+    if (m_owns_device && m_device) cudaFree(m_device);
+    m_device = pointer; m_owns_device = false;
+}
+
+} // namespace optix
+
+namespace OptiXRenderer {
+
+static const int MAX_RNG_SAMPLE_OFFSETS = 256; // Renderer.cpp:46
+
+struct Renderer::Implementation {
+    bpt_ctx* ctx = nullptr;
+    optix::Context context;
+    Core::RendererID owning_renderer_ID;
+
+    struct CameraState {
+        unsigned int accumulations = 0;
+        unsigned int max_accumulation_count = UINT_MAX;
+        unsigned int max_bounce_count = 4; // Renderer.cpp:216
+        Vector2i frame_size = Vector2i(0, 0);
+        Matrix4x4f inverse_view_projection_matrix = {};
+        Backend backend = Backend::None;
+        bool initialized = false;
+    };
+    std::vector<CameraState> per_camera_state;
+
+    int next_event_sample_count = 3;                         // Renderer.cpp:479
+    PathRegularizationSettings path_regularization = { 0.5f, 0.0f }; // Renderer.cpp:482-483
+    AIDenoiserFlags AI_denoiser_flags = AIDenoiserFlag::Default;
+    bool scene_uploaded = false;
+
+    Implementation(int cuda_device_ID, Core::RendererID renderer_ID) : owning_renderer_ID(renderer_ID) {
+        // NB the reference ignores cuda_device_ID and always uses OptiX device 0 (Renderer.cpp:289-291); here it is honoured
+        // so one process per GPU can shard samples.
+        if (bpt_create(cuda_device_ID, &ctx) != BPT_OK)
+            throw optix::Exception("no CUDA device available for the B200 path tracer");
+        // Rho / alpha tables: the reference uploads the same arrays as textures (Renderer.cpp:400-466).
+        using namespace Assets::Shading;
+        if (bpt_set_tables(ctx, Rho::GGX_with_fresnel, Rho::GGX, Estimate_GGX_bounded_VNDF_alpha::alphas) != BPT_OK)
+            throw optix::Exception(bpt_last_error(ctx));
+        context = optix::Context(new optix::ContextObj());
+    }
+    ~Implementation() { bpt_destroy(ctx); }
+
+    void conditional_per_camera_state_resize(CameraID camera_ID) {
+        if (per_camera_state.size() <= camera_ID)
+            per_camera_state.resize(Cameras::capacity());
+    }
+
+    static void check(bpt_ctx* ctx, int status, const char* what) {
+        if (status != BPT_OK) printf("OptiXRenderer(B200) error in %s: %s\n", what, bpt_last_error(ctx));
+    }
+
+    void upload_geometry_and_materials() {
+        // load_mesh, Renderer.cpp:92-136: every mesh referenced by a model.
+        std::map<unsigned int, bool> uploaded;
+        std::vector<bpt_instance> instances;
+        for (MeshModelID model_ID : MeshModels::get_iterable()) {
+            MeshID mesh_ID = MeshModels::get_mesh_ID(model_ID);
+            if (!Meshes::has(mesh_ID)) continue;
+            if (!uploaded[mesh_ID]) {
+                unsigned int vertex_count = Meshes::get_vertex_count(mesh_ID);
+                static_assert(sizeof(TintRoughness) == 4, "TintRoughness is uchar4");
+                check(ctx, bpt_upload_mesh(ctx, int(mesh_ID.get_index()), Meshes::get_indices(mesh_ID), int(Meshes::get_primitive_count(mesh_ID)),
+                                           (const float*)Meshes::get_positions(mesh_ID), (const float*)Meshes::get_normals(mesh_ID),
+                                           (const float*)Meshes::get_texcoords(mesh_ID), (const uint8_t*)Meshes::get_tint_and_roughness(mesh_ID),
+                                           int(vertex_count)), "bpt_upload_mesh");
+                uploaded[mesh_ID] = true;
+            }
+            // Transform + model, Renderer.cpp:1010-1110: object -> world from the node's global transform.
+            Matrix3x4f m = to_matrix3x4(SceneNodes::get_global_transform(MeshModels::get_scene_node_ID(model_ID)));
+            bpt_instance inst = {};
+            inst.mesh_id = int(mesh_ID.get_index());
+            inst.material_id = int(MeshModels::get_material_ID(model_ID).get_index());
+            memcpy(inst.to_world, m.begin(), sizeof(inst.to_world));
+            instances.push_back(inst);
+        }
+
+        // upload_material, Renderer.cpp:753-812; index = MaterialID, the invalid material 0 is uploaded as well (:821).
+        std::vector<bpt_material> materials(Materials::capacity());
+        for (auto& m : materials) { memset(&m, 0, sizeof(m)); m.coverage = 1.0f; }
+        for (MaterialID material_ID : Materials::get_iterable()) {
+            Assets::Material host = material_ID;
+            bpt_material& d = materials[material_ID];
+            d.flags = uint16_t(host.get_flags().raw());
+            d.shading_model = uint16_t(int(host.get_shading_model()));
+            RGB tint = host.get_tint();
+            d.tint[0] = tint.r; d.tint[1] = tint.g; d.tint[2] = tint.b;
+            d.roughness = host.get_roughness();
+            d.specularity = host.get_specularity();
+            d.metallic = host.get_metallic();
+            d.coat = uint16_t(fminf(fmaxf(host.get_coat(), 0.0f), 1.0f) * 65535.0f + 0.5f);            // UNorm16, Types.h:86
+            d.coat_roughness = uint16_t(fminf(fmaxf(host.get_coat_roughness(), 0.0f), 1.0f) * 65535.0f + 0.5f);
+            d.coverage = host.is_cutout() ? host.get_cutout_threshold() : host.get_coverage();
+            RGB emission = host.get_emission();
+            d.emission[0] = emission.r; d.emission[1] = emission.g; d.emission[2] = emission.b;
+            if (host.has_tint_texture() || host.has_roughness_texture() || host.get_metallic_texture_ID() != TextureID::invalid_UID() ||
+                host.get_coverage_texture_ID() != TextureID::invalid_UID())
+                printf("OptiXRenderer(B200) warning: material %u is textured; textures are not implemented and are ignored.\n", material_ID.get_index());
+        }
+        check(ctx, bpt_set_materials(ctx, materials.data(), int(materials.size())), "bpt_set_materials");
+        check(ctx, bpt_set_instances(ctx, instances.data(), int(instances.size())), "bpt_set_instances");
+        check(ctx, bpt_build_accel(ctx), "bpt_build_accel");
+    }
+
+    void upload_lights() {
+        // Renderer.cpp:852-1008: linearised light list; unknown types become the magenta warning sphere (:892-898).
+        std::vector<bpt_light> lights;
+        for (LightSourceID light_ID : LightSources::get_iterable()) {
+            bpt_light l = {};
+            switch (LightSources::get_type(light_ID)) {
+            case LightSources::Type::Sphere: {
+                Scene::SphereLight host = Scene::LightSource(light_ID);
+                Vector3f p = host.get_node().get_global_transform().translation; RGB power = host.get_power();
+                l.flags = BPT_LIGHT_SPHERE;
+                l.data[0] = power.r; l.data[1] = power.g; l.data[2] = power.b; l.data[3] = p.x; l.data[4] = p.y; l.data[5] = p.z; l.data[6] = host.get_radius();
+                break;
+            }
+            case LightSources::Type::Spot: {
+                Scene::SpotLight host = Scene::LightSource(light_ID);
+                Transform t = host.get_node().get_global_transform();
+                Vector3f p = t.translation, d = t.rotation.forward(); RGB power = host.get_power();
+                l.flags = BPT_LIGHT_SPOT;
+                l.data[0] = power.r; l.data[1] = power.g; l.data[2] = power.b; l.data[3] = p.x; l.data[4] = p.y; l.data[5] = p.z; l.data[6] = host.get_radius();
+                l.data[7] = d.x; l.data[8] = d.y; l.data[9] = d.z; l.data[10] = host.get_cos_angle();
+                break;
+            }
+            case LightSources::Type::Directional: {
+                Scene::DirectionalLight host = Scene::LightSource(light_ID);
+                Vector3f d = host.get_node().get_global_transform().rotation.forward(); RGB radiance = host.get_radiance();
+                l.flags = BPT_LIGHT_DIRECTIONAL;
+                l.data[0] = radiance.r; l.data[1] = radiance.g; l.data[2] = radiance.b; l.data[3] = d.x; l.data[4] = d.y; l.data[5] = d.z;
+                break;
+            }
+            default:
+                printf("OptiXRenderer warning: Unknown light source type %u on light %u\n", unsigned(LightSources::get_type(light_ID)), light_ID.get_index());
+                l.flags = BPT_LIGHT_SPHERE;
+                l.data[0] = 100000; l.data[2] = 100000; l.data[6] = 5;
+            }
+            lights.push_back(l);
+        }
+        check(ctx, bpt_set_lights(ctx, lights.data(), int(lights.size())), "bpt_set_lights");
+    }
+
+    void handle_updates() {
+        bool should_reset_accumulations = false;
+
+        // Cameras, Renderer.cpp:581-619
+        for (CameraID cam_ID : Cameras::get_changed_cameras()) {
+            auto changes = Cameras::get_changes(cam_ID);
+            if (changes.contains(Cameras::Change::Destroyed)) {
+                if (cam_ID < per_camera_state.size()) per_camera_state[cam_ID] = CameraState();
+                continue;
+            }
+            bool uses_this_renderer = owning_renderer_ID == Cameras::get_renderer_ID(cam_ID);
+            bool created = uses_this_renderer && changes.is_set(Cameras::Change::Created);
+            bool switched = uses_this_renderer && changes.is_set(Cameras::Change::Renderer);
+            conditional_per_camera_state_resize(cam_ID);
+            CameraState& state = per_camera_state[cam_ID];
+            if (!state.initialized && (created || switched)) {
+                state.accumulations = 0u;
+                state.frame_size = Vector2i(1, 1);
+                state.inverse_view_projection_matrix = {};
+                if (state.backend == Backend::None) state.backend = Backend::PathTracing;
+                state.initialized = true;
+            }
+        }
+
+        bool geometry_changed = !scene_uploaded;
+        geometry_changed |= !Meshes::get_changed_meshes().is_empty();
+        geometry_changed |= !MeshModels::get_changed_models().is_empty();
+        geometry_changed |= !Materials::get_changed_materials().is_empty();
+        for (SceneNodeID node_ID : SceneNodes::get_changed_nodes())
+            if (SceneNodes::get_changes(node_ID).contains(SceneNodes::Change::Transform)) geometry_changed = true;
+        if (geometry_changed) {
+            upload_geometry_and_materials();
+            should_reset_accumulations = true;
+        }
+
+        bool lights_changed = !scene_uploaded || !LightSources::get_changed_lights().is_empty() || geometry_changed;
+        if (lights_changed) {
+            upload_lights();
+            should_reset_accumulations = true;
+        }
+
+        // Scene roots, Renderer.cpp:1112-1200: environment tint (environment maps need textures: "next" row).
+        for (SceneRoot scene_data : SceneRoots::get_changed_scenes()) {
+            float tint[3] = { 0, 0, 0 };
+            if (!scene_data.get_changes().contains(SceneRoots::Change::Destroyed)) {
+                RGB env_tint = scene_data.get_environment_tint();
+                tint[0] = env_tint.r; tint[1] = env_tint.g; tint[2] = env_tint.b;
+                if (scene_data.get_environment_map().exists())
+                    printf("OptiXRenderer(B200) warning: environment maps through the Bifrost Texture manager are not implemented; using the tint only.\n");
+            }
+            check(ctx, bpt_set_environment(ctx, tint, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0), "bpt_set_environment");
+            should_reset_accumulations = true;
+        }
+        scene_uploaded = true;
+
+        if (should_reset_accumulations)
+            for (auto& camera_state : per_camera_state) camera_state.accumulations = 0u;
+    }
+
+    unsigned int render(CameraID camera_ID, optix::Buffer buffer, Vector2i frame_size, unsigned int first_sample) {
+        conditional_per_camera_state_resize(camera_ID);
+        CameraState& state = per_camera_state[camera_ID];
+
+        // prepare_camera_state, Renderer.cpp:1207-1248
+        if (frame_size != state.frame_size) { state.frame_size = frame_size; state.accumulations = 0u; }
+        Matrix4x4f inverse_projection_matrix = Cameras::get_inverse_projection_matrix(camera_ID);
+        Matrix4x4f inverse_view_projection_matrix = Cameras::get_inverse_view_projection_matrix(camera_ID);
+        if (state.inverse_view_projection_matrix != inverse_view_projection_matrix) state.accumulations = 0u;
+        state.inverse_view_projection_matrix = inverse_view_projection_matrix;
+        Matrix3x3f view_to_world_rotation = to_matrix3x3(Cameras::get_inverse_view_transform(camera_ID).rotation);
+
+        if (state.accumulations >= state.max_accumulation_count)
+            return state.accumulations;
+
+        if (state.backend != Backend::PathTracing && state.backend != Backend::None) {
+            printf("OptiXRenderer(B200): Backend %u not supported; only path tracing is implemented.\n", unsigned(state.backend));
+            return state.accumulations;
+        }
+
+        bpt_camera camera;
+        memcpy(camera.view_to_world_rotation, view_to_world_rotation.begin(), sizeof(camera.view_to_world_rotation));
+        memcpy(camera.inverse_projection, inverse_projection_matrix.begin(), sizeof(camera.inverse_projection));
+        memcpy(camera.inverse_view_projection, inverse_view_projection_matrix.begin(), sizeof(camera.inverse_view_projection));
+        bpt_settings settings = {};
+        settings.max_bounce_count = state.max_bounce_count;
+        settings.next_event_sample_count = next_event_sample_count;
+        settings.path_regularization_pdf_scale = path_regularization.PDF_scale_at_accumulation(int(state.accumulations));
+
+        int status = bpt_render(ctx, &camera, &settings, frame_size.x, frame_size.y, first_sample + state.accumulations, 1, state.accumulations == 0 ? 1 : 0);
+        check(ctx, status, "bpt_render");
+        if (status == BPT_OK) {
+            check(ctx, bpt_resolve_half4(ctx, (uint16_t*)buffer->getDevicePointer(0), 1), "bpt_resolve_half4");
+            check(ctx, bpt_synchronize(ctx), "bpt_synchronize");
+            ++state.accumulations;
+        }
+        return state.accumulations;
+    }
+};
+
+Renderer* Renderer::initialize(int cuda_device_ID, const std::filesystem::path& data_directory) {
+    try {
+        return new Renderer(cuda_device_ID, data_directory);
+    } catch (optix::Exception e) {
+        printf("OptiXRenderer failed to initialize:\n%s\n", e.getErrorString().c_str());
+        return nullptr;
+    }
+}
+
+Renderer::Renderer(int cuda_device_ID, const std::filesystem::path&)
+    : m_renderer_ID(Core::Renderers::create("OptiXRenderer")), m_impl(nullptr) {
+    try {
+        m_impl = new Implementation(cuda_device_ID, m_renderer_ID);
+    } catch (...) {
+        Core::Renderers::destroy(m_renderer_ID);
+        throw;
+    }
+}
+
+Renderer::~Renderer() {
+    Core::Renderers::destroy(m_renderer_ID);
+    delete m_impl;
+}
+
+Backend Renderer::get_backend(CameraID camera_ID) const { m_impl->conditional_per_camera_state_resize(camera_ID); return m_impl->per_camera_state[camera_ID].backend; }
+void Renderer::set_backend(CameraID camera_ID, Backend backend) {
+    if (backend == Backend::None) return;
+    m_impl->conditional_per_camera_state_resize(camera_ID);
+    auto& state = m_impl->per_camera_state[camera_ID];
+    state.backend = backend;
+    state.accumulations = 0u;
+}
+unsigned int Renderer::get_max_bounce_count(CameraID camera_ID) const { m_impl->conditional_per_camera_state_resize(camera_ID); return m_impl->per_camera_state[camera_ID].max_bounce_count; }
+void Renderer::set_max_bounce_count(CameraID camera_ID, unsigned int bounce_count) { m_impl->conditional_per_camera_state_resize(camera_ID); m_impl->per_camera_state[camera_ID].max_bounce_count = bounce_count; }
+unsigned int Renderer::get_max_accumulation_count(CameraID camera_ID) const { m_impl->conditional_per_camera_state_resize(camera_ID); return m_impl->per_camera_state[camera_ID].max_accumulation_count; }
+void Renderer::set_max_accumulation_count(CameraID camera_ID, unsigned int accumulation_count) { m_impl->conditional_per_camera_state_resize(camera_ID); m_impl->per_camera_state[camera_ID].max_accumulation_count = accumulation_count; }
+int Renderer::get_next_event_sample_count(SceneRootID) const { return m_impl->next_event_sample_count; }
+void Renderer::set_next_event_sample_count(SceneRootID, int sample_count) { m_impl->next_event_sample_count = sample_count < MAX_RNG_SAMPLE_OFFSETS ? sample_count : MAX_RNG_SAMPLE_OFFSETS; }
+PathRegularizationSettings Renderer::get_path_regularization_settings() const { return m_impl->path_regularization; }
+void Renderer::set_path_regularization_settings(PathRegularizationSettings settings) { m_impl->path_regularization = settings; }
+AIDenoiserFlags Renderer::get_AI_denoiser_flags() const { return m_impl->AI_denoiser_flags; }
+void Renderer::set_AI_denoiser_flags(AIDenoiserFlags flags) { m_impl->AI_denoiser_flags = flags; }
+void Renderer::handle_updates() { m_impl->handle_updates(); }
+unsigned int Renderer::render(CameraID camera_ID, optix::Buffer buffer, Vector2i frame_size) { return m_impl->render(camera_ID, buffer, frame_size, m_first_sample); }
+std::vector<Screenshot> Renderer::request_auxiliary_buffers(CameraID, Cameras::ScreenshotContent, Vector2i) {
+    printf("OptiXRenderer(B200): auxiliary buffers (AOV backends) are not implemented yet.\n");
+    return {};
+}
+optix::Context& Renderer::get_context() { return m_impl->context; }
+
+} // namespace OptiXRenderer
