@@ -197,7 +197,8 @@ def main():
             torch.cuda.synchronize()
 
     # Each rank renders its own contiguous range of sample indices (weak scaling: K samples per GPU).
-    first = rank * (K + Wm)
+    from bifrost3d_b200.sharding import sample_range
+    first = sample_range(rank, K, warmup=Wm)[0] - Wm
     # ---- device-timed region -----------------------------------------------------------------------
     ctx.render(cam, W, H, first, Wm, reset=True, **settings)  # warm-up
     barrier()
