@@ -220,65 +220,70 @@ __global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     TreeNode tn = tree[i];
-    int link[2], count[2];
+    int link[2];
     Aabb box[2];
     int child[2] = { tn.left, tn.right };
     for (int k = 0; k < 2; ++k) {
         if (child[k] < 0) {
-            link[k] = child[k]; count[k] = 1; box[k] = leaf_boxes[~child[k]];
+            link[k] = pack_leaf(~child[k], 1); box[k] = leaf_boxes[~child[k]];
         } else {
             TreeNode c = tree[child[k]];
             int size = c.last - c.first + 1;
             box[k] = node_boxes[child[k]];
-            if (size <= LEAF_MAX) { link[k] = ~c.first; count[k] = size; }
-            else { link[k] = child[k]; count[k] = 0; }
+            link[k] = size <= LEAF_MAX ? pack_leaf(c.first, size) : child[k];
         }
     }
     BvhNode out;
     out.lo_l_hi_l_x = make_float4(box[0].lo.x, box[0].lo.y, box[0].lo.z, box[0].hi.x);
     out.hi_l_lo_r = make_float4(box[0].hi.y, box[0].hi.z, box[1].lo.x, box[1].lo.y);
     out.lo_r_hi_r = make_float4(box[1].lo.z, box[1].hi.x, box[1].hi.y, box[1].hi.z);
-    out.left = link[0]; out.right = link[1]; out.left_count = count[0]; out.right_count = count[1];
+    out.left = link[0]; out.right = link[1]; out.pad0 = 0; out.pad1 = 0;
     nodes[i] = out;
 }
 
 __global__ void tiny_root_kernel(int n, const Aabb* __restrict__ leaf_boxes, BvhNode* __restrict__ nodes) {
-    // n == 0: both children absent. n == 1: the left child is the only triangle.
-    BvhNode out = {};
-    out.left = out.right = -1; out.left_count = out.right_count = -1;
+    // n == 0: both children absent. n == 1: the left child is the only triangle. An absent child is a point box at
+    // (3e38, 3e38, 3e38): for a normalised direction its slab distances are >= 3e38 in magnitude, outside any [tmin, tmax].
+    const float far = 3.0e38f;
+    BvhNode out;
+    out.lo_l_hi_l_x = make_float4(far, far, far, far);
+    out.hi_l_lo_r = make_float4(far, far, far, far);
+    out.lo_r_hi_r = make_float4(far, far, far, far);
+    out.left = out.right = NODE_EMPTY; out.pad0 = out.pad1 = 0;
     if (n == 1) {
         Aabb b = leaf_boxes[0];
         out.lo_l_hi_l_x = make_float4(b.lo.x, b.lo.y, b.lo.z, b.hi.x);
-        out.hi_l_lo_r = make_float4(b.hi.y, b.hi.z, 0.0f, 0.0f);
-        out.left = ~0; out.left_count = 1;
+        out.hi_l_lo_r = make_float4(b.hi.y, b.hi.z, far, far);
+        out.left = pack_leaf(0, 1);
     }
     nodes[0] = out;
 }
 
 // ---- batched queries -----------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel, int64_t n, const float* __restrict__ origins,
-                                                                const float* __restrict__ directions, const float* __restrict__ tmin,
-                                                                const float* __restrict__ tmax, const float* __restrict__ coverage,
-                                                                int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        Ray ray;
-        ray.origin = f3(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
-        ray.direction = f3(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
+struct BatchSource {
+    const float* origins; const float* directions; const float* tmin; const float* tmax;
+    int32_t* out_primitive; float* out_t; float* out_uv; uint8_t* out_occluded;
+    __device__ void load(unsigned int i, Ray& ray, int& skip) const {
+        ray.origin = f3(origins[3ll * i], origins[3ll * i + 1], origins[3ll * i + 2]);
+        ray.direction = f3(directions[3ll * i], directions[3ll * i + 1], directions[3ll * i + 2]);
         ray.tmin = tmin[i]; ray.tmax = tmax[i];
-        float transmission;
-        if (out_primitive || out_t || out_uv) {
-            Hit h = trace<false>(accel, ray, -1, s_stack + threadIdx.x, transmission, coverage);
-            if (out_primitive) out_primitive[i] = h.primitive;
-            if (out_t) out_t[i] = h.primitive >= 0 ? h.t : INFINITY;
-            if (out_uv) { out_uv[2 * i] = h.u; out_uv[2 * i + 1] = h.v; }
-        }
-        if (out_occluded) {
-            trace<true>(accel, ray, -1, s_stack + threadIdx.x, transmission, coverage);
-            out_occluded[i] = transmission < 1.0f ? 1 : 0;
-        }
+        skip = -1;
     }
+    __device__ void store(unsigned int i, const Traversal<false>& tr) const {
+        Hit h = tr.result();
+        if (out_primitive) out_primitive[i] = h.primitive;
+        if (out_t) out_t[i] = h.primitive >= 0 ? h.t : INFINITY;
+        if (out_uv) { out_uv[2ll * i] = h.u; out_uv[2ll * i + 1] = h.v; }
+    }
+    __device__ void store(unsigned int i, const Traversal<true>& tr) const { out_occluded[i] = tr.transmission < 1.0f ? 1 : 0; }
+};
+
+template <bool ANY_HIT>
+__global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel, unsigned int n, BatchSource source, const float* __restrict__ coverage,
+                                                                unsigned int* fetch_counter) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    traverse_queue<ANY_HIT>(accel, coverage, source, n, fetch_counter, s_stack + threadIdx.x);
 }
 
 } // namespace
@@ -339,8 +344,8 @@ int build_accel(Context* ctx) {
             for (int k = 0; k < 9; ++k) h_normal_matrices.push_back(float(det != 0.0 ? c[k] / det : (k % 4 == 0 ? 1.0 : 0.0)));
         }
         prim_total += mesh.primitive_count;
-        if (prim_total > 0x7ffffff0ll)
-            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_build_accel: more than 2^31 triangles");
+        if (prim_total > MAX_TRIANGLES)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_build_accel: more than 2^28 - 1 triangles");
     }
     const int n = int(prim_total);
 
@@ -432,7 +437,7 @@ int build_accel(Context* ctx) {
 int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* directions, const float* tmin, const float* tmax,
                     int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded) {
     if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_intersect: call bpt_build_accel first");
-    if (n < 0 || !origins || !directions || !tmin || !tmax) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_intersect: bad arguments");
+    if (n < 0 || n > 0x7fffffff || !origins || !directions || !tmin || !tmax) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_intersect: bad arguments");
     if (n == 0) return BPT_OK;
     cudaStream_t st = ctx->stream;
     std::vector<float> h_cov(ctx->host_materials.size());
@@ -455,9 +460,18 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     if (out_uv) Q_CHECK(cudaMalloc((void**)&d_uv, 2 * n * sizeof(float)));
     if (out_occluded) Q_CHECK(cudaMalloc((void**)&d_occ, n));
     AccelView view = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr };
-    int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 16);
-    intersect_kernel<<<grid, TRACE_BLOCK, 0, st>>>(view, n, d_o, d_d, d_tmin, d_tmax, d_cov, d_prim, d_t, d_uv, d_occ);
-    ctx->counters.kernel_launches++;
+    int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 8);
+    BatchSource source = { d_o, d_d, d_tmin, d_tmax, d_prim, d_t, d_uv, d_occ };
+    unsigned int* d_fetch = reinterpret_cast<unsigned int*>(ctx->device_counters + 4); // two scratch fetch counters
+    Q_CHECK(cudaMemsetAsync(d_fetch, 0, 2 * sizeof(unsigned int), st));
+    if (out_primitive || out_t || out_uv) {
+        intersect_kernel<false><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch);
+        ctx->counters.kernel_launches++;
+    }
+    if (out_occluded) {
+        intersect_kernel<true><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch + 1);
+        ctx->counters.kernel_launches++;
+    }
     Q_CHECK(cudaGetLastError());
     if (out_primitive) Q_CHECK(cudaMemcpyAsync(out_primitive, d_prim, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (out_t) Q_CHECK(cudaMemcpyAsync(out_t, d_t, n * sizeof(float), cudaMemcpyDeviceToHost, st));

@@ -42,15 +42,15 @@ struct HostMesh {
     int vertex_count = 0;
 };
 
-// BVH node, 64 bytes, two children per node: child AABBs are stored in the parent so one 64 byte
-// (4 x 128-bit) load decides both children. A negative child index c encodes a leaf: ~c = first
-// triangle slot; leaf triangle counts are in `counts` (0 for inner children).
+// BVH node, 64 bytes, two children per node: the child AABBs are stored in the parent so one 64 byte (4 x 128-bit)
+// load decides both children. A link >= 0 is a child node index; a negative link is a leaf packed as
+// ~(first_triangle | (count - 1) << 28) (bpt_trace.cuh: pack_leaf). An absent child is a far-away point box.
 struct __align__(16) BvhNode {
     float4 lo_l_hi_l_x;   // left.lo.x, left.lo.y, left.lo.z, left.hi.x
     float4 hi_l_lo_r;     // left.hi.y, left.hi.z, right.lo.x, right.lo.y
     float4 lo_r_hi_r;     // right.lo.z, right.hi.x, right.hi.y, right.hi.z
-    int left, right;      // child node index, or ~first_triangle for leaves
-    int left_count, right_count;
+    int left, right;
+    int pad0, pad1;
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 

@@ -32,7 +32,9 @@ struct QueueCounters {
     unsigned int active;       // entries in the current extend/shade queue
     unsigned int next_active;  // entries appended for the next iteration
     unsigned int shadow;       // entries in the shadow queue
-    unsigned int pad;
+    unsigned int fetch_extend; // dynamic ray fetch cursors of the two traversal kernels
+    unsigned int fetch_shadow;
+    unsigned int pad[3];
 };
 
 struct Wavefront {
@@ -131,60 +133,76 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.counters->active = (unsigned int)pixel_count;
         w.counters->next_active = 0;
         w.counters->shadow = 0;
+        w.counters->fetch_extend = 0;
+        w.counters->fetch_shadow = 0;
     }
 }
 
 // ---- extend: closest hit over triangles and analytic lights -------------------------------------------------
 
-__global__ void __launch_bounds__(TRACE_BLOCK) extend_kernel(WavefrontView w, SceneView s) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    const unsigned int count = w.counters->active;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+struct ExtendSource {
+    WavefrontView w;
+    const Light* __restrict__ lights;
+    int analytic_light_count;
+    __device__ void load(unsigned int i, Ray& ray, int& skip) const {
         unsigned int pixel = w.queue_in[i];
         float4 o = w.ray_o[pixel], d = w.ray_d[pixel];
-        int previous_primitive = __float_as_int(w.rad[pixel].w);
-        Ray ray;
         ray.origin = f3(o); ray.tmin = o.w; ray.direction = f3(d); ray.tmax = RT_DEFAULT_MAX;
-        float transmission;
-        Hit h = trace<false>(s.accel, ray, previous_primitive, s_stack + threadIdx.x, transmission, s.coverage);
+        skip = __float_as_int(w.rad[pixel].w); // the primitive the path is leaving (MonteCarlo.cu:137-142)
+    }
+    __device__ void store(unsigned int i, const Traversal<false>& tr) const {
+        Hit h = tr.result();
         float t_closest = h.primitive >= 0 ? h.t : RT_DEFAULT_MAX;
         // Analytic sphere / disk lights (LightSources.cu:31-70): intersectable by MonteCarlo rays only.
-        for (int l = 0; l < s.analytic_light_count; ++l) {
-            Light light = s.lights[l];
+        for (int l = 0; l < analytic_light_count; ++l) {
+            Light light = lights[l];
             float t = -1e30f, radius = 0.0f;
             if (light_type(light) == BPT_LIGHT_SPHERE) {
                 SphereLight sl = as_sphere(light); radius = sl.radius;
-                t = isect::ray_sphere(ray.origin, ray.direction, sl.position, sl.radius);
+                t = isect::ray_sphere(tr.ray.origin, tr.ray.direction, sl.position, sl.radius);
             } else if (light_type(light) == BPT_LIGHT_SPOT) {
                 SpotLight sp = as_spot(light); radius = sp.radius;
-                t = isect::ray_disk(ray.origin, ray.direction, sp.position, sp.direction, sp.radius);
+                t = isect::ray_disk(tr.ray.origin, tr.ray.direction, sp.position, sp.direction, sp.radius);
             }
-            if (radius > 0.0f && t > ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
+            if (radius > 0.0f && t > tr.ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
         }
-        w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
+        w.hit[w.queue_in[i]] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
     }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK) extend_kernel(WavefrontView w, SceneView s) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    const unsigned int count = w.counters->active;
+    ExtendSource source = { w, s.lights, s.analytic_light_count };
+    traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
 
 // ---- shadow: accumulated transmission along the light sample's segment ---------------------------------------
 
-__global__ void __launch_bounds__(TRACE_BLOCK) shadow_kernel(WavefrontView w, SceneView s) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    const unsigned int count = w.counters->shadow;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+struct ShadowSource {
+    WavefrontView w;
+    __device__ void load(unsigned int i, Ray& ray, int& skip) const {
         float4 o = w.sh_o[i], d = w.sh_d[i];
-        Ray ray;
         ray.origin = f3(o); ray.tmin = 0.0f; ray.direction = f3(d); ray.tmax = o.w;
-        float transmission;
-        trace<true>(s.accel, ray, -1, s_stack + threadIdx.x, transmission, s.coverage);
-        if (transmission > 0.0f) {
-            unsigned int pixel = __float_as_uint(d.w);
+        skip = -1;
+    }
+    __device__ void store(unsigned int i, const Traversal<true>& tr) const {
+        if (tr.transmission > 0.0f) {
+            unsigned int pixel = __float_as_uint(w.sh_d[i].w);
             float4 rad = w.rad[pixel];
             float4 l = w.sh_rad[i];
-            rad.x += l.x * transmission; rad.y += l.y * transmission; rad.z += l.z * transmission;
+            rad.x += l.x * tr.transmission; rad.y += l.y * tr.transmission; rad.z += l.z * tr.transmission;
             w.rad[pixel] = rad;
         }
     }
+};
+
+__global__ void __launch_bounds__(TRACE_BLOCK) shadow_kernel(WavefrontView w, SceneView s) {
+    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    const unsigned int count = w.counters->shadow;
+    ShadowSource source = { w };
+    traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
 }
 
@@ -193,6 +211,8 @@ __global__ void advance_kernel(QueueCounters* c) {
     c->active = c->next_active;
     c->next_active = 0;
     c->shadow = 0;
+    c->fetch_extend = 0;
+    c->fetch_shadow = 0;
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------

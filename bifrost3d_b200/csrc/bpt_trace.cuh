@@ -1,17 +1,21 @@
-// Ray traversal of the two-wide BVH: closest hit and any hit. Replaces OptiX' proprietary Trbvh/RTX
-// traversal that the reference configures at Renderer.cpp:116-135,161-182,470-477 and queries with rtTrace
-// (SimpleRGPs.cu:114-125).
+// Ray traversal of the two-wide BVH: closest hit and any hit. Replaces OptiX' proprietary Trbvh/RTX traversal that the
+// reference configures at Renderer.cpp:116-135,161-182,470-477 and queries with rtTrace (SimpleRGPs.cu:114-125).
 //
 // * Nodes are 64 bytes and hold both children's boxes: one node visit = four 128-bit loads.
 // * Triangles are 48 bytes (three float4 world-space vertices) in Morton order: three 128-bit loads.
-// * The ray/triangle test is the watertight test of Woop, Benthin and Wald (JCGT 2013): shear to ray space,
-//   2D edge functions with an fp64 fallback when an edge function is exactly zero. It is evaluated with
-//   explicitly rounded operations (no FMA contraction) so the CPU oracle reproduces t and the barycentrics
-//   bit for bit; shared edges evaluate to exact negations of each other, which is what makes it watertight.
-// * Closest hit is the minimum over (t, global primitive index): ties in t resolve to the lower index so that
-//   the result does not depend on traversal order.
-// * The traversal stack lives in shared memory (STACK_SMEM entries per thread, column layout so that a warp's
-//   accesses hit 32 different banks); deeper paths spill to a per-thread local array.
+// * The ray/triangle test is the watertight test of Woop, Benthin and Wald (JCGT 2013): shear to ray space, 2D edge
+//   functions with an fp64 fallback when an edge function is exactly zero. It is evaluated with explicitly rounded
+//   operations (no FMA contraction) so the CPU oracle reproduces t and the barycentrics bit for bit; shared edges
+//   evaluate to exact negations of each other, which is what makes it watertight.
+// * Closest hit is the minimum over (t, global primitive index): ties in t resolve to the lower index so that the
+//   result does not depend on traversal order.
+// * Control flow is "while-while" (Aila and Laine, HPG 2009): a warp first runs inner-node steps until every lane that is
+//   still searching has reached a leaf, then intersects leaves together; leaves travel through the stack like nodes.
+// * Persistent threads with dynamic ray fetch: a lane whose ray has terminated takes the next ray of the queue (one
+//   atomicAdd per warp for all idle lanes) every TRAVERSAL_BUDGET node visits instead of idling until the slowest ray of
+//   its warp finishes.
+// * The traversal stack lives in shared memory (STACK_SMEM entries per thread, column layout so that a warp's accesses
+//   hit 32 different banks); deeper paths spill to a per-thread local array.
 #pragma once
 #include "bpt_context.h"
 #include "bpt_math.cuh"
@@ -104,6 +108,15 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
 constexpr int TRACE_BLOCK = 128;
 constexpr int STACK_SMEM = 24;
 constexpr int STACK_LOCAL = 72;
+constexpr int TRAVERSAL_BUDGET = 48;          // node visits between two refills of a warp's idle lanes
+constexpr int NODE_EMPTY = (int)0x80000000;   // "no node": neither an inner index (>= 0) nor a leaf (~packed)
+
+// Leaf link: ~(first_triangle | (count - 1) << 28), always in [-2^30, -1].
+BPT_HD int pack_leaf(int first, int count) { return ~(first | ((count - 1) << 28)); }
+BPT_HD bool is_leaf(int link) { return link < 0 && link != NODE_EMPTY; }
+BPT_HD int leaf_first(int link) { return (~link) & 0x0fffffff; }
+BPT_HD int leaf_count(int link) { return ((~link) >> 28) + 1; }
+constexpr int MAX_TRIANGLES = 0x0fffffff;
 
 struct TraversalStack {
     int* smem;                // [STACK_SMEM][TRACE_BLOCK], this thread's column
@@ -115,6 +128,7 @@ struct TraversalStack {
         ++sp;
     }
     BPT_D int pop() {
+        if (sp == 0) return NODE_EMPTY;
         --sp;
         return sp < STACK_SMEM ? smem[sp * TRACE_BLOCK] : local[min(sp - STACK_SMEM, STACK_LOCAL - 1)];
     }
@@ -129,6 +143,7 @@ BPT_D float4 ldg4(const float4* p) { return __ldg(p); }
 
 // Slab test against one child box. Conservative: the far distance is padded by a few ulp (Ize, "Robust BVH ray
 // traversal", JCGT 2013) and the near one shrunk, so a triangle the watertight test would accept is never culled.
+// An absent child (scenes with fewer than two triangles) is a point box at 3e38 and never passes.
 BPT_D bool slab(float3 lo, float3 hi, float3 o, float3 inv_d, float tmin, float tmax, float& tnear) {
     float t0x = (lo.x - o.x) * inv_d.x, t1x = (hi.x - o.x) * inv_d.x;
     float t0y = (lo.y - o.y) * inv_d.y, t1y = (hi.y - o.y) * inv_d.y;
@@ -141,100 +156,134 @@ BPT_D bool slab(float3 lo, float3 hi, float3 o, float3 inv_d, float tmin, float 
     return tn <= tf;
 }
 
+// Everything one lane needs to carry a ray through the hierarchy.
 template <bool ANY_HIT>
-BPT_D void intersect_leaf(const AccelView& a, int first, int count, const RayShear& shear, const Ray& ray, Hit& hit, float& tmax,
-                          int skip_primitive, float& transmission, const float* __restrict__ coverage_by_material) {
-    for (int i = 0; i < count; ++i) {
-        const float4* tri = reinterpret_cast<const float4*>(a.triangles + first + i);
-        float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
-        int primitive = __float_as_int(v0.w);
-        if (primitive == skip_primitive)
-            continue;
-        float t, u, v;
-        if (!watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v))
-            continue;
-        if (ANY_HIT) {
-            if (t > ray.tmin && t < ray.tmax) {
-                // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
-                float coverage = coverage_by_material[__float_as_int(v1.w)];
-                transmission *= 1.0f - coverage;
-                if (transmission < 0.0000001f) { transmission = 0.0f; hit.primitive = primitive; hit.t = t; tmax = -1.0f; return; }
-            }
-        } else {
-            if (t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
-                // NB hit.t starts at ray.tmax and hit.primitive at INT_MAX, so t must be < tmax for a first hit.
+struct Traversal {
+    Ray ray;
+    RayShear shear;
+    float3 inv_d;
+    float tmax;          // closest hit: shrinks to the best t; any hit: < 0 once the ray is blocked
+    Hit hit;
+    float transmission;
+    int skip_primitive;
+    int node;
+    TraversalStack stack;
+
+    BPT_D void begin(const Ray& r, int skip) {
+        ray = r;
+        shear = make_ray_shear(r.direction);
+        inv_d = f3(1.0f / r.direction.x, 1.0f / r.direction.y, 1.0f / r.direction.z);
+        tmax = r.tmax;
+        hit.t = r.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
+        transmission = 1.0f;
+        skip_primitive = skip;
+        stack.sp = 0;
+        node = 0; // root
+    }
+
+    // One inner-node visit: tests both children, descends into the nearer hit child, defers the other.
+    BPT_D void inner_step(const AccelView& a) {
+        const float4* n = reinterpret_cast<const float4*>(a.nodes + node);
+        float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2);
+        int2 links = __ldg(reinterpret_cast<const int2*>(n + 3));
+        float tn_l, tn_r;
+        bool hit_l = slab(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), ray.origin, inv_d, ray.tmin, tmax, tn_l);
+        bool hit_r = slab(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), ray.origin, inv_d, ray.tmin, tmax, tn_r);
+        if (hit_l && hit_r) {
+            bool left_first = tn_l <= tn_r;
+            node = left_first ? links.x : links.y;
+            stack.push(left_first ? links.y : links.x);
+        } else if (hit_l)
+            node = links.x;
+        else if (hit_r)
+            node = links.y;
+        else
+            node = stack.pop();
+    }
+
+    BPT_D void leaf_step(const AccelView& a, const float* __restrict__ coverage_by_material) {
+        const int first = leaf_first(node), count = leaf_count(node);
+        for (int i = 0; i < count; ++i) {
+            const float4* tri = reinterpret_cast<const float4*>(a.triangles + first + i);
+            float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
+            int primitive = __float_as_int(v0.w);
+            if (primitive == skip_primitive)
+                continue;
+            float t, u, v;
+            if (!watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v))
+                continue;
+            if (ANY_HIT) {
+                if (t > ray.tmin && t < ray.tmax) {
+                    // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
+                    float coverage = coverage_by_material[__float_as_int(v1.w)];
+                    transmission *= 1.0f - coverage;
+                    if (transmission < 0.0000001f) { transmission = 0.0f; node = NODE_EMPTY; stack.sp = 0; return; }
+                }
+            } else if (t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
+                // hit.t starts at ray.tmax and hit.primitive at INT_MAX, so a first hit needs t < tmax.
                 hit.t = t; hit.primitive = primitive; hit.u = u; hit.v = v;
                 tmax = t;
             }
         }
+        node = stack.pop();
     }
-}
 
-// Closest hit (ANY_HIT = false) or accumulated transmission along [tmin, tmax] (ANY_HIT = true).
-// `stack_smem` points at this thread's column of a [STACK_SMEM][TRACE_BLOCK] shared array.
-template <bool ANY_HIT>
-BPT_D Hit trace(const AccelView& a, const Ray& ray, int skip_primitive, int* stack_smem, float& transmission,
-                const float* __restrict__ coverage_by_material) {
-    Hit hit;
-    hit.t = ray.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
-    transmission = 1.0f;
-    float tmax = ray.tmax; // shrinks as closer hits are found; ties (t == tmax) must still be visited
+    // Runs up to `budget` inner-node visits (and the leaves met on the way). Returns when the ray is done or the budget
+    // is used up; `node == NODE_EMPTY` tells which.
+    BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget) {
+        while (node != NODE_EMPTY && budget > 0) {
+            while (node >= 0 && budget > 0) { inner_step(a); --budget; }
+            while (is_leaf(node)) leaf_step(a, coverage_by_material);
+        }
+    }
 
-    const RayShear shear = make_ray_shear(ray.direction);
-    const float3 inv_d = f3(1.0f / ray.direction.x, 1.0f / ray.direction.y, 1.0f / ray.direction.z);
+    BPT_D Hit result() const {
+        Hit h = hit;
+        if (!ANY_HIT && h.primitive == 0x7fffffff) h.primitive = -1;
+        return h;
+    }
+};
 
-    TraversalStack stack;
-    stack.smem = stack_smem;
-    stack.sp = 0;
+// Persistent-thread driver. `Source` supplies rays and consumes results:
+//   bool load(unsigned int index, Ray& ray, int& skip_primitive)
+//   void store(unsigned int index, const Traversal<ANY_HIT>& traversal)
+// `fetch_counter` is a zero-initialised global counter shared by all CTAs of the launch. Must be called by whole warps.
+template <bool ANY_HIT, class Source>
+BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
+                          unsigned int* fetch_counter, int* stack_smem) {
+    Traversal<ANY_HIT> tr;
+    tr.stack.smem = stack_smem;
+    tr.stack.sp = 0;
+    tr.node = NODE_EMPTY;
+    unsigned int index = 0;
+    bool has_ray = false, exhausted = false;
+    const int lane = threadIdx.x & 31;
 
-    int node_index = 0;
     while (true) {
-        const float4* n = reinterpret_cast<const float4*>(a.nodes + node_index);
-        float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2);
-        int4 links = __ldg(reinterpret_cast<const int4*>(n + 3));
-
-        float tn_l, tn_r;
-        bool hit_l = slab(f3(n0.x, n0.y, n0.z), f3(n0.w, n1.x, n1.y), ray.origin, inv_d, ray.tmin, tmax, tn_l);
-        bool hit_r = slab(f3(n1.z, n1.w, n2.x), f3(n2.y, n2.z, n2.w), ray.origin, inv_d, ray.tmin, tmax, tn_r);
-        hit_l = hit_l && links.z >= 0; // count -1 marks an absent child
-        hit_r = hit_r && links.w >= 0;
-
-        // Leaves are intersected on the spot; inner children are descended into, nearest first.
-        if (hit_l && links.z > 0) {
-            intersect_leaf<ANY_HIT>(a, ~links.x, links.z, shear, ray, hit, tmax, skip_primitive, transmission, coverage_by_material);
-            hit_l = false;
+        // Retire finished rays and refill idle lanes: one atomic per warp.
+        if (has_ray && tr.node == NODE_EMPTY) { source.store(index, tr); has_ray = false; }
+        unsigned int idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
+        if (idle) {
+            int leader = __ffs(idle) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(fetch_counter, __popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!has_ray && !exhausted) {
+                index = base + __popc(idle & ((1u << lane) - 1u));
+                if (index < count) {
+                    Ray ray; int skip;
+                    source.load(index, ray, skip);
+                    tr.begin(ray, skip);
+                    has_ray = true;
+                } else
+                    exhausted = true;
+            }
         }
-        if (hit_r && links.w > 0) {
-            if (!ANY_HIT && tn_r > tmax) { /* culled by the hit just found in the left leaf */ }
-            else intersect_leaf<ANY_HIT>(a, ~links.y, links.w, shear, ray, hit, tmax, skip_primitive, transmission, coverage_by_material);
-            hit_r = false;
-        }
-        if (ANY_HIT && tmax < 0.0f)
+        if (__ballot_sync(0xffffffffu, has_ray) == 0)
             break;
-        if (!ANY_HIT) {
-            // re-test inner children against the possibly shortened interval
-            hit_l = hit_l && tn_l <= tmax;
-            hit_r = hit_r && tn_r <= tmax;
-        }
-
-        if (hit_l && hit_r) {
-            bool left_first = tn_l <= tn_r;
-            node_index = left_first ? links.x : links.y;
-            stack.push(left_first ? links.y : links.x);
-        } else if (hit_l) {
-            node_index = links.x;
-        } else if (hit_r) {
-            node_index = links.y;
-        } else {
-            if (stack.sp == 0)
-                break;
-            node_index = stack.pop();
-        }
+        if (has_ray)
+            tr.run(a, coverage_by_material, TRAVERSAL_BUDGET);
     }
-
-    if (!ANY_HIT && hit.primitive == 0x7fffffff)
-        hit.primitive = -1;
-    return hit;
 }
 
 } // namespace bpt
