@@ -14,7 +14,8 @@ class BptError(RuntimeError):
 
 
 def library_path() -> Path:
-    return _PKG / "libbpt.so"
+    # BPT_LIB selects an alternative build of the same library (kernel tuning experiments); the default is the product.
+    return Path(os.environ["BPT_LIB"]) if os.environ.get("BPT_LIB") else _PKG / "libbpt.so"
 
 
 class Material(C.Structure):  # Types.h:353-416

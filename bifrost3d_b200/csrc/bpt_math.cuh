@@ -9,6 +9,9 @@
 
 #define BPT_HD __host__ __device__ __forceinline__
 #define BPT_D __device__ __forceinline__
+// Large shading routines that are called from several places: one out-of-line copy keeps the shade kernel's code inside
+// the instruction cache (ncu: 'stalled_no_instruction' was the top stall reason with everything inlined).
+#define BPT_CALL static __device__ __noinline__
 
 namespace bpt {
 

@@ -281,7 +281,10 @@ __device__ LightSample sample_single_light(const SceneView& s, const ShadingTabl
     return ls;
 }
 
-__global__ void __launch_bounds__(SHADE_BLOCK) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
+#ifndef BPT_SHADE_MIN_BLOCKS
+#define BPT_SHADE_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
     __shared__ __align__(16) float s_tables[3 * TABLE_FLOATS];
     for (int i = threadIdx.x; i < 3 * TABLE_FLOATS; i += blockDim.x) s_tables[i] = s.tables[i];
     __syncthreads();
@@ -617,7 +620,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
 
     // Persistent grids: a whole number of CTAs per SM.
     const int trace_grid = ctx->sm_count * 8;
-    const int shade_grid = ctx->sm_count * 4;
+    const int shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
     const int stream_grid = ctx->sm_count * 8;
 
     for (uint32_t k = 0; k < sample_count; ++k) {

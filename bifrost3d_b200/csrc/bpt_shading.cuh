@@ -52,13 +52,13 @@ struct DirectionalSample { float3 direction; float pdf; };
 // is only accurate to a few ulp, and the two call sites (Oren-Nayar lobe selection probability, coat
 // roughness modulation) feed cancellation-prone expressions, so the extra fp64 work buys parity. Both are
 // evaluated once per shading setup, not per BSDF evaluation.
-BPT_D float powf_exact(float x, float y) { return (float)pow((double)x, (double)y); }
+BPT_CALL float powf_exact(float x, float y) { return (float)pow((double)x, (double)y); }
 
 // sin/cos of a float angle evaluated in double precision and rounded once: correctly rounded results, which
 // is what the oracle's glibc sinf/cosf deliver in all but ~1e-3 of cases (CUDA's sincosf is 2 ulp). Several
 // samplers square and subtract the results (sqrt(1 - x*x - y*y) in the clipped-LTC and VNDF samplers), which
 // amplifies a 1 ulp difference beyond the 1e-5 parity bound; B200's FP64 rate (half of FP32) makes this cheap.
-BPT_D void sincos_(float theta, float& s, float& c) {
+BPT_CALL void sincos_(float theta, float& s, float& c) {
     double sd, cd;
     sincos((double)theta, &sd, &cd);
     s = (float)sd; c = (float)cd;
@@ -362,14 +362,14 @@ BPT_D Pdf pdf(float alpha, float3 wo, float3 wi) {
     return Pdf(dist::ggx_bounded_vndf_reflection_pdf(alpha, wo, wi));
 }
 
-BPT_D BsdfResponse evaluate_with_pdf(float alpha, float3 specularity, float3 wo, float3 wi) {
+BPT_CALL BsdfResponse evaluate_with_pdf(float alpha, float3 specularity, float3 wo, float3 wi) {
     BsdfResponse r;
     r.reflectance = evaluate(alpha, specularity, wo, wi);
     r.pdf = pdf(alpha, wo, wi);
     return r;
 }
 
-BPT_D BsdfSample sample(float alpha, float3 specularity, float3 wo, float2 u) {
+BPT_CALL BsdfSample sample(float alpha, float3 specularity, float3 wo, float2 u) {
     BsdfSample s;
     if (ggx::effectively_smooth(alpha)) {
         s.direction = f3(-wo.x, -wo.y, wo.z);
@@ -439,14 +439,14 @@ BPT_D Pdf pdf(float roughness, float roughness_factor, float3 wo, float3 wi) {
     return Pdf(uniform_probability * uniform_PDF + cltc_probability * cltc_PDF);
 }
 
-BPT_D BsdfResponse evaluate_with_pdf(float3 albedo, float roughness, float roughness_factor, float3 wo, float3 wi) {
+BPT_CALL BsdfResponse evaluate_with_pdf(float3 albedo, float roughness, float roughness_factor, float3 wo, float3 wi) {
     BsdfResponse r;
     r.reflectance = albedo * evaluate(roughness, wo, wi);
     r.pdf = pdf(roughness, roughness_factor, wo, wi);
     return r;
 }
 
-BPT_D BsdfSample sample(float3 albedo, float roughness, float roughness_factor, float3 wo, float2 u) {
+BPT_CALL BsdfSample sample(float3 albedo, float roughness, float roughness_factor, float3 wo, float2 u) {
     float uniform_probability = uniform_lobe_probability(roughness_factor, wo.z);
     float cltc_probability = 1.0f - uniform_probability;
 
