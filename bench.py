@@ -51,8 +51,14 @@ def build_scene(name):
         return scenes.cornell_box(), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
     if name == "cornell_small":
         return scenes.cornell_box(sphere_quads=(24, 12), width=256, height=256), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
-    if hasattr(scenes, name):
-        return getattr(scenes, name)()
+    if name == "materials":      # configs[2]: 10x10 material grid + HDR environment, 1920x1080
+        return scenes.material_grid(), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
+    if name == "materials_small":
+        return scenes.material_grid(320, 180, grid=4, sphere_quads=(24, 12), env_size=(256, 128), env_samples=512), {"max_bounces": 4, "nee_samples": 3, "pdf_scale": 0.5}
+    if name == "terrain":        # configs[3]: 50M triangles, 3840x2160, 8 bounces
+        return scenes.instanced_terrain(), {"max_bounces": 8, "nee_samples": 3, "pdf_scale": 0.5}
+    if name == "terrain_small":
+        return scenes.instanced_terrain(480, 270, (5, 4), 32, 3), {"max_bounces": 8, "nee_samples": 3, "pdf_scale": 0.5}
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -148,7 +154,7 @@ def workload_config(args, scene, settings):
     from bifrost3d_b200 import scenes
     return {"workload": f"{scene['name']}: {scene['width']}x{scene['height']}, {scenes.triangle_count(scene)} triangles, {len(scene['lights'])} light(s), "
                         f"max_bounce_count {settings['max_bounces']}, next_event_sample_count {settings['nee_samples']}, 1 sample per pixel per step",
-            "baseline_config": "configs[1] (SmallPT-style Cornell box)" if args.workload == "cornell" else args.workload,
+            "baseline_config": {"cornell": "configs[1] (SmallPT-style Cornell box)", "materials": "configs[2] (material grid + HDR environment, 1080p)", "terrain": "configs[3] (50M-triangle instanced scene, 4K, 8 bounces)"}.get(args.workload, args.workload),
             "l2_policy": "per-step working set (path state + frame buffers) exceeds L2; no explicit flush",
             "parallelism": f"sample-index sharding x{args.gpus}, replicated BVH"}
 

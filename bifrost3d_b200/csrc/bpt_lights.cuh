@@ -279,7 +279,7 @@ BPT_D float3 fetch_bilinear(const EnvironmentView& e, float2 uv) {
 BPT_D float fetch_pdf_nearest(const EnvironmentView& e, float2 uv) {
     int x = int(floorf(uv.x * e.pdf_width));
     int y = int(floorf(uv.y * e.pdf_height));
-    x = ((x % e.pdf_width) + e.pdf_width) % e.pdf_width;
+    x = max(0, min(e.pdf_width - 1, x)); // RT_WRAP_CLAMP_TO_EDGE in both directions (PresampledEnvironmentMap.cpp:46-47)
     y = max(0, min(e.pdf_height - 1, y));
     return e.per_pixel_pdf[y * e.pdf_width + x];
 }

@@ -200,6 +200,54 @@ def cornell_box(sphere_quads=(100, 50), width=1024, height=1024):
             "environment": {"tint": (0.0, 0.0, 0.0)}, "camera": camera, "width": width, "height": height}
 
 
+def material_grid(width=1920, height=1080, grid=10, sphere_quads=(100, 50), env_size=(2048, 1024), env_samples=8192):
+    """BASELINE.json configs[2]: grid x grid DefaultMaterial spheres sweeping roughness (x) and metallic (z) on a ground plane,
+    lit by a procedural HDR environment with importance sampling + MIS (~1M triangles at the default tessellation)."""
+    from . import environment
+    meshes = {0: plane(1), 1: revolved_sphere(*sphere_quads)}
+    mats = [material((0, 0, 0), 0.0), material((0.5, 0.5, 0.5), 0.9, 0.02)]
+    instances = [_instance(0, 1, affine((0, 0, 0), None, 3.0 * grid))]
+    spacing = 1.25
+    for j in range(grid):
+        for i in range(grid):
+            mats.append(material((0.8, 0.5, 0.3), i / max(grid - 1, 1), 0.04, metallic=j / max(grid - 1, 1)))
+            pos = ((i - (grid - 1) / 2) * spacing, 0.5, (j - (grid - 1) / 2) * spacing)
+            instances.append(_instance(1, len(mats) - 1, affine(pos)))
+    env = environment.build_environment(environment.procedural_sky(*env_size), sample_count=env_samples)
+    rot = quat_from_angle_axis(np.radians(32.0), (1, 0, 0))
+    extent = grid * spacing
+    camera = perspective_camera((0.0, 0.62 * extent + 1.0, -0.95 * extent - 1.0), rot, np.radians(45.0), width / height)
+    return {"name": "material_grid", "meshes": meshes, "materials": np.array(mats, capi.MATERIAL_DTYPE),
+            "instances": np.array(instances, capi.INSTANCE_DTYPE), "lights": np.zeros(0, capi.LIGHT_DTYPE),
+            "environment": env, "camera": camera, "width": width, "height": height}
+
+
+def instanced_terrain(width=3840, height=2160, instances_per_side=(25, 20), quads_per_edge=224, distinct_meshes=8):
+    """BASELINE.json configs[3]: displaced meshes (2 * quads^2 triangles each) instanced on a jittered grid with random rigid
+    transforms, 16 materials, sphere + spot + directional lights. Defaults: 500 instances x 100 352 triangles = 50.2M."""
+    rng = np.random.default_rng(13)
+    meshes = {k: displaced_grid(quads_per_edge, seed=11 + k) for k in range(distinct_meshes)}
+    mats = [material((0, 0, 0), 0.0)]
+    for k in range(16):
+        mats.append(material(tuple(0.25 + 0.6 * rng.random(3)), 0.1 + 0.9 * (k % 4) / 3.0, 0.04, metallic=float(k // 4) / 3.0))
+    nx, nz = instances_per_side
+    inst = []
+    for iz in range(nz):
+        for ix in range(nx):
+            jitter = rng.uniform(-0.08, 0.08, 2)
+            pos = ((ix - (nx - 1) / 2) * 0.98 + jitter[0], rng.uniform(-0.02, 0.02), (iz - (nz - 1) / 2) * 0.98 + jitter[1])
+            rot = quat_from_angle_axis(rng.uniform(0, 2 * np.pi), (rng.normal(scale=0.06), 1.0, rng.normal(scale=0.06)))
+            inst.append(_instance(int(rng.integers(0, distinct_meshes)), 1 + int(rng.integers(0, 16)), affine(pos, rot, 1.05)))
+    lights = np.array([sphere_light((400.0, 380.0, 350.0), (0.0, 6.0, 0.0), 0.5),
+                       spot_light((300.0, 300.0, 360.0), (-6.0, 5.0, -4.0), 0.2, (0.7, -0.6, 0.4), 0.8),
+                       directional_light((1.2, 1.1, 1.0), (0.3, -1.0, 0.2))], capi.LIGHT_DTYPE)
+    rot = quat_from_angle_axis(np.radians(38.0), (1, 0, 0))
+    camera = perspective_camera((0.0, 9.5, -13.5), rot, np.radians(45.0), width / height)
+    return {"name": "instanced_terrain", "meshes": meshes, "materials": np.array(mats, capi.MATERIAL_DTYPE),
+            "instances": np.array(inst, capi.INSTANCE_DTYPE), "lights": lights, "environment": {"tint": (0.02, 0.03, 0.05)},
+            "camera": camera, "width": width, "height": height}
+
+
 def random_triangles(n, seed, extent=1.0, size=0.2):
     """Triangle soup for traversal parity tests."""
     rng = np.random.default_rng(seed)

@@ -382,7 +382,7 @@ inline float3 env_fetch_bilinear(const EnvironmentIn& e, float2 uv) {
 }
 inline float env_fetch_pdf(const EnvironmentIn& e, float2 uv) {
     int x = int(floorf(uv.x * e.pdf_width)), y = int(floorf(uv.y * e.pdf_height));
-    x = ((x % e.pdf_width) + e.pdf_width) % e.pdf_width;
+    x = std::max(0, std::min(e.pdf_width - 1, x)); // RT_WRAP_CLAMP_TO_EDGE, PresampledEnvironmentMap.cpp:46-47
     y = std::max(0, std::min(e.pdf_height - 1, y));
     return e.pdf[y * e.pdf_width + x];
 }

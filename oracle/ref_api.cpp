@@ -35,7 +35,11 @@
 #undef private
 
 #include <Bifrost/Assets/Shading/Fittings.h>
+#include <Bifrost/Assets/Image.h>
+#include <Bifrost/Assets/InfiniteAreaLight.h>
+#include <Bifrost/Assets/Texture.h>
 #include <Bifrost/Math/OctahedralNormal.h>
+#include <Bifrost/Math/RNG.h>
 
 #include <omp.h>
 #include <cstdint>
@@ -264,6 +268,58 @@ void ref_light_sample_pdf_evaluate(int64_t n, const void* lights, int light_stri
         out_pdf[i] = pdf.m_PDF;
         st3(out_radiance, i, e);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Environment map: the reference's own CPU build of the sampling data (run once per environment).
+//   per pixel PDF : Assets::InfiniteAreaLight ctor (InfiniteAreaLight.cpp:24-110: (r+g+b)*sin(theta) importance, 3x3 tent filter,
+//                   Distribution2D CDFs) + reconstruct_solid_angle_PDF_sans_sin_theta (InfiniteAreaLight.cpp:140-157)
+//   light samples : PresampledEnvironmentMap ctor (PresampledEnvironmentMap.cpp:60-96): PMJ blue-noise points in
+//                   bit-reversed order through InfiniteAreaLight::sample (InfiniteAreaLight.h:90-101)
+// texels: width*height RGBA float, latlong. per_pixel_pdf must hold width * max(height, 128) floats.
+// Returns the sample count actually produced (1 = importance sampling disabled for a dark image) or -1 on error.
+// ---------------------------------------------------------------------------------------------
+int ref_environment_build(const float* texels, int width, int height, int requested_sample_count,
+                          int* pdf_width, int* pdf_height, float* per_pixel_pdf, float* out_samples /*8 floats each*/, float* image_integral) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    static bool allocated = false;
+    if (!allocated) { Images::allocate(4u); Textures::allocate(4u); allocated = true; }
+    Image image = Image::create2D("environment", PixelFormat::RGBA_Float, false, Math::Vector2ui(width, height));
+    memcpy(image.get_pixels(), texels, sizeof(float) * 4 * size_t(width) * height);
+    // Latlong sampler as SimpleViewer creates it: linear filtering, repeat in u, clamp in v.
+    Texture latlong = Textures::create2D(image.get_ID(), MagnificationFilter::Linear, MinificationFilter::Linear, WrapMode::Repeat, WrapMode::Clamp);
+    int produced = -1;
+    {
+        InfiniteAreaLight light(latlong);
+        *pdf_width = light.get_PDF_width(); *pdf_height = light.get_PDF_height();
+        if (image_integral) *image_integral = light.image_integral();
+        InfiniteAreaLightUtils::reconstruct_solid_angle_PDF_sans_sin_theta(light, per_pixel_pdf);
+
+        bool is_dark_image = light.image_integral() < 0.00001f;
+        unsigned int sample_count = std::max(2u, Math::next_power_of_two((unsigned int)requested_sample_count));
+        int exponent = (int)log2(sample_count);
+        if (is_dark_image || requested_sample_count == 0) {
+            OptiXRenderer::LightSample none = OptiXRenderer::LightSample::none();
+            memcpy(out_samples, &none, sizeof(none));
+            produced = 1;
+        } else {
+            std::vector<Math::Vector2f> rng_samples(sample_count);
+            Math::RNG::fill_progressive_multijittered_bluenoise_samples(rng_samples.data(), rng_samples.data() + sample_count);
+            #pragma omp parallel for schedule(dynamic, 16)
+            for (int i = 0; i < int(sample_count); ++i) {
+                int adjusted_sample_index = Math::reverse_bits(i) >> (32 - exponent);
+                Assets::LightSample sample = light.sample(rng_samples[adjusted_sample_index]);
+                float* o = out_samples + 8 * i;
+                o[0] = sample.radiance.r; o[1] = sample.radiance.g; o[2] = sample.radiance.b; o[3] = sample.PDF;
+                o[4] = sample.direction_to_light.x; o[5] = sample.direction_to_light.y; o[6] = sample.direction_to_light.z; o[7] = sample.distance;
+            }
+            produced = int(sample_count);
+        }
+    }
+    Textures::destroy(latlong.get_ID());
+    Images::destroy(image.get_ID());
+    return produced;
 }
 
 // MIS balance heuristic (MonteCarlo.h:20-35).

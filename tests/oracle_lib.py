@@ -192,3 +192,17 @@ class OracleScene:
         r0, r1 = (0, height) if rows is None else rows
         self.lib.pto_render(self.h, C.byref(cam), C.byref(s), width, height, first_sample, sample_count, r0, r1, _p(accum), _p(counters), threads)
         return accum, counters
+
+
+def reference_environment(texels, sample_count=8192):
+    """The reference's own environment build (InfiniteAreaLight + PresampledEnvironmentMap) through oracle/ref_api.cpp."""
+    lib = load().lib
+    lib.ref_environment_build.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ref_environment_build.restype = C.c_int
+    tex = _f32(texels); h, w = tex.shape[:2]
+    pw, ph = C.c_int(), C.c_int(); integral = C.c_float()
+    pdf = np.zeros(w * max(h, 128), np.float32)
+    n = max(2, 1 << int(np.ceil(np.log2(max(sample_count, 1)))))
+    samples = np.zeros((n, 8), np.float32)
+    produced = lib.ref_environment_build(_p(tex), w, h, sample_count, C.byref(pw), C.byref(ph), _p(pdf), _p(samples), C.byref(integral))
+    return {"per_pixel_pdf": pdf[: pw.value * ph.value].reshape(ph.value, pw.value), "samples": samples[:produced], "integral": integral.value}

@@ -108,3 +108,33 @@ def test_vertex_tints_coverage_and_light_types(bpt):
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
     assert close.mean() > 0.97
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_environment_map_importance_sampling_and_mis(bpt):
+    """configs[2] in small: material grid lit only by an HDR environment (presampled NEE + MIS on escaped rays)."""
+    scene = scenes.material_grid(96, 54, grid=3, sphere_quads=(24, 12), env_size=(256, 128), env_samples=512)
+    gpu, cpu, counters, oc = render_both(bpt, scene, 96, 54, 6)
+    assert cpu.mean() > 0.01
+    e = rel_mse(gpu, cpu)
+    diff = np.abs(gpu[..., :3] - cpu).max(axis=-1)
+    close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
+    print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert e <= REL_MSE_BOUND
+    assert close.mean() > 0.97
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_instanced_terrain_small(bpt):
+    """configs[3] in small: rotated instances of displaced meshes with shading normals, three light types, 8 bounces."""
+    scene = scenes.instanced_terrain(80, 45, (3, 2), 16, 2)
+    gpu, cpu, counters, oc = render_both(bpt, scene, 80, 45, 4, max_bounces=8)
+    e = rel_mse(gpu, cpu)
+    diff = np.abs(gpu[..., :3] - cpu).max(axis=-1)
+    close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
+    print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert cpu.mean() > 0.005
+    assert e <= REL_MSE_BOUND
+    assert close.mean() > 0.97
