@@ -16,7 +16,10 @@ namespace bpt {
 
 namespace {
 
-constexpr int LEAF_MAX = 4;
+#ifndef BPT_LEAF_MAX
+#define BPT_LEAF_MAX 4
+#endif
+constexpr int LEAF_MAX = BPT_LEAF_MAX;
 
 struct InstanceRecord {
     int prim_offset;   // first global primitive index

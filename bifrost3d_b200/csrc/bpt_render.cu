@@ -170,7 +170,7 @@ struct ExtendSource {
     }
 };
 
-__global__ void __launch_bounds__(TRACE_BLOCK) extend_kernel(WavefrontView w, SceneView s) {
+__global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
     ExtendSource source = { w, s.lights, s.analytic_light_count };
@@ -198,7 +198,7 @@ struct ShadowSource {
     }
 };
 
-__global__ void __launch_bounds__(TRACE_BLOCK) shadow_kernel(WavefrontView w, SceneView s) {
+__global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kernel(WavefrontView w, SceneView s) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->shadow;
     ShadowSource source = { w };
@@ -619,7 +619,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     f.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
 
     // Persistent grids: a whole number of CTAs per SM.
-    const int trace_grid = ctx->sm_count * 8;
+    const int trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;
     const int shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
     const int stream_grid = ctx->sm_count * 8;
 

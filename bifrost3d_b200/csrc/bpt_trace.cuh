@@ -105,10 +105,19 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
 
 // ---- traversal ---------------------------------------------------------------------------------
 
+#ifndef BPT_TRACE_MIN_BLOCKS
+#define BPT_TRACE_MIN_BLOCKS 8
+#endif
+#ifndef BPT_TRAVERSAL_BUDGET
+#define BPT_TRAVERSAL_BUDGET 48
+#endif
 constexpr int TRACE_BLOCK = 128;
-constexpr int STACK_SMEM = 24;
+#ifndef BPT_STACK_SMEM
+#define BPT_STACK_SMEM 32
+#endif
+constexpr int STACK_SMEM = BPT_STACK_SMEM;
 constexpr int STACK_LOCAL = 72;
-constexpr int TRAVERSAL_BUDGET = 48;          // node visits between two refills of a warp's idle lanes
+constexpr int TRAVERSAL_BUDGET = BPT_TRAVERSAL_BUDGET; // node visits between two refills of a warp's idle lanes
 constexpr int NODE_EMPTY = (int)0x80000000;   // "no node": neither an inner index (>= 0) nor a leaf (~packed)
 
 // Leaf link: ~(first_triangle | (count - 1) << 28), always in [-2^30, -1].
@@ -118,19 +127,22 @@ BPT_HD int leaf_first(int link) { return (~link) & 0x0fffffff; }
 BPT_HD int leaf_count(int link) { return ((~link) >> 28) + 1; }
 constexpr int MAX_TRIANGLES = 0x0fffffff;
 
+// The first STACK_SMEM entries of a lane's stack live in shared memory; deeper ones spill to a per-thread array in local
+// memory. The spill array is referenced through a pointer so that the rest of the traversal state stays in registers
+// (a struct that contains a dynamically indexed array is placed in local memory as a whole).
 struct TraversalStack {
     int* smem;                // [STACK_SMEM][TRACE_BLOCK], this thread's column
-    int local[STACK_LOCAL];
+    int* spill;               // [STACK_LOCAL]
     int sp;
-    BPT_D void push(int v) {
-        if (sp < STACK_SMEM) smem[sp * TRACE_BLOCK] = v;
-        else if (sp - STACK_SMEM < STACK_LOCAL) local[sp - STACK_SMEM] = v;
+    BPT_D void push(int link) {
+        if (sp < STACK_SMEM) smem[sp * TRACE_BLOCK] = link;
+        else if (sp - STACK_SMEM < STACK_LOCAL) spill[sp - STACK_SMEM] = link;
         ++sp;
     }
     BPT_D int pop() {
         if (sp == 0) return NODE_EMPTY;
         --sp;
-        return sp < STACK_SMEM ? smem[sp * TRACE_BLOCK] : local[min(sp - STACK_SMEM, STACK_LOCAL - 1)];
+        return sp < STACK_SMEM ? smem[sp * TRACE_BLOCK] : spill[min(sp - STACK_SMEM, STACK_LOCAL - 1)];
     }
 };
 
@@ -251,8 +263,10 @@ struct Traversal {
 template <bool ANY_HIT, class Source>
 BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
                           unsigned int* fetch_counter, int* stack_smem) {
+    int spill[STACK_LOCAL];
     Traversal<ANY_HIT> tr;
     tr.stack.smem = stack_smem;
+    tr.stack.spill = spill;
     tr.stack.sp = 0;
     tr.node = NODE_EMPTY;
     unsigned int index = 0;
