@@ -64,7 +64,7 @@ assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SA
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_upload_mesh", "bpt_set_instances",
-           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render",
+           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
@@ -94,6 +94,7 @@ def load_library():
     lib.bpt_build_accel.argtypes = [vp]
     lib.bpt_accel_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
     lib.bpt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), i32, i32, u32, u32, i32]
+    lib.bpt_render_aov.argtypes = [vp, C.POINTER(Camera), i32, i32, i32, u32, u32, i32]
     lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
     lib.bpt_resolve_float4.argtypes = [vp, vp]
@@ -218,6 +219,13 @@ class Bpt:
         cam = camera if isinstance(camera, Camera) else make_camera(*camera)
         s = Settings(max_bounces, nee_samples, pdf_scale, 0)
         self._check(self.lib.bpt_render(self.h, C.byref(cam), C.byref(s), width, height, first_sample, sample_count, int(reset)))
+        self._size = (width, height)
+
+    AOV = {"depth": 3, "albedo": 4, "tint": 5, "roughness": 6, "shading_normal": 7, "primitive_id": 8}
+
+    def render_aov(self, camera, kind, width, height, first_sample=0, sample_count=1, reset=True):
+        cam = camera if isinstance(camera, Camera) else make_camera(*camera)
+        self._check(self.lib.bpt_render_aov(self.h, C.byref(cam), self.AOV[kind], width, height, first_sample, sample_count, int(reset)))
         self._size = (width, height)
 
     def accumulation_device_ptr(self):

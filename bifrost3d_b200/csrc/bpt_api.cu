@@ -415,8 +415,8 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     Context* ctx = as_context(c);
     if (count <= 0 || !materials) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: need at least material 0");
     for (int i = 0; i < count; ++i) {
-        if (materials[i].shading_model != SHADING_DEFAULT)
-            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: only the Default shading model is implemented");
+        if (materials[i].shading_model != SHADING_DEFAULT && materials[i].shading_model != SHADING_DIFFUSE)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: only the Default and Diffuse shading models are implemented");
         if (materials[i].tint_roughness_texture_id || materials[i].roughness_texture_id || materials[i].metallic_texture_id || materials[i].coverage_texture_id)
             return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: textured materials are not implemented");
     }
@@ -491,6 +491,12 @@ int bpt_render(bpt_ctx* c, const bpt_camera* camera, const bpt_settings* setting
     Context* ctx = as_context(c);
     cudaSetDevice(ctx->device);
     return render(ctx, camera, settings, width, height, first_sample, sample_count, reset_accumulation);
+}
+
+int bpt_render_aov(bpt_ctx* c, const bpt_camera* camera, int aov_kind, int width, int height, uint32_t first_sample, uint32_t sample_count, int reset_accumulation) {
+    Context* ctx = as_context(c);
+    cudaSetDevice(ctx->device);
+    return render_aov(ctx, camera, aov_kind, width, height, first_sample, sample_count, reset_accumulation);
 }
 
 void* bpt_accumulation_device_ptr(bpt_ctx* c) { return as_context(c)->accumulation.ptr; }

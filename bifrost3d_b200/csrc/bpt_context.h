@@ -115,6 +115,7 @@ struct Context {
     int width = 0, height = 0;
     DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
     DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
+    float half4_scale = 1.0f; // depth backend: the displayed value is depth / (far - near), SimpleRGPs.cu:247-258
     uint64_t material_version = 0;
     bool env_light_uploaded = false;
     void* wavefront = nullptr;         // integrator-owned state (bpt_render.cu)
@@ -151,6 +152,8 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
 int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
            uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
 int resolve_half4(Context* ctx, uint16_t* out, int on_device);
+// Implemented in bpt_aov.cu
+int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int height, uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
 int resolve_float4(Context* ctx, float* out);
 void release_wavefront(Context* ctx);
 

@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                     // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
                     // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
                     Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
-                    const DefaultShading material = DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                    const DefaultShading material = material_parameter.shading_model == SHADING_DIFFUSE
+                        ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
+                        : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
 
                     radiance += throughput * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
 
@@ -499,12 +501,13 @@ __global__ void accumulate_kernel(const float4* __restrict__ rad, double* __rest
     }
 }
 
-__global__ void resolve_half4_kernel(const double* __restrict__ accum, ushort4* __restrict__ out, int64_t pixel_count) {
+__global__ void resolve_half4_kernel(const double* __restrict__ accum, ushort4* __restrict__ out, int64_t pixel_count, float scale) {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
         const double2* a = reinterpret_cast<const double2*>(accum + 4 * p);
         double2 rg = a[0], bw = a[1];
         double inv = bw.y > 0.0 ? 1.0 / bw.y : 0.0;
         float3 mean = f3(float(rg.x * inv), float(rg.y * inv), float(bw.x * inv));
+        if (scale != 1.0f) mean = mean / scale; // depth backend: d = depth / max_depth
         // float_to_half, SimpleRGPs.cu:39-42
         out[p] = make_ushort4(__half_as_ushort(__float2half_rn(mean.x)), __half_as_ushort(__float2half_rn(mean.y)),
                               __half_as_ushort(__float2half_rn(mean.z)), __half_as_ushort(__float2half_rn(1.0f)));
@@ -545,6 +548,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     const int64_t pixels = (int64_t)width * height;
     if (pixels > 0x7fffffffll) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: frame too large");
 
+    ctx->half4_scale = 1.0f;
     if (!ctx->wavefront) ctx->wavefront = new Wavefront();
     Wavefront* wf = wavefront(ctx);
     if (wf->pixel_capacity < pixels) {
@@ -679,7 +683,7 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device) {
         BPT_CUDA_CHECK(ctx, ctx->output_half4.resize(4 * pixels));
         d = reinterpret_cast<ushort4*>(ctx->output_half4.ptr);
     }
-    resolve_half4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels);
+    resolve_half4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels, ctx->half4_scale);
     ctx->counters.kernel_launches++;
     if (!on_device) {
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, pixels * sizeof(ushort4), cudaMemcpyDeviceToHost, st));

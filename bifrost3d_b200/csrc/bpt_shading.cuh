@@ -536,6 +536,7 @@ struct DefaultShading {
     float diffuse_roughness_factor; // pow(roughness, 0.1), hoisted out of the Oren-Nayar PDF
     unsigned short specular_probability_q; // quantised to 16 bit exactly like the reference
     unsigned short coat_probability_q;
+    bool diffuse_only; // ShadingModel::Diffuse (DiffuseShading.h:21-49): the Oren-Nayar lobe alone, no regularisation
 
     BPT_D static float compute_specular_properties(const ShadingTables& t, float roughness, float specularity, float scale, float abs_cos_theta_o,
                                                    float& alpha, float& reflection_scale, float& transmission_scale) {
@@ -628,6 +629,7 @@ struct DefaultShading {
         s.setup_shading(t, tint, roughness, specularity, metallic, coat, coat_roughness, abs_cos_theta_o, coat_rho);
         s.setup_sampling_probabilities(t, abs_cos_theta_o, coat_rho);
         s.diffuse_roughness_factor = oren_nayar::uniform_lobe_roughness_factor(s.roughness);
+        s.diffuse_only = false;
         return s;
     }
 
@@ -643,6 +645,18 @@ struct DefaultShading {
         return create(t, tint, roughness, m.specularity, metallic, unorm16_to_float(m.coat), coat_roughness, abs_cos_theta_o);
     }
 
+    // DiffuseMaterialCreator::create, MonteCarlo.cu:250-255.
+    BPT_D static DefaultShading create_diffuse(const Material& m, float4 tint_and_roughness_scale) {
+        DefaultShading s;
+        s.diffuse_tint = f3(m.tint[0] * tint_and_roughness_scale.x, m.tint[1] * tint_and_roughness_scale.y, m.tint[2] * tint_and_roughness_scale.z);
+        s.roughness = m.roughness * tint_and_roughness_scale.w;
+        s.specularity = f3(0.0f); s.specular_scale = 0.0f; s.coat_scale = 0.0f; s.coat_alpha = 0.0f;
+        s.specular_probability_q = 0; s.coat_probability_q = 0;
+        s.diffuse_roughness_factor = oren_nayar::uniform_lobe_roughness_factor(s.roughness);
+        s.diffuse_only = true;
+        return s;
+    }
+
     BPT_D float get_specular_alpha() const { return ggx::alpha_from_roughness(roughness); }
     BPT_D float get_diffuse_probability() const { return 1.0f - (specular_probability_q + coat_probability_q) / 65535.0f; }
     BPT_D float get_specular_probability() const { return specular_probability_q / 65535.0f; }
@@ -651,6 +665,8 @@ struct DefaultShading {
     BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
         if (wo.z < 0.000001f || wi.z < 0.000001f)
             return bsdf_response_none();
+        if (diffuse_only)
+            return oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, diffuse_roughness_factor, wo, wi);
 
         BsdfResponse diffuse_response = oren_nayar::evaluate_with_pdf(diffuse_tint, roughness, diffuse_roughness_factor, wo, wi);
         BsdfResponse specular_response = ggx_r::evaluate_with_pdf(get_specular_alpha(), specularity, wo, wi);
@@ -675,6 +691,8 @@ struct DefaultShading {
     BPT_D BsdfSample sample(float3 wo, float3 u) const {
         if (wo.z < 0.000001f)
             return bsdf_sample_none();
+        if (diffuse_only)
+            return oren_nayar::sample(diffuse_tint, roughness, diffuse_roughness_factor, wo, f2(u.x, u.y));
 
         float specular_probability = get_specular_probability();
         float coat_probability = get_coat_probability();

@@ -14,6 +14,8 @@
 #include <Bifrost/Assets/Shading/Fittings.h>
 #include <Bifrost/Core/Renderer.h>
 #include <Bifrost/Math/Conversions.h>
+#include <Bifrost/Math/FixedPointTypes.h>
+#include <Bifrost/Math/half.h>
 #include <Bifrost/Scene/Camera.h>
 #include <Bifrost/Scene/LightSource.h>
 #include <Bifrost/Scene/SceneNode.h>
@@ -99,6 +101,68 @@ struct Renderer::Implementation {
     void conditional_per_camera_state_resize(CameraID camera_ID) {
         if (per_camera_state.size() <= camera_ID)
             per_camera_state.resize(Cameras::capacity());
+    }
+
+    // set_backend, Renderer.cpp:1411-1453: backend -> entry point.
+    static int aov_of(Backend backend) {
+        switch (backend) {
+        case Backend::DepthVisualization: return BPT_AOV_DEPTH;
+        case Backend::AlbedoVisualization: return BPT_AOV_ALBEDO;
+        case Backend::TintVisualization: return BPT_AOV_TINT;
+        case Backend::RoughnessVisualization: return BPT_AOV_ROUGHNESS;
+        case Backend::ShadingNormalVisualization: return BPT_AOV_SHADING_NORMAL;
+        case Backend::PrimitiveIdVisualization: return BPT_AOV_PRIMITIVE_ID;
+        default: return 0;
+        }
+    }
+
+    bpt_camera camera_of(CameraID camera_ID) {
+        bpt_camera camera;
+        Matrix4x4f inverse_projection_matrix = Cameras::get_inverse_projection_matrix(camera_ID);
+        Matrix4x4f inverse_view_projection_matrix = Cameras::get_inverse_view_projection_matrix(camera_ID);
+        Matrix3x3f view_to_world_rotation = to_matrix3x3(Cameras::get_inverse_view_transform(camera_ID).rotation);
+        memcpy(camera.view_to_world_rotation, view_to_world_rotation.begin(), sizeof(camera.view_to_world_rotation));
+        memcpy(camera.inverse_projection, inverse_projection_matrix.begin(), sizeof(camera.inverse_projection));
+        memcpy(camera.inverse_view_projection, inverse_view_projection_matrix.begin(), sizeof(camera.inverse_view_projection));
+        return camera;
+    }
+
+    // request_auxiliary_buffers, Renderer.cpp:1267-1358: re-render the requested features into scratch buffers.
+    std::vector<Screenshot> request_auxiliary_buffers(CameraID camera_ID, Cameras::ScreenshotContent content_requested, Vector2i frame_size) {
+        std::vector<Screenshot> screenshots;
+        conditional_per_camera_state_resize(camera_ID);
+        unsigned int accumulation_count = per_camera_state[camera_ID].accumulations > 1u ? per_camera_state[camera_ID].accumulations : 1u;
+        int pixel_count = frame_size.x * frame_size.y;
+        bpt_camera camera = camera_of(camera_ID);
+        std::vector<float> mean(4 * size_t(pixel_count));
+        auto render_feature = [&](int aov) {
+            check(ctx, bpt_render_aov(ctx, &camera, aov, frame_size.x, frame_size.y, 0, accumulation_count, 1), "bpt_render_aov");
+            check(ctx, bpt_resolve_float4(ctx, mean.data()), "bpt_resolve_float4");
+        };
+        auto half_round = [](float v) { return float(half_float::half(v)); }; // the reference reads the half4 output buffer back
+        if (content_requested.contains(Screenshot::Content::Depth)) {
+            render_feature(BPT_AOV_DEPTH);
+            float* pixels = new float[pixel_count];
+            for (int i = 0; i < pixel_count; ++i) pixels[i] = mean[4 * i];
+            screenshots.emplace_back(frame_size.x, frame_size.y, Screenshot::Content::Depth, PixelFormat::Intensity_Float, pixels);
+        }
+        auto rgb24 = [&](Screenshot::Content content, int aov) {
+            render_feature(aov);
+            RGB24* pixels = new RGB24[pixel_count];
+            for (int i = 0; i < pixel_count; ++i) { pixels[i].r = half_round(mean[4 * i]); pixels[i].g = half_round(mean[4 * i + 1]); pixels[i].b = half_round(mean[4 * i + 2]); }
+            screenshots.emplace_back(frame_size.x, frame_size.y, content, PixelFormat::RGB24, pixels);
+        };
+        if (content_requested.contains(Screenshot::Content::Albedo)) rgb24(Screenshot::Content::Albedo, BPT_AOV_ALBEDO);
+        if (content_requested.contains(Screenshot::Content::Tint)) rgb24(Screenshot::Content::Tint, BPT_AOV_TINT);
+        if (content_requested.contains(Screenshot::Content::Roughness)) {
+            render_feature(BPT_AOV_ROUGHNESS);
+            unsigned char* pixels = new unsigned char[pixel_count];
+            for (int i = 0; i < pixel_count; ++i) pixels[i] = UNorm8::to_byte(half_round(mean[4 * i]));
+            screenshots.emplace_back(frame_size.x, frame_size.y, Screenshot::Content::Roughness, PixelFormat::Intensity8, pixels);
+        }
+        // the scratch render replaced the camera's accumulation: restart it
+        per_camera_state[camera_ID].accumulations = 0u;
+        return screenshots;
     }
 
     static void check(bpt_ctx* ctx, int status, const char* what) {
@@ -270,11 +334,6 @@ struct Renderer::Implementation {
         if (state.accumulations >= state.max_accumulation_count)
             return state.accumulations;
 
-        if (state.backend != Backend::PathTracing && state.backend != Backend::None) {
-            printf("OptiXRenderer(B200): Backend %u not supported; only path tracing is implemented.\n", unsigned(state.backend));
-            return state.accumulations;
-        }
-
         bpt_camera camera;
         memcpy(camera.view_to_world_rotation, view_to_world_rotation.begin(), sizeof(camera.view_to_world_rotation));
         memcpy(camera.inverse_projection, inverse_projection_matrix.begin(), sizeof(camera.inverse_projection));
@@ -284,7 +343,16 @@ struct Renderer::Implementation {
         settings.next_event_sample_count = next_event_sample_count;
         settings.path_regularization_pdf_scale = path_regularization.PDF_scale_at_accumulation(int(state.accumulations));
 
-        int status = bpt_render(ctx, &camera, &settings, frame_size.x, frame_size.y, first_sample + state.accumulations, 1, state.accumulations == 0 ? 1 : 0);
+        int status;
+        int aov = aov_of(state.backend);
+        if (state.backend == Backend::AIDenoisedPathTracing) {
+            printf("OptiXRenderer(B200): Backend %u not supported (proprietary OptiX denoiser).\n", unsigned(state.backend));
+            return state.accumulations;
+        }
+        if (aov == 0)
+            status = bpt_render(ctx, &camera, &settings, frame_size.x, frame_size.y, first_sample + state.accumulations, 1, state.accumulations == 0 ? 1 : 0);
+        else
+            status = bpt_render_aov(ctx, &camera, aov, frame_size.x, frame_size.y, first_sample + state.accumulations, 1, state.accumulations == 0 ? 1 : 0);
         check(ctx, status, "bpt_render");
         if (status == BPT_OK) {
             check(ctx, bpt_resolve_half4(ctx, (uint16_t*)buffer->getDevicePointer(0), 1), "bpt_resolve_half4");
@@ -339,9 +407,8 @@ AIDenoiserFlags Renderer::get_AI_denoiser_flags() const { return m_impl->AI_deno
 void Renderer::set_AI_denoiser_flags(AIDenoiserFlags flags) { m_impl->AI_denoiser_flags = flags; }
 void Renderer::handle_updates() { m_impl->handle_updates(); }
 unsigned int Renderer::render(CameraID camera_ID, optix::Buffer buffer, Vector2i frame_size) { return m_impl->render(camera_ID, buffer, frame_size, m_first_sample); }
-std::vector<Screenshot> Renderer::request_auxiliary_buffers(CameraID, Cameras::ScreenshotContent, Vector2i) {
-    printf("OptiXRenderer(B200): auxiliary buffers (AOV backends) are not implemented yet.\n");
-    return {};
+std::vector<Screenshot> Renderer::request_auxiliary_buffers(CameraID camera_ID, Cameras::ScreenshotContent content_requested, Vector2i frame_size) {
+    return m_impl->request_auxiliary_buffers(camera_ID, content_requested, frame_size);
 }
 optix::Context& Renderer::get_context() { return m_impl->context; }
 

@@ -36,7 +36,7 @@ typedef enum bpt_status {
 /* Types.h:353-416 `Material` (64 bytes). Texture ids must be 0: textures are a "next" row. */
 typedef struct bpt_material {
     uint16_t flags;              /* 1 = ThinWalled, 2 = Cutout */
-    uint16_t shading_model;      /* 0 = Default (the only model implemented), 1 = Diffuse, 2 = Transmissive */
+    uint16_t shading_model;      /* 0 = Default, 1 = Diffuse, 2 = Transmissive (not implemented: rejected) */
     float tint[3];
     float roughness;
     int32_t tint_roughness_texture_id;
@@ -156,6 +156,12 @@ int bpt_accel_info(bpt_ctx* ctx, int64_t* triangle_count, int64_t* node_count, f
  * `reset_accumulation` != 0 or the frame size changes (Renderer.cpp:1207-1248). */
 int bpt_render(bpt_ctx* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
                uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
+/* First-hit feature ("AOV") backends; values mirror EntryPoints in Types.h:33-44. Replaces depth_RPG, albedo_RPG, tint_RPG,
+ * roughness_RPG, shading_normal_RPG, primitive_id_RPG (SimpleRGPs.cu:227-340). Accumulates like bpt_render; the depth
+ * backend accumulates the raw distance (the caller divides by far - near like SimpleRGPs.cu:247-258). */
+enum { BPT_AOV_DEPTH = 3, BPT_AOV_ALBEDO = 4, BPT_AOV_TINT = 5, BPT_AOV_ROUGHNESS = 6, BPT_AOV_SHADING_NORMAL = 7, BPT_AOV_PRIMITIVE_ID = 8 };
+int bpt_render_aov(bpt_ctx* ctx, const bpt_camera* camera, int aov_kind, int width, int height,
+                   uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
 /* Device pointer to the double4[width*height] accumulation (sum) buffer, e.g. for an NCCL reduce. */
 void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
 /* mean = sum / w, converted to half4 (alpha 1) exactly like SimpleRGPs.cu:39-42,106; written to `out` which is

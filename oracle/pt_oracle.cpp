@@ -15,6 +15,7 @@
 #include <OptiXRenderer/MonteCarlo.h>
 #include <OptiXRenderer/RNG.h>
 #include <OptiXRenderer/Intersect.h>
+#include <OptiXRenderer/Shading/ShadingModels/DiffuseShading.h>
 #include <OptiXRenderer/Shading/LightSources/DirectionalLightImpl.h>
 #include <OptiXRenderer/Shading/LightSources/SphereLightImpl.h>
 #include <OptiXRenderer/Shading/LightSources/SpotLightImpl.h>
@@ -446,7 +447,8 @@ inline float4 rng_sample4f(const MonteCarloPayload& p, unsigned int sampling_dim
 }
 
 // sample_single_light, MonteCarlo.cu:61-87
-LightSample sample_single_light(const Scene& sc, const DefaultShading& material, float3 intersection_point, float3 wo, const TBN& world_shading_tbn, float3 random_sample) {
+template <class ShadingModel>
+LightSample sample_single_light(const Scene& sc, const ShadingModel& material, float3 intersection_point, float3 wo, const TBN& world_shading_tbn, float3 random_sample) {
     int light_index = std::min(sc.light_count - 1, int(random_sample.z * sc.light_count));
     const Light& light = sc.lights[light_index];
     LightSample light_sample = light_sample_radiance(sc, light, intersection_point, make_float2(random_sample));
@@ -467,7 +469,8 @@ LightSample sample_single_light(const Scene& sc, const DefaultShading& material,
 }
 
 // reestimated_light_samples, MonteCarlo.cu:91-123
-LightSample reestimated_light_samples(const Scene& sc, const SettingsIn& settings, const MonteCarloPayload& payload, const DefaultShading& material,
+template <class ShadingModel>
+LightSample reestimated_light_samples(const Scene& sc, const SettingsIn& settings, const MonteCarloPayload& payload, const ShadingModel& material,
                                       float3 intersection_point, float3 wo, const TBN& world_shading_tbn) {
     if (sc.light_count == 0)
         return LightSample::none();
@@ -568,16 +571,25 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
     float3 wo = world_shading_tbn * world_wo;
 
     float cos_theta = hit_from_front || material_parameter.is_thin_walled() ? wo.z : -wo.z;
-    PDF max_PDF_hint = payload.bsdf_PDF * st.settings->path_regularization_pdf_scale;
-    const DefaultShading material = create_default_shading(material_parameter, tint_and_roughness_scale, cos_theta, max_PDF_hint);
-
     payload.radiance += payload.throughput * emission * material_parameter.emission;
 
-    payload.light_sample = reestimated_light_samples(sc, *st.settings, payload, material, world_intersection_point, wo, world_shading_tbn);
-    payload.light_sample_origin = offset_ray_origin(world_intersection_point, payload.light_sample.direction_to_light, world_geometric_normal);
-    payload.light_sample.radiance *= payload.throughput;
+    // The shading-model specific part of path_tracing_closest_hit<MaterialCreator>, MonteCarlo.cu:191-212.
+    BSDFSample bsdf_sample;
+    auto light_and_bsdf = [&](const auto& material) {
+        payload.light_sample = reestimated_light_samples(sc, *st.settings, payload, material, world_intersection_point, wo, world_shading_tbn);
+        payload.light_sample_origin = offset_ray_origin(world_intersection_point, payload.light_sample.direction_to_light, world_geometric_normal);
+        payload.light_sample.radiance *= payload.throughput;
+        bsdf_sample = material.sample(wo, bsdf_random_uvs);
+    };
+    if (material_parameter.shading_model == Material::ShadingModel::Diffuse) {
+        // DiffuseMaterialCreator::create, MonteCarlo.cu:250-255
+        float4 tint_roughness = make_float4(material_parameter.tint, material_parameter.roughness) * tint_and_roughness_scale;
+        light_and_bsdf(Shading::ShadingModels::DiffuseShading(make_float3(tint_roughness), tint_roughness.w));
+    } else {
+        PDF max_PDF_hint = payload.bsdf_PDF * st.settings->path_regularization_pdf_scale;
+        light_and_bsdf(create_default_shading(material_parameter, tint_and_roughness_scale, cos_theta, max_PDF_hint));
+    }
 
-    BSDFSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
     bool is_reflection = bsdf_sample.direction.z >= 0;
     payload.direction = bsdf_sample.direction * world_shading_tbn;
     payload.bsdf_PDF = bsdf_sample.PDF;

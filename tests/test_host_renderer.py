@@ -19,6 +19,17 @@ def test_reference_renderer_fixture_background_color():
     assert "[  PASSED  ] 1 test." in out.stdout
 
 
+@pytest.mark.gpu
+@pytest.mark.skipif(not BINARY.exists(), reason="host shim not built (needs the staged Bifrost core)")
+def test_reference_renderer_fixture_all_cases():
+    """All three reference renderer tests (RendererTest.h:142-194): background colour, vertex-tint gradient through the
+    TintVisualization backend, and the auxiliary tint screenshot (request_auxiliary_buffers)."""
+    out = subprocess.run([str(BINARY)], capture_output=True, text=True, timeout=300)
+    print(out.stdout[-2500:])
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+    assert "[  PASSED  ] 3 tests." in out.stdout
+
+
 def test_host_shim_exports_the_reference_api():
     """The shared library of the host shim defines every public OptiXRenderer::Renderer method of Renderer.h:40-86."""
     lib = REPO / "bifrost3d_b200" / "libOptiXRendererB200.so"

@@ -138,3 +138,55 @@ def test_instanced_terrain_small(bpt):
     assert cpu.mean() > 0.005
     assert e <= REL_MSE_BOUND
     assert close.mean() > 0.97
+
+
+@pytest.mark.gpu
+def test_aov_backends_on_a_tinted_quad(bpt):
+    """RendererTest.h:155-172 in Python: an orthographic view of a quad whose vertex tints encode the pixel position; plus
+    roughness, shading normal and depth of the same quad."""
+    w, h = 8, 6
+    mesh = {"indices": np.array([[0, 1, 2], [1, 2, 3]], np.uint32),
+            "positions": np.array([[-0.5 * w, -0.5 * h, 1], [-0.5 * w, 0.5 * h, 1], [0.5 * w, -0.5 * h, 1], [0.5 * w, 0.5 * h, 1]], np.float32),
+            "tints": np.array([[0, 0, 255, 255], [0, 255, 255, 255], [255, 0, 255, 255], [255, 255, 255, 255]], np.uint8)}
+    mat = scenes.material((1, 1, 1), 0.5, thin_walled=True); mat["shading_model"] = 1  # Diffuse, as in the reference's fixture
+    scene = {"meshes": {0: mesh}, "materials": np.array([scenes.material((0, 0, 0), 0), mat], capi.MATERIAL_DTYPE),
+             "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE), "lights": np.zeros(0, capi.LIGHT_DTYPE),
+             "environment": {"tint": (1, 1, 1)}}
+    # compute_orthographic_projection(width, height, depth = 1000), Camera.cpp:269-287
+    inv_proj = np.zeros((4, 4), np.float32); inv_proj[0, 0] = 0.5 * w; inv_proj[1, 1] = 0.5 * h; inv_proj[2, 2] = 500; inv_proj[2, 3] = 500; inv_proj[3, 3] = 1
+    cam = (np.eye(3, dtype=np.float32), inv_proj, inv_proj.copy())
+    scenes.upload(bpt, scene)
+    bpt.render_aov(cam, "tint", w, h)
+    tint = bpt.resolve_half4().astype(np.float32)
+    ys, xs = np.mgrid[0:h, 0:w]
+    assert np.abs(tint[..., 0] - (xs + 0.5) / w).max() < 0.003
+    assert np.abs(tint[..., 1] - (ys + 0.5) / h).max() < 0.003
+    assert np.abs(tint[..., 2] - 1.0).max() < 0.003
+    bpt.render_aov(cam, "roughness", w, h)
+    assert np.abs(bpt.resolve_float4()[..., 0] - 0.5).max() < 1e-6
+    bpt.render_aov(cam, "shading_normal", w, h)
+    n = bpt.resolve_float4()[..., :3] * 2 - 1
+    assert np.abs(np.abs(n[..., 2]) - 1).max() < 1e-5  # faces the camera whichever way the quad winds
+    bpt.render_aov(cam, "depth", w, h)
+    assert np.abs(bpt.resolve_float4()[..., 0] - 1.0).max() < 1e-5
+    assert np.abs(bpt.resolve_half4().astype(np.float32)[..., 0] - 1.0 / 1000.0).max() < 1e-5
+    bpt.render_aov(cam, "albedo", w, h)
+    assert np.abs(bpt.resolve_float4()[..., 0] - (xs + 0.5) / w).max() < 0.003
+    # and the path tracer shades the Diffuse model: white environment, white-ish quad -> finite, positive radiance
+    bpt.render(cam, w, h, 0, 4, reset=True)
+    img = bpt.resolve_float4()
+    assert np.isfinite(img).all() and img[..., 2].min() > 0.1
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_diffuse_shading_model_matches_oracle(bpt):
+    scene = scenes.cornell_box(sphere_quads=(16, 8))
+    mats = scene["materials"].copy()
+    for i in (1, 2, 3):
+        mats[i]["shading_model"] = 1
+    scene["materials"] = mats
+    gpu, cpu, counters, oc = render_both(bpt, scene, 64, 64, 4)
+    e = rel_mse(gpu, cpu)
+    print(f"relMSE {e:.3e}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert e <= REL_MSE_BOUND and e < 1e-8
