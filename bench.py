@@ -275,6 +275,8 @@ def main():
     if rank == 0:
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": device_ms / K,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "extend_node_visits_per_ray": counters["extend_node_visits"] / max(counters["extend_rays"], 1),
+                "extend_triangle_tests_per_ray": counters["extend_triangle_tests"] / max(counters["extend_rays"], 1),
                 "mrays_per_s": mrays, "extend_rays_per_step": counters["extend_rays"] / K, "shadow_rays_per_step": counters["shadow_rays"] / K,
                 "config": workload_config(args, scene, settings),
                 "bvh": {"triangles": info["triangles"], "nodes": info["nodes"], "build_ms": info["build_ms"], "mtris_per_s": info["triangles"] / max(info["build_ms"], 1e-6) / 1e3},

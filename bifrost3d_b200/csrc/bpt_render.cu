@@ -167,6 +167,10 @@ struct ExtendSource {
             if (radius > 0.0f && t > tr.ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
         }
         w.hit[w.queue_in[i]] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
+#ifdef BPT_TRAVERSAL_STATS
+        atomicAdd(w.ray_counters + 2, (unsigned long long)tr.stat_nodes);
+        atomicAdd(w.ray_counters + 3, (unsigned long long)tr.stat_triangles);
+#endif
     }
 };
 

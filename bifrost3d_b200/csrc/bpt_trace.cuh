@@ -179,7 +179,11 @@ struct Traversal {
     float transmission;
     int skip_primitive;
     int node;
+    int postponed;       // a leaf found while other lanes were still descending; NODE_EMPTY when none
     TraversalStack stack;
+#ifdef BPT_TRAVERSAL_STATS
+    unsigned int stat_nodes, stat_triangles;
+#endif
 
     BPT_D void begin(const Ray& r, int skip) {
         ray = r;
@@ -191,10 +195,17 @@ struct Traversal {
         skip_primitive = skip;
         stack.sp = 0;
         node = 0; // root
+        postponed = NODE_EMPTY;
+#ifdef BPT_TRAVERSAL_STATS
+        stat_nodes = stat_triangles = 0;
+#endif
     }
 
     // One inner-node visit: tests both children, descends into the nearer hit child, defers the other.
     BPT_D void inner_step(const AccelView& a) {
+#ifdef BPT_TRAVERSAL_STATS
+        ++stat_nodes;
+#endif
         const float4* n = reinterpret_cast<const float4*>(a.nodes + node);
         float4 n0 = ldg4(n), n1 = ldg4(n + 1), n2 = ldg4(n + 2);
         int2 links = __ldg(reinterpret_cast<const int2*>(n + 3));
@@ -213,14 +224,18 @@ struct Traversal {
             node = stack.pop();
     }
 
-    BPT_D void leaf_step(const AccelView& a, const float* __restrict__ coverage_by_material) {
-        const int first = leaf_first(node), count = leaf_count(node);
+    // Intersects the triangles of one leaf. Returns false when an any-hit ray got blocked (traversal is over).
+    BPT_D bool intersect_leaf(const AccelView& a, const float* __restrict__ coverage_by_material, int leaf) {
+        const int first = leaf_first(leaf), count = leaf_count(leaf);
         for (int i = 0; i < count; ++i) {
             const float4* tri = reinterpret_cast<const float4*>(a.triangles + first + i);
             float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
             int primitive = __float_as_int(v0.w);
             if (primitive == skip_primitive)
                 continue;
+#ifdef BPT_TRAVERSAL_STATS
+            ++stat_triangles;
+#endif
             float t, u, v;
             if (!watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v))
                 continue;
@@ -229,7 +244,7 @@ struct Traversal {
                     // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
                     float coverage = coverage_by_material[__float_as_int(v1.w)];
                     transmission *= 1.0f - coverage;
-                    if (transmission < 0.0000001f) { transmission = 0.0f; node = NODE_EMPTY; stack.sp = 0; return; }
+                    if (transmission < 0.0000001f) { transmission = 0.0f; return false; }
                 }
             } else if (t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
                 // hit.t starts at ray.tmax and hit.primitive at INT_MAX, so a first hit needs t < tmax.
@@ -237,17 +252,36 @@ struct Traversal {
                 tmax = t;
             }
         }
-        node = stack.pop();
+        return true;
     }
 
     // Runs up to `budget` inner-node visits (and the leaves met on the way). Returns when the ray is done or the budget
-    // is used up; `node == NODE_EMPTY` tells which.
+    // is used up; `node == NODE_EMPTY && postponed == NODE_EMPTY` tells which.
+    // Speculative traversal (Aila and Laine): a lane that reaches a leaf parks it in `postponed` and keeps descending while
+    // other lanes of the warp are still looking for theirs, so the inner-node loop runs with more lanes active.
     BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget) {
-        while (node != NODE_EMPTY && budget > 0) {
-            while (node >= 0 && budget > 0) { inner_step(a); --budget; }
-            while (is_leaf(node)) leaf_step(a, coverage_by_material);
+        while ((node != NODE_EMPTY || postponed != NODE_EMPTY) && budget > 0) {
+            while (node >= 0 && budget > 0) {
+                inner_step(a);
+                --budget;
+                if (postponed == NODE_EMPTY && is_leaf(node)) { postponed = node; node = stack.pop(); }
+                if (!__any_sync(__activemask(), postponed == NODE_EMPTY && node >= 0))
+                    break;
+            }
+            if (postponed != NODE_EMPTY) {
+                bool alive = intersect_leaf(a, coverage_by_material, postponed);
+                postponed = NODE_EMPTY;
+                if (!alive) { node = NODE_EMPTY; stack.sp = 0; }
+            }
+            while (is_leaf(node)) {
+                bool alive = intersect_leaf(a, coverage_by_material, node);
+                node = stack.pop();
+                if (!alive) { node = NODE_EMPTY; stack.sp = 0; }
+            }
         }
     }
+
+    BPT_D bool finished() const { return node == NODE_EMPTY && postponed == NODE_EMPTY; }
 
     BPT_D Hit result() const {
         Hit h = hit;
@@ -269,13 +303,14 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
     tr.stack.spill = spill;
     tr.stack.sp = 0;
     tr.node = NODE_EMPTY;
+    tr.postponed = NODE_EMPTY;
     unsigned int index = 0;
     bool has_ray = false, exhausted = false;
     const int lane = threadIdx.x & 31;
 
     while (true) {
         // Retire finished rays and refill idle lanes: one atomic per warp.
-        if (has_ray && tr.node == NODE_EMPTY) { source.store(index, tr); has_ray = false; }
+        if (has_ray && tr.finished()) { source.store(index, tr); has_ray = false; }
         unsigned int idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
         if (idle) {
             int leader = __ffs(idle) - 1;

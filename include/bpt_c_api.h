@@ -105,6 +105,8 @@ typedef struct bpt_counters {
     float shadow_ms;
     float shade_ms;
     float other_ms;
+    uint64_t extend_node_visits;     /* diagnostics, only filled by builds with -DBPT_TRAVERSAL_STATS */
+    uint64_t extend_triangle_tests;
 } bpt_counters;
 
 /* ---- context ----------------------------------------------------------------------------------- */

@@ -18,6 +18,7 @@ for lib in [None] + libs:
         d = json.loads(out.stdout.strip().splitlines()[-1])
         r = d["roofline"]
         print(f"{(lib.name if lib else 'libbpt.so'):28s} {d['value']:8.1f} Msamples/s {d['ms_per_step']:7.3f} ms/step  extend {r['share_of_step']['extend'] * d['ms_per_step']:.3f} "
-              f"shade {r['share_of_step']['shade'] * d['ms_per_step']:.3f} shadow {r['share_of_step']['shadow'] * d['ms_per_step']:.3f} ms  {r['grays_per_s_extend']:.2f} Grays/s", flush=True)
+              f"shade {r['share_of_step']['shade'] * d['ms_per_step']:.3f} shadow {r['share_of_step']['shadow'] * d['ms_per_step']:.3f} ms  {r['grays_per_s_extend']:.2f} Grays/s"
+              f"  nodes/ray {d.get('extend_node_visits_per_ray', 0):.1f} tris/ray {d.get('extend_triangle_tests_per_ray', 0):.1f}", flush=True)
     except Exception as e:
         print(lib, "failed", e, out.stderr[-500:])
