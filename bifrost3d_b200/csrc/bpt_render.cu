@@ -34,7 +34,9 @@ struct QueueCounters {
     unsigned int shadow;       // entries in the shadow queue
     unsigned int fetch_extend; // dynamic ray fetch cursors of the two traversal kernels
     unsigned int fetch_shadow;
-    unsigned int pad[3];
+    unsigned int surface;      // paths whose ray hit a triangle (shaded by shade_kernel<true>)
+    unsigned int escaped;      // paths whose ray left the scene or hit an analytic light (shade_kernel<false>)
+    unsigned int pad;
 };
 
 struct Wavefront {
@@ -45,6 +47,7 @@ struct Wavefront {
     // shadow rays: origin.xyz + tmax, direction.xyz + pixel (bits), radiance.xyz
     DeviceBuffer<float4> sh_o, sh_d, sh_rad;
     DeviceBuffer<unsigned int> queue_a, queue_b;
+    DeviceBuffer<unsigned int> queue_surface, queue_escaped; // extend sorts its results by what shading they need
     DeviceBuffer<QueueCounters> counters;
     DeviceBuffer<float> coverage; // per material
     uint64_t coverage_version = ~0ull;
@@ -54,6 +57,7 @@ struct WavefrontView {
     float4 *ray_o, *ray_d, *thr, *rad, *hit;
     float4 *sh_o, *sh_d, *sh_rad;
     unsigned int *queue_in, *queue_out;
+    unsigned int *queue_surface, *queue_escaped;
     QueueCounters* counters;
     unsigned long long* ray_counters; // [0] extend, [1] shadow
 };
@@ -135,6 +139,8 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.counters->shadow = 0;
         w.counters->fetch_extend = 0;
         w.counters->fetch_shadow = 0;
+        w.counters->surface = 0;
+        w.counters->escaped = 0;
     }
 }
 
@@ -166,7 +172,13 @@ struct ExtendSource {
             }
             if (radius > 0.0f && t > tr.ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
         }
-        w.hit[w.queue_in[i]] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
+        unsigned int pixel = w.queue_in[i];
+        w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
+        // Sort the paths by the shading they need: surface hits go to the (large) surface shading kernel, escaped rays and
+        // light hits to a small one, so neither runs with lanes masked off for the other's work. Same-address atomics of a
+        // warp are aggregated by the compiler (REDUX + one atomic).
+        if (h.primitive >= 0 && !(h.primitive & LIGHT_HIT_FLAG)) w.queue_surface[atomicAdd(&w.counters->surface, 1u)] = pixel;
+        else w.queue_escaped[atomicAdd(&w.counters->escaped, 1u)] = pixel;
 #ifdef BPT_TRAVERSAL_STATS
         atomicAdd(w.ray_counters + 2, (unsigned long long)tr.stat_nodes);
         atomicAdd(w.ray_counters + 3, (unsigned long long)tr.stat_triangles);
@@ -217,6 +229,8 @@ __global__ void advance_kernel(QueueCounters* c) {
     c->shadow = 0;
     c->fetch_extend = 0;
     c->fetch_shadow = 0;
+    c->surface = 0;
+    c->escaped = 0;
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
@@ -288,13 +302,17 @@ __device__ LightSample sample_single_light(const SceneView& s, const ShadingTabl
 #ifndef BPT_SHADE_MIN_BLOCKS
 #define BPT_SHADE_MIN_BLOCKS 8
 #endif
+template <bool SURFACE>
 __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
-    __shared__ __align__(16) float s_tables[3 * TABLE_FLOATS];
-    for (int i = threadIdx.x; i < 3 * TABLE_FLOATS; i += blockDim.x) s_tables[i] = s.tables[i];
-    __syncthreads();
+    __shared__ __align__(16) float s_tables[SURFACE ? 3 * TABLE_FLOATS : 4];
+    if (SURFACE) {
+        for (int i = threadIdx.x; i < 3 * TABLE_FLOATS; i += blockDim.x) s_tables[i] = s.tables[i];
+        __syncthreads();
+    }
     const ShadingTables tables = { s_tables, s_tables + TABLE_FLOATS, s_tables + 2 * TABLE_FLOATS };
 
-    const unsigned int count = w.counters->active;
+    const unsigned int count = SURFACE ? w.counters->surface : w.counters->escaped;
+    const unsigned int* __restrict__ queue = SURFACE ? w.queue_surface : w.queue_escaped;
     const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool valid = i < count;
@@ -303,7 +321,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
         float4 shadow_o = make_float4(0, 0, 0, 0), shadow_d = make_float4(0, 0, 0, 0), shadow_rad = make_float4(0, 0, 0, 0);
 
         if (valid) {
-            pixel = w.queue_in[i];
+            pixel = queue[i];
             const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
             float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
             const float4 hit4 = w.hit[pixel];
@@ -319,7 +337,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
             float3 next_origin = ray_origin, next_direction = ray_direction;
             float next_tmin = ro.w;
 
-            if (primitive < 0) {
+            if (!SURFACE && primitive < 0) {
                 // miss, SimpleRGPs.cu:349-362
                 float3 environment_radiance = s.env.tint;
                 if (s.env.texels != nullptr) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 }
                 radiance += throughput * environment_radiance;
                 throughput = f3(0.0f);
-            } else if (primitive & LIGHT_HIT_FLAG) {
+            } else if (!SURFACE) {
                 // light_closest_hit, MonteCarlo.cu:291-302; evaluate_intersection, LightImpl.h:86-108
                 Light light = s.lights[primitive & ~LIGHT_HIT_FLAG];
                 float3 light_radiance = light_evaluate(light, s.env, ray_origin, ray_direction);
@@ -338,7 +356,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 throughput = min3(throughput, f3(4.0f));
                 radiance += throughput * light_radiance;
                 throughput = f3(0.0f);
-            } else {
+            } else if (SURFACE) {
                 // interpolate_attributes, TriangleAttributes.cu:35-84 (geometry is pre-transformed to world space)
                 const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
                              p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
@@ -536,6 +554,7 @@ void release_wavefront(Context* ctx) {
     if (!wf) return;
     wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
     wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
+    wf->queue_surface.release(); wf->queue_escaped.release();
     wf->counters.release(); wf->coverage.release();
     delete wf;
     ctx->wavefront = nullptr;
@@ -560,6 +579,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, wf->rad.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->hit.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_a.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_b.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->queue_surface.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_escaped.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->counters.resize(1));
         wf->pixel_capacity = pixels;
     }
@@ -617,6 +637,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     WavefrontView w = {};
     w.ray_o = wf->ray_o.ptr; w.ray_d = wf->ray_d.ptr; w.thr = wf->thr.ptr; w.rad = wf->rad.ptr; w.hit = wf->hit.ptr;
     w.sh_o = wf->sh_o.ptr; w.sh_d = wf->sh_d.ptr; w.sh_rad = wf->sh_rad.ptr;
+    w.queue_surface = wf->queue_surface.ptr; w.queue_escaped = wf->queue_escaped.ptr;
     w.counters = wf->counters.ptr;
     w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
 
@@ -630,6 +651,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     const int trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;
     const int shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
     const int stream_grid = ctx->sm_count * 8;
+    const int escaped_grid = ctx->sm_count * 4;
 
     for (uint32_t k = 0; k < sample_count; ++k) {
         f.accumulation_count = first_sample + k;
@@ -646,13 +668,14 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
                 if (ctx->profiling) { first_event = ctx->stage_event(it * 4 + 0); cudaEventRecord(ctx->stage_events[first_event], st); }
                 extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
-                shade_kernel<<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                shade_kernel<false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                shade_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
                 shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);
                 advance_kernel<<<1, 1, 0, st>>>(w.counters);
                 std::swap(w.queue_in, w.queue_out);
-                ctx->counters.kernel_launches += 4;
+                ctx->counters.kernel_launches += 5;
             }
             done += planned;
             QueueCounters h;
