@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kern
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
     ExtendSource source = { w, s.lights, s.analytic_light_count };
-    traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x);
+    traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
 
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kern
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->shadow;
     ShadowSource source = { w };
-    traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x);
+    traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
 }
 
@@ -601,7 +601,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
 
     SceneView s = {};
-    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr };
+    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_budget_for(ctx->accel.triangle_count) };
     s.world_vertices = ctx->accel.world_vertices.ptr;
     s.shade = ctx->accel.shade.ptr;
     s.normal_matrices = ctx->accel.normal_matrices.ptr;

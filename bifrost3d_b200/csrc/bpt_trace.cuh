@@ -149,11 +149,16 @@ struct TraversalStack {
 struct AccelView {
     const BvhNode* __restrict__ nodes;
     const TraceTriangle* __restrict__ triangles;
+    int budget; // node visits between two refills of a warp's idle lanes: ~ the depth of the tree (measured: 24 up to a few
+                // million triangles, 48 for the 50M-triangle scene whose rays visit 80+ nodes)
 };
+BPT_HD int traversal_budget_for(long long triangle_count) { return triangle_count > 8000000ll ? 48 : 24; }
 
 BPT_D float4 ldg4(const float4* p) { return __ldg(p); }
 
-// Slab test against one child box. Conservative: the far distance is padded by a few ulp (Ize, "Robust BVH ray
+// Slab test against one child box, (plane - origin) * inv_d per plane. (A fused lo * inv_d - o * inv_d form needs an absolute
+// error pad proportional to |o * inv_d|; measured on B200 it made the 1M / 50M triangle scenes 2-3x slower because rays with
+// one small direction component then visit large parts of the tree.) Conservative: the far distance is padded by a few ulp (Ize, "Robust BVH ray
 // traversal", JCGT 2013) and the near one shrunk, so a triangle the watertight test would accept is never culled.
 // An absent child (scenes with fewer than two triangles) is a point box at 3e38 and never passes.
 BPT_D bool slab(float3 lo, float3 hi, float3 o, float3 inv_d, float tmin, float tmax, float& tnear) {
@@ -296,7 +301,7 @@ struct Traversal {
 // `fetch_counter` is a zero-initialised global counter shared by all CTAs of the launch. Must be called by whole warps.
 template <bool ANY_HIT, class Source>
 BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
-                          unsigned int* fetch_counter, int* stack_smem) {
+                          unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
     int spill[STACK_LOCAL];
     Traversal<ANY_HIT> tr;
     tr.stack.smem = stack_smem;
@@ -331,7 +336,7 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
         if (__ballot_sync(0xffffffffu, has_ray) == 0)
             break;
         if (has_ray)
-            tr.run(a, coverage_by_material, TRAVERSAL_BUDGET);
+            tr.run(a, coverage_by_material, budget);
     }
 }
 
