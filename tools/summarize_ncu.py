@@ -43,10 +43,13 @@ def launches(csv_path, out_path):
     print("\n".join(lines))
 
 
-def kernel(rep_path, out_path, traffic_key=None):
+def kernel(rep_path, out_path, traffic_key=None, top=0):
     raw = subprocess.run(["ncu", "-i", rep_path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units, data = rows[0], rows[1], rows[2:]
+    if top:  # keep the `top` longest launches (tail launches of a wavefront step carry few rays)
+        ti = hdr.index("gpu__time_duration.sum")
+        data = sorted(data, key=lambda r: -float(r[ti]))[:top]
     lines = [f"# ncu --set full summary ({Path(rep_path).name})", "", f"kernel: `{data[0][hdr.index('Kernel Name')]}`", "",
              "| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |", "|---|---|" + "---:|" * len(data)]
     for k in KEYS:
@@ -81,4 +84,5 @@ if __name__ == "__main__":
         launches(sys.argv[2], sys.argv[3])
     else:
         key = sys.argv[sys.argv.index("--traffic-key") + 1] if "--traffic-key" in sys.argv else None
-        kernel(sys.argv[2], sys.argv[3], key)
+        top = int(sys.argv[sys.argv.index("--top") + 1]) if "--top" in sys.argv else 0
+        kernel(sys.argv[2], sys.argv[3], key, top)
