@@ -84,12 +84,10 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
         W = (float)__dsub_rn(BxAy, ByAx);
     }
 
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f))
-        return false;
-
+    // Straight-line from here on (no early exits): lanes of a warp test different triangles, and a lane that leaves early
+    // only idles until the others are done.
+    const bool outside = (U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f);
     const float det = __fadd_rn(__fadd_rn(U, V), W);
-    if (det == 0.0f)
-        return false;
 
     const float Az = __fmul_rn(s.Sz, Akz);
     const float Bz = __fmul_rn(s.Sz, Bkz);
@@ -100,7 +98,7 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
     t = __fmul_rn(T, rcp_det);
     u = __fmul_rn(V, rcp_det); // weight of p1
     v = __fmul_rn(W, rcp_det); // weight of p2
-    return true;
+    return !outside && det != 0.0f;
 }
 
 // ---- traversal ---------------------------------------------------------------------------------
@@ -236,22 +234,19 @@ struct Traversal {
             const float4* tri = reinterpret_cast<const float4*>(a.triangles + first + i);
             float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
             int primitive = __float_as_int(v0.w);
-            if (primitive == skip_primitive)
-                continue;
 #ifdef BPT_TRAVERSAL_STATS
             ++stat_triangles;
 #endif
             float t, u, v;
-            if (!watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v))
-                continue;
+            bool candidate = watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v) && primitive != skip_primitive;
             if (ANY_HIT) {
-                if (t > ray.tmin && t < ray.tmax) {
+                if (candidate && t > ray.tmin && t < ray.tmax) {
                     // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
                     float coverage = coverage_by_material[__float_as_int(v1.w)];
                     transmission *= 1.0f - coverage;
                     if (transmission < 0.0000001f) { transmission = 0.0f; return false; }
                 }
-            } else if (t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
+            } else if (candidate && t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
                 // hit.t starts at ray.tmax and hit.primitive at INT_MAX, so a first hit needs t < tmax.
                 hit.t = t; hit.primitive = primitive; hit.u = u; hit.v = v;
                 tmax = t;
@@ -273,15 +268,14 @@ struct Traversal {
                 if (!__any_sync(__activemask(), postponed == NODE_EMPTY && node >= 0))
                     break;
             }
-            if (postponed != NODE_EMPTY) {
+            if (postponed == NODE_EMPTY && is_leaf(node)) { postponed = node; node = stack.pop(); }
+            // One leaf loop for both the parked leaf and a leaf that is the current node, so that all lanes holding a leaf
+            // run the triangle tests together.
+            while (postponed != NODE_EMPTY) {
                 bool alive = intersect_leaf(a, coverage_by_material, postponed);
                 postponed = NODE_EMPTY;
                 if (!alive) { node = NODE_EMPTY; stack.sp = 0; }
-            }
-            while (is_leaf(node)) {
-                bool alive = intersect_leaf(a, coverage_by_material, node);
-                node = stack.pop();
-                if (!alive) { node = NODE_EMPTY; stack.sp = 0; }
+                else if (is_leaf(node)) { postponed = node; node = stack.pop(); }
             }
         }
     }
