@@ -64,7 +64,7 @@ assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SA
 
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
-EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_upload_mesh", "bpt_set_instances",
+EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
@@ -87,6 +87,7 @@ def load_library():
     lib.bpt_last_error.argtypes = [vp]; lib.bpt_last_error.restype = C.c_char_p
     lib.bpt_stream.argtypes = [vp]; lib.bpt_stream.restype = vp
     lib.bpt_set_tables.argtypes = [vp, vp, vp, vp]
+    lib.bpt_set_dielectric_tables.argtypes = [vp, vp, vp]
     lib.bpt_upload_mesh.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
     lib.bpt_set_instances.argtypes = [vp, vp, i32]
     lib.bpt_set_materials.argtypes = [vp, vp, i32]
@@ -131,6 +132,13 @@ def default_tables():
     return t[:1024].copy(), t[1024:2048].copy(), t[2048:].copy()
 
 
+def default_dielectric_tables():
+    """[into_light_medium | into_dense_medium], each 16^3 {total_rho, reflected_rho} pairs (oracle/export_tables.py)."""
+    t = np.fromfile(_PKG / "data" / "dielectric_tables.bin", dtype="<f4")
+    assert t.size == 2 * 8192
+    return t[:8192].copy(), t[8192:].copy()
+
+
 class Bpt:
     """One path tracer context on one CUDA device (mirrors OptiXRenderer::Renderer::initialize)."""
 
@@ -143,6 +151,7 @@ class Bpt:
         self.h = handle
         if tables:
             self.set_tables(*default_tables())
+            self.set_dielectric_tables(*default_dielectric_tables())
 
     def close(self):
         if getattr(self, "h", None):
@@ -173,6 +182,11 @@ class Bpt:
         a, b, c = _f32(ggx_with_fresnel), _f32(ggx), _f32(alpha)
         assert a.size == b.size == c.size == 1024
         self._check(self.lib.bpt_set_tables(self.h, _ptr(a), _ptr(b), _ptr(c)))
+
+    def set_dielectric_tables(self, into_light_medium, into_dense_medium):
+        a, b = _f32(into_light_medium), _f32(into_dense_medium)
+        assert a.size == b.size == 8192
+        self._check(self.lib.bpt_set_dielectric_tables(self.h, _ptr(a), _ptr(b)))
 
     # ---- scene ----
     def upload_mesh(self, mesh_id, indices, positions, normals=None, texcoords=None, tint_roughness=None):

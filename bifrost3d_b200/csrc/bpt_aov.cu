@@ -46,7 +46,7 @@ __device__ __forceinline__ unsigned int compact_by_2(unsigned int v) {
 __global__ void __launch_bounds__(TRACE_BLOCK) aov_kernel(AccelView accel, const float4* __restrict__ world_vertices, const ShadeTriangle* __restrict__ shade,
                                                           const float* __restrict__ normal_matrices, const Material* __restrict__ materials,
                                                           const float* __restrict__ coverage, const Light* __restrict__ lights, int analytic_light_count,
-                                                          const float* __restrict__ tables_, AovParams f, float4* __restrict__ out) {
+                                                          const float* __restrict__ tables_, const float2* __restrict__ dielectric_tables, AovParams f, float4* __restrict__ out) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     int spill[STACK_LOCAL];
     const ShadingTables tables = { tables_, tables_ + TABLE_FLOATS, tables_ + 2 * TABLE_FLOATS };
@@ -133,7 +133,11 @@ __global__ void __launch_bounds__(TRACE_BLOCK) aov_kernel(AccelView accel, const
             case BPT_AOV_ALBEDO: {
                 float abs_cos_theta = fabsf(dot(direction, shading_normal));
                 if (m.shading_model == SHADING_DIFFUSE) value = tint;
-                else {
+                else if (m.shading_model == SHADING_TRANSMISSIVE) {
+                    // SimpleRGPs.cu:293-295
+                    TransmissiveShading s = TransmissiveShading::create(dielectric_tables, tint, m.roughness * scale.w, m.specularity, abs_cos_theta);
+                    value = s.rho(dielectric_tables, abs_cos_theta);
+                } else {
                     DefaultShading s = DefaultShading::create(tables, tint, m.roughness * scale.w, m.specularity, m.metallic, unorm16_to_float(m.coat),
                                                               unorm16_to_float(m.coat_roughness), abs_cos_theta);
                     value = s.rho(tables, abs_cos_theta);
@@ -163,6 +167,8 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render_aov: bad arguments");
     if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render_aov: call bpt_build_accel first");
     if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render_aov: call bpt_set_tables first");
+    if (kind == BPT_AOV_ALBEDO && ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
+        return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render_aov: transmissive materials need bpt_set_dielectric_tables");
     cudaStream_t st = ctx->stream;
     const int64_t pixels = (int64_t)width * height;
     bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
@@ -191,7 +197,7 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
     for (uint32_t k = 0; k < sample_count; ++k) {
         f.accumulation_count = first_sample + k;
         aov_kernel<<<grid, TRACE_BLOCK, 0, st>>>(accel, ctx->accel.world_vertices.ptr, ctx->accel.shade.ptr, ctx->accel.normal_matrices.ptr, ctx->materials.ptr,
-                                                  d_cov, ctx->lights.ptr, ctx->light_count, ctx->tables.ptr, f, d_out);
+                                                  d_cov, ctx->lights.ptr, ctx->light_count, ctx->tables.ptr, ctx->dielectric_tables.ptr, f, d_out);
         accumulate_kernel_aov<<<grid, 256, 0, st>>>(d_out, ctx->accumulation.ptr, pixels);
         ctx->counters.kernel_launches += 2;
     }

@@ -56,6 +56,7 @@ struct BsdfBatchArgs {
     const float* wo; const float* wi; const float* tint; const float* rms; const float* coat; const float* u;
     float* eval_f; float* eval_pdf; float* sample_f; float* sample_pdf; float* sample_dir;
     const float* tables;
+    const float2* dielectric_tables;
     int64_t n;
 };
 
@@ -114,9 +115,19 @@ __global__ void __launch_bounds__(BSDF_BLOCK) bsdf_batch_kernel(BsdfBatchArgs a)
                 float roughness_factor = oren_nayar::uniform_lobe_roughness_factor(roughness);
                 r = oren_nayar::evaluate_with_pdf(tint, roughness, roughness_factor, wo, wi);
                 s = oren_nayar::sample(tint, roughness, roughness_factor, wo, f2(u.x, u.y));
-            } else {
+            } else if (KIND == BPT_BSDF_BURLEY) {
                 r = burley::evaluate_with_pdf(tint, roughness, wo, wi);
                 s = burley::sample(tint, roughness, wo, f2(u.x, u.y));
+            } else if (KIND == BPT_BSDF_TRANSMISSIVE_SHADING) {
+                // rms.y carries the signed cos_theta_o of TransmissiveShading::setup_shading.
+                TransmissiveShading shading = TransmissiveShading::create(a.dielectric_tables, tint, roughness, specularity, metallic);
+                r = shading.evaluate_with_pdf(wo, wi);
+                s = shading.sample(wo, u);
+            } else {
+                // rms.y carries ior_i_over_o of the combined GGX BSDF.
+                float alpha = ggx::alpha_from_roughness(roughness);
+                r = ggx_rt::evaluate_with_pdf(tint, alpha, specularity, metallic, wo, wi);
+                s = ggx_rt::sample(tint, alpha, specularity, metallic, wo, u);
             }
         }
         __syncthreads(); // everyone has consumed the inputs; reuse the staging areas for the outputs
@@ -338,7 +349,7 @@ void bpt_destroy(bpt_ctx* c) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     release_wavefront(ctx);
-    ctx->tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
+    ctx->tables.release(); ctx->dielectric_tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
     ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
@@ -374,6 +385,19 @@ int bpt_set_tables(bpt_ctx* c, const float* ggx_with_fresnel_rho, const float* g
     BPT_CUDA_CHECK(ctx, upload(ctx, ctx->tables, all.data(), all.size()));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_tables = true;
+    return BPT_OK;
+}
+
+int bpt_set_dielectric_tables(bpt_ctx* c, const float* into_light_medium, const float* into_dense_medium) {
+    Context* ctx = as_context(c);
+    if (!into_light_medium || !into_dense_medium) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_dielectric_tables: null table");
+    cudaSetDevice(ctx->device);
+    std::vector<float2> all(2 * DIELECTRIC_TABLE_FLOAT2S);
+    memcpy(all.data(), into_light_medium, DIELECTRIC_TABLE_FLOAT2S * sizeof(float2));
+    memcpy(all.data() + DIELECTRIC_TABLE_FLOAT2S, into_dense_medium, DIELECTRIC_TABLE_FLOAT2S * sizeof(float2));
+    BPT_CUDA_CHECK(ctx, upload(ctx, ctx->dielectric_tables, all.data(), all.size()));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_dielectric_tables = true;
     return BPT_OK;
 }
 
@@ -414,9 +438,11 @@ int bpt_set_instances(bpt_ctx* c, const bpt_instance* instances, int count) {
 int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     Context* ctx = as_context(c);
     if (count <= 0 || !materials) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: need at least material 0");
+    bool any_transmissive = false;
     for (int i = 0; i < count; ++i) {
-        if (materials[i].shading_model != SHADING_DEFAULT && materials[i].shading_model != SHADING_DIFFUSE)
-            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: only the Default and Diffuse shading models are implemented");
+        if (materials[i].shading_model > SHADING_TRANSMISSIVE)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: unknown shading model");
+        any_transmissive |= materials[i].shading_model == SHADING_TRANSMISSIVE;
         if (materials[i].tint_roughness_texture_id || materials[i].roughness_texture_id || materials[i].metallic_texture_id || materials[i].coverage_texture_id)
             return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: textured materials are not implemented");
     }
@@ -424,6 +450,7 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     ctx->host_materials.assign(materials, materials + count);
     BPT_CUDA_CHECK(ctx, upload(ctx, ctx->materials, materials, (size_t)count));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->has_transmissive_materials = any_transmissive;
     ctx->material_version++;
     ctx->accel.valid = false; // cull / coverage flags are baked into the triangle records
     return BPT_OK;
@@ -527,15 +554,17 @@ int bpt_bsdf_eval_sample_pdf(bpt_ctx* c, int kind, int64_t n, const float* wo, c
                              const float* coat, const float* u, float* eval_f, float* eval_pdf, float* sample_f, float* sample_pdf,
                              float* sample_dir, int on_device) {
     Context* ctx = as_context(c);
-    if (kind < 0 || kind > 3 || n < 0 || !wo || !wi || !tint || !rms || !u || !eval_f || !eval_pdf || !sample_f || !sample_pdf || !sample_dir)
+    if (kind < 0 || kind > BPT_BSDF_GGX || n < 0 || !wo || !wi || !tint || !rms || !u || !eval_f || !eval_pdf || !sample_f || !sample_pdf || !sample_dir)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_bsdf_eval_sample_pdf: bad arguments");
     if (kind == BPT_BSDF_DEFAULT_SHADING && !ctx->has_tables)
         return ctx->fail(BPT_ERROR_NOT_READY, "bpt_bsdf_eval_sample_pdf: call bpt_set_tables first");
+    if (kind == BPT_BSDF_TRANSMISSIVE_SHADING && !ctx->has_dielectric_tables)
+        return ctx->fail(BPT_ERROR_NOT_READY, "bpt_bsdf_eval_sample_pdf: call bpt_set_dielectric_tables first");
     if (n == 0) return BPT_OK;
     cudaSetDevice(ctx->device);
 
     BsdfBatchArgs a;
-    a.n = n; a.tables = ctx->tables.ptr;
+    a.n = n; a.tables = ctx->tables.ptr; a.dielectric_tables = ctx->dielectric_tables.ptr;
     float* staging = nullptr;
     if (on_device) {
         a.wo = wo; a.wi = wi; a.tint = tint; a.rms = rms; a.coat = coat; a.u = u;
@@ -564,7 +593,9 @@ int bpt_bsdf_eval_sample_pdf(bpt_ctx* c, int kind, int64_t n, const float* wo, c
     case BPT_BSDF_DEFAULT_SHADING: bsdf_batch_kernel<BPT_BSDF_DEFAULT_SHADING><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
     case BPT_BSDF_GGX_R: bsdf_batch_kernel<BPT_BSDF_GGX_R><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
     case BPT_BSDF_OREN_NAYAR: bsdf_batch_kernel<BPT_BSDF_OREN_NAYAR><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
-    default: bsdf_batch_kernel<BPT_BSDF_BURLEY><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
+    case BPT_BSDF_BURLEY: bsdf_batch_kernel<BPT_BSDF_BURLEY><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
+    case BPT_BSDF_TRANSMISSIVE_SHADING: bsdf_batch_kernel<BPT_BSDF_TRANSMISSIVE_SHADING><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
+    default: bsdf_batch_kernel<BPT_BSDF_GGX><<<grid, BSDF_BLOCK, 0, ctx->stream>>>(a); break;
     }
     ctx->counters.kernel_launches++;
     BPT_CUDA_CHECK(ctx, cudaGetLastError());

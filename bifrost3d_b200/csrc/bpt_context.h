@@ -93,6 +93,10 @@ struct Context {
     // Tables: [ggx_with_fresnel_rho | ggx_rho | estimate_alpha], 3 x 1024 floats.
     DeviceBuffer<float> tables;
     bool has_tables = false;
+    // Dielectric GGX rho: [into_light_medium | into_dense_medium], 2 x 16^3 float2 (TransmissiveShading).
+    DeviceBuffer<float2> dielectric_tables;
+    bool has_dielectric_tables = false;
+    bool has_transmissive_materials = false;
     DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
 
     std::map<int, HostMesh> meshes;

@@ -74,6 +74,7 @@ struct SceneView {
     int analytic_light_count; // lights that rays can hit
     EnvironmentView env;
     const float* __restrict__ tables;
+    const float2* __restrict__ dielectric_tables;
     const float4* __restrict__ nee_offsets;
 };
 
@@ -278,8 +279,8 @@ __device__ __forceinline__ float3 oct_decode(const int16_t e[2]) {
 __device__ __forceinline__ unsigned char unorm8(float v) { return (unsigned char)(saturate(v) * 255.0f + 0.5f); }
 
 // sample_single_light, MonteCarlo.cu:61-87
-__device__ LightSample sample_single_light(const SceneView& s, const ShadingTables& tables, const DefaultShading& material, float3 position,
-                                           float3 wo, const Tbn& tbn, float3 u) {
+template <typename Bsdf>
+__device__ LightSample sample_single_light(const SceneView& s, const Bsdf& material, float3 position, float3 wo, const Tbn& tbn, float3 u) {
     int light_index = min(s.light_count - 1, int(u.z * s.light_count));
     Light light = s.lights[light_index];
     LightSample ls = light_sample_radiance(light, s.env, position, f2(u.x, u.y));
@@ -302,7 +303,9 @@ __device__ LightSample sample_single_light(const SceneView& s, const ShadingTabl
 #ifndef BPT_SHADE_MIN_BLOCKS
 #define BPT_SHADE_MIN_BLOCKS 8
 #endif
-template <bool SURFACE>
+// TRANSMISSIVE: the scene holds ShadingModel::Transmissive materials (transmissive_closest_hit, MonteCarlo.cu:259-268).
+// Scenes without them run the instantiation that only knows DefaultShading.
+template <bool SURFACE, bool TRANSMISSIVE>
 __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
     __shared__ __align__(16) float s_tables[SURFACE ? 3 * TABLE_FLOATS : 4];
     if (SURFACE) {
@@ -422,9 +425,23 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                     // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
                     // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
                     Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
-                    const DefaultShading material = material_parameter.shading_model == SHADING_DIFFUSE
-                        ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
-                        : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                    const auto material = [&]() {
+                        if constexpr (TRANSMISSIVE) {
+                            SurfaceBsdf bsdf;
+                            bsdf.transmissive = material_parameter.shading_model == SHADING_TRANSMISSIVE;
+                            if (bsdf.transmissive)
+                                bsdf.transmission = TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter,
+                                                                                            tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                            else
+                                bsdf.standard = material_parameter.shading_model == SHADING_DIFFUSE
+                                    ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
+                                    : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                            return bsdf;
+                        } else
+                            return material_parameter.shading_model == SHADING_DIFFUSE
+                                ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
+                                : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                    }();
 
                     radiance += throughput * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
 
@@ -436,7 +453,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                             float4 shift = __ldg(s.nee_offsets + k);
                             float4 r = light_random_base + shift; // toroidal_shift, Utils.h:46-49
                             r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
-                            LightSample candidate = sample_single_light(s, tables, material, world_intersection_point, wo, tbn, f3(r));
+                            LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
                             float light_weight = sum(light_sample.radiance);
                             float new_light_weight = sum(candidate.radiance);
                             float new_light_probability = new_light_weight / (light_weight + new_light_weight);
@@ -565,6 +582,8 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     if (!camera || !settings || width <= 0 || height <= 0) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: bad arguments");
     if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_build_accel first");
     if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_set_tables first");
+    if (ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
+        return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: transmissive materials need bpt_set_dielectric_tables");
     if (settings->next_event_sample_count < 0 || settings->next_event_sample_count > 256)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: next_event_sample_count must be in [0, 256]");
     cudaStream_t st = ctx->stream;
@@ -632,6 +651,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         }
     }
     s.tables = ctx->tables.ptr;
+    s.dielectric_tables = ctx->dielectric_tables.ptr;
     s.nee_offsets = ctx->nee_offsets.ptr;
 
     WavefrontView w = {};
@@ -668,8 +688,11 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
                 if (ctx->profiling) { first_event = ctx->stage_event(it * 4 + 0); cudaEventRecord(ctx->stage_events[first_event], st); }
                 extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
-                shade_kernel<false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                shade_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                shade_kernel<false, false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                if (ctx->has_transmissive_materials)
+                    shade_kernel<true, true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                else
+                    shade_kernel<true, false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
                 shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);

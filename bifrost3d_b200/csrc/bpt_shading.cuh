@@ -508,6 +508,266 @@ BPT_D BsdfSample sample(float3 tint, float roughness, float3 wo, float2 u) {
 } // namespace burley
 
 // ------------------------------------------------------------------------------------------------
+// Combined reflection + transmission GGX for dielectrics (GGX.h:258-443), the BSDF of ShadingModel::Transmissive.
+// Out of line: only transmissive materials pay for it.
+// ------------------------------------------------------------------------------------------------
+BPT_D float signf(float v) { return v >= 0.0f ? 1.0f : -1.0f; }                     // Utils.h:76-78
+BPT_D bool same_hemisphere(float3 wo, float3 wi) { return wo.z * wi.z >= 0.0f; }     // Utils.h:55-57
+
+// Utils.h:192-204
+BPT_D float dielectric_schlick_fresnel(float incident_specular, float abs_cos_theta, float ior_i_over_o) {
+    float sin2_theta = 1.0f - pow2(abs_cos_theta);
+    if (sin2_theta >= pow2(ior_i_over_o))
+        return 1.0f;
+    float t = pow5(1.0f - abs_cos_theta);
+    return (1.0f - t) * incident_specular + t;
+}
+
+// Utils.h:242-256: refraction about the normal (0, 0, 1).
+BPT_D bool refract_z(float3& refraction_direction, float3 wi, float ior_i_over_o) {
+    float normal_z = 1.0f;
+    float cos_theta_i = wi.z;
+    if (cos_theta_i > 0.0f) {
+        normal_z = -1.0f;
+        cos_theta_i = -cos_theta_i;
+    } else
+        ior_i_over_o = 1.0f / ior_i_over_o;
+    float k = 1.0f - ior_i_over_o * ior_i_over_o * (1.0f - cos_theta_i * cos_theta_i);
+    refraction_direction = ior_i_over_o * wi - f3(0.0f, 0.0f, (ior_i_over_o * cos_theta_i + sqrtf(k)) * normal_z);
+    return k >= 0.0f;
+}
+
+// optix::refract(r, i, n, ior) as the reference's host build uses it (GGX.h:232,415).
+BPT_D bool refract_n(float3& r, float3 i, float3 n, float ior) {
+    float3 nn = n;
+    float negNdotV = dot(i, nn);
+    float eta;
+    if (negNdotV > 0.0f) {
+        eta = ior;
+        nn = -n;
+        negNdotV = -negNdotV;
+    } else
+        eta = 1.0f / ior;
+    const float k = 1.0f - eta * eta * (1.0f - negNdotV * negNdotV);
+    if (k < 0.0f) {
+        r = f3(0.0f);
+        return false;
+    }
+    r = normalize(eta * i - (eta * negNdotV + sqrtf(k)) * nn);
+    return true;
+}
+
+namespace dist {
+// Sampling Visible GGX Normals with Spherical Caps (Distributions.h:347-381), isotropic alpha.
+BPT_D float3 ggx_vndf_sample_halfway(float alpha, float3 wo, float2 u) {
+    float3 wo_std = normalize(f3(alpha * wo.x, alpha * wo.y, wo.z));
+    float phi = 2.0f * PI_F * u.y;
+    float z = fmaf(1.0f - u.x, 1.0f + wo_std.z, -wo_std.z);
+    float sin_theta = sqrtf(clampf(1.0f - z * z, 0.0f, 1.0f));
+    float sin_phi, cos_phi;
+    sincos_(phi, sin_phi, cos_phi);
+    float3 c = f3(sin_theta * cos_phi, sin_theta * sin_phi, z);
+    float3 wi_std = c + wo_std;
+    return normalize(f3(alpha * wi_std.x, alpha * wi_std.y, fmaxf(0.0f, wi_std.z)));
+}
+BPT_D float ggx_vndf_pdf(float alpha, float3 wo, float3 halfway) {
+    float recip_G1 = 1.0f + ggx_lambda(alpha, wo);
+    float D = ggx_D(alpha, halfway);
+    return dot(wo, halfway) * D / (recip_G1 * fabsf(wo.z));
+}
+} // namespace dist
+
+namespace ggx_rt {
+
+BPT_D float transmission_pdf_scale(float ior_i_over_o, float3 wo, float3 wi, float3 halfway) {
+    float sqrt_denom = dot(wo, halfway) + ior_i_over_o * dot(wi, halfway);
+    return pow2(ior_i_over_o / sqrt_denom) * fabsf(dot(wi, halfway));
+}
+
+BPT_D float3 compute_halfway_vector(float ior_i_over_o, float3 wo, float3 wi) {
+    float3 halfway = normalize(wo + ior_i_over_o * wi);
+    if (halfway.z < 0.0f)
+        halfway = -halfway;
+    return halfway;
+}
+
+BPT_D float normalize_reflection_probability(float reflection_probability, float3 transmission_tint) {
+    float transmission_probability = 1.0f - reflection_probability;
+    float scaled_transmission_probability = sum(transmission_tint) * transmission_probability;
+    float scaled_reflection_probability = 3.0f * reflection_probability;
+    return scaled_reflection_probability / (scaled_reflection_probability + scaled_transmission_probability);
+}
+
+BPT_D float evaluate(float alpha, float specularity, float ior_i_over_o, float3 wo, float3 wi) {
+    if (ggx::effectively_smooth(alpha) || wo.z == 0.0f || wi.z == 0.0f)
+        return 0.0f;
+    bool entering = wo.z >= 0.0f;
+    if (!entering) {
+        wo.z = -wo.z;
+        wi.z = -wi.z;
+    }
+    bool is_reflection = same_hemisphere(wo, wi);
+    float halfway_ior = is_reflection ? 1.0f : ior_i_over_o;
+    float3 halfway = compute_halfway_vector(halfway_ior, wo, wi);
+
+    float G = ggx::height_correlated_G(alpha, wo, wi);
+    float D = dist::ggx_D(alpha, halfway);
+    float F = dielectric_schlick_fresnel(specularity, dot(wo, halfway), ior_i_over_o);
+
+    if (is_reflection)
+        return F * D * G / (4.0f * wo.z * wi.z);
+    if (dot(wi, halfway) * wi.z <= 0.0f || dot(wo, halfway) * wo.z <= 0.0f)
+        return 0.0f;
+    float f1 = fabsf(dot(wo, halfway) * dot(wi, halfway) / (wo.z * wi.z));
+    float f2 = (1.0f - F) * G * D * pow2(ior_i_over_o / (dot(wo, halfway) + ior_i_over_o * dot(wi, halfway)));
+    return f1 * f2;
+}
+
+BPT_D float3 evaluate(float3 transmission_tint, float alpha, float specularity, float ior_i_over_o, float3 wo, float3 wi) {
+    float f = evaluate(alpha, specularity, ior_i_over_o, wo, wi);
+    bool is_transmission = signf(wo.z) != signf(wi.z);
+    return f * (is_transmission ? transmission_tint : f3(1.0f));
+}
+
+BPT_D Pdf pdf(float3 transmission_tint, float alpha, float specularity, float ior_i_over_o, float3 wo, float3 wi) {
+    if (ggx::effectively_smooth(alpha))
+        return Pdf::invalid();
+    bool entering = wo.z >= 0.0f;
+    if (!entering) {
+        wo.z = -wo.z;
+        wi.z = -wi.z;
+    }
+    bool is_reflection = same_hemisphere(wo, wi);
+    float halfway_ior = is_reflection ? 1.0f : ior_i_over_o;
+    float3 halfway = compute_halfway_vector(halfway_ior, wo, wi);
+
+    bool backfacing_microfacet = !is_reflection && (dot(wo, halfway) < 0.0f || dot(wi, halfway) >= 0.0f);
+    if (backfacing_microfacet)
+        return Pdf::invalid();
+
+    float p = dist::ggx_vndf_pdf(alpha, wo, halfway);
+    float reflection_probability = dielectric_schlick_fresnel(specularity, dot(wo, halfway), ior_i_over_o);
+    float normalized_reflection_probability = normalize_reflection_probability(reflection_probability, transmission_tint);
+    p *= is_reflection ? normalized_reflection_probability : (1.0f - normalized_reflection_probability);
+    if (is_reflection)
+        p *= 1.0f / (4.0f * dot(wo, halfway));
+    else
+        p *= transmission_pdf_scale(ior_i_over_o, wo, wi, halfway);
+    return Pdf(p);
+}
+
+BPT_CALL BsdfResponse evaluate_with_pdf(float3 transmission_tint, float alpha, float specularity, float ior_i_over_o, float3 wo, float3 wi) {
+    BsdfResponse r;
+    r.reflectance = evaluate(transmission_tint, alpha, specularity, ior_i_over_o, wo, wi);
+    r.pdf = pdf(transmission_tint, alpha, specularity, ior_i_over_o, wo, wi);
+    return r;
+}
+
+BPT_CALL BsdfSample sample(float3 transmission_tint, float alpha, float specularity, float ior_i_over_o, float3 wo, float3 u) {
+    BsdfSample s;
+    s.reflectance = f3(0.0f); s.pdf = Pdf(0.0f); s.direction = f3(0.0f);
+
+    bool entering = wo.z >= 0.0f;
+    if (!entering)
+        wo.z = -wo.z;
+
+    if (ggx::effectively_smooth(alpha)) {
+        float reflection_probability = dielectric_schlick_fresnel(specularity, fabsf(wo.z), ior_i_over_o);
+        float normalized_reflection_probability = normalize_reflection_probability(reflection_probability, transmission_tint);
+        bool is_reflection = u.z < normalized_reflection_probability;
+        if (is_reflection) {
+            s.pdf = Pdf::delta_dirac(normalized_reflection_probability);
+            s.direction = f3(-wo.x, -wo.y, wo.z);
+        } else {
+            s.pdf = Pdf::delta_dirac(1.0f - normalized_reflection_probability);
+            if (!refract_z(s.direction, -wo, ior_i_over_o))
+                return bsdf_sample_none();
+        }
+        float reflectance = (is_reflection ? reflection_probability : (1.0f - reflection_probability)) / fabsf(s.direction.z);
+        s.reflectance = f3(reflectance);
+    } else {
+        float3 halfway = dist::ggx_vndf_sample_halfway(alpha, wo, f2(u.x, u.y));
+        float p = dist::ggx_vndf_pdf(alpha, wo, halfway);
+
+        float reflection_probability = dielectric_schlick_fresnel(specularity, dot(wo, halfway), ior_i_over_o);
+        float normalized_reflection_probability = normalize_reflection_probability(reflection_probability, transmission_tint);
+        bool is_reflection = u.z < normalized_reflection_probability;
+
+        if (is_reflection) {
+            s.direction = reflect(-wo, halfway);
+            p *= normalized_reflection_probability / (4.0f * dot(wo, halfway));
+        } else {
+            if (!refract_n(s.direction, -wo, halfway, ior_i_over_o))
+                return bsdf_sample_none();
+            p *= 1.0f - normalized_reflection_probability;
+            p *= transmission_pdf_scale(ior_i_over_o, wo, s.direction, halfway);
+        }
+        s.pdf = Pdf(p);
+
+        bool energyloss = is_reflection ? s.direction.z < 0.0f : s.direction.z >= 0.0f;
+        if (energyloss)
+            return bsdf_sample_none();
+
+        float f = evaluate(alpha, specularity, ior_i_over_o, wo, s.direction);
+        s.reflectance = f3(f);
+    }
+
+    bool is_transmission = signf(wo.z) != signf(s.direction.z);
+    if (is_transmission)
+        s.reflectance *= transmission_tint;
+    if (!entering)
+        s.direction.z = -s.direction.z;
+    return s;
+}
+
+} // namespace ggx_rt
+
+// Dielectric rho tables (Fittings.h:27-46, DielectricGGXRho.cpp:1086-1110): two 16 x 16 x 16 tables of
+// {total rho, reflected rho}, sampled trilinearly like Math::ImageSampling::trilinear (ImageSampling.h:43-60).
+constexpr int DIELECTRIC_DIM = 16;
+constexpr int DIELECTRIC_TABLE_FLOAT2S = DIELECTRIC_DIM * DIELECTRIC_DIM * DIELECTRIC_DIM;
+
+BPT_D float2 bilinear2(const float2* __restrict__ pixels, int width, int height, float u, float v) {
+    u = clampf(u, 0.0f, 1.0f);
+    float u_coord = u * (width - 1);
+    int lower_u = int(u_coord);
+    int upper_u = min(lower_u + 1, width - 1);
+    v = clampf(v, 0.0f, 1.0f);
+    float v_coord = v * (height - 1);
+    int lower_v = int(v_coord);
+    int upper_v = min(lower_v + 1, height - 1);
+    float u_t = u_coord - lower_u;
+    const float2* lower_row = pixels + lower_v * width;
+    float2 a0 = lower_row[lower_u], a1 = lower_row[upper_u];
+    float2 lower_pixel = make_float2(a0.x + (a1.x - a0.x) * u_t, a0.y + (a1.y - a0.y) * u_t);
+    const float2* upper_row = pixels + upper_v * width;
+    float2 b0 = upper_row[lower_u], b1 = upper_row[upper_u];
+    float2 upper_pixel = make_float2(b0.x + (b1.x - b0.x) * u_t, b0.y + (b1.y - b0.y) * u_t);
+    float v_t = v_coord - lower_v;
+    return make_float2(lower_pixel.x + (upper_pixel.x - lower_pixel.x) * v_t, lower_pixel.y + (upper_pixel.y - lower_pixel.y) * v_t);
+}
+
+// tables: [into_light 16^3 | into_dense 16^3] float2. Returns {total_rho, reflected_rho}.
+BPT_CALL float2 dielectric_rho_fetch(const float2* __restrict__ tables, float abs_cos_theta, float roughness, float ior_i_over_o) {
+    const float2* table = tables;
+    float w;
+    if (ior_i_over_o < 1.0f)
+        w = (ior_i_over_o - 0.331492f) / 0.457982f;
+    else {
+        w = (ior_i_over_o - 1.26667f) / 1.75f;
+        table = tables + DIELECTRIC_TABLE_FLOAT2S;
+    }
+    w = clampf(w, 0.0f, 1.0f);
+    float w_coord = w * (DIELECTRIC_DIM - 1);
+    int lower_w = int(w_coord);
+    int upper_w = min(lower_w + 1, DIELECTRIC_DIM - 1);
+    float2 lower_pixel = bilinear2(table + lower_w * DIELECTRIC_DIM * DIELECTRIC_DIM, DIELECTRIC_DIM, DIELECTRIC_DIM, abs_cos_theta, roughness);
+    float2 upper_pixel = bilinear2(table + upper_w * DIELECTRIC_DIM * DIELECTRIC_DIM, DIELECTRIC_DIM, DIELECTRIC_DIM, abs_cos_theta, roughness);
+    float w_t = w_coord - lower_w;
+    return make_float2(lower_pixel.x + (upper_pixel.x - lower_pixel.x) * w_t, lower_pixel.y + (upper_pixel.y - lower_pixel.y) * w_t);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Path regularisation: smallest GGX roughness whose bounded-VNDF peak PDF stays below a hint
 // (ShadingModels/Utils.h:104-130, host branch; EstimateGGXBoundedVNDFAlpha.cpp encode_PDF / estimate_alpha).
 // ------------------------------------------------------------------------------------------------
@@ -742,6 +1002,78 @@ struct DefaultShading {
         }
         return s;
     }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Transmissive shading: rough dielectric interface with tinted transmission. TransmissiveShading.h:22-98
+// ------------------------------------------------------------------------------------------------
+struct TransmissiveShading {
+    float3 transmission_tint;
+    float specularity;
+    float ggx_alpha;
+    float ior_i_over_o;
+    float energy_loss_adjustment;
+
+    BPT_D static TransmissiveShading create(const float2* __restrict__ dielectric_tables, float3 tint, float roughness, float specularity_, float cos_theta_o) {
+        TransmissiveShading s;
+        s.transmission_tint = tint;
+        s.specularity = specularity_;
+        s.ggx_alpha = ggx::alpha_from_roughness(roughness);
+        float medium_ior = dielectric_ior_from_specularity(specularity_);
+        bool entering = cos_theta_o >= 0.0f;
+        float ior_o = entering ? AIR_IOR : medium_ior;
+        float ior_i = entering ? medium_ior : AIR_IOR;
+        s.ior_i_over_o = ior_i / ior_o;
+        float rho = dielectric_rho_fetch(dielectric_tables, fabsf(cos_theta_o), roughness, s.ior_i_over_o).x;
+        s.energy_loss_adjustment = 1.0f / rho;
+        return s;
+    }
+
+    // Renderer constructor (TransmissiveShading.h:51-66) for untextured materials.
+    BPT_D static TransmissiveShading create_regularized(const ShadingTables& t, const float2* __restrict__ dielectric_tables, const Material& m,
+                                                        float4 tint_and_roughness_scale, float cos_theta_o, Pdf max_pdf_hint) {
+        float min_roughness = ggx_min_roughness_from_pdf(t, fabsf(cos_theta_o), max_pdf_hint);
+        float3 tint = f3(m.tint[0] * tint_and_roughness_scale.x, m.tint[1] * tint_and_roughness_scale.y, m.tint[2] * tint_and_roughness_scale.z);
+        float roughness = fmaxf(m.roughness * tint_and_roughness_scale.w, min_roughness);
+        return create(dielectric_tables, tint, roughness, m.specularity, cos_theta_o);
+    }
+
+    BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
+        if (wo.z < 0.000001f)
+            return bsdf_response_none();
+        BsdfResponse r = ggx_rt::evaluate_with_pdf(transmission_tint, ggx_alpha, specularity, ior_i_over_o, wo, wi);
+        r.reflectance *= energy_loss_adjustment;
+        return r;
+    }
+
+    BPT_D BsdfSample sample(float3 wo, float3 u) const {
+        if (wo.z < 0.000001f)
+            return bsdf_sample_none();
+        BsdfSample s = ggx_rt::sample(transmission_tint, ggx_alpha, specularity, ior_i_over_o, wo, u);
+        s.reflectance *= energy_loss_adjustment;
+        return s;
+    }
+
+    BPT_D float3 rho(const float2* __restrict__ dielectric_tables, float abs_cos_theta_o) const {
+        float roughness = ggx::roughness_from_alpha(ggx_alpha);
+        float2 r = dielectric_rho_fetch(dielectric_tables, abs_cos_theta_o, roughness, ior_i_over_o);
+        float reflection = r.y / r.x;
+        return f3(reflection) + (1.0f - reflection) * transmission_tint;
+    }
+};
+
+// One surface BSDF of any shading model (Material::ShadingModel, Types.h:360-364): the integrator's `material`.
+struct SurfaceBsdf {
+    bool transmissive;
+    union {
+        DefaultShading standard;        // Default and Diffuse
+        TransmissiveShading transmission;
+    };
+    BPT_D SurfaceBsdf() {}
+    BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
+        return transmissive ? transmission.evaluate_with_pdf(wo, wi) : standard.evaluate_with_pdf(wo, wi);
+    }
+    BPT_D BsdfSample sample(float3 wo, float3 u) const { return transmissive ? transmission.sample(wo, u) : standard.sample(wo, u); }
 };
 
 } // namespace bpt

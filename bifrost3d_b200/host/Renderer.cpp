@@ -94,6 +94,9 @@ struct Renderer::Implementation {
         using namespace Assets::Shading;
         if (bpt_set_tables(ctx, Rho::GGX_with_fresnel, Rho::GGX, Estimate_GGX_bounded_VNDF_alpha::alphas) != BPT_OK)
             throw optix::Exception(bpt_last_error(ctx));
+        // Dielectric GGX rho (Renderer.cpp:436-466): Vector2f arrays are {total_rho, reflected_rho} float pairs.
+        if (bpt_set_dielectric_tables(ctx, &Rho::dielectric_GGX_into_light_medium[0].x, &Rho::dielectric_GGX_into_dense_medium[0].x) != BPT_OK)
+            throw optix::Exception(bpt_last_error(ctx));
         context = optix::Context(new optix::ContextObj());
     }
     ~Implementation() { bpt_destroy(ctx); }

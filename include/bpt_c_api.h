@@ -36,7 +36,7 @@ typedef enum bpt_status {
 /* Types.h:353-416 `Material` (64 bytes). Texture ids must be 0: textures are a "next" row. */
 typedef struct bpt_material {
     uint16_t flags;              /* 1 = ThinWalled, 2 = Cutout */
-    uint16_t shading_model;      /* 0 = Default, 1 = Diffuse, 2 = Transmissive (not implemented: rejected) */
+    uint16_t shading_model;      /* 0 = Default, 1 = Diffuse, 2 = Transmissive (needs bpt_set_dielectric_tables) */
     float tint[3];
     float roughness;
     int32_t tint_roughness_texture_id;
@@ -122,6 +122,11 @@ void* bpt_stream(bpt_ctx* ctx);
  * Bifrost::Assets::Shading::{Rho::GGX_with_fresnel, Rho::GGX, Estimate_GGX_bounded_VNDF_alpha::alphas}
  * (core/Bifrost/Bifrost/Assets/Shading/Fittings.h:58-74). */
 int bpt_set_tables(bpt_ctx* ctx, const float* ggx_with_fresnel_rho, const float* ggx_rho, const float* estimate_ggx_alpha);
+/* Dielectric GGX rho tables that Renderer.cpp:436-466 uploads as one 3D texture. Each 16x16x16 {total_rho, reflected_rho}
+ * pairs (8192 floats), [ior_i_over_o][roughness][cos_theta], from Bifrost::Assets::Shading::Rho::
+ * {dielectric_GGX_into_light_medium, dielectric_GGX_into_dense_medium} (Fittings.h:36-46). Required before a
+ * Transmissive material is rendered; sampled trilinearly like Rho::sample_dielectric_GGX (DielectricGGXRho.cpp:1087-1110). */
+int bpt_set_dielectric_tables(bpt_ctx* ctx, const float* into_light_medium, const float* into_dense_medium);
 
 /* ---- scene upload (Renderer::handle_updates, Renderer.cpp:578-1205) ---------------------------- */
 
@@ -179,9 +184,14 @@ int bpt_get_counters(bpt_ctx* ctx, bpt_counters* out, int reset);
 
 /* ---- batched unit entry points (parity tests and the C1 workload) ------------------------------ */
 
-enum { BPT_BSDF_DEFAULT_SHADING = 0, BPT_BSDF_GGX_R = 1, BPT_BSDF_OREN_NAYAR = 2, BPT_BSDF_BURLEY = 3 };
+enum { BPT_BSDF_DEFAULT_SHADING = 0, BPT_BSDF_GGX_R = 1, BPT_BSDF_OREN_NAYAR = 2, BPT_BSDF_BURLEY = 3,
+       BPT_BSDF_TRANSMISSIVE_SHADING = 4, BPT_BSDF_GGX = 5 };
 /* evaluate_with_PDF(wo, wi) and sample(wo, u) for n tuples. wo, wi, tint, u: 3n floats; rms: {roughness, metallic,
  * specularity} 3n floats; coat (nullable): {coat, coat_roughness} 2n floats.
+ * BPT_BSDF_TRANSMISSIVE_SHADING (TransmissiveShading.h:22-98): rms = {roughness, cos_theta_o, specularity}, where the
+ * sign of cos_theta_o says whether the path enters (>= 0) or leaves the medium, as in MonteCarlo.cu:190-191.
+ * BPT_BSDF_GGX (combined reflection + transmission, GGX.h:258-443): tint = transmission tint,
+ * rms = {roughness, ior_i_over_o, specularity}.
  * Outputs: eval_f 3n, eval_pdf n, sample_f 3n, sample_pdf n, sample_dir 3n.
  * on_device != 0: all pointers are device pointers and nothing is copied. */
 int bpt_bsdf_eval_sample_pdf(bpt_ctx* ctx, int kind, int64_t n, const float* wo, const float* wi, const float* tint,

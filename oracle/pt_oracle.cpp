@@ -16,6 +16,9 @@
 #include <OptiXRenderer/RNG.h>
 #include <OptiXRenderer/Intersect.h>
 #include <OptiXRenderer/Shading/ShadingModels/DiffuseShading.h>
+#include <OptiXRenderer/Shading/BSDFs/GGX.h>
+#include <OptiXRenderer/Shading/ShadingModels/Utils.h> // DielectricRho, which TransmissiveShading.h uses without including
+#include <OptiXRenderer/Shading/ShadingModels/TransmissiveShading.h>
 #include <OptiXRenderer/Shading/LightSources/DirectionalLightImpl.h>
 #include <OptiXRenderer/Shading/LightSources/SphereLightImpl.h>
 #include <OptiXRenderer/Shading/LightSources/SpotLightImpl.h>
@@ -585,6 +588,15 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
         // DiffuseMaterialCreator::create, MonteCarlo.cu:250-255
         float4 tint_roughness = make_float4(material_parameter.tint, material_parameter.roughness) * tint_and_roughness_scale;
         light_and_bsdf(Shading::ShadingModels::DiffuseShading(make_float3(tint_roughness), tint_roughness.w));
+    } else if (material_parameter.shading_model == Material::ShadingModel::Transmissive) {
+        // TransmissiveMaterialCreator::create, MonteCarlo.cu:261-266 -> TransmissiveShading::initialize_with_max_PDF_hint
+        // (TransmissiveShading.h:51-66, GPU_DEVICE only) restated through the class' public setup_shading.
+        PDF max_PDF_hint = payload.bsdf_PDF * st.settings->path_regularization_pdf_scale;
+        float min_roughness = Shading::ShadingModels::GGXMinimumRoughness::from_PDF(abs(cos_theta), max_PDF_hint);
+        float4 tint_roughness = make_float4(material_parameter.tint, material_parameter.roughness) * tint_and_roughness_scale;
+        Shading::ShadingModels::TransmissiveShading transmissive(material_parameter, cos_theta);
+        transmissive.setup_shading(make_float3(tint_roughness), fmaxf(tint_roughness.w, min_roughness), material_parameter.specularity, cos_theta);
+        light_and_bsdf(transmissive);
     } else {
         PDF max_PDF_hint = payload.bsdf_PDF * st.settings->path_regularization_pdf_scale;
         light_and_bsdf(create_default_shading(material_parameter, tint_and_roughness_scale, cos_theta, max_PDF_hint));

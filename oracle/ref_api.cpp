@@ -10,6 +10,7 @@
 //   OrenNayar      .../Shading/BSDFs/OrenNayar.h:61-127
 //   Burley         .../Shading/BSDFs/Burley.h:35-71
 //   DefaultShading .../Shading/ShadingModels/DefaultShading.h:149-280
+//   TransmissiveShading .../Shading/ShadingModels/TransmissiveShading.h:22-98, combined GGX .../BSDFs/GGX.h:258-443
 //   lights         .../Shading/LightSources/{Sphere,Spot,Directional}LightImpl.h
 //   rho tables     core/Bifrost/Bifrost/Assets/Shading/Fittings.h:16-76
 // Array arguments are plain host pointers; vectors are packed xyz triples.
@@ -33,6 +34,9 @@
 #define private public
 #include <OptiXRenderer/Shading/ShadingModels/DefaultShading.h>
 #undef private
+#include <OptiXRenderer/Shading/BSDFs/GGX.h>
+#include <OptiXRenderer/Shading/ShadingModels/Utils.h> // DielectricRho, which TransmissiveShading.h uses without including
+#include <OptiXRenderer/Shading/ShadingModels/TransmissiveShading.h>
 
 #include <Bifrost/Assets/Shading/Fittings.h>
 #include <Bifrost/Assets/Image.h>
@@ -102,6 +106,23 @@ void ref_get_tables(float* ggx_with_fresnel_rho, float* ggx_rho, float* estimate
     if (ggx_with_fresnel_rho) memcpy(ggx_with_fresnel_rho, Rho::GGX_with_fresnel, sizeof(float) * dims[0] * dims[1]);
     if (ggx_rho) memcpy(ggx_rho, Rho::GGX, sizeof(float) * dims[2] * dims[3]);
     if (estimate_alpha) memcpy(estimate_alpha, Estimate_GGX_bounded_VNDF_alpha::alphas, sizeof(float) * dims[4] * dims[5]);
+}
+
+// Dielectric GGX rho (Fittings.h:36-46): two 16x16x16 tables of {total_rho, reflected_rho}.
+void ref_get_dielectric_tables(float* into_light_medium, float* into_dense_medium, int* dims /*[3]*/) {
+    using namespace Bifrost::Assets::Shading;
+    dims[0] = Rho::dielectric_GGX_angle_sample_count; dims[1] = Rho::dielectric_GGX_roughness_sample_count;
+    dims[2] = Rho::dielectric_GGX_ior_i_over_o_sample_count;
+    size_t bytes = sizeof(float) * 2 * dims[0] * dims[1] * dims[2];
+    if (into_light_medium) memcpy(into_light_medium, Rho::dielectric_GGX_into_light_medium, bytes);
+    if (into_dense_medium) memcpy(into_dense_medium, Rho::dielectric_GGX_into_dense_medium, bytes);
+}
+
+void ref_sample_dielectric_rho(int64_t n, const float* cos_theta, const float* roughness, const float* ior_i_over_o, float* out_total_reflected) {
+    for (int64_t i = 0; i < n; ++i) {
+        auto rho = Bifrost::Assets::Shading::Rho::sample_dielectric_GGX(cos_theta[i], roughness[i], ior_i_over_o[i]);
+        out_total_reflected[2 * i] = rho.total_rho; out_total_reflected[2 * i + 1] = rho.reflected_rho;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -185,9 +206,20 @@ void ref_bsdf_eval_sample_pdf(int kind, int64_t n, const float* wo, const float*
         } else if (kind == 2) {
             r = BSDFs::OrenNayar::evaluate_with_PDF(ld3(tint, i), rms[3 * i], o, in);
             s = BSDFs::OrenNayar::sample(ld3(tint, i), rms[3 * i], o, make_float2(rnd));
-        } else {
+        } else if (kind == 3) {
             r = BSDFs::Burley::evaluate_with_PDF(ld3(tint, i), rms[3 * i], o, in);
             s = BSDFs::Burley::sample(ld3(tint, i), rms[3 * i], o, make_float2(rnd));
+        } else if (kind == 4) {
+            // rms = {roughness, cos_theta_o (signed: entering / leaving), specularity}
+            Material m = make_material(tint, rms, nullptr, i);
+            ShadingModels::TransmissiveShading shading(m, rms[3 * i + 1]);
+            r = shading.evaluate_with_PDF(o, in);
+            s = shading.sample(o, rnd);
+        } else {
+            // rms = {roughness, ior_i_over_o, specularity}
+            float alpha = BSDFs::GGX::alpha_from_roughness(rms[3 * i]);
+            r = BSDFs::GGX::evaluate_with_PDF(ld3(tint, i), alpha, rms[3 * i + 2], rms[3 * i + 1], o, in);
+            s = BSDFs::GGX::sample(ld3(tint, i), alpha, rms[3 * i + 2], rms[3 * i + 1], o, rnd);
         }
         st3(eval_f, i, r.reflectance); eval_pdf[i] = r.PDF.m_PDF;
         st3(sample_f, i, s.reflectance); sample_pdf[i] = s.PDF.m_PDF; st3(sample_dir, i, s.direction);

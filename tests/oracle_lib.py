@@ -31,6 +31,8 @@ class Ref:
         vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
         lib.ref_sizeof.argtypes = [C.c_char_p]
         lib.ref_get_tables.argtypes = [vp, vp, vp, vp]; lib.ref_get_tables.restype = None
+        lib.ref_get_dielectric_tables.argtypes = [vp, vp, vp]; lib.ref_get_dielectric_tables.restype = None
+        lib.ref_sample_dielectric_rho.argtypes = [i64, vp, vp, vp, vp]; lib.ref_sample_dielectric_rho.restype = None
         lib.ref_pcg2d.argtypes = [i64, vp, vp, vp]; lib.ref_pcg2d.restype = None
         lib.ref_sobol_sample4.argtypes = [i64, vp, vp, vp, vp, vp]; lib.ref_sobol_sample4.restype = None
         lib.ref_reverse_halton4.argtypes = [i32, vp]; lib.ref_reverse_halton4.restype = None
@@ -54,6 +56,12 @@ class Ref:
         dims = np.zeros(6, np.int32)
         self.lib.ref_get_tables(_p(a), _p(b), _p(c), _p(dims))
         return a, b, c, dims
+
+    def dielectric_tables(self):
+        a, b = np.zeros(8192, np.float32), np.zeros(8192, np.float32)
+        dims = np.zeros(3, np.int32)
+        self.lib.ref_get_dielectric_tables(_p(a), _p(b), _p(dims))
+        return a, b, dims
 
     def sobol_sample4(self, accumulation, pixel_hash, dimension):
         a, h, d = (np.ascontiguousarray(x, dtype=np.uint32).reshape(-1) for x in (accumulation, pixel_hash, dimension))

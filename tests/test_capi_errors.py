@@ -25,9 +25,9 @@ def test_bad_inputs_are_rejected_loudly():
         ctx.upload_mesh(0, tri["indices"], tri["positions"])
     with pytest.raises(b.BptError, match="unknown mesh"):
         ctx.set_instances(np.array([scenes._instance(7, 0, scenes.affine())], capi.INSTANCE_DTYPE))
-    glass = scenes.material((1, 1, 1), 0.1); glass["shading_model"] = 2
-    with pytest.raises(b.BptError, match="shading models"):
-        ctx.set_materials(np.array([glass], capi.MATERIAL_DTYPE))
+    unknown = scenes.material((1, 1, 1), 0.1); unknown["shading_model"] = 3
+    with pytest.raises(b.BptError, match="unknown shading model"):
+        ctx.set_materials(np.array([unknown], capi.MATERIAL_DTYPE))
     textured = scenes.material((1, 1, 1), 0.1); textured["coverage_texture_id"] = 3
     with pytest.raises(b.BptError, match="textured"):
         ctx.set_materials(np.array([textured], capi.MATERIAL_DTYPE))
@@ -43,6 +43,23 @@ def test_tables_are_required_for_default_shading():
         ctx.bsdf_eval_sample_pdf(0, z, z, z, z, z)
     out = ctx.bsdf_eval_sample_pdf(3, z + np.float32([0, 0, 1]), z + np.float32([0, 0, 1]), z + 0.5, z + 0.5, z + 0.5)  # Burley needs no tables
     assert np.isfinite(out["eval_f"]).all()
+    ctx.close()
+
+
+def test_dielectric_tables_are_required_for_transmissive_materials():
+    ctx = b.Bpt(0, tables=False)
+    ctx.set_tables(*capi.default_tables())
+    z = np.zeros((4, 3), np.float32)
+    with pytest.raises(b.BptError, match="bpt_set_dielectric_tables"):
+        ctx.bsdf_eval_sample_pdf(4, z, z, z, z, z)
+    scene = scenes.cornell_box(sphere_quads=(8, 4))
+    scene["materials"][4]["shading_model"] = 2
+    scenes.upload(ctx, scene)
+    with pytest.raises(b.BptError, match="bpt_set_dielectric_tables"):
+        ctx.render(scene["camera"], 8, 8, 0, 1)
+    ctx.set_dielectric_tables(*capi.default_dielectric_tables())
+    ctx.render(scene["camera"], 8, 8, 0, 1)
+    assert np.isfinite(ctx.resolve_float4()).all()
     ctx.close()
 
 

@@ -63,6 +63,45 @@ def regression_inputs(ref):
             "u": np.array([r[3] for r in rows], np.float32), "coat": np.array([r[4] for r in rows], np.float32)}
 
 
+# TransmissiveShadingTest.h:203-238: frosted glass, 4 cos_theta_o x 2 sample02 points -> {reflectance, |PDF|}
+TRANSMISSIVE_REGRESSION = np.array([
+    [102.196815, 102.196815, 102.196815, 70.955925], [30.308733, 30.308733, 30.308733, 19.304911],
+    [4075.826172, 4075.826172, 4075.826172, 445.397308], [4660.390625, 4660.390625, 4660.390625, 235.904617],
+    [610.321655, 623.170593, 610.321655, 504.575867], [149.033539, 152.171082, 149.033539, 125.492897],
+    [1633.225708, 1667.609497, 1633.225708, 1715.760010], [408.740875, 417.345978, 408.740875, 429.358185]], np.float32)
+
+
+def transmissive_regression_inputs(ref):
+    """frosted_glass_parameters() (TransmissiveShadingTest.h:25-38) at cos_theta_o in {-0.7, -0.1, 0.4, 1}."""
+    s02 = ref.sample02(2)
+    rows = []
+    for cos_theta_o in (np.float32(-0.7), np.float32(-0.1), np.float32(0.4), np.float32(1.0)):
+        wo = np.array([np.sqrt(np.float32(1) - cos_theta_o * cos_theta_o), 0, abs(cos_theta_o)], np.float32)
+        for s in range(2):
+            rows.append((wo, (0.95, 0.97, 0.95), (0.2, cos_theta_o, 0.04), (s02[s, 0], s02[s, 1], (s + 0.5) / 2)))
+    n = len(rows)
+    return {"wo": np.array([r[0] for r in rows], np.float32), "wi": np.tile(np.array([0, 0, 1], np.float32), (n, 1)),
+            "tint": np.array([r[1] for r in rows], np.float32), "rms": np.array([r[2] for r in rows], np.float32),
+            "u": np.array([r[3] for r in rows], np.float32)}
+
+
+def test_transmissive_shading_regression_vectors(ref):
+    """The oracle reproduces the golden vectors of the reference's own TransmissiveShadingModel.regression_test."""
+    got = ref.bsdf_eval_sample_pdf(4, **transmissive_regression_inputs(ref))
+    values = np.concatenate([got["sample_f"], np.abs(got["sample_pdf"])[:, None]], axis=1).astype(np.float64)
+    golden = TRANSMISSIVE_REGRESSION.astype(np.float64)
+    assert np.all(np.abs(values - golden) <= golden * 1e-4), np.abs(values - golden) / golden
+
+
+def test_dielectric_tables_match_committed_data(ref):
+    from bifrost3d_b200.capi import default_dielectric_tables
+    light, dense, dims = ref.dielectric_tables()
+    assert list(dims) == [16] * 3
+    tl, td = default_dielectric_tables()
+    assert np.array_equal(light, tl) and np.array_equal(dense, td)
+    assert np.all(light[0::2] >= light[1::2]) and np.all(dense[0::2] >= dense[1::2])  # total rho >= reflected rho
+
+
 def test_tables_match_committed_data(ref):
     from bifrost3d_b200.capi import default_tables
     a, b, c, dims = ref.tables()

@@ -190,3 +190,52 @@ def test_diffuse_shading_model_matches_oracle(bpt):
     e = rel_mse(gpu, cpu)
     print(f"relMSE {e:.3e}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND and e < 1e-8
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_transmissive_shading_model_matches_oracle(bpt):
+    """ShadingModel::Transmissive (transmissive_closest_hit, MonteCarlo.cu:259-268): a frosted and a smooth glass sphere in
+    the Cornell box; paths enter and leave the medium, refract through both interfaces and pick up the tinted transmission."""
+    scene = scenes.cornell_box(sphere_quads=(24, 12))
+    mats = scene["materials"].copy()
+    mats[4] = scenes.material((0.95, 0.97, 0.95), 0.2, 0.04); mats[4]["shading_model"] = 2
+    mats[5] = scenes.material((0.6, 0.9, 0.7), 0.0, 0.06); mats[5]["shading_model"] = 2
+    scene["materials"] = mats
+    gpu, cpu, counters, oc = render_both(bpt, scene, 96, 96, 6, max_bounces=8)
+    assert np.isfinite(gpu).all() and cpu.mean() > 0.01
+    e = rel_mse(gpu, cpu)
+    diff = np.abs(gpu[..., :3] - cpu).max(axis=-1)
+    close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
+    print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert e <= REL_MSE_BOUND
+    assert close.mean() > 0.97
+    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.003 * int(oc[0])
+    # the glass spheres transmit: with the same spheres opaque (Default model) the image differs visibly
+    opaque = scene["materials"].copy()
+    opaque[4]["shading_model"] = 0; opaque[5]["shading_model"] = 0
+    scene["materials"] = opaque
+    scenes.upload(bpt, scene)
+    bpt.render(scene["camera"], 96, 96, 0, 6, reset=True, max_bounces=8)
+    assert rel_mse(bpt.resolve_float4(), cpu) > 1e-2
+
+
+@pytest.mark.gpu
+def test_transmissive_albedo_aov(bpt):
+    """SimpleRGPs.cu:293-295: albedo of a transmissive surface = reflected share + (1 - share) * transmission tint."""
+    scene = scenes.cornell_box(sphere_quads=(16, 8))
+    mats = scene["materials"].copy()
+    mats[4] = scenes.material((0.9, 0.2, 0.9), 0.3, 0.04); mats[4]["shading_model"] = 2
+    scene["materials"] = mats
+    scenes.upload(bpt, scene)
+    bpt.render_aov(scene["camera"], "albedo", 64, 64)
+    img = bpt.resolve_float4()
+    assert np.isfinite(img).all()
+    # the glass sphere is the only magenta surface in the box
+    on_sphere = (img[..., 0] > img[..., 1] + 0.2) & (img[..., 2] > img[..., 1] + 0.2)
+    assert on_sphere.sum() > 50
+    r, g, b = (img[..., c][on_sphere] for c in range(3))
+    assert np.abs(r - b).max() < 1e-6
+    reflection = (g - 0.2) / 0.8  # g = reflection + (1 - reflection) * 0.2
+    assert reflection.min() >= 0.0 and reflection.max() < 0.9
+    assert np.abs(r - (reflection + (1 - reflection) * 0.9)).max() < 1e-5

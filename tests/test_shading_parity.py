@@ -6,7 +6,7 @@ import pytest
 
 from tests import oracle_lib
 from tests.parity import REL_TOL, pdf_class, rel_err, report
-from bifrost3d_b200.workloads import bsdf_tuples
+from bifrost3d_b200.workloads import bsdf_tuples, transmissive_tuples
 from bifrost3d_b200 import capi
 
 pytestmark = pytest.mark.gpu
@@ -80,6 +80,31 @@ def test_default_shading_regression_vectors_on_gpu(bpt, ref):
     want = ref.bsdf_eval_sample_pdf(0, **t)
     assert np.all(rel_err(got["sample_f"], want["sample_f"], 1e-12) <= 1e-4)
     assert np.all(rel_err(np.abs(got["sample_pdf"]), np.abs(want["sample_pdf"]), 1e-12) <= 1e-4)
+
+
+@pytest.mark.skipif(not oracle_lib.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name,kind", [("transmissive_shading", 4), ("ggx", 5)])
+@pytest.mark.parametrize("n", [1, 255, 1 << 18])
+def test_transmissive_bsdfs_match_reference(bpt, ref, name, kind, n):
+    """TransmissiveShading (TransmissiveShading.h:22-98) and the combined reflection + transmission GGX (GGX.h:258-443)."""
+    t = transmissive_tuples(n, seed=77 + n, combined_ggx=(kind == 5))
+    got = bpt.bsdf_eval_sample_pdf(kind, t["wo"], t["wi"], t["tint"], t["rms"], t["u"])
+    want = ref.bsdf_eval_sample_pdf(kind, t["wo"], t["wi"], t["tint"], t["rms"], t["u"])
+    for m in compare_bsdf(got, want, f"{name}[n={n}]"):
+        print(m)
+    if n > 1000:  # the batch covers reflection and refraction, both directions through the interface
+        valid = np.isin(pdf_class(got["sample_pdf"]), (1, 3))
+        refracted = valid & (got["sample_dir"][:, 2] * t["wo"][:, 2] < 0)
+        assert 0.2 < refracted.sum() / max(1, valid.sum()) < 0.98
+
+
+@pytest.mark.skipif(not oracle_lib.available(), reason="oracle/_ref not built")
+def test_transmissive_shading_regression_vectors_on_gpu(bpt, ref):
+    """The reference's own golden vectors (TransmissiveShadingTest.h:203-238), 1e-4 relative as in the reference test."""
+    from tests.test_oracle_reference import TRANSMISSIVE_REGRESSION, transmissive_regression_inputs
+    got = bpt.bsdf_eval_sample_pdf(4, **transmissive_regression_inputs(ref))
+    assert np.all(rel_err(got["sample_f"], TRANSMISSIVE_REGRESSION[:, :3], 1e-12) <= 1e-4)
+    assert np.all(rel_err(np.abs(got["sample_pdf"]), TRANSMISSIVE_REGRESSION[:, 3], 1e-12) <= 1e-4)
 
 
 def test_empty_batch_is_a_no_op(bpt):
