@@ -190,7 +190,7 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
         float far_z = (m[10] * 1.0f + m[11]) / (m[14] * 1.0f + m[15]);
         ctx->half4_scale = far_z - near_z;
     }
-    AccelView accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_budget_for(ctx->accel.triangle_count) };
+    AccelView accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
     AovParams f = {};
     f.camera = *camera; f.width = width; f.height = height; f.kind = kind;
     const int grid = ctx->sm_count * 8;

@@ -462,7 +462,7 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     if (out_t) Q_CHECK(cudaMalloc((void**)&d_t, n * sizeof(float)));
     if (out_uv) Q_CHECK(cudaMalloc((void**)&d_uv, 2 * n * sizeof(float)));
     if (out_occluded) Q_CHECK(cudaMalloc((void**)&d_occ, n));
-    AccelView view = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_budget_for(ctx->accel.triangle_count) };
+    AccelView view = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
     int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 8);
     BatchSource source = { d_o, d_d, d_tmin, d_tmax, d_prim, d_t, d_uv, d_occ };
     unsigned int* d_fetch = reinterpret_cast<unsigned int*>(ctx->device_counters + 4); // two scratch fetch counters

@@ -620,7 +620,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
 
     SceneView s = {};
-    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_budget_for(ctx->accel.triangle_count) };
+    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
     s.world_vertices = ctx->accel.world_vertices.ptr;
     s.shade = ctx->accel.shade.ptr;
     s.normal_matrices = ctx->accel.normal_matrices.ptr;
