@@ -110,9 +110,6 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
 #define BPT_TRAVERSAL_BUDGET 48
 #endif
 constexpr int TRACE_BLOCK = 128;
-#ifndef BPT_TRAVERSAL_SCHEDULER
-#define BPT_TRAVERSAL_SCHEDULER 0
-#endif
 #ifndef BPT_MIN_ACTIVE_LANES
 #define BPT_MIN_ACTIVE_LANES 12
 #endif
@@ -271,13 +268,6 @@ struct Traversal {
         return true;
     }
 
-    // One triangle of the parked leaf.
-    BPT_D void triangle_step(const AccelView& a, const float* __restrict__ coverage_by_material) {
-        const int first = leaf_first(postponed), remaining = leaf_count(postponed);
-        postponed = remaining == 1 ? NODE_EMPTY : pack_leaf(first + 1, remaining - 1);
-        if (!intersect_leaf(a, coverage_by_material, pack_leaf(first, 1))) { node = NODE_EMPTY; stack.sp = 0; postponed = NODE_EMPTY; }
-    }
-
     // Runs up to `budget` inner-node visits (and the leaves met on the way). Returns when the ray is done or the budget
     // is used up; `node == NODE_EMPTY && postponed == NODE_EMPTY` tells which.
     // Speculative traversal (Aila and Laine): a lane that reaches a leaf parks it in `postponed` and keeps descending while
@@ -315,70 +305,6 @@ struct Traversal {
     }
 };
 
-// Warp-scheduled driver: the warp stays converged in one loop and each iteration runs the step most of its lanes are
-// waiting for - an inner-node visit, one triangle test, or a refill of the idle lanes from the queue - with the other
-// lanes predicated off. Rays are not speculated: a lane holding a leaf waits until triangle tests win the vote.
-#ifndef BPT_SCHED_REFILL
-#define BPT_SCHED_REFILL 8
-#endif
-#ifndef BPT_SCHED_INNER_WEIGHT
-#define BPT_SCHED_INNER_WEIGHT 1
-#endif
-#ifndef BPT_SCHED_TRI_WEIGHT
-#define BPT_SCHED_TRI_WEIGHT 1
-#endif
-template <bool ANY_HIT, class Source>
-BPT_D void traverse_queue_scheduled(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
-                                    unsigned int* fetch_counter, int* stack_smem) {
-    int spill[STACK_LOCAL];
-    Traversal<ANY_HIT> tr;
-    tr.stack.smem = stack_smem;
-    tr.stack.spill = spill;
-    tr.stack.sp = 0;
-    tr.node = NODE_EMPTY;
-    tr.postponed = NODE_EMPTY;
-    unsigned int index = 0;
-    bool has_ray = false, exhausted = false; // exhausted is warp uniform
-    const int lane = threadIdx.x & 31;
-    const unsigned int FULL = 0xffffffffu;
-
-    while (true) {
-        if (has_ray) {
-            if (tr.postponed == NODE_EMPTY && is_leaf(tr.node)) { tr.postponed = tr.node; tr.node = tr.stack.pop(); }
-            if (tr.postponed == NODE_EMPTY && tr.node == NODE_EMPTY) { source.store(index, tr); has_ray = false; }
-        }
-        const bool want_triangle = has_ray && tr.postponed != NODE_EMPTY;
-        const bool want_inner = has_ray && !want_triangle;
-        const int n_triangle = __popc(__ballot_sync(FULL, want_triangle));
-        const unsigned int idle = __ballot_sync(FULL, !has_ray);
-        const int n_idle = __popc(idle);
-        const int n_inner = 32 - n_triangle - n_idle;
-
-        if ((!exhausted && n_idle >= BPT_SCHED_REFILL) || n_idle == 32) {
-            if (exhausted) break;
-            int leader = __ffs(idle) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(fetch_counter, (unsigned int)n_idle);
-            base = __shfl_sync(FULL, base, leader);
-            exhausted = base + (unsigned int)n_idle >= count;
-            if (!has_ray) {
-                index = base + __popc(idle & ((1u << lane) - 1u));
-                if (index < count) {
-                    Ray ray; int skip;
-                    source.load(index, ray, skip);
-                    tr.begin(ray, skip);
-                    has_ray = true;
-                }
-            }
-            continue;
-        }
-        if (n_inner * BPT_SCHED_INNER_WEIGHT >= n_triangle * BPT_SCHED_TRI_WEIGHT) {
-            if (want_inner) tr.inner_step(a);
-        } else if (want_triangle)
-            tr.triangle_step(a, coverage_by_material);
-    }
-}
-
 // Persistent-thread driver. `Source` supplies rays and consumes results:
 //   bool load(unsigned int index, Ray& ray, int& skip_primitive)
 //   void store(unsigned int index, const Traversal<ANY_HIT>& traversal)
@@ -386,10 +312,6 @@ BPT_D void traverse_queue_scheduled(const AccelView& a, const float* __restrict_
 template <bool ANY_HIT, class Source>
 BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
                           unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
-#if BPT_TRAVERSAL_SCHEDULER
-    traverse_queue_scheduled<ANY_HIT>(a, coverage_by_material, source, count, fetch_counter, stack_smem);
-    return;
-#endif
     int spill[STACK_LOCAL];
     Traversal<ANY_HIT> tr;
     tr.stack.smem = stack_smem;
