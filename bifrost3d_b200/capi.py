@@ -64,11 +64,34 @@ assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SA
 
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
-EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_mesh", "bpt_set_instances",
+EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
+
+
+class TextureDesc(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("pixel_format", C.c_int32), ("is_srgb", C.c_int32),
+                ("wrap_u", C.c_int32), ("wrap_v", C.c_int32), ("linear_filter", C.c_int32), ("reserved", C.c_int32)]
+
+
+PIXEL_ALPHA8, PIXEL_RGB24, PIXEL_RGBA32, PIXEL_RGB_FLOAT, PIXEL_RGBA_FLOAT = 1, 3, 4, 6, 7
+WRAP_CLAMP, WRAP_REPEAT = 0, 1
+
+
+def pixel_format_of(pixels):
+    """(format, contiguous array) for an image array of shape (H, W) / (H, W, C), uint8 or float32."""
+    p = np.asarray(pixels)
+    if p.ndim == 2:
+        p = p[..., None]
+    channels = p.shape[2]
+    if p.dtype == np.uint8:
+        fmt = {1: PIXEL_ALPHA8, 3: PIXEL_RGB24, 4: PIXEL_RGBA32}[channels]
+    else:
+        p = p.astype(np.float32)
+        fmt = {3: PIXEL_RGB_FLOAT, 4: PIXEL_RGBA_FLOAT}[channels]
+    return fmt, np.ascontiguousarray(p)
 
 
 def load_library():
@@ -88,6 +111,9 @@ def load_library():
     lib.bpt_stream.argtypes = [vp]; lib.bpt_stream.restype = vp
     lib.bpt_set_tables.argtypes = [vp, vp, vp, vp]
     lib.bpt_set_dielectric_tables.argtypes = [vp, vp, vp]
+    lib.bpt_upload_texture.argtypes = [vp, i32, C.POINTER(TextureDesc), vp]
+    lib.bpt_destroy_texture.argtypes = [vp, i32]
+    lib.bpt_texture_sample.argtypes = [vp, i32, i64, vp, vp]
     lib.bpt_upload_mesh.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
     lib.bpt_set_instances.argtypes = [vp, vp, i32]
     lib.bpt_set_materials.argtypes = [vp, vp, i32]
@@ -198,6 +224,20 @@ class Bpt:
         for a in (nrm, uv, tr):
             assert a is None or a.shape[0] == pos.shape[0]
         self._check(self.lib.bpt_upload_mesh(self.h, mesh_id, _ptr(idx), idx.shape[0], _ptr(pos), _ptr(nrm), _ptr(uv), _ptr(tr), pos.shape[0]))
+
+    def upload_texture(self, texture_id, pixels, srgb=False, wrap_u=WRAP_REPEAT, wrap_v=WRAP_REPEAT, linear=True):
+        fmt, p = pixel_format_of(pixels)
+        desc = TextureDesc(p.shape[1], p.shape[0], fmt, int(srgb), int(wrap_u), int(wrap_v), int(linear), 0)
+        self._check(self.lib.bpt_upload_texture(self.h, int(texture_id), C.byref(desc), _ptr(p)))
+
+    def destroy_texture(self, texture_id):
+        self._check(self.lib.bpt_destroy_texture(self.h, int(texture_id)))
+
+    def texture_sample(self, texture_id, uv):
+        uv = _f32(uv).reshape(-1, 2)
+        out = np.empty((uv.shape[0], 4), np.float32)
+        self._check(self.lib.bpt_texture_sample(self.h, int(texture_id), uv.shape[0], _ptr(uv), _ptr(out)))
+        return out
 
     def set_instances(self, instances):
         inst = np.ascontiguousarray(instances, dtype=INSTANCE_DTYPE)

@@ -90,12 +90,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK) aov_kernel(AccelView accel, const
 
             const float3 p0 = f3(world_vertices[3ll * h.primitive]), p1 = f3(world_vertices[3ll * h.primitive + 1]), p2 = f3(world_vertices[3ll * h.primitive + 2]);
             const ShadeTriangle st = shade[h.primitive];
-            const Material m = materials[st.material_index];
+            const float2 texcoord = interpolate_texcoord(accel.textures, h.primitive, h.u, h.v);
+            const Material m = material_at(materials[st.material_index], accel.textures, texcoord);
             float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
             bool hit_from_front = dot(geometric_normal, direction) < 0.0f;
             bool backside_cull = !hit_from_front && !material_is_thin_walled(m) && !material_is_transmissive(m);
             float4 bsdf_random = path_rng_sample4f(f.accumulation_count, pixel_hash, 0u, DIM_BSDF);
-            if (backside_cull || material_coverage(m) < bsdf_random.w) { tmin = nextafterf(h.t, INFINITY); continue; }
+            if (backside_cull || material_coverage(m, accel.textures, texcoord) < bsdf_random.w) { tmin = nextafterf(h.t, INFINITY); continue; }
 
             const float bx = h.u, by = h.v, bz = 1.0f - bx - by;
             float4 scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
@@ -169,6 +170,7 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
     if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render_aov: call bpt_set_tables first");
     if (kind == BPT_AOV_ALBEDO && ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
         return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render_aov: transmissive materials need bpt_set_dielectric_tables");
+    if (int status = sync_texture_table(ctx)) return status;
     cudaStream_t st = ctx->stream;
     const int64_t pixels = (int64_t)width * height;
     bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
@@ -176,7 +178,7 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
     if (size_changed || reset_accumulation) BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
 
     std::vector<float> h_cov(ctx->host_materials.size());
-    for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
+    for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
     float* d_cov = nullptr; float4* d_out = nullptr;
     BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d_cov, h_cov.size() * sizeof(float), st));
     BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d_out, pixels * sizeof(float4), st));
@@ -190,7 +192,7 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
         float far_z = (m[10] * 1.0f + m[11]) / (m[14] * 1.0f + m[15]);
         ctx->half4_scale = far_z - near_z;
     }
-    AccelView accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
+    AccelView accel = accel_view(ctx);
     AovParams f = {};
     f.camera = *camera; f.width = width; f.height = height; f.kind = kind;
     const int grid = ctx->sm_count * 8;

@@ -275,6 +275,17 @@ cudaError_t upload(Context* ctx, DeviceBuffer<T>& buf, const T* host, size_t n) 
 
 namespace {
 // Small RAII helper for the host-pointer unit entry points: device scratch that mirrors host arrays.
+__global__ void texture_sample_kernel(cudaTextureObject_t texture, int64_t n, const float2* __restrict__ uv, float4* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = tex2D<float4>(texture, uv[i].x, uv[i].y);
+}
+
+void destroy_texture(DeviceTexture& t) {
+    if (t.object) cudaDestroyTextureObject(t.object);
+    if (t.array) cudaFreeArray(t.array);
+    t = DeviceTexture();
+}
+
 struct Scratch {
     Context* ctx;
     std::vector<void*> allocations;
@@ -299,6 +310,20 @@ struct Scratch {
     }
 };
 } // namespace
+
+namespace bpt {
+int sync_texture_table(Context* ctx) {
+    if (!ctx->texture_table_dirty) return BPT_OK;
+    int max_id = ctx->textures.empty() ? 0 : ctx->textures.rbegin()->first;
+    std::vector<unsigned long long> table(max_id + 1, 0ull);
+    for (const auto& kv : ctx->textures) table[kv.first] = (unsigned long long)kv.second.object;
+    BPT_CUDA_CHECK(ctx, ctx->texture_objects.resize(table.size()));
+    BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->texture_objects.ptr, table.data(), table.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->texture_table_dirty = false;
+    return BPT_OK;
+}
+} // namespace bpt
 
 extern "C" {
 
@@ -351,6 +376,8 @@ void bpt_destroy(bpt_ctx* c) {
     release_wavefront(ctx);
     ctx->tables.release(); ctx->dielectric_tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
+    for (auto& kv : ctx->textures) destroy_texture(kv.second);
+    ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release();
     ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
     if (ctx->device_counters) cudaFree(ctx->device_counters);
@@ -401,6 +428,103 @@ int bpt_set_dielectric_tables(bpt_ctx* c, const float* into_light_medium, const 
     return BPT_OK;
 }
 
+// Image + sampler creation, Renderer.cpp:650-751.
+int bpt_upload_texture(bpt_ctx* c, int texture_id, const bpt_texture_desc* desc, const void* pixels) {
+    Context* ctx = as_context(c);
+    if (texture_id < 1 || texture_id > (1 << 20) || !desc || !pixels || desc->width <= 0 || desc->height <= 0)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_texture: bad arguments (texture ids start at 1)");
+    if (desc->wrap_u < BPT_WRAP_CLAMP || desc->wrap_u > BPT_WRAP_REPEAT || desc->wrap_v < BPT_WRAP_CLAMP || desc->wrap_v > BPT_WRAP_REPEAT)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_texture: unknown wrap mode");
+    cudaSetDevice(ctx->device);
+    const size_t texels = (size_t)desc->width * desc->height;
+    cudaChannelFormatDesc channels;
+    std::vector<unsigned char> widened_bytes; std::vector<float> widened_floats;
+    const void* source = pixels;
+    size_t texel_bytes = 0;
+    int channel_count = 4;
+    bool eight_bit = true;
+    switch (desc->pixel_format) {
+    case BPT_PIXEL_ALPHA8: channels = cudaCreateChannelDesc<unsigned char>(); texel_bytes = 1; channel_count = 1; break;
+    case BPT_PIXEL_RGB24: { // Renderer.cpp:683-694: ubyte3 cannot back a sampler, widen with alpha 255
+        channels = cudaCreateChannelDesc<uchar4>(); texel_bytes = 4;
+        widened_bytes.resize(4 * texels);
+        const unsigned char* p = static_cast<const unsigned char*>(pixels);
+        for (size_t i = 0; i < texels; ++i) { widened_bytes[4 * i] = p[3 * i]; widened_bytes[4 * i + 1] = p[3 * i + 1]; widened_bytes[4 * i + 2] = p[3 * i + 2]; widened_bytes[4 * i + 3] = 255; }
+        source = widened_bytes.data();
+        break;
+    }
+    case BPT_PIXEL_RGBA32: channels = cudaCreateChannelDesc<uchar4>(); texel_bytes = 4; break;
+    case BPT_PIXEL_RGB_FLOAT: { // CUDA arrays have no three-channel float format: widen with alpha 1
+        channels = cudaCreateChannelDesc<float4>(); texel_bytes = 16; eight_bit = false;
+        widened_floats.resize(4 * texels);
+        const float* p = static_cast<const float*>(pixels);
+        for (size_t i = 0; i < texels; ++i) { widened_floats[4 * i] = p[3 * i]; widened_floats[4 * i + 1] = p[3 * i + 1]; widened_floats[4 * i + 2] = p[3 * i + 2]; widened_floats[4 * i + 3] = 1.0f; }
+        source = widened_floats.data();
+        break;
+    }
+    case BPT_PIXEL_RGBA_FLOAT: channels = cudaCreateChannelDesc<float4>(); texel_bytes = 16; eight_bit = false; break;
+    default: return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_texture: unsupported pixel format (Alpha8, RGB24, RGBA32, RGB_Float, RGBA_Float)");
+    }
+
+    DeviceTexture fresh;
+    fresh.width = desc->width; fresh.height = desc->height; fresh.channels = channel_count;
+    BPT_CUDA_CHECK(ctx, cudaMallocArray(&fresh.array, &channels, desc->width, desc->height));
+    cudaError_t e = cudaMemcpy2DToArrayAsync(fresh.array, 0, 0, source, desc->width * texel_bytes, desc->width * texel_bytes, desc->height,
+                                             cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream); // `source` may be a local staging vector
+    cudaResourceDesc resource = {};
+    resource.resType = cudaResourceTypeArray;
+    resource.res.array.array = fresh.array;
+    cudaTextureDesc sampler = {};
+    sampler.addressMode[0] = desc->wrap_u == BPT_WRAP_REPEAT ? cudaAddressModeWrap : cudaAddressModeClamp;
+    sampler.addressMode[1] = desc->wrap_v == BPT_WRAP_REPEAT ? cudaAddressModeWrap : cudaAddressModeClamp;
+    sampler.filterMode = desc->linear_filter ? cudaFilterModeLinear : cudaFilterModePoint;
+    sampler.readMode = eight_bit ? cudaReadModeNormalizedFloat : cudaReadModeElementType;
+    sampler.sRGB = (eight_bit && desc->is_srgb) ? 1 : 0;
+    sampler.normalizedCoords = 1;
+    if (e == cudaSuccess) e = cudaCreateTextureObject(&fresh.object, &resource, &sampler, nullptr);
+    if (e != cudaSuccess) { destroy_texture(fresh); return ctx->cuda_fail(e, "bpt_upload_texture"); }
+
+    DeviceTexture& slot = ctx->textures[texture_id];
+    destroy_texture(slot);
+    slot = fresh;
+    ctx->texture_table_dirty = true;
+    return BPT_OK;
+}
+
+int bpt_destroy_texture(bpt_ctx* c, int texture_id) {
+    Context* ctx = as_context(c);
+    auto it = ctx->textures.find(texture_id);
+    if (it == ctx->textures.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_destroy_texture: unknown texture id");
+    for (const Material& m : ctx->host_materials)
+        if (m.tint_roughness_texture_id == texture_id || m.roughness_texture_id == texture_id || m.metallic_texture_id == texture_id || m.coverage_texture_id == texture_id)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_destroy_texture: a material still references the texture");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    destroy_texture(it->second);
+    ctx->textures.erase(it);
+    ctx->texture_table_dirty = true;
+    return BPT_OK;
+}
+
+int bpt_texture_sample(bpt_ctx* c, int texture_id, int64_t n, const float* uv, float* out_rgba) {
+    Context* ctx = as_context(c);
+    auto it = ctx->textures.find(texture_id);
+    if (it == ctx->textures.end() || n < 0 || !uv || !out_rgba) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_texture_sample: bad arguments or unknown texture id");
+    if (n == 0) return BPT_OK;
+    cudaSetDevice(ctx->device);
+    {
+        Scratch s(ctx);
+        auto d_uv = s.in(reinterpret_cast<const float2*>(uv), n);
+        auto d_out = s.out<float4>(n);
+        texture_sample_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(it->second.object, n, d_uv, d_out);
+        ctx->counters.kernel_launches++;
+        s.back(reinterpret_cast<float4*>(out_rgba), d_out, n);
+    }
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
 int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primitive_count, const float* positions, const float* normals,
                     const float* texcoords, const uint8_t* tint_roughness, int vertex_count) {
     Context* ctx = as_context(c);
@@ -438,19 +562,28 @@ int bpt_set_instances(bpt_ctx* c, const bpt_instance* instances, int count) {
 int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     Context* ctx = as_context(c);
     if (count <= 0 || !materials) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: need at least material 0");
-    bool any_transmissive = false;
+    bool any_transmissive = false, any_textured = false;
     for (int i = 0; i < count; ++i) {
         if (materials[i].shading_model > SHADING_TRANSMISSIVE)
             return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: unknown shading model");
         any_transmissive |= materials[i].shading_model == SHADING_TRANSMISSIVE;
-        if (materials[i].tint_roughness_texture_id || materials[i].roughness_texture_id || materials[i].metallic_texture_id || materials[i].coverage_texture_id)
-            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: textured materials are not implemented");
+        for (int id : { materials[i].tint_roughness_texture_id, materials[i].roughness_texture_id, materials[i].metallic_texture_id, materials[i].coverage_texture_id })
+            if (id != 0 && ctx->textures.find(id) == ctx->textures.end())
+                return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: a material references a texture id that was not uploaded");
+        // Renderer.cpp:763-780,789,803 assert the channel counts; a mismatch would sample garbage
+        if (materials[i].tint_roughness_texture_id && ctx->textures[materials[i].tint_roughness_texture_id].channels != 4)
+            return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: the tint/roughness texture needs four channels");
+        for (int id : { materials[i].roughness_texture_id, materials[i].metallic_texture_id, materials[i].coverage_texture_id })
+            if (id != 0 && ctx->textures[id].channels != 1)
+                return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: roughness, metallic and coverage textures need one channel");
+        any_textured |= material_is_textured(materials[i]);
     }
     cudaSetDevice(ctx->device);
     ctx->host_materials.assign(materials, materials + count);
     BPT_CUDA_CHECK(ctx, upload(ctx, ctx->materials, materials, (size_t)count));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->has_transmissive_materials = any_transmissive;
+    ctx->has_textured_materials = any_textured;
     ctx->material_version++;
     ctx->accel.valid = false; // cull / coverage flags are baked into the triangle records
     return BPT_OK;

@@ -27,7 +27,7 @@ struct InstanceRecord {
     int index_offset;  // first index triple in the concatenated index buffer
     int vertex_offset; // first vertex in the concatenated vertex buffers
     int material;
-    uint32_t flags;    // bit0: has normals, bit1: has tints
+    uint32_t flags;    // bit0: has normals, bit1: has tints, bit2: has texcoords
     float m[12];       // object -> world, row-major 3x4
 };
 
@@ -52,8 +52,9 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // One thread per global primitive: world-space vertices, shading record, centroid bounds.
 __global__ void flatten_kernel(int64_t prim_total, int instance_count, const InstanceRecord* __restrict__ instances,
                                const uint32_t* __restrict__ indices, const float* __restrict__ positions,
-                               const int16_t* __restrict__ normals, const uint8_t* __restrict__ tints,
-                               float4* __restrict__ world_vertices, ShadeTriangle* __restrict__ shade, float* scene_bounds /*[6]*/) {
+                               const int16_t* __restrict__ normals, const uint8_t* __restrict__ tints, const float2* __restrict__ texcoords,
+                               float4* __restrict__ world_vertices, ShadeTriangle* __restrict__ shade, float2* __restrict__ shade_uv,
+                               float* scene_bounds /*[6]*/) {
     float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
     for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < prim_total; gp += (int64_t)gridDim.x * blockDim.x) {
         // binary search: last instance with prim_offset <= gp
@@ -85,6 +86,13 @@ __global__ void flatten_kernel(int64_t prim_total, int instance_count, const Ins
         s.material_index = inst.material;
         s.flags = (uint32_t(a) << 2) | (inst.flags & 3u);
         shade[gp] = s;
+        if (shade_uv != nullptr) { // TriangleAttributes.cu:57-64; meshes without texcoords read (0, 0)
+            const bool has_uv = inst.flags & 4u;
+            const float2 zero = make_float2(0.0f, 0.0f);
+            shade_uv[3 * gp] = has_uv ? texcoords[i0] : zero;
+            shade_uv[3 * gp + 1] = has_uv ? texcoords[i1] : zero;
+            shade_uv[3 * gp + 2] = has_uv ? texcoords[i2] : zero;
+        }
 
         float3 c = (min3(min3(p0, p1), p2) + max3(max3(p0, p1), p2)) * 0.5f;
         lo = min3(lo, c); hi = max3(hi, c);
@@ -310,6 +318,10 @@ int build_accel(Context* ctx) {
     struct MeshSlot { int index_offset, vertex_offset; };
     std::vector<MeshSlot> slots;
     std::vector<uint32_t> h_indices; std::vector<float> h_positions; std::vector<int16_t> h_normals; std::vector<uint8_t> h_tints;
+    std::vector<float> h_texcoords; // 2 per vertex; only filled when a textured material could read them
+    bool any_texcoords = false;
+    if (ctx->has_textured_materials)
+        for (const bpt_instance& inst : ctx->instances) any_texcoords |= !ctx->meshes[inst.mesh_id].texcoords.empty();
     std::vector<InstanceRecord> records;
     std::vector<float> h_normal_matrices; // 9 floats per record, row-major
     int64_t prim_total = 0;
@@ -324,6 +336,10 @@ int build_accel(Context* ctx) {
             if (!mesh.normals.empty()) std::copy(mesh.normals.begin(), mesh.normals.end(), h_normals.begin() + 2ll * s.vertex_offset);
             h_tints.resize(4 * (h_positions.size() / 3), 255);
             if (!mesh.tints.empty()) std::copy(mesh.tints.begin(), mesh.tints.end(), h_tints.begin() + 4ll * s.vertex_offset);
+            if (any_texcoords) {
+                h_texcoords.resize(2 * (h_positions.size() / 3), 0.0f);
+                if (!mesh.texcoords.empty()) std::copy(mesh.texcoords.begin(), mesh.texcoords.end(), h_texcoords.begin() + 2ll * s.vertex_offset);
+            }
             slots.push_back(s);
             it = mesh_slot.emplace(inst.mesh_id, int(slots.size()) - 1).first;
         }
@@ -334,7 +350,7 @@ int build_accel(Context* ctx) {
         r.prim_offset = int(prim_total); r.prim_count = mesh.primitive_count;
         r.index_offset = slots[it->second].index_offset; r.vertex_offset = slots[it->second].vertex_offset;
         r.material = inst.material_id;
-        r.flags = (mesh.normals.empty() ? 0u : 1u) | (mesh.tints.empty() ? 0u : 2u);
+        r.flags = (mesh.normals.empty() ? 0u : 1u) | (mesh.tints.empty() ? 0u : 2u) | ((any_texcoords && !mesh.texcoords.empty()) ? 4u : 0u);
         memcpy(r.m, inst.to_world, sizeof(r.m));
         records.push_back(r);
         { // normal matrix = inverse transpose of the upper 3x3 (rtTransformNormal, MonteCarlo.cu:147,176), in double
@@ -356,11 +372,11 @@ int build_accel(Context* ctx) {
     for (size_t i = 0; i < h_flags.size(); ++i) h_flags[i] = material_trace_flags(ctx->host_materials[i]);
 
     DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<uint32_t> d_indices; DeviceBuffer<float> d_positions;
-    DeviceBuffer<int16_t> d_normals; DeviceBuffer<uint8_t> d_tints; DeviceBuffer<uint32_t> d_flags; DeviceBuffer<float> d_bounds;
+    DeviceBuffer<int16_t> d_normals; DeviceBuffer<uint8_t> d_tints; DeviceBuffer<float> d_texcoords; DeviceBuffer<uint32_t> d_flags; DeviceBuffer<float> d_bounds;
     DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<unsigned char> d_temp;
     DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
     auto release_all = [&]() {
-        d_records.release(); d_indices.release(); d_positions.release(); d_normals.release(); d_tints.release(); d_flags.release(); d_bounds.release();
+        d_records.release(); d_indices.release(); d_positions.release(); d_normals.release(); d_tints.release(); d_texcoords.release(); d_flags.release(); d_bounds.release();
         d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
         d_tree.release(); d_parent_internal.release(); d_parent_leaf.release(); d_arrival.release(); d_leaf_boxes.release(); d_node_boxes.release();
     };
@@ -372,7 +388,7 @@ int build_accel(Context* ctx) {
         return cudaMemcpyAsync(buf.ptr, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st);
     };
     BUILD_CHECK(up(d_records, records)); BUILD_CHECK(up(d_indices, h_indices)); BUILD_CHECK(up(d_positions, h_positions));
-    BUILD_CHECK(up(d_normals, h_normals)); BUILD_CHECK(up(d_tints, h_tints)); BUILD_CHECK(up(d_flags, h_flags));
+    BUILD_CHECK(up(d_normals, h_normals)); BUILD_CHECK(up(d_tints, h_tints)); BUILD_CHECK(up(d_texcoords, h_texcoords)); BUILD_CHECK(up(d_flags, h_flags));
     BUILD_CHECK(up(A.normal_matrices, h_normal_matrices));
     float init_bounds[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
     BUILD_CHECK(d_bounds.resize(6));
@@ -380,6 +396,8 @@ int build_accel(Context* ctx) {
 
     BUILD_CHECK(A.world_vertices.resize(std::max<size_t>(3ull * n, 1)));
     BUILD_CHECK(A.shade.resize(std::max<size_t>(n, 1)));
+    A.has_uv = any_texcoords && n > 0;
+    if (A.has_uv) BUILD_CHECK(A.shade_uv.resize(3ull * n)); else A.shade_uv.release();
     BUILD_CHECK(A.triangles.resize(std::max<size_t>(n, 1)));
     BUILD_CHECK(A.nodes.resize(std::max<size_t>(n > 1 ? n - 1 : 1, 1)));
     BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
@@ -391,7 +409,8 @@ int build_accel(Context* ctx) {
 
     if (n > 0) {
         flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, d_indices.ptr, d_positions.ptr, d_normals.ptr, d_tints.ptr,
-                                                  A.world_vertices.ptr, A.shade.ptr, d_bounds.ptr);
+                                                  reinterpret_cast<const float2*>(d_texcoords.ptr), A.world_vertices.ptr, A.shade.ptr,
+                                                  A.has_uv ? A.shade_uv.ptr : nullptr, d_bounds.ptr);
         ctx->counters.kernel_launches++;
         BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
         morton_kernel<<<grid(n), block, 0, st>>>(n, A.world_vertices.ptr, d_bounds.ptr, d_keys.ptr, d_vals.ptr);
@@ -442,9 +461,10 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_intersect: call bpt_build_accel first");
     if (n < 0 || n > 0x7fffffff || !origins || !directions || !tmin || !tmax) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_intersect: bad arguments");
     if (n == 0) return BPT_OK;
+    if (int status = sync_texture_table(ctx)) return status;
     cudaStream_t st = ctx->stream;
     std::vector<float> h_cov(ctx->host_materials.size());
-    for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
+    for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
 
     float *d_o = nullptr, *d_d = nullptr, *d_tmin = nullptr, *d_tmax = nullptr, *d_cov = nullptr, *d_t = nullptr, *d_uv = nullptr;
     int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
@@ -462,7 +482,7 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     if (out_t) Q_CHECK(cudaMalloc((void**)&d_t, n * sizeof(float)));
     if (out_uv) Q_CHECK(cudaMalloc((void**)&d_uv, 2 * n * sizeof(float)));
     if (out_occluded) Q_CHECK(cudaMalloc((void**)&d_occ, n));
-    AccelView view = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
+    AccelView view = accel_view(ctx);
     int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 8);
     BatchSource source = { d_o, d_d, d_tmin, d_tmax, d_prim, d_t, d_uv, d_occ };
     unsigned int* d_fetch = reinterpret_cast<unsigned int*>(ctx->device_counters + 4); // two scratch fetch counters

@@ -71,11 +71,20 @@ struct __align__(16) ShadeTriangle {
 };
 static_assert(sizeof(ShadeTriangle) == 32, "ShadeTriangle must be 32 bytes");
 
+// One image + sampler pair (Renderer.cpp:650-751): a CUDA array and the texture object that reads it.
+struct DeviceTexture {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t object = 0;
+    int width = 0, height = 0, channels = 0;
+};
+
 struct Accel {
     DeviceBuffer<BvhNode> nodes;
     DeviceBuffer<TraceTriangle> triangles;      // traversal order (Morton sorted)
     DeviceBuffer<float4> world_vertices;        // 3 per primitive, instance-major order: position.xyz, w unused
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
+    DeviceBuffer<float2> shade_uv;              // 3 texcoords per primitive, instance-major order; only when a mesh has texcoords
+    bool has_uv = false;
     DeviceBuffer<float> normal_matrices;        // 9 floats per instance record: inverse transpose of the upper 3x3
     int64_t triangle_count = 0;
     int64_t node_count = 0;
@@ -102,6 +111,10 @@ struct Context {
     std::map<int, HostMesh> meshes;
     std::vector<bpt_instance> instances;
     DeviceBuffer<Material> materials;
+    std::map<int, DeviceTexture> textures;                  // by texture id (>= 1)
+    DeviceBuffer<unsigned long long> texture_objects;       // cudaTextureObject_t by texture id, 0 where there is none
+    bool texture_table_dirty = true;
+    bool has_textured_materials = false;
     std::vector<Material> host_materials;
     DeviceBuffer<Light> lights;
     int light_count = 0;
@@ -160,5 +173,6 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device);
 int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int height, uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
 int resolve_float4(Context* ctx, float* out);
 void release_wavefront(Context* ctx);
+int sync_texture_table(Context* ctx); // uploads the texture id -> cudaTextureObject_t table when it changed (bpt_api.cu)
 
 } // namespace bpt

@@ -390,7 +390,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
 
                 // path_tracing_closest_hit, MonteCarlo.cu:129-233. The same-primitive test (:137-142) already
                 // happened inside the traversal, which skips `previous_primitive`.
-                const Material material_parameter = s.materials[st.material_index];
+                const float2 texcoord = interpolate_texcoord(s.accel.textures, primitive, bx, by);
+                const Material material_parameter = material_at(s.materials[st.material_index], s.accel.textures, texcoord);
                 float3 world_geometric_normal = geometric_normal;
                 bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
                 bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 float4 bsdf_coverage_random = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF);
                 float coverage_cutoff = bsdf_coverage_random.w;
                 float3 bsdf_random_uvs = f3(bsdf_coverage_random);
-                float coverage = material_coverage(material_parameter);
+                float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
                 bool discard_from_coverage = coverage < coverage_cutoff;
 
                 if (backside_cull || discard_from_coverage) {
@@ -584,6 +585,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_set_tables first");
     if (ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
         return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: transmissive materials need bpt_set_dielectric_tables");
+    if (int status = sync_texture_table(ctx)) return status;
     if (settings->next_event_sample_count < 0 || settings->next_event_sample_count > 256)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: next_event_sample_count must be in [0, 256]");
     cudaStream_t st = ctx->stream;
@@ -604,7 +606,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     }
     if (wf->coverage_version != ctx->material_version) {
         std::vector<float> h_cov(ctx->host_materials.size());
-        for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage(ctx->host_materials[i]);
+        for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
         BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->coverage.ptr, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // h_cov goes out of scope
@@ -620,7 +622,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
 
     SceneView s = {};
-    s.accel = { ctx->accel.nodes.ptr, ctx->accel.triangles.ptr, traversal_min_active_for(ctx->accel.triangle_count), traversal_budget_for(ctx->accel.triangle_count) };
+    s.accel = accel_view(ctx);
     s.world_vertices = ctx->accel.world_vertices.ptr;
     s.shade = ctx->accel.shade.ptr;
     s.normal_matrices = ctx->accel.normal_matrices.ptr;

@@ -150,6 +150,8 @@ struct TraversalStack {
 struct AccelView {
     const BvhNode* __restrict__ nodes;
     const TraceTriangle* __restrict__ triangles;
+    const Material* __restrict__ materials; // with `textures`: only read by any-hit rays that meet a coverage-textured material
+    TextureView textures;
     int min_active; // see traversal_min_active_for
     int budget; // node visits between two refills of a warp's idle lanes: ~ the depth of the tree (measured: 24 up to a few
                 // million triangles, 48 for the 50M-triangle scene whose rays visit 80+ nodes)
@@ -164,6 +166,17 @@ BPT_HD int traversal_budget_for(long long triangle_count) { return triangle_coun
 // A round also ends once fewer than this many lanes of the warp are still traversing (measured on B200: +4 % on the 20 k
 // and 1 M triangle scenes; the 50 M triangle scene, bound by memory latency rather than issue slots, loses 1 % and opts out).
 BPT_HD int traversal_min_active_for(long long triangle_count) { return triangle_count > 8000000ll ? 0 : BPT_MIN_ACTIVE_LANES; }
+
+inline AccelView accel_view(const Context* ctx) {
+    AccelView a;
+    a.nodes = ctx->accel.nodes.ptr; a.triangles = ctx->accel.triangles.ptr;
+    a.materials = ctx->materials.ptr;
+    a.textures.objects = ctx->texture_objects.ptr;
+    a.textures.uv = ctx->accel.has_uv ? ctx->accel.shade_uv.ptr : nullptr;
+    a.min_active = traversal_min_active_for(ctx->accel.triangle_count);
+    a.budget = traversal_budget_for(ctx->accel.triangle_count);
+    return a;
+}
 
 BPT_D float4 ldg4(const float4* p) { return __ldg(p); }
 
@@ -256,6 +269,8 @@ struct Traversal {
                 if (candidate && t > ray.tmin && t < ray.tmax) {
                     // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
                     float coverage = coverage_by_material[__float_as_int(v1.w)];
+                    if (coverage < 0.0f) // coverage texture: Material::get_coverage(texcoord), Types.h:405-414
+                        coverage = material_coverage(a.materials[__float_as_int(v1.w)], a.textures, interpolate_texcoord(a.textures, primitive, u, v));
                     transmission *= 1.0f - coverage;
                     if (transmission < 0.0000001f) { transmission = 0.0f; return false; }
                 }

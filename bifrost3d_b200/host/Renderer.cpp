@@ -2,13 +2,17 @@
 // C ABI (include/bpt_c_api.h). Mirrors the behaviour of the reference's
 // extensions/OptiXRenderer/OptiXRenderer/Renderer.cpp (initialize :1365-1378, handle_updates :578-1205,
 // prepare_camera_state + render :1207-1265, setters :1389-1474) but flattens the scene into device arrays instead of an
-// OptiX scene graph. Scene synchronisation is non-incremental in this revision: any mesh / model / transform / material
-// change re-uploads the flattened scene and rebuilds the BVH (incremental refit is a "next" row).
+// OptiX scene graph. Scene synchronisation is non-incremental in this revision: any mesh / model / transform / material /
+// texture change re-uploads the flattened scene and rebuilds the BVH (incremental refit is a "next" row).
 #include <OptiXRenderer/Renderer.h>
 
 #include <optixu/optixpp_namespace.h>
 
+#include <Bifrost/Assets/Image.h>
+#include <Bifrost/Assets/InfiniteAreaLight.h>
 #include <Bifrost/Assets/Material.h>
+#include <Bifrost/Assets/Texture.h>
+#include <Bifrost/Math/RNG.h>
 #include <Bifrost/Assets/Mesh.h>
 #include <Bifrost/Assets/MeshModel.h>
 #include <Bifrost/Assets/Shading/Fittings.h>
@@ -172,6 +176,47 @@ struct Renderer::Implementation {
         if (status != BPT_OK) printf("OptiXRenderer(B200) error in %s: %s\n", what, bpt_last_error(ctx));
     }
 
+    // Images and textures, Renderer.cpp:650-751: every 2D texture becomes a texture object keyed by its TextureID.
+    // Returns true when something changed.
+    std::map<unsigned int, bool> uploaded_textures;
+    bool upload_textures() {
+        bool changed = false;
+        for (TextureID texture_ID : Textures::get_iterable()) {
+            if (uploaded_textures[texture_ID] && !Textures::get_changes(texture_ID).contains(Textures::Change::Created)) continue;
+            Image image = Textures::get_image_ID(texture_ID);
+            if (!image.exists() || image.get_depth() > 1) continue;
+            bpt_texture_desc desc = {};
+            desc.width = int(image.get_width()); desc.height = int(image.get_height());
+            switch (image.get_pixel_format()) {
+            case PixelFormat::Alpha8: desc.pixel_format = BPT_PIXEL_ALPHA8; break;
+            case PixelFormat::RGB24: desc.pixel_format = BPT_PIXEL_RGB24; break;
+            case PixelFormat::RGBA32: desc.pixel_format = BPT_PIXEL_RGBA32; break;
+            case PixelFormat::RGB_Float: desc.pixel_format = BPT_PIXEL_RGB_FLOAT; break;
+            case PixelFormat::RGBA_Float: desc.pixel_format = BPT_PIXEL_RGBA_FLOAT; break;
+            default:
+                printf("OptiXRenderer(B200) warning: texture %u has a pixel format the renderer does not sample; ignored.\n", texture_ID.get_index());
+                continue;
+            }
+            desc.is_srgb = image.is_sRGB() ? 1 : 0;
+            desc.wrap_u = Textures::get_wrapmode_U(texture_ID) == WrapMode::Repeat ? BPT_WRAP_REPEAT : BPT_WRAP_CLAMP;
+            desc.wrap_v = Textures::get_wrapmode_V(texture_ID) == WrapMode::Repeat ? BPT_WRAP_REPEAT : BPT_WRAP_CLAMP;
+            // rtTex2D reads mip level 0 of a single-level sampler: the magnification filter applies (Renderer.cpp:742-744).
+            desc.linear_filter = Textures::get_magnification_filter(texture_ID) == MagnificationFilter::Linear ? 1 : 0;
+            int status = bpt_upload_texture(ctx, int(texture_ID.get_index()), &desc, image.get_pixels());
+            check(ctx, status, "bpt_upload_texture");
+            uploaded_textures[texture_ID] = status == BPT_OK;
+            changed = true;
+        }
+        return changed;
+    }
+
+    // A material's texture id if the texture made it to the device, else 0 (untextured).
+    int device_texture_id(TextureID texture_ID) {
+        if (texture_ID == TextureID::invalid_UID()) return 0;
+        auto it = uploaded_textures.find(texture_ID);
+        return (it != uploaded_textures.end() && it->second) ? int(texture_ID.get_index()) : 0;
+    }
+
     void upload_geometry_and_materials() {
         // load_mesh, Renderer.cpp:92-136: every mesh referenced by a model.
         std::map<unsigned int, bool> uploaded;
@@ -215,13 +260,60 @@ struct Renderer::Implementation {
             d.coverage = host.is_cutout() ? host.get_cutout_threshold() : host.get_coverage();
             RGB emission = host.get_emission();
             d.emission[0] = emission.r; d.emission[1] = emission.g; d.emission[2] = emission.b;
-            if (host.has_tint_texture() || host.has_roughness_texture() || host.get_metallic_texture_ID() != TextureID::invalid_UID() ||
-                host.get_coverage_texture_ID() != TextureID::invalid_UID())
-                printf("OptiXRenderer(B200) warning: material %u is textured; textures are not implemented and are ignored.\n", material_ID.get_index());
+            // Renderer.cpp:760-806: one texture carries tint (rgb) and roughness (a), or roughness alone.
+            if (host.has_tint_texture())
+                d.tint_roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID());
+            else if (host.has_roughness_texture())
+                d.roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID());
+            d.metallic_texture_id = device_texture_id(host.get_metallic_texture_ID());
+            d.coverage_texture_id = device_texture_id(host.get_coverage_texture_ID());
         }
         check(ctx, bpt_set_materials(ctx, materials.data(), int(materials.size())), "bpt_set_materials");
         check(ctx, bpt_set_instances(ctx, instances.data(), int(instances.size())), "bpt_set_instances");
         check(ctx, bpt_build_accel(ctx), "bpt_build_accel");
+    }
+
+    // PresampledEnvironmentMap, PresampledEnvironmentMap.cpp:19-101: the latlong radiance map, the per pixel solid angle PDF
+    // (sans sin theta) of the core's InfiniteAreaLight and a list of light samples drawn from it up front.
+    bool upload_environment_map(const float tint[3], Image image, const InfiniteAreaLight& light, unsigned int sample_count = 8192u) {
+        const int width = int(image.get_width()), height = int(image.get_height());
+        std::vector<float> texels(4ull * width * height);
+        for (int y = 0; y < height; ++y)
+            for (int x = 0; x < width; ++x) {
+                RGBA pixel = image.get_pixel(Vector2ui(x, y));
+                float* texel = texels.data() + 4ull * (size_t(y) * width + x);
+                texel[0] = pixel.r; texel[1] = pixel.g; texel[2] = pixel.b; texel[3] = pixel.a;
+            }
+
+        const bool importance_sample = light.image_integral() >= 0.00001f && sample_count > 0;
+        std::vector<float> per_pixel_pdf(1, 0.0f);
+        int pdf_width = 1, pdf_height = 1;
+        std::vector<bpt_light_sample> samples(1); // a single invalid sample disables next event estimation (:63-64)
+        memset(samples.data(), 0, sizeof(bpt_light_sample));
+        if (importance_sample) {
+            pdf_width = int(light.get_PDF_width()); pdf_height = int(light.get_PDF_height());
+            per_pixel_pdf.resize(size_t(pdf_width) * pdf_height);
+            InfiniteAreaLightUtils::reconstruct_solid_angle_PDF_sans_sin_theta(light, per_pixel_pdf.data());
+
+            sample_count = max(2u, next_power_of_two(sample_count));
+            const int exponent = int(log2(sample_count));
+            std::vector<Vector2f> random_numbers(sample_count);
+            RNG::fill_progressive_multijittered_bluenoise_samples(random_numbers.data(), random_numbers.data() + sample_count);
+            samples.resize(sample_count);
+            // Bit-reversed indexing keeps samples of one stratum next to each other in the list (:75-83).
+            #pragma omp parallel for schedule(dynamic, 16)
+            for (int i = 0; i < int(sample_count); ++i) {
+                Assets::LightSample s = light.sample(random_numbers[reverse_bits(unsigned(i)) >> (32 - exponent)]);
+                bpt_light_sample& d = samples[i];
+                d.radiance[0] = s.radiance.r; d.radiance[1] = s.radiance.g; d.radiance[2] = s.radiance.b;
+                d.pdf = s.PDF;
+                d.direction_to_light[0] = s.direction_to_light.x; d.direction_to_light[1] = s.direction_to_light.y; d.direction_to_light[2] = s.direction_to_light.z;
+                d.distance = s.distance;
+            }
+        }
+        int status = bpt_set_environment(ctx, tint, texels.data(), width, height, per_pixel_pdf.data(), pdf_width, pdf_height, samples.data(), int(samples.size()));
+        check(ctx, status, "bpt_set_environment");
+        return status == BPT_OK;
     }
 
     void upload_lights() {
@@ -287,7 +379,8 @@ struct Renderer::Implementation {
             }
         }
 
-        bool geometry_changed = !scene_uploaded;
+        bool textures_changed = upload_textures();
+        bool geometry_changed = !scene_uploaded || textures_changed;
         geometry_changed |= !Meshes::get_changed_meshes().is_empty();
         geometry_changed |= !MeshModels::get_changed_models().is_empty();
         geometry_changed |= !Materials::get_changed_materials().is_empty();
@@ -304,16 +397,24 @@ struct Renderer::Implementation {
             should_reset_accumulations = true;
         }
 
-        // Scene roots, Renderer.cpp:1112-1200: environment tint (environment maps need textures: "next" row).
+        // Scene roots, Renderer.cpp:1112-1200: environment tint and map.
         for (SceneRoot scene_data : SceneRoots::get_changed_scenes()) {
             float tint[3] = { 0, 0, 0 };
+            bool has_map = false;
             if (!scene_data.get_changes().contains(SceneRoots::Change::Destroyed)) {
                 RGB env_tint = scene_data.get_environment_tint();
                 tint[0] = env_tint.r; tint[1] = env_tint.g; tint[2] = env_tint.b;
-                if (scene_data.get_environment_map().exists())
-                    printf("OptiXRenderer(B200) warning: environment maps through the Bifrost Texture manager are not implemented; using the tint only.\n");
+                Texture environment_map = scene_data.get_environment_map();
+                if (environment_map.exists()) {
+                    Image image = environment_map.get_image();
+                    if (channel_count(image.get_pixel_format()) == 4 && scene_data.get_environment_light() != nullptr)
+                        has_map = upload_environment_map(tint, image, *scene_data.get_environment_light());
+                    else // Renderer.cpp:1151-1160
+                        printf("OptiXRenderer only supports environments with 4 channels. '%s' has %u.\n", image.get_name().c_str(), channel_count(image.get_pixel_format()));
+                }
             }
-            check(ctx, bpt_set_environment(ctx, tint, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0), "bpt_set_environment");
+            if (!has_map)
+                check(ctx, bpt_set_environment(ctx, tint, nullptr, 0, 0, nullptr, 0, 0, nullptr, 0), "bpt_set_environment");
             should_reset_accumulations = true;
         }
         scene_uploaded = true;

@@ -26,7 +26,8 @@ def plane(quads_per_edge=1):
     zz, xx = np.meshgrid(np.arange(quads_per_edge), np.arange(quads_per_edge), indexing="ij")
     base = (xx + zz * size).reshape(-1)
     tris = np.stack([np.stack([base, base + size, base + 1], axis=1), np.stack([base + 1, base + size, base + size + 1], axis=1)], axis=1)
-    return {"indices": tris.reshape(-1, 3).astype(np.uint32), "positions": positions, "normals": normals}
+    texcoords = np.stack([x, z], axis=-1).reshape(-1, 2).astype(np.float32)  # MeshCreation::plane: texcoord = (x, z) in [0, 1]
+    return {"indices": tris.reshape(-1, 3).astype(np.uint32), "positions": positions, "normals": normals, "texcoords": texcoords}
 
 
 def revolved_sphere(longitude_quads=100, latitude_quads=50):
@@ -50,7 +51,9 @@ def revolved_sphere(longitude_quads=100, latitude_quads=50):
         if y != latitude_quads - 1:
             tris.append(np.stack([base + 1, base + lon_size + 1, base + lon_size], axis=1))
     # the reference interleaves the two triangles of each quad; the order only permutes primitive ids
-    return {"indices": np.concatenate(tris).astype(np.uint32), "positions": positions.astype(np.float32), "normals": normals.astype(np.float32)}
+    texcoords = np.stack(np.broadcast_arrays(tx[None, :], ty[:, None]), axis=-1).reshape(-1, 2).astype(np.float32)  # (longitude, latitude) in [0, 1]
+    return {"indices": np.concatenate(tris).astype(np.uint32), "positions": positions.astype(np.float32), "normals": normals.astype(np.float32),
+            "texcoords": texcoords}
 
 
 def displaced_grid(quads_per_edge, seed, amplitude=0.08, octaves=4):
@@ -263,8 +266,11 @@ def triangle_count(scene):
 
 def upload(ctx, scene):
     """Feeds a scene dict through the C ABI (mirrors Renderer::handle_updates, Renderer.cpp:578-1205)."""
+    for texture_id, tex in scene.get("textures", {}).items():
+        ctx.upload_texture(texture_id, tex["pixels"], tex.get("srgb", False), tex.get("wrap_u", capi.WRAP_REPEAT), tex.get("wrap_v", capi.WRAP_REPEAT),
+                           tex.get("linear", True))
     for mesh_id, m in scene["meshes"].items():
-        ctx.upload_mesh(mesh_id, m["indices"], m["positions"], m.get("normals"), None, m.get("tints"))
+        ctx.upload_mesh(mesh_id, m["indices"], m["positions"], m.get("normals"), m.get("texcoords"), m.get("tints"))
     ctx.set_materials(scene["materials"])
     ctx.set_instances(scene["instances"])
     ctx.set_lights(scene["lights"])

@@ -33,7 +33,7 @@ typedef enum bpt_status {
 
 /* ---- PODs, layout identical to extensions/OptiXRenderer/OptiXRenderer/Types.h ------------------ */
 
-/* Types.h:353-416 `Material` (64 bytes). Texture ids must be 0: textures are a "next" row. */
+/* Types.h:353-416 `Material` (64 bytes). A texture id is 0 (none) or the id of a texture uploaded with bpt_upload_texture. */
 typedef struct bpt_material {
     uint16_t flags;              /* 1 = ThinWalled, 2 = Cutout */
     uint16_t shading_model;      /* 0 = Default, 1 = Diffuse, 2 = Transmissive (needs bpt_set_dielectric_tables) */
@@ -129,6 +129,29 @@ int bpt_set_tables(bpt_ctx* ctx, const float* ggx_with_fresnel_rho, const float*
 int bpt_set_dielectric_tables(bpt_ctx* ctx, const float* into_light_medium, const float* into_dense_medium);
 
 /* ---- scene upload (Renderer::handle_updates, Renderer.cpp:578-1205) ---------------------------- */
+
+/* Images and textures (Renderer.cpp:650-751). Pixel formats carry the values of Bifrost::Assets::PixelFormat (Image.h:27-38);
+ * the ones the reference uploads are accepted. RGB24 / RGB_Float are widened to four channels (alpha 255 / 1) like
+ * Renderer.cpp:683-694. Texel (x, y) is pixels[y * width + x]; texcoord (0, 0) is the corner of texel (0, 0).
+ * Sampling follows the OptiX sampler the reference creates (:729-747): normalized coordinates, one mip level, hardware
+ * bilinear (linear_filter != 0, from MagnificationFilter::Linear) or nearest filtering, sRGB decode of 8-bit texels before
+ * filtering when is_srgb != 0 (RT_TEXTURE_READ_NORMALIZED_FLOAT_SRGB), wrap 0 = clamp to edge, 1 = repeat. */
+enum { BPT_PIXEL_ALPHA8 = 1, BPT_PIXEL_RGB24 = 3, BPT_PIXEL_RGBA32 = 4, BPT_PIXEL_RGB_FLOAT = 6, BPT_PIXEL_RGBA_FLOAT = 7 };
+enum { BPT_WRAP_CLAMP = 0, BPT_WRAP_REPEAT = 1 };
+typedef struct bpt_texture_desc {
+    int32_t width, height;
+    int32_t pixel_format;   /* BPT_PIXEL_* */
+    int32_t is_srgb;
+    int32_t wrap_u, wrap_v; /* BPT_WRAP_* */
+    int32_t linear_filter;
+    int32_t reserved;
+} bpt_texture_desc;
+/* texture_id >= 1 (0 means "no texture" in bpt_material). Re-uploading an id replaces the texture. Upload textures before the
+ * materials that reference them. */
+int bpt_upload_texture(bpt_ctx* ctx, int texture_id, const bpt_texture_desc* desc, const void* pixels);
+int bpt_destroy_texture(bpt_ctx* ctx, int texture_id);
+/* rtTex2D<float4>(texture, u, v) for n texcoords (uv: 2n floats, out_rgba: 4n floats); unit entry point for the parity tests. */
+int bpt_texture_sample(bpt_ctx* ctx, int texture_id, int64_t n, const float* uv, float* out_rgba);
 
 /* load_mesh, Renderer.cpp:92-136. indices: 3*primitive_count uint32; positions: 3*vertex_count floats;
  * normals (nullable): 3*vertex_count floats, octahedral-encoded to short2 like OctahedralNormal::encode_precise;

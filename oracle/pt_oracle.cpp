@@ -55,6 +55,7 @@ struct SettingsIn { uint32_t max_bounce_count; int32_t next_event_sample_count; 
 struct Mesh {
     std::vector<uint32_t> indices;
     std::vector<float3> positions;
+    std::vector<float2> texcoords;         // empty when the mesh has none
     std::vector<OctahedralNormal> normals; // empty when the mesh has none
     std::vector<uchar4> tints;
 };
@@ -63,10 +64,52 @@ struct Triangle {
     float3 p0, p1, p2;
     OctahedralNormal n0, n1, n2;
     uchar4 t0, t1, t2;
+    float2 uv0, uv1, uv2;
     int material;
     int instance;
-    bool has_normals, has_tints;
+    bool has_normals, has_tints, has_texcoords;
 };
+
+// Restatement of the sampler the reference creates for a Bifrost texture (Renderer.cpp:650-751) and reads with rtTex2D
+// (Types.h:388-414). OptiX 6.5 hands this to the CUDA texture unit, whose arithmetic is documented in the CUDA C++
+// Programming Guide, appendix "Texture Fetching": normalized coordinates x = u * N; wrap: x = frac(u) * N, clamp: x stays
+// in [0, N); nearest: T[floor(x)]; linear: xB = x - 0.5, i = floor(xB), alpha = frac(xB) held in 1.8 fixed point,
+// (1 - alpha) T[i] + alpha T[i + 1] with i and i + 1 wrapped or clamped. 8-bit texels read as v / 255, sRGB images are
+// decoded per texel before filtering (alpha excluded). PARITY UNPINNED by the reference: no reference test samples a texture.
+struct Texture {
+    int width = 0, height = 0, channels = 0;
+    bool linear = true;
+    int wrap_u = 1, wrap_v = 1; // 0 clamp, 1 repeat
+    std::vector<float4> texels;
+};
+
+inline float srgb_to_linear(float c) { return c <= 0.04045f ? c / 12.92f : powf((c + 0.055f) / 1.055f, 2.4f); }
+
+inline int wrap_index(int i, int n, int mode) {
+    if (mode == 1) { i %= n; return i < 0 ? i + n : i; }
+    return i < 0 ? 0 : (i >= n ? n - 1 : i);
+}
+
+inline float4 texture_sample(const Texture& tex, float u, float v) {
+    auto coord = [](float s, int n, int mode) {
+        if (mode == 1) s = s - floorf(s);
+        float x = s * n;
+        if (mode == 0) x = fminf(fmaxf(x, 0.0f), (float)n); // texel indices are clamped below
+        return x;
+    };
+    float x = coord(u, tex.width, tex.wrap_u), y = coord(v, tex.height, tex.wrap_v);
+    auto texel = [&](int i, int j) { return tex.texels[(size_t)wrap_index(j, tex.height, tex.wrap_v) * tex.width + wrap_index(i, tex.width, tex.wrap_u)]; };
+    if (!tex.linear)
+        return texel((int)floorf(x), (int)floorf(y));
+    float xb = x - 0.5f, yb = y - 0.5f;
+    int i = (int)floorf(xb), j = (int)floorf(yb);
+    // Rounded to nearest: measured against B200's texture unit this halves the mean deviation compared with truncation
+    // (4.6e-4 against 1.1e-3 of the texel range); what remains (<= 2/256) is the unit's own fixed-point coordinate handling.
+    float alpha = floorf((xb - floorf(xb)) * 256.0f + 0.5f) / 256.0f;
+    float beta = floorf((yb - floorf(yb)) * 256.0f + 0.5f) / 256.0f;
+    float4 t00 = texel(i, j), t10 = texel(i + 1, j), t01 = texel(i, j + 1), t11 = texel(i + 1, j + 1);
+    return (1.0f - alpha) * (1.0f - beta) * t00 + alpha * (1.0f - beta) * t10 + (1.0f - alpha) * beta * t01 + alpha * beta * t11;
+}
 
 struct Box { float3 lo, hi; };
 
@@ -87,6 +130,7 @@ struct Scene {
     std::map<int, Mesh> meshes;
     std::vector<InstanceIn> instances;
     std::vector<Material> materials;
+    std::map<int, Texture> textures;
     std::vector<Light> lights; // analytical lights, then (optionally) the environment
     int light_count = 0;
     EnvironmentIn env;
@@ -98,6 +142,37 @@ struct Scene {
     std::vector<Node> nodes;
     float4 nee_offsets[256];
 };
+
+// Material::get_coverage / get_tint_roughness / get_metallic (Types.h:388-414, GPU_DEVICE only) with rtTex2D restated by
+// texture_sample above.
+inline float material_coverage(const Scene& sc, const Material& m, float2 texcoord) {
+    float coverage_tex_sample = 1.0f;
+    if (m.coverage_texture_ID)
+        coverage_tex_sample = texture_sample(sc.textures.at(m.coverage_texture_ID), texcoord.x, texcoord.y).x;
+    if (m.is_cutout()) return coverage_tex_sample < m.coverage ? 0.0f : 1.0f;
+    return m.coverage * coverage_tex_sample;
+}
+
+inline float2 interpolate_texcoord(const Triangle& tri, float bx, float by) {
+    // TriangleAttributes.cu:57-64; `texcoord - make_float2(0)` is a no-op there, an untextured mesh reads (0, 0) here.
+    if (!tri.has_texcoords) return make_float2(0.0f, 0.0f);
+    float bz = 1.0f - bx - by;
+    return tri.uv1 * bx + tri.uv2 * by + tri.uv0 * bz;
+}
+
+// The material as the shading models see it through get_tint_roughness(texcoord) and get_metallic(texcoord).
+inline Material material_at(const Scene& sc, const Material& m, float2 texcoord) {
+    Material r = m;
+    float4 tint_roughness = make_float4(m.tint, m.roughness);
+    if (m.tint_roughness_texture_ID)
+        tint_roughness *= texture_sample(sc.textures.at(m.tint_roughness_texture_ID), texcoord.x, texcoord.y);
+    if (m.roughness_texture_ID)
+        tint_roughness.w *= texture_sample(sc.textures.at(m.roughness_texture_ID), texcoord.x, texcoord.y).x;
+    r.tint = make_float3(tint_roughness); r.roughness = tint_roughness.w;
+    if (m.metallic_texture_ID)
+        r.metallic = m.metallic * texture_sample(sc.textures.at(m.metallic_texture_ID), texcoord.x, texcoord.y).x;
+    return r;
+}
 
 // ---- watertight ray / triangle (Woop et al. 2013), plain fp32 -----------------------------------
 struct Shear { int kx, ky, kz; float Sx, Sy, Sz; };
@@ -228,7 +303,7 @@ float transmission_bvh(const Scene& sc, float3 o, float3 d, float tmin, float tm
         if (!watertight(sh, o, tri.p0, tri.p1, tri.p2, t, u, v)) return false;
         if (!(t > tmin && t < tmax)) return false;
         const Material& m = sc.materials[tri.material];
-        float coverage = m.is_cutout() ? (1.0f < m.coverage ? 0.0f : 1.0f) : m.coverage * 1.0f;
+        float coverage = material_coverage(sc, m, interpolate_texcoord(tri, u, v));
         transmission *= 1.0f - coverage;
         if (transmission < 0.0000001f) { transmission = 0.0f; return true; }
         return false;
@@ -283,6 +358,8 @@ void flatten(Scene& sc) {
             t.has_normals = !mesh.normals.empty(); t.has_tints = !mesh.tints.empty();
             if (t.has_normals) { t.n0 = mesh.normals[i0]; t.n1 = mesh.normals[i1]; t.n2 = mesh.normals[i2]; }
             if (t.has_tints) { t.t0 = mesh.tints[i0]; t.t1 = mesh.tints[i1]; t.t2 = mesh.tints[i2]; }
+            t.has_texcoords = !mesh.texcoords.empty();
+            if (t.has_texcoords) { t.uv0 = mesh.texcoords[i0]; t.uv1 = mesh.texcoords[i1]; t.uv2 = mesh.texcoords[i2]; }
             t.material = inst.material_id; t.instance = instance_index;
             sc.triangles.push_back(t);
         }
@@ -360,11 +437,7 @@ void build_bvh(Scene& sc) {
 
 struct Counters { uint64_t extend_rays = 0, shadow_rays = 0; };
 
-inline float material_coverage(const Material& m) {
-    // Material::get_coverage (Types.h:405-414) without a coverage texture: the texture sample is 1.
-    if (m.is_cutout()) return 1.0f < m.coverage ? 0.0f : 1.0f;
-    return m.coverage * 1.0f;
-}
+
 
 inline float3 transform_normal(const float* nm, float3 n) {
     return make_float3(nm[0] * n.x + nm[1] * n.y + nm[2] * n.z, nm[3] * n.x + nm[4] * n.y + nm[5] * n.z, nm[6] * n.x + nm[7] * n.y + nm[8] * n.z);
@@ -517,7 +590,7 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
         shading_normal = normalize(shading_normal);
     } else
         shading_normal = geometric_normal;
-    float2 texcoord = make_float2(0.0f, 0.0f);
+    float2 texcoord = interpolate_texcoord(tri, barycentrics.x, barycentrics.y);
     float4 tint_and_roughness_scale;
     if (tri.has_tints) {
         const float byte_to_float_normalizer = 1.0f / 255.0f;
@@ -538,7 +611,7 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
         payload.ray_min_t = nextafterf(t_hit, INFINITY);
         return;
     }
-    const Material& material_parameter = sc.materials[tri.material];
+    const Material material_parameter = material_at(sc, sc.materials[tri.material], texcoord);
 
     // The geometry is already in world space: the geometric normal needs no transform, the shading normal
     // (object space, per vertex) goes through the instance's inverse transpose like rtTransformNormal.
@@ -550,7 +623,7 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
     float4 bsdf_coverage_random_4f = rng_sample4f(payload, RngSamplingDimension::BSDF);
     float coverage_cutoff = bsdf_coverage_random_4f.w;
     float3 bsdf_random_uvs = make_float3(bsdf_coverage_random_4f);
-    float coverage = material_coverage(material_parameter);
+    float coverage = material_coverage(sc, material_parameter, texcoord);
     bool discard_from_coverage = coverage < coverage_cutoff;
     if (backside_cull || discard_from_coverage) {
         payload.ray_min_t = nextafterf(t_hit, INFINITY);
@@ -772,6 +845,37 @@ void pto_scene_add_mesh(void* s, int mesh_id, const uint32_t* indices, int primi
     if (tint_roughness) {
         m.tints.resize(vertex_count);
         for (int i = 0; i < vertex_count; ++i) m.tints[i] = make_uchar4(tint_roughness[4 * i], tint_roughness[4 * i + 1], tint_roughness[4 * i + 2], tint_roughness[4 * i + 3]);
+    }
+}
+void pto_scene_set_mesh_texcoords(void* s, int mesh_id, const float* texcoords, int vertex_count) {
+    Mesh& m = ((Scene*)s)->meshes[mesh_id];
+    m.texcoords.resize(vertex_count);
+    for (int i = 0; i < vertex_count; ++i) m.texcoords[i] = make_float2(texcoords[2 * i], texcoords[2 * i + 1]);
+}
+// pixel_format: Bifrost::Assets::PixelFormat values (Alpha8 1, RGB24 3, RGBA32 4, RGB_Float 6, RGBA_Float 7).
+void pto_scene_add_texture(void* s, int texture_id, int width, int height, int pixel_format, int is_srgb, int wrap_u, int wrap_v, int linear_filter,
+                           const void* pixels) {
+    Texture& tex = ((Scene*)s)->textures[texture_id];
+    tex.width = width; tex.height = height; tex.linear = linear_filter != 0; tex.wrap_u = wrap_u; tex.wrap_v = wrap_v;
+    tex.texels.resize((size_t)width * height);
+    const unsigned char* bytes = (const unsigned char*)pixels;
+    const float* floats = (const float*)pixels;
+    auto decode = [&](unsigned char b, bool color) { float c = b / 255.0f; return (is_srgb && color) ? srgb_to_linear(c) : c; };
+    for (size_t i = 0; i < tex.texels.size(); ++i) {
+        switch (pixel_format) {
+        case 1: tex.channels = 1; tex.texels[i] = make_float4(decode(bytes[i], true), 0.0f, 0.0f, 1.0f); break;
+        case 3: tex.channels = 4; tex.texels[i] = make_float4(decode(bytes[3 * i], true), decode(bytes[3 * i + 1], true), decode(bytes[3 * i + 2], true), 1.0f); break;
+        case 4: tex.channels = 4; tex.texels[i] = make_float4(decode(bytes[4 * i], true), decode(bytes[4 * i + 1], true), decode(bytes[4 * i + 2], true), decode(bytes[4 * i + 3], false)); break;
+        case 6: tex.channels = 4; tex.texels[i] = make_float4(floats[3 * i], floats[3 * i + 1], floats[3 * i + 2], 1.0f); break;
+        default: tex.channels = 4; tex.texels[i] = make_float4(floats[4 * i], floats[4 * i + 1], floats[4 * i + 2], floats[4 * i + 3]); break;
+        }
+    }
+}
+void pto_texture_sample(void* s, int texture_id, int64_t n, const float* uv, float* out_rgba) {
+    const Texture& tex = ((Scene*)s)->textures.at(texture_id);
+    for (int64_t i = 0; i < n; ++i) {
+        float4 r = texture_sample(tex, uv[2 * i], uv[2 * i + 1]);
+        out_rgba[4 * i] = r.x; out_rgba[4 * i + 1] = r.y; out_rgba[4 * i + 2] = r.z; out_rgba[4 * i + 3] = r.w;
     }
 }
 void pto_scene_set_instances(void* s, const void* instances, int count) { ((Scene*)s)->instances.assign((const InstanceIn*)instances, (const InstanceIn*)instances + count); }

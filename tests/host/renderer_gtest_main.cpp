@@ -21,6 +21,88 @@
 
 #include <RendererTest.h>
 
+// ---- additional cases for the rows the reference's fixture does not reach: textures and environment maps ----
+namespace OptiXRenderer {
+
+// A quad that fills the orthographic frame with texcoords (0,0)..(1,1) and a nearest-filtered RGBA32 tint texture with one
+// texel per pixel: the TintVisualization backend must show the texels (Material::get_tint_roughness, Types.h:388-396).
+TEST_F(RendererFixture, b200_render_tint_texture) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    using namespace Bifrost::Scene;
+
+    auto size = Math::Vector2i(4, 3);
+    CameraID camera_ID = create_ortho_camera(size);
+    SceneRoot root = Cameras::get_scene_ID(camera_ID);
+
+    Mesh mesh = Mesh("Quad", 2, 4, { MeshFlag::Position, MeshFlag::Texcoord });
+    mesh.get_primitives()[0] = { 0, 1, 2 };
+    mesh.get_primitives()[1] = { 1, 2, 3 };
+    mesh.get_positions()[0] = { -0.5f * size.x, -0.5f * size.y, 1.0f };
+    mesh.get_positions()[1] = { -0.5f * size.x, 0.5f * size.y, 1.0f };
+    mesh.get_positions()[2] = { 0.5f * size.x, -0.5f * size.y, 1.0f };
+    mesh.get_positions()[3] = { 0.5f * size.x, 0.5f * size.y, 1.0f };
+    mesh.get_texcoords()[0] = { 0.0f, 0.0f };
+    mesh.get_texcoords()[1] = { 0.0f, 1.0f };
+    mesh.get_texcoords()[2] = { 1.0f, 0.0f };
+    mesh.get_texcoords()[3] = { 1.0f, 1.0f };
+
+    Image image = Image::create2D("Tint", PixelFormat::RGBA32, false, Math::Vector2ui(size.x, size.y));
+    for (int y = 0; y < size.y; ++y)
+        for (int x = 0; x < size.x; ++x)
+            image.set_pixel(Math::RGBA(x / float(size.x - 1), y / float(size.y - 1), 0.5f, 1.0f), Math::Vector2ui(x, y));
+    Texture texture = Texture::create2D(image, MagnificationFilter::None, MinificationFilter::None, WrapMode::Clamp, WrapMode::Clamp);
+
+    auto material = Bifrost::Assets::Material::create_dielectric("Material", Math::RGB::white(), 0.0f);
+    material.set_flags(MaterialFlag::ThinWalled);
+    material.set_shading_model(ShadingModel::Diffuse);
+    material.set_tint_roughness_texture(texture);
+
+    SceneNode node = SceneNode("Node");
+    node.set_parent(root.get_root_node());
+    MeshModel(node, mesh, material);
+
+    render(camera_ID, size, Backend::TintVisualization, [=](half4* pixels) {
+        for (int y = 0; y < size.y; ++y)
+            for (int x = 0; x < size.x; ++x) {
+                half4 pixel = pixels[x + y * size.x];
+                EXPECT_FLOAT_EQ_EPS(x / float(size.x - 1), float(pixel.r), 0.003f) << " at pixel (" << x << ", " << y << ")";
+                EXPECT_FLOAT_EQ_EPS(y / float(size.y - 1), float(pixel.g), 0.003f) << " at pixel (" << x << ", " << y << ")";
+                EXPECT_FLOAT_EQ_EPS(0.5f, float(pixel.b), 0.003f) << " at pixel (" << x << ", " << y << ")";
+            }
+    });
+}
+
+// An empty scene under a constant RGBA_Float environment map: every pixel shows map * tint (miss program,
+// SimpleRGPs.cu:349-362), with the map going Texture -> InfiniteAreaLight -> presampled light list on the way.
+TEST_F(RendererFixture, b200_render_environment_map) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    using namespace Bifrost::Scene;
+
+    auto size = Math::Vector2i(8, 6);
+    Image image = Image::create2D("Environment", PixelFormat::RGBA_Float, false, Math::Vector2ui(16, 8));
+    for (unsigned int i = 0; i < 16 * 8; ++i)
+        image.set_pixel(Math::RGBA(0.5f, 1.0f, 2.0f, 1.0f), i);
+    Texture environment = Texture::create2D(image, MagnificationFilter::Linear, MinificationFilter::Linear, WrapMode::Repeat, WrapMode::Clamp);
+    SceneRoot scene = SceneRoot("Test", environment, Math::RGB(0.5f, 0.5f, 0.25f));
+
+    Math::Matrix4x4f orthographic_matrix, inverse_orthographic_matrix;
+    CameraUtils::compute_orthographic_projection(float(size.x), float(size.y), 1000.0f, orthographic_matrix, inverse_orthographic_matrix);
+    CameraID camera_ID = Cameras::create("Test", scene.get_ID(), orthographic_matrix, inverse_orthographic_matrix);
+    Cameras::set_renderer_ID(camera_ID, renderer->get_renderer_ID());
+
+    render(camera_ID, size, [=](half4* pixels) {
+        for (int i = 0; i < size.x * size.y; ++i) {
+            EXPECT_FLOAT_EQ_EPS(0.25f, float(pixels[i].r), 1e-3f);
+            EXPECT_FLOAT_EQ_EPS(0.5f, float(pixels[i].g), 1e-3f);
+            EXPECT_FLOAT_EQ_EPS(0.5f, float(pixels[i].b), 1e-3f);
+        }
+    });
+}
+
+} // namespace OptiXRenderer
+
 // tests/OptiXRendererTests/Utils.cpp uses windows.h; the data directory is unused by this implementation.
 std::filesystem::path get_data_directory() { return std::filesystem::path("."); }
 

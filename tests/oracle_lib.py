@@ -144,6 +144,9 @@ class OracleScene:
         for name in ("pto_scene_set_instances", "pto_scene_set_materials", "pto_scene_set_lights"):
             getattr(lib, name).argtypes = [vp, vp, i32]; getattr(lib, name).restype = None
         lib.pto_scene_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]; lib.pto_scene_set_environment.restype = None
+        lib.pto_scene_set_mesh_texcoords.argtypes = [vp, i32, vp, i32]; lib.pto_scene_set_mesh_texcoords.restype = None
+        lib.pto_scene_add_texture.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]; lib.pto_scene_add_texture.restype = None
+        lib.pto_texture_sample.argtypes = [vp, i32, i64, vp, vp]; lib.pto_texture_sample.restype = None
         lib.pto_scene_build.argtypes = [vp]; lib.pto_scene_build.restype = None
         lib.pto_triangle_count.argtypes = [vp]; lib.pto_triangle_count.restype = i64
         lib.pto_world_vertices.argtypes = [vp, vp]; lib.pto_world_vertices.restype = None
@@ -156,6 +159,14 @@ class OracleScene:
             nrm = None if m.get("normals") is None else _f32(m["normals"])
             tints = None if m.get("tints") is None else np.ascontiguousarray(m["tints"], np.uint8)
             lib.pto_scene_add_mesh(self.h, int(mesh_id), _p(idx), idx.shape[0], _p(pos), _p(nrm), _p(tints), pos.shape[0])
+            if m.get("texcoords") is not None:
+                uv = _f32(m["texcoords"])
+                lib.pto_scene_set_mesh_texcoords(self.h, int(mesh_id), _p(uv), uv.shape[0])
+        from bifrost3d_b200 import capi
+        for texture_id, tex in scene.get("textures", {}).items():
+            fmt, pixels = capi.pixel_format_of(tex["pixels"])
+            lib.pto_scene_add_texture(self.h, int(texture_id), pixels.shape[1], pixels.shape[0], fmt, int(tex.get("srgb", False)),
+                                      int(tex.get("wrap_u", capi.WRAP_REPEAT)), int(tex.get("wrap_v", capi.WRAP_REPEAT)), int(tex.get("linear", True)), _p(pixels))
         mats = np.ascontiguousarray(scene["materials"]); inst = np.ascontiguousarray(scene["instances"]); lights = np.ascontiguousarray(scene["lights"])
         lib.pto_scene_set_materials(self.h, _p(mats), mats.shape[0])
         lib.pto_scene_set_instances(self.h, _p(inst), inst.shape[0])
@@ -172,6 +183,12 @@ class OracleScene:
     def close(self):
         if self.h:
             self.lib.pto_scene_destroy(self.h); self.h = None
+
+    def texture_sample(self, texture_id, uv):
+        uv = _f32(uv).reshape(-1, 2)
+        out = np.empty((uv.shape[0], 4), np.float32)
+        self.lib.pto_texture_sample(self.h, int(texture_id), uv.shape[0], _p(uv), _p(out))
+        return out
 
     def triangle_count(self):
         return self.lib.pto_triangle_count(self.h)

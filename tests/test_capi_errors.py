@@ -29,7 +29,7 @@ def test_bad_inputs_are_rejected_loudly():
     with pytest.raises(b.BptError, match="unknown shading model"):
         ctx.set_materials(np.array([unknown], capi.MATERIAL_DTYPE))
     textured = scenes.material((1, 1, 1), 0.1); textured["coverage_texture_id"] = 3
-    with pytest.raises(b.BptError, match="textured"):
+    with pytest.raises(b.BptError, match="not uploaded"):
         ctx.set_materials(np.array([textured], capi.MATERIAL_DTYPE))
     with pytest.raises(b.BptError):
         ctx.set_lights(np.zeros(1, capi.LIGHT_DTYPE))  # type 0 = None
