@@ -42,7 +42,7 @@ class Camera(C.Structure):
 
 
 class Settings(C.Structure):
-    _fields_ = [("max_bounce_count", C.c_uint32), ("next_event_sample_count", C.c_int32), ("path_regularization_pdf_scale", C.c_float), ("reserved", C.c_uint32)]
+    _fields_ = [("max_bounce_count", C.c_uint32), ("next_event_sample_count", C.c_int32), ("path_regularization_pdf_scale", C.c_float), ("russian_roulette_start_bounce", C.c_uint32)]
 
 
 class Counters(C.Structure):
@@ -270,9 +270,10 @@ class Bpt:
         return {"triangles": t.value, "nodes": n.value, "build_ms": ms.value}
 
     # ---- rendering ----
-    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, reset=False):
+    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, reset=False,
+               russian_roulette_start=0):
         cam = camera if isinstance(camera, Camera) else make_camera(*camera)
-        s = Settings(max_bounces, nee_samples, pdf_scale, 0)
+        s = Settings(max_bounces, nee_samples, pdf_scale, russian_roulette_start)
         self._check(self.lib.bpt_render(self.h, C.byref(cam), C.byref(s), width, height, first_sample, sample_count, int(reset)))
         self._size = (width, height)
 

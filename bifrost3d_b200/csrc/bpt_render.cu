@@ -85,6 +85,7 @@ struct FrameParams {
     unsigned int max_bounce_count;
     int next_event_sample_count;
     float path_regularization_pdf_scale;
+    unsigned int russian_roulette_start_bounce; // 0 = off (the reference has no Russian roulette)
 };
 
 // Appends `value` to a queue for every lane with `pred` set: one atomicAdd per warp.
@@ -485,6 +486,14 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
 
                     next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
                     next_tmin = 0.0f;
+                    // Russian roulette, opt-in (bpt_settings.russian_roulette_start_bounce): survival probability =
+                    // the largest throughput component, decided by the otherwise unused RNG dimension 3 of this bounce.
+                    if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
+                        float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
+                        float u = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
+                        if (u < survival) throughput = throughput / survival;
+                        else throughput = f3(0.0f);
+                    }
                     bounces += 1u;
                     if (!light_sample.pdf.is_valid())
                         bsdf_pdf.disable_MIS();
@@ -668,6 +677,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     f.max_bounce_count = settings->max_bounce_count;
     f.next_event_sample_count = settings->next_event_sample_count;
     f.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
+    f.russian_roulette_start_bounce = settings->russian_roulette_start_bounce;
 
     // Persistent grids: a whole number of CTAs per SM.
     const int trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;

@@ -118,7 +118,7 @@ BPT_D float4 sobol_sample4f(uint32_t accumulation_count, uint32_t pixel_hash, ui
 }
 
 // RngSamplingDimension, Types.h:422-427
-enum : uint32_t { DIM_CAMERA = 0, DIM_NEE = 1, DIM_BSDF = 2, DIM_MAX = 8 };
+enum : uint32_t { DIM_CAMERA = 0, DIM_NEE = 1, DIM_BSDF = 2, DIM_ROULETTE = 3 /* not used by the reference */, DIM_MAX = 8 };
 
 BPT_D float4 path_rng_sample4f(uint32_t accumulation_count, uint32_t pixel_hash, uint32_t bounces, uint32_t sampling_dimension) {
     return sobol_sample4f(accumulation_count, pixel_hash, DIM_MAX * bounces + sampling_dimension);

@@ -93,7 +93,10 @@ typedef struct bpt_settings {
     uint32_t max_bounce_count;
     int32_t next_event_sample_count;
     float path_regularization_pdf_scale;
-    uint32_t reserved;
+    /* Russian roulette: 0 = off, which is the reference's behaviour (it has none). n > 0: from the n-th surface interaction
+     * of a path on, the path survives with probability clamp(max(throughput), 0.05, 1) and its throughput is divided by it;
+     * the decision uses RNG dimension 3 of that bounce (Types.h:422-427 leaves dimensions 3..7 free). */
+    uint32_t russian_roulette_start_bounce;
 } bpt_settings;
 
 typedef struct bpt_counters {

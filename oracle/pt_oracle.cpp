@@ -50,7 +50,7 @@ namespace {
 
 struct InstanceIn { int32_t mesh_id; int32_t material_id; float to_world[12]; };
 struct CameraIn { float view_to_world_rotation[9]; float inverse_projection[16]; float inverse_view_projection[16]; };
-struct SettingsIn { uint32_t max_bounce_count; int32_t next_event_sample_count; float path_regularization_pdf_scale; uint32_t reserved; };
+struct SettingsIn { uint32_t max_bounce_count; int32_t next_event_sample_count; float path_regularization_pdf_scale; uint32_t russian_roulette_start_bounce; };
 
 struct Mesh {
     std::vector<uint32_t> indices;
@@ -689,6 +689,15 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
 
     payload.position = offset_ray_origin(world_intersection_point, payload.direction, world_geometric_normal);
     payload.ray_min_t = 0.0f;
+    // Russian roulette: NOT in the reference. An opt-in extension of the product (bpt_settings.russian_roulette_start_bounce)
+    // restated here so that it can be checked sample for sample; it draws from RNG dimension 3, which the reference leaves free.
+    if (st.settings->russian_roulette_start_bounce != 0u && payload.bounces + 1u >= st.settings->russian_roulette_start_bounce &&
+        (payload.throughput.x > 0.0f || payload.throughput.y > 0.0f || payload.throughput.z > 0.0f)) {
+        float survival = fminf(fmaxf(fmaxf(fmaxf(payload.throughput.x, payload.throughput.y), payload.throughput.z), 0.05f), 1.0f);
+        float u = rng_sample4f(payload, RngSamplingDimension(3)).x;
+        if (u < survival) payload.throughput = payload.throughput / survival;
+        else payload.throughput = make_float3(0.0f);
+    }
     payload.bounces += 1u;
     if (!payload.light_sample.PDF.is_valid())
         payload.bsdf_PDF.disable_MIS();

@@ -207,10 +207,11 @@ class OracleScene:
         self.lib.pto_intersect(self.h, n, _p(o), _p(d), _p(tmin), _p(tmax), int(brute), _p(prim), _p(t), _p(uv), _p(occ))
         return prim, t, uv, occ
 
-    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, rows=None, threads=0, accum=None):
+    def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, rows=None, threads=0, accum=None,
+               russian_roulette_start=0):
         from bifrost3d_b200 import capi
         cam = capi.make_camera(*camera)
-        s = capi.Settings(max_bounces, nee_samples, pdf_scale, 0)
+        s = capi.Settings(max_bounces, nee_samples, pdf_scale, russian_roulette_start)
         if accum is None:
             accum = np.zeros((height, width, 4), np.float64)
         counters = np.zeros(2, np.uint64)

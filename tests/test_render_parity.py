@@ -239,3 +239,58 @@ def test_transmissive_albedo_aov(bpt):
     reflection = (g - 0.2) / 0.8  # g = reflection + (1 - reflection) * 0.2
     assert reflection.min() >= 0.0 and reflection.max() < 0.9
     assert np.abs(r - (reflection + (1 - reflection) * 0.9)).max() < 1e-5
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_russian_roulette_extension_matches_oracle_and_is_unbiased(bpt):
+    """Russian roulette is not in the reference; it is an opt-in setting (configs[3] names it). Sample for sample it matches
+    the oracle's restatement, it traces fewer rays, and its expectation is the image rendered without it."""
+    scene = scenes.cornell_box(sphere_quads=(16, 8))
+    gpu, cpu, counters, oc = render_both(bpt, scene, 64, 64, 8, max_bounces=8, russian_roulette_start=2)
+    e = rel_mse(gpu, cpu)
+    print(f"relMSE {e:.3e}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert e <= REL_MSE_BOUND
+    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.003 * int(oc[0])
+    bpt.counters(reset=True)
+    bpt.render(scene["camera"], 64, 64, 0, 256, reset=True, max_bounces=8, russian_roulette_start=2)
+    with_rr, rays_rr = bpt.resolve_float4(), bpt.counters()["extend_rays"]
+    bpt.counters(reset=True)
+    bpt.render(scene["camera"], 64, 64, 0, 256, reset=True, max_bounces=8)
+    without, rays = bpt.resolve_float4(), bpt.counters()["extend_rays"]
+    assert rays_rr < 0.8 * rays
+    assert abs(with_rr[..., :3].mean() / without[..., :3].mean() - 1.0) < 0.01  # same expectation
+    assert rel_mse(with_rr, without) < 0.05
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_converged_image_within_monte_carlo_confidence_intervals(bpt):
+    """a converged GPU render (2048 spp, sample indices 0..) against a CPU render that uses DIFFERENT sample
+    indices (1024 spp from index 2^17 on): >= 99.9 % of the per-pixel means lie within 4 sigma of the CPU estimate, whose
+    standard error comes from its 32 batches of 32 samples. The scene is kept light-tailed (rough spheres, a large light): with
+    the near-mirror sphere and the 5 cm light the batch means are far from normal and CPU against CPU already fails this
+    statistic (98.5 %), which says nothing about the renderer."""
+    scene = scenes.cornell_box(sphere_quads=(16, 8))
+    mats = scene["materials"].copy()
+    mats[4]["roughness"] = 1.0; mats[5]["roughness"] = 1.0
+    scene["materials"] = mats
+    scene["lights"]["data"][0, 6] = 0.25
+    w = h = 48
+    scenes.upload(bpt, scene)
+    bpt.render(scene["camera"], w, h, 0, 2048, reset=True)
+    gpu = bpt.resolve_float4()[..., :3].astype(np.float64)
+    sc = oracle_lib.OracleScene(scene)
+    batches = []
+    for b in range(32):
+        accum, _ = sc.render(scene["camera"], w, h, (1 << 17) + 32 * b, 32)
+        batches.append(accum[..., :3] / accum[..., 3:4])
+    sc.close()
+    batches = np.stack(batches)
+    cpu_mean = batches.mean(axis=0)
+    standard_error = batches.std(axis=0, ddof=1) / np.sqrt(batches.shape[0])
+    sigma = np.sqrt(standard_error ** 2 * (1.0 + 1024.0 / 2048.0)) + 1e-4  # CPU error + the GPU's own (twice the samples)
+    inside = np.abs(gpu - cpu_mean) <= 4.0 * sigma
+    print(f"pixels x channels within 4 sigma: {inside.mean():.4f}; relMSE {rel_mse(gpu, cpu_mean):.3e}")
+    assert inside.mean() >= 0.999
+    assert rel_mse(gpu, cpu_mean) < 1e-3
