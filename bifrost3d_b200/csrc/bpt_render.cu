@@ -34,9 +34,9 @@ struct QueueCounters {
     unsigned int shadow;       // entries in the shadow queue
     unsigned int fetch_extend; // dynamic ray fetch cursors of the two traversal kernels
     unsigned int fetch_shadow;
-    unsigned int surface;      // paths whose ray hit a triangle (shaded by shade_kernel<true>)
-    unsigned int escaped;      // paths whose ray left the scene or hit an analytic light (shade_kernel<false>)
-    unsigned int pad;
+    unsigned int surface;      // paths whose ray hit a Default / Diffuse surface (shade_kernel<true, false>)
+    unsigned int escaped;      // paths whose ray left the scene or hit an analytic light (shade_kernel<false, false>)
+    unsigned int transmissive; // paths whose ray hit a Transmissive surface (shade_kernel<true, true>)
 };
 
 struct Wavefront {
@@ -58,6 +58,7 @@ struct WavefrontView {
     float4 *sh_o, *sh_d, *sh_rad;
     unsigned int *queue_in, *queue_out;
     unsigned int *queue_surface, *queue_escaped;
+    unsigned int queue_capacity;      // entries per queue; the transmissive queue grows down from the end of queue_surface
     QueueCounters* counters;
     unsigned long long* ray_counters; // [0] extend, [1] shadow
 };
@@ -76,6 +77,7 @@ struct SceneView {
     const float* __restrict__ tables;
     const float2* __restrict__ dielectric_tables;
     const float4* __restrict__ nee_offsets;
+    bool split_by_shading_model; // the scene has Transmissive materials: extend keys surface hits by shading model
 };
 
 struct FrameParams {
@@ -143,6 +145,7 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.counters->fetch_shadow = 0;
         w.counters->surface = 0;
         w.counters->escaped = 0;
+        w.counters->transmissive = 0;
     }
 }
 
@@ -152,6 +155,9 @@ struct ExtendSource {
     WavefrontView w;
     const Light* __restrict__ lights;
     int analytic_light_count;
+    // Set when the scene has Transmissive materials: surface hits are then keyed by shading model.
+    const ShadeTriangle* __restrict__ shade;
+    const Material* __restrict__ materials;
     __device__ void load(unsigned int i, Ray& ray, int& skip) const {
         unsigned int pixel = w.queue_in[i];
         float4 o = w.ray_o[pixel], d = w.ray_d[pixel];
@@ -176,11 +182,16 @@ struct ExtendSource {
         }
         unsigned int pixel = w.queue_in[i];
         w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
-        // Sort the paths by the shading they need: surface hits go to the (large) surface shading kernel, escaped rays and
-        // light hits to a small one, so neither runs with lanes masked off for the other's work. Same-address atomics of a
-        // warp are aggregated by the compiler (REDUX + one atomic).
-        if (h.primitive >= 0 && !(h.primitive & LIGHT_HIT_FLAG)) w.queue_surface[atomicAdd(&w.counters->surface, 1u)] = pixel;
-        else w.queue_escaped[atomicAdd(&w.counters->escaped, 1u)] = pixel;
+        // Sort the paths by the shading they need: surface hits go to the (large) surface shading kernels - keyed by the
+        // material's shading model when the scene mixes them - and escaped rays and light hits to a small one, so none runs
+        // with lanes masked off for another's work. Same-address atomics of a warp are aggregated by the compiler
+        // (REDUX + one atomic).
+        if (h.primitive >= 0 && !(h.primitive & LIGHT_HIT_FLAG)) {
+            bool transmissive = shade != nullptr && materials[shade[h.primitive].material_index].shading_model == SHADING_TRANSMISSIVE;
+            if (transmissive) w.queue_surface[w.queue_capacity - 1u - atomicAdd(&w.counters->transmissive, 1u)] = pixel;
+            else w.queue_surface[atomicAdd(&w.counters->surface, 1u)] = pixel;
+        } else
+            w.queue_escaped[atomicAdd(&w.counters->escaped, 1u)] = pixel;
 #ifdef BPT_TRAVERSAL_STATS
         atomicAdd(w.ray_counters + 2, (unsigned long long)tr.stat_nodes);
         atomicAdd(w.ray_counters + 3, (unsigned long long)tr.stat_triangles);
@@ -191,7 +202,7 @@ struct ExtendSource {
 __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
-    ExtendSource source = { w, s.lights, s.analytic_light_count };
+    ExtendSource source = { w, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials };
     traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
@@ -233,6 +244,7 @@ __global__ void advance_kernel(QueueCounters* c) {
     c->fetch_shadow = 0;
     c->surface = 0;
     c->escaped = 0;
+    c->transmissive = 0;
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
@@ -304,8 +316,8 @@ __device__ LightSample sample_single_light(const SceneView& s, const Bsdf& mater
 #ifndef BPT_SHADE_MIN_BLOCKS
 #define BPT_SHADE_MIN_BLOCKS 8
 #endif
-// TRANSMISSIVE: the scene holds ShadingModel::Transmissive materials (transmissive_closest_hit, MonteCarlo.cu:259-268).
-// Scenes without them run the instantiation that only knows DefaultShading.
+// SURFACE, !TRANSMISSIVE: default_closest_hit / diffuse_closest_hit (MonteCarlo.cu:246-257); SURFACE, TRANSMISSIVE:
+// transmissive_closest_hit (:259-268), launched only for scenes that hold such materials; !SURFACE: miss and light hits.
 template <bool SURFACE, bool TRANSMISSIVE>
 __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kernel(WavefrontView w, SceneView s, FrameParams f) {
     __shared__ __align__(16) float s_tables[SURFACE ? 3 * TABLE_FLOATS : 4];
@@ -315,8 +327,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     }
     const ShadingTables tables = { s_tables, s_tables + TABLE_FLOATS, s_tables + 2 * TABLE_FLOATS };
 
-    const unsigned int count = SURFACE ? w.counters->surface : w.counters->escaped;
-    const unsigned int* __restrict__ queue = SURFACE ? w.queue_surface : w.queue_escaped;
+    const unsigned int count = SURFACE ? (TRANSMISSIVE ? w.counters->transmissive : w.counters->surface) : w.counters->escaped;
+    const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count) : w.queue_surface) : w.queue_escaped;
     const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool valid = i < count;
@@ -428,18 +440,10 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                     // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
                     Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
                     const auto material = [&]() {
-                        if constexpr (TRANSMISSIVE) {
-                            SurfaceBsdf bsdf;
-                            bsdf.transmissive = material_parameter.shading_model == SHADING_TRANSMISSIVE;
-                            if (bsdf.transmissive)
-                                bsdf.transmission = TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter,
-                                                                                            tint_and_roughness_scale, cos_theta, max_pdf_hint);
-                            else
-                                bsdf.standard = material_parameter.shading_model == SHADING_DIFFUSE
-                                    ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
-                                    : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
-                            return bsdf;
-                        } else
+                        if constexpr (TRANSMISSIVE)
+                            return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
+                                                                           cos_theta, max_pdf_hint);
+                        else
                             return material_parameter.shading_model == SHADING_DIFFUSE
                                 ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
                                 : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
@@ -663,12 +667,14 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     }
     s.tables = ctx->tables.ptr;
     s.dielectric_tables = ctx->dielectric_tables.ptr;
+    s.split_by_shading_model = ctx->has_transmissive_materials;
     s.nee_offsets = ctx->nee_offsets.ptr;
 
     WavefrontView w = {};
     w.ray_o = wf->ray_o.ptr; w.ray_d = wf->ray_d.ptr; w.thr = wf->thr.ptr; w.rad = wf->rad.ptr; w.hit = wf->hit.ptr;
     w.sh_o = wf->sh_o.ptr; w.sh_d = wf->sh_d.ptr; w.sh_rad = wf->sh_rad.ptr;
     w.queue_surface = wf->queue_surface.ptr; w.queue_escaped = wf->queue_escaped.ptr;
+    w.queue_capacity = (unsigned int)pixels;
     w.counters = wf->counters.ptr;
     w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
 
@@ -701,10 +707,11 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
                 extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
                 shade_kernel<false, false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                if (ctx->has_transmissive_materials)
+                shade_kernel<true, false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                if (ctx->has_transmissive_materials) {
                     shade_kernel<true, true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                else
-                    shade_kernel<true, false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                    ctx->counters.kernel_launches++;
+                }
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
                 shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);

@@ -1062,18 +1062,4 @@ struct TransmissiveShading {
     }
 };
 
-// One surface BSDF of any shading model (Material::ShadingModel, Types.h:360-364): the integrator's `material`.
-struct SurfaceBsdf {
-    bool transmissive;
-    union {
-        DefaultShading standard;        // Default and Diffuse
-        TransmissiveShading transmission;
-    };
-    BPT_D SurfaceBsdf() {}
-    BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
-        return transmissive ? transmission.evaluate_with_pdf(wo, wi) : standard.evaluate_with_pdf(wo, wi);
-    }
-    BPT_D BsdfSample sample(float3 wo, float3 u) const { return transmissive ? transmission.sample(wo, u) : standard.sample(wo, u); }
-};
-
 } // namespace bpt
