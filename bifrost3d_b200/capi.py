@@ -66,9 +66,22 @@ LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
-           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
+           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
+
+
+class TonemapSettings(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("exposure", C.c_float), ("black_clip", C.c_float), ("toe", C.c_float), ("slope", C.c_float),
+                ("shoulder", C.c_float), ("white_clip", C.c_float), ("reserved", C.c_int32)]
+
+
+TONEMAP = {"linear": 0, "filmic": 1, "agx": 2, "khronos_neutral": 3}
+FILMIC_ACES = (0.0, 0.53, 0.91, 0.23, 0.035)  # TonemappingSettings::ACES(): black_clip, toe, slope, shoulder, white_clip
+
+
+def tonemap_settings(mode="filmic", exposure=1.0, filmic=FILMIC_ACES):
+    return TonemapSettings(TONEMAP[mode] if isinstance(mode, str) else int(mode), exposure, *filmic, 0)
 
 
 class TextureDesc(C.Structure):
@@ -126,6 +139,8 @@ def load_library():
     lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
     lib.bpt_resolve_float4.argtypes = [vp, vp]
+    lib.bpt_resolve_tonemapped.argtypes = [vp, C.POINTER(TonemapSettings), vp, i32]
+    lib.bpt_tonemap_colors.argtypes = [vp, C.POINTER(TonemapSettings), i64, vp, vp]
     lib.bpt_synchronize.argtypes = [vp]
     lib.bpt_set_profiling.argtypes = [vp, i32]
     lib.bpt_get_counters.argtypes = [vp, C.POINTER(Counters), i32]
@@ -291,6 +306,21 @@ class Bpt:
         w, h = self._size
         out = np.empty((h, w, 4), np.float32)
         self._check(self.lib.bpt_resolve_float4(self.h, _ptr(out)))
+        return out
+
+    def resolve_tonemapped(self, mode="filmic", exposure=1.0, filmic=FILMIC_ACES, rgba8=False):
+        """Mean radiance -> exposure -> tonemapping operator: linear float4, or sRGB-encoded RGBA8 when rgba8 is set."""
+        w, h = self._size
+        s = tonemap_settings(mode, exposure, filmic)
+        out = np.empty((h, w, 4), np.uint8 if rgba8 else np.float32)
+        self._check(self.lib.bpt_resolve_tonemapped(self.h, C.byref(s), _ptr(out), 1 if rgba8 else 0))
+        return out
+
+    def tonemap_colors(self, rgb, mode="filmic", exposure=1.0, filmic=FILMIC_ACES):
+        rgb = _f32(rgb).reshape(-1, 3)
+        out = np.empty_like(rgb)
+        s = tonemap_settings(mode, exposure, filmic)
+        self._check(self.lib.bpt_tonemap_colors(self.h, C.byref(s), rgb.shape[0], _ptr(rgb), _ptr(out)))
         return out
 
     def resolve_half4(self):

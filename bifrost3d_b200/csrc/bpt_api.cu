@@ -661,6 +661,12 @@ int bpt_render_aov(bpt_ctx* c, const bpt_camera* camera, int aov_kind, int width
 
 void* bpt_accumulation_device_ptr(bpt_ctx* c) { return as_context(c)->accumulation.ptr; }
 int bpt_resolve_half4(bpt_ctx* c, uint16_t* out, int on_device) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_half4(ctx, out, on_device); }
+int bpt_resolve_tonemapped(bpt_ctx* c, const bpt_tonemap_settings* settings, void* out, int output_format) {
+    Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_tonemapped(ctx, settings, out, output_format);
+}
+int bpt_tonemap_colors(bpt_ctx* c, const bpt_tonemap_settings* settings, int64_t n, const float* rgb_in, float* rgb_out) {
+    Context* ctx = as_context(c); cudaSetDevice(ctx->device); return tonemap_batch(ctx, settings, n, rgb_in, rgb_out);
+}
 int bpt_resolve_float4(bpt_ctx* c, float* out) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_float4(ctx, out); }
 
 int bpt_get_counters(bpt_ctx* c, bpt_counters* out, int reset) {

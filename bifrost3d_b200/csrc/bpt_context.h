@@ -173,6 +173,8 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device);
 int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int height, uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
 int resolve_float4(Context* ctx, float* out);
 void release_wavefront(Context* ctx);
+int tonemap_batch(Context* ctx, const bpt_tonemap_settings* settings, int64_t n, const float* rgb_in, float* rgb_out); // bpt_tonemap.cu
+int resolve_tonemapped(Context* ctx, const bpt_tonemap_settings* settings, void* out, int output_format);
 int sync_texture_table(Context* ctx); // uploads the texture id -> cudaTextureObject_t table when it changed (bpt_api.cu)
 
 } // namespace bpt

@@ -202,6 +202,23 @@ void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
 int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
 /* mean as float4 to a HOST buffer of width*height*4 floats. */
 int bpt_resolve_float4(bpt_ctx* ctx, float* out);
+/* Tonemapped resolve. Operators and parameters are the core's camera effects (core/Bifrost/Bifrost/Math/CameraEffects.h:
+ * TonemappingMode :18, TonemappingSettings :21-32 with ACES() = {0, 0.53, 0.91, 0.23, 0.035}, filmic :161-224, agx :236-265,
+ * khronos_neutral_tone_mapping :272-291); `exposure` is a linear scale applied first (ExposureMode::Fixed). The filmic
+ * parameters are only read by BPT_TONEMAP_FILMIC. */
+enum { BPT_TONEMAP_LINEAR = 0, BPT_TONEMAP_FILMIC = 1, BPT_TONEMAP_AGX = 2, BPT_TONEMAP_KHRONOS_NEUTRAL = 3 };
+enum { BPT_OUTPUT_FLOAT4 = 0, BPT_OUTPUT_SRGB_RGBA8 = 1 };
+typedef struct bpt_tonemap_settings {
+    int32_t mode;
+    float exposure;
+    float black_clip, toe, slope, shoulder, white_clip;
+    int32_t reserved;
+} bpt_tonemap_settings;
+/* mean radiance -> exposure -> operator, to a HOST buffer: width*height float4 (linear, alpha 1) or width*height RGBA8 with
+ * the sRGB transfer function applied (Color.h:372-377). */
+int bpt_resolve_tonemapped(bpt_ctx* ctx, const bpt_tonemap_settings* settings, void* out, int output_format);
+/* the operator alone for n colours (rgb_in, rgb_out: 3n floats): unit entry point for the parity test */
+int bpt_tonemap_colors(bpt_ctx* ctx, const bpt_tonemap_settings* settings, int64_t n, const float* rgb_in, float* rgb_out);
 int bpt_synchronize(bpt_ctx* ctx);
 /* enabled != 0: bpt_render brackets its stage kernels with CUDA events on the context's stream and accumulates their
  * durations into bpt_counters.{extend,shade,shadow}_ms (used by bench.py for the roofline figures). */

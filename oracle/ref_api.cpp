@@ -42,6 +42,7 @@
 #include <Bifrost/Assets/Image.h>
 #include <Bifrost/Assets/InfiniteAreaLight.h>
 #include <Bifrost/Assets/Texture.h>
+#include <Bifrost/Math/CameraEffects.h>
 #include <Bifrost/Math/OctahedralNormal.h>
 #include <Bifrost/Math/RNG.h>
 
@@ -123,6 +124,28 @@ void ref_sample_dielectric_rho(int64_t n, const float* cos_theta, const float* r
         auto rho = Bifrost::Assets::Shading::Rho::sample_dielectric_GGX(cos_theta[i], roughness[i], ior_i_over_o[i]);
         out_total_reflected[2 * i] = rho.total_rho; out_total_reflected[2 * i + 1] = rho.reflected_rho;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tonemapping operators of the core (Math/CameraEffects.h:161-291). mode: TonemappingMode (Linear, Filmic, AgX, KhronosNeutral);
+// filmic_settings: {black_clip, toe, slope, shoulder, white_clip}.
+// ---------------------------------------------------------------------------------------------
+void ref_tonemap(int mode, float exposure, const float* filmic_settings, int64_t n, const float* rgb_in, float* rgb_out) {
+    using namespace Bifrost::Math;
+    for (int64_t i = 0; i < n; ++i) {
+        RGB c = RGB(rgb_in[3 * i], rgb_in[3 * i + 1], rgb_in[3 * i + 2]) * exposure;
+        switch (mode) {
+        case 1: c = CameraEffects::filmic(c, filmic_settings[2], filmic_settings[1], filmic_settings[3], filmic_settings[0], filmic_settings[4]); break;
+        case 2: c = CameraEffects::agx(c); break;
+        case 3: c = CameraEffects::khronos_neutral_tone_mapping(c); break;
+        default: break;
+        }
+        rgb_out[3 * i] = c.r; rgb_out[3 * i + 1] = c.g; rgb_out[3 * i + 2] = c.b;
+    }
+}
+
+void ref_linear_to_srgb(int64_t n, const float* in, float* out) {
+    for (int64_t i = 0; i < n; ++i) out[i] = Bifrost::Math::linear_to_sRGB(in[i]);
 }
 
 // ---------------------------------------------------------------------------------------------

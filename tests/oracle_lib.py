@@ -33,6 +33,8 @@ class Ref:
         lib.ref_get_tables.argtypes = [vp, vp, vp, vp]; lib.ref_get_tables.restype = None
         lib.ref_get_dielectric_tables.argtypes = [vp, vp, vp]; lib.ref_get_dielectric_tables.restype = None
         lib.ref_sample_dielectric_rho.argtypes = [i64, vp, vp, vp, vp]; lib.ref_sample_dielectric_rho.restype = None
+        lib.ref_tonemap.argtypes = [i32, C.c_float, vp, i64, vp, vp]; lib.ref_tonemap.restype = None
+        lib.ref_linear_to_srgb.argtypes = [i64, vp, vp]; lib.ref_linear_to_srgb.restype = None
         lib.ref_pcg2d.argtypes = [i64, vp, vp, vp]; lib.ref_pcg2d.restype = None
         lib.ref_sobol_sample4.argtypes = [i64, vp, vp, vp, vp, vp]; lib.ref_sobol_sample4.restype = None
         lib.ref_reverse_halton4.argtypes = [i32, vp]; lib.ref_reverse_halton4.restype = None
@@ -62,6 +64,16 @@ class Ref:
         dims = np.zeros(3, np.int32)
         self.lib.ref_get_dielectric_tables(_p(a), _p(b), _p(dims))
         return a, b, dims
+
+    def tonemap(self, mode, rgb, exposure=1.0, filmic=(0.0, 0.53, 0.91, 0.23, 0.035)):
+        rgb = _f32(rgb).reshape(-1, 3); out = np.empty_like(rgb); s = _f32(filmic)
+        self.lib.ref_tonemap(int(mode), float(exposure), _p(s), rgb.shape[0], _p(rgb), _p(out))
+        return out
+
+    def linear_to_srgb(self, values):
+        v = _f32(values).reshape(-1); out = np.empty_like(v)
+        self.lib.ref_linear_to_srgb(v.shape[0], _p(v), _p(out))
+        return out
 
     def sobol_sample4(self, accumulation, pixel_hash, dimension):
         a, h, d = (np.ascontiguousarray(x, dtype=np.uint32).reshape(-1) for x in (accumulation, pixel_hash, dimension))
