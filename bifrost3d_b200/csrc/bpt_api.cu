@@ -376,6 +376,7 @@ void bpt_destroy(bpt_ctx* c) {
     release_wavefront(ctx);
     ctx->tables.release(); ctx->dielectric_tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
+    for (auto& kv : ctx->meshes) kv.second.release();
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release();
     ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
@@ -533,18 +534,35 @@ int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primit
     for (int64_t i = 0; i < 3ll * primitive_count; ++i)
         if (indices[i] >= (uint32_t)vertex_count)
             return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_mesh: vertex index out of range");
-    HostMesh& m = ctx->meshes[mesh_id];
+    cudaSetDevice(ctx->device);
+    DeviceMesh& m = ctx->meshes[mesh_id];
     m.primitive_count = primitive_count; m.vertex_count = vertex_count;
-    m.indices.assign(indices, indices + 3ll * primitive_count);
-    m.positions.assign(positions, positions + 3ll * vertex_count);
-    m.normals.clear(); m.texcoords.clear(); m.tints.clear();
+    BPT_CUDA_CHECK(ctx, upload(ctx, m.indices, indices, 3ull * primitive_count));
+    BPT_CUDA_CHECK(ctx, upload(ctx, m.positions, positions, 3ull * vertex_count));
+    m.normals.release(); m.texcoords.release(); m.tints.release();
+    std::vector<int16_t> encoded_normals;
     if (normals) {
-        m.normals.resize(2ll * vertex_count);
-        for (int v = 0; v < vertex_count; ++v) oct_encode_precise(normals + 3ll * v, m.normals.data() + 2ll * v);
+        encoded_normals.resize(2ull * vertex_count);
+        for (int v = 0; v < vertex_count; ++v) oct_encode_precise(normals + 3ll * v, encoded_normals.data() + 2ll * v);
+        BPT_CUDA_CHECK(ctx, upload(ctx, m.normals, encoded_normals.data(), encoded_normals.size()));
     }
-    if (texcoords) m.texcoords.assign(texcoords, texcoords + 2ll * vertex_count);
-    if (tint_roughness) m.tints.assign(tint_roughness, tint_roughness + 4ll * vertex_count);
+    if (texcoords) BPT_CUDA_CHECK(ctx, upload(ctx, m.texcoords, texcoords, 2ull * vertex_count));
+    if (tint_roughness) BPT_CUDA_CHECK(ctx, upload(ctx, m.tints, tint_roughness, 4ull * vertex_count));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's arrays (and encoded_normals) may go away
     ctx->accel.valid = false;
+    return BPT_OK;
+}
+
+int bpt_remove_mesh(bpt_ctx* c, int mesh_id) {
+    Context* ctx = as_context(c);
+    auto it = ctx->meshes.find(mesh_id);
+    if (it == ctx->meshes.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_remove_mesh: unknown mesh id");
+    for (const bpt_instance& inst : ctx->instances)
+        if (inst.mesh_id == mesh_id) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_remove_mesh: an instance still references the mesh");
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    it->second.release();
+    ctx->meshes.erase(it);
     return BPT_OK;
 }
 
@@ -585,7 +603,11 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     ctx->has_transmissive_materials = any_transmissive;
     ctx->has_textured_materials = any_textured;
     ctx->material_version++;
-    ctx->accel.valid = false; // cull / coverage flags are baked into the triangle records
+    // Materials are read at shading time: the acceleration structure stays valid, unless the scene now needs the
+    // per-primitive texcoords that an untextured build left out.
+    if (any_textured && !ctx->accel.has_uv) ctx->accel.valid = false;
+    for (const bpt_instance& inst : ctx->instances)
+        if (inst.material_id >= count) ctx->accel.valid = false; // bpt_build_accel will report the dangling material id
     return BPT_OK;
 }
 

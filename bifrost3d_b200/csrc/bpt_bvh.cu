@@ -24,10 +24,14 @@ constexpr int LEAF_MAX = BPT_LEAF_MAX;
 struct InstanceRecord {
     int prim_offset;   // first global primitive index
     int prim_count;
-    int index_offset;  // first index triple in the concatenated index buffer
-    int vertex_offset; // first vertex in the concatenated vertex buffers
     int material;
     uint32_t flags;    // bit0: has normals, bit1: has tints, bit2: has texcoords
+    // the instance's mesh, resident on the device since bpt_upload_mesh
+    const uint32_t* indices;
+    const float* positions;
+    const int16_t* normals;
+    const uint8_t* tints;
+    const float2* texcoords;
     float m[12];       // object -> world, row-major 3x4
 };
 
@@ -51,8 +55,6 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 
 // One thread per global primitive: world-space vertices, shading record, centroid bounds.
 __global__ void flatten_kernel(int64_t prim_total, int instance_count, const InstanceRecord* __restrict__ instances,
-                               const uint32_t* __restrict__ indices, const float* __restrict__ positions,
-                               const int16_t* __restrict__ normals, const uint8_t* __restrict__ tints, const float2* __restrict__ texcoords,
                                float4* __restrict__ world_vertices, ShadeTriangle* __restrict__ shade, float2* __restrict__ shade_uv,
                                float* scene_bounds /*[6]*/) {
     float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
@@ -65,8 +67,12 @@ __global__ void flatten_kernel(int64_t prim_total, int instance_count, const Ins
         }
         const InstanceRecord& inst = instances[a];
         int lp = int(gp - inst.prim_offset);
-        const uint32_t* tri = indices + 3ll * (inst.index_offset + lp);
-        uint32_t i0 = tri[0] + inst.vertex_offset, i1 = tri[1] + inst.vertex_offset, i2 = tri[2] + inst.vertex_offset;
+        const uint32_t* tri = inst.indices + 3ll * lp;
+        const uint32_t i0 = tri[0], i1 = tri[1], i2 = tri[2];
+        const float* __restrict__ positions = inst.positions;
+        const int16_t* __restrict__ normals = inst.normals;
+        const uint8_t* __restrict__ tints = inst.tints;
+        const float2* __restrict__ texcoords = inst.texcoords;
         float3 p0 = transform_point(inst.m, f3(positions[3ll * i0], positions[3ll * i0 + 1], positions[3ll * i0 + 2]));
         float3 p1 = transform_point(inst.m, f3(positions[3ll * i1], positions[3ll * i1 + 1], positions[3ll * i1 + 2]));
         float3 p2 = transform_point(inst.m, f3(positions[3ll * i2], positions[3ll * i2 + 1], positions[3ll * i2 + 2]));
@@ -189,7 +195,7 @@ __device__ __forceinline__ Aabb load_box_cg(const Aabb* p) {
 // Writes the Morton-ordered triangle array and the leaf boxes, then climbs: the second thread to reach an
 // internal node merges its children's boxes (classic atomic-counter refit).
 __global__ void fit_kernel(int n, const uint32_t* __restrict__ sorted_prims, const float4* __restrict__ world_vertices,
-                           const ShadeTriangle* __restrict__ shade, const uint32_t* __restrict__ material_trace_flags,
+                           const ShadeTriangle* __restrict__ shade,
                            TraceTriangle* __restrict__ triangles, Aabb* __restrict__ leaf_boxes, Aabb* __restrict__ node_boxes,
                            const TreeNode* __restrict__ tree, const int* __restrict__ parent_of_internal, const int* __restrict__ parent_of_leaf,
                            int* __restrict__ arrival) {
@@ -201,7 +207,7 @@ __global__ void fit_kernel(int n, const uint32_t* __restrict__ sorted_prims, con
     TraceTriangle t;
     t.v0 = make_float4(v0.x, v0.y, v0.z, __int_as_float((int)gp));
     t.v1 = make_float4(v1.x, v1.y, v1.z, __int_as_float(material));
-    t.v2 = make_float4(v2.x, v2.y, v2.z, __uint_as_float(material_trace_flags[material]));
+    t.v2 = make_float4(v2.x, v2.y, v2.z, 0.0f);
     triangles[p] = t;
     Aabb box;
     box.lo = min3(min3(f3(v0), f3(v1)), f3(v2));
@@ -299,58 +305,29 @@ __global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel,
 
 } // namespace
 
-// Per-material flags baked into the triangle records (v2.w). bit0: backface culled (not thin walled, not
-// transmissive: MonteCarlo.cu:146-150), bit1: fully opaque (coverage >= 1, not cutout).
-static uint32_t material_trace_flags(const Material& m) {
-    uint32_t f = 0;
-    if (!material_is_thin_walled(m) && !material_is_transmissive(m)) f |= 1u;
-    if (material_coverage(m) >= 1.0f) f |= 2u;
-    return f;
-}
-
 int build_accel(Context* ctx) {
     Accel& A = ctx->accel;
     A.valid = false;
     cudaStream_t st = ctx->stream;
 
-    // ---- concatenate the meshes that are referenced and lay out the instances ----
-    std::map<int, int> mesh_slot; // mesh id -> record index
-    struct MeshSlot { int index_offset, vertex_offset; };
-    std::vector<MeshSlot> slots;
-    std::vector<uint32_t> h_indices; std::vector<float> h_positions; std::vector<int16_t> h_normals; std::vector<uint8_t> h_tints;
-    std::vector<float> h_texcoords; // 2 per vertex; only filled when a textured material could read them
-    bool any_texcoords = false;
-    if (ctx->has_textured_materials)
-        for (const bpt_instance& inst : ctx->instances) any_texcoords |= !ctx->meshes[inst.mesh_id].texcoords.empty();
+    // ---- lay out the instances over the device-resident meshes ----
     std::vector<InstanceRecord> records;
     std::vector<float> h_normal_matrices; // 9 floats per record, row-major
+    bool any_texcoords = false;
+    if (ctx->has_textured_materials)
+        for (const bpt_instance& inst : ctx->instances) any_texcoords |= ctx->meshes[inst.mesh_id].texcoords.size != 0;
     int64_t prim_total = 0;
     for (const bpt_instance& inst : ctx->instances) {
-        const HostMesh& mesh = ctx->meshes[inst.mesh_id];
-        auto it = mesh_slot.find(inst.mesh_id);
-        if (it == mesh_slot.end()) {
-            MeshSlot s = { int(h_indices.size() / 3), int(h_positions.size() / 3) };
-            h_indices.insert(h_indices.end(), mesh.indices.begin(), mesh.indices.end());
-            h_positions.insert(h_positions.end(), mesh.positions.begin(), mesh.positions.end());
-            h_normals.resize(2 * (h_positions.size() / 3), 0);
-            if (!mesh.normals.empty()) std::copy(mesh.normals.begin(), mesh.normals.end(), h_normals.begin() + 2ll * s.vertex_offset);
-            h_tints.resize(4 * (h_positions.size() / 3), 255);
-            if (!mesh.tints.empty()) std::copy(mesh.tints.begin(), mesh.tints.end(), h_tints.begin() + 4ll * s.vertex_offset);
-            if (any_texcoords) {
-                h_texcoords.resize(2 * (h_positions.size() / 3), 0.0f);
-                if (!mesh.texcoords.empty()) std::copy(mesh.texcoords.begin(), mesh.texcoords.end(), h_texcoords.begin() + 2ll * s.vertex_offset);
-            }
-            slots.push_back(s);
-            it = mesh_slot.emplace(inst.mesh_id, int(slots.size()) - 1).first;
-        }
+        const DeviceMesh& mesh = ctx->meshes[inst.mesh_id];
         if (inst.material_id < 0 || inst.material_id >= (int)ctx->host_materials.size())
             return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_build_accel: instance references a material that was not uploaded");
         if (mesh.primitive_count == 0) continue;
         InstanceRecord r = {};
         r.prim_offset = int(prim_total); r.prim_count = mesh.primitive_count;
-        r.index_offset = slots[it->second].index_offset; r.vertex_offset = slots[it->second].vertex_offset;
         r.material = inst.material_id;
-        r.flags = (mesh.normals.empty() ? 0u : 1u) | (mesh.tints.empty() ? 0u : 2u) | ((any_texcoords && !mesh.texcoords.empty()) ? 4u : 0u);
+        r.flags = (mesh.normals.size ? 1u : 0u) | (mesh.tints.size ? 2u : 0u) | ((any_texcoords && mesh.texcoords.size) ? 4u : 0u);
+        r.indices = mesh.indices.ptr; r.positions = mesh.positions.ptr; r.normals = mesh.normals.ptr; r.tints = mesh.tints.ptr;
+        r.texcoords = reinterpret_cast<const float2*>(mesh.texcoords.ptr);
         memcpy(r.m, inst.to_world, sizeof(r.m));
         records.push_back(r);
         { // normal matrix = inverse transpose of the upper 3x3 (rtTransformNormal, MonteCarlo.cu:147,176), in double
@@ -368,15 +345,12 @@ int build_accel(Context* ctx) {
     }
     const int n = int(prim_total);
 
-    std::vector<uint32_t> h_flags(ctx->host_materials.size());
-    for (size_t i = 0; i < h_flags.size(); ++i) h_flags[i] = material_trace_flags(ctx->host_materials[i]);
 
-    DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<uint32_t> d_indices; DeviceBuffer<float> d_positions;
-    DeviceBuffer<int16_t> d_normals; DeviceBuffer<uint8_t> d_tints; DeviceBuffer<float> d_texcoords; DeviceBuffer<uint32_t> d_flags; DeviceBuffer<float> d_bounds;
+    DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<float> d_bounds;
     DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<unsigned char> d_temp;
     DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
     auto release_all = [&]() {
-        d_records.release(); d_indices.release(); d_positions.release(); d_normals.release(); d_tints.release(); d_texcoords.release(); d_flags.release(); d_bounds.release();
+        d_records.release(); d_bounds.release();
         d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
         d_tree.release(); d_parent_internal.release(); d_parent_leaf.release(); d_arrival.release(); d_leaf_boxes.release(); d_node_boxes.release();
     };
@@ -387,8 +361,7 @@ int build_accel(Context* ctx) {
         if (e != cudaSuccess || host.empty()) return e;
         return cudaMemcpyAsync(buf.ptr, host.data(), host.size() * sizeof(host[0]), cudaMemcpyHostToDevice, st);
     };
-    BUILD_CHECK(up(d_records, records)); BUILD_CHECK(up(d_indices, h_indices)); BUILD_CHECK(up(d_positions, h_positions));
-    BUILD_CHECK(up(d_normals, h_normals)); BUILD_CHECK(up(d_tints, h_tints)); BUILD_CHECK(up(d_texcoords, h_texcoords)); BUILD_CHECK(up(d_flags, h_flags));
+    BUILD_CHECK(up(d_records, records));
     BUILD_CHECK(up(A.normal_matrices, h_normal_matrices));
     float init_bounds[6] = { FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX };
     BUILD_CHECK(d_bounds.resize(6));
@@ -408,8 +381,7 @@ int build_accel(Context* ctx) {
     auto full_grid = [&](int64_t count) { return (int)((count + block - 1) / block); };
 
     if (n > 0) {
-        flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, d_indices.ptr, d_positions.ptr, d_normals.ptr, d_tints.ptr,
-                                                  reinterpret_cast<const float2*>(d_texcoords.ptr), A.world_vertices.ptr, A.shade.ptr,
+        flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, A.world_vertices.ptr, A.shade.ptr,
                                                   A.has_uv ? A.shade_uv.ptr : nullptr, d_bounds.ptr);
         ctx->counters.kernel_launches++;
         BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
@@ -431,7 +403,7 @@ int build_accel(Context* ctx) {
             hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, keys.Current(), d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
             ctx->counters.kernel_launches++;
         }
-        fit_kernel<<<full_grid(n), block, 0, st>>>(n, vals.Current(), A.world_vertices.ptr, A.shade.ptr, d_flags.ptr, A.triangles.ptr,
+        fit_kernel<<<full_grid(n), block, 0, st>>>(n, vals.Current(), A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr,
                                                    d_leaf_boxes.ptr, d_node_boxes.ptr, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr, d_arrival.ptr);
         ctx->counters.kernel_launches++;
         if (n > 1) {

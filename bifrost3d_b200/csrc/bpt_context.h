@@ -32,14 +32,17 @@ struct DeviceBuffer {
     size_t bytes() const { return size * sizeof(T); }
 };
 
-struct HostMesh {
-    std::vector<uint32_t> indices;   // 3 per primitive
-    std::vector<float> positions;    // 3 per vertex
-    std::vector<int16_t> normals;    // 2 per vertex (octahedral), empty if the mesh has none
-    std::vector<float> texcoords;    // 2 per vertex or empty
-    std::vector<uint8_t> tints;      // 4 per vertex or empty
+// A mesh lives on the device from bpt_upload_mesh on (load_mesh, Renderer.cpp:92-136): rebuilding the acceleration
+// structure after a transform change re-flattens the resident meshes without touching the host again.
+struct DeviceMesh {
+    DeviceBuffer<uint32_t> indices;  // 3 per primitive
+    DeviceBuffer<float> positions;   // 3 per vertex
+    DeviceBuffer<int16_t> normals;   // 2 per vertex (octahedral); empty if the mesh has none
+    DeviceBuffer<float> texcoords;   // 2 per vertex or empty
+    DeviceBuffer<uint8_t> tints;     // 4 per vertex or empty
     int primitive_count = 0;
     int vertex_count = 0;
+    void release() { indices.release(); positions.release(); normals.release(); texcoords.release(); tints.release(); primitive_count = vertex_count = 0; }
 };
 
 // BVH node, 64 bytes, two children per node: the child AABBs are stored in the parent so one 64 byte (4 x 128-bit)
@@ -55,7 +58,7 @@ struct __align__(16) BvhNode {
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
 // World-space triangle in traversal order: three float4 loads. The w lanes carry the global primitive
-// index (bits of v0.w), the material index (v1.w) and the cull/coverage flags (v2.w).
+// index (bits of v0.w) and the material index (v1.w); v2.w is unused.
 struct __align__(16) TraceTriangle {
     float4 v0, v1, v2;
 };
@@ -108,7 +111,7 @@ struct Context {
     bool has_transmissive_materials = false;
     DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
 
-    std::map<int, HostMesh> meshes;
+    std::map<int, DeviceMesh> meshes;
     std::vector<bpt_instance> instances;
     DeviceBuffer<Material> materials;
     std::map<int, DeviceTexture> textures;                  // by texture id (>= 1)

@@ -2,8 +2,9 @@
 // C ABI (include/bpt_c_api.h). Mirrors the behaviour of the reference's
 // extensions/OptiXRenderer/OptiXRenderer/Renderer.cpp (initialize :1365-1378, handle_updates :578-1205,
 // prepare_camera_state + render :1207-1265, setters :1389-1474) but flattens the scene into device arrays instead of an
-// OptiX scene graph. Scene synchronisation is non-incremental in this revision: any mesh / model / transform / material /
-// texture change re-uploads the flattened scene and rebuilds the BVH (incremental refit is a "next" row).
+// OptiX scene graph. Scene synchronisation is incremental at the granularity of the C ABI: meshes and textures are uploaded
+// once and stay resident, a material edit uploads the material records only, and a transform or model change re-flattens the
+// resident meshes and rebuilds the BVH on the device (the counterpart of the reference's acceleration refit).
 #include <OptiXRenderer/Renderer.h>
 
 #include <optixu/optixpp_namespace.h>
@@ -217,23 +218,41 @@ struct Renderer::Implementation {
         return (it != uploaded_textures.end() && it->second) ? int(texture_ID.get_index()) : 0;
     }
 
-    void upload_geometry_and_materials() {
-        // load_mesh, Renderer.cpp:92-136: every mesh referenced by a model.
-        std::map<unsigned int, bool> uploaded;
+    // load_mesh, Renderer.cpp:92-136 / mesh updates :621-648: a mesh is uploaded once and stays on the device; only created
+    // (or re-created) meshes travel again. Returns true when something changed.
+    std::map<unsigned int, bool> uploaded_meshes;
+    bool upload_meshes() {
+        bool changed = false;
+        for (MeshID mesh_ID : Meshes::get_iterable()) {
+            if (uploaded_meshes[mesh_ID] && !Meshes::get_changes(mesh_ID).contains(Meshes::Change::Created)) continue;
+            static_assert(sizeof(TintRoughness) == 4, "TintRoughness is uchar4");
+            int status = bpt_upload_mesh(ctx, int(mesh_ID.get_index()), Meshes::get_indices(mesh_ID), int(Meshes::get_primitive_count(mesh_ID)),
+                                         (const float*)Meshes::get_positions(mesh_ID), (const float*)Meshes::get_normals(mesh_ID),
+                                         (const float*)Meshes::get_texcoords(mesh_ID), (const uint8_t*)Meshes::get_tint_and_roughness(mesh_ID),
+                                         int(Meshes::get_vertex_count(mesh_ID)));
+            check(ctx, status, "bpt_upload_mesh");
+            uploaded_meshes[mesh_ID] = status == BPT_OK;
+            changed = true;
+        }
+        return changed;
+    }
+
+    // Meshes destroyed in the core are dropped from the device once no instance references them any more.
+    void remove_destroyed_meshes() {
+        for (MeshID mesh_ID : Meshes::get_changed_meshes())
+            if (Meshes::get_changes(mesh_ID) == Meshes::Change::Destroyed && uploaded_meshes[mesh_ID]) {
+                check(ctx, bpt_remove_mesh(ctx, int(mesh_ID.get_index())), "bpt_remove_mesh");
+                uploaded_meshes[mesh_ID] = false;
+            }
+    }
+
+    // Transform + model, Renderer.cpp:1010-1110: object -> world from the node's global transform. The acceleration
+    // structure is rebuilt on the device from the resident meshes (no mesh traffic).
+    void upload_instances_and_build() {
         std::vector<bpt_instance> instances;
         for (MeshModelID model_ID : MeshModels::get_iterable()) {
             MeshID mesh_ID = MeshModels::get_mesh_ID(model_ID);
-            if (!Meshes::has(mesh_ID)) continue;
-            if (!uploaded[mesh_ID]) {
-                unsigned int vertex_count = Meshes::get_vertex_count(mesh_ID);
-                static_assert(sizeof(TintRoughness) == 4, "TintRoughness is uchar4");
-                check(ctx, bpt_upload_mesh(ctx, int(mesh_ID.get_index()), Meshes::get_indices(mesh_ID), int(Meshes::get_primitive_count(mesh_ID)),
-                                           (const float*)Meshes::get_positions(mesh_ID), (const float*)Meshes::get_normals(mesh_ID),
-                                           (const float*)Meshes::get_texcoords(mesh_ID), (const uint8_t*)Meshes::get_tint_and_roughness(mesh_ID),
-                                           int(vertex_count)), "bpt_upload_mesh");
-                uploaded[mesh_ID] = true;
-            }
-            // Transform + model, Renderer.cpp:1010-1110: object -> world from the node's global transform.
+            if (!Meshes::has(mesh_ID) || !uploaded_meshes[mesh_ID]) continue;
             Matrix3x4f m = to_matrix3x4(SceneNodes::get_global_transform(MeshModels::get_scene_node_ID(model_ID)));
             bpt_instance inst = {};
             inst.mesh_id = int(mesh_ID.get_index());
@@ -241,7 +260,11 @@ struct Renderer::Implementation {
             memcpy(inst.to_world, m.begin(), sizeof(inst.to_world));
             instances.push_back(inst);
         }
+        check(ctx, bpt_set_instances(ctx, instances.data(), int(instances.size())), "bpt_set_instances");
+        check(ctx, bpt_build_accel(ctx), "bpt_build_accel");
+    }
 
+    void upload_materials() {
         // upload_material, Renderer.cpp:753-812; index = MaterialID, the invalid material 0 is uploaded as well (:821).
         std::vector<bpt_material> materials(Materials::capacity());
         for (auto& m : materials) { memset(&m, 0, sizeof(m)); m.coverage = 1.0f; }
@@ -269,8 +292,6 @@ struct Renderer::Implementation {
             d.coverage_texture_id = device_texture_id(host.get_coverage_texture_ID());
         }
         check(ctx, bpt_set_materials(ctx, materials.data(), int(materials.size())), "bpt_set_materials");
-        check(ctx, bpt_set_instances(ctx, instances.data(), int(instances.size())), "bpt_set_instances");
-        check(ctx, bpt_build_accel(ctx), "bpt_build_accel");
     }
 
     // PresampledEnvironmentMap, PresampledEnvironmentMap.cpp:19-101: the latlong radiance map, the per pixel solid angle PDF
@@ -379,17 +400,23 @@ struct Renderer::Implementation {
             }
         }
 
+        // Incremental scene synchronisation (Renderer.cpp:621-1110): textures and meshes travel only when created, a material
+        // edit uploads the 64-byte material records and nothing else, and a transform or model change re-flattens the resident
+        // meshes and rebuilds the BVH on the device.
         bool textures_changed = upload_textures();
-        bool geometry_changed = !scene_uploaded || textures_changed;
-        geometry_changed |= !Meshes::get_changed_meshes().is_empty();
-        geometry_changed |= !MeshModels::get_changed_models().is_empty();
-        geometry_changed |= !Materials::get_changed_materials().is_empty();
+        bool meshes_changed = upload_meshes();
+        bool materials_changed = !scene_uploaded || textures_changed || !Materials::get_changed_materials().is_empty();
+        if (materials_changed) upload_materials();
+        bool instances_changed = !scene_uploaded || meshes_changed || !Meshes::get_changed_meshes().is_empty();
+        instances_changed |= !MeshModels::get_changed_models().is_empty();
         for (SceneNodeID node_ID : SceneNodes::get_changed_nodes())
-            if (SceneNodes::get_changes(node_ID).contains(SceneNodes::Change::Transform)) geometry_changed = true;
-        if (geometry_changed) {
-            upload_geometry_and_materials();
-            should_reset_accumulations = true;
-        }
+            if (SceneNodes::get_changes(node_ID).contains(SceneNodes::Change::Transform)) instances_changed = true;
+        int64_t triangle_count = 0;
+        bool accel_lost = bpt_accel_info(ctx, &triangle_count, nullptr, nullptr) != BPT_OK; // e.g. a first textured material
+        if (instances_changed || accel_lost) upload_instances_and_build();
+        remove_destroyed_meshes();
+        bool geometry_changed = materials_changed || instances_changed || accel_lost;
+        if (geometry_changed) should_reset_accumulations = true;
 
         bool lights_changed = !scene_uploaded || !LightSources::get_changed_lights().is_empty() || geometry_changed;
         if (lights_changed) {

@@ -162,9 +162,15 @@ int bpt_texture_sample(bpt_ctx* ctx, int texture_id, int64_t n, const float* uv,
 int bpt_upload_mesh(bpt_ctx* ctx, int mesh_id, const uint32_t* indices, int primitive_count,
                     const float* positions, const float* normals, const float* texcoords,
                     const uint8_t* tint_roughness, int vertex_count);
-/* Renderer.cpp:1043-1110 (mesh models) + :1010-1041 (transforms). Replaces all instances. */
+/* Meshes::Change::Destroyed, Renderer.cpp:628-640. Fails while an instance still references the mesh. */
+int bpt_remove_mesh(bpt_ctx* ctx, int mesh_id);
+/* Renderer.cpp:1043-1110 (mesh models) + :1010-1041 (transforms). Replaces all instances. Meshes stay resident on the
+ * device, so a transform-only change costs bpt_set_instances + bpt_build_accel (device-side re-flatten and rebuild:
+ * the counterpart of the reference's acceleration refit, Renderer.cpp:470-477) and no mesh traffic. */
 int bpt_set_instances(bpt_ctx* ctx, const bpt_instance* instances, int count);
-/* upload_material, Renderer.cpp:753-850. Index = MaterialID; index 0 is the invalid material. */
+/* upload_material, Renderer.cpp:753-850. Index = MaterialID; index 0 is the invalid material. Materials are read at
+ * shading time: changing them does not invalidate the acceleration structure (except when a first textured material makes
+ * the per-primitive texcoords necessary). */
 int bpt_set_materials(bpt_ctx* ctx, const bpt_material* materials, int count);
 /* Renderer.cpp:852-1008. Sphere, spot and directional lights. */
 int bpt_set_lights(bpt_ctx* ctx, const bpt_light* lights, int count);

@@ -101,6 +101,49 @@ TEST_F(RendererFixture, b200_render_environment_map) {
     });
 }
 
+// Incremental updates: moving the quad's scene node out of the view re-flattens the resident mesh (no mesh upload) and the
+// next frame shows the background; a material edit alone changes the tint without touching the geometry.
+TEST_F(RendererFixture, b200_incremental_transform_and_material_updates) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    using namespace Bifrost::Scene;
+
+    auto size = Math::Vector2i(4, 3);
+    CameraID camera_ID = create_ortho_camera_with_quad_scene(size, optix::make_float3(0.25f, 0.5f, 0.75f));
+    render(camera_ID, size, Backend::TintVisualization, [=](half4* pixels) {
+        EXPECT_FLOAT_EQ_EPS(0.125f, float(pixels[0].r), 0.003f); // vertex tints, as in render_tint
+    });
+
+    auto reset_changes = []() {
+        Images::reset_change_notifications(); Textures::reset_change_notifications(); Materials::reset_change_notifications();
+        Meshes::reset_change_notifications(); MeshModels::reset_change_notifications(); SceneNodes::reset_change_notifications();
+        SceneRoots::reset_change_notifications(); Cameras::reset_change_notifications(); LightSources::reset_change_notifications();
+    };
+    reset_changes();
+
+    // material edit only
+    for (MaterialID material_ID : Materials::get_iterable())
+        Materials::set_tint(material_ID, Math::RGB(0.5f, 0.5f, 0.5f));
+    render(camera_ID, size, Backend::TintVisualization, [=](half4* pixels) {
+        EXPECT_FLOAT_EQ_EPS(0.0625f, float(pixels[0].r), 0.003f); // material tint 0.5 x vertex tint 0.125
+    });
+    reset_changes();
+
+    // transform edit only: the quad leaves the frustum
+    for (MeshModelID model_ID : MeshModels::get_iterable()) {
+        SceneNode node = MeshModels::get_scene_node_ID(model_ID);
+        Math::Transform t = node.get_global_transform();
+        t.translation.x += 100.0f;
+        node.set_global_transform(t);
+    }
+    render(camera_ID, size, [=](half4* pixels) {
+        for (int i = 0; i < size.x * size.y; ++i) {
+            EXPECT_FLOAT_EQ_EPS(0.25f, float(pixels[i].r), 1e-3f);
+            EXPECT_FLOAT_EQ_EPS(0.75f, float(pixels[i].b), 1e-3f);
+        }
+    });
+}
+
 } // namespace OptiXRenderer
 
 // tests/OptiXRendererTests/Utils.cpp uses windows.h; the data directory is unused by this implementation.
