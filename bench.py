@@ -253,19 +253,25 @@ def main():
 
     # ---- end-to-end through the C ABI with host buffers ---------------------------------------------
     barrier()
-    frame_t = torch.empty((H, W, 4), dtype=torch.int16).pin_memory()  # pinned host frame, as a display path would use
-    frame = frame_t.numpy().view(np.uint16)
+    # Two pinned host frames, as a display path would use: the read-back of frame k (bpt_resolve_half4_async) overlaps the
+    # rendering of frame k + 1; every frame is complete in host memory before the timed region ends.
+    frames_t = [torch.empty((H, W, 4), dtype=torch.int16).pin_memory() for _ in range(2)]
+    frames = [f.numpy().view(np.uint16) for f in frames_t]
     for k in range(2):
-        ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.lib.bpt_resolve_half4(ctx.h, frame.ctypes.data, 0)
+        ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.resolve_half4_async(frames[k & 1], k & 1)
+    ctx.wait_frame(0); ctx.wait_frame(1)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = min(K, 32)
     for k in range(e2e_steps):
         cam_k = capi.make_camera(*scene["camera"])  # host-side camera state is rebuilt and uploaded every step
         ctx.render(cam_k, W, H, first + k, 1, reset=(k == 0), **settings)
-        ctx.lib.bpt_resolve_half4(ctx.h, frame.ctypes.data, 0)  # device -> host read of the displayed frame
+        ctx.wait_frame(k & 1)                         # the frame this slot delivered two steps ago has been consumed
+        ctx.resolve_half4_async(frames[k & 1], k & 1)  # device -> host read of the displayed frame
+    ctx.wait_frame(0); ctx.wait_frame(1)
     barrier()
     e2e_s = time.perf_counter() - t0
+    frame = frames[(e2e_steps - 1) & 1]
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

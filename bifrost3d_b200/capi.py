@@ -66,7 +66,7 @@ LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_remove_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
-           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
+           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
 
@@ -139,6 +139,8 @@ def load_library():
     lib.bpt_render_aov.argtypes = [vp, C.POINTER(Camera), i32, i32, i32, u32, u32, i32]
     lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
+    lib.bpt_resolve_half4_async.argtypes = [vp, vp, i32]
+    lib.bpt_wait_frame.argtypes = [vp, i32]
     lib.bpt_resolve_float4.argtypes = [vp, vp]
     lib.bpt_resolve_tonemapped.argtypes = [vp, C.POINTER(TonemapSettings), vp, i32]
     lib.bpt_tonemap_colors.argtypes = [vp, C.POINTER(TonemapSettings), i64, vp, vp]
@@ -311,6 +313,13 @@ class Bpt:
         out = np.empty((h, w, 4), np.float32)
         self._check(self.lib.bpt_resolve_float4(self.h, _ptr(out)))
         return out
+
+    def resolve_half4_async(self, out_host, slot):
+        """out_host: a (H, W, 4) uint16 array (pinned for a truly asynchronous copy); complete after wait_frame(slot)."""
+        self._check(self.lib.bpt_resolve_half4_async(self.h, out_host.ctypes.data, int(slot)))
+
+    def wait_frame(self, slot):
+        self._check(self.lib.bpt_wait_frame(self.h, int(slot)))
 
     def resolve_tonemapped(self, mode="filmic", exposure=1.0, filmic=FILMIC_ACES, rgba8=False):
         """Mean radiance -> exposure -> tonemapping operator: linear float4, or sRGB-encoded RGBA8 when rgba8 is set."""

@@ -381,6 +381,11 @@ void bpt_destroy(bpt_ctx* c) {
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release();
     ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->frame_resolved[i]); cudaEventDestroy(ctx->frame_copied[i]); ctx->frame_staging[i].release(); }
+        cudaStreamDestroy(ctx->copy_stream);
+    }
     if (ctx->device_counters) cudaFree(ctx->device_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->stage_events) cudaEventDestroy(e);
@@ -683,6 +688,8 @@ int bpt_render_aov(bpt_ctx* c, const bpt_camera* camera, int aov_kind, int width
 
 void* bpt_accumulation_device_ptr(bpt_ctx* c) { return as_context(c)->accumulation.ptr; }
 int bpt_resolve_half4(bpt_ctx* c, uint16_t* out, int on_device) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_half4(ctx, out, on_device); }
+int bpt_resolve_half4_async(bpt_ctx* c, uint16_t* out_host, int slot) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_half4_async(ctx, out_host, slot); }
+int bpt_wait_frame(bpt_ctx* c, int slot) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return wait_frame(ctx, slot); }
 int bpt_resolve_tonemapped(bpt_ctx* c, const bpt_tonemap_settings* settings, void* out, int output_format) {
     Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_tonemapped(ctx, settings, out, output_format);
 }

@@ -135,6 +135,12 @@ struct Context {
     int width = 0, height = 0;
     DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
     DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
+    // Pipelined frame read-back (bpt_resolve_half4_async): two staging frames, a copy stream and per-slot events, so the
+    // device -> host copy of frame k overlaps the rendering of frame k + 1.
+    DeviceBuffer<uint16_t> frame_staging[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t frame_resolved[2] = {}, frame_copied[2] = {};
+    bool frame_in_flight[2] = { false, false };
     float half4_scale = 1.0f; // depth backend: the displayed value is depth / (far - near), SimpleRGPs.cu:247-258
     uint64_t material_version = 0;
     bool env_light_uploaded = false;
@@ -177,6 +183,8 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
 int resolve_float4(Context* ctx, float* out);
 void release_wavefront(Context* ctx);
 int tonemap_batch(Context* ctx, const bpt_tonemap_settings* settings, int64_t n, const float* rgb_in, float* rgb_out); // bpt_tonemap.cu
+int resolve_half4_async(Context* ctx, uint16_t* out_host, int slot); // bpt_render.cu
+int wait_frame(Context* ctx, int slot);
 int resolve_tonemapped(Context* ctx, const bpt_tonemap_settings* settings, void* out, int output_format);
 int sync_texture_table(Context* ctx); // uploads the texture id -> cudaTextureObject_t table when it changed (bpt_api.cu)
 

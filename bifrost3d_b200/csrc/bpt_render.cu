@@ -762,6 +762,47 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device) {
     return BPT_OK;
 }
 
+// Enqueues the half4 resolve of the current accumulation on the render stream and its device -> host copy on the copy
+// stream, and returns without waiting: the next bpt_render overlaps the copy. `out_host` should be pinned memory.
+int resolve_half4_async(Context* ctx, uint16_t* out_host, int slot) {
+    if (!out_host || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_half4_async: nothing rendered");
+    if (slot < 0 || slot > 1) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_resolve_half4_async: slot must be 0 or 1");
+    const int64_t pixels = (int64_t)ctx->width * ctx->height;
+    cudaStream_t st = ctx->stream;
+    if (!ctx->copy_stream) {
+        BPT_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->frame_resolved[i], cudaEventDisableTiming));
+            BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->frame_copied[i], cudaEventDisableTiming));
+        }
+    }
+    if (ctx->frame_staging[slot].size != (size_t)(4 * pixels)) {
+        if (ctx->frame_in_flight[slot]) BPT_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->frame_copied[slot]));
+        BPT_CUDA_CHECK(ctx, ctx->frame_staging[slot].resize(4 * pixels));
+    }
+    // the staging frame of this slot may still be read by its previous copy
+    if (ctx->frame_in_flight[slot]) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->frame_copied[slot], 0));
+    resolve_half4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, reinterpret_cast<ushort4*>(ctx->frame_staging[slot].ptr), pixels,
+                                                             ctx->half4_scale);
+    ctx->counters.kernel_launches++;
+    BPT_CUDA_CHECK(ctx, cudaEventRecord(ctx->frame_resolved[slot], st));
+    BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->frame_resolved[slot], 0));
+    BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out_host, ctx->frame_staging[slot].ptr, pixels * sizeof(ushort4), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    BPT_CUDA_CHECK(ctx, cudaEventRecord(ctx->frame_copied[slot], ctx->copy_stream));
+    ctx->frame_in_flight[slot] = true;
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
+int wait_frame(Context* ctx, int slot) {
+    if (slot < 0 || slot > 1) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_wait_frame: slot must be 0 or 1");
+    if (ctx->frame_in_flight[slot]) {
+        BPT_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->frame_copied[slot]));
+        ctx->frame_in_flight[slot] = false;
+    }
+    return BPT_OK;
+}
+
 int resolve_float4(Context* ctx, float* out) {
     if (!out || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_float4: nothing rendered");
     int64_t pixels = (int64_t)ctx->width * ctx->height;

@@ -217,7 +217,7 @@ struct Traversal {
     BPT_D void begin(const Ray& r, int skip) {
         ray = r;
         shear = make_ray_shear(r.direction);
-        inv_d = f3(1.0f / r.direction.x, 1.0f / r.direction.y, 1.0f / r.direction.z);
+        inv_d = f3(__fdiv_rn(1.0f, r.direction.x), __fdiv_rn(1.0f, r.direction.y), __fdiv_rn(1.0f, r.direction.z)); // IEEE whatever -prec-div says
         tmax = r.tmax;
         hit.t = r.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
         transmission = 1.0f;

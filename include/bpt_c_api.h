@@ -206,6 +206,12 @@ void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
 /* mean = sum / w, converted to half4 (alpha 1) exactly like SimpleRGPs.cu:39-42,106; written to `out` which is
  * a HOST pointer to width*height*4 uint16 (on_device == 0) or a DEVICE pointer (on_device != 0). */
 int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
+/* Pipelined read-back for progressive display: enqueues the half4 resolve on the render stream and its device -> host copy
+ * on a second stream, then returns; the copy of frame k overlaps the rendering of frame k + 1. `out_host` (width*height*4
+ * uint16, ideally pinned) is complete after bpt_wait_frame(ctx, slot). Two slots (0, 1) alternate; re-using a slot waits for
+ * its previous copy on the device, not on the host. */
+int bpt_resolve_half4_async(bpt_ctx* ctx, uint16_t* out_host, int slot);
+int bpt_wait_frame(bpt_ctx* ctx, int slot);
 /* mean as float4 to a HOST buffer of width*height*4 floats. */
 int bpt_resolve_float4(bpt_ctx* ctx, float* out);
 /* Tonemapped resolve. Operators and parameters are the core's camera effects (core/Bifrost/Bifrost/Math/CameraEffects.h:

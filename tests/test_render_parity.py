@@ -294,3 +294,26 @@ def test_converged_image_within_monte_carlo_confidence_intervals(bpt):
     print(f"pixels x channels within 4 sigma: {inside.mean():.4f}; relMSE {rel_mse(gpu, cpu_mean):.3e}")
     assert inside.mean() >= 0.999
     assert rel_mse(gpu, cpu_mean) < 1e-3
+
+
+@pytest.mark.gpu
+def test_pipelined_frame_readback_equals_the_synchronous_one(bpt):
+    """bpt_resolve_half4_async + bpt_wait_frame deliver the frames bpt_resolve_half4 delivers, while later samples render."""
+    scene = scenes.cornell_box(sphere_quads=(8, 4))
+    scenes.upload(bpt, scene)
+    cam, w, h = scene["camera"], 40, 32
+    expected = []
+    for k in range(4):
+        bpt.render(cam, w, h, k, 1, reset=(k == 0))
+        expected.append(bpt.resolve_half4().view(np.uint16).copy())
+    frames = [np.zeros((h, w, 4), np.uint16) for _ in range(2)]
+    for k in range(4):
+        bpt.render(cam, w, h, k, 1, reset=(k == 0))
+        bpt.wait_frame(k & 1)
+        if k >= 2:
+            assert np.array_equal(frames[k & 1], expected[k - 2])
+        bpt.resolve_half4_async(frames[k & 1], k & 1)
+    bpt.wait_frame(0); bpt.wait_frame(1)
+    assert np.array_equal(frames[0], expected[2]) and np.array_equal(frames[1], expected[3])
+    with pytest.raises(capi.BptError, match="slot"):
+        bpt.resolve_half4_async(frames[0], 2)
