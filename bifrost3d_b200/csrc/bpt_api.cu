@@ -339,6 +339,7 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     if (cudaSetDevice(cuda_device) != cudaSuccess) return BPT_ERROR_CUDA;
     Context* ctx = new Context();
     ctx->device = cuda_device;
+    if (const char* bvh = getenv("BPT_BVH")) ctx->use_ploc = strcmp(bvh, "lbvh") != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPT_ERROR_CUDA; }

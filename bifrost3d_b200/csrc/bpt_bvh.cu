@@ -8,6 +8,7 @@
 #include "bpt_trace.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <float.h>
@@ -258,6 +259,113 @@ __global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb
     nodes[i] = out;
 }
 
+// ---- PLOC: parallel locally-ordered clustering (Meister and Bittner, TVCG 2018) over the LBVH's leaf clusters ----------
+// The Morton-ordered LBVH above is kept for its bottom: its subtrees of at most LEAF_MAX triangles become the leaf
+// clusters (contiguous ranges of the sorted triangle array). The hierarchy ABOVE them is rebuilt bottom-up: every
+// cluster looks for the neighbour within PLOC_RADIUS positions whose union with it has the smallest surface area,
+// mutual nearest neighbours merge into a node, the cluster list is compacted (order preserving) and the search repeats.
+// This follows the surface area heuristic locally instead of the Morton code's bit pattern: fewer node visits per ray.
+#ifndef BPT_PLOC_RADIUS
+#define BPT_PLOC_RADIUS 8
+#endif
+constexpr int PLOC_RADIUS = BPT_PLOC_RADIUS;
+constexpr int PLOC_MAX_DEPTH = 96; // the traversal stack holds STACK_SMEM + STACK_LOCAL = 104 entries
+
+__device__ __forceinline__ bool is_leaf_cluster_child(const TreeNode* __restrict__ tree, int child, int& first, int& size) {
+    if (child < 0) { first = ~child; size = 1; return true; }
+    TreeNode c = tree[child];
+    first = c.first; size = c.last - c.first + 1;
+    return size <= LEAF_MAX;
+}
+
+// flag[p] = 1 where a leaf cluster starts (p = position in the sorted triangle array).
+__global__ void ploc_mark_kernel(int n, const TreeNode* __restrict__ tree, uint32_t* __restrict__ flag) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    TreeNode tn = tree[i];
+    if (i != 0 && tn.last - tn.first + 1 <= LEAF_MAX) return; // inside a leaf cluster
+    int first, size;
+    if (is_leaf_cluster_child(tree, tn.left, first, size)) flag[first] = 1u;
+    if (is_leaf_cluster_child(tree, tn.right, first, size)) flag[first] = 1u;
+}
+
+__global__ void ploc_gather_kernel(int n, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
+                                   const uint32_t* __restrict__ position, int* __restrict__ cl_link, Aabb* __restrict__ cl_box, int* __restrict__ cl_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    TreeNode tn = tree[i];
+    if (i != 0 && tn.last - tn.first + 1 <= LEAF_MAX) return;
+    int child[2] = { tn.left, tn.right };
+    for (int k = 0; k < 2; ++k) {
+        int first, size;
+        if (!is_leaf_cluster_child(tree, child[k], first, size)) continue;
+        uint32_t c = position[first];
+        cl_link[c] = pack_leaf(first, size);
+        cl_box[c] = child[k] < 0 ? leaf_boxes[~child[k]] : node_boxes[child[k]];
+        cl_depth[c] = 0;
+    }
+}
+
+__device__ __forceinline__ float union_area(const Aabb& a, const Aabb& b) {
+    float3 d = max3(a.hi, b.hi) - min3(a.lo, b.lo);
+    return d.x * d.y + d.y * d.z + d.z * d.x;
+}
+
+__global__ void ploc_nearest_kernel(int m, const Aabb* __restrict__ cl_box, int* __restrict__ nearest) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const Aabb mine = cl_box[i];
+    float best = FLT_MAX; int best_j = -1, best_rank = 0x7fffffff;
+    const int lo = max(0, i - PLOC_RADIUS), hi = min(m - 1, i + PLOC_RADIUS);
+    for (int j = lo; j <= hi; ++j) {
+        if (j == i) continue;
+        float a = union_area(mine, cl_box[j]);
+        // exact ties (regular or coincident geometry): prefer the aligned partner i ^ 1, then the closer position, then the
+        // lower one, so that equal boxes still pair up instead of forming a chain that merges one pair per pass
+        int rank = (j == (i ^ 1)) ? 0 : 2 * abs(j - i) + (j > i ? 1 : 0);
+        if (a < best || (a == best && rank < best_rank)) { best = a; best_j = j; best_rank = rank; }
+    }
+    nearest[i] = best_j;
+}
+
+// Mutual nearest neighbours merge: the lower position keeps the new node, the higher one is dropped.
+__global__ void ploc_merge_kernel(int m, const int* __restrict__ nearest, int* __restrict__ cl_link, Aabb* __restrict__ cl_box, int* __restrict__ cl_depth,
+                                  uint32_t* __restrict__ keep, BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    int j = nearest[i];
+    bool mutual = j >= 0 && nearest[j] == i;
+    if (!mutual) { keep[i] = 1u; return; }
+    if (i > j) { keep[i] = 0u; return; }
+    Aabb a = cl_box[i], b = cl_box[j];
+    int index = atomicAdd(node_counter, 1);
+    BvhNode out;
+    out.lo_l_hi_l_x = make_float4(a.lo.x, a.lo.y, a.lo.z, a.hi.x);
+    out.hi_l_lo_r = make_float4(a.hi.y, a.hi.z, b.lo.x, b.lo.y);
+    out.lo_r_hi_r = make_float4(b.lo.z, b.hi.x, b.hi.y, b.hi.z);
+    out.left = cl_link[i]; out.right = cl_link[j]; out.pad0 = 0; out.pad1 = 0;
+    nodes[index] = out;
+    Aabb merged; merged.lo = min3(a.lo, b.lo); merged.hi = max3(a.hi, b.hi);
+    int depth = max(cl_depth[i], cl_depth[j]) + 1;
+    // cluster j is only read by this thread (its own thread returned above), so updating slot i in place is race free:
+    // no other cluster has i or j as a MUTUAL partner, and non-mutual clusters only read `nearest`.
+    cl_box[i] = merged; cl_link[i] = index; cl_depth[i] = depth;
+    keep[i] = 1u;
+    atomicMax(max_depth, depth);
+}
+
+__global__ void ploc_compact_kernel(int m, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ position, const int* __restrict__ link_in,
+                                    const Aabb* __restrict__ box_in, const int* __restrict__ depth_in, int* __restrict__ link_out,
+                                    Aabb* __restrict__ box_out, int* __restrict__ depth_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || !keep[i]) return;
+    uint32_t c = position[i];
+    link_out[c] = link_in[i]; box_out[c] = box_in[i]; depth_out[c] = depth_in[i];
+}
+
+// The traversal enters at node 0: move the root there (no link points at the root, so its old slot just stays unused).
+__global__ void ploc_root_kernel(const int* __restrict__ cl_link, BvhNode* __restrict__ nodes) { nodes[0] = nodes[cl_link[0]]; }
+
 __global__ void tiny_root_kernel(int n, const Aabb* __restrict__ leaf_boxes, BvhNode* __restrict__ nodes) {
     // n == 0: both children absent. n == 1: the left child is the only triangle. An absent child is a point box at
     // (3e38, 3e38, 3e38): for a normalised direction its slab distances are >= 3e38 in magnitude, outside any [tmin, tmax].
@@ -406,9 +514,70 @@ int build_accel(Context* ctx) {
         fit_kernel<<<full_grid(n), block, 0, st>>>(n, vals.Current(), A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr,
                                                    d_leaf_boxes.ptr, d_node_boxes.ptr, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr, d_arrival.ptr);
         ctx->counters.kernel_launches++;
-        if (n > 1) {
+        // ---- upper hierarchy: PLOC over the leaf clusters; the plain LBVH emit is the fallback ----
+        bool ploc_done = false;
+        if (ctx->use_ploc && n > LEAF_MAX) {
+            DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
+            DeviceBuffer<unsigned char> d_scan_temp;
+            auto release_ploc = [&]() { d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release();
+                                        for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); } };
+#define PLOC_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { release_ploc(); release_all(); return ctx->cuda_fail(_e, #expr); } } while (0)
+            PLOC_CHECK(d_flag.resize(n)); PLOC_CHECK(d_pos.resize(n)); PLOC_CHECK(d_scalars.resize(2));
+            PLOC_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(uint32_t) * n, st));
+            size_t scan_bytes = 0;
+            PLOC_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
+            PLOC_CHECK(d_scan_temp.resize(std::max<size_t>(scan_bytes, 1)));
+            ploc_mark_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_flag.ptr);
+            PLOC_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_temp.ptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
+            uint32_t last_pos = 0, last_flag = 0;
+            PLOC_CHECK(cudaMemcpyAsync(&last_pos, d_pos.ptr + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PLOC_CHECK(cudaMemcpyAsync(&last_flag, d_flag.ptr + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PLOC_CHECK(cudaStreamSynchronize(st));
+            int m = int(last_pos + last_flag);
+            ctx->counters.kernel_launches += 3;
+            if (m >= 2) {
+                for (int k = 0; k < 2; ++k) { PLOC_CHECK(d_link[k].resize(m)); PLOC_CHECK(d_depth[k].resize(m)); PLOC_CHECK(d_box[k].resize(m)); }
+                PLOC_CHECK(d_nearest.resize(m));
+                PLOC_CHECK(A.nodes.resize((size_t)m + 1)); // m - 1 nodes from index 1 on, the root is copied to index 0
+                ploc_gather_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, d_pos.ptr, d_link[0].ptr, d_box[0].ptr,
+                                                                       d_depth[0].ptr);
+                int h_scalars[2] = { 1, 0 }; // next node index, deepest cluster
+                PLOC_CHECK(cudaMemcpyAsync(d_scalars.ptr, h_scalars, sizeof(h_scalars), cudaMemcpyHostToDevice, st));
+                ctx->counters.kernel_launches++;
+                int cur = 0, passes = 0;
+                bool failed = false;
+                while (m > 1) {
+                    ploc_nearest_kernel<<<full_grid(m), block, 0, st>>>(m, d_box[cur].ptr, d_nearest.ptr);
+                    ploc_merge_kernel<<<full_grid(m), block, 0, st>>>(m, d_nearest.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, d_flag.ptr, A.nodes.ptr,
+                                                                     d_scalars.ptr, d_scalars.ptr + 1);
+                    PLOC_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_temp.ptr, scan_bytes, d_flag.ptr, d_pos.ptr, m, st));
+                    ploc_compact_kernel<<<full_grid(m), block, 0, st>>>(m, d_flag.ptr, d_pos.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr,
+                                                                       d_link[cur ^ 1].ptr, d_box[cur ^ 1].ptr, d_depth[cur ^ 1].ptr);
+                    PLOC_CHECK(cudaMemcpyAsync(&last_pos, d_pos.ptr + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    PLOC_CHECK(cudaMemcpyAsync(&last_flag, d_flag.ptr + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    PLOC_CHECK(cudaStreamSynchronize(st));
+                    ctx->counters.kernel_launches += 4;
+                    int next_m = int(last_pos + last_flag);
+                    if (next_m >= m || ++passes > 4096) { failed = true; break; } // cannot happen: the globally closest pair is always mutual
+                    m = next_m; cur ^= 1;
+                }
+                PLOC_CHECK(cudaMemcpyAsync(h_scalars, d_scalars.ptr, sizeof(h_scalars), cudaMemcpyDeviceToHost, st));
+                PLOC_CHECK(cudaStreamSynchronize(st));
+                if (!failed && h_scalars[1] <= PLOC_MAX_DEPTH) {
+                    ploc_root_kernel<<<1, 1, 0, st>>>(d_link[cur].ptr, A.nodes.ptr);
+                    ctx->counters.kernel_launches++;
+                    A.node_count = h_scalars[0];
+                    A.ploc_passes = passes; A.ploc_depth = h_scalars[1];
+                    ploc_done = true;
+                }
+            }
+            release_ploc();
+#undef PLOC_CHECK
+        }
+        if (!ploc_done && n > 1) {
             emit_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, A.nodes.ptr);
             ctx->counters.kernel_launches++;
+            A.node_count = n - 1; A.ploc_passes = 0; A.ploc_depth = 0;
         }
     }
     if (n <= 1) {
@@ -423,7 +592,7 @@ int build_accel(Context* ctx) {
 #undef BUILD_CHECK
 
     A.triangle_count = n;
-    A.node_count = n > 1 ? n - 1 : 1;
+    if (n <= 1) { A.node_count = 1; A.ploc_passes = 0; A.ploc_depth = 0; }
     A.valid = true;
     return BPT_OK;
 }

@@ -92,6 +92,7 @@ struct Accel {
     int64_t triangle_count = 0;
     int64_t node_count = 0;
     float build_ms = 0.0f;
+    int ploc_passes = 0, ploc_depth = 0;        // 0 when the plain LBVH hierarchy is in use
     float3 scene_lo, scene_hi;
     bool valid = false;
 };
@@ -109,6 +110,7 @@ struct Context {
     DeviceBuffer<float2> dielectric_tables;
     bool has_dielectric_tables = false;
     bool has_transmissive_materials = false;
+    bool use_ploc = true; // BPT_BVH=lbvh in the environment selects the plain Morton hierarchy (for A/B measurements)
     DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
 
     std::map<int, DeviceMesh> meshes;
