@@ -18,7 +18,7 @@ namespace bpt {
 namespace {
 
 #ifndef BPT_LEAF_MAX
-#define BPT_LEAF_MAX 4
+#define BPT_LEAF_MAX 2
 #endif
 constexpr int LEAF_MAX = BPT_LEAF_MAX;
 
@@ -266,7 +266,7 @@ __global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb
 // mutual nearest neighbours merge into a node, the cluster list is compacted (order preserving) and the search repeats.
 // This follows the surface area heuristic locally instead of the Morton code's bit pattern: fewer node visits per ray.
 #ifndef BPT_PLOC_RADIUS
-#define BPT_PLOC_RADIUS 8
+#define BPT_PLOC_RADIUS 16
 #endif
 constexpr int PLOC_RADIUS = BPT_PLOC_RADIUS;
 constexpr int PLOC_MAX_DEPTH = 96; // the traversal stack holds STACK_SMEM + STACK_LOCAL = 104 entries
@@ -457,7 +457,12 @@ int build_accel(Context* ctx) {
     DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<float> d_bounds;
     DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<unsigned char> d_temp;
     DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
+    // PLOC scratch
+    DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
+    DeviceBuffer<unsigned char> d_scan_temp;
     auto release_all = [&]() {
+        d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release();
+        for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); }
         d_records.release(); d_bounds.release();
         d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
         d_tree.release(); d_parent_internal.release(); d_parent_leaf.release(); d_arrival.release(); d_leaf_boxes.release(); d_node_boxes.release();
@@ -480,7 +485,16 @@ int build_accel(Context* ctx) {
     A.has_uv = any_texcoords && n > 0;
     if (A.has_uv) BUILD_CHECK(A.shade_uv.resize(3ull * n)); else A.shade_uv.release();
     BUILD_CHECK(A.triangles.resize(std::max<size_t>(n, 1)));
-    BUILD_CHECK(A.nodes.resize(std::max<size_t>(n > 1 ? n - 1 : 1, 1)));
+    BUILD_CHECK(A.nodes.resize((size_t)n + 1));
+    // PLOC scratch is sized for the worst case of one cluster per triangle and allocated outside the timed region.
+    const bool try_ploc = ctx->use_ploc && n > LEAF_MAX;
+    size_t scan_bytes = 0;
+    if (try_ploc) {
+        BUILD_CHECK(d_flag.resize(n)); BUILD_CHECK(d_pos.resize(n)); BUILD_CHECK(d_scalars.resize(2)); BUILD_CHECK(d_nearest.resize(n));
+        for (int k = 0; k < 2; ++k) { BUILD_CHECK(d_link[k].resize(n)); BUILD_CHECK(d_depth[k].resize(n)); BUILD_CHECK(d_box[k].resize(n)); }
+        BUILD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
+        BUILD_CHECK(d_scan_temp.resize(std::max<size_t>(scan_bytes, 1)));
+    }
     BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
 
     BUILD_CHECK(cudaEventRecord(ctx->ev[0], st));
@@ -516,17 +530,9 @@ int build_accel(Context* ctx) {
         ctx->counters.kernel_launches++;
         // ---- upper hierarchy: PLOC over the leaf clusters; the plain LBVH emit is the fallback ----
         bool ploc_done = false;
-        if (ctx->use_ploc && n > LEAF_MAX) {
-            DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
-            DeviceBuffer<unsigned char> d_scan_temp;
-            auto release_ploc = [&]() { d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release();
-                                        for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); } };
-#define PLOC_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { release_ploc(); release_all(); return ctx->cuda_fail(_e, #expr); } } while (0)
-            PLOC_CHECK(d_flag.resize(n)); PLOC_CHECK(d_pos.resize(n)); PLOC_CHECK(d_scalars.resize(2));
+        if (try_ploc) {
+#define PLOC_CHECK(expr) BUILD_CHECK(expr)
             PLOC_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(uint32_t) * n, st));
-            size_t scan_bytes = 0;
-            PLOC_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
-            PLOC_CHECK(d_scan_temp.resize(std::max<size_t>(scan_bytes, 1)));
             ploc_mark_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_flag.ptr);
             PLOC_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_temp.ptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
             uint32_t last_pos = 0, last_flag = 0;
@@ -536,9 +542,7 @@ int build_accel(Context* ctx) {
             int m = int(last_pos + last_flag);
             ctx->counters.kernel_launches += 3;
             if (m >= 2) {
-                for (int k = 0; k < 2; ++k) { PLOC_CHECK(d_link[k].resize(m)); PLOC_CHECK(d_depth[k].resize(m)); PLOC_CHECK(d_box[k].resize(m)); }
-                PLOC_CHECK(d_nearest.resize(m));
-                PLOC_CHECK(A.nodes.resize((size_t)m + 1)); // m - 1 nodes from index 1 on, the root is copied to index 0
+                // m - 1 nodes from index 1 on, the root is copied to index 0: A.nodes holds n + 1 entries
                 ploc_gather_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, d_pos.ptr, d_link[0].ptr, d_box[0].ptr,
                                                                        d_depth[0].ptr);
                 int h_scalars[2] = { 1, 0 }; // next node index, deepest cluster
@@ -571,7 +575,6 @@ int build_accel(Context* ctx) {
                     ploc_done = true;
                 }
             }
-            release_ploc();
 #undef PLOC_CHECK
         }
         if (!ploc_done && n > 1) {

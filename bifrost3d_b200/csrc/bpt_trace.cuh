@@ -153,19 +153,22 @@ struct AccelView {
     const Material* __restrict__ materials; // with `textures`: only read by any-hit rays that meet a coverage-textured material
     TextureView textures;
     int min_active; // see traversal_min_active_for
-    int budget; // node visits between two refills of a warp's idle lanes: ~ the depth of the tree (measured: 24 up to a few
-                // million triangles, 48 for the 50M-triangle scene whose rays visit 80+ nodes)
+    int budget; // upper bound on the node visits between two refills of a warp's idle lanes
 };
 #ifndef BPT_BUDGET_SMALL
-#define BPT_BUDGET_SMALL 24
+#define BPT_BUDGET_SMALL 48
 #endif
 #ifndef BPT_BUDGET_LARGE
-#define BPT_BUDGET_LARGE 48
+#define BPT_BUDGET_LARGE 96
 #endif
 BPT_HD int traversal_budget_for(long long triangle_count) { return triangle_count > 8000000ll ? BPT_BUDGET_LARGE : BPT_BUDGET_SMALL; }
 // A round also ends once fewer than this many lanes of the warp are still traversing (measured on B200: +4 % on the 20 k
-// and 1 M triangle scenes; the 50 M triangle scene, bound by memory latency rather than issue slots, loses 1 % and opts out).
-BPT_HD int traversal_min_active_for(long long triangle_count) { return triangle_count > 8000000ll ? 0 : BPT_MIN_ACTIVE_LANES; }
+// and 1 M triangle scenes with 12 lanes; +2 % on the 50 M triangle scene with 8). With this trigger in place the node
+// budget is only a backstop, and larger budgets (48 / 96) measured 1-3 % faster than 24 / 48.
+#ifndef BPT_MIN_ACTIVE_LANES_LARGE
+#define BPT_MIN_ACTIVE_LANES_LARGE 8
+#endif
+BPT_HD int traversal_min_active_for(long long triangle_count) { return triangle_count > 8000000ll ? BPT_MIN_ACTIVE_LANES_LARGE : BPT_MIN_ACTIVE_LANES; }
 
 inline AccelView accel_view(const Context* ctx) {
     AccelView a;
