@@ -340,6 +340,7 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     Context* ctx = new Context();
     ctx->device = cuda_device;
     if (const char* bvh = getenv("BPT_BVH")) ctx->use_ploc = strcmp(bvh, "lbvh") != 0;
+    if (const char* wide = getenv("BPT_WIDE")) ctx->use_wide = strcmp(wide, "0") != 0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPT_ERROR_CUDA; }
@@ -380,7 +381,7 @@ void bpt_destroy(bpt_ctx* c) {
     for (auto& kv : ctx->meshes) kv.second.release();
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release();
-    ctx->accel.nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
+    ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);

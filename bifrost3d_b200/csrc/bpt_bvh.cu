@@ -366,6 +366,53 @@ __global__ void ploc_compact_kernel(int m, const uint32_t* __restrict__ keep, co
 // The traversal enters at node 0: move the root there (no link points at the root, so its old slot just stays unused).
 __global__ void ploc_root_kernel(const int* __restrict__ cl_link, BvhNode* __restrict__ nodes) { nodes[0] = nodes[cl_link[0]]; }
 
+// ---- four-wide collapse ---------------------------------------------------------------------------------------------
+// Top down over the finished binary hierarchy: a wide node starts from a binary node's two children and twice replaces the
+// inner child with the largest surface area by that child's own two children. One kernel launch per level of the wide
+// tree; the tasks of the next level are appended with an atomic counter.
+struct WideTask { int wide_index, binary_index; };
+
+__device__ __forceinline__ float box_area(float3 lo, float3 hi) {
+    float3 d = hi - lo;
+    return d.x * d.y + d.y * d.z + d.z * d.x;
+}
+
+__global__ void collapse_kernel(int count, const WideTask* __restrict__ tasks, WideTask* __restrict__ next_tasks, int* __restrict__ counters /*[0] next, [1] wide nodes*/,
+                                const BvhNode* __restrict__ nodes, WideNode* __restrict__ wide) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const WideTask task = tasks[i];
+    const float far = 3.0e38f;
+    int link[4] = { NODE_EMPTY, NODE_EMPTY, NODE_EMPTY, NODE_EMPTY };
+    float3 lo[4] = { f3(far), f3(far), f3(far), f3(far) }, hi[4] = { f3(far), f3(far), f3(far), f3(far) };
+    auto children = [&](int binary_index, int a, int b) {
+        BvhNode n = nodes[binary_index];
+        lo[a] = f3(n.lo_l_hi_l_x.x, n.lo_l_hi_l_x.y, n.lo_l_hi_l_x.z); hi[a] = f3(n.lo_l_hi_l_x.w, n.hi_l_lo_r.x, n.hi_l_lo_r.y); link[a] = n.left;
+        lo[b] = f3(n.hi_l_lo_r.z, n.hi_l_lo_r.w, n.lo_r_hi_r.x); hi[b] = f3(n.lo_r_hi_r.y, n.lo_r_hi_r.z, n.lo_r_hi_r.w); link[b] = n.right;
+    };
+    children(task.binary_index, 0, 1);
+    for (int used = 2; used < 4; ++used) {
+        int best = -1; float best_area = -1.0f;
+        for (int k = 0; k < used; ++k)
+            if (link[k] >= 0) { float area = box_area(lo[k], hi[k]); if (area > best_area) { best_area = area; best = k; } }
+        if (best < 0) break;
+        children(link[best], best, used);
+    }
+    for (int k = 0; k < 4; ++k)
+        if (link[k] >= 0) {
+            int w = atomicAdd(counters + 1, 1);
+            next_tasks[atomicAdd(counters, 1)] = { w, link[k] };
+            link[k] = w;
+        }
+    WideNode out;
+    out.lo_x = make_float4(lo[0].x, lo[1].x, lo[2].x, lo[3].x); out.lo_y = make_float4(lo[0].y, lo[1].y, lo[2].y, lo[3].y);
+    out.lo_z = make_float4(lo[0].z, lo[1].z, lo[2].z, lo[3].z); out.hi_x = make_float4(hi[0].x, hi[1].x, hi[2].x, hi[3].x);
+    out.hi_y = make_float4(hi[0].y, hi[1].y, hi[2].y, hi[3].y); out.hi_z = make_float4(hi[0].z, hi[1].z, hi[2].z, hi[3].z);
+    out.link = make_int4(link[0], link[1], link[2], link[3]);
+    out.pad = make_int4(0, 0, 0, 0);
+    wide[task.wide_index] = out;
+}
+
 __global__ void tiny_root_kernel(int n, const Aabb* __restrict__ leaf_boxes, BvhNode* __restrict__ nodes) {
     // n == 0: both children absent. n == 1: the left child is the only triangle. An absent child is a point box at
     // (3e38, 3e38, 3e38): for a normalised direction its slab distances are >= 3e38 in magnitude, outside any [tmin, tmax].
@@ -586,6 +633,34 @@ int build_accel(Context* ctx) {
     if (n <= 1) {
         tiny_root_kernel<<<1, 1, 0, st>>>(n, d_leaf_boxes.ptr, A.nodes.ptr);
         ctx->counters.kernel_launches++;
+        A.node_count = 1; A.ploc_passes = 0; A.ploc_depth = 0;
+    }
+    // ---- four-wide collapse of whichever binary hierarchy was built ----
+    A.wide_levels = 0; A.wide_node_count = 0;
+    if (ctx->use_wide) {
+        const size_t binary_nodes = (size_t)std::max<int64_t>(A.node_count, 1) + 1;
+        DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters;
+        auto release_wide = [&]() { d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); };
+#define WIDE_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { release_wide(); release_all(); return ctx->cuda_fail(_e, #expr); } } while (0)
+        WIDE_CHECK(A.wide_nodes.resize(binary_nodes)); WIDE_CHECK(d_tasks[0].resize(binary_nodes)); WIDE_CHECK(d_tasks[1].resize(binary_nodes));
+        WIDE_CHECK(d_counters.resize(2));
+        WideTask root = { 0, 0 };
+        WIDE_CHECK(cudaMemcpyAsync(d_tasks[0].ptr, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+        int h_counters[2] = { 0, 1 }; // tasks of the next level, wide nodes allocated (the root is node 0)
+        int count = 1, cur = 0, levels = 0;
+        while (count > 0) {
+            h_counters[0] = 0;
+            WIDE_CHECK(cudaMemcpyAsync(d_counters.ptr, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+            collapse_kernel<<<full_grid(count), block, 0, st>>>(count, d_tasks[cur].ptr, d_tasks[cur ^ 1].ptr, d_counters.ptr, A.nodes.ptr, A.wide_nodes.ptr);
+            ctx->counters.kernel_launches++;
+            WIDE_CHECK(cudaMemcpyAsync(h_counters, d_counters.ptr, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            WIDE_CHECK(cudaStreamSynchronize(st));
+            count = h_counters[0]; cur ^= 1; ++levels;
+        }
+        release_wide();
+#undef WIDE_CHECK
+        // a ray pushes at most three links per level: fall back to the binary nodes if that could overflow the stack
+        if (3 * levels + 1 <= STACK_SMEM + STACK_LOCAL) { A.wide_levels = levels; A.wide_node_count = h_counters[1]; }
     }
     BUILD_CHECK(cudaEventRecord(ctx->ev[1], st));
     BUILD_CHECK(cudaGetLastError());
@@ -595,7 +670,6 @@ int build_accel(Context* ctx) {
 #undef BUILD_CHECK
 
     A.triangle_count = n;
-    if (n <= 1) { A.node_count = 1; A.ploc_passes = 0; A.ploc_depth = 0; }
     A.valid = true;
     return BPT_OK;
 }

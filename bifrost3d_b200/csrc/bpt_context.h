@@ -57,6 +57,16 @@ struct __align__(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+// Four-wide node, 128 bytes: the binary hierarchy with every other level removed (bpt_bvh.cu: collapse). Child boxes are
+// stored per axis so that one 128-bit load brings the same plane of all four children; links as in BvhNode, an absent
+// child is a far-away point box with link NODE_EMPTY.
+struct __align__(16) WideNode {
+    float4 lo_x, lo_y, lo_z, hi_x, hi_y, hi_z;
+    int4 link;
+    int4 pad;
+};
+static_assert(sizeof(WideNode) == 128, "WideNode must be 128 bytes");
+
 // World-space triangle in traversal order: three float4 loads. The w lanes carry the global primitive
 // index (bits of v0.w) and the material index (v1.w); v2.w is unused.
 struct __align__(16) TraceTriangle {
@@ -83,6 +93,9 @@ struct DeviceTexture {
 
 struct Accel {
     DeviceBuffer<BvhNode> nodes;
+    DeviceBuffer<WideNode> wide_nodes;           // four-wide collapse of `nodes`; used by traversal when wide_levels > 0
+    int64_t wide_node_count = 0;
+    int wide_levels = 0;                          // depth of the four-wide tree; 0 = traverse the binary nodes
     DeviceBuffer<TraceTriangle> triangles;      // traversal order (Morton sorted)
     DeviceBuffer<float4> world_vertices;        // 3 per primitive, instance-major order: position.xyz, w unused
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
@@ -110,6 +123,7 @@ struct Context {
     DeviceBuffer<float2> dielectric_tables;
     bool has_dielectric_tables = false;
     bool has_transmissive_materials = false;
+    bool use_wide = true; // BPT_WIDE=0 in the environment traverses the binary nodes (for A/B measurements)
     bool use_ploc = true; // BPT_BVH=lbvh in the environment selects the plain Morton hierarchy (for A/B measurements)
     DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
 

@@ -17,6 +17,7 @@
 // * The traversal stack lives in shared memory (STACK_SMEM entries per thread, column layout so that a warp's accesses
 //   hit 32 different banks); deeper paths spill to a per-thread local array.
 #pragma once
+#include <cfloat>
 #include "bpt_context.h"
 #include "bpt_math.cuh"
 
@@ -149,6 +150,7 @@ struct TraversalStack {
 
 struct AccelView {
     const BvhNode* __restrict__ nodes;
+    const WideNode* __restrict__ wide; // four-wide nodes; nullptr = traverse the binary nodes
     const TraceTriangle* __restrict__ triangles;
     const Material* __restrict__ materials; // with `textures`: only read by any-hit rays that meet a coverage-textured material
     TextureView textures;
@@ -173,6 +175,7 @@ BPT_HD int traversal_min_active_for(long long triangle_count) { return triangle_
 inline AccelView accel_view(const Context* ctx) {
     AccelView a;
     a.nodes = ctx->accel.nodes.ptr; a.triangles = ctx->accel.triangles.ptr;
+    a.wide = ctx->accel.wide_levels > 0 ? ctx->accel.wide_nodes.ptr : nullptr;
     a.materials = ctx->materials.ptr;
     a.textures.objects = ctx->texture_objects.ptr;
     a.textures.uv = ctx->accel.has_uv ? ctx->accel.shade_uv.ptr : nullptr;
@@ -256,6 +259,37 @@ struct Traversal {
             node = stack.pop();
     }
 
+    // One visit of a four-wide node: tests the four children, continues with the nearest one that is hit and defers the
+    // others, farthest first, so that they come off the stack nearest first.
+    BPT_D void wide_step(const AccelView& a) {
+#ifdef BPT_TRAVERSAL_STATS
+        ++stat_nodes;
+#endif
+        const float4* n = reinterpret_cast<const float4*>(a.wide + node);
+        const float4 lox = ldg4(n), loy = ldg4(n + 1), loz = ldg4(n + 2), hix = ldg4(n + 3), hiy = ldg4(n + 4), hiz = ldg4(n + 5);
+        const int4 links = __ldg(reinterpret_cast<const int4*>(n + 6));
+        float t0, t1, t2, t3;
+        const bool h0 = slab(f3(lox.x, loy.x, loz.x), f3(hix.x, hiy.x, hiz.x), ray.origin, inv_d, ray.tmin, tmax, t0);
+        const bool h1 = slab(f3(lox.y, loy.y, loz.y), f3(hix.y, hiy.y, hiz.y), ray.origin, inv_d, ray.tmin, tmax, t1);
+        const bool h2 = slab(f3(lox.z, loy.z, loz.z), f3(hix.z, hiy.z, hiz.z), ray.origin, inv_d, ray.tmin, tmax, t2);
+        const bool h3 = slab(f3(lox.w, loy.w, loz.w), f3(hix.w, hiy.w, hiz.w), ray.origin, inv_d, ray.tmin, tmax, t3);
+        const int hits = int(h0) + int(h1) + int(h2) + int(h3);
+        if (hits == 0) { node = stack.pop(); return; }
+        // children that are missed sort to the end
+        t0 = h0 ? t0 : FLT_MAX; t1 = h1 ? t1 : FLT_MAX; t2 = h2 ? t2 : FLT_MAX; t3 = h3 ? t3 : FLT_MAX;
+        int l0 = links.x, l1 = links.y, l2 = links.z, l3 = links.w;
+        if (hits > 1) { // sorting network for four keys: (0,1) (2,3) (0,2) (1,3) (1,2)
+#define BPT_CSWAP(ta, la, tb, lb) { bool s = tb < ta; float tt = s ? tb : ta; tb = s ? ta : tb; ta = tt; int ll = s ? lb : la; lb = s ? la : lb; la = ll; }
+            BPT_CSWAP(t0, l0, t1, l1) BPT_CSWAP(t2, l2, t3, l3) BPT_CSWAP(t0, l0, t2, l2) BPT_CSWAP(t1, l1, t3, l3) BPT_CSWAP(t1, l1, t2, l2)
+#undef BPT_CSWAP
+            if (hits > 3) stack.push(l3);
+            if (hits > 2) stack.push(l2);
+            stack.push(l1);
+            node = l0;
+        } else
+            node = h0 ? l0 : (h1 ? l1 : (h2 ? l2 : l3));
+    }
+
     // Intersects the triangles of one leaf. Returns false when an any-hit ray got blocked (traversal is over).
     BPT_D bool intersect_leaf(const AccelView& a, const float* __restrict__ coverage_by_material, int leaf) {
         const int first = leaf_first(leaf), count = leaf_count(leaf);
@@ -293,7 +327,7 @@ struct Traversal {
     BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget, int min_active = 0) {
         while ((node != NODE_EMPTY || postponed != NODE_EMPTY) && budget > 0) {
             while (node >= 0 && budget > 0) {
-                inner_step(a);
+                if (a.wide != nullptr) wide_step(a); else inner_step(a);
                 --budget;
                 if (postponed == NODE_EMPTY && is_leaf(node)) { postponed = node; node = stack.pop(); }
                 const unsigned int active = __activemask();
