@@ -1,7 +1,9 @@
-// Ray traversal of the two-wide BVH: closest hit and any hit. Replaces OptiX' proprietary Trbvh/RTX traversal that the
+// Ray traversal of the BVH (four-wide nodes, binary fallback): closest hit and any hit. Replaces OptiX' proprietary Trbvh/RTX traversal that the
 // reference configures at Renderer.cpp:116-135,161-182,470-477 and queries with rtTrace (SimpleRGPs.cu:114-125).
 //
-// * Nodes are 64 bytes and hold both children's boxes: one node visit = four 128-bit loads.
+// * Nodes are four wide (128 bytes, child boxes stored per axis: one visit = seven 128-bit loads, four slab tests and a
+//   five-comparator sort of the hit children); the 64-byte binary nodes they are collapsed from remain as the fallback for
+//   hierarchies too deep for the stack.
 // * Triangles are 48 bytes (three float4 world-space vertices) in Morton order: three 128-bit loads.
 // * The ray/triangle test is the watertight test of Woop, Benthin and Wald (JCGT 2013): shear to ray space, 2D edge
 //   functions with an fp64 fallback when an edge function is exactly zero. It is evaluated with explicitly rounded
@@ -165,10 +167,10 @@ struct AccelView {
 #endif
 BPT_HD int traversal_budget_for(long long triangle_count) { return triangle_count > 8000000ll ? BPT_BUDGET_LARGE : BPT_BUDGET_SMALL; }
 // A round also ends once fewer than this many lanes of the warp are still traversing (measured on B200: +4 % on the 20 k
-// and 1 M triangle scenes with 12 lanes; +2 % on the 50 M triangle scene with 8). With this trigger in place the node
+// and 1 M triangle scenes with 12 lanes; +3 % on the 50 M triangle scene with 4). With this trigger in place the node
 // budget is only a backstop, and larger budgets (48 / 96) measured 1-3 % faster than 24 / 48.
 #ifndef BPT_MIN_ACTIVE_LANES_LARGE
-#define BPT_MIN_ACTIVE_LANES_LARGE 8
+#define BPT_MIN_ACTIVE_LANES_LARGE 4
 #endif
 BPT_HD int traversal_min_active_for(long long triangle_count) { return triangle_count > 8000000ll ? BPT_MIN_ACTIVE_LANES_LARGE : BPT_MIN_ACTIVE_LANES; }
 
