@@ -9,6 +9,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/block/block_scan.cuh>
 
 #include <algorithm>
 #include <float.h>
@@ -363,8 +364,69 @@ __global__ void ploc_compact_kernel(int m, const uint32_t* __restrict__ keep, co
     link_out[c] = link_in[i]; box_out[c] = box_in[i]; depth_out[c] = depth_in[i];
 }
 
-// The traversal enters at node 0: move the root there (no link points at the root, so its old slot just stays unused).
-__global__ void ploc_root_kernel(const int* __restrict__ cl_link, BvhNode* __restrict__ nodes) { nodes[0] = nodes[cl_link[0]]; }
+// The last PLOC_TAIL clusters finish inside one block: the same search / merge / compact passes as above on shared memory,
+// without a kernel launch and a host round trip per pass (the top of the tree takes ~50 passes that merge a few pairs each).
+constexpr int PLOC_TAIL = 1024;
+
+__global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int m, const int* __restrict__ cl_link, const Aabb* __restrict__ cl_box, const int* __restrict__ cl_depth,
+                                                              BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
+    __shared__ Aabb s_box[PLOC_TAIL];
+    __shared__ int s_link[PLOC_TAIL], s_depth[PLOC_TAIL], s_nearest[PLOC_TAIL];
+    typedef cub::BlockScan<int, PLOC_TAIL> BlockScan;
+    __shared__ typename BlockScan::TempStorage scan_storage;
+    const int i = threadIdx.x;
+    if (i < m) { s_box[i] = cl_box[i]; s_link[i] = cl_link[i]; s_depth[i] = cl_depth[i]; }
+    int count = m;
+    __syncthreads();
+    while (count > 1) {
+        if (i < count) {
+            const Aabb mine = s_box[i];
+            float best = FLT_MAX; int best_j = -1, best_rank = 0x7fffffff;
+            const int lo = max(0, i - PLOC_RADIUS), hi = min(count - 1, i + PLOC_RADIUS);
+            for (int j = lo; j <= hi; ++j) {
+                if (j == i) continue;
+                float a = union_area(mine, s_box[j]);
+                int rank = (j == (i ^ 1)) ? 0 : 2 * abs(j - i) + (j > i ? 1 : 0);
+                if (a < best || (a == best && rank < best_rank)) { best = a; best_j = j; best_rank = rank; }
+            }
+            s_nearest[i] = best_j;
+        }
+        __syncthreads();
+        int keep = 0, link = 0, depth = 0;
+        Aabb box = {};
+        if (i < count) {
+            const int j = s_nearest[i];
+            const bool mutual = s_nearest[j] == i;
+            box = s_box[i]; link = s_link[i]; depth = s_depth[i];
+            keep = (!mutual || i < j) ? 1 : 0;
+            if (mutual && i < j) {
+                const Aabb other = s_box[j];
+                const int index = atomicAdd(node_counter, 1);
+                BvhNode out;
+                out.lo_l_hi_l_x = make_float4(box.lo.x, box.lo.y, box.lo.z, box.hi.x);
+                out.hi_l_lo_r = make_float4(box.hi.y, box.hi.z, other.lo.x, other.lo.y);
+                out.lo_r_hi_r = make_float4(other.lo.z, other.hi.x, other.hi.y, other.hi.z);
+                out.left = link; out.right = s_link[j]; out.pad0 = 0; out.pad1 = 0;
+                nodes[index] = out;
+                box.lo = min3(box.lo, other.lo); box.hi = max3(box.hi, other.hi);
+                depth = max(depth, s_depth[j]) + 1;
+                link = index;
+                atomicMax(max_depth, depth);
+            }
+        }
+        int position, total;
+        BlockScan(scan_storage).ExclusiveSum(keep, position, total);
+        __syncthreads(); // every read of the old cluster list is done
+        if (keep) { s_box[position] = box; s_link[position] = link; s_depth[position] = depth; }
+        count = total;
+        __syncthreads();
+    }
+    if (i == 0) {
+        __threadfence();
+        nodes[0] = nodes[s_link[0]]; // the traversal enters at node 0
+    }
+}
+
 
 // ---- four-wide collapse ---------------------------------------------------------------------------------------------
 // Top down over the finished binary hierarchy: a wide node starts from a binary node's two children and twice replaces the
@@ -597,7 +659,7 @@ int build_accel(Context* ctx) {
                 ctx->counters.kernel_launches++;
                 int cur = 0, passes = 0;
                 bool failed = false;
-                while (m > 1) {
+                while (m > PLOC_TAIL) {
                     ploc_nearest_kernel<<<full_grid(m), block, 0, st>>>(m, d_box[cur].ptr, d_nearest.ptr);
                     ploc_merge_kernel<<<full_grid(m), block, 0, st>>>(m, d_nearest.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, d_flag.ptr, A.nodes.ptr,
                                                                      d_scalars.ptr, d_scalars.ptr + 1);
@@ -612,11 +674,13 @@ int build_accel(Context* ctx) {
                     if (next_m >= m || ++passes > 4096) { failed = true; break; } // cannot happen: the globally closest pair is always mutual
                     m = next_m; cur ^= 1;
                 }
+                if (!failed) {
+                    ploc_tail_kernel<<<1, PLOC_TAIL, 0, st>>>(m, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, A.nodes.ptr, d_scalars.ptr, d_scalars.ptr + 1);
+                    ctx->counters.kernel_launches++;
+                }
                 PLOC_CHECK(cudaMemcpyAsync(h_scalars, d_scalars.ptr, sizeof(h_scalars), cudaMemcpyDeviceToHost, st));
                 PLOC_CHECK(cudaStreamSynchronize(st));
                 if (!failed && h_scalars[1] <= PLOC_MAX_DEPTH) {
-                    ploc_root_kernel<<<1, 1, 0, st>>>(d_link[cur].ptr, A.nodes.ptr);
-                    ctx->counters.kernel_launches++;
                     A.node_count = h_scalars[0];
                     A.ploc_passes = passes; A.ploc_depth = h_scalars[1];
                     ploc_done = true;
