@@ -569,7 +569,9 @@ int build_accel(Context* ctx) {
     // PLOC scratch
     DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
     DeviceBuffer<unsigned char> d_scan_temp;
+    DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four-wide collapse
     auto release_all = [&]() {
+        d_tasks[0].release(); d_tasks[1].release(); d_counters.release();
         d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release();
         for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); }
         d_records.release(); d_bounds.release();
@@ -605,6 +607,21 @@ int build_accel(Context* ctx) {
         BUILD_CHECK(d_scan_temp.resize(std::max<size_t>(scan_bytes, 1)));
     }
     BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
+    // every scratch buffer is allocated here, outside the timed region (cudaMalloc / cudaFree of gigabytes take tens of ms)
+    size_t temp_bytes = 0;
+    if (n > 0) {
+        BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
+        cub::DoubleBuffer<uint64_t> keys(d_keys.ptr, d_keys_alt.ptr);
+        cub::DoubleBuffer<uint32_t> vals(d_vals.ptr, d_vals_alt.ptr);
+        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, n, 0, 63, st));
+        BUILD_CHECK(d_temp.resize(std::max<size_t>(temp_bytes, 1)));
+        BUILD_CHECK(d_tree.resize(std::max(n - 1, 1))); BUILD_CHECK(d_parent_internal.resize(std::max(n - 1, 1)));
+        BUILD_CHECK(d_parent_leaf.resize(n)); BUILD_CHECK(d_arrival.resize(std::max(n - 1, 1))); BUILD_CHECK(d_node_boxes.resize(std::max(n - 1, 1)));
+    }
+    if (ctx->use_wide) { // worst case: as many wide nodes and tasks as binary nodes; trimmed after the build
+        BUILD_CHECK(A.wide_nodes.resize((size_t)n + 1)); BUILD_CHECK(d_tasks[0].resize((size_t)n + 1)); BUILD_CHECK(d_tasks[1].resize((size_t)n + 1));
+        BUILD_CHECK(d_counters.resize(2));
+    }
 
     BUILD_CHECK(cudaEventRecord(ctx->ev[0], st));
     const int block = 256;
@@ -615,20 +632,14 @@ int build_accel(Context* ctx) {
         flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, A.world_vertices.ptr, A.shade.ptr,
                                                   A.has_uv ? A.shade_uv.ptr : nullptr, d_bounds.ptr);
         ctx->counters.kernel_launches++;
-        BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
         morton_kernel<<<grid(n), block, 0, st>>>(n, A.world_vertices.ptr, d_bounds.ptr, d_keys.ptr, d_vals.ptr);
         ctx->counters.kernel_launches++;
 
         cub::DoubleBuffer<uint64_t> keys(d_keys.ptr, d_keys_alt.ptr);
         cub::DoubleBuffer<uint32_t> vals(d_vals.ptr, d_vals_alt.ptr);
-        size_t temp_bytes = 0;
-        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, n, 0, 63, st));
-        BUILD_CHECK(d_temp.resize(std::max<size_t>(temp_bytes, 1)));
         BUILD_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.ptr, temp_bytes, keys, vals, n, 0, 63, st));
         ctx->counters.kernel_launches += 8;
 
-        BUILD_CHECK(d_tree.resize(std::max(n - 1, 1))); BUILD_CHECK(d_parent_internal.resize(std::max(n - 1, 1)));
-        BUILD_CHECK(d_parent_leaf.resize(n)); BUILD_CHECK(d_arrival.resize(std::max(n - 1, 1))); BUILD_CHECK(d_node_boxes.resize(std::max(n - 1, 1)));
         BUILD_CHECK(cudaMemsetAsync(d_arrival.ptr, 0, sizeof(int) * std::max(n - 1, 1), st));
         if (n > 1) {
             hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, keys.Current(), d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
@@ -672,6 +683,7 @@ int build_accel(Context* ctx) {
                     ctx->counters.kernel_launches += 4;
                     int next_m = int(last_pos + last_flag);
                     if (next_m >= m || ++passes > 4096) { failed = true; break; } // cannot happen: the globally closest pair is always mutual
+                    if (getenv("BPT_PLOC_DEBUG")) fprintf(stderr, "ploc pass %d: %d -> %d clusters\n", passes, m, next_m);
                     m = next_m; cur ^= 1;
                 }
                 if (!failed) {
@@ -702,12 +714,7 @@ int build_accel(Context* ctx) {
     // ---- four-wide collapse of whichever binary hierarchy was built ----
     A.wide_levels = 0; A.wide_node_count = 0;
     if (ctx->use_wide) {
-        const size_t binary_nodes = (size_t)std::max<int64_t>(A.node_count, 1) + 1;
-        DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters;
-        auto release_wide = [&]() { d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); };
-#define WIDE_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { release_wide(); release_all(); return ctx->cuda_fail(_e, #expr); } } while (0)
-        WIDE_CHECK(A.wide_nodes.resize(binary_nodes)); WIDE_CHECK(d_tasks[0].resize(binary_nodes)); WIDE_CHECK(d_tasks[1].resize(binary_nodes));
-        WIDE_CHECK(d_counters.resize(2));
+#define WIDE_CHECK(expr) BUILD_CHECK(expr)
         WideTask root = { 0, 0 };
         WIDE_CHECK(cudaMemcpyAsync(d_tasks[0].ptr, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         int h_counters[2] = { 0, 1 }; // tasks of the next level, wide nodes allocated (the root is node 0)
@@ -721,7 +728,6 @@ int build_accel(Context* ctx) {
             WIDE_CHECK(cudaStreamSynchronize(st));
             count = h_counters[0]; cur ^= 1; ++levels;
         }
-        release_wide();
 #undef WIDE_CHECK
         // a ray pushes at most three links per level: fall back to the binary nodes if that could overflow the stack
         if (3 * levels + 1 <= STACK_SMEM + STACK_LOCAL) { A.wide_levels = levels; A.wide_node_count = h_counters[1]; }
@@ -731,6 +737,21 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&A.build_ms, ctx->ev[0], ctx->ev[1]);
     release_all();
+    // Give back the worst-case slack of the node arrays when it is large (outside the timed region).
+    auto trim = [&](auto& buffer, size_t used) -> cudaError_t {
+        typedef typename std::remove_reference<decltype(*buffer.ptr)>::type T;
+        if (buffer.capacity < used + (64u << 20) / sizeof(T)) return cudaSuccess;
+        T* exact = nullptr;
+        cudaError_t e = cudaMalloc((void**)&exact, std::max<size_t>(used, 1) * sizeof(T));
+        if (e != cudaSuccess) return cudaSuccess; // keep the larger allocation
+        e = cudaMemcpy(exact, buffer.ptr, used * sizeof(T), cudaMemcpyDeviceToDevice);
+        cudaFree(buffer.ptr);
+        buffer.ptr = exact; buffer.capacity = buffer.size = std::max<size_t>(used, 1);
+        return e;
+    };
+    BUILD_CHECK(trim(A.nodes, (size_t)A.node_count + 1));
+    if (A.wide_levels > 0) BUILD_CHECK(trim(A.wide_nodes, (size_t)A.wide_node_count));
+    else A.wide_nodes.release();
 #undef BUILD_CHECK
 
     A.triangle_count = n;
