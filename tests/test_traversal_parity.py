@@ -138,3 +138,23 @@ def test_empty_scene_misses_everything(bpt):
     o, d = random_rays(1000, 1)
     p, t, _, occ = bpt.intersect(o, d)
     assert (p == -1).all() and np.isinf(t).all() and (occ == 0).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variable,value", [("BPT_WIDE", "0"), ("BPT_BVH", "lbvh")])
+def test_every_hierarchy_returns_the_same_hits(bpt, variable, value, monkeypatch):
+    """The four-wide PLOC hierarchy (default), its binary form (BPT_WIDE=0: the fallback for trees too deep for the stack)
+    and the plain Morton hierarchy (BPT_BVH=lbvh: the fallback when PLOC gives up) must return identical hits: the result
+    is defined by min (t, primitive id), not by the traversal order."""
+    scene = soup_scene(20000, 11, size=0.08)
+    o, d = random_rays(60000, 12)
+    scenes.upload(bpt, scene)
+    want = bpt.intersect(o, d)
+    monkeypatch.setenv(variable, value)
+    other = capi.Bpt(0)
+    scenes.upload(other, scene)
+    got = other.intersect(o, d)
+    other.close()
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+    assert (want[0] >= 0).mean() > 0.2
