@@ -64,7 +64,7 @@ assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SA
 
 LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
 
-EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_remove_mesh", "bpt_set_instances",
+EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_mesh_emission", "bpt_remove_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
@@ -128,6 +128,7 @@ def load_library():
     lib.bpt_destroy_texture.argtypes = [vp, i32]
     lib.bpt_texture_sample.argtypes = [vp, i32, i64, vp, vp]
     lib.bpt_upload_mesh.argtypes = [vp, i32, vp, i32, vp, vp, vp, vp, i32]
+    lib.bpt_set_mesh_emission.argtypes = [vp, i32, vp, i32]
     lib.bpt_remove_mesh.argtypes = [vp, i32]
     lib.bpt_set_instances.argtypes = [vp, vp, i32]
     lib.bpt_set_materials.argtypes = [vp, vp, i32]
@@ -256,6 +257,10 @@ class Bpt:
         out = np.empty((uv.shape[0], 4), np.float32)
         self._check(self.lib.bpt_texture_sample(self.h, int(texture_id), uv.shape[0], _ptr(uv), _ptr(out)))
         return out
+
+    def set_mesh_emission(self, mesh_id, emission):
+        e = None if emission is None else _f32(emission).reshape(-1, 3)
+        self._check(self.lib.bpt_set_mesh_emission(self.h, int(mesh_id), _ptr(e), 0 if e is None else e.shape[0]))
 
     def remove_mesh(self, mesh_id):
         self._check(self.lib.bpt_remove_mesh(self.h, int(mesh_id)))

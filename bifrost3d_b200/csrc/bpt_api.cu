@@ -380,7 +380,7 @@ void bpt_destroy(bpt_ctx* c) {
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
     for (auto& kv : ctx->meshes) kv.second.release();
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
-    ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release();
+    ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release(); ctx->accel.shade_emission.release();
     ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
     if (ctx->copy_stream) {
@@ -546,7 +546,7 @@ int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primit
     m.primitive_count = primitive_count; m.vertex_count = vertex_count;
     BPT_CUDA_CHECK(ctx, upload(ctx, m.indices, indices, 3ull * primitive_count));
     BPT_CUDA_CHECK(ctx, upload(ctx, m.positions, positions, 3ull * vertex_count));
-    m.normals.release(); m.texcoords.release(); m.tints.release();
+    m.normals.release(); m.texcoords.release(); m.tints.release(); m.emission.release();
     std::vector<int16_t> encoded_normals;
     if (normals) {
         encoded_normals.resize(2ull * vertex_count);
@@ -556,6 +556,22 @@ int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primit
     if (texcoords) BPT_CUDA_CHECK(ctx, upload(ctx, m.texcoords, texcoords, 2ull * vertex_count));
     if (tint_roughness) BPT_CUDA_CHECK(ctx, upload(ctx, m.tints, tint_roughness, 4ull * vertex_count));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // the caller's arrays (and encoded_normals) may go away
+    ctx->accel.valid = false;
+    return BPT_OK;
+}
+
+int bpt_set_mesh_emission(bpt_ctx* c, int mesh_id, const float* emission, int vertex_count) {
+    Context* ctx = as_context(c);
+    auto it = ctx->meshes.find(mesh_id);
+    if (it == ctx->meshes.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_mesh_emission: unknown mesh id");
+    if (emission && vertex_count != it->second.vertex_count)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_mesh_emission: vertex count differs from the mesh");
+    cudaSetDevice(ctx->device);
+    if (emission) {
+        BPT_CUDA_CHECK(ctx, upload(ctx, it->second.emission, emission, 3ull * vertex_count));
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    } else
+        it->second.emission.release();
     ctx->accel.valid = false;
     return BPT_OK;
 }

@@ -27,13 +27,14 @@ struct InstanceRecord {
     int prim_offset;   // first global primitive index
     int prim_count;
     int material;
-    uint32_t flags;    // bit0: has normals, bit1: has tints, bit2: has texcoords
+    uint32_t flags;    // bit0: has normals, bit1: has tints, bit2: has texcoords, bit3: has emission
     // the instance's mesh, resident on the device since bpt_upload_mesh
     const uint32_t* indices;
     const float* positions;
     const int16_t* normals;
     const uint8_t* tints;
     const float2* texcoords;
+    const float* emission;
     float m[12];       // object -> world, row-major 3x4
 };
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v) {
 // One thread per global primitive: world-space vertices, shading record, centroid bounds.
 __global__ void flatten_kernel(int64_t prim_total, int instance_count, const InstanceRecord* __restrict__ instances,
                                float4* __restrict__ world_vertices, ShadeTriangle* __restrict__ shade, float2* __restrict__ shade_uv,
-                               float* scene_bounds /*[6]*/) {
+                               float* __restrict__ shade_emission, float* scene_bounds /*[6]*/) {
     float3 lo = f3(FLT_MAX), hi = f3(-FLT_MAX);
     for (int64_t gp = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; gp < prim_total; gp += (int64_t)gridDim.x * blockDim.x) {
         // binary search: last instance with prim_offset <= gp
@@ -100,6 +101,14 @@ __global__ void flatten_kernel(int64_t prim_total, int instance_count, const Ins
             shade_uv[3 * gp] = has_uv ? texcoords[i0] : zero;
             shade_uv[3 * gp + 1] = has_uv ? texcoords[i1] : zero;
             shade_uv[3 * gp + 2] = has_uv ? texcoords[i2] : zero;
+        }
+
+        if (shade_emission != nullptr) { // TriangleAttributes.cu:78-83; meshes without the buffer scale by 1
+            const bool has_emission = inst.flags & 8u;
+            const uint32_t vertex[3] = { i0, i1, i2 };
+            for (int k = 0; k < 3; ++k)
+                for (int ch = 0; ch < 3; ++ch)
+                    shade_emission[9 * gp + 3 * k + ch] = has_emission ? inst.emission[3ll * vertex[k] + ch] : 1.0f;
         }
 
         float3 c = (min3(min3(p0, p1), p2) + max3(max3(p0, p1), p2)) * 0.5f;
@@ -533,6 +542,8 @@ int build_accel(Context* ctx) {
     bool any_texcoords = false;
     if (ctx->has_textured_materials)
         for (const bpt_instance& inst : ctx->instances) any_texcoords |= ctx->meshes[inst.mesh_id].texcoords.size != 0;
+    bool any_emission = false;
+    for (const bpt_instance& inst : ctx->instances) any_emission |= ctx->meshes[inst.mesh_id].emission.size != 0;
     int64_t prim_total = 0;
     for (const bpt_instance& inst : ctx->instances) {
         const DeviceMesh& mesh = ctx->meshes[inst.mesh_id];
@@ -542,9 +553,9 @@ int build_accel(Context* ctx) {
         InstanceRecord r = {};
         r.prim_offset = int(prim_total); r.prim_count = mesh.primitive_count;
         r.material = inst.material_id;
-        r.flags = (mesh.normals.size ? 1u : 0u) | (mesh.tints.size ? 2u : 0u) | ((any_texcoords && mesh.texcoords.size) ? 4u : 0u);
+        r.flags = (mesh.normals.size ? 1u : 0u) | (mesh.tints.size ? 2u : 0u) | ((any_texcoords && mesh.texcoords.size) ? 4u : 0u) | (mesh.emission.size ? 8u : 0u);
         r.indices = mesh.indices.ptr; r.positions = mesh.positions.ptr; r.normals = mesh.normals.ptr; r.tints = mesh.tints.ptr;
-        r.texcoords = reinterpret_cast<const float2*>(mesh.texcoords.ptr);
+        r.texcoords = reinterpret_cast<const float2*>(mesh.texcoords.ptr); r.emission = mesh.emission.ptr;
         memcpy(r.m, inst.to_world, sizeof(r.m));
         records.push_back(r);
         { // normal matrix = inverse transpose of the upper 3x3 (rtTransformNormal, MonteCarlo.cu:147,176), in double
@@ -595,6 +606,8 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(A.shade.resize(std::max<size_t>(n, 1)));
     A.has_uv = any_texcoords && n > 0;
     if (A.has_uv) BUILD_CHECK(A.shade_uv.resize(3ull * n)); else A.shade_uv.release();
+    A.has_emission = any_emission && n > 0;
+    if (A.has_emission) BUILD_CHECK(A.shade_emission.resize(9ull * n)); else A.shade_emission.release();
     BUILD_CHECK(A.triangles.resize(std::max<size_t>(n, 1)));
     BUILD_CHECK(A.nodes.resize((size_t)n + 1));
     // PLOC scratch is sized for the worst case of one cluster per triangle and allocated outside the timed region.
@@ -630,7 +643,7 @@ int build_accel(Context* ctx) {
 
     if (n > 0) {
         flatten_kernel<<<grid(n), block, 0, st>>>(n, (int)records.size(), d_records.ptr, A.world_vertices.ptr, A.shade.ptr,
-                                                  A.has_uv ? A.shade_uv.ptr : nullptr, d_bounds.ptr);
+                                                  A.has_uv ? A.shade_uv.ptr : nullptr, A.has_emission ? A.shade_emission.ptr : nullptr, d_bounds.ptr);
         ctx->counters.kernel_launches++;
         morton_kernel<<<grid(n), block, 0, st>>>(n, A.world_vertices.ptr, d_bounds.ptr, d_keys.ptr, d_vals.ptr);
         ctx->counters.kernel_launches++;

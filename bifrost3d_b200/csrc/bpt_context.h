@@ -40,9 +40,10 @@ struct DeviceMesh {
     DeviceBuffer<int16_t> normals;   // 2 per vertex (octahedral); empty if the mesh has none
     DeviceBuffer<float> texcoords;   // 2 per vertex or empty
     DeviceBuffer<uint8_t> tints;     // 4 per vertex or empty
+    DeviceBuffer<float> emission;    // 3 per vertex or empty
     int primitive_count = 0;
     int vertex_count = 0;
-    void release() { indices.release(); positions.release(); normals.release(); texcoords.release(); tints.release(); primitive_count = vertex_count = 0; }
+    void release() { indices.release(); positions.release(); normals.release(); texcoords.release(); tints.release(); emission.release(); primitive_count = vertex_count = 0; }
 };
 
 // BVH node, 64 bytes, two children per node: the child AABBs are stored in the parent so one 64 byte (4 x 128-bit)
@@ -101,6 +102,8 @@ struct Accel {
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
     DeviceBuffer<float2> shade_uv;              // 3 texcoords per primitive, instance-major order; only when a mesh has texcoords
     bool has_uv = false;
+    DeviceBuffer<float> shade_emission;         // 9 floats per primitive (per-vertex emission scale); only when a mesh has emission
+    bool has_emission = false;
     DeviceBuffer<float> normal_matrices;        // 9 floats per instance record: inverse transpose of the upper 3x3
     int64_t triangle_count = 0;
     int64_t node_count = 0;

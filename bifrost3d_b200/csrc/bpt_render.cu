@@ -68,6 +68,7 @@ struct SceneView {
     const float4* __restrict__ world_vertices;
     const ShadeTriangle* __restrict__ shade;
     const float* __restrict__ normal_matrices;
+    const float* __restrict__ shade_emission; // 9 floats per primitive or nullptr (scale 1)
     const Material* __restrict__ materials;
     const float* __restrict__ coverage;
     const Light* __restrict__ lights;
@@ -449,7 +450,12 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                                 : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
                     }();
 
-                    radiance += throughput * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
+                    float3 emission = f3(1.0f); // multiplicative identity, TriangleAttributes.cu:83
+                    if (s.shade_emission != nullptr) { // per-vertex emission scale, TriangleAttributes.cu:78-81
+                        const float* e = s.shade_emission + 9ll * primitive;
+                        emission = f3(e[3], e[4], e[5]) * bx + f3(e[6], e[7], e[8]) * by + f3(e[0], e[1], e[2]) * bz;
+                    }
+                    radiance += throughput * emission * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
 
                     // reestimated_light_samples, MonteCarlo.cu:91-123
                     LightSample light_sample = light_sample_none();
@@ -639,6 +645,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     s.world_vertices = ctx->accel.world_vertices.ptr;
     s.shade = ctx->accel.shade.ptr;
     s.normal_matrices = ctx->accel.normal_matrices.ptr;
+    s.shade_emission = ctx->accel.has_emission ? ctx->accel.shade_emission.ptr : nullptr;
     s.materials = ctx->materials.ptr;
     s.coverage = wf->coverage.ptr;
     s.lights = ctx->lights.ptr;

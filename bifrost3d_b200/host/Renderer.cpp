@@ -231,6 +231,9 @@ struct Renderer::Implementation {
                                          (const float*)Meshes::get_texcoords(mesh_ID), (const uint8_t*)Meshes::get_tint_and_roughness(mesh_ID),
                                          int(Meshes::get_vertex_count(mesh_ID)));
             check(ctx, status, "bpt_upload_mesh");
+            if (status == BPT_OK && Meshes::get_emission(mesh_ID) != nullptr) // MeshFlag::Emissive, Renderer.cpp:114,131,154
+                check(ctx, bpt_set_mesh_emission(ctx, int(mesh_ID.get_index()), (const float*)Meshes::get_emission(mesh_ID), int(Meshes::get_vertex_count(mesh_ID))),
+                      "bpt_set_mesh_emission");
             uploaded_meshes[mesh_ID] = status == BPT_OK;
             changed = true;
         }

@@ -271,6 +271,8 @@ def upload(ctx, scene):
                            tex.get("linear", True))
     for mesh_id, m in scene["meshes"].items():
         ctx.upload_mesh(mesh_id, m["indices"], m["positions"], m.get("normals"), m.get("texcoords"), m.get("tints"))
+        if m.get("emission") is not None:
+            ctx.set_mesh_emission(mesh_id, m["emission"])
     ctx.set_materials(scene["materials"])
     ctx.set_instances(scene["instances"])
     ctx.set_lights(scene["lights"])

@@ -162,6 +162,9 @@ int bpt_texture_sample(bpt_ctx* ctx, int texture_id, int64_t n, const float* uv,
 int bpt_upload_mesh(bpt_ctx* ctx, int mesh_id, const uint32_t* indices, int primitive_count,
                     const float* positions, const float* normals, const float* texcoords,
                     const uint8_t* tint_roughness, int vertex_count);
+/* Per-vertex emission scale of a mesh (MeshFlag::Emissive, Renderer.cpp:114,131; TriangleAttributes.cu:78-83): 3*vertex_count
+ * floats, interpolated over the triangle and multiplied with the material's emission. nullptr removes it (scale 1). */
+int bpt_set_mesh_emission(bpt_ctx* ctx, int mesh_id, const float* emission, int vertex_count);
 /* Meshes::Change::Destroyed, Renderer.cpp:628-640. Fails while an instance still references the mesh. */
 int bpt_remove_mesh(bpt_ctx* ctx, int mesh_id);
 /* Renderer.cpp:1043-1110 (mesh models) + :1010-1041 (transforms). Replaces all instances. Meshes stay resident on the

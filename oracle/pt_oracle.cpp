@@ -56,6 +56,7 @@ struct Mesh {
     std::vector<uint32_t> indices;
     std::vector<float3> positions;
     std::vector<float2> texcoords;         // empty when the mesh has none
+    std::vector<float3> emission;          // per-vertex emission scale, empty when the mesh has none
     std::vector<OctahedralNormal> normals; // empty when the mesh has none
     std::vector<uchar4> tints;
 };
@@ -65,9 +66,10 @@ struct Triangle {
     OctahedralNormal n0, n1, n2;
     uchar4 t0, t1, t2;
     float2 uv0, uv1, uv2;
+    float3 e0, e1, e2;
     int material;
     int instance;
-    bool has_normals, has_tints, has_texcoords;
+    bool has_normals, has_tints, has_texcoords, has_emission;
 };
 
 // Restatement of the sampler the reference creates for a Bifrost texture (Renderer.cpp:650-751) and reads with rtTex2D
@@ -358,6 +360,8 @@ void flatten(Scene& sc) {
             t.has_normals = !mesh.normals.empty(); t.has_tints = !mesh.tints.empty();
             if (t.has_normals) { t.n0 = mesh.normals[i0]; t.n1 = mesh.normals[i1]; t.n2 = mesh.normals[i2]; }
             if (t.has_tints) { t.t0 = mesh.tints[i0]; t.t1 = mesh.tints[i1]; t.t2 = mesh.tints[i2]; }
+            t.has_emission = !mesh.emission.empty();
+            if (t.has_emission) { t.e0 = mesh.emission[i0]; t.e1 = mesh.emission[i1]; t.e2 = mesh.emission[i2]; }
             t.has_texcoords = !mesh.texcoords.empty();
             if (t.has_texcoords) { t.uv0 = mesh.texcoords[i0]; t.uv1 = mesh.texcoords[i1]; t.uv2 = mesh.texcoords[i2]; }
             t.material = inst.material_id; t.instance = instance_index;
@@ -601,7 +605,9 @@ void triangle_closest_hit(PathState& st, const HitRecord& hit, float3 ray_origin
         tint_and_roughness_scale.w = (tint1.w * barycentrics.x + tint2.w * barycentrics.y + tint0.w * barycentrics_z) * byte_to_float_normalizer;
     } else
         tint_and_roughness_scale = make_float4(1.0f);
-    float3 emission = make_float3(1.0f);
+    float3 emission = make_float3(1.0f); // TriangleAttributes.cu:78-83
+    if (tri.has_emission)
+        emission = tri.e1 * barycentrics.x + tri.e2 * barycentrics.y + tri.e0 * barycentrics_z;
 
     // -- closest hit --
     payload.light_sample = LightSample::none();
@@ -855,6 +861,11 @@ void pto_scene_add_mesh(void* s, int mesh_id, const uint32_t* indices, int primi
         m.tints.resize(vertex_count);
         for (int i = 0; i < vertex_count; ++i) m.tints[i] = make_uchar4(tint_roughness[4 * i], tint_roughness[4 * i + 1], tint_roughness[4 * i + 2], tint_roughness[4 * i + 3]);
     }
+}
+void pto_scene_set_mesh_emission(void* s, int mesh_id, const float* emission, int vertex_count) {
+    Mesh& m = ((Scene*)s)->meshes[mesh_id];
+    m.emission.resize(vertex_count);
+    for (int i = 0; i < vertex_count; ++i) m.emission[i] = make_float3(emission[3 * i], emission[3 * i + 1], emission[3 * i + 2]);
 }
 void pto_scene_set_mesh_texcoords(void* s, int mesh_id, const float* texcoords, int vertex_count) {
     Mesh& m = ((Scene*)s)->meshes[mesh_id];

@@ -11,6 +11,7 @@ void* pto_scene_create(void);
 void pto_scene_destroy(void* scene);
 void pto_scene_add_mesh(void* scene, int mesh_id, const uint32_t* indices, int primitive_count, const float* positions, const float* normals,
                         const uint8_t* tint_roughness, int vertex_count);
+void pto_scene_set_mesh_emission(void* scene, int mesh_id, const float* emission, int vertex_count);
 void pto_scene_set_mesh_texcoords(void* scene, int mesh_id, const float* texcoords, int vertex_count);
 /* pixel_format = BPT_PIXEL_* of include/bpt_c_api.h; the sampler restates the CUDA texture unit's documented arithmetic */
 void pto_scene_add_texture(void* scene, int texture_id, int width, int height, int pixel_format, int is_srgb, int wrap_u, int wrap_v,

@@ -156,6 +156,7 @@ class OracleScene:
         for name in ("pto_scene_set_instances", "pto_scene_set_materials", "pto_scene_set_lights"):
             getattr(lib, name).argtypes = [vp, vp, i32]; getattr(lib, name).restype = None
         lib.pto_scene_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]; lib.pto_scene_set_environment.restype = None
+        lib.pto_scene_set_mesh_emission.argtypes = [vp, i32, vp, i32]; lib.pto_scene_set_mesh_emission.restype = None
         lib.pto_scene_set_mesh_texcoords.argtypes = [vp, i32, vp, i32]; lib.pto_scene_set_mesh_texcoords.restype = None
         lib.pto_scene_add_texture.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]; lib.pto_scene_add_texture.restype = None
         lib.pto_texture_sample.argtypes = [vp, i32, i64, vp, vp]; lib.pto_texture_sample.restype = None
@@ -171,6 +172,9 @@ class OracleScene:
             nrm = None if m.get("normals") is None else _f32(m["normals"])
             tints = None if m.get("tints") is None else np.ascontiguousarray(m["tints"], np.uint8)
             lib.pto_scene_add_mesh(self.h, int(mesh_id), _p(idx), idx.shape[0], _p(pos), _p(nrm), _p(tints), pos.shape[0])
+            if m.get("emission") is not None:
+                em = _f32(m["emission"])
+                lib.pto_scene_set_mesh_emission(self.h, int(mesh_id), _p(em), em.shape[0])
             if m.get("texcoords") is not None:
                 uv = _f32(m["texcoords"])
                 lib.pto_scene_set_mesh_texcoords(self.h, int(mesh_id), _p(uv), uv.shape[0])

@@ -317,3 +317,25 @@ def test_pipelined_frame_readback_equals_the_synchronous_one(bpt):
     assert np.array_equal(frames[0], expected[2]) and np.array_equal(frames[1], expected[3])
     with pytest.raises(capi.BptError, match="slot"):
         bpt.resolve_half4_async(frames[0], 2)
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_per_vertex_emission_matches_oracle(bpt):
+    """MeshFlag::Emissive (TriangleAttributes.cu:78-83): the per-vertex emission scale is interpolated over the triangle and
+    multiplies the material's emission; meshes without the buffer keep scale 1."""
+    scene = scenes.cornell_box(sphere_quads=(16, 8))
+    rng = np.random.default_rng(21)
+    scene["meshes"][1]["emission"] = (rng.random((scene["meshes"][1]["positions"].shape[0], 3)) * 3.0).astype(np.float32)
+    mats = scene["materials"].copy()
+    mats[4]["emission"] = (0.6, 0.5, 0.2)   # sphere mesh (has the buffer)
+    mats[2]["emission"] = (0.2, 0.0, 0.0)   # wall (plane mesh, no buffer)
+    scene["materials"] = mats
+    gpu, cpu, counters, oc = render_both(bpt, scene, 64, 64, 4)
+    e = rel_mse(gpu, cpu)
+    print(f"relMSE {e:.3e}")
+    assert e <= REL_MSE_BOUND and e < 1e-8
+    plain = scenes.cornell_box(sphere_quads=(16, 8)); plain["materials"] = mats
+    scenes.upload(bpt, plain)
+    bpt.render(plain["camera"], 64, 64, 0, 4, reset=True)
+    assert rel_mse(bpt.resolve_float4(), cpu) > 1e-4  # the buffer changes the image
