@@ -10,7 +10,7 @@ python bench.py --steps 16 --warmup 3 --workload terrain --no-cpu-baseline 2>/de
 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > $O/${R}_bench_reference.json
 python tools/bench_bsdf.py 2>/dev/null | tail -1 > $O/${R}_bench_bsdf_tuples.json
 BPT_BVH=lbvh python bench.py --steps 32 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/${R}_bench_materials_lbvh.json
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${R}_launches_materials.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_a.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"generate_kernel|extend_kernel|shade_kernel|shadow_kernel|advance_kernel|accumulate_kernel" -c 600 --csv --log-file $O/${R}_launches_materials.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_a.log 2>&1
 NCU="ncu --set full --clock-control none --import-source on -f"
 $NCU -k regex:extend_kernel -s 6 -c 3 -o $O/prof_${R}_extend_materials python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_c.log 2>&1
 $NCU -k regex:shade_kernel -s 12 -c 4 -o $O/prof_${R}_shade_materials python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_d.log 2>&1
