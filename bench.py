@@ -137,6 +137,8 @@ def run_reference(args):
     if rank != 0:
         return 0
     scene, settings = build_scene(args.workload)
+    if args.russian_roulette:
+        settings["russian_roulette_start"] = args.russian_roulette
     steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
     r = cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=max(2.0, 60.0 / (steps + warmup)))
     line = {"impl": "reference", "metric": "Msamples/s", "value": r["msamples_per_s"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
@@ -153,7 +155,8 @@ def run_reference(args):
 def workload_config(args, scene, settings):
     from bifrost3d_b200 import scenes
     return {"workload": f"{scene['name']}: {scene['width']}x{scene['height']}, {scenes.triangle_count(scene)} triangles, {len(scene['lights'])} light(s), "
-                        f"max_bounce_count {settings['max_bounces']}, next_event_sample_count {settings['nee_samples']}, 1 sample per pixel per step",
+                        f"max_bounce_count {settings['max_bounces']}, next_event_sample_count {settings['nee_samples']}, 1 sample per pixel per step"
+                        + (f", Russian roulette from bounce {settings['russian_roulette_start']} (extension, not in the reference)" if settings.get("russian_roulette_start") else ""),
             "baseline_config": {"cornell": "configs[1] (SmallPT-style Cornell box)", "materials": "configs[2] (material grid + HDR environment, 1080p)", "terrain": "configs[3] (50M-triangle instanced scene, 4K, 8 bounces)"}.get(args.workload, args.workload),
             "l2_policy": "per-step working set (path state + frame buffers) exceeds L2; no explicit flush",
             "parallelism": f"sample-index sharding x{args.gpus}, replicated BVH"}
@@ -167,6 +170,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="materials", help="materials = BASELINE.json configs[2] (1080p, 4 bounces: the configuration the metric is quoted on); cornell = configs[1]; terrain = configs[3]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--russian-roulette", type=int, default=0, metavar="N",
+                    help="opt-in Russian roulette from the N-th surface interaction on (configs[3] names it; 0 = off = the reference's behaviour)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -187,6 +192,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     scene, settings = build_scene(args.workload)
+    if args.russian_roulette:
+        settings["russian_roulette_start"] = args.russian_roulette
     W, H = scene["width"], scene["height"]
     ctx = b.Bpt(local_rank)
     scenes.upload(ctx, scene)
