@@ -144,3 +144,24 @@ def test_texture_aovs_and_errors(bpt):
         desc = capi.TextureDesc(2, 2, 2, 0, 0, 0, 1, 0)  # Intensity8: the reference does not upload it either
         import ctypes
         bpt._check(bpt.lib.bpt_upload_texture(bpt.h, 9, ctypes.byref(desc), np.zeros(4, np.uint8).ctypes.data_as(ctypes.c_void_p)))
+
+
+@pytest.mark.gpu
+def test_first_textured_material_asks_for_a_rebuild(bpt):
+    """An acceleration structure built for untextured materials carries no per-primitive texcoords: the first textured
+    material invalidates it (bpt_set_materials), and after the rebuild the scene renders like one uploaded from scratch."""
+    scene = textured_cornell()
+    plain = dict(scene); plain["materials"] = scenes.cornell_box(sphere_quads=(24, 12))["materials"]
+    scenes.upload(bpt, plain)                      # textures are uploaded, but no material references them yet
+    bpt.render(scene["camera"], 48, 48, 0, 2, reset=True)
+    bpt.set_materials(scene["materials"])
+    with pytest.raises(capi.BptError, match="bpt_build_accel"):
+        bpt.render(scene["camera"], 48, 48, 0, 1)
+    bpt.build_accel()
+    bpt.render(scene["camera"], 48, 48, 0, 2, reset=True)
+    edited = bpt.resolve_float4()
+    fresh = capi.Bpt(0)
+    scenes.upload(fresh, scene)
+    fresh.render(scene["camera"], 48, 48, 0, 2, reset=True)
+    assert np.array_equal(edited, fresh.resolve_float4())
+    fresh.close()
