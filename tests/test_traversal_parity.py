@@ -158,3 +158,50 @@ def test_every_hierarchy_returns_the_same_hits(bpt, variable, value, monkeypatch
     for a, b in zip(got, want):
         assert np.array_equal(a, b)
     assert (want[0] >= 0).mean() > 0.2
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_degenerate_geometry_ties_and_large_coordinates(bpt):
+    """Coincident triangles (exact ties in t resolve to the lower primitive id), zero-area triangles (never hit, must not
+    break the build), identical centroids (equal Morton codes) and a scene 10 km from the origin, bit exact vs brute force."""
+    rng = np.random.default_rng(31)
+    base = scenes.random_triangles(600, 32, extent=1.0, size=0.3)
+    pos = base["positions"].reshape(-1, 3, 3)
+    dup = np.concatenate([pos, pos[:200], pos[:50]])                        # duplicates: ties in t
+    zero = np.repeat(rng.uniform(-1, 1, (100, 1, 3)).astype(np.float32), 3, axis=1)          # three coincident vertices
+    sliver = pos[:100].copy(); sliver[:, 2] = sliver[:, 0] + (sliver[:, 1] - sliver[:, 0]) * 0.5  # collinear vertices
+    same_centroid = np.tile(pos[:1], (64, 1, 1))                              # 64 identical triangles
+    tris = (np.concatenate([dup, zero, sliver, same_centroid]) + np.float32([10000.0, -2500.0, 400.0])).astype(np.float32)
+    mesh = {"indices": np.arange(3 * tris.shape[0], dtype=np.uint32).reshape(-1, 3), "positions": tris.reshape(-1, 3)}
+    mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
+    scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
+             "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
+    scenes.upload(bpt, scene)
+    sc = oracle_lib.OracleScene(scene)
+    o, d = random_rays(60000, 33)
+    o = (o + np.float32([10000.0, -2500.0, 400.0])).astype(np.float32)
+    gp, gt, guv, gocc = bpt.intersect(o, d)
+    rp, rt, ruv, rocc = sc.intersect(o, d, brute=True)
+    assert np.array_equal(gp, rp)
+    hit = rp >= 0
+    assert np.array_equal(gt[hit], rt[hit]) and np.array_equal(guv[hit], ruv[hit]) and np.array_equal(gocc, rocc)
+    assert hit.mean() > 0.2
+    n_dup = pos.shape[0]
+    assert not np.isin(rp, np.arange(n_dup, n_dup + 250)).any()            # a duplicate never wins against its lower-id twin
+    sc.close()
+
+
+@pytest.mark.gpu
+def test_odd_frame_sizes_and_dark_scene(bpt):
+    """Frames that are not a multiple of the warp size, a 1 x 1 frame, and a scene without any light (every path dies black)."""
+    scene = scenes.cornell_box(sphere_quads=(8, 4))
+    scenes.upload(bpt, scene)
+    for w, h in ((33, 17), (1, 1), (7, 129)):
+        bpt.render(scene["camera"], w, h, 0, 3, reset=True)
+        img = bpt.resolve_float4()
+        assert img.shape == (h, w, 4) and np.isfinite(img).all()
+    dark = dict(scene); dark["lights"] = np.zeros(0, capi.LIGHT_DTYPE)
+    scenes.upload(bpt, dark)
+    bpt.render(dark["camera"], 33, 17, 0, 2, reset=True)
+    assert np.all(bpt.resolve_float4()[..., :3] == 0.0)
