@@ -19,6 +19,10 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 
+#ifndef BPT_TILED_QUEUE
+#define BPT_TILED_QUEUE 1
+#endif
+
 namespace bpt {
 
 namespace {
@@ -112,8 +116,17 @@ __device__ __forceinline__ float4 mul4x4(const float* m, float4 v) {
 
 __global__ void generate_kernel(WavefrontView w, FrameParams f) {
     int64_t pixel_count = (int64_t)f.width * f.height;
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
-        int x = int(p % f.width), y = int(p / f.width);
+    // Queue order: 8 x 4 pixel tiles, one per warp, so that the camera rays (and the first hits) of a warp are neighbours in
+    // both image directions; plain row order when the frame is not a whole number of tiles. Path state stays indexed by pixel.
+    const bool tiled = BPT_TILED_QUEUE && (f.width % 8 == 0) && (f.height % 4 == 0);
+    const int tiles_x = f.width / 8;
+    for (int64_t slot = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; slot < pixel_count; slot += (int64_t)gridDim.x * blockDim.x) {
+        int x, y;
+        if (tiled) {
+            const int64_t tile = slot >> 5; const int lane = int(slot & 31);
+            x = int(tile % tiles_x) * 8 + (lane & 7); y = int(tile / tiles_x) * 4 + (lane >> 3);
+        } else { x = int(slot % f.width); y = int(slot / f.width); }
+        const int64_t p = (int64_t)y * f.width + x;
         unsigned int pixel_hash = pcg2d((unsigned int)x, (unsigned int)y).x;
         float2 jitter = f2(0.5f, 0.5f);
         if (f.accumulation_count != 0) {
@@ -136,7 +149,7 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.ray_d[p] = f4(direction, Pdf::delta_dirac(1.0f).v);
         w.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
         w.rad[p] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-        w.queue_in[p] = (unsigned int)p;
+        w.queue_in[slot] = (unsigned int)p;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         w.counters->active = (unsigned int)pixel_count;
