@@ -310,7 +310,7 @@ BPT_D float3 evaluate(const EnvironmentView& e, float3 direction_to_light) {
 } // namespace environment_light
 
 // ---- dispatch (LightImpl.h:38-108) -------------------------------------------------------------
-BPT_CALL LightSample light_sample_radiance(const Light& light, const EnvironmentView& env, float3 position, float2 u) {
+BPT_CALL1 LightSample light_sample_radiance(const Light& light, const EnvironmentView& env, float3 position, float2 u) {
     switch (light_type(light)) {
     case BPT_LIGHT_SPHERE: return sphere_light::sample_radiance(as_sphere(light), position, u);
     case BPT_LIGHT_DIRECTIONAL: return directional_light::sample_radiance(as_directional(light));

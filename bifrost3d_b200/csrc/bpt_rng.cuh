@@ -95,7 +95,7 @@ BPT_D uint32_t sobol_dim23(int d, uint32_t index) {
     return r;
 }
 
-BPT_CALL uint4 sobol_sample4ui(uint32_t accumulation_count, uint32_t pixel_hash, uint32_t dimension) {
+BPT_CALL1 uint4 sobol_sample4ui(uint32_t accumulation_count, uint32_t pixel_hash, uint32_t dimension) {
     uint32_t seed = pcg2d(pixel_hash, dimension).x;
     uint32_t index = nested_uniform_scramble(accumulation_count, seed);
     uint4 xs;
