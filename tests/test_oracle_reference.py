@@ -114,3 +114,57 @@ def test_golden_fixture_matches_oracle(ref):
     """tests/golden/bsdf_c1_small.npz was generated from this oracle (tests/golden/make_golden.py)."""
     from tests.golden import make_golden
     make_golden.check(ref)
+
+
+# ---- the integrator restatement on its own (CPU only): properties that do not need the GPU -------------------------
+
+def _cornell(**kw):
+    from bifrost3d_b200 import scenes
+    return scenes.cornell_box(sphere_quads=(8, 4), **kw)
+
+
+def test_oracle_russian_roulette_keeps_the_expectation():
+    """The opt-in roulette restated in the oracle is unbiased: same mean image (within Monte Carlo noise), fewer rays."""
+    scene = _cornell()
+    sc = oracle_lib.OracleScene(scene)
+    plain, rays_plain = sc.render(scene["camera"], 24, 24, 0, 256, max_bounces=8)
+    rr, rays_rr = sc.render(scene["camera"], 24, 24, 0, 256, max_bounces=8, russian_roulette_start=2)
+    sc.close()
+    mean_plain = (plain[..., :3] / plain[..., 3:4]).mean(); mean_rr = (rr[..., :3] / rr[..., 3:4]).mean()
+    assert abs(mean_rr / mean_plain - 1.0) < 0.02
+    assert rays_rr[0] < 0.85 * rays_plain[0]
+
+
+def test_oracle_per_vertex_emission_scales_the_material_emission():
+    """TriangleAttributes.cu:78-83: a constant per-vertex emission scale s multiplies the emitted radiance by s."""
+    from bifrost3d_b200 import capi
+    scene = _cornell()
+    scene["lights"] = np.zeros(0, capi.LIGHT_DTYPE)
+    mats = scene["materials"].copy(); mats[4]["emission"] = (0.5, 0.25, 0.125); scene["materials"] = mats
+    images = []
+    for scale in (1.0, 3.0):
+        scene["meshes"][1]["emission"] = np.full((scene["meshes"][1]["positions"].shape[0], 3), scale, np.float32)
+        sc = oracle_lib.OracleScene(scene)
+        accum, _ = sc.render(scene["camera"], 24, 24, 0, 8, max_bounces=1)
+        sc.close()
+        images.append(accum[..., :3] / accum[..., 3:4])
+    assert images[0].max() > 0.1
+    assert np.allclose(images[1], 3.0 * images[0], rtol=1e-5, atol=1e-7)
+
+
+def test_oracle_coverage_texture_controls_visibility():
+    """A cutout texture that is 0 on one half of a quad lets rays through that half only (Material::get_coverage)."""
+    from bifrost3d_b200 import capi, scenes
+    quad = scenes.plane(1)
+    tex = np.zeros((2, 2, 1), np.uint8); tex[:, 1] = 255           # u < 0.5 transparent, u > 0.5 opaque
+    mat = scenes.material((1, 1, 1), 1.0, thin_walled=True); mat["flags"] = 3; mat["coverage"] = 0.5; mat["coverage_texture_id"] = 1
+    scene = {"meshes": {0: quad}, "materials": np.array([scenes.material((0, 0, 0), 0), mat], capi.MATERIAL_DTYPE),
+             "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE), "lights": np.zeros(0, capi.LIGHT_DTYPE),
+             "environment": {"tint": (0, 0, 0)}, "textures": {1: {"pixels": tex, "linear": False, "wrap_u": capi.WRAP_CLAMP, "wrap_v": capi.WRAP_CLAMP}}}
+    sc = oracle_lib.OracleScene(scene)
+    x = np.float32([-0.25, 0.25])                                    # texcoord u = x + 0.5
+    o = np.stack([x, np.full(2, 1.0, np.float32), np.zeros(2, np.float32)], axis=1)
+    d = np.tile(np.float32([0, -1, 0]), (2, 1))
+    _, _, _, occluded = sc.intersect(o, d, brute=True)
+    sc.close()
+    assert list(occluded) == [0, 1]
