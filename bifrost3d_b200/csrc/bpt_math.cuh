@@ -19,6 +19,20 @@
 
 namespace bpt {
 
+// Reciprocal behind the vector operators below. With -DBPT_OUTLINE_DIV=1 the correctly rounded division becomes one
+// out-of-line routine instead of ~9 inlined instructions plus a slow-path call per site (the IEEE divisions
+// are about half of the surface shade kernel's code, which is instruction-fetch bound). Same rounding either way; off by
+// default until it has been measured.
+#ifndef BPT_OUTLINE_DIV
+#define BPT_OUTLINE_DIV 0
+#endif
+#if BPT_OUTLINE_DIV && defined(__CUDA_ARCH__)
+static __device__ __noinline__ float rcp_rn_outlined(float s) { return __fdiv_rn(1.0f, s); }
+BPT_HD float rcp(float s) { return rcp_rn_outlined(s); }
+#else
+BPT_HD float rcp(float s) { return 1.0f / s; }
+#endif
+
 constexpr float PI_F = 3.14159265358979323846f;
 constexpr float TWO_PI_F = 6.283185307f;
 constexpr float RECIP_PI_F = 0.31830988618379067153776752674503f;
@@ -39,18 +53,18 @@ BPT_HD float3 operator+(float3 a, float s) { return f3(a.x + s, a.y + s, a.z + s
 BPT_HD float3 operator-(float3 a, float s) { return f3(a.x - s, a.y - s, a.z - s); }
 BPT_HD float3 operator-(float s, float3 a) { return f3(s - a.x, s - a.y, s - a.z); }
 BPT_HD float3 operator/(float3 a, float3 b) { return f3(a.x / b.x, a.y / b.y, a.z / b.z); }
-BPT_HD float3 operator/(float3 a, float s) { float inv = 1.0f / s; return a * inv; }
+BPT_HD float3 operator/(float3 a, float s) { float inv = rcp(s); return a * inv; }
 BPT_HD float3 operator/(float s, float3 a) { return f3(s / a.x, s / a.y, s / a.z); }
 BPT_HD void operator+=(float3& a, float3 b) { a.x += b.x; a.y += b.y; a.z += b.z; }
 BPT_HD void operator*=(float3& a, float3 b) { a.x *= b.x; a.y *= b.y; a.z *= b.z; }
 BPT_HD void operator*=(float3& a, float s) { a.x *= s; a.y *= s; a.z *= s; }
-BPT_HD void operator/=(float3& a, float s) { float inv = 1.0f / s; a *= inv; }
+BPT_HD void operator/=(float3& a, float s) { float inv = rcp(s); a *= inv; }
 
 BPT_HD float2 operator+(float2 a, float2 b) { return f2(a.x + b.x, a.y + b.y); }
 BPT_HD float2 operator-(float2 a, float2 b) { return f2(a.x - b.x, a.y - b.y); }
 BPT_HD float2 operator*(float2 a, float s) { return f2(a.x * s, a.y * s); }
 BPT_HD float2 operator*(float s, float2 a) { return f2(a.x * s, a.y * s); }
-BPT_HD float2 operator/(float2 a, float s) { float inv = 1.0f / s; return a * inv; }
+BPT_HD float2 operator/(float2 a, float s) { float inv = rcp(s); return a * inv; }
 
 BPT_HD float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 BPT_HD float4 operator-(float4 a, float4 b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
@@ -61,7 +75,7 @@ BPT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z;
 BPT_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 BPT_HD float length(float3 v) { return sqrtf(dot(v, v)); }
 BPT_HD float length(float2 v) { return sqrtf(dot(v, v)); }
-BPT_HD float3 normalize(float3 v) { float inv_len = 1.0f / sqrtf(dot(v, v)); return v * inv_len; }
+BPT_HD float3 normalize(float3 v) { float inv_len = rcp(sqrtf(dot(v, v))); return v * inv_len; }
 BPT_HD float lerp(float a, float b, float t) { return a + t * (b - a); }
 BPT_HD float3 lerp(float3 a, float3 b, float t) { return a + t * (b - a); }
 BPT_HD float clampf(float v, float lo, float hi) { return fmaxf(lo, fminf(v, hi)); }
