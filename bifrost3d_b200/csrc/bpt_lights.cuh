@@ -32,7 +32,7 @@ struct Tbn {
     float3 tangent, bitangent, normal;
     BPT_D explicit Tbn(float3 n) : normal(n) {
         float sign = copysignf(1.0f, n.z);
-        const float a = -1.0f / (sign + n.z);
+        const float a = fdiv(-1.0f, sign + n.z);
         const float b = n.x * n.y * a;
         tangent = f3(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
         bitangent = f3(b, sign + n.y * n.y * a, -n.y);
@@ -51,14 +51,14 @@ BPT_D float ray_sphere(float3 ray_origin, float3 ray_direction, float3 sphere_ce
     float3 fbd = direction_to_sphere - b * ray_direction;
     float d = radius_squared - dot(fbd, fbd);
     if (d > 0.0f)
-        return -b - sqrtf(d);
+        return -b - fsqrt(d);
     return nanf("");
 }
 BPT_D float ray_plane(float3 ray_origin, float3 ray_direction, float3 plane_point, float3 plane_normal) {
     float d = dot(plane_normal, plane_point);
     float n_dot_o = dot(plane_normal, ray_origin);
     float n_dot_d = dot(plane_normal, ray_direction);
-    return (d - n_dot_o) / n_dot_d;
+    return fdiv(d - n_dot_o, n_dot_d);
 }
 BPT_D float ray_disk(float3 ray_origin, float3 ray_direction, float3 disk_center, float3 disk_normal, float disk_radius) {
     float distance_to_plane = ray_plane(ray_origin, ray_direction, disk_center, disk_normal);
@@ -99,13 +99,13 @@ BPT_D float surface_area(const SphereLight& l) { return 4.0f * PI_F * l.radius *
 
 BPT_D bool is_delta(const SphereLight& l, float3 position) {
     float3 v = l.position - position;
-    float sin_theta_squared = l.radius * l.radius / dot(v, v);
+    float sin_theta_squared = fdiv(l.radius * l.radius, dot(v, v));
     return sin_theta_squared <= small_sin_theta_squared;
 }
 
 BPT_D LightSample sample_radiance(const SphereLight& l, float3 position, float2 u) {
     float3 vector_to_light = l.position - position;
-    float sin_theta_squared = l.radius * l.radius / dot(vector_to_light, vector_to_light);
+    float sin_theta_squared = fdiv(l.radius * l.radius, dot(vector_to_light, vector_to_light));
 
     LightSample s;
     if (sin_theta_squared <= small_sin_theta_squared) {
@@ -116,7 +116,7 @@ BPT_D LightSample sample_radiance(const SphereLight& l, float3 position, float2 
         s.distance -= l.radius;
         s.pdf = Pdf::delta_dirac(1.0f);
     } else {
-        float cos_theta = sqrtf(1.0f - sin_theta_squared);
+        float cos_theta = fsqrt(1.0f - sin_theta_squared);
         DirectionalSample cone = dist::cone_sample(cos_theta, u);
         const Tbn tbn(normalize(vector_to_light));
         s.direction_to_light = tbn.to_world(cone.direction);
@@ -124,7 +124,7 @@ BPT_D LightSample sample_radiance(const SphereLight& l, float3 position, float2 
         s.distance = isect::ray_sphere(position, s.direction_to_light, l.position, l.radius);
         if (s.distance <= 0.0f)
             s.distance = dot(vector_to_light, s.direction_to_light);
-        float inv_divisor = 1.0f / (PI_F * surface_area(l));
+        float inv_divisor = fdiv(1.0f, PI_F * surface_area(l));
         s.radiance = l.power * inv_divisor;
     }
     s.distance = nextafterf(s.distance, 0.0f);
@@ -133,17 +133,17 @@ BPT_D LightSample sample_radiance(const SphereLight& l, float3 position, float2 
 
 BPT_D Pdf pdf(const SphereLight& l, float3 lit_position, float3 direction_to_light) {
     float3 v = l.position - lit_position;
-    float sin_theta_squared = l.radius * l.radius / dot(v, v);
+    float sin_theta_squared = fdiv(l.radius * l.radius, dot(v, v));
     if (sin_theta_squared < small_sin_theta_squared)
         return Pdf::delta_dirac(0.0f);
-    float cos_theta_max = sqrtf(1.0f - sin_theta_squared);
+    float cos_theta_max = fsqrt(1.0f - sin_theta_squared);
     float cos_theta = dot(direction_to_light, normalize(v));
     float valid_direction = cos_theta >= cos_theta_max ? 1.0f : 0.0f;
     return Pdf(dist::cone_pdf(cos_theta_max) * valid_direction);
 }
 
 BPT_D float3 evaluate(const SphereLight& l, float3 position) {
-    float inv_divisor = 1.0f / (is_delta(l, position) ? (4.0f * PI_F) : (PI_F * surface_area(l)));
+    float inv_divisor = fdiv(1.0f, is_delta(l, position) ? (4.0f * PI_F) : (PI_F * surface_area(l)));
     return l.power * inv_divisor;
 }
 } // namespace sphere_light
@@ -159,12 +159,12 @@ BPT_D Pdf pdf(const SpotLight& l, float3 lit_position, float3 direction_to_light
     float cos_theta = -dot(l.direction, direction_to_light);
     if (cos_theta > 0.0f && !is_delta(l)) {
         float t = isect::ray_plane(lit_position, -l.direction, l.position, l.direction);
-        float cone_radius_at_intersection = t * sqrtf(1.0f - pow2(l.cos_angle)) / l.cos_angle;
+        float cone_radius_at_intersection = fdiv(t * fsqrt(1.0f - pow2(l.cos_angle)), l.cos_angle);
         if (l.radius > cone_radius_at_intersection && l.cos_angle > min_cone_angle_to_sample)
             return Pdf(dist::cone_pdf(l.cos_angle));
         float td = isect::ray_disk(lit_position, direction_to_light, l.position, l.direction, l.radius);
         if (td >= 0.0f) {
-            float area_PDF_to_solid_angle_PDF = (td * td) / cos_theta;
+            float area_PDF_to_solid_angle_PDF = fdiv(td * td, cos_theta);
             return Pdf(dist::disk_pdf(l.radius) * area_PDF_to_solid_angle_PDF);
         }
     }
@@ -196,7 +196,7 @@ BPT_D LightSample sample_radiance(const SpotLight& l, float3 lit_position, float
     const Tbn light_to_world(l.direction);
 
     float t = isect::ray_plane(lit_position, -l.direction, l.position, l.direction);
-    float cone_radius_at_intersection = t * sqrtf(1.0f - pow2(l.cos_angle)) / l.cos_angle;
+    float cone_radius_at_intersection = fdiv(t * fsqrt(1.0f - pow2(l.cos_angle)), l.cos_angle);
     if (l.radius > cone_radius_at_intersection && l.cos_angle > min_cone_angle_to_sample) {
         DirectionalSample cone = dist::cone_sample(l.cos_angle, u);
         s.direction_to_light = light_to_world.to_world(-cone.direction);
@@ -214,7 +214,7 @@ BPT_D LightSample sample_radiance(const SpotLight& l, float3 lit_position, float
         s.distance = length(s.direction_to_light);
         s.direction_to_light /= s.distance;
         float cos_theta = -dot(l.direction, s.direction_to_light);
-        float area_PDF_to_solid_angle_PDF = pow2(s.distance) / cos_theta;
+        float area_PDF_to_solid_angle_PDF = fdiv(pow2(s.distance), cos_theta);
         s.pdf = Pdf(dist::disk_pdf(l.radius) * area_PDF_to_solid_angle_PDF);
         s.radiance = evaluate(l, lit_position, s.direction_to_light);
     }
@@ -250,8 +250,8 @@ struct EnvironmentView {
 };
 
 BPT_D float2 direction_to_latlong_texcoord(float3 direction) {
-    float u = (atan2f(direction.z, direction.x) + PI_F) * 0.5f / PI_F;
-    float v = (asinf(direction.y) + PI_F * 0.5f) / PI_F;
+    float u = fdiv((atan2f(direction.z, direction.x) + PI_F) * 0.5f, PI_F);
+    float v = fdiv(asinf(direction.y) + PI_F * 0.5f, PI_F);
     return f2(u, v);
 }
 
@@ -297,8 +297,8 @@ BPT_D LightSample sample_radiance(const EnvironmentView& e, float2 u) {
 
 BPT_D Pdf pdf(const EnvironmentView& e, float3 direction_to_light) {
     float2 uv = direction_to_latlong_texcoord(direction_to_light);
-    float sin_theta = sqrtf(1.0f - direction_to_light.y * direction_to_light.y);
-    float p = fetch_pdf_nearest(e, uv) / sin_theta;
+    float sin_theta = fsqrt(1.0f - direction_to_light.y * direction_to_light.y);
+    float p = fdiv(fetch_pdf_nearest(e, uv), sin_theta);
     return sin_theta == 0.0f ? Pdf::delta_dirac(0.0f) : Pdf(p);
 }
 
@@ -343,7 +343,7 @@ BPT_D float3 light_evaluate(const Light& light, const EnvironmentView& env, floa
 // MonteCarlo.h:20-35
 BPT_D float balance_heuristic(float pdf1, float pdf2) {
     float divisor = pdf1 + pdf2;
-    float result = pdf1 / divisor;
+    float result = fdiv(pdf1, divisor);
     bool result_is_invalid = isinf(divisor) || isnan(result);
     return result_is_invalid ? (pdf1 <= pdf2 ? 0.0f : 1.0f) : result;
 }

@@ -19,7 +19,7 @@
 
 namespace bpt {
 
-// Reciprocal behind the vector operators below. With -DBPT_OUTLINE_DIV=1 the correctly rounded division becomes one
+// Division used by the vector operators below and by the scalar divisions of the shading routines. With -DBPT_OUTLINE_DIV=1 the correctly rounded division becomes one
 // out-of-line routine instead of ~9 inlined instructions plus a slow-path call per site (the IEEE divisions
 // are about half of the surface shade kernel's code, which is instruction-fetch bound). Same rounding either way; off by
 // default until it has been measured.
@@ -27,10 +27,21 @@ namespace bpt {
 #define BPT_OUTLINE_DIV 0
 #endif
 #if BPT_OUTLINE_DIV && defined(__CUDA_ARCH__)
-static __device__ __noinline__ float rcp_rn_outlined(float s) { return __fdiv_rn(1.0f, s); }
-BPT_HD float rcp(float s) { return rcp_rn_outlined(s); }
+static __device__ __noinline__ float div_rn_outlined(float a, float b) { return __fdiv_rn(a, b); }
+BPT_HD float fdiv(float a, float b) { return div_rn_outlined(a, b); }
 #else
-BPT_HD float rcp(float s) { return 1.0f / s; }
+BPT_HD float fdiv(float a, float b) { return a / b; }
+#endif
+BPT_HD float rcp(float s) { return fdiv(1.0f, s); }
+// The same hook for the correctly rounded square root (-DBPT_OUTLINE_SQRT=1).
+#ifndef BPT_OUTLINE_SQRT
+#define BPT_OUTLINE_SQRT 0
+#endif
+#if BPT_OUTLINE_SQRT && defined(__CUDA_ARCH__)
+static __device__ __noinline__ float sqrt_rn_outlined(float x) { return __fsqrt_rn(x); }
+BPT_HD float fsqrt(float x) { return sqrt_rn_outlined(x); }
+#else
+BPT_HD float fsqrt(float x) { return sqrtf(x); }
 #endif
 
 constexpr float PI_F = 3.14159265358979323846f;
@@ -73,9 +84,9 @@ BPT_HD float4 operator*(float4 a, float s) { return make_float4(a.x * s, a.y * s
 BPT_HD float dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
 BPT_HD float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 BPT_HD float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-BPT_HD float length(float3 v) { return sqrtf(dot(v, v)); }
-BPT_HD float length(float2 v) { return sqrtf(dot(v, v)); }
-BPT_HD float3 normalize(float3 v) { float inv_len = rcp(sqrtf(dot(v, v))); return v * inv_len; }
+BPT_HD float length(float3 v) { return fsqrt(dot(v, v)); }
+BPT_HD float length(float2 v) { return fsqrt(dot(v, v)); }
+BPT_HD float3 normalize(float3 v) { float inv_len = rcp(fsqrt(dot(v, v))); return v * inv_len; }
 BPT_HD float lerp(float a, float b, float t) { return a + t * (b - a); }
 BPT_HD float3 lerp(float3 a, float3 b, float t) { return a + t * (b - a); }
 BPT_HD float clampf(float v, float lo, float hi) { return fmaxf(lo, fminf(v, hi)); }

@@ -314,7 +314,7 @@ __device__ LightSample sample_single_light(const SceneView& s, const Bsdf& mater
     ls.radiance *= float(s.light_count);
 
     float N_dot_L = dot(tbn.normal, ls.direction_to_light);
-    ls.radiance *= fabsf(N_dot_L) / ls.pdf.value();
+    ls.radiance *= fdiv(fabsf(N_dot_L), ls.pdf.value());
 
     const float3 shading_light_direction = tbn.to_local(ls.direction_to_light);
     BsdfResponse response = material.evaluate_with_pdf(wo, shading_light_direction);
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                             LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
                             float light_weight = sum(light_sample.radiance);
                             float new_light_weight = sum(candidate.radiance);
-                            float new_light_probability = new_light_weight / (light_weight + new_light_weight);
+                            float new_light_probability = fdiv(new_light_weight, light_weight + new_light_weight);
                             if (r.w < new_light_probability) {
                                 light_sample = candidate;
                                 light_sample.radiance /= new_light_probability;

@@ -103,7 +103,7 @@ struct SpecularRho {
     float base, full;
     BPT_D float rho(float specularity) const { return lerp(base, full, specularity); }
     BPT_D float3 rho(float3 s) const { return f3(rho(s.x), rho(s.y), rho(s.z)); }
-    BPT_D float energy_loss_adjustment() const { return 1.0f / full; }
+    BPT_D float energy_loss_adjustment() const { return fdiv(1.0f, full); }
     BPT_D static SpecularRho fetch(const ShadingTables& t, float abs_cos_theta, float roughness) {
         SpecularRho r;
         r.base = bilinear(t.ggx_with_fresnel_rho, RHO_TABLE_DIM, RHO_TABLE_DIM, abs_cos_theta, roughness);
@@ -117,11 +117,11 @@ struct SpecularRho {
 // ------------------------------------------------------------------------------------------------
 namespace dist {
 
-BPT_D float cone_pdf(float cos_theta_max) { return 1.0f / (2.0f * PI_F * (1.0f - cos_theta_max)); }
+BPT_D float cone_pdf(float cos_theta_max) { return fdiv(1.0f, 2.0f * PI_F * (1.0f - cos_theta_max)); }
 
 BPT_D DirectionalSample cone_sample(float cos_theta_max, float2 u) {
     float cos_theta = (1.0f - u.x) + u.x * cos_theta_max;
-    float sin_theta = sqrtf(1.0f - cos_theta * cos_theta);
+    float sin_theta = fsqrt(1.0f - cos_theta * cos_theta);
     float phi = 2.0f * PI_F * u.y;
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
@@ -131,10 +131,10 @@ BPT_D DirectionalSample cone_sample(float cos_theta_max, float2 u) {
     return res;
 }
 
-BPT_D float disk_pdf(float radius) { return 1.0f / (PI_F * pow2(radius)); }
+BPT_D float disk_pdf(float radius) { return fdiv(1.0f, PI_F * pow2(radius)); }
 
 BPT_D float2 disk_sample(float radius, float2 u) {
-    float r = sqrtf(u.x) * radius;
+    float r = fsqrt(u.x) * radius;
     float phi = 2.0f * PI_F * u.y;
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
@@ -145,7 +145,7 @@ BPT_D float uniform_hemisphere_pdf() { return 0.5f * RECIP_PI_F; }
 
 BPT_D DirectionalSample uniform_hemisphere_sample(float2 u) {
     float z = u.x;
-    float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float r = fsqrt(fmaxf(0.0f, 1.0f - z * z));
     float phi = TWO_PI_F * u.y;
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
@@ -159,8 +159,8 @@ BPT_D float cosine_pdf(float abs_cos_theta) { return abs_cos_theta * RECIP_PI_F;
 
 BPT_D DirectionalSample cosine_sample(float2 u) {
     float r2 = u.x;
-    float r = sqrtf(1.0f - r2);
-    float z = sqrtf(r2);
+    float r = fsqrt(1.0f - r2);
+    float z = fsqrt(r2);
     float phi = 2.0f * PI_F * u.y;
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
@@ -175,36 +175,36 @@ BPT_D DirectionalSample cosine_sample(float2 u) {
 BPT_D float2 ltc_tangent_x(float3 w) {
     float2 wh = f2(w.x, w.y);
     float len_sqr = dot(wh, wh);
-    return len_sqr > 0.0f ? wh / sqrtf(len_sqr) : f2(1.0f, 0.0f);
+    return len_sqr > 0.0f ? wh / fsqrt(len_sqr) : f2(1.0f, 0.0f);
 }
 
 BPT_D void oren_nayar_ltc_coefficients(float cos_theta, float roughness, float& a, float& b, float& c, float& d) {
     a = 1.0f + roughness * (0.303392f + (-0.518982f + 0.111709f * cos_theta) * cos_theta + (-0.276266f + 0.335918f * cos_theta) * roughness);
-    b = roughness * (-1.16407f + 1.15859f * cos_theta + (0.150815f - 0.150105f * cos_theta) * roughness) / (cos_theta * cos_theta * cos_theta - 1.43545f);
+    b = fdiv(roughness * (-1.16407f + 1.15859f * cos_theta + (0.150815f - 0.150105f * cos_theta) * roughness), cos_theta * cos_theta * cos_theta - 1.43545f);
     c = 1.0f + (0.20013f + (-0.506373f + 0.261777f * cos_theta) * cos_theta) * roughness;
-    d = ((0.540852f + (-1.01625f + 0.475392f * cos_theta) * cos_theta) * roughness) / (-1.0743f + cos_theta * (0.0725628f + cos_theta));
+    d = fdiv((0.540852f + (-1.01625f + 0.475392f * cos_theta) * cos_theta) * roughness, -1.0743f + cos_theta * (0.0725628f + cos_theta));
 }
 
 BPT_D DirectionalSample oren_nayar_cltc_sample(float roughness, float3 wo, float2 u) {
     float a, b, c, d;
     oren_nayar_ltc_coefficients(wo.z, roughness, a, b, c, d);
 
-    float radius = sqrtf(u.x);
+    float radius = fsqrt(u.x);
     float phi = 2.0f * PI_F * u.y;
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
     float x = radius * cos_phi;
     float y = radius * sin_phi;
 
-    float vz = 1.0f / sqrtf(d * d + 1.0f);
+    float vz = fdiv(1.0f, fsqrt(d * d + 1.0f));
     float s = 0.5f * (1.0f + vz);
-    x = -lerp(sqrtf(1.0f - y * y), x, s);
-    float3 wh = f3(x, y, sqrtf(fmaxf(1.0f - (x * x + y * y), 0.0f)));
-    float pdf_wh = wh.z / (PI_F * s);
+    x = -lerp(fsqrt(1.0f - y * y), x, s);
+    float3 wh = f3(x, y, fsqrt(fmaxf(1.0f - (x * x + y * y), 0.0f)));
+    float pdf_wh = fdiv(wh.z, PI_F * s);
     float3 wi = f3(a * wh.x + b * wh.z, c * wh.y, d * wh.x + wh.z);
     float wi_magnitude = length(wi);
     float determinant_M = c * (a - b * d);
-    float pdf_wi = pdf_wh * wi_magnitude * wi_magnitude * wi_magnitude / determinant_M;
+    float pdf_wi = fdiv(pdf_wh * wi_magnitude * wi_magnitude * wi_magnitude, determinant_M);
     // wi -> local space: [X Y] * wi.xy
     float2 X = ltc_tangent_x(wo);
     float2 Y = f2(-X.y, X.x);
@@ -229,19 +229,19 @@ BPT_D float oren_nayar_cltc_pdf(float roughness, float3 wo, float3 wi_shading) {
     float determinant_M = c * (a - b * d);
     float3 wh = f3(c * (wi.x - b * wi.z), (a - b * d) * wi.y, -c * (d * wi.x - a * wi.z));
     float wh_magnitude_squared = dot(wh, wh);
-    float vz = 1.0f / sqrtf(d * d + 1.0f);
+    float vz = fdiv(1.0f, fsqrt(d * d + 1.0f));
     float s = 0.5f * (1.0f + vz);
-    return determinant_M * determinant_M / pow2(wh_magnitude_squared) * fmaxf(wh.z, 0.0f) / (PI_F * s);
+    return fdiv(fdiv(determinant_M * determinant_M, pow2(wh_magnitude_squared)) * fmaxf(wh.z, 0.0f), PI_F * s);
 }
 
 // --- GGX visible normals (Distributions.h:304-461) -----------------------------------------------
 BPT_D float ggx_D(float alpha, float3 halfway) {
-    float m = pow2(halfway.x / alpha) + pow2(halfway.y / alpha) + pow2(halfway.z);
-    return 1.0f / (PI_F * alpha * alpha * pow2(m));
+    float m = pow2(fdiv(halfway.x, alpha)) + pow2(fdiv(halfway.y, alpha)) + pow2(halfway.z);
+    return fdiv(1.0f, PI_F * alpha * alpha * pow2(m));
 }
 
 BPT_D float ggx_lambda(float alpha, float3 w) {
-    return 0.5f * (-1.0f + sqrtf(1.0f + (pow2(alpha * w.x) + pow2(alpha * w.y)) / pow2(w.z)));
+    return 0.5f * (-1.0f + fsqrt(1.0f + fdiv(pow2(alpha * w.x) + pow2(alpha * w.y), pow2(w.z))));
 }
 
 // Bounded VNDF (Eto et al. 2023), isotropic alpha.
@@ -252,10 +252,10 @@ BPT_D float3 ggx_bounded_vndf_sample_reflection(float alpha, float3 wo, float2 u
     float a = fminf(alpha, alpha);
     float s = 1.0f + length(f2(wo.x, wo.y));
     float a2 = a * a; float s2 = s * s;
-    float k = (1.0f - a2) * s2 / (s2 + a2 * wo.z * wo.z);
+    float k = fdiv((1.0f - a2) * s2, s2 + a2 * wo.z * wo.z);
     float b = wo.z >= 0.0f ? k * wo_std.z : wo_std.z;
     float z = fmaf(1.0f - u.x, 1.0f + b, -b);
-    float sin_theta = sqrtf(fmaxf(1.0f - z * z, 0.0f));
+    float sin_theta = fsqrt(fmaxf(1.0f - z * z, 0.0f));
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
     float3 o_std = f3(sin_theta * cos_phi, sin_theta * sin_phi, z);
@@ -270,15 +270,15 @@ BPT_D float ggx_bounded_vndf_reflection_pdf(float alpha, float3 wo, float3 wi) {
     float ndf = ggx_D(alpha, halfway);
     float2 ao = f2(alpha * wo.x, alpha * wo.y);
     float len2 = dot(ao, ao);
-    float t = sqrtf(len2 + wo.z * wo.z);
+    float t = fsqrt(len2 + wo.z * wo.z);
     if (wo.z >= 0.0f) {
         float min_alpha = fminf(alpha, alpha);
         float s = 1.0f + length(f2(wo.x, wo.y));
         float min_alpha_squared = min_alpha * min_alpha; float s2 = s * s;
-        float k = (1.0f - min_alpha_squared) * s2 / (s2 + min_alpha_squared * wo.z * wo.z);
-        return ndf / (2.0f * (k * wo.z + t));
+        float k = fdiv((1.0f - min_alpha_squared) * s2, s2 + min_alpha_squared * wo.z * wo.z);
+        return fdiv(ndf, 2.0f * (k * wo.z + t));
     }
-    return ndf * (t - wo.z) / (2.0f * len2);
+    return fdiv(ndf * (t - wo.z), 2.0f * len2);
 }
 
 } // namespace dist
@@ -295,8 +295,8 @@ BPT_D float3 schlick_fresnel(float3 incident_specular, float abs_cos_theta) {
     return (1.0f - t) * incident_specular + t;
 }
 
-BPT_D float dielectric_specularity(float ior_o, float ior_i) { return pow2((ior_o - ior_i) / (ior_o + ior_i)); }
-BPT_D float dielectric_ior_from_specularity(float specularity) { return 2.0f / (1.0f - sqrtf(specularity)) - 1.0f; }
+BPT_D float dielectric_specularity(float ior_o, float ior_i) { return pow2(fdiv(ior_o - ior_i, ior_o + ior_i)); }
+BPT_D float dielectric_ior_from_specularity(float specularity) { return fdiv(2.0f, 1.0f - fsqrt(specularity)) - 1.0f; }
 BPT_D float adjust_dielectric_specularity_to_exterior_medium(float exterior_ior, float specularity_through_air) {
     float base_ior = dielectric_ior_from_specularity(specularity_through_air);
     return dielectric_specularity(exterior_ior, base_ior);
@@ -309,7 +309,7 @@ BPT_D float3 conductor_ior_from_specularity(float3 specularity, float3 ext_i) {
     float3 b = 2.0f * specularity + 2.0f;
     float3 c = a + (specularity - 1.0f) * (ext_i * ext_i);
     float3 d = b * b - 4.0f * a * c;
-    float3 sqrt_d = f3(sqrtf(d.x), sqrtf(d.y), sqrtf(d.z));
+    float3 sqrt_d = f3(fsqrt(d.x), fsqrt(d.y), fsqrt(d.z));
     return (-b + sqrt_d) / (2.0f * a);
 }
 BPT_D float3 conductor_specularity(float3 ior_o, float3 ior_i, float3 ext_i) {
@@ -334,10 +334,10 @@ BPT_D float modulate_roughness_under_coat(float base_roughness, float coat_rough
 namespace ggx {
 constexpr float MIN_ALPHA = 1e-4f;
 BPT_D float alpha_from_roughness(float roughness) { return fmaxf(MIN_ALPHA, roughness * roughness); }
-BPT_D float roughness_from_alpha(float alpha) { return sqrtf(alpha); }
+BPT_D float roughness_from_alpha(float alpha) { return fsqrt(alpha); }
 BPT_D bool effectively_smooth(float alpha) { return alpha <= MIN_ALPHA; }
 BPT_D float height_correlated_G(float alpha, float3 wo, float3 wi) {
-    return 1.0f / (1.0f + dist::ggx_lambda(alpha, wo) + dist::ggx_lambda(alpha, wi));
+    return fdiv(1.0f, 1.0f + dist::ggx_lambda(alpha, wo) + dist::ggx_lambda(alpha, wi));
 }
 } // namespace ggx
 
@@ -353,7 +353,7 @@ BPT_D float3 evaluate(float alpha, float3 specularity, float3 wo, float3 wi) {
     float G = ggx::height_correlated_G(alpha, wo, wi);
     float D = dist::ggx_D(alpha, halfway);
     float3 F = schlick_fresnel(specularity, dot(wo, halfway));
-    return F * (D * G / (4.0f * wo.z * wi.z));
+    return F * fdiv(D * G, 4.0f * wo.z * wi.z);
 }
 
 BPT_D Pdf pdf(float alpha, float3 wo, float3 wi) {
@@ -408,8 +408,8 @@ BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
     float cos_theta_i = wi.z;
     float cos_theta_o = wo.z;
     float s = dot(wi, wo) - cos_theta_i * cos_theta_o;
-    float s_over_t = s > 0.0f ? s / fmaxf(cos_theta_i, cos_theta_o) : s;
-    float A = 1.0f / (1.0f + constant1_FON * roughness);
+    float s_over_t = s > 0.0f ? fdiv(s, fmaxf(cos_theta_i, cos_theta_o)) : s;
+    float A = fdiv(1.0f, 1.0f + constant1_FON * roughness);
     float B = roughness * A;
 
     float f_single_scatter = RECIP_PI_F * A * (1.0f + roughness * s_over_t);
@@ -417,9 +417,9 @@ BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
     float EF_o = E_FON_approx(cos_theta_o, A, B);
     float EF_i = E_FON_approx(cos_theta_i, A, B);
     float average_EF = A * (1.0f + constant2_FON * roughness);
-    float multi_scatter_rho = average_EF / (1.0f - (1.0f - average_EF));
-    float f_multi_scatter = (multi_scatter_rho * RECIP_PI_F) * fabsf(1.0f - EF_o) * fabsf(1.0f - EF_i)
-        / fmaxf(1.0e-7f, 1.0f - average_EF);
+    float multi_scatter_rho = fdiv(average_EF, 1.0f - (1.0f - average_EF));
+    float f_multi_scatter = fdiv((multi_scatter_rho * RECIP_PI_F) * fabsf(1.0f - EF_o) * fabsf(1.0f - EF_i),
+                                 fmaxf(1.0e-7f, 1.0f - average_EF));
     return f_single_scatter + f_multi_scatter;
 }
 
@@ -453,11 +453,11 @@ BPT_CALL BsdfSample sample(float3 albedo, float roughness, float roughness_facto
     DirectionalSample ds;
     float cltc_PDF;
     if (u.x <= uniform_probability) {
-        u.x = u.x / uniform_probability;
+        u.x = fdiv(u.x, uniform_probability);
         ds = dist::uniform_hemisphere_sample(u);
         cltc_PDF = dist::oren_nayar_cltc_pdf(roughness, wo, ds.direction);
     } else {
-        u.x = (u.x - uniform_probability) / cltc_probability;
+        u.x = fdiv(u.x - uniform_probability, cltc_probability);
         ds = dist::oren_nayar_cltc_sample(roughness, wo, u);
         cltc_PDF = ds.pdf;
     }
@@ -485,7 +485,7 @@ BPT_D float evaluate(float roughness, float3 wo, float3 wi) {
     float fd90 = 0.5f + 2.0f * wi_dot_halfway * wi_dot_halfway * roughness;
     float fresnel_wo = schlick(wo.z);
     float fresnel_wi = schlick(wi.z);
-    float normalizer = 1.0f / lerp(0.969371021f, 1.04337633f, roughness);
+    float normalizer = fdiv(1.0f, lerp(0.969371021f, 1.04337633f, roughness));
     return lerp(1.0f, fd90, fresnel_wo) * lerp(1.0f, fd90, fresnel_wi) * RECIP_PI_F * normalizer;
 }
 
@@ -533,7 +533,7 @@ BPT_D bool refract_z(float3& refraction_direction, float3 wi, float ior_i_over_o
     } else
         ior_i_over_o = 1.0f / ior_i_over_o;
     float k = 1.0f - ior_i_over_o * ior_i_over_o * (1.0f - cos_theta_i * cos_theta_i);
-    refraction_direction = ior_i_over_o * wi - f3(0.0f, 0.0f, (ior_i_over_o * cos_theta_i + sqrtf(k)) * normal_z);
+    refraction_direction = ior_i_over_o * wi - f3(0.0f, 0.0f, (ior_i_over_o * cos_theta_i + fsqrt(k)) * normal_z);
     return k >= 0.0f;
 }
 
@@ -553,7 +553,7 @@ BPT_D bool refract_n(float3& r, float3 i, float3 n, float ior) {
         r = f3(0.0f);
         return false;
     }
-    r = normalize(eta * i - (eta * negNdotV + sqrtf(k)) * nn);
+    r = normalize(eta * i - (eta * negNdotV + fsqrt(k)) * nn);
     return true;
 }
 
@@ -563,7 +563,7 @@ BPT_D float3 ggx_vndf_sample_halfway(float alpha, float3 wo, float2 u) {
     float3 wo_std = normalize(f3(alpha * wo.x, alpha * wo.y, wo.z));
     float phi = 2.0f * PI_F * u.y;
     float z = fmaf(1.0f - u.x, 1.0f + wo_std.z, -wo_std.z);
-    float sin_theta = sqrtf(clampf(1.0f - z * z, 0.0f, 1.0f));
+    float sin_theta = fsqrt(clampf(1.0f - z * z, 0.0f, 1.0f));
     float sin_phi, cos_phi;
     sincos_(phi, sin_phi, cos_phi);
     float3 c = f3(sin_theta * cos_phi, sin_theta * sin_phi, z);
@@ -775,8 +775,8 @@ BPT_D float ggx_min_roughness_from_pdf(const ShadingTables& t, float abs_cos_the
     if (max_pdf.is_delta_dirac())
         return 0.0f;
     float pdf = max_pdf.value();
-    float non_linear_PDF = pdf / (1.0f + pdf);
-    float encoded_PDF = (non_linear_PDF - 0.13f) / 0.87f;
+    float non_linear_PDF = fdiv(pdf, 1.0f + pdf);
+    float encoded_PDF = fdiv(non_linear_PDF - 0.13f, 0.87f);
     if (isnan(encoded_PDF))
         encoded_PDF = 1.0f;
     float min_alpha = bilinear(t.estimate_alpha, RHO_TABLE_DIM, RHO_TABLE_DIM, encoded_PDF, abs_cos_theta);
@@ -873,7 +873,7 @@ struct DefaultShading {
         float diffuse_rho_sum = sum(diffuse_tint);
         float specular_rho_sum = sum(specular_rho(t, abs_cos_theta_o));
         float coat_rho_sum = 3.0f * coat_rho;
-        float recip_total_rho = 1.0f / (diffuse_rho_sum + specular_rho_sum + coat_rho_sum);
+        float recip_total_rho = fdiv(1.0f, diffuse_rho_sum + specular_rho_sum + coat_rho_sum);
 
         float specular_probability = specular_rho_sum * recip_total_rho;
         specular_probability_q = (unsigned short)(specular_probability * USHORT_MAX_F + 0.5f);
@@ -918,9 +918,9 @@ struct DefaultShading {
     }
 
     BPT_D float get_specular_alpha() const { return ggx::alpha_from_roughness(roughness); }
-    BPT_D float get_diffuse_probability() const { return 1.0f - (specular_probability_q + coat_probability_q) / 65535.0f; }
-    BPT_D float get_specular_probability() const { return specular_probability_q / 65535.0f; }
-    BPT_D float get_coat_probability() const { return coat_probability_q / 65535.0f; }
+    BPT_D float get_diffuse_probability() const { return 1.0f - fdiv(float(specular_probability_q + coat_probability_q), 65535.0f); }
+    BPT_D float get_specular_probability() const { return fdiv(float(specular_probability_q), 65535.0f); }
+    BPT_D float get_coat_probability() const { return fdiv(float(coat_probability_q), 65535.0f); }
 
     BPT_D BsdfResponse evaluate_with_pdf(float3 wo, float3 wi) const {
         if (wo.z < 0.000001f || wi.z < 0.000001f)
