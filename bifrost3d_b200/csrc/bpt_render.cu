@@ -27,7 +27,10 @@ namespace bpt {
 
 namespace {
 
-constexpr int SHADE_BLOCK = 128;
+#ifndef BPT_SHADE_BLOCK
+#define BPT_SHADE_BLOCK 128
+#endif
+constexpr int SHADE_BLOCK = BPT_SHADE_BLOCK; // threads per CTA of the shade kernels (with BPT_SHADE_MIN_BLOCKS CTAs per SM)
 constexpr int LIGHT_HIT_FLAG = 0x40000000; // hit.primitive = LIGHT_HIT_FLAG | light index
 constexpr float RT_DEFAULT_MAX = 1e27f;    // tmax of optix::Ray when none is given (SimpleRGPs.cu:114)
 
