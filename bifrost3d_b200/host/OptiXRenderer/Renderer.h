@@ -1,8 +1,8 @@
-// OptiXRenderer::Renderer re-created on top of libbpt.so (include/bpt_c_api.h): same class, same public methods and
-// semantics as extensions/OptiXRenderer/OptiXRenderer/Renderer.h:40-86, so code written against the reference
-// (DX11OptiXAdaptor, OptiXRendererTests/RendererTest.h) compiles and runs unchanged. No OptiX underneath.
-#ifndef _OPTIXRENDERER_RENDERER_H_
-#define _OPTIXRENDERER_RENDERER_H_
+// Drop-in replacement of the reference's renderer class (extensions/OptiXRenderer/OptiXRenderer/Renderer.h:40-86) on top of
+// libbpt.so (include/bpt_c_api.h). Class name, method names, argument types and behaviour follow the reference so that code
+// written against it (DX11OptiXAdaptor, tests/OptiXRendererTests/RendererTest.h) compiles and links unchanged; there is no
+// OptiX underneath, `optix::Buffer` / `optix::Context` are the small facade types of host/optix_facade.
+#pragma once
 
 #include <OptiXRenderer/PublicTypes.h>
 
@@ -15,60 +15,70 @@
 namespace optix {
 template <class T> class Handle;
 class BufferObj;
-typedef Handle<BufferObj> Buffer;
 class ContextObj;
-typedef Handle<ContextObj> Context;
-}
+using Buffer = Handle<BufferObj>;
+using Context = Handle<ContextObj>;
+} // namespace optix
 
 namespace OptiXRenderer {
 
 class Renderer final {
+    using CameraID = Bifrost::Scene::CameraID;
+    using SceneRootID = Bifrost::Scene::SceneRootID;
+    using Vector2i = Bifrost::Math::Vector2i;
+
 public:
-    // Returns nullptr (and prints why) when no CUDA device / context can be created; never throws. Renderer.cpp:1365-1378.
+    // ---- life time -------------------------------------------------------------------------------------------------
+    // nullptr (with the reason printed) when no CUDA device is usable; never throws (Renderer.cpp:1365-1378).
     static Renderer* initialize(int cuda_device_ID, const std::filesystem::path& data_directory);
     ~Renderer();
+    Renderer(Renderer&) = delete;
+    Renderer& operator=(const Renderer&) = delete;
 
     Bifrost::Core::RendererID get_renderer_ID() const { return m_renderer_ID; }
-
-    Backend get_backend(Bifrost::Scene::CameraID camera_ID) const;
-    void set_backend(Bifrost::Scene::CameraID camera_ID, Backend backend);
-    unsigned int get_max_bounce_count(Bifrost::Scene::CameraID camera_ID) const;
-    void set_max_bounce_count(Bifrost::Scene::CameraID camera_ID, unsigned int bounce_count);
-    unsigned int get_max_accumulation_count(Bifrost::Scene::CameraID camera_ID) const;
-    void set_max_accumulation_count(Bifrost::Scene::CameraID camera_ID, unsigned int accumulation_count);
-    int get_next_event_sample_count(Bifrost::Scene::SceneRootID scene_root_ID) const;
-    void set_next_event_sample_count(Bifrost::Scene::SceneRootID scene_root_ID, int sample_count);
-    PathRegularizationSettings get_path_regularization_settings() const;
-    void set_path_regularization_settings(PathRegularizationSettings settings);
-    AIDenoiserFlags get_AI_denoiser_flags() const;
-    void set_AI_denoiser_flags(AIDenoiserFlags flags);
-
-    // Reads the change lists of the Bifrost core managers and mirrors the scene on the device.
-    void handle_updates();
-
-    // Renders one more progressive sample into the camera's accumulation buffer and writes the running mean as half4
-    // into `buffer`. Returns the accumulation count.
-    unsigned int render(Bifrost::Scene::CameraID camera_ID, optix::Buffer buffer, Bifrost::Math::Vector2i frame_size);
-
-    std::vector<Bifrost::Scene::Screenshot> request_auxiliary_buffers(Bifrost::Scene::CameraID camera_ID,
-        Bifrost::Scene::Cameras::ScreenshotContent content_requested, Bifrost::Math::Vector2i frame_size);
-
     optix::Context& get_context();
 
-    // Additions for sample-sharded multi-GPU rendering: render accumulation indices [first, first + count).
+    // ---- per-camera, per-scene and global settings (Renderer.cpp:1389-1474) ------------------------------------------
+    Backend get_backend(CameraID camera) const;
+    void set_backend(CameraID camera, Backend backend);
+
+    unsigned int get_max_bounce_count(CameraID camera) const;
+    void set_max_bounce_count(CameraID camera, unsigned int bounces);
+
+    unsigned int get_max_accumulation_count(CameraID camera) const;
+    void set_max_accumulation_count(CameraID camera, unsigned int accumulations);
+
+    int get_next_event_sample_count(SceneRootID scene_root) const;
+    void set_next_event_sample_count(SceneRootID scene_root, int samples);
+
+    PathRegularizationSettings get_path_regularization_settings() const;
+    void set_path_regularization_settings(PathRegularizationSettings settings);
+
+    AIDenoiserFlags get_AI_denoiser_flags() const; // accepted and stored; the OptiX denoiser backend is out of scope
+    void set_AI_denoiser_flags(AIDenoiserFlags flags);
+
+    // ---- per frame ---------------------------------------------------------------------------------------------------
+    // Mirrors what changed in the Bifrost core managers since the last call onto the device (incrementally).
+    void handle_updates();
+
+    // One more progressive sample of every pixel; the running mean goes to `target` as half4. Returns the accumulation count.
+    unsigned int render(CameraID camera, optix::Buffer target, Vector2i frame_size);
+
+    // Depth / albedo / tint / roughness screenshots of the current scene (Renderer.cpp:1267-1358).
+    std::vector<Bifrost::Scene::Screenshot> request_auxiliary_buffers(CameraID camera, Bifrost::Scene::Cameras::ScreenshotContent content,
+                                                                      Vector2i frame_size);
+
+    // ---- addition: sample-sharded multi-GPU rendering ------------------------------------------------------------------
+    // This renderer's accumulation indices start at `first_sample` (rank r of R renders [r * spp / R, (r + 1) * spp / R)).
     void set_sample_range(unsigned int first_sample) { m_first_sample = first_sample; }
 
 private:
     Renderer(int cuda_device_ID, const std::filesystem::path& data_directory);
-    Renderer(Renderer& other) = delete;
-    Renderer& operator=(const Renderer& rhs) = delete;
 
     Bifrost::Core::RendererID m_renderer_ID;
     unsigned int m_first_sample = 0;
-    struct Implementation;
+    struct Implementation; // everything CUDA / C ABI related lives behind this pointer
     Implementation* m_impl;
 };
 
 } // namespace OptiXRenderer
-
-#endif
