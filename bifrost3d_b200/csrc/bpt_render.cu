@@ -19,6 +19,12 @@
 #include <cuda_fp16.h>
 #include <algorithm>
 
+// Experimental (off by default, written but not yet run on a GPU): the surface shading as three kernels - set-up, next event
+// estimation, BSDF sampling - that hand a 112-byte record per path through memory. Motivation in DESIGN.md 6: the single
+// surface kernel is instruction-fetch bound (105 KB of code) and keeps 248 bytes of spills and call frames per thread.
+#ifndef BPT_SHADE_SPLIT
+#define BPT_SHADE_SPLIT 0
+#endif
 #ifndef BPT_TILED_QUEUE
 #define BPT_TILED_QUEUE 1
 #endif
@@ -44,6 +50,9 @@ struct QueueCounters {
     unsigned int surface;      // paths whose ray hit a Default / Diffuse surface (shade_kernel<true, false>)
     unsigned int escaped;      // paths whose ray left the scene or hit an analytic light (shade_kernel<false, false>)
     unsigned int transmissive; // paths whose ray hit a Transmissive surface (shade_kernel<true, true>)
+#if BPT_SHADE_SPLIT
+    unsigned int nee;          // paths accepted by shade_setup_kernel: next event estimation + BSDF sampling follow
+#endif
 };
 
 struct Wavefront {
@@ -55,6 +64,10 @@ struct Wavefront {
     DeviceBuffer<float4> sh_o, sh_d, sh_rad;
     DeviceBuffer<unsigned int> queue_a, queue_b;
     DeviceBuffer<unsigned int> queue_surface, queue_escaped; // extend sorts its results by what shading they need
+#if BPT_SHADE_SPLIT
+    DeviceBuffer<unsigned int> queue_nee;
+    DeviceBuffer<float4> record;
+#endif
     DeviceBuffer<QueueCounters> counters;
     DeviceBuffer<float> coverage; // per material
     uint64_t coverage_version = ~0ull;
@@ -66,6 +79,10 @@ struct WavefrontView {
     unsigned int *queue_in, *queue_out;
     unsigned int *queue_surface, *queue_escaped;
     unsigned int queue_capacity;      // entries per queue; the transmissive queue grows down from the end of queue_surface
+#if BPT_SHADE_SPLIT
+    unsigned int* queue_nee;          // pixels whose surface record is waiting for the NEE and BSDF sampling kernels
+    float4* record;                   // 7 float4 per pixel: shading normal + cos_theta, geometric normal + light-valid flag, point, material (4)
+#endif
     QueueCounters* counters;
     unsigned long long* ray_counters; // [0] extend, [1] shadow
 };
@@ -163,6 +180,9 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.counters->surface = 0;
         w.counters->escaped = 0;
         w.counters->transmissive = 0;
+#if BPT_SHADE_SPLIT
+        w.counters->nee = 0;
+#endif
     }
 }
 
@@ -262,6 +282,9 @@ __global__ void advance_kernel(QueueCounters* c) {
     c->surface = 0;
     c->escaped = 0;
     c->transmissive = 0;
+#if BPT_SHADE_SPLIT
+    c->nee = 0;
+#endif
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
@@ -558,6 +581,275 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     }
 }
 
+#if BPT_SHADE_SPLIT
+// ---- split surface shading (experimental) ---------------------------------------------------------------------
+// shade_setup_kernel: interpolate_attributes + the reject rules + frame and material set-up + emission
+// (TriangleAttributes.cu:35-84, MonteCarlo.cu:129-195) -> one SurfaceRecord per accepted path.
+// shade_nee_kernel:    reestimated_light_samples + shadow ray (MonteCarlo.cu:91-123,197-202, SimpleRGPs.cu:117-125).
+// shade_sample_kernel: BSDF sampling, throughput, mirror fix, ray offset, roulette (MonteCarlo.cu:204-232).
+// The arithmetic is the single kernel's, statement for statement; only the place where values live changes.
+template <bool TRANSMISSIVE> struct SurfaceMaterialOf { typedef DefaultShading type; };
+template <> struct SurfaceMaterialOf<true> { typedef TransmissiveShading type; };
+static_assert(sizeof(DefaultShading) <= 64 && sizeof(TransmissiveShading) <= 64, "a surface material must fit four float4 of the record");
+constexpr int RECORD_FLOAT4S = 7; // shading normal + cos_theta, geometric normal + light-valid flag, point, material (4)
+
+template <typename Material_>
+__device__ __forceinline__ void store_material(float4* __restrict__ slot, const Material_& m) {
+    float4 packed[4] = { make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0) };
+    memcpy(packed, &m, sizeof(Material_));
+    slot[0] = packed[0]; slot[1] = packed[1]; slot[2] = packed[2]; slot[3] = packed[3];
+}
+template <typename Material_>
+__device__ __forceinline__ Material_ load_material(const float4* __restrict__ slot) {
+    float4 packed[4] = { slot[0], slot[1], slot[2], slot[3] };
+    Material_ m;
+    memcpy(&m, packed, sizeof(Material_));
+    return m;
+}
+
+template <bool TRANSMISSIVE>
+__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_setup_kernel(WavefrontView w, SceneView s, FrameParams f) {
+    const ShadingTables tables = { s.tables, s.tables + TABLE_FLOATS, s.tables + 2 * TABLE_FLOATS };
+    const unsigned int count = TRANSMISSIVE ? w.counters->transmissive : w.counters->surface;
+    const unsigned int* __restrict__ queue = TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count) : w.queue_surface;
+    const unsigned int rounded = (count + 31u) & ~31u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool retrace = false, accepted = false;
+        unsigned int pixel = 0;
+        if (i < count) {
+            pixel = queue[i];
+            const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
+            const float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
+            const float4 hit4 = w.hit[pixel];
+            const float3 ray_origin = f3(ro), ray_direction = f3(rd);
+            const Pdf bsdf_pdf(rd.w);
+            const float3 throughput = f3(thr4);
+            float3 radiance = f3(rad4);
+            const unsigned int bounces = __float_as_uint(thr4.w);
+            const float t_hit = hit4.x;
+            const int primitive = __float_as_int(hit4.y);
+            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
+
+            const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
+                         p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
+            const int4* shade_raw = reinterpret_cast<const int4*>(s.shade + primitive);
+            int4 sr0 = __ldg(shade_raw), sr1 = __ldg(shade_raw + 1);
+            ShadeTriangle st;
+            memcpy(&st, &sr0, 16); memcpy(reinterpret_cast<char*>(&st) + 16, &sr1, 16);
+
+            float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
+            const float bx = hit4.z, by = hit4.w;
+            const float bz = 1.0f - bx - by;
+            const float3 intersection_point = p1 * bx + p2 * by + p0 * bz;
+            const bool has_normals = st.flags & 1u, has_tints = st.flags & 2u;
+            float3 shading_normal;
+            if (has_normals) {
+                shading_normal = oct_decode(st.n1) * bx + oct_decode(st.n2) * by + oct_decode(st.n0) * bz;
+                shading_normal = normalize(shading_normal);
+            } else
+                shading_normal = geometric_normal;
+            float4 tint_and_roughness_scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            if (has_tints) {
+                const float n255 = 1.0f / 255.0f;
+                tint_and_roughness_scale.x = (st.t1[0] * bx + st.t2[0] * by + st.t0[0] * bz) * n255;
+                tint_and_roughness_scale.y = (st.t1[1] * bx + st.t2[1] * by + st.t0[1] * bz) * n255;
+                tint_and_roughness_scale.z = (st.t1[2] * bx + st.t2[2] * by + st.t0[2] * bz) * n255;
+                tint_and_roughness_scale.w = (st.t1[3] * bx + st.t2[3] * by + st.t0[3] * bz) * n255;
+            }
+
+            const float2 texcoord = interpolate_texcoord(s.accel.textures, primitive, bx, by);
+            const Material material_parameter = material_at(s.materials[st.material_index], s.accel.textures, texcoord);
+            float3 world_geometric_normal = geometric_normal;
+            bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
+            bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
+            backside_cull &= !material_is_transmissive(material_parameter);
+
+            float4 bsdf_coverage_random = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF);
+            float coverage_cutoff = bsdf_coverage_random.w;
+            float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
+            bool discard_from_coverage = coverage < coverage_cutoff;
+
+            if (backside_cull || discard_from_coverage) {
+                w.ray_o[pixel] = f4(ray_origin, nextafterf(t_hit, INFINITY)); // same ray, advanced past this surface
+                retrace = true; // bounces and throughput are unchanged, so the path continues
+            } else {
+                world_geometric_normal = hit_from_front ? world_geometric_normal : -world_geometric_normal;
+                float3 world_shading_normal = shading_normal;
+                if (has_normals) {
+                    const float* nm = s.normal_matrices + 9 * (st.flags >> 2);
+                    world_shading_normal = normalize(f3(nm[0] * shading_normal.x + nm[1] * shading_normal.y + nm[2] * shading_normal.z,
+                                                        nm[3] * shading_normal.x + nm[4] * shading_normal.y + nm[5] * shading_normal.z,
+                                                        nm[6] * shading_normal.x + nm[7] * shading_normal.y + nm[8] * shading_normal.z));
+                }
+                world_shading_normal = hit_from_front ? world_shading_normal : -world_shading_normal;
+                world_shading_normal = fix_backfacing_shading_normal(-ray_direction, world_shading_normal, 0.002f);
+                const Tbn tbn(world_shading_normal);
+                const float3 wo = tbn.to_local(-ray_direction);
+                float cos_theta = hit_from_front || material_is_thin_walled(material_parameter) ? wo.z : -wo.z;
+
+                Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
+                const auto material = [&]() {
+                    if constexpr (TRANSMISSIVE)
+                        return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
+                                                                       cos_theta, max_pdf_hint);
+                    else
+                        return material_parameter.shading_model == SHADING_DIFFUSE
+                            ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
+                            : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+                }();
+
+                float3 emission = f3(1.0f);
+                if (s.shade_emission != nullptr) {
+                    const float* e = s.shade_emission + 9ll * primitive;
+                    emission = f3(e[3], e[4], e[5]) * bx + f3(e[6], e[7], e[8]) * by + f3(e[0], e[1], e[2]) * bz;
+                }
+                radiance += throughput * emission * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
+                w.rad[pixel] = f4(radiance, __int_as_float(primitive)); // previous_primitive = primitive
+
+                float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
+                record[0] = f4(world_shading_normal, cos_theta);
+                record[1] = f4(world_geometric_normal, 1.0f); // w: "the light sample is valid", set by shade_nee_kernel
+                record[2] = f4(intersection_point, 0.0f);
+                store_material(record + 3, material);
+                accepted = true;
+            }
+        }
+        warp_append(retrace, w.queue_out, &w.counters->next_active, pixel);
+        warp_append(accepted, w.queue_nee, &w.counters->nee, pixel);
+    }
+}
+
+template <bool TRANSMISSIVE>
+__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_nee_kernel(WavefrontView w, SceneView s, FrameParams f) {
+    typedef typename SurfaceMaterialOf<TRANSMISSIVE>::type SurfaceMaterial;
+    const unsigned int count = w.counters->nee;
+    const unsigned int rounded = (count + 31u) & ~31u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool cast_shadow = false;
+        float4 shadow_o = make_float4(0, 0, 0, 0), shadow_d = make_float4(0, 0, 0, 0), shadow_rad = make_float4(0, 0, 0, 0);
+        if (i < count) {
+            const unsigned int pixel = w.queue_nee[i];
+            float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
+            const float4 r0 = record[0], r1 = record[1], r2 = record[2];
+            const SurfaceMaterial material = load_material<SurfaceMaterial>(record + 3);
+            const float3 ray_direction = f3(w.ray_d[pixel]);
+            const float4 thr4 = w.thr[pixel];
+            const float3 throughput = f3(thr4);
+            const unsigned int bounces = __float_as_uint(thr4.w);
+            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
+            const float3 world_geometric_normal = f3(r1), world_intersection_point = f3(r2);
+            const Tbn tbn(f3(r0));
+            const float3 wo = tbn.to_local(-ray_direction);
+
+            LightSample light_sample = light_sample_none();
+            if (s.light_count != 0) {
+                float4 light_random_base = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_NEE);
+                for (int k = 0; k < f.next_event_sample_count; ++k) {
+                    float4 shift = __ldg(s.nee_offsets + k);
+                    float4 r = light_random_base + shift;
+                    r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
+                    LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
+                    float light_weight = sum(light_sample.radiance);
+                    float new_light_weight = sum(candidate.radiance);
+                    float new_light_probability = fdiv(new_light_weight, light_weight + new_light_weight);
+                    if (r.w < new_light_probability) {
+                        light_sample = candidate;
+                        light_sample.radiance /= new_light_probability;
+                    } else
+                        light_sample.radiance /= 1.0f - new_light_probability;
+                }
+                light_sample.radiance /= float(f.next_event_sample_count);
+            }
+            float3 light_sample_origin = offset_ray_origin(world_intersection_point, light_sample.direction_to_light, world_geometric_normal);
+            light_sample.radiance *= throughput;
+            if (!light_sample.pdf.is_valid())
+                record[1] = f4(world_geometric_normal, 0.0f); // shade_sample_kernel disables MIS on the BSDF PDF
+
+            if (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0) {
+                cast_shadow = true;
+                shadow_o = f4(light_sample_origin, light_sample.distance);
+                shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
+                shadow_rad = f4(light_sample.radiance, 0.0f);
+            }
+        }
+        unsigned int mask = __ballot_sync(0xffffffffu, cast_shadow);
+        if (mask) {
+            int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+            unsigned int base = 0;
+            if (lane == leader) base = atomicAdd(&w.counters->shadow, __popc(mask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (cast_shadow) {
+                unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
+                w.sh_o[slot] = shadow_o; w.sh_d[slot] = shadow_d; w.sh_rad[slot] = shadow_rad;
+            }
+        }
+    }
+}
+
+template <bool TRANSMISSIVE>
+__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_sample_kernel(WavefrontView w, SceneView s, FrameParams f) {
+    typedef typename SurfaceMaterialOf<TRANSMISSIVE>::type SurfaceMaterial;
+    const unsigned int count = w.counters->nee;
+    const unsigned int rounded = (count + 31u) & ~31u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+        bool continue_path = false;
+        unsigned int pixel = 0;
+        if (i < count) {
+            pixel = w.queue_nee[i];
+            const float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
+            const float4 r0 = record[0], r1 = record[1], r2 = record[2];
+            const SurfaceMaterial material = load_material<SurfaceMaterial>(record + 3);
+            const float3 ray_direction = f3(w.ray_d[pixel]);
+            const float4 thr4 = w.thr[pixel];
+            float3 throughput = f3(thr4);
+            unsigned int bounces = __float_as_uint(thr4.w);
+            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
+            const float3 world_geometric_normal = f3(r1), world_intersection_point = f3(r2);
+            const bool light_sample_valid = r1.w != 0.0f;
+            const Tbn tbn(f3(r0));
+            const float3 wo = tbn.to_local(-ray_direction);
+            const float3 bsdf_random_uvs = f3(path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF));
+
+            BsdfSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
+            bool is_reflection = bsdf_sample.direction.z >= 0;
+            float3 next_direction = tbn.to_world(bsdf_sample.direction);
+            Pdf bsdf_pdf = bsdf_sample.pdf;
+            if (bsdf_sample.pdf.is_valid())
+                throughput *= bsdf_sample.reflectance * fabsf(bsdf_sample.direction.z) / bsdf_sample.pdf.value();
+            else
+                throughput = f3(0.0f);
+
+            float cos_geometric_theta_i = dot(next_direction, world_geometric_normal);
+            if (is_reflection ? cos_geometric_theta_i < 0.0f : cos_geometric_theta_i >= 0.0f)
+                next_direction = reflect(next_direction, world_geometric_normal);
+
+            const float3 next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
+            if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
+                float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
+                float u = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
+                if (u < survival) throughput = throughput / survival;
+                else throughput = f3(0.0f);
+            }
+            bounces += 1u;
+            if (!light_sample_valid)
+                bsdf_pdf.disable_MIS();
+
+            continue_path = bounces <= f.max_bounce_count && !is_black(throughput);
+            if (continue_path) {
+                w.ray_o[pixel] = f4(next_origin, 0.0f);
+                w.ray_d[pixel] = f4(next_direction, bsdf_pdf.v);
+                w.thr[pixel] = f4(throughput, __uint_as_float(bounces));
+            }
+        }
+        warp_append(continue_path, w.queue_out, &w.counters->next_active, pixel);
+    }
+}
+
+// The three kernels share one queue and one counter: the Default/Diffuse and the Transmissive paths of an iteration run one
+// after the other, and the counter is cleared in between.
+__global__ void reset_nee_counter_kernel(QueueCounters* c) { c->nee = 0; }
+#endif // BPT_SHADE_SPLIT
+
 // ---- accumulate / resolve --------------------------------------------------------------------------------
 
 // accumulate<>, SimpleRGPs.cu:74-107. The reference keeps a running mean in fp64; here the fp64 SUM and the
@@ -605,6 +897,9 @@ void release_wavefront(Context* ctx) {
     wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
     wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
     wf->queue_surface.release(); wf->queue_escaped.release();
+#if BPT_SHADE_SPLIT
+    wf->queue_nee.release(); wf->record.release();
+#endif
     wf->counters.release(); wf->coverage.release();
     delete wf;
     ctx->wavefront = nullptr;
@@ -633,6 +928,9 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_a.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_b.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_surface.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_escaped.resize(pixels));
+#if BPT_SHADE_SPLIT
+        BPT_CUDA_CHECK(ctx, wf->queue_nee.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->record.resize(7 * pixels)); // RECORD_FLOAT4S per pixel
+#endif
         BPT_CUDA_CHECK(ctx, wf->counters.resize(1));
         wf->pixel_capacity = pixels;
     }
@@ -695,6 +993,9 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     w.sh_o = wf->sh_o.ptr; w.sh_d = wf->sh_d.ptr; w.sh_rad = wf->sh_rad.ptr;
     w.queue_surface = wf->queue_surface.ptr; w.queue_escaped = wf->queue_escaped.ptr;
     w.queue_capacity = (unsigned int)pixels;
+#if BPT_SHADE_SPLIT
+    w.queue_nee = wf->queue_nee.ptr; w.record = wf->record.ptr;
+#endif
     w.counters = wf->counters.ptr;
     w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
 
@@ -727,11 +1028,25 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
                 extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
                 shade_kernel<false, false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+#if BPT_SHADE_SPLIT
+                shade_setup_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                shade_nee_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                shade_sample_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                ctx->counters.kernel_launches += 2;
+                if (ctx->has_transmissive_materials) {
+                    reset_nee_counter_kernel<<<1, 1, 0, st>>>(w.counters);
+                    shade_setup_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                    shade_nee_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                    shade_sample_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
+                    ctx->counters.kernel_launches += 4;
+                }
+#else
                 shade_kernel<true, false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
                 if (ctx->has_transmissive_materials) {
                     shade_kernel<true, true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
                     ctx->counters.kernel_launches++;
                 }
+#endif
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
                 shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
                 if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);

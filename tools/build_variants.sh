@@ -10,3 +10,5 @@ build odsq   "-DBPT_OUTLINE_DIV=1 -DBPT_OUTLINE_SQRT=1"
 build pl2    "-DBPT_PARKED_LEAVES=2"
 build sb64   "-DBPT_SHADE_BLOCK=64 -DBPT_SHADE_MIN_BLOCKS=16"
 build odsqpl "-DBPT_OUTLINE_DIV=1 -DBPT_OUTLINE_SQRT=1 -DBPT_PARKED_LEAVES=2"
+build split  "-DBPT_SHADE_SPLIT=1"
+build splito "-DBPT_SHADE_SPLIT=1 -DBPT_OUTLINE_DIV=1 -DBPT_OUTLINE_SQRT=1"
