@@ -140,7 +140,9 @@ def run_reference(args):
     if args.russian_roulette:
         settings["russian_roulette_start"] = args.russian_roulette
     steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
-    r = cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=max(2.0, 60.0 / (steps + warmup)))
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: ask for every core this process may run on instead
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    r = cpu_oracle_run(scene, settings, steps, warmup, target_seconds_per_step=max(2.0, 60.0 / (steps + warmup)), threads=threads)
     line = {"impl": "reference", "metric": "Msamples/s", "value": r["msamples_per_s"], "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "mrays_per_s": r["mrays_per_s"],
@@ -283,7 +285,10 @@ def main():
     if distributed:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = W * H * e2e_steps * world / float(te.item()) / 1e6
-    assert np.isfinite(frame.view(np.float16).astype(np.float32)).all()
+    frame_finite = bool(np.isfinite(frame.view(np.float16).astype(np.float32)).all())
+    nonfinite = torch.tensor([float(ctx.counters()["nonfinite_samples"]) + float(counters["nonfinite_samples"]), 0.0 if frame_finite else 1.0], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(nonfinite, op=dist.ReduceOp.SUM)
 
     if rank == 0:
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": device_ms / K,
@@ -296,6 +301,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.Settings)),
                         "d2h_bytes_per_step": int(frame.nbytes), "steps": e2e_steps},
                 "gpu_launches": int(counters["kernel_launches"]), "gpu_launches_per_step": launches_per_step,
+                "nonfinite_samples": int(nonfinite[0].item()), "frames_with_nonfinite_pixels": int(nonfinite[1].item()),
                 "roofline": roofline, "clocks": clocks}
         if not args.no_cpu_baseline and world == 1 and cpu_baseline_available():
             r = cpu_oracle_run(scene, settings, steps=3, warmup=1, target_seconds_per_step=4.0)

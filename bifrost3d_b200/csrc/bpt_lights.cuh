@@ -249,9 +249,12 @@ struct EnvironmentView {
     float3 tint;
 };
 
+// Utils.h:288-292, with one deviation: direction.y is clamped to [-1, 1] first. A normalised bounce direction can come
+// out as y = 1 + 1 ulp at the zenith; asinf then returns NaN, which the reference hands to the texture unit (rtTex2D
+// tolerates a NaN coordinate) but which a software bilinear fetch turns into NaN radiance that the fp64 sum never loses.
 BPT_D float2 direction_to_latlong_texcoord(float3 direction) {
     float u = fdiv((atan2f(direction.z, direction.x) + PI_F) * 0.5f, PI_F);
-    float v = fdiv(asinf(direction.y) + PI_F * 0.5f, PI_F);
+    float v = fdiv(asinf(fminf(fmaxf(direction.y, -1.0f), 1.0f)) + PI_F * 0.5f, PI_F);
     return f2(u, v);
 }
 
@@ -297,7 +300,7 @@ BPT_D LightSample sample_radiance(const EnvironmentView& e, float2 u) {
 
 BPT_D Pdf pdf(const EnvironmentView& e, float3 direction_to_light) {
     float2 uv = direction_to_latlong_texcoord(direction_to_light);
-    float sin_theta = fsqrt(1.0f - direction_to_light.y * direction_to_light.y);
+    float sin_theta = fsqrt(fmaxf(0.0f, 1.0f - direction_to_light.y * direction_to_light.y)); // |y| = 1 + 1 ulp: see above
     float p = fdiv(fetch_pdf_nearest(e, uv), sin_theta);
     return sin_theta == 0.0f ? Pdf::delta_dirac(0.0f) : Pdf(p);
 }

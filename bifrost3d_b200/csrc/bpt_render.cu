@@ -855,14 +855,19 @@ __global__ void reset_nee_counter_kernel(QueueCounters* c) { c->nee = 0; }
 // accumulate<>, SimpleRGPs.cu:74-107. The reference keeps a running mean in fp64; here the fp64 SUM and the
 // sample count are kept (mean = sum / count on resolve), which lets sample ranges rendered on different GPUs be
 // combined with one sum-reduce.
-__global__ void accumulate_kernel(const float4* __restrict__ rad, double* __restrict__ accum, int64_t pixel_count) {
+// A sample whose radiance is not finite is dropped (neither the sum nor the pixel's sample count change) and counted in
+// bpt_counters.nonfinite_samples: a single NaN would otherwise poison the pixel's fp64 sum for the rest of the render.
+__global__ void accumulate_kernel(const float4* __restrict__ rad, double* __restrict__ accum, int64_t pixel_count, unsigned long long* __restrict__ nonfinite) {
+    unsigned int dropped = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
         float4 r = rad[p];
+        if (!(isfinite(r.x) && isfinite(r.y) && isfinite(r.z))) { ++dropped; continue; }
         double2* a = reinterpret_cast<double2*>(accum + 4 * p);
         double2 rg = a[0], bw = a[1];
         rg.x += (double)r.x; rg.y += (double)r.y; bw.x += (double)r.z; bw.y += 1.0;
         a[0] = rg; a[1] = bw;
     }
+    if (dropped) atomicAdd(nonfinite, (unsigned long long)dropped);
 }
 
 __global__ void resolve_half4_kernel(const double* __restrict__ accum, ushort4* __restrict__ out, int64_t pixel_count, float scale) {
@@ -1069,7 +1074,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
             if (done > 4096) return ctx->fail(BPT_ERROR_CUDA, "bpt_render: path queue did not drain");
             planned = 2;
         }
-        accumulate_kernel<<<stream_grid, 256, 0, st>>>(wf->rad.ptr, ctx->accumulation.ptr, pixels);
+        accumulate_kernel<<<stream_grid, 256, 0, st>>>(wf->rad.ptr, ctx->accumulation.ptr, pixels, w.ray_counters + 6);
         ctx->counters.kernel_launches++;
         ctx->counters.samples += (uint64_t)pixels;
     }

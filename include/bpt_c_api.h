@@ -110,6 +110,7 @@ typedef struct bpt_counters {
     float other_ms;
     uint64_t extend_node_visits;     /* diagnostics, only filled by builds with -DBPT_TRAVERSAL_STATS */
     uint64_t extend_triangle_tests;
+    uint64_t nonfinite_samples;      /* pixel samples whose radiance was NaN / inf: dropped from the accumulation, counted here */
 } bpt_counters;
 
 /* ---- context ----------------------------------------------------------------------------------- */

@@ -473,14 +473,21 @@ inline LightSample env_sample_radiance(const EnvironmentIn& e, float2 u) {
     s.radiance *= e.tint;
     return s;
 }
+// Deviation from Utils.h:288-292 (shared with the product, bpt_lights.cuh): direction.y is clamped to [-1, 1] before asinf.
+// A normalised direction can be y = 1 + 1 ulp; the reference then passes a NaN coordinate to the texture unit, which
+// tolerates it, while this software fetch would return NaN radiance.
+inline float2 latlong_texcoord_clamped(float3 direction) {
+    direction.y = fminf(fmaxf(direction.y, -1.0f), 1.0f);
+    return direction_to_latlong_texcoord(direction);
+}
 inline PDF env_pdf(const EnvironmentIn& e, float3 direction_to_light) {
-    float2 uv = direction_to_latlong_texcoord(direction_to_light);
-    float sin_theta = sqrtf(1.0f - direction_to_light.y * direction_to_light.y);
+    float2 uv = latlong_texcoord_clamped(direction_to_light);
+    float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - direction_to_light.y * direction_to_light.y));
     float p = env_fetch_pdf(e, uv) / sin_theta;
     return sin_theta == 0.0f ? PDF::delta_dirac(0) : PDF(p);
 }
 inline float3 env_evaluate(const EnvironmentIn& e, float3 direction_to_light) {
-    float2 uv = direction_to_latlong_texcoord(direction_to_light);
+    float2 uv = latlong_texcoord_clamped(direction_to_light);
     return e.tint * env_fetch_bilinear(e, uv);
 }
 

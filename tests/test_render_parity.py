@@ -339,3 +339,56 @@ def test_per_vertex_emission_matches_oracle(bpt):
     scenes.upload(bpt, plain)
     bpt.render(plain["camera"], 64, 64, 0, 4, reset=True)
     assert rel_mse(bpt.resolve_float4(), cpu) > 1e-4  # the buffer changes the image
+
+
+# ---- full-size checks (parity at the sizes that are benchmarked) ---------------------------------------------
+
+@pytest.mark.gpu
+@needs_oracle
+def test_material_grid_full_res_finite(bpt):
+    """configs[2] at full size. Samples 57 and 67 hold bounce directions that normalise to y = 1 + 1 ulp (zenith): asinf(y) is
+    NaN there, which a software bilinear fetch turned into NaN radiance in round 1 (pixels (1063, 631) and (765, 367)).
+    Both the product and the oracle clamp y now; every pixel must be finite, nothing may be dropped by the accumulation, and
+    the two rows must match the oracle sample for sample."""
+    scene = scenes.material_grid()
+    W, H = scene["width"], scene["height"]
+    assert (W, H) == (1920, 1080)
+    scenes.upload(bpt, scene)
+    sc = oracle_lib.OracleScene(scene)
+    try:
+        for sample, (x, y) in ((57, (1063, 631)), (67, (765, 367))):
+            bpt.counters(reset=True)
+            bpt.render(scene["camera"], W, H, sample, 1, reset=True)
+            gpu = bpt.resolve_float4()
+            assert np.isfinite(gpu).all(), f"sample {sample}: {np.argwhere(~np.isfinite(gpu[..., 0]))[:4]}"
+            assert bpt.counters()["nonfinite_samples"] == 0
+            accum, _ = sc.render(scene["camera"], W, H, sample, 1, rows=(y, y + 1))
+            cpu = (accum[y, :, :3] / accum[y, :, 3:4]).astype(np.float32)
+            assert np.isfinite(cpu).all()
+            diff = np.abs(gpu[y, :, :3] - cpu).max(axis=-1)
+            close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
+            print(f"sample {sample} row {y}: pixel ({x},{y}) gpu {gpu[y, x, :3]} cpu {cpu[x]}; within 1e-4: {close.mean():.4f}")
+            assert close[x], "the formerly NaN pixel matches the oracle"
+            assert close.mean() > 0.97
+    finally:
+        sc.close()
+
+
+@pytest.mark.gpu
+@needs_oracle
+@pytest.mark.parametrize("workload", ["cornell", "materials"])
+def test_full_resolution_one_sample_image_parity(bpt, workload):
+    """One sample of every pixel of configs[1] (1024 x 1024) / configs[2] (1920 x 1080) against the CPU integrator: the same
+    relMSE bound and per-pixel agreement as the small scenes, at the size bench.py measures."""
+    scene = scenes.cornell_box() if workload == "cornell" else scenes.material_grid()
+    W, H = scene["width"], scene["height"]
+    gpu, cpu, counters, oc = render_both(bpt, scene, W, H, 1, first=3)
+    assert np.isfinite(gpu).all() and np.isfinite(cpu).all()
+    e = rel_mse(gpu, cpu)
+    diff = np.abs(gpu[..., :3] - cpu).max(axis=-1)
+    close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
+    print(f"{workload} {W}x{H}: relMSE {e:.3e}; pixels within 1e-4: {close.mean():.5f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
+    assert e <= REL_MSE_BOUND
+    assert close.mean() > 0.97
+    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.002 * int(oc[0])
+    assert abs(int(counters["shadow_rays"]) - int(oc[1])) <= 0.002 * int(oc[1])
