@@ -62,10 +62,11 @@ LIGHT_SAMPLE_DTYPE = np.dtype([("radiance", "<f4", 3), ("pdf", "<f4"), ("directi
 INSTANCE_DTYPE = np.dtype([("mesh_id", "<i4"), ("material_id", "<i4"), ("to_world", "<f4", 12)])
 assert MATERIAL_DTYPE.itemsize == 64 and LIGHT_DTYPE.itemsize == 48 and LIGHT_SAMPLE_DTYPE.itemsize == 32 and INSTANCE_DTYPE.itemsize == 56
 
-LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_SPOT = 1, 2, 5
+LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_ENVIRONMENT, LIGHT_PRESAMPLED_ENVIRONMENT, LIGHT_SPOT = 1, 2, 3, 4, 5
+ENVIRONMENT_NEE_PRESAMPLED, ENVIRONMENT_NEE_CDF = 0, 1
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_mesh_emission", "bpt_remove_mesh", "bpt_set_instances",
-           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
+           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
@@ -134,6 +135,8 @@ def load_library():
     lib.bpt_set_materials.argtypes = [vp, vp, i32]
     lib.bpt_set_lights.argtypes = [vp, vp, i32]
     lib.bpt_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]
+    lib.bpt_set_environment_cdfs.argtypes = [vp, vp, vp, i32, i32]
+    lib.bpt_set_environment_sampling.argtypes = [vp, i32]
     lib.bpt_build_accel.argtypes = [vp]
     lib.bpt_accel_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
     lib.bpt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), i32, i32, u32, u32, i32]
@@ -286,6 +289,19 @@ class Bpt:
         pdf = _f32(per_pixel_pdf); assert pdf.ndim == 2
         s = np.ascontiguousarray(samples, dtype=LIGHT_SAMPLE_DTYPE)
         self._check(self.lib.bpt_set_environment(self.h, _ptr(t), _ptr(tex), tex.shape[1], tex.shape[0], _ptr(pdf), pdf.shape[1], pdf.shape[0], _ptr(s), s.shape[0]))
+
+    def set_environment_cdfs(self, marginal_cdf=None, conditional_cdf=None):
+        """Distribution2D CDFs of the environment map: marginal (H + 1), conditional (H, W + 1); None, None removes them."""
+        if marginal_cdf is None:
+            self._check(self.lib.bpt_set_environment_cdfs(self.h, None, None, 0, 0))
+            return
+        m = _f32(marginal_cdf); c = _f32(conditional_cdf)
+        assert m.ndim == 1 and c.ndim == 2 and m.shape[0] == c.shape[0] + 1
+        self._check(self.lib.bpt_set_environment_cdfs(self.h, _ptr(m), _ptr(c), c.shape[1] - 1, c.shape[0]))
+
+    def set_environment_sampling(self, mode):
+        """mode: "presampled" (the reference renderer's behaviour) or "cdf" (CDF inversion on the device)."""
+        self._check(self.lib.bpt_set_environment_sampling(self.h, {"presampled": ENVIRONMENT_NEE_PRESAMPLED, "cdf": ENVIRONMENT_NEE_CDF}[mode]))
 
     def build_accel(self):
         self._check(self.lib.bpt_build_accel(self.h))

@@ -166,8 +166,7 @@ __global__ void default_shading_regularized_kernel(int64_t n, const Material* __
 
 __global__ void light_batch_kernel(int64_t n, const Light* __restrict__ lights, int light_stride, const float* __restrict__ position,
                                    const float* __restrict__ u2, const float* __restrict__ query, bpt_light_sample* out_samples,
-                                   float* out_pdf, float* out_radiance) {
-    EnvironmentView env = {};
+                                   float* out_pdf, float* out_radiance, EnvironmentView env) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         Light light = lights[light_stride ? i : 0];
         float3 p = f3(position[3 * i], position[3 * i + 1], position[3 * i + 2]);
@@ -177,7 +176,8 @@ __global__ void light_batch_kernel(int64_t n, const Light* __restrict__ lights, 
         Pdf pdf = Pdf::invalid();
         float3 e = f3(0.0f);
         uint32_t type = light_type(light);
-        if (type == BPT_LIGHT_SPHERE || type == BPT_LIGHT_SPOT || type == BPT_LIGHT_DIRECTIONAL) {
+        const bool environment = (type == BPT_LIGHT_ENVIRONMENT || type == BPT_LIGHT_PRESAMPLED_ENVIRONMENT) && env.texels != nullptr;
+        if (type == BPT_LIGHT_SPHERE || type == BPT_LIGHT_SPOT || type == BPT_LIGHT_DIRECTIONAL || environment) {
             s = light_sample_radiance(light, env, p, u);
             pdf = light_pdf(light, env, p, q);
             e = light_evaluate(light, env, p, q);
@@ -661,6 +661,7 @@ int bpt_set_environment(bpt_ctx* c, const float tint[3], const float* texels, in
     cudaSetDevice(ctx->device);
     memcpy(ctx->env_tint, tint, 3 * sizeof(float));
     ctx->env_light_uploaded = false;
+    ctx->env_has_cdfs = false; // the CDFs belong to one map: bpt_set_environment_cdfs follows bpt_set_environment
     if (!texels) {
         ctx->env_width = ctx->env_height = ctx->env_pdf_width = ctx->env_pdf_height = ctx->env_sample_count = 0;
         return BPT_OK;
@@ -673,6 +674,31 @@ int bpt_set_environment(bpt_ctx* c, const float tint[3], const float* texels, in
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->env_width = width; ctx->env_height = height; ctx->env_pdf_width = pdf_width; ctx->env_pdf_height = pdf_height;
     ctx->env_sample_count = sample_count;
+    return BPT_OK;
+}
+
+int bpt_set_environment_cdfs(bpt_ctx* c, const float* marginal_cdf, const float* conditional_cdf, int pdf_width, int pdf_height) {
+    Context* ctx = as_context(c);
+    cudaSetDevice(ctx->device);
+    ctx->env_light_uploaded = false;
+    if (!marginal_cdf && !conditional_cdf) { ctx->env_has_cdfs = false; return BPT_OK; }
+    if (!marginal_cdf || !conditional_cdf) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment_cdfs: both CDFs or none");
+    if (ctx->env_width <= 0) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_set_environment_cdfs: call bpt_set_environment with a map first");
+    if (pdf_width != ctx->env_pdf_width || pdf_height != ctx->env_pdf_height)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment_cdfs: the CDFs must have the size of the per pixel PDF");
+    BPT_CUDA_CHECK(ctx, upload(ctx, ctx->env_marginal_cdf, marginal_cdf, (size_t)pdf_height + 1));
+    BPT_CUDA_CHECK(ctx, upload(ctx, ctx->env_conditional_cdf, conditional_cdf, (size_t)(pdf_width + 1) * pdf_height));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->env_has_cdfs = true;
+    return BPT_OK;
+}
+
+int bpt_set_environment_sampling(bpt_ctx* c, int mode) {
+    Context* ctx = as_context(c);
+    if (mode != BPT_ENVIRONMENT_NEE_PRESAMPLED && mode != BPT_ENVIRONMENT_NEE_CDF)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment_sampling: unknown mode");
+    if (ctx->env_nee_mode != mode) ctx->env_light_uploaded = false;
+    ctx->env_nee_mode = mode;
     return BPT_OK;
 }
 
@@ -832,7 +858,7 @@ int bpt_light_sample_pdf_evaluate(bpt_ctx* c, int64_t n, const bpt_light* lights
         Scratch s(ctx);
         auto d_l = s.in(lights, light_stride ? n : 1); auto d_p = s.in(position, 3 * n); auto d_u = s.in(u2, 2 * n); auto d_q = s.in(query_direction, 3 * n);
         auto o_s = s.out<bpt_light_sample>(n); auto o_p = s.out<float>(n); auto o_r = s.out<float>(3 * n);
-        light_batch_kernel<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(n, d_l, light_stride, d_p, d_u, d_q, o_s, o_p, o_r);
+        light_batch_kernel<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(n, d_l, light_stride, d_p, d_u, d_q, o_s, o_p, o_r, environment_view(ctx, true));
         ctx->counters.kernel_launches++;
         s.back(out_samples, o_s, n); s.back(out_pdf, o_p, n); s.back(out_radiance, o_r, 3 * n);
     }

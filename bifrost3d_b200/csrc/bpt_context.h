@@ -147,6 +147,9 @@ struct Context {
     DeviceBuffer<bpt_light_sample> env_samples;
     int env_width = 0, env_height = 0, env_pdf_width = 0, env_pdf_height = 0, env_sample_count = 0;
     float env_tint[3] = {0.0f, 0.0f, 0.0f};
+    DeviceBuffer<float> env_marginal_cdf, env_conditional_cdf; // bpt_set_environment_cdfs; sized for env_pdf_width x env_pdf_height
+    bool env_has_cdfs = false;
+    int env_nee_mode = 0; // BPT_ENVIRONMENT_NEE_PRESAMPLED / BPT_ENVIRONMENT_NEE_CDF
 
     Accel accel;
 

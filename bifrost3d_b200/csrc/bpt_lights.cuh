@@ -7,6 +7,7 @@
 //   TBN          .../TBN.h:27-58, compute_tangents Utils.h:347-356
 //   environment  .../PresampledEnvironmentLightImpl.h:17-55, latlong mapping Utils.h:288-301
 #pragma once
+#include "bpt_context.h"
 #include "bpt_shading.cuh"
 
 namespace bpt {
@@ -247,6 +248,10 @@ struct EnvironmentView {
     const bpt_light_sample* samples;
     int sample_count;
     float3 tint;
+    // 2-D distribution of the map for CDF inversion on the device (EnvironmentLightImpl.h:22-83): marginal CDF, pdf_height + 1
+    // floats, and one conditional CDF row of pdf_width + 1 floats per PDF row (Distribution2D.h:172-207). nullptr = not uploaded.
+    const float* marginal_cdf;
+    const float* conditional_cdf;
 };
 
 // Utils.h:288-292, with one deviation: direction.y is clamped to [-1, 1] first. A normalised bounce direction can come
@@ -298,6 +303,65 @@ BPT_D LightSample sample_radiance(const EnvironmentView& e, float2 u) {
     return s;
 }
 
+// Utils.h:294-301
+BPT_D float3 latlong_texcoord_to_direction(float2 uv) {
+    float phi = uv.x * 2.0f * PI_F;
+    float theta = uv.y * PI_F;
+    float sin_theta, cos_theta, sin_phi, cos_phi;
+    sincos_(theta, sin_theta, cos_theta);
+    sincos_(phi, sin_phi, cos_phi);
+    return -f3(sin_theta * cos_phi, cos_theta, sin_theta * sin_phi);
+}
+
+// sample_CDFs_for_uv, EnvironmentLightImpl.h:22-66: two binary searches (marginal CDF for the row, that row's conditional CDF
+// for the column; the reference reads them through unfiltered integer-coordinate textures) and an inverse lerp inside the
+// bracketing pair. 10 + 11 dependent loads for a 2048 x 1024 map, all but the last few from a handful of hot cache lines.
+BPT_D float2 sample_cdfs_for_uv(const EnvironmentView& e, float2 random_sample) {
+    float2 uv;
+    int conditional_row;
+    {
+        int lowerbound = 0, upperbound = e.pdf_height;
+        while (lowerbound + 1 != upperbound) {
+            int middlebound = (lowerbound + upperbound) / 2;
+            float cdf = __ldg(e.marginal_cdf + middlebound);
+            if (random_sample.y < cdf) upperbound = middlebound; else lowerbound = middlebound;
+        }
+        conditional_row = lowerbound;
+        float cdf_at_lowerbound = __ldg(e.marginal_cdf + lowerbound);
+        float dv = random_sample.y - cdf_at_lowerbound;
+        dv = fdiv(dv, __ldg(e.marginal_cdf + lowerbound + 1) - cdf_at_lowerbound);
+        uv.y = fdiv(float(lowerbound) + dv, float(e.pdf_height));
+    }
+    {
+        const float* __restrict__ row = e.conditional_cdf + (long long)conditional_row * (e.pdf_width + 1);
+        int lowerbound = 0, upperbound = e.pdf_width;
+        while (lowerbound + 1 != upperbound) {
+            int middlebound = (lowerbound + upperbound) / 2;
+            float cdf = __ldg(row + middlebound);
+            if (random_sample.x < cdf) upperbound = middlebound; else lowerbound = middlebound;
+        }
+        float cdf_at_lowerbound = __ldg(row + lowerbound);
+        float du = random_sample.x - cdf_at_lowerbound;
+        du = fdiv(du, __ldg(row + lowerbound + 1) - cdf_at_lowerbound);
+        uv.x = fdiv(float(lowerbound) + du, float(e.pdf_width));
+    }
+    return uv;
+}
+
+// sample_radiance(EnvironmentLight), EnvironmentLightImpl.h:69-83: importance sampling by CDF inversion.
+BPT_D LightSample sample_radiance_cdf(const EnvironmentView& e, float2 u) {
+    if (e.marginal_cdf == nullptr) return light_sample_none();
+    float2 uv = sample_cdfs_for_uv(e, u);
+    LightSample s;
+    s.direction_to_light = latlong_texcoord_to_direction(uv);
+    s.distance = 1e30f;
+    s.radiance = fetch_bilinear(e, uv) * e.tint;
+    float sin_theta = fsqrt(fmaxf(0.0f, 1.0f - s.direction_to_light.y * s.direction_to_light.y));
+    float p = fdiv(fetch_pdf_nearest(e, uv), sin_theta);
+    s.pdf = Pdf(sin_theta == 0.0f ? 0.0f : p);
+    return s;
+}
+
 BPT_D Pdf pdf(const EnvironmentView& e, float3 direction_to_light) {
     float2 uv = direction_to_latlong_texcoord(direction_to_light);
     float sin_theta = fsqrt(fmaxf(0.0f, 1.0f - direction_to_light.y * direction_to_light.y)); // |y| = 1 + 1 ulp: see above
@@ -317,6 +381,7 @@ BPT_CALL1 LightSample light_sample_radiance(const Light& light, const Environmen
     switch (light_type(light)) {
     case BPT_LIGHT_SPHERE: return sphere_light::sample_radiance(as_sphere(light), position, u);
     case BPT_LIGHT_DIRECTIONAL: return directional_light::sample_radiance(as_directional(light));
+    case BPT_LIGHT_ENVIRONMENT: return environment_light::sample_radiance_cdf(env, u);
     case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::sample_radiance(env, u);
     case BPT_LIGHT_SPOT: return spot_light::sample_radiance(as_spot(light), position, u);
     }
@@ -327,6 +392,7 @@ BPT_D Pdf light_pdf(const Light& light, const EnvironmentView& env, float3 lit_p
     switch (light_type(light)) {
     case BPT_LIGHT_SPHERE: return sphere_light::pdf(as_sphere(light), lit_position, direction_to_light);
     case BPT_LIGHT_DIRECTIONAL: return Pdf::delta_dirac(0.0f);
+    case BPT_LIGHT_ENVIRONMENT:
     case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::pdf(env, direction_to_light);
     case BPT_LIGHT_SPOT: return spot_light::pdf(as_spot(light), lit_position, direction_to_light);
     }
@@ -337,10 +403,24 @@ BPT_D float3 light_evaluate(const Light& light, const EnvironmentView& env, floa
     switch (light_type(light)) {
     case BPT_LIGHT_SPHERE: return sphere_light::evaluate(as_sphere(light), position);
     case BPT_LIGHT_DIRECTIONAL: return f3(0.0f);
+    case BPT_LIGHT_ENVIRONMENT:
     case BPT_LIGHT_PRESAMPLED_ENVIRONMENT: return environment_light::evaluate(env, direction_to_light);
     case BPT_LIGHT_SPOT: return spot_light::evaluate(as_spot(light), position, direction_to_light);
     }
     return f3(0.0f);
+}
+
+// The context's environment as the kernels see it; CDFs only when the host uploaded them and asked for CDF inversion.
+inline EnvironmentView environment_view(const Context* ctx, bool with_cdfs) {
+    EnvironmentView e = {};
+    e.tint = f3(ctx->env_tint[0], ctx->env_tint[1], ctx->env_tint[2]);
+    if (ctx->env_width > 0) {
+        e.texels = ctx->env_texels.ptr; e.width = ctx->env_width; e.height = ctx->env_height;
+        e.per_pixel_pdf = ctx->env_pdf.ptr; e.pdf_width = ctx->env_pdf_width; e.pdf_height = ctx->env_pdf_height;
+        e.samples = ctx->env_samples.ptr; e.sample_count = ctx->env_sample_count;
+        if (with_cdfs && ctx->env_has_cdfs) { e.marginal_cdf = ctx->env_marginal_cdf.ptr; e.conditional_cdf = ctx->env_conditional_cdf.ptr; }
+    }
+    return e;
 }
 
 // MonteCarlo.h:20-35

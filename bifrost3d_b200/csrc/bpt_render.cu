@@ -967,26 +967,21 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     s.lights = ctx->lights.ptr;
     s.analytic_light_count = ctx->light_count;
     s.light_count = ctx->light_count;
-    s.env = {};
-    s.env.tint = f3(ctx->env_tint[0], ctx->env_tint[1], ctx->env_tint[2]);
-    if (ctx->env_width > 0) {
-        s.env.texels = ctx->env_texels.ptr; s.env.width = ctx->env_width; s.env.height = ctx->env_height;
-        s.env.per_pixel_pdf = ctx->env_pdf.ptr; s.env.pdf_width = ctx->env_pdf_width; s.env.pdf_height = ctx->env_pdf_height;
-        s.env.samples = ctx->env_samples.ptr; s.env.sample_count = ctx->env_sample_count;
-        if (ctx->env_sample_count > 1) {
-            // next_event_estimation_possible (PresampledEnvironmentMap.h:64): the environment is appended to the light list
-            // (Renderer.cpp:1180-1195). bpt_set_lights reserved the slot.
-            if (!ctx->lights.ptr) BPT_CUDA_CHECK(ctx, ctx->lights.resize(1));
-            if (!ctx->env_light_uploaded) {
-                Light env_light = {};
-                env_light.flags = BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
-                BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
-                BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-                ctx->env_light_uploaded = true;
-            }
-            s.lights = ctx->lights.ptr;
-            s.light_count = ctx->light_count + 1;
+    const bool env_by_cdf = ctx->env_nee_mode == BPT_ENVIRONMENT_NEE_CDF;
+    s.env = environment_view(ctx, env_by_cdf);
+    if (ctx->env_width > 0 && ctx->env_sample_count > 1) {
+        // next_event_estimation_possible (PresampledEnvironmentMap.h:64): the environment is appended to the light list
+        // (Renderer.cpp:1180-1195). bpt_set_lights reserved the slot.
+        if (!ctx->lights.ptr) BPT_CUDA_CHECK(ctx, ctx->lights.resize(1));
+        if (!ctx->env_light_uploaded) {
+            Light env_light = {};
+            env_light.flags = env_by_cdf ? BPT_LIGHT_ENVIRONMENT : BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
+            BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
+            BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+            ctx->env_light_uploaded = true;
         }
+        s.lights = ctx->lights.ptr;
+        s.light_count = ctx->light_count + 1;
     }
     s.tables = ctx->tables.ptr;
     s.dielectric_tables = ctx->dielectric_tables.ptr;

@@ -278,4 +278,7 @@ def upload(ctx, scene):
     ctx.set_lights(scene["lights"])
     env = scene.get("environment", {"tint": (0, 0, 0)})
     ctx.set_environment(env["tint"], env.get("texels"), env.get("per_pixel_pdf"), env.get("samples"))
+    if env.get("marginal_cdf") is not None and env["per_pixel_pdf"].shape == env["conditional_cdf"][:, 1:].shape:
+        ctx.set_environment_cdfs(env["marginal_cdf"], env["conditional_cdf"])
+    ctx.set_environment_sampling(env.get("nee", "presampled"))
     ctx.build_accel()

@@ -185,6 +185,20 @@ int bpt_set_lights(bpt_ctx* ctx, const bpt_light* lights, int count);
 int bpt_set_environment(bpt_ctx* ctx, const float tint[3], const float* texels, int width, int height,
                         const float* per_pixel_pdf, int pdf_width, int pdf_height,
                         const bpt_light_sample* samples, int sample_count);
+/* The 2-D distribution of the environment map for importance sampling by CDF inversion ON THE DEVICE
+ * (Shading/LightSources/EnvironmentLightImpl.h:22-83, the `EnvironmentLight` of Types.h:244-271): marginal_cdf holds
+ * pdf_height + 1 floats, conditional_cdf pdf_height rows of pdf_width + 1 floats, normalised as Distribution2D::compute_CDFs
+ * leaves them (core/Bifrost/Bifrost/Math/Distribution2D.h:172-207; the host reads them from InfiniteAreaLight::
+ * get_image_marginal_CDF / get_image_conditional_CDF, InfiniteAreaLight.h:66-69). Call after bpt_set_environment (which
+ * drops the CDFs of the previous map); pdf_width x pdf_height must equal the per pixel PDF's size. NULL, NULL removes them. */
+int bpt_set_environment_cdfs(bpt_ctx* ctx, const float* marginal_cdf, const float* conditional_cdf, int pdf_width, int pdf_height);
+/* How next event estimation samples the environment. PRESAMPLED (default) is what the reference's renderer does
+ * (Renderer.cpp:1180-1195, PresampledEnvironmentLightImpl.h:22-27): pick one of the presampled lights. CDF inverts the 2-D
+ * CDF per sample (Light::Environment, LightImpl.h:38-52) and needs bpt_set_environment_cdfs; without CDFs the environment
+ * then yields no light samples, like EnvironmentLightImpl.h:70. BSDF-sampled rays that escape are evaluated the same way
+ * (texel + per pixel PDF) in both modes. */
+enum { BPT_ENVIRONMENT_NEE_PRESAMPLED = 0, BPT_ENVIRONMENT_NEE_CDF = 1 };
+int bpt_set_environment_sampling(bpt_ctx* ctx, int mode);
 /* Acceleration structure build; replaces OptiX Trbvh (Renderer.cpp:161-182,470-477). Flattens the
  * instances to world space, builds the LBVH on the device. Must be called after meshes/instances change. */
 int bpt_build_accel(bpt_ctx* ctx);

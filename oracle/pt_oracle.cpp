@@ -126,6 +126,7 @@ struct EnvironmentIn {
     std::vector<float> pdf; int pdf_width = 0, pdf_height = 0;
     std::vector<LightSample> samples;
     float3 tint = { 0, 0, 0 };
+    std::vector<float> marginal_cdf, conditional_cdf; // Distribution2D CDFs for Light::Environment (CDF inversion per sample)
 };
 
 struct Scene {
@@ -480,6 +481,48 @@ inline float2 latlong_texcoord_clamped(float3 direction) {
     direction.y = fminf(fmaxf(direction.y, -1.0f), 1.0f);
     return direction_to_latlong_texcoord(direction);
 }
+// sample_CDFs_for_uv + sample_radiance(EnvironmentLight), EnvironmentLightImpl.h:22-83. The reference reads the CDFs through
+// unfiltered textures at integer coordinates (plain array reads here), the map bilinearly and the per pixel PDF nearest.
+inline LightSample env_sample_radiance_cdf(const EnvironmentIn& e, float2 random_sample) {
+    if (e.marginal_cdf.empty()) return LightSample::none();
+    float2 uv;
+    int conditional_row = 0;
+    {
+        int lowerbound = 0, upperbound = e.pdf_height;
+        while (lowerbound + 1 != upperbound) {
+            int middlebound = (lowerbound + upperbound) / 2;
+            float cdf = e.marginal_cdf[middlebound];
+            if (random_sample.y < cdf) upperbound = middlebound; else lowerbound = middlebound;
+        }
+        conditional_row = lowerbound;
+        float cdf_at_lowerbound = e.marginal_cdf[lowerbound];
+        float dv = random_sample.y - cdf_at_lowerbound;
+        dv /= e.marginal_cdf[lowerbound + 1] - cdf_at_lowerbound;
+        uv.y = (lowerbound + dv) / float(e.pdf_height);
+    }
+    {
+        const float* row = e.conditional_cdf.data() + (size_t)conditional_row * (e.pdf_width + 1);
+        int lowerbound = 0, upperbound = e.pdf_width;
+        while (lowerbound + 1 != upperbound) {
+            int middlebound = (lowerbound + upperbound) / 2;
+            float cdf = row[middlebound];
+            if (random_sample.x < cdf) upperbound = middlebound; else lowerbound = middlebound;
+        }
+        float cdf_at_lowerbound = row[lowerbound];
+        float du = random_sample.x - cdf_at_lowerbound;
+        du /= row[lowerbound + 1] - cdf_at_lowerbound;
+        uv.x = (lowerbound + du) / float(e.pdf_width);
+    }
+    LightSample sample;
+    sample.direction_to_light = latlong_texcoord_to_direction(uv);
+    sample.distance = 1e30f;
+    sample.radiance = env_fetch_bilinear(e, uv);
+    sample.radiance *= e.tint;
+    float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - sample.direction_to_light.y * sample.direction_to_light.y));
+    float PDF = env_fetch_pdf(e, uv) / sin_theta;
+    sample.PDF = sin_theta == 0.0f ? 0.0f : PDF;
+    return sample;
+}
 inline PDF env_pdf(const EnvironmentIn& e, float3 direction_to_light) {
     float2 uv = latlong_texcoord_clamped(direction_to_light);
     float sin_theta = sqrtf(fmaxf(0.0f, 1.0f - direction_to_light.y * direction_to_light.y));
@@ -496,6 +539,7 @@ LightSample light_sample_radiance(const Scene& sc, const Light& light, float3 po
     switch (light.get_type()) {
     case Light::Sphere: return LightSources::sample_radiance(light.sphere, position, u);
     case Light::Directional: return LightSources::sample_radiance(light.directional, u);
+    case Light::Environment: return env_sample_radiance_cdf(sc.env, u);
     case Light::PresampledEnvironment: return env_sample_radiance(sc.env, u);
     case Light::Spot: return LightSources::sample_radiance(light.spot, position, u);
     default: return LightSample::none();
@@ -932,6 +976,18 @@ void pto_scene_set_environment(void* s, const float* tint, const float* texels, 
         sc->light_count++;
         sc->env_in_light_list = true;
     }
+}
+// Light::Environment instead of Light::PresampledEnvironment for next event estimation (bpt_set_environment_cdfs +
+// bpt_set_environment_sampling(BPT_ENVIRONMENT_NEE_CDF) on the product side). Call after pto_scene_set_environment.
+void pto_scene_set_environment_cdfs(void* s, const float* marginal, const float* conditional, int pdf_width, int pdf_height, int sample_by_cdf) {
+    Scene* sc = (Scene*)s;
+    EnvironmentIn& e = sc->env;
+    e.marginal_cdf.clear(); e.conditional_cdf.clear();
+    if (marginal && conditional && pdf_width == e.pdf_width && pdf_height == e.pdf_height) {
+        e.marginal_cdf.assign(marginal, marginal + pdf_height + 1);
+        e.conditional_cdf.assign(conditional, conditional + (size_t)(pdf_width + 1) * pdf_height);
+    }
+    if (sc->env_in_light_list) sc->lights.back().flags = sample_by_cdf ? Light::Environment : Light::PresampledEnvironment;
 }
 void pto_scene_build(void* s) { Scene* sc = (Scene*)s; flatten(*sc); build_bvh(*sc); }
 int64_t pto_triangle_count(void* s) { return (int64_t)((Scene*)s)->triangles.size(); }

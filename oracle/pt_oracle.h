@@ -22,6 +22,8 @@ void pto_scene_set_materials(void* scene, const void* materials, int count);
 void pto_scene_set_lights(void* scene, const void* lights, int count);
 void pto_scene_set_environment(void* scene, const float* tint, const float* texels, int width, int height, const float* pdf, int pdf_width,
                                int pdf_height, const void* samples, int sample_count);
+void pto_scene_set_environment_cdfs(void* scene, const float* marginal_cdf, const float* conditional_cdf, int pdf_width, int pdf_height,
+                                    int sample_by_cdf);
 void pto_scene_build(void* scene);                      /* flatten to world space + median split BVH */
 int64_t pto_triangle_count(void* scene);
 void pto_world_vertices(void* scene, float* out9);

@@ -377,6 +377,38 @@ int ref_environment_build(const float* texels, int width, int height, int reques
     return produced;
 }
 
+// The reference's own importance sampling of an environment map at caller-supplied random points:
+// InfiniteAreaLight::sample (InfiniteAreaLight.h:90-101, Distribution2D::sample_continuous) and InfiniteAreaLight::PDF of the
+// sampled direction (:103-110). Also exports the distribution's CDFs (marginal: pdf_height + 1 floats, conditional:
+// pdf_height x (pdf_width + 1) floats) so that the product can be fed the reference's own tables.
+int ref_environment_sample(const float* texels, int width, int height, int64_t n, const float* points /*2n*/, float* out_samples /*8n*/,
+                           float* out_pdf_of_direction /*n*/, float* marginal_cdf, float* conditional_cdf) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    static bool allocated = false;
+    if (!allocated) { Images::allocate(4u); Textures::allocate(4u); allocated = true; }
+    Image image = Image::create2D("environment", PixelFormat::RGBA_Float, false, Math::Vector2ui(width, height));
+    memcpy(image.get_pixels(), texels, sizeof(float) * 4 * size_t(width) * height);
+    Texture latlong = Textures::create2D(image.get_ID(), MagnificationFilter::Linear, MinificationFilter::Linear, WrapMode::Repeat, WrapMode::Clamp);
+    {
+        InfiniteAreaLight light(latlong);
+        int pw = light.get_PDF_width(), ph = light.get_PDF_height();
+        if (marginal_cdf) memcpy(marginal_cdf, light.get_image_marginal_CDF(), sizeof(float) * (ph + 1));
+        if (conditional_cdf) memcpy(conditional_cdf, light.get_image_conditional_CDF(), sizeof(float) * size_t(pw + 1) * ph);
+        #pragma omp parallel for schedule(dynamic, 64)
+        for (int64_t i = 0; i < n; ++i) {
+            Assets::LightSample sample = light.sample(Math::Vector2f(points[2 * i], points[2 * i + 1]));
+            float* o = out_samples + 8 * i;
+            o[0] = sample.radiance.r; o[1] = sample.radiance.g; o[2] = sample.radiance.b; o[3] = sample.PDF;
+            o[4] = sample.direction_to_light.x; o[5] = sample.direction_to_light.y; o[6] = sample.direction_to_light.z; o[7] = sample.distance;
+            if (out_pdf_of_direction) out_pdf_of_direction[i] = light.PDF(sample.direction_to_light);
+        }
+    }
+    Textures::destroy(latlong.get_ID());
+    Images::destroy(image.get_ID());
+    return 0;
+}
+
 // MIS balance heuristic (MonteCarlo.h:20-35).
 void ref_balance_heuristic(int64_t n, const float* pdf1, const float* pdf2, float* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = MonteCarlo::balance_heuristic(pdf1[i], pdf2[i]);

@@ -156,6 +156,7 @@ class OracleScene:
         for name in ("pto_scene_set_instances", "pto_scene_set_materials", "pto_scene_set_lights"):
             getattr(lib, name).argtypes = [vp, vp, i32]; getattr(lib, name).restype = None
         lib.pto_scene_set_environment.argtypes = [vp, vp, vp, i32, i32, vp, i32, i32, vp, i32]; lib.pto_scene_set_environment.restype = None
+        lib.pto_scene_set_environment_cdfs.argtypes = [vp, vp, vp, i32, i32, i32]; lib.pto_scene_set_environment_cdfs.restype = None
         lib.pto_scene_set_mesh_emission.argtypes = [vp, i32, vp, i32]; lib.pto_scene_set_mesh_emission.restype = None
         lib.pto_scene_set_mesh_texcoords.argtypes = [vp, i32, vp, i32]; lib.pto_scene_set_mesh_texcoords.restype = None
         lib.pto_scene_add_texture.argtypes = [vp, i32, i32, i32, i32, i32, i32, i32, i32, vp]; lib.pto_scene_add_texture.restype = None
@@ -194,6 +195,9 @@ class OracleScene:
         else:
             tex = _f32(env["texels"]); pdf = _f32(env["per_pixel_pdf"]); s = np.ascontiguousarray(env["samples"])
             lib.pto_scene_set_environment(self.h, _p(tint), _p(tex), tex.shape[1], tex.shape[0], _p(pdf), pdf.shape[1], pdf.shape[0], _p(s), s.shape[0])
+            if env.get("marginal_cdf") is not None and env["conditional_cdf"].shape[1] - 1 == pdf.shape[1]:
+                m = _f32(env["marginal_cdf"]); c = _f32(env["conditional_cdf"])
+                lib.pto_scene_set_environment_cdfs(self.h, _p(m), _p(c), pdf.shape[1], pdf.shape[0], int(env.get("nee", "presampled") == "cdf"))
         lib.pto_scene_build(self.h)
 
     def close(self):
@@ -248,3 +252,18 @@ def reference_environment(texels, sample_count=8192):
     samples = np.zeros((n, 8), np.float32)
     produced = lib.ref_environment_build(_p(tex), w, h, sample_count, C.byref(pw), C.byref(ph), _p(pdf), _p(samples), C.byref(integral))
     return {"per_pixel_pdf": pdf[: pw.value * ph.value].reshape(ph.value, pw.value), "samples": samples[:produced], "integral": integral.value}
+
+
+def reference_environment_sample(texels, points):
+    """InfiniteAreaLight::sample at `points` (n x 2 in [0, 1)) and InfiniteAreaLight::PDF of the sampled directions, plus the
+    reference's own marginal / conditional CDFs of the map (oracle/ref_api.cpp: ref_environment_sample)."""
+    lib = load().lib
+    lib.ref_environment_sample.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64] + [C.c_void_p] * 5
+    lib.ref_environment_sample.restype = C.c_int
+    tex = _f32(texels); h, w = tex.shape[:2]
+    assert h >= 128, "lower maps are resampled by the reference (InfiniteAreaLight.cpp:45-52)"
+    pts = _f32(points).reshape(-1, 2); n = pts.shape[0]
+    samples = np.zeros((n, 8), np.float32); pdf = np.zeros(n, np.float32)
+    marginal = np.zeros(h + 1, np.float32); conditional = np.zeros((h, w + 1), np.float32)
+    lib.ref_environment_sample(_p(tex), w, h, n, _p(pts), _p(samples), _p(pdf), _p(marginal), _p(conditional))
+    return {"samples": samples, "pdf_of_direction": pdf, "marginal_cdf": marginal, "conditional_cdf": conditional}
