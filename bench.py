@@ -216,7 +216,14 @@ def main():
     from bifrost3d_b200.sharding import sample_range
     first = sample_range(rank, K, warmup=Wm)[0] - Wm
     # ---- device-timed region -----------------------------------------------------------------------
+    if distributed:
+        # The library's own communicator (NCCL bound inside libbpt.so): rank 0 creates the unique id, torch.distributed only carries it.
+        ids = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], world, rank)
     ctx.render(cam, W, H, first, Wm, reset=True, **settings)  # warm-up
+    if distributed:
+        ctx.reduce_accumulation(0)  # warm-up of the collective too: NCCL sets its channels up on first use
     barrier()
     ctx.counters(reset=True)
     sampler = ClockSampler(local_rank); sampler.start()
@@ -224,11 +231,9 @@ def main():
     e0.record(stream)
     ctx.render(cam, W, H, first + Wm, K, reset=True, **settings)
     if distributed:
-        # combine the per-GPU radiance sums: one NCCL reduce over NVLink of the double4 accumulation buffer
-        ctx.synchronize()
-        acc = accumulation_tensor(ctx, W, H, local_rank)
-        dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.current_stream().synchronize()
+        # combine the per-GPU radiance sums: one ncclReduce over NVLink of the double4 accumulation buffer, enqueued on the
+        # render stream behind the last sample (no host synchronisation inside the timed region)
+        ctx.reduce_accumulation(0)
     e1.record(stream)
     barrier()
     device_ms = e0.elapsed_time(e1)

@@ -67,7 +67,7 @@ ENVIRONMENT_NEE_PRESAMPLED, ENVIRONMENT_NEE_CDF = 0, 1
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_mesh_emission", "bpt_remove_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
-           "bpt_accumulation_device_ptr", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
+           "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect"]
 
@@ -142,6 +142,12 @@ def load_library():
     lib.bpt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), i32, i32, u32, u32, i32]
     lib.bpt_render_aov.argtypes = [vp, C.POINTER(Camera), i32, i32, i32, u32, u32, i32]
     lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
+    lib.bpt_comm_unique_id.argtypes = [vp]
+    lib.bpt_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.bpt_comm_destroy.argtypes = [vp]
+    lib.bpt_reduce_accumulation.argtypes = [vp, i32]
+    lib.bpt_select_accumulation.argtypes = [vp, i32]
+    lib.bpt_release_accumulation.argtypes = [vp, i32]
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
     lib.bpt_resolve_half4_async.argtypes = [vp, vp, i32]
     lib.bpt_wait_frame.argtypes = [vp, i32]
@@ -328,6 +334,41 @@ class Bpt:
 
     def accumulation_device_ptr(self):
         return self.lib.bpt_accumulation_device_ptr(self.h)
+
+    # ---- multi-GPU (NCCL bound at run time inside libbpt.so) ----
+    def comm_unique_id(self):
+        """ncclGetUniqueId as 128 plain bytes (rank 0 creates it, the host distributes it)."""
+        buf = C.create_string_buffer(128)
+        status = self.lib.bpt_comm_unique_id(buf)
+        if status != 0:
+            raise BptError(f"bpt_comm_unique_id failed with status {status}: libnccl.so.2 not loadable?")
+        return buf.raw
+
+    def comm_init(self, unique_id, rank_count, rank):
+        assert len(unique_id) == 128
+        self._check(self.lib.bpt_comm_init(self.h, C.create_string_buffer(unique_id, 128), int(rank_count), int(rank)))
+
+    def comm_destroy(self):
+        self._check(self.lib.bpt_comm_destroy(self.h))
+
+    def reduce_accumulation(self, root=0):
+        """Sum of all ranks' selected accumulation targets into `root` (ncclReduce on the render stream); root < 0: all-reduce."""
+        self._check(self.lib.bpt_reduce_accumulation(self.h, int(root)))
+
+    def select_accumulation(self, slot):
+        """One accumulation target per camera (Renderer.cpp:199-222): render / resolve act on the selected slot."""
+        sizes = self.__dict__.setdefault("_target_sizes", {})
+        sizes[getattr(self, "_slot", 0)] = getattr(self, "_size", None)
+        self._check(self.lib.bpt_select_accumulation(self.h, int(slot)))
+        self._slot = int(slot)
+        self._size = sizes.get(self._slot)
+
+    def release_accumulation(self, slot):
+        self._check(self.lib.bpt_release_accumulation(self.h, int(slot)))
+        if int(slot) == getattr(self, "_slot", 0):
+            self._size = None
+        else:
+            self.__dict__.setdefault("_target_sizes", {}).pop(int(slot), None)
 
     def resolve_float4(self):
         w, h = self._size

@@ -375,6 +375,7 @@ void bpt_destroy(bpt_ctx* c) {
     Context* ctx = as_context(c);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    bpt_comm_destroy(c);
     release_wavefront(ctx);
     ctx->tables.release(); ctx->dielectric_tables.release(); ctx->nee_offsets.release(); ctx->materials.release(); ctx->lights.release();
     ctx->env_texels.release(); ctx->env_pdf.release(); ctx->env_samples.release();
@@ -383,6 +384,7 @@ void bpt_destroy(bpt_ctx* c) {
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release(); ctx->accel.shade_emission.release();
     ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
+    for (auto& target : ctx->parked_targets) target.second.buffer.release();
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->frame_resolved[i]); cudaEventDestroy(ctx->frame_copied[i]); ctx->frame_staging[i].release(); }
@@ -731,6 +733,40 @@ int bpt_render_aov(bpt_ctx* c, const bpt_camera* camera, int aov_kind, int width
 }
 
 void* bpt_accumulation_device_ptr(bpt_ctx* c) { return as_context(c)->accumulation.ptr; }
+
+int bpt_select_accumulation(bpt_ctx* c, int slot) {
+    Context* ctx = as_context(c);
+    if (slot < 0) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_select_accumulation: slot must be >= 0");
+    if (slot == ctx->selected_target) return BPT_OK;
+    // Work already enqueued on the stream keeps using the buffers it was given; only the host-side selection moves.
+    Context::AccumulationTarget& parked = ctx->parked_targets[ctx->selected_target];
+    parked.buffer = ctx->accumulation; parked.width = ctx->width; parked.height = ctx->height; parked.half4_scale = ctx->half4_scale;
+    auto it = ctx->parked_targets.find(slot);
+    if (it != ctx->parked_targets.end()) {
+        ctx->accumulation = it->second.buffer; ctx->width = it->second.width; ctx->height = it->second.height; ctx->half4_scale = it->second.half4_scale;
+        ctx->parked_targets.erase(it);
+    } else {
+        ctx->accumulation = DeviceBuffer<double>(); ctx->width = ctx->height = 0; ctx->half4_scale = 1.0f;
+    }
+    ctx->selected_target = slot;
+    return BPT_OK;
+}
+
+int bpt_release_accumulation(bpt_ctx* c, int slot) {
+    Context* ctx = as_context(c);
+    cudaSetDevice(ctx->device);
+    if (slot == ctx->selected_target) {
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->accumulation.release(); ctx->width = ctx->height = 0; ctx->half4_scale = 1.0f;
+        return BPT_OK;
+    }
+    auto it = ctx->parked_targets.find(slot);
+    if (it == ctx->parked_targets.end()) return BPT_OK;
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    it->second.buffer.release();
+    ctx->parked_targets.erase(it);
+    return BPT_OK;
+}
 int bpt_resolve_half4(bpt_ctx* c, uint16_t* out, int on_device) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_half4(ctx, out, on_device); }
 int bpt_resolve_half4_async(bpt_ctx* c, uint16_t* out_host, int slot) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return resolve_half4_async(ctx, out_host, slot); }
 int bpt_wait_frame(bpt_ctx* c, int slot) { Context* ctx = as_context(c); cudaSetDevice(ctx->device); return wait_frame(ctx, slot); }

@@ -153,7 +153,11 @@ struct Context {
 
     Accel accel;
 
-    // Render state
+    // Render state. `accumulation`, `width`, `height` and `half4_scale` are those of the SELECTED accumulation target
+    // (bpt_select_accumulation: one per camera, Renderer.cpp:199-222); the others are parked in `parked_targets`.
+    struct AccumulationTarget { DeviceBuffer<double> buffer; int width = 0, height = 0; float half4_scale = 1.0f; };
+    std::map<int, AccumulationTarget> parked_targets;
+    int selected_target = 0;
     int width = 0, height = 0;
     DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
     DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
@@ -167,6 +171,10 @@ struct Context {
     uint64_t material_version = 0;
     bool env_light_uploaded = false;
     void* wavefront = nullptr;         // integrator-owned state (bpt_render.cu)
+
+    // Multi-GPU (bpt_comm.cu): ncclComm_t of this rank, bound at run time.
+    void* comm = nullptr;
+    int comm_rank = 0, comm_rank_count = 1;
 
     bpt_counters counters = {};
     uint64_t* device_counters = nullptr; // [extend, shadow]

@@ -84,6 +84,7 @@ struct Renderer::Implementation {
         bool initialized = false;
     };
     std::vector<CameraState> per_camera_state;
+    static constexpr int SCRATCH_ACCUMULATION_SLOT = 0x7fffffff; // request_auxiliary_buffers renders here
 
     int next_event_sample_count = 3;                         // Renderer.cpp:479
     PathRegularizationSettings path_regularization = { 0.5f, 0.0f }; // Renderer.cpp:482-483
@@ -143,6 +144,9 @@ struct Renderer::Implementation {
         int pixel_count = frame_size.x * frame_size.y;
         bpt_camera camera = camera_of(camera_ID);
         std::vector<float> mean(4 * size_t(pixel_count));
+        // The features are rendered into a scratch accumulation target (Renderer.cpp:1280 allocates scratch buffers), so the
+        // camera's own progressive accumulation is left alone.
+        check(ctx, bpt_select_accumulation(ctx, SCRATCH_ACCUMULATION_SLOT), "bpt_select_accumulation");
         auto render_feature = [&](int aov) {
             check(ctx, bpt_render_aov(ctx, &camera, aov, frame_size.x, frame_size.y, 0, accumulation_count, 1), "bpt_render_aov");
             check(ctx, bpt_resolve_float4(ctx, mean.data()), "bpt_resolve_float4");
@@ -168,8 +172,7 @@ struct Renderer::Implementation {
             for (int i = 0; i < pixel_count; ++i) pixels[i] = UNorm8::to_byte(half_round(mean[4 * i]));
             screenshots.emplace_back(frame_size.x, frame_size.y, Screenshot::Content::Roughness, PixelFormat::Intensity8, pixels);
         }
-        // the scratch render replaced the camera's accumulation: restart it
-        per_camera_state[camera_ID].accumulations = 0u;
+        check(ctx, bpt_release_accumulation(ctx, SCRATCH_ACCUMULATION_SLOT), "bpt_release_accumulation");
         return screenshots;
     }
 
@@ -387,6 +390,7 @@ struct Renderer::Implementation {
             auto changes = Cameras::get_changes(cam_ID);
             if (changes.contains(Cameras::Change::Destroyed)) {
                 if (cam_ID < per_camera_state.size()) per_camera_state[cam_ID] = CameraState();
+                check(ctx, bpt_release_accumulation(ctx, int((unsigned int)cam_ID)), "bpt_release_accumulation");
                 continue;
             }
             bool uses_this_renderer = owning_renderer_ID == Cameras::get_renderer_ID(cam_ID);
@@ -477,6 +481,8 @@ struct Renderer::Implementation {
         settings.next_event_sample_count = next_event_sample_count;
         settings.path_regularization_pdf_scale = path_regularization.PDF_scale_at_accumulation(int(state.accumulations));
 
+        // One accumulation target per camera, Renderer.cpp:199-222.
+        check(ctx, bpt_select_accumulation(ctx, int((unsigned int)camera_ID)), "bpt_select_accumulation");
         int status;
         int aov = aov_of(state.backend);
         if (state.backend == Backend::AIDenoisedPathTracing) {

@@ -219,8 +219,32 @@ int bpt_render(bpt_ctx* ctx, const bpt_camera* camera, const bpt_settings* setti
 enum { BPT_AOV_DEPTH = 3, BPT_AOV_ALBEDO = 4, BPT_AOV_TINT = 5, BPT_AOV_ROUGHNESS = 6, BPT_AOV_SHADING_NORMAL = 7, BPT_AOV_PRIMITIVE_ID = 8 };
 int bpt_render_aov(bpt_ctx* ctx, const bpt_camera* camera, int aov_kind, int width, int height,
                    uint32_t first_sample, uint32_t sample_count, int reset_accumulation);
+/* Accumulation targets. The reference keeps one accumulation buffer per camera (Renderer.cpp:199-222) and renders auxiliary
+ * screenshots into scratch buffers (:1280). A context owns any number of targets, addressed by a caller-chosen slot >= 0
+ * (the host shim uses the CameraID); bpt_render, bpt_render_aov, bpt_resolve_*, bpt_accumulation_device_ptr and
+ * bpt_reduce_accumulation act on the SELECTED target. Slot 0 is selected after bpt_create; a slot is created (empty) the first
+ * time it is selected. Selecting is host-side bookkeeping only: no device work, no synchronisation. */
+int bpt_select_accumulation(bpt_ctx* ctx, int slot);
+/* Frees the device memory of a target (waits for the stream). Releasing the selected slot leaves it selected and empty. */
+int bpt_release_accumulation(bpt_ctx* ctx, int slot);
 /* Device pointer to the double4[width*height] accumulation (sum) buffer, e.g. for an NCCL reduce. */
 void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
+/* ---- multi-GPU: sample-index sharding -------------------------------------------------------------
+ * The reference renders on one device (Renderer.cpp:289-291). Here every rank (one process per GPU) uploads the same scene,
+ * renders a disjoint range of accumulation indices (`first_sample`) into its own fp64 sum buffer, and ONE collective adds the
+ * buffers: sum and sample count (w) both add, so bpt_resolve_* on the root yields the mean over all ranks' samples.
+ * NCCL is loaded at run time (libnccl.so.2; BPT_NCCL_LIB overrides the path); single-GPU hosts never touch it.
+ *   rank 0:    bpt_comm_unique_id(id); send `id` to the other ranks by any means (MPI, socket, file, torch.distributed)
+ *   all ranks: bpt_comm_init(ctx, id, rank_count, rank); ... bpt_render(...) ...; bpt_reduce_accumulation(ctx, 0);
+ *   root:      bpt_resolve_half4(...)                                                                                 */
+enum { BPT_COMM_ID_BYTES = 128 }; /* sizeof(ncclUniqueId) */
+int bpt_comm_unique_id(char out_id[BPT_COMM_ID_BYTES]);
+int bpt_comm_init(bpt_ctx* ctx, const char id[BPT_COMM_ID_BYTES], int rank_count, int rank);
+int bpt_comm_destroy(bpt_ctx* ctx);
+/* ncclReduce(sum, fp64) of the selected accumulation target into rank `root`'s, in place, enqueued on the context's stream
+ * after the samples already enqueued (no host synchronisation); root < 0: ncclAllReduce, every rank gets the total.
+ * All ranks must call it with the same frame size. Call it once per job: the root's buffer then already holds the total. */
+int bpt_reduce_accumulation(bpt_ctx* ctx, int root);
 /* mean = sum / w, converted to half4 (alpha 1) exactly like SimpleRGPs.cu:39-42,106; written to `out` which is
  * a HOST pointer to width*height*4 uint16 (on_device == 0) or a DEVICE pointer (on_device != 0). */
 int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
