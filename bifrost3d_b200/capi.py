@@ -48,7 +48,7 @@ class Settings(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("extend_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
-                ("extend_node_visits", C.c_uint64), ("extend_triangle_tests", C.c_uint64), ("nonfinite_samples", C.c_uint64)]
+                ("extend_node_visits", C.c_uint64), ("extend_triangle_tests", C.c_uint64), ("nonfinite_samples", C.c_uint64), ("iterations", C.c_uint64)]
 
 
 assert C.sizeof(Material) == 64 and C.sizeof(Light) == 48 and C.sizeof(LightSample) == 32
@@ -69,7 +69,7 @@ EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
-           "bpt_intersect"]
+           "bpt_intersect", "bpt_sort_pairs", "bpt_exclusive_scan"]
 
 
 class TonemapSettings(C.Structure):
@@ -146,6 +146,8 @@ def load_library():
     lib.bpt_comm_init.argtypes = [vp, vp, i32, i32]
     lib.bpt_comm_destroy.argtypes = [vp]
     lib.bpt_reduce_accumulation.argtypes = [vp, i32]
+    lib.bpt_sort_pairs.argtypes = [vp, i64, vp, vp, i32, i32]
+    lib.bpt_exclusive_scan.argtypes = [vp, i64, vp, vp, vp]
     lib.bpt_select_accumulation.argtypes = [vp, i32]
     lib.bpt_release_accumulation.argtypes = [vp, i32]
     lib.bpt_resolve_half4.argtypes = [vp, vp, i32]
@@ -448,6 +450,19 @@ class Bpt:
         self._check(self.lib.bpt_light_sample_pdf_evaluate(self.h, n, _ptr(l), stride, _ptr(position), _ptr(u2), _ptr(query_direction),
                                                            _ptr(samples), _ptr(pdf), _ptr(rad)))
         return samples, pdf, rad
+
+    def sort_pairs(self, keys, values, begin_bit=0, end_bit=64):
+        """Stable radix sort of (uint64 key, uint32 value) pairs by key bits [begin_bit, end_bit): the sort of the BVH build."""
+        k = np.array(keys, dtype=np.uint64).reshape(-1); v = np.array(values, dtype=np.uint32).reshape(-1)
+        assert k.shape == v.shape
+        self._check(self.lib.bpt_sort_pairs(self.h, k.shape[0], _ptr(k), _ptr(v), int(begin_bit), int(end_bit)))
+        return k, v
+
+    def exclusive_scan(self, values):
+        v = np.ascontiguousarray(values, dtype=np.uint32).reshape(-1)
+        out = np.empty_like(v); total = np.zeros(1, np.uint32)
+        self._check(self.lib.bpt_exclusive_scan(self.h, v.shape[0], _ptr(v), _ptr(out), _ptr(total)))
+        return out, int(total[0])
 
     def rng_sample4(self, accumulation, pixel_hash, dimension):
         a, h, d = (np.ascontiguousarray(x, dtype=np.uint32).reshape(-1) for x in (accumulation, pixel_hash, dimension))

@@ -3,6 +3,7 @@
 #include "bpt_context.h"
 #include "bpt_lights.cuh"
 #include "bpt_rng.cuh"
+#include "bpt_sort.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -289,19 +290,21 @@ void destroy_texture(DeviceTexture& t) {
 struct Scratch {
     Context* ctx;
     std::vector<void*> allocations;
+    bool failed = false; // an allocation failed: the caller returns BPT_ERROR_OUT_OF_MEMORY instead of launching with null pointers
     explicit Scratch(Context* c) : ctx(c) {}
     ~Scratch() { for (void* p : allocations) cudaFreeAsync(p, ctx->stream); cudaStreamSynchronize(ctx->stream); }
     template <typename T> T* in(const T* host, size_t n) {
         if (!host || n == 0) return nullptr;
         T* d = nullptr;
-        if (cudaMallocAsync((void**)&d, n * sizeof(T), ctx->stream) != cudaSuccess) return nullptr;
+        if (cudaMallocAsync((void**)&d, n * sizeof(T), ctx->stream) != cudaSuccess) { failed = true; cudaGetLastError(); return nullptr; }
         allocations.push_back(d);
         cudaMemcpyAsync(d, host, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
         return d;
     }
     template <typename T> T* out(size_t n) {
         T* d = nullptr;
-        if (n == 0 || cudaMallocAsync((void**)&d, n * sizeof(T), ctx->stream) != cudaSuccess) return nullptr;
+        if (n == 0) return nullptr;
+        if (cudaMallocAsync((void**)&d, n * sizeof(T), ctx->stream) != cudaSuccess) { failed = true; cudaGetLastError(); return nullptr; }
         allocations.push_back(d);
         return d;
     }
@@ -527,6 +530,7 @@ int bpt_texture_sample(bpt_ctx* c, int texture_id, int64_t n, const float* uv, f
         Scratch s(ctx);
         auto d_uv = s.in(reinterpret_cast<const float2*>(uv), n);
         auto d_out = s.out<float4>(n);
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
         texture_sample_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(it->second.object, n, d_uv, d_out);
         ctx->counters.kernel_launches++;
         s.back(reinterpret_cast<float4*>(out_rgba), d_out, n);
@@ -789,7 +793,11 @@ int bpt_get_counters(bpt_ctx* c, bpt_counters* out, int reset) {
     ctx->counters.extend_node_visits = host[2];   // only counted by builds with -DBPT_TRAVERSAL_STATS
     ctx->counters.extend_triangle_tests = host[3];
     ctx->counters.nonfinite_samples = host[6];
-    if (out) *out = ctx->counters;
+    ctx->counters.iterations = host[7];
+    if (out) {
+        *out = ctx->counters;
+        out->kernel_launches += host[7] * (uint64_t)ctx->launches_per_iteration; // wavefront iterations, counted by advance_kernel
+    }
     if (reset) {
         ctx->counters = {};
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->device_counters, 0, sizeof(host), ctx->stream));
@@ -815,6 +823,8 @@ int bpt_bsdf_eval_sample_pdf(bpt_ctx* c, int kind, int64_t n, const float* wo, c
     BsdfBatchArgs a;
     a.n = n; a.tables = ctx->tables.ptr; a.dielectric_tables = ctx->dielectric_tables.ptr;
     float* staging = nullptr;
+    // frees the staging block on every exit, error paths included
+    struct StagingGuard { float*& p; cudaStream_t st; ~StagingGuard() { if (p) { cudaFreeAsync(p, st); cudaStreamSynchronize(st); } } } staging_guard = { staging, ctx->stream };
     if (on_device) {
         a.wo = wo; a.wi = wi; a.tint = tint; a.rms = rms; a.coat = coat; a.u = u;
         a.eval_f = eval_f; a.eval_pdf = eval_pdf; a.sample_f = sample_f; a.sample_pdf = sample_pdf; a.sample_dir = sample_dir;
@@ -855,9 +865,46 @@ int bpt_bsdf_eval_sample_pdf(bpt_ctx* c, int kind, int64_t n, const float* wo, c
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(sample_dir, a.sample_dir, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(eval_pdf, a.eval_pdf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(sample_pdf, a.sample_pdf, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-        BPT_CUDA_CHECK(ctx, cudaFreeAsync(staging, ctx->stream));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return BPT_OK;
+}
+
+int bpt_sort_pairs(bpt_ctx* c, int64_t n, uint64_t* keys, uint32_t* values, int begin_bit, int end_bit) {
+    Context* ctx = as_context(c);
+    if (n < 0 || n > 0x7fffffff || !keys || !values || begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_sort_pairs: bad arguments");
+    if (n == 0) return BPT_OK;
+    cudaSetDevice(ctx->device);
+    {
+        Scratch s(ctx);
+        uint64_t* d_keys = s.in(keys, n); uint32_t* d_values = s.in(values, n);
+        uint64_t* d_keys_alt = s.out<uint64_t>(n); uint32_t* d_values_alt = s.out<uint32_t>(n);
+        uint32_t* d_scratch = s.out<uint32_t>(sort::sort_scratch_words((uint32_t)n));
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
+        const int in_alt = sort::radix_sort_pairs<uint64_t>(d_keys, d_values, d_keys_alt, d_values_alt, (uint32_t)n, nullptr, begin_bit, end_bit, d_scratch,
+                                                            ctx->sm_count, ctx->stream, &ctx->counters.kernel_launches);
+        s.back(keys, in_alt ? d_keys_alt : d_keys, n); s.back(values, in_alt ? d_values_alt : d_values, n);
+    }
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
+    return BPT_OK;
+}
+
+int bpt_exclusive_scan(bpt_ctx* c, int64_t n, const uint32_t* in, uint32_t* out, uint32_t* out_total) {
+    Context* ctx = as_context(c);
+    if (n < 0 || n > 0x7fffffff || !in || !out) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_exclusive_scan: bad arguments");
+    if (n == 0) { if (out_total) *out_total = 0; return BPT_OK; }
+    cudaSetDevice(ctx->device);
+    {
+        Scratch s(ctx);
+        const uint32_t* d_in = s.in(in, n); uint32_t* d_out = s.out<uint32_t>(n);
+        uint32_t* d_scratch = s.out<uint32_t>(sort::scan_scratch_words((uint32_t)n)); uint32_t* d_total = s.out<uint32_t>(1);
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
+        sort::exclusive_scan(d_in, d_out, (uint32_t)n, nullptr, d_scratch, d_total, ctx->sm_count, ctx->stream);
+        ctx->counters.kernel_launches += sort::SCAN_LAUNCHES;
+        s.back(out, d_out, n); s.back(out_total, d_total, 1);
+    }
+    BPT_CUDA_CHECK(ctx, cudaGetLastError());
     return BPT_OK;
 }
 
@@ -875,6 +922,7 @@ int bpt_default_shading_regularized(bpt_ctx* c, int64_t n, const bpt_material* m
         auto d_m = s.in(materials, n); auto d_sc = s.in(tint_roughness_scale, 4 * n); auto d_hint = s.in(max_pdf_hint, n);
         auto d_wo = s.in(wo, 3 * n); auto d_wi = s.in(wi, 3 * n); auto d_u = s.in(u, 3 * n);
         auto o_ef = s.out<float>(3 * n); auto o_ep = s.out<float>(n); auto o_sf = s.out<float>(3 * n); auto o_sp = s.out<float>(n); auto o_sd = s.out<float>(3 * n);
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
         default_shading_regularized_kernel<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(n, d_m, d_sc, d_hint, d_wo, d_wi, d_u, ctx->tables.ptr, o_ef, o_ep, o_sf, o_sp, o_sd);
         ctx->counters.kernel_launches++;
         s.back(eval_f, o_ef, 3 * n); s.back(eval_pdf, o_ep, n); s.back(sample_f, o_sf, 3 * n); s.back(sample_pdf, o_sp, n); s.back(sample_dir, o_sd, 3 * n);
@@ -894,6 +942,7 @@ int bpt_light_sample_pdf_evaluate(bpt_ctx* c, int64_t n, const bpt_light* lights
         Scratch s(ctx);
         auto d_l = s.in(lights, light_stride ? n : 1); auto d_p = s.in(position, 3 * n); auto d_u = s.in(u2, 2 * n); auto d_q = s.in(query_direction, 3 * n);
         auto o_s = s.out<bpt_light_sample>(n); auto o_p = s.out<float>(n); auto o_r = s.out<float>(3 * n);
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
         light_batch_kernel<<<grid_for(ctx, n, 128), 128, 0, ctx->stream>>>(n, d_l, light_stride, d_p, d_u, d_q, o_s, o_p, o_r, environment_view(ctx, true));
         ctx->counters.kernel_launches++;
         s.back(out_samples, o_s, n); s.back(out_pdf, o_p, n); s.back(out_radiance, o_r, 3 * n);
@@ -912,6 +961,7 @@ int bpt_rng_sample4(bpt_ctx* c, int64_t n, const uint32_t* accumulation, const u
         Scratch s(ctx);
         auto d_a = s.in(accumulation, n); auto d_h = s.in(pixel_hash, n); auto d_d = s.in(dimension, n);
         uint4* o_u = out_ui4 ? s.out<uint4>(n) : nullptr; float4* o_f = out_f4 ? s.out<float4>(n) : nullptr;
+        if (s.failed) return ctx->cuda_fail(cudaErrorMemoryAllocation, "scratch allocation");
         rng_batch_kernel<<<grid_for(ctx, n, 256), 256, 0, ctx->stream>>>(n, d_a, d_h, d_d, o_u, o_f);
         ctx->counters.kernel_launches++;
         s.back(reinterpret_cast<uint4*>(out_ui4), o_u, n); s.back(reinterpret_cast<float4*>(out_f4), o_f, n);

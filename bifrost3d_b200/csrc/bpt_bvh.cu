@@ -7,9 +7,7 @@
 #include "bpt_context.h"
 #include "bpt_trace.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <cub/block/block_scan.cuh>
+#include "bpt_sort.cuh"
 
 #include <algorithm>
 #include <float.h>
@@ -381,8 +379,7 @@ __global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int m, const int* 
                                                               BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
     __shared__ Aabb s_box[PLOC_TAIL];
     __shared__ int s_link[PLOC_TAIL], s_depth[PLOC_TAIL], s_nearest[PLOC_TAIL];
-    typedef cub::BlockScan<int, PLOC_TAIL> BlockScan;
-    __shared__ typename BlockScan::TempStorage scan_storage;
+    __shared__ int s_warp_sums[32];
     const int i = threadIdx.x;
     if (i < m) { s_box[i] = cl_box[i]; s_link[i] = cl_link[i]; s_depth[i] = cl_depth[i]; }
     int count = m;
@@ -423,9 +420,26 @@ __global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int m, const int* 
                 atomicMax(max_depth, depth);
             }
         }
+        // exclusive scan of `keep` over the 32 warps of the block: shuffle scan inside each warp, then over the warp totals
         int position, total;
-        BlockScan(scan_storage).ExclusiveSum(keep, position, total);
-        __syncthreads(); // every read of the old cluster list is done
+        {
+            const int lane = i & 31, warp = i >> 5;
+            int inclusive = keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inclusive, o); if (lane >= o) inclusive += t; }
+            if (lane == 31) s_warp_sums[warp] = inclusive;
+            __syncthreads();
+            if (warp == 0) {
+                int w = s_warp_sums[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+                s_warp_sums[lane] = w;
+            }
+            __syncthreads();
+            position = (warp ? s_warp_sums[warp - 1] : 0) + inclusive - keep;
+            total = s_warp_sums[31];
+        }
+        __syncthreads(); // every read of the old cluster list (and of the warp totals) is done
         if (keep) { s_box[position] = box; s_link[position] = link; s_depth[position] = depth; }
         count = total;
         __syncthreads();
@@ -575,15 +589,15 @@ int build_accel(Context* ctx) {
 
 
     DeviceBuffer<InstanceRecord> d_records; DeviceBuffer<float> d_bounds;
-    DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<unsigned char> d_temp;
+    DeviceBuffer<uint64_t> d_keys, d_keys_alt; DeviceBuffer<uint32_t> d_vals, d_vals_alt; DeviceBuffer<uint32_t> d_temp;
     DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
     // PLOC scratch
     DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
-    DeviceBuffer<unsigned char> d_scan_temp;
+    DeviceBuffer<uint32_t> d_scan_temp, d_scan_total;
     DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four-wide collapse
     auto release_all = [&]() {
         d_tasks[0].release(); d_tasks[1].release(); d_counters.release();
-        d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release();
+        d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release();
         for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); }
         d_records.release(); d_bounds.release();
         d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
@@ -612,22 +626,16 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(A.nodes.resize((size_t)n + 1));
     // PLOC scratch is sized for the worst case of one cluster per triangle and allocated outside the timed region.
     const bool try_ploc = ctx->use_ploc && n > LEAF_MAX;
-    size_t scan_bytes = 0;
     if (try_ploc) {
         BUILD_CHECK(d_flag.resize(n)); BUILD_CHECK(d_pos.resize(n)); BUILD_CHECK(d_scalars.resize(2)); BUILD_CHECK(d_nearest.resize(n));
         for (int k = 0; k < 2; ++k) { BUILD_CHECK(d_link[k].resize(n)); BUILD_CHECK(d_depth[k].resize(n)); BUILD_CHECK(d_box[k].resize(n)); }
-        BUILD_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
-        BUILD_CHECK(d_scan_temp.resize(std::max<size_t>(scan_bytes, 1)));
+        BUILD_CHECK(d_scan_temp.resize(sort::scan_scratch_words(n))); BUILD_CHECK(d_scan_total.resize(1));
     }
     BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
     // every scratch buffer is allocated here, outside the timed region (cudaMalloc / cudaFree of gigabytes take tens of ms)
-    size_t temp_bytes = 0;
     if (n > 0) {
         BUILD_CHECK(d_keys.resize(n)); BUILD_CHECK(d_keys_alt.resize(n)); BUILD_CHECK(d_vals.resize(n)); BUILD_CHECK(d_vals_alt.resize(n));
-        cub::DoubleBuffer<uint64_t> keys(d_keys.ptr, d_keys_alt.ptr);
-        cub::DoubleBuffer<uint32_t> vals(d_vals.ptr, d_vals_alt.ptr);
-        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, keys, vals, n, 0, 63, st));
-        BUILD_CHECK(d_temp.resize(std::max<size_t>(temp_bytes, 1)));
+        BUILD_CHECK(d_temp.resize(sort::sort_scratch_words(n)));
         BUILD_CHECK(d_tree.resize(std::max(n - 1, 1))); BUILD_CHECK(d_parent_internal.resize(std::max(n - 1, 1)));
         BUILD_CHECK(d_parent_leaf.resize(n)); BUILD_CHECK(d_arrival.resize(std::max(n - 1, 1))); BUILD_CHECK(d_node_boxes.resize(std::max(n - 1, 1)));
     }
@@ -648,17 +656,18 @@ int build_accel(Context* ctx) {
         morton_kernel<<<grid(n), block, 0, st>>>(n, A.world_vertices.ptr, d_bounds.ptr, d_keys.ptr, d_vals.ptr);
         ctx->counters.kernel_launches++;
 
-        cub::DoubleBuffer<uint64_t> keys(d_keys.ptr, d_keys_alt.ptr);
-        cub::DoubleBuffer<uint32_t> vals(d_vals.ptr, d_vals_alt.ptr);
-        BUILD_CHECK(cub::DeviceRadixSort::SortPairs(d_temp.ptr, temp_bytes, keys, vals, n, 0, 63, st));
-        ctx->counters.kernel_launches += 8;
+        // 63-bit Morton codes: eight 8-bit passes of the radix sort in bpt_sort.cuh
+        const int sorted_in_alt = sort::radix_sort_pairs<uint64_t>(d_keys.ptr, d_vals.ptr, d_keys_alt.ptr, d_vals_alt.ptr, (uint32_t)n, nullptr, 0, 64, d_temp.ptr,
+                                                                   ctx->sm_count, st, &ctx->counters.kernel_launches);
+        const uint64_t* sorted_keys = sorted_in_alt ? d_keys_alt.ptr : d_keys.ptr;
+        const uint32_t* sorted_vals = sorted_in_alt ? d_vals_alt.ptr : d_vals.ptr;
 
         BUILD_CHECK(cudaMemsetAsync(d_arrival.ptr, 0, sizeof(int) * std::max(n - 1, 1), st));
         if (n > 1) {
-            hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, keys.Current(), d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
+            hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, sorted_keys, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
             ctx->counters.kernel_launches++;
         }
-        fit_kernel<<<full_grid(n), block, 0, st>>>(n, vals.Current(), A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr,
+        fit_kernel<<<full_grid(n), block, 0, st>>>(n, sorted_vals, A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr,
                                                    d_leaf_boxes.ptr, d_node_boxes.ptr, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr, d_arrival.ptr);
         ctx->counters.kernel_launches++;
         // ---- upper hierarchy: PLOC over the leaf clusters; the plain LBVH emit is the fallback ----
@@ -667,13 +676,12 @@ int build_accel(Context* ctx) {
 #define PLOC_CHECK(expr) BUILD_CHECK(expr)
             PLOC_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(uint32_t) * n, st));
             ploc_mark_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_flag.ptr);
-            PLOC_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_temp.ptr, scan_bytes, d_flag.ptr, d_pos.ptr, n, st));
-            uint32_t last_pos = 0, last_flag = 0;
-            PLOC_CHECK(cudaMemcpyAsync(&last_pos, d_pos.ptr + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            PLOC_CHECK(cudaMemcpyAsync(&last_flag, d_flag.ptr + (n - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            sort::exclusive_scan(d_flag.ptr, d_pos.ptr, (uint32_t)n, nullptr, d_scan_temp.ptr, d_scan_total.ptr, ctx->sm_count, st);
+            uint32_t kept = 0; // number of flags set = the scan's grand total
+            PLOC_CHECK(cudaMemcpyAsync(&kept, d_scan_total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             PLOC_CHECK(cudaStreamSynchronize(st));
-            int m = int(last_pos + last_flag);
-            ctx->counters.kernel_launches += 3;
+            int m = int(kept);
+            ctx->counters.kernel_launches += 1 + sort::SCAN_LAUNCHES;
             if (m >= 2) {
                 // m - 1 nodes from index 1 on, the root is copied to index 0: A.nodes holds n + 1 entries
                 ploc_gather_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, d_pos.ptr, d_link[0].ptr, d_box[0].ptr,
@@ -687,14 +695,13 @@ int build_accel(Context* ctx) {
                     ploc_nearest_kernel<<<full_grid(m), block, 0, st>>>(m, d_box[cur].ptr, d_nearest.ptr);
                     ploc_merge_kernel<<<full_grid(m), block, 0, st>>>(m, d_nearest.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, d_flag.ptr, A.nodes.ptr,
                                                                      d_scalars.ptr, d_scalars.ptr + 1);
-                    PLOC_CHECK(cub::DeviceScan::ExclusiveSum(d_scan_temp.ptr, scan_bytes, d_flag.ptr, d_pos.ptr, m, st));
+                    sort::exclusive_scan(d_flag.ptr, d_pos.ptr, (uint32_t)m, nullptr, d_scan_temp.ptr, d_scan_total.ptr, ctx->sm_count, st);
                     ploc_compact_kernel<<<full_grid(m), block, 0, st>>>(m, d_flag.ptr, d_pos.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr,
                                                                        d_link[cur ^ 1].ptr, d_box[cur ^ 1].ptr, d_depth[cur ^ 1].ptr);
-                    PLOC_CHECK(cudaMemcpyAsync(&last_pos, d_pos.ptr + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                    PLOC_CHECK(cudaMemcpyAsync(&last_flag, d_flag.ptr + (m - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                    PLOC_CHECK(cudaMemcpyAsync(&kept, d_scan_total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                     PLOC_CHECK(cudaStreamSynchronize(st));
-                    ctx->counters.kernel_launches += 4;
-                    int next_m = int(last_pos + last_flag);
+                    ctx->counters.kernel_launches += 3 + sort::SCAN_LAUNCHES;
+                    int next_m = int(kept);
                     if (next_m >= m || ++passes > 4096) { failed = true; break; } // cannot happen: the globally closest pair is always mutual
                     if (getenv("BPT_PLOC_DEBUG")) fprintf(stderr, "ploc pass %d: %d -> %d clusters\n", passes, m, next_m);
                     m = next_m; cur ^= 1;

@@ -177,6 +177,7 @@ struct Context {
     int comm_rank = 0, comm_rank_count = 1;
 
     bpt_counters counters = {};
+    int launches_per_iteration = 5; // kernels per wavefront iteration; the iterations themselves are counted on the device
     uint64_t* device_counters = nullptr; // [extend, shadow]
 
     cudaEvent_t ev[8] = {};

@@ -7,9 +7,12 @@
 //   interpolate_attributes                                            Shading/TriangleAttributes.cu:35-84
 //   analytic light intersect                                          Shading/LightSources/LightSources.cu:31-70
 //
-// One progressive sample of every pixel = generate -> { extend -> shade -> shadow } x bounces -> accumulate.
-// Every stage is a persistent-thread kernel over a queue of pixel indices whose length lives in device memory, so
-// the host never synchronises inside a sample. Queues are compacted with warp ballot + one atomic per warp.
+// One progressive sample of every pixel =
+//     generate -> { extend(k) || shadow(k - 1) -> shade(k) -> advance } while paths are alive -> shadow(last) -> accumulate.
+// Every stage is a persistent-thread kernel over a queue of pixel indices whose length lives in device memory. The whole
+// sample is ONE CUDA graph whose loop is a conditional WHILE node: the device decides when the queues have drained, the host
+// never synchronises inside bpt_render, and the shadow rays of bounce k - 1 are traced concurrently with the closest-hit
+// rays of bounce k (both only depend on shade(k - 1)). Queues are compacted with warp ballot + one atomic per warp.
 // Path state is SoA, indexed by pixel, in 16-byte records so every access is a 128-bit transaction.
 #include "bpt_context.h"
 #include "bpt_lights.cuh"
@@ -18,13 +21,9 @@
 
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <stdlib.h>
+#include <string.h>
 
-// Experimental (off by default, written but not yet run on a GPU): the surface shading as three kernels - set-up, next event
-// estimation, BSDF sampling - that hand a 112-byte record per path through memory. Motivation in DESIGN.md 6: the single
-// surface kernel is instruction-fetch bound (105 KB of code) and keeps 248 bytes of spills and call frames per thread.
-#ifndef BPT_SHADE_SPLIT
-#define BPT_SHADE_SPLIT 0
-#endif
 #ifndef BPT_TILED_QUEUE
 #define BPT_TILED_QUEUE 1
 #endif
@@ -40,19 +39,29 @@ constexpr int SHADE_BLOCK = BPT_SHADE_BLOCK; // threads per CTA of the shade ker
 constexpr int LIGHT_HIT_FLAG = 0x40000000; // hit.primitive = LIGHT_HIT_FLAG | light index
 constexpr float RT_DEFAULT_MAX = 1e27f;    // tmax of optix::Ray when none is given (SimpleRGPs.cu:114)
 
-// Queue counters in device memory.
+// Queue counters in device memory. Queues ping-pong: in iteration k the extend / shade kernels read queue[parity] and append
+// the continuing paths to queue[parity ^ 1]; shade(k) appends its shadow rays under shadow[parity] and the shadow kernel that
+// runs beside extend(k + 1) (parity flipped by then) reads shadow[parity ^ 1].
 struct QueueCounters {
     unsigned int active;       // entries in the current extend/shade queue
     unsigned int next_active;  // entries appended for the next iteration
-    unsigned int shadow;       // entries in the shadow queue
+    unsigned int shadow[2];    // entries in the shadow queue, by the parity of the iteration that filled it
     unsigned int fetch_extend; // dynamic ray fetch cursors of the two traversal kernels
     unsigned int fetch_shadow;
     unsigned int surface;      // paths whose ray hit a Default / Diffuse surface (shade_kernel<true, false>)
     unsigned int escaped;      // paths whose ray left the scene or hit an analytic light (shade_kernel<false, false>)
     unsigned int transmissive; // paths whose ray hit a Transmissive surface (shade_kernel<true, true>)
-#if BPT_SHADE_SPLIT
-    unsigned int nee;          // paths accepted by shade_setup_kernel: next event estimation + BSDF sampling follow
-#endif
+    unsigned int parity;       // 0 / 1, flipped by advance_kernel
+    unsigned int iteration;    // iterations of the current sample (guards against a queue that never drains)
+};
+
+// What changes from frame to frame lives in device memory, so that one instantiated graph serves every bpt_render call of a
+// scene: the host copies this small record in front of the launches, accumulate_kernel advances sample_index.
+struct FrameState {
+    bpt_camera camera;
+    float path_regularization_pdf_scale;
+    unsigned int sample_index; // accumulation index of the sample being rendered (Types.h:486-501 `accumulations`)
+    double* accumulation;      // the selected accumulation target (one per camera): double4 per pixel
 };
 
 struct Wavefront {
@@ -64,27 +73,28 @@ struct Wavefront {
     DeviceBuffer<float4> sh_o, sh_d, sh_rad;
     DeviceBuffer<unsigned int> queue_a, queue_b;
     DeviceBuffer<unsigned int> queue_surface, queue_escaped; // extend sorts its results by what shading they need
-#if BPT_SHADE_SPLIT
-    DeviceBuffer<unsigned int> queue_nee;
-    DeviceBuffer<float4> record;
-#endif
     DeviceBuffer<QueueCounters> counters;
+    DeviceBuffer<FrameState> frame_state;
     DeviceBuffer<float> coverage; // per material
     uint64_t coverage_version = ~0ull;
+
+    // The sample graph and what it was built for (rebuilt when any launch parameter changes).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    std::vector<unsigned char> graph_signature;
+    bool graph_unavailable = false; // conditional graph nodes could not be created: stream launches + host polling instead
 };
 
 struct WavefrontView {
     float4 *ray_o, *ray_d, *thr, *rad, *hit;
     float4 *sh_o, *sh_d, *sh_rad;
-    unsigned int *queue_in, *queue_out;
+    unsigned int *queue_a, *queue_b; // selected by parity with a conditional, never indexed: a dynamically indexed kernel
+                                     // parameter would make the compiler copy the whole struct to local memory
     unsigned int *queue_surface, *queue_escaped;
     unsigned int queue_capacity;      // entries per queue; the transmissive queue grows down from the end of queue_surface
-#if BPT_SHADE_SPLIT
-    unsigned int* queue_nee;          // pixels whose surface record is waiting for the NEE and BSDF sampling kernels
-    float4* record;                   // 7 float4 per pixel: shading normal + cos_theta, geometric normal + light-valid flag, point, material (4)
-#endif
     QueueCounters* counters;
-    unsigned long long* ray_counters; // [0] extend, [1] shadow
+    const FrameState* frame;
+    unsigned long long* ray_counters; // [0] extend, [1] shadow, [6] dropped non-finite samples, [7] iterations
 };
 
 struct SceneView {
@@ -105,13 +115,11 @@ struct SceneView {
     bool split_by_shading_model; // the scene has Transmissive materials: extend keys surface hits by shading model
 };
 
+// Per-configuration constants (kernel parameters, baked into the graph).
 struct FrameParams {
-    bpt_camera camera;
     int width, height;
-    unsigned int accumulation_count;
     unsigned int max_bounce_count;
     int next_event_sample_count;
-    float path_regularization_pdf_scale;
     unsigned int russian_roulette_start_bounce; // 0 = off (the reference has no Russian roulette)
 };
 
@@ -136,6 +144,9 @@ __device__ __forceinline__ float4 mul4x4(const float* m, float4 v) {
 
 __global__ void generate_kernel(WavefrontView w, FrameParams f) {
     int64_t pixel_count = (int64_t)f.width * f.height;
+    const bpt_camera& camera = w.frame->camera;
+    const unsigned int accumulation_count = w.frame->sample_index;
+    unsigned int* __restrict__ queue_in = w.queue_a; // a sample starts with parity 0
     // Queue order: 8 x 4 pixel tiles, one per warp, so that the camera rays (and the first hits) of a warp are neighbours in
     // both image directions; plain row order when the frame is not a whole number of tiles. Path state stays indexed by pixel.
     const bool tiled = BPT_TILED_QUEUE && (f.width % 8 == 0) && (f.height % 4 == 0);
@@ -149,19 +160,19 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         const int64_t p = (int64_t)y * f.width + x;
         unsigned int pixel_hash = pcg2d((unsigned int)x, (unsigned int)y).x;
         float2 jitter = f2(0.5f, 0.5f);
-        if (f.accumulation_count != 0) {
-            float4 r = path_rng_sample4f(f.accumulation_count, pixel_hash, 0u, DIM_CAMERA);
+        if (accumulation_count != 0) {
+            float4 r = path_rng_sample4f(accumulation_count, pixel_hash, 0u, DIM_CAMERA);
             jitter = f2(r.x, r.y);
         }
         float2 screen_pos = f2(float(x) + jitter.x, float(y) + jitter.y);
         float2 viewport_pos = f2(screen_pos.x / float(f.width), screen_pos.y / float(f.height));
 
         float4 ndc_near = make_float4(viewport_pos.x * 2.0f - 1.0f, viewport_pos.y * 2.0f - 1.0f, -1.0f, 1.0f);
-        float4 near_world = mul4x4(f.camera.inverse_view_projection, ndc_near);
+        float4 near_world = mul4x4(camera.inverse_view_projection, ndc_near);
         float3 origin = f3(near_world) / near_world.w;
         float4 ndc_far = make_float4(ndc_near.x, ndc_near.y, 1.0f, 1.0f);
-        float4 far_view = mul4x4(f.camera.inverse_projection, ndc_far);
-        const float* r = f.camera.view_to_world_rotation;
+        float4 far_view = mul4x4(camera.inverse_projection, ndc_far);
+        const float* r = camera.view_to_world_rotation;
         float3 v = f3(far_view);
         float3 direction = normalize(f3(r[0] * v.x + r[1] * v.y + r[2] * v.z, r[3] * v.x + r[4] * v.y + r[5] * v.z, r[6] * v.x + r[7] * v.y + r[8] * v.z));
 
@@ -169,20 +180,12 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
         w.ray_d[p] = f4(direction, Pdf::delta_dirac(1.0f).v);
         w.thr[p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(0u));
         w.rad[p] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1));
-        w.queue_in[slot] = (unsigned int)p;
+        queue_in[slot] = (unsigned int)p;
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        w.counters->active = (unsigned int)pixel_count;
-        w.counters->next_active = 0;
-        w.counters->shadow = 0;
-        w.counters->fetch_extend = 0;
-        w.counters->fetch_shadow = 0;
-        w.counters->surface = 0;
-        w.counters->escaped = 0;
-        w.counters->transmissive = 0;
-#if BPT_SHADE_SPLIT
-        w.counters->nee = 0;
-#endif
+        QueueCounters c = {};
+        c.active = (unsigned int)pixel_count;
+        *w.counters = c;
     }
 }
 
@@ -190,16 +193,19 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
 
 struct ExtendSource {
     WavefrontView w;
+    const unsigned int* __restrict__ queue_in;
     const Light* __restrict__ lights;
     int analytic_light_count;
     // Set when the scene has Transmissive materials: surface hits are then keyed by shading model.
     const ShadeTriangle* __restrict__ shade;
     const Material* __restrict__ materials;
     __device__ void load(unsigned int i, Ray& ray, int& skip) const {
-        unsigned int pixel = w.queue_in[i];
+        unsigned int pixel = queue_in[i];
         float4 o = w.ray_o[pixel], d = w.ray_d[pixel];
         ray.origin = f3(o); ray.tmin = o.w; ray.direction = f3(d); ray.tmax = RT_DEFAULT_MAX;
-        skip = __float_as_int(w.rad[pixel].w); // the primitive the path is leaving (MonteCarlo.cu:137-142)
+        // the primitive the path is leaving (MonteCarlo.cu:137-142). Only the w lane is read: the shadow kernel that runs
+        // concurrently adds to the xyz lanes of the same record.
+        skip = __float_as_int(reinterpret_cast<const float*>(w.rad + pixel)[3]);
     }
     __device__ void store(unsigned int i, const Traversal<false>& tr) const {
         Hit h = tr.result();
@@ -217,7 +223,7 @@ struct ExtendSource {
             }
             if (radius > 0.0f && t > tr.ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
         }
-        unsigned int pixel = w.queue_in[i];
+        unsigned int pixel = queue_in[i];
         w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
         // Sort the paths by the shading they need: surface hits go to the (large) surface shading kernels - keyed by the
         // material's shading model when the scene mixes them - and escaped rays and light hits to a small one, so none runs
@@ -239,7 +245,7 @@ struct ExtendSource {
 __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
-    ExtendSource source = { w, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials };
+    ExtendSource source = { w, w.counters->parity ? w.queue_b : w.queue_a, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials };
     traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
@@ -256,35 +262,41 @@ struct ShadowSource {
     __device__ void store(unsigned int i, const Traversal<true>& tr) const {
         if (tr.transmission > 0.0f) {
             unsigned int pixel = __float_as_uint(w.sh_d[i].w);
-            float4 rad = w.rad[pixel];
             float4 l = w.sh_rad[i];
-            rad.x += l.x * tr.transmission; rad.y += l.y * tr.transmission; rad.z += l.z * tr.transmission;
-            w.rad[pixel] = rad;
+            // One shadow ray per pixel and iteration, so the read-modify-write needs no atomic; the w lane (previous primitive)
+            // is left alone because the concurrent extend kernel reads it.
+            float* rad = reinterpret_cast<float*>(w.rad + pixel);
+            rad[0] += l.x * tr.transmission; rad[1] += l.y * tr.transmission; rad[2] += l.z * tr.transmission;
         }
     }
 };
 
 __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kernel(WavefrontView w, SceneView s) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    const unsigned int count = w.counters->shadow;
+    const unsigned int count = w.counters->shadow[w.counters->parity ^ 1u]; // filled by the previous iteration's shade kernels
     ShadowSource source = { w };
     traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
 }
 
-// Swaps the roles of the queues for the next iteration (the pointers are swapped on the host).
-__global__ void advance_kernel(QueueCounters* c) {
+// Ends an iteration: the appended paths become the active queue, the queue roles flip, and the graph's WHILE node is told
+// whether another iteration is needed (a null handle: the host polls `active` instead).
+constexpr unsigned int MAX_ITERATIONS_PER_SAMPLE = 4096; // rejected hits re-trace without consuming a bounce; this is only a backstop
+__global__ void advance_kernel(QueueCounters* c, unsigned long long* ray_counters, cudaGraphConditionalHandle loop_handle, int has_handle) {
+    const unsigned int parity = c->parity;
     c->active = c->next_active;
     c->next_active = 0;
-    c->shadow = 0;
+    c->shadow[parity ^ 1u] = 0; // consumed by this iteration's shadow kernel; the next iteration's shade kernels fill it
     c->fetch_extend = 0;
     c->fetch_shadow = 0;
     c->surface = 0;
     c->escaped = 0;
     c->transmissive = 0;
-#if BPT_SHADE_SPLIT
-    c->nee = 0;
-#endif
+    c->parity = parity ^ 1u;
+    c->iteration += 1u;
+    ray_counters[7] += 1ull;
+    if (c->iteration >= MAX_ITERATIONS_PER_SAMPLE) c->active = 0; // the leftover paths are dropped; never observed
+    if (has_handle) cudaGraphSetConditional(loop_handle, c->active != 0u ? 1u : 0u);
 }
 
 // ---- shade ---------------------------------------------------------------------------------------------
@@ -364,6 +376,11 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     // spills and call frames (~0.5 KB per thread) need the L1 capacity more. Measured: shade -5 %.
     const ShadingTables tables = { s.tables, s.tables + TABLE_FLOATS, s.tables + 2 * TABLE_FLOATS };
 
+    const unsigned int accumulation_count = w.frame->sample_index;
+    const float path_regularization_pdf_scale = w.frame->path_regularization_pdf_scale;
+    const unsigned int parity = w.counters->parity;
+    unsigned int* __restrict__ queue_out = parity ? w.queue_a : w.queue_b;
+    unsigned int* shadow_counter = w.counters->shadow + parity;
     const unsigned int count = SURFACE ? (TRANSMISSIVE ? w.counters->transmissive : w.counters->surface) : w.counters->escaped;
     const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count) : w.queue_surface) : w.queue_escaped;
     const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
@@ -447,7 +464,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
                 backside_cull &= !material_is_transmissive(material_parameter);
 
-                float4 bsdf_coverage_random = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF);
+                float4 bsdf_coverage_random = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_BSDF);
                 float coverage_cutoff = bsdf_coverage_random.w;
                 float3 bsdf_random_uvs = f3(bsdf_coverage_random);
                 float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
@@ -475,7 +492,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
 
                     // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
                     // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
-                    Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
+                    Pdf max_pdf_hint(bsdf_pdf.v * path_regularization_pdf_scale);
                     const auto material = [&]() {
                         if constexpr (TRANSMISSIVE)
                             return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
@@ -496,7 +513,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                     // reestimated_light_samples, MonteCarlo.cu:91-123
                     LightSample light_sample = light_sample_none();
                     if (s.light_count != 0) {
-                        float4 light_random_base = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_NEE);
+                        float4 light_random_base = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_NEE);
                         for (int k = 0; k < f.next_event_sample_count; ++k) {
                             float4 shift = __ldg(s.nee_offsets + k);
                             float4 r = light_random_base + shift; // toroidal_shift, Utils.h:46-49
@@ -536,7 +553,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                     // the largest throughput component, decided by the otherwise unused RNG dimension 3 of this bounce.
                     if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
                         float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
-                        float u = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
+                        float u = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
                         if (u < survival) throughput = throughput / survival;
                         else throughput = f3(0.0f);
                     }
@@ -564,13 +581,13 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
         }
 
         // Queue compaction: ballot + popc inside the warp, one atomic per warp and queue.
-        warp_append(continue_path, w.queue_out, &w.counters->next_active, pixel);
+        warp_append(continue_path, queue_out, &w.counters->next_active, pixel);
         {
             unsigned int mask = __ballot_sync(0xffffffffu, cast_shadow);
             if (mask) {
                 int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
                 unsigned int base = 0;
-                if (lane == leader) base = atomicAdd(&w.counters->shadow, __popc(mask));
+                if (lane == leader) base = atomicAdd(shadow_counter, __popc(mask));
                 base = __shfl_sync(0xffffffffu, base, leader);
                 if (cast_shadow) {
                     unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
@@ -581,274 +598,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     }
 }
 
-#if BPT_SHADE_SPLIT
-// ---- split surface shading (experimental) ---------------------------------------------------------------------
-// shade_setup_kernel: interpolate_attributes + the reject rules + frame and material set-up + emission
-// (TriangleAttributes.cu:35-84, MonteCarlo.cu:129-195) -> one SurfaceRecord per accepted path.
-// shade_nee_kernel:    reestimated_light_samples + shadow ray (MonteCarlo.cu:91-123,197-202, SimpleRGPs.cu:117-125).
-// shade_sample_kernel: BSDF sampling, throughput, mirror fix, ray offset, roulette (MonteCarlo.cu:204-232).
-// The arithmetic is the single kernel's, statement for statement; only the place where values live changes.
-template <bool TRANSMISSIVE> struct SurfaceMaterialOf { typedef DefaultShading type; };
-template <> struct SurfaceMaterialOf<true> { typedef TransmissiveShading type; };
-static_assert(sizeof(DefaultShading) <= 64 && sizeof(TransmissiveShading) <= 64, "a surface material must fit four float4 of the record");
-constexpr int RECORD_FLOAT4S = 7; // shading normal + cos_theta, geometric normal + light-valid flag, point, material (4)
 
-template <typename Material_>
-__device__ __forceinline__ void store_material(float4* __restrict__ slot, const Material_& m) {
-    float4 packed[4] = { make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0), make_float4(0, 0, 0, 0) };
-    memcpy(packed, &m, sizeof(Material_));
-    slot[0] = packed[0]; slot[1] = packed[1]; slot[2] = packed[2]; slot[3] = packed[3];
-}
-template <typename Material_>
-__device__ __forceinline__ Material_ load_material(const float4* __restrict__ slot) {
-    float4 packed[4] = { slot[0], slot[1], slot[2], slot[3] };
-    Material_ m;
-    memcpy(&m, packed, sizeof(Material_));
-    return m;
-}
-
-template <bool TRANSMISSIVE>
-__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_setup_kernel(WavefrontView w, SceneView s, FrameParams f) {
-    const ShadingTables tables = { s.tables, s.tables + TABLE_FLOATS, s.tables + 2 * TABLE_FLOATS };
-    const unsigned int count = TRANSMISSIVE ? w.counters->transmissive : w.counters->surface;
-    const unsigned int* __restrict__ queue = TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count) : w.queue_surface;
-    const unsigned int rounded = (count + 31u) & ~31u;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
-        bool retrace = false, accepted = false;
-        unsigned int pixel = 0;
-        if (i < count) {
-            pixel = queue[i];
-            const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
-            const float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
-            const float4 hit4 = w.hit[pixel];
-            const float3 ray_origin = f3(ro), ray_direction = f3(rd);
-            const Pdf bsdf_pdf(rd.w);
-            const float3 throughput = f3(thr4);
-            float3 radiance = f3(rad4);
-            const unsigned int bounces = __float_as_uint(thr4.w);
-            const float t_hit = hit4.x;
-            const int primitive = __float_as_int(hit4.y);
-            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
-
-            const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
-                         p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
-            const int4* shade_raw = reinterpret_cast<const int4*>(s.shade + primitive);
-            int4 sr0 = __ldg(shade_raw), sr1 = __ldg(shade_raw + 1);
-            ShadeTriangle st;
-            memcpy(&st, &sr0, 16); memcpy(reinterpret_cast<char*>(&st) + 16, &sr1, 16);
-
-            float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
-            const float bx = hit4.z, by = hit4.w;
-            const float bz = 1.0f - bx - by;
-            const float3 intersection_point = p1 * bx + p2 * by + p0 * bz;
-            const bool has_normals = st.flags & 1u, has_tints = st.flags & 2u;
-            float3 shading_normal;
-            if (has_normals) {
-                shading_normal = oct_decode(st.n1) * bx + oct_decode(st.n2) * by + oct_decode(st.n0) * bz;
-                shading_normal = normalize(shading_normal);
-            } else
-                shading_normal = geometric_normal;
-            float4 tint_and_roughness_scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-            if (has_tints) {
-                const float n255 = 1.0f / 255.0f;
-                tint_and_roughness_scale.x = (st.t1[0] * bx + st.t2[0] * by + st.t0[0] * bz) * n255;
-                tint_and_roughness_scale.y = (st.t1[1] * bx + st.t2[1] * by + st.t0[1] * bz) * n255;
-                tint_and_roughness_scale.z = (st.t1[2] * bx + st.t2[2] * by + st.t0[2] * bz) * n255;
-                tint_and_roughness_scale.w = (st.t1[3] * bx + st.t2[3] * by + st.t0[3] * bz) * n255;
-            }
-
-            const float2 texcoord = interpolate_texcoord(s.accel.textures, primitive, bx, by);
-            const Material material_parameter = material_at(s.materials[st.material_index], s.accel.textures, texcoord);
-            float3 world_geometric_normal = geometric_normal;
-            bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
-            bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
-            backside_cull &= !material_is_transmissive(material_parameter);
-
-            float4 bsdf_coverage_random = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF);
-            float coverage_cutoff = bsdf_coverage_random.w;
-            float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
-            bool discard_from_coverage = coverage < coverage_cutoff;
-
-            if (backside_cull || discard_from_coverage) {
-                w.ray_o[pixel] = f4(ray_origin, nextafterf(t_hit, INFINITY)); // same ray, advanced past this surface
-                retrace = true; // bounces and throughput are unchanged, so the path continues
-            } else {
-                world_geometric_normal = hit_from_front ? world_geometric_normal : -world_geometric_normal;
-                float3 world_shading_normal = shading_normal;
-                if (has_normals) {
-                    const float* nm = s.normal_matrices + 9 * (st.flags >> 2);
-                    world_shading_normal = normalize(f3(nm[0] * shading_normal.x + nm[1] * shading_normal.y + nm[2] * shading_normal.z,
-                                                        nm[3] * shading_normal.x + nm[4] * shading_normal.y + nm[5] * shading_normal.z,
-                                                        nm[6] * shading_normal.x + nm[7] * shading_normal.y + nm[8] * shading_normal.z));
-                }
-                world_shading_normal = hit_from_front ? world_shading_normal : -world_shading_normal;
-                world_shading_normal = fix_backfacing_shading_normal(-ray_direction, world_shading_normal, 0.002f);
-                const Tbn tbn(world_shading_normal);
-                const float3 wo = tbn.to_local(-ray_direction);
-                float cos_theta = hit_from_front || material_is_thin_walled(material_parameter) ? wo.z : -wo.z;
-
-                Pdf max_pdf_hint(bsdf_pdf.v * f.path_regularization_pdf_scale);
-                const auto material = [&]() {
-                    if constexpr (TRANSMISSIVE)
-                        return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
-                                                                       cos_theta, max_pdf_hint);
-                    else
-                        return material_parameter.shading_model == SHADING_DIFFUSE
-                            ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
-                            : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
-                }();
-
-                float3 emission = f3(1.0f);
-                if (s.shade_emission != nullptr) {
-                    const float* e = s.shade_emission + 9ll * primitive;
-                    emission = f3(e[3], e[4], e[5]) * bx + f3(e[6], e[7], e[8]) * by + f3(e[0], e[1], e[2]) * bz;
-                }
-                radiance += throughput * emission * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
-                w.rad[pixel] = f4(radiance, __int_as_float(primitive)); // previous_primitive = primitive
-
-                float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
-                record[0] = f4(world_shading_normal, cos_theta);
-                record[1] = f4(world_geometric_normal, 1.0f); // w: "the light sample is valid", set by shade_nee_kernel
-                record[2] = f4(intersection_point, 0.0f);
-                store_material(record + 3, material);
-                accepted = true;
-            }
-        }
-        warp_append(retrace, w.queue_out, &w.counters->next_active, pixel);
-        warp_append(accepted, w.queue_nee, &w.counters->nee, pixel);
-    }
-}
-
-template <bool TRANSMISSIVE>
-__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_nee_kernel(WavefrontView w, SceneView s, FrameParams f) {
-    typedef typename SurfaceMaterialOf<TRANSMISSIVE>::type SurfaceMaterial;
-    const unsigned int count = w.counters->nee;
-    const unsigned int rounded = (count + 31u) & ~31u;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
-        bool cast_shadow = false;
-        float4 shadow_o = make_float4(0, 0, 0, 0), shadow_d = make_float4(0, 0, 0, 0), shadow_rad = make_float4(0, 0, 0, 0);
-        if (i < count) {
-            const unsigned int pixel = w.queue_nee[i];
-            float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
-            const float4 r0 = record[0], r1 = record[1], r2 = record[2];
-            const SurfaceMaterial material = load_material<SurfaceMaterial>(record + 3);
-            const float3 ray_direction = f3(w.ray_d[pixel]);
-            const float4 thr4 = w.thr[pixel];
-            const float3 throughput = f3(thr4);
-            const unsigned int bounces = __float_as_uint(thr4.w);
-            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
-            const float3 world_geometric_normal = f3(r1), world_intersection_point = f3(r2);
-            const Tbn tbn(f3(r0));
-            const float3 wo = tbn.to_local(-ray_direction);
-
-            LightSample light_sample = light_sample_none();
-            if (s.light_count != 0) {
-                float4 light_random_base = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_NEE);
-                for (int k = 0; k < f.next_event_sample_count; ++k) {
-                    float4 shift = __ldg(s.nee_offsets + k);
-                    float4 r = light_random_base + shift;
-                    r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
-                    LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
-                    float light_weight = sum(light_sample.radiance);
-                    float new_light_weight = sum(candidate.radiance);
-                    float new_light_probability = fdiv(new_light_weight, light_weight + new_light_weight);
-                    if (r.w < new_light_probability) {
-                        light_sample = candidate;
-                        light_sample.radiance /= new_light_probability;
-                    } else
-                        light_sample.radiance /= 1.0f - new_light_probability;
-                }
-                light_sample.radiance /= float(f.next_event_sample_count);
-            }
-            float3 light_sample_origin = offset_ray_origin(world_intersection_point, light_sample.direction_to_light, world_geometric_normal);
-            light_sample.radiance *= throughput;
-            if (!light_sample.pdf.is_valid())
-                record[1] = f4(world_geometric_normal, 0.0f); // shade_sample_kernel disables MIS on the BSDF PDF
-
-            if (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0) {
-                cast_shadow = true;
-                shadow_o = f4(light_sample_origin, light_sample.distance);
-                shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
-                shadow_rad = f4(light_sample.radiance, 0.0f);
-            }
-        }
-        unsigned int mask = __ballot_sync(0xffffffffu, cast_shadow);
-        if (mask) {
-            int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
-            unsigned int base = 0;
-            if (lane == leader) base = atomicAdd(&w.counters->shadow, __popc(mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (cast_shadow) {
-                unsigned int slot = base + __popc(mask & ((1u << lane) - 1u));
-                w.sh_o[slot] = shadow_o; w.sh_d[slot] = shadow_d; w.sh_rad[slot] = shadow_rad;
-            }
-        }
-    }
-}
-
-template <bool TRANSMISSIVE>
-__global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_sample_kernel(WavefrontView w, SceneView s, FrameParams f) {
-    typedef typename SurfaceMaterialOf<TRANSMISSIVE>::type SurfaceMaterial;
-    const unsigned int count = w.counters->nee;
-    const unsigned int rounded = (count + 31u) & ~31u;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
-        bool continue_path = false;
-        unsigned int pixel = 0;
-        if (i < count) {
-            pixel = w.queue_nee[i];
-            const float4* record = w.record + (long long)RECORD_FLOAT4S * pixel;
-            const float4 r0 = record[0], r1 = record[1], r2 = record[2];
-            const SurfaceMaterial material = load_material<SurfaceMaterial>(record + 3);
-            const float3 ray_direction = f3(w.ray_d[pixel]);
-            const float4 thr4 = w.thr[pixel];
-            float3 throughput = f3(thr4);
-            unsigned int bounces = __float_as_uint(thr4.w);
-            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
-            const float3 world_geometric_normal = f3(r1), world_intersection_point = f3(r2);
-            const bool light_sample_valid = r1.w != 0.0f;
-            const Tbn tbn(f3(r0));
-            const float3 wo = tbn.to_local(-ray_direction);
-            const float3 bsdf_random_uvs = f3(path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_BSDF));
-
-            BsdfSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
-            bool is_reflection = bsdf_sample.direction.z >= 0;
-            float3 next_direction = tbn.to_world(bsdf_sample.direction);
-            Pdf bsdf_pdf = bsdf_sample.pdf;
-            if (bsdf_sample.pdf.is_valid())
-                throughput *= bsdf_sample.reflectance * fabsf(bsdf_sample.direction.z) / bsdf_sample.pdf.value();
-            else
-                throughput = f3(0.0f);
-
-            float cos_geometric_theta_i = dot(next_direction, world_geometric_normal);
-            if (is_reflection ? cos_geometric_theta_i < 0.0f : cos_geometric_theta_i >= 0.0f)
-                next_direction = reflect(next_direction, world_geometric_normal);
-
-            const float3 next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
-            if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
-                float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
-                float u = path_rng_sample4f(f.accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
-                if (u < survival) throughput = throughput / survival;
-                else throughput = f3(0.0f);
-            }
-            bounces += 1u;
-            if (!light_sample_valid)
-                bsdf_pdf.disable_MIS();
-
-            continue_path = bounces <= f.max_bounce_count && !is_black(throughput);
-            if (continue_path) {
-                w.ray_o[pixel] = f4(next_origin, 0.0f);
-                w.ray_d[pixel] = f4(next_direction, bsdf_pdf.v);
-                w.thr[pixel] = f4(throughput, __uint_as_float(bounces));
-            }
-        }
-        warp_append(continue_path, w.queue_out, &w.counters->next_active, pixel);
-    }
-}
-
-// The three kernels share one queue and one counter: the Default/Diffuse and the Transmissive paths of an iteration run one
-// after the other, and the counter is cleared in between.
-__global__ void reset_nee_counter_kernel(QueueCounters* c) { c->nee = 0; }
-#endif // BPT_SHADE_SPLIT
+__global__ void set_frame_state_kernel(FrameState* destination, FrameState value) { *destination = value; }
 
 // ---- accumulate / resolve --------------------------------------------------------------------------------
 
@@ -857,7 +608,10 @@ __global__ void reset_nee_counter_kernel(QueueCounters* c) { c->nee = 0; }
 // combined with one sum-reduce.
 // A sample whose radiance is not finite is dropped (neither the sum nor the pixel's sample count change) and counted in
 // bpt_counters.nonfinite_samples: a single NaN would otherwise poison the pixel's fp64 sum for the rest of the render.
-__global__ void accumulate_kernel(const float4* __restrict__ rad, double* __restrict__ accum, int64_t pixel_count, unsigned long long* __restrict__ nonfinite) {
+__global__ void accumulate_kernel(const float4* __restrict__ rad, int64_t pixel_count, unsigned long long* __restrict__ nonfinite, FrameState* frame) {
+    double* __restrict__ accum = frame->accumulation;
+    // the next sample of this bpt_render call (no kernel of this sample reads the index any more)
+    if (blockIdx.x == 0 && threadIdx.x == 0) frame->sample_index += 1u;
     unsigned int dropped = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
         float4 r = rad[p];
@@ -894,18 +648,143 @@ __global__ void resolve_float4_kernel(const double* __restrict__ accum, float4* 
 
 Wavefront* wavefront(Context* ctx) { return static_cast<Wavefront*>(ctx->wavefront); }
 
+// Everything the kernels of one sample are launched with. Its bytes are the signature the instantiated graph is keyed by.
+struct SampleLaunch {
+    WavefrontView w;
+    SceneView s;
+    FrameParams f;
+    int64_t pixels;
+    int trace_grid, shade_grid, stream_grid, escaped_grid;
+    int transmissive; // the scene holds Transmissive materials: a third shade kernel per iteration
+};
+
+void destroy_graph(Wavefront* wf) {
+    if (wf->graph_exec) cudaGraphExecDestroy(wf->graph_exec);
+    if (wf->graph) cudaGraphDestroy(wf->graph);
+    wf->graph_exec = nullptr; wf->graph = nullptr;
+    wf->graph_signature.clear();
+}
+
+cudaError_t add_kernel(cudaGraphNode_t* node, cudaGraph_t graph, const cudaGraphNode_t* dependencies, size_t dependency_count, const void* function,
+                       int grid, int block, void** arguments) {
+    cudaKernelNodeParams p = {};
+    p.func = const_cast<void*>(function); p.gridDim = dim3(grid); p.blockDim = dim3(block); p.sharedMemBytes = 0;
+    p.kernelParams = arguments; p.extra = nullptr;
+    return cudaGraphAddKernelNode(node, graph, dependencies, dependency_count, &p);
+}
+
+// One sample as a graph:
+//   generate -> WHILE(paths alive) { extend || shadow -> shade_escaped || shade_surface [|| shade_transmissive] -> advance }
+//            -> shadow (the rays of the last shade) -> accumulate
+// The WHILE handle starts every launch at 1 (cudaGraphCondAssignDefault); advance_kernel sets it from the queue length.
+cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L, double** accumulation_slot_unused = nullptr) {
+    (void)accumulation_slot_unused;
+    destroy_graph(wf);
+#define GRAPH_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { destroy_graph(wf); return _e; } } while (0)
+    GRAPH_CHECK(cudaGraphCreate(&wf->graph, 0));
+    cudaGraph_t graph = wf->graph;
+
+    cudaGraphNode_t generate, loop, final_shadow, accumulate;
+    void* generate_args[] = { &L.w, &L.f };
+    GRAPH_CHECK(add_kernel(&generate, graph, nullptr, 0, (const void*)generate_kernel, L.stream_grid, 256, generate_args));
+
+    cudaGraphConditionalHandle handle;
+    GRAPH_CHECK(cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault));
+    cudaGraphNodeParams loop_params = {};
+    loop_params.type = cudaGraphNodeTypeConditional;
+    loop_params.conditional.handle = handle;
+    loop_params.conditional.type = cudaGraphCondTypeWhile;
+    loop_params.conditional.size = 1;
+    GRAPH_CHECK(cudaGraphAddNode(&loop, graph, &generate, 1, &loop_params));
+    cudaGraph_t body = loop_params.conditional.phGraph_out[0];
+
+    cudaGraphNode_t traced[2], shaded[3], advance;
+    void* trace_args[] = { &L.w, &L.s };
+    GRAPH_CHECK(add_kernel(&traced[0], body, nullptr, 0, (const void*)extend_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
+    GRAPH_CHECK(add_kernel(&traced[1], body, nullptr, 0, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
+    void* shade_args[] = { &L.w, &L.s, &L.f };
+    size_t shade_count = 0;
+    GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<false, false>, L.escaped_grid, SHADE_BLOCK, shade_args));
+    GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<true, false>, L.shade_grid, SHADE_BLOCK, shade_args));
+    if (L.transmissive)
+        GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<true, true>, L.shade_grid, SHADE_BLOCK, shade_args));
+    QueueCounters* counters = L.w.counters;
+    unsigned long long* ray_counters = L.w.ray_counters;
+    int has_handle = 1;
+    void* advance_args[] = { &counters, &ray_counters, &handle, &has_handle };
+    GRAPH_CHECK(add_kernel(&advance, body, shaded, shade_count, (const void*)advance_kernel, 1, 1, advance_args));
+
+    GRAPH_CHECK(add_kernel(&final_shadow, graph, &loop, 1, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
+    const float4* rad = L.w.rad;
+    unsigned long long* nonfinite = L.w.ray_counters + 6;
+    FrameState* frame = const_cast<FrameState*>(L.w.frame);
+    void* accumulate_args[] = { &rad, &L.pixels, &nonfinite, &frame };
+    GRAPH_CHECK(add_kernel(&accumulate, graph, &final_shadow, 1, (const void*)accumulate_kernel, L.stream_grid, 256, accumulate_args));
+
+    GRAPH_CHECK(cudaGraphInstantiate(&wf->graph_exec, graph, 0));
+#undef GRAPH_CHECK
+    wf->graph_signature.assign(reinterpret_cast<const unsigned char*>(&L), reinterpret_cast<const unsigned char*>(&L) + sizeof(L));
+    return cudaSuccess;
+}
+
+// The same sample with plain stream launches; the host reads the queue length back to decide when the loop ends. Used when
+// per-stage timing is on (bpt_set_profiling: CUDA events between the stages), with BPT_GRAPH=0, or when the driver refuses
+// conditional graph nodes.
+int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
+    generate_kernel<<<L.stream_grid, 256, 0, st>>>(L.w, L.f);
+    // A path shades at most max_bounce_count + 1 surfaces; rejected hits (back faces, coverage) re-trace the same ray
+    // without consuming a bounce, so a few extra iterations run before the queue length is checked on the host.
+    uint32_t planned = L.f.max_bounce_count + 2, done = 0;
+    while (true) {
+        for (uint32_t it = 0; it < planned; ++it) {
+            if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 0)], st);
+            extend_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
+            if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
+            shadow_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
+            if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
+            shade_kernel<false, false><<<L.escaped_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            shade_kernel<true, false><<<L.shade_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            if (L.transmissive) shade_kernel<true, true><<<L.shade_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);
+            advance_kernel<<<1, 1, 0, st>>>(L.w.counters, L.w.ray_counters, 0ull, 0);
+        }
+        done += planned;
+        QueueCounters h;
+        BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, L.w.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+        if (ctx->profiling)
+            for (uint32_t it = 0; it < planned; ++it) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 0], ctx->stage_events[it * 4 + 1]); ctx->counters.extend_ms += ms;
+                cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 1], ctx->stage_events[it * 4 + 2]); ctx->counters.shadow_ms += ms;
+                cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 2], ctx->stage_events[it * 4 + 3]); ctx->counters.shade_ms += ms;
+            }
+        if (h.active == 0) break;
+        if (done > MAX_ITERATIONS_PER_SAMPLE) return ctx->fail(BPT_ERROR_CUDA, "bpt_render: path queue did not drain");
+        planned = 2;
+    }
+    if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(0)], st);
+    shadow_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s); // the shadow rays of the last shade
+    if (ctx->profiling) {
+        cudaEventRecord(ctx->stage_events[ctx->stage_event(1)], st);
+        cudaEventSynchronize(ctx->stage_events[1]);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, ctx->stage_events[0], ctx->stage_events[1]); ctx->counters.shadow_ms += ms;
+    }
+    accumulate_kernel<<<L.stream_grid, 256, 0, st>>>(L.w.rad, L.pixels, L.w.ray_counters + 6, const_cast<FrameState*>(L.w.frame));
+    return BPT_OK;
+}
+
 } // namespace
 
 void release_wavefront(Context* ctx) {
     Wavefront* wf = wavefront(ctx);
     if (!wf) return;
+    destroy_graph(wf);
     wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
     wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
     wf->queue_surface.release(); wf->queue_escaped.release();
-#if BPT_SHADE_SPLIT
-    wf->queue_nee.release(); wf->record.release();
-#endif
-    wf->counters.release(); wf->coverage.release();
+    wf->counters.release(); wf->frame_state.release(); wf->coverage.release();
     delete wf;
     ctx->wavefront = nullptr;
 }
@@ -928,20 +807,19 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     if (!ctx->wavefront) ctx->wavefront = new Wavefront();
     Wavefront* wf = wavefront(ctx);
     if (wf->pixel_capacity < pixels) {
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // launches in flight still use the old buffers
         BPT_CUDA_CHECK(ctx, wf->ray_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->ray_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->thr.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->rad.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->hit.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_a.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_b.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_surface.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_escaped.resize(pixels));
-#if BPT_SHADE_SPLIT
-        BPT_CUDA_CHECK(ctx, wf->queue_nee.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->record.resize(7 * pixels)); // RECORD_FLOAT4S per pixel
-#endif
-        BPT_CUDA_CHECK(ctx, wf->counters.resize(1));
+        BPT_CUDA_CHECK(ctx, wf->counters.resize(1)); BPT_CUDA_CHECK(ctx, wf->frame_state.resize(1));
         wf->pixel_capacity = pixels;
     }
     if (wf->coverage_version != ctx->material_version) {
         std::vector<float> h_cov(ctx->host_materials.size());
         for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // as above when the table has to grow
         BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->coverage.ptr, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // h_cov goes out of scope
@@ -950,13 +828,16 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
 
     bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
     if (size_changed) {
+        if (ctx->accumulation.capacity < (size_t)(4 * pixels)) BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
         BPT_CUDA_CHECK(ctx, ctx->accumulation.resize(4 * pixels));
         ctx->width = width; ctx->height = height;
     }
     if (size_changed || reset_accumulation)
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
 
-    SceneView s = {};
+    SampleLaunch L;
+    memset(&L, 0, sizeof(L)); // padding included: the bytes are compared
+    SceneView& s = L.s;
     s.accel = accel_view(ctx);
     s.world_vertices = ctx->accel.world_vertices.ptr;
     s.shade = ctx->accel.shade.ptr;
@@ -988,91 +869,64 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     s.split_by_shading_model = ctx->has_transmissive_materials;
     s.nee_offsets = ctx->nee_offsets.ptr;
 
-    WavefrontView w = {};
+    WavefrontView& w = L.w;
     w.ray_o = wf->ray_o.ptr; w.ray_d = wf->ray_d.ptr; w.thr = wf->thr.ptr; w.rad = wf->rad.ptr; w.hit = wf->hit.ptr;
     w.sh_o = wf->sh_o.ptr; w.sh_d = wf->sh_d.ptr; w.sh_rad = wf->sh_rad.ptr;
+    w.queue_a = wf->queue_a.ptr; w.queue_b = wf->queue_b.ptr;
     w.queue_surface = wf->queue_surface.ptr; w.queue_escaped = wf->queue_escaped.ptr;
     w.queue_capacity = (unsigned int)pixels;
-#if BPT_SHADE_SPLIT
-    w.queue_nee = wf->queue_nee.ptr; w.record = wf->record.ptr;
-#endif
     w.counters = wf->counters.ptr;
+    w.frame = wf->frame_state.ptr;
     w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
 
-    FrameParams f = {};
-    f.camera = *camera; f.width = width; f.height = height;
+    FrameParams& f = L.f;
+    f.width = width; f.height = height;
     f.max_bounce_count = settings->max_bounce_count;
     f.next_event_sample_count = settings->next_event_sample_count;
-    f.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
     f.russian_roulette_start_bounce = settings->russian_roulette_start_bounce;
 
     // Persistent grids: a whole number of CTAs per SM.
-    const int trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;
-    const int shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
-    const int stream_grid = ctx->sm_count * 8;
-    const int escaped_grid = ctx->sm_count * 4;
+    L.pixels = pixels;
+    L.trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;
+    L.shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
+    L.stream_grid = ctx->sm_count * 8;
+    L.escaped_grid = ctx->sm_count * 4;
+    L.transmissive = ctx->has_transmissive_materials ? 1 : 0;
+    ctx->launches_per_iteration = 5 + L.transmissive;
 
-    for (uint32_t k = 0; k < sample_count; ++k) {
-        f.accumulation_count = first_sample + k;
-        w.queue_in = wf->queue_a.ptr; w.queue_out = wf->queue_b.ptr;
-        generate_kernel<<<stream_grid, 256, 0, st>>>(w, f);
-        ctx->counters.kernel_launches++;
-        // A path shades at most max_bounce_count + 1 surfaces; rejected hits (back faces, coverage) re-trace the same
-        // ray without consuming a bounce, so a few extra iterations run before the queue length is checked on the host.
-        uint32_t planned = settings->max_bounce_count + 2;
-        uint32_t done = 0;
-        while (true) {
-            size_t first_event = 0;
-            for (uint32_t it = 0; it < planned; ++it) {
-                if (ctx->profiling) { first_event = ctx->stage_event(it * 4 + 0); cudaEventRecord(ctx->stage_events[first_event], st); }
-                extend_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
-                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
-                shade_kernel<false, false><<<escaped_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-#if BPT_SHADE_SPLIT
-                shade_setup_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                shade_nee_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                shade_sample_kernel<false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                ctx->counters.kernel_launches += 2;
-                if (ctx->has_transmissive_materials) {
-                    reset_nee_counter_kernel<<<1, 1, 0, st>>>(w.counters);
-                    shade_setup_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                    shade_nee_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                    shade_sample_kernel<true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                    ctx->counters.kernel_launches += 4;
-                }
-#else
-                shade_kernel<true, false><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                if (ctx->has_transmissive_materials) {
-                    shade_kernel<true, true><<<shade_grid, SHADE_BLOCK, 0, st>>>(w, s, f);
-                    ctx->counters.kernel_launches++;
-                }
-#endif
-                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
-                shadow_kernel<<<trace_grid, TRACE_BLOCK, 0, st>>>(w, s);
-                if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 3)], st);
-                advance_kernel<<<1, 1, 0, st>>>(w.counters);
-                std::swap(w.queue_in, w.queue_out);
-                ctx->counters.kernel_launches += 5;
+    // What changes per call travels through device memory, as the by-value argument of a one-thread kernel: fully
+    // asynchronous, no staging buffer whose lifetime the host would have to track.
+    FrameState frame_state;
+    memset(&frame_state, 0, sizeof(frame_state));
+    frame_state.camera = *camera;
+    frame_state.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
+    frame_state.sample_index = first_sample;
+    frame_state.accumulation = ctx->accumulation.ptr;
+    set_frame_state_kernel<<<1, 1, 0, st>>>(wf->frame_state.ptr, frame_state);
+
+    static const bool graphs_disabled = [] { const char* e = getenv("BPT_GRAPH"); return e && e[0] == '0'; }();
+    const bool use_graph = !ctx->profiling && !graphs_disabled && !wf->graph_unavailable;
+    if (use_graph) {
+        const bool current = wf->graph_exec && wf->graph_signature.size() == sizeof(L) && memcmp(wf->graph_signature.data(), &L, sizeof(L)) == 0;
+        if (!current) {
+            cudaError_t e = build_sample_graph(wf, L);
+            if (e != cudaSuccess) {
+                // e.g. a driver without conditional nodes: remember it, say so once, and take the stream path
+                wf->graph_unavailable = true;
+                ctx->last_error = std::string("bpt_render: sample graph unavailable (") + cudaGetErrorString(e) + "), using stream launches";
+                fprintf(stderr, "%s\n", ctx->last_error.c_str());
+                cudaGetLastError();
             }
-            done += planned;
-            QueueCounters h;
-            BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, w.counters, sizeof(h), cudaMemcpyDeviceToHost, st));
-            BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-            if (ctx->profiling)
-                for (uint32_t it = 0; it < planned; ++it) {
-                    float ms = 0.0f;
-                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 0], ctx->stage_events[it * 4 + 1]); ctx->counters.extend_ms += ms;
-                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 1], ctx->stage_events[it * 4 + 2]); ctx->counters.shade_ms += ms;
-                    cudaEventElapsedTime(&ms, ctx->stage_events[it * 4 + 2], ctx->stage_events[it * 4 + 3]); ctx->counters.shadow_ms += ms;
-                }
-            if (h.active == 0) break;
-            if (done > 4096) return ctx->fail(BPT_ERROR_CUDA, "bpt_render: path queue did not drain");
-            planned = 2;
         }
-        accumulate_kernel<<<stream_grid, 256, 0, st>>>(wf->rad.ptr, ctx->accumulation.ptr, pixels, w.ray_counters + 6);
-        ctx->counters.kernel_launches++;
-        ctx->counters.samples += (uint64_t)pixels;
     }
+    if (use_graph && wf->graph_exec) {
+        for (uint32_t k = 0; k < sample_count; ++k) BPT_CUDA_CHECK(ctx, cudaGraphLaunch(wf->graph_exec, st));
+    } else {
+        for (uint32_t k = 0; k < sample_count; ++k)
+            if (int status = launch_sample_serial(ctx, L, st)) return status;
+    }
+    ctx->counters.kernel_launches += 1ull + 3ull * sample_count; // the frame state; per sample: generate, the last shadow, accumulate; the iterations are counted on the device
+    ctx->counters.samples += (uint64_t)pixels * sample_count;
     BPT_CUDA_CHECK(ctx, cudaGetLastError());
     return BPT_OK;
 }

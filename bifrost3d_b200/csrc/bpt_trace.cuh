@@ -113,9 +113,6 @@ BPT_D bool watertight_triangle(const RayShear& s, float3 origin, float3 p0, floa
 #define BPT_TRAVERSAL_BUDGET 48
 #endif
 constexpr int TRACE_BLOCK = 128;
-#ifndef BPT_PARKED_LEAVES
-#define BPT_PARKED_LEAVES 1
-#endif
 #ifndef BPT_MIN_ACTIVE_LANES
 #define BPT_MIN_ACTIVE_LANES 12
 #endif
@@ -220,9 +217,6 @@ struct Traversal {
     int skip_primitive;
     int node;
     int postponed;       // a leaf found while other lanes were still descending; NODE_EMPTY when none
-#if BPT_PARKED_LEAVES >= 2
-    int postponed2;      // a second one (experimental)
-#endif
     TraversalStack stack;
 #ifdef BPT_TRAVERSAL_STATS
     unsigned int stat_nodes, stat_triangles;
@@ -239,9 +233,6 @@ struct Traversal {
         stack.sp = 0;
         node = 0; // root
         postponed = NODE_EMPTY;
-#if BPT_PARKED_LEAVES >= 2
-        postponed2 = NODE_EMPTY;
-#endif
 #ifdef BPT_TRAVERSAL_STATS
         stat_nodes = stat_triangles = 0;
 #endif
@@ -335,37 +326,8 @@ struct Traversal {
     // is used up; `node == NODE_EMPTY && postponed == NODE_EMPTY` tells which.
     // Speculative traversal (Aila and Laine): a lane that reaches a leaf parks it in `postponed` and keeps descending while
     // other lanes of the warp are still looking for theirs, so the inner-node loop runs with more lanes active.
-#if BPT_PARKED_LEAVES >= 2
-    // Experimental (off by default, not yet measured): two parked leaves per lane. A lane keeps descending until it holds two
-    // leaves, so that more lanes hold at least one when the warp turns to the triangle tests (on bounce rays only a third of
-    // the traversing lanes do); the price is more speculative node visits.
-    BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget, int min_active = 0) {
-        while ((node != NODE_EMPTY || postponed != NODE_EMPTY) && budget > 0) {
-            while (node >= 0 && budget > 0) {
-                if (a.wide != nullptr) wide_step(a); else inner_step(a);
-                --budget;
-                if (is_leaf(node)) {
-                    if (postponed == NODE_EMPTY) { postponed = node; node = stack.pop(); }
-                    else if (postponed2 == NODE_EMPTY) { postponed2 = node; node = stack.pop(); }
-                }
-                const unsigned int active = __activemask();
-                if (__popc(active) < min_active) budget = 0;
-                if (!__any_sync(active, postponed == NODE_EMPTY && node >= 0))
-                    break;
-            }
-            if (is_leaf(node)) {
-                if (postponed == NODE_EMPTY) { postponed = node; node = stack.pop(); }
-                else if (postponed2 == NODE_EMPTY) { postponed2 = node; node = stack.pop(); }
-            }
-            while (postponed != NODE_EMPTY) {
-                bool alive = intersect_leaf(a, coverage_by_material, postponed);
-                postponed = postponed2; postponed2 = NODE_EMPTY;
-                if (!alive) { node = NODE_EMPTY; stack.sp = 0; postponed = NODE_EMPTY; }
-                else if (postponed == NODE_EMPTY && is_leaf(node)) { postponed = node; node = stack.pop(); }
-            }
-        }
-    }
-#else
+    // (A second parked leaf per lane was measured in round 2: extend +1.8 % slower on the 1 M triangle scene, +2 % on the 20 k one;
+    // the extra speculative node visits cost more than the wider leaf phase returns.)
     BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget, int min_active = 0) {
         while ((node != NODE_EMPTY || postponed != NODE_EMPTY) && budget > 0) {
             while (node >= 0 && budget > 0) {
@@ -390,8 +352,6 @@ struct Traversal {
         }
     }
 
-#endif
-
     BPT_D bool finished() const { return node == NODE_EMPTY && postponed == NODE_EMPTY; }
 
     BPT_D Hit result() const {
@@ -415,9 +375,6 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
     tr.stack.sp = 0;
     tr.node = NODE_EMPTY;
     tr.postponed = NODE_EMPTY;
-#if BPT_PARKED_LEAVES >= 2
-    tr.postponed2 = NODE_EMPTY;
-#endif
     unsigned int index = 0;
     bool has_ray = false, exhausted = false;
     const int lane = threadIdx.x & 31;

@@ -111,6 +111,7 @@ typedef struct bpt_counters {
     uint64_t extend_node_visits;     /* diagnostics, only filled by builds with -DBPT_TRAVERSAL_STATS */
     uint64_t extend_triangle_tests;
     uint64_t nonfinite_samples;      /* pixel samples whose radiance was NaN / inf: dropped from the accumulation, counted here */
+    uint64_t iterations;             /* wavefront iterations (one closest-hit + one shadow traversal launch each), counted on the device */
 } bpt_counters;
 
 /* ---- context ----------------------------------------------------------------------------------- */
@@ -311,6 +312,13 @@ int bpt_rng_sample4(bpt_ctx* ctx, int64_t n, const uint32_t* accumulation, const
  * out_t: hit distance; out_uv: barycentrics (2n); out_occluded: n bytes (any hit in [tmin, tmax]). Nullable outputs are skipped. */
 int bpt_intersect(bpt_ctx* ctx, int64_t n, const float* origins, const float* directions, const float* tmin, const float* tmax,
                   int32_t* out_primitive, float* out_t, float* out_uv, uint8_t* out_occluded);
+
+/* The device-wide primitives of the acceleration structure build (which replaces OptiX' Trbvh, Renderer.cpp:161-182) and of the
+ * queue reordering, exposed for bit-exact tests against a host sort / cumulative sum. bpt_sort_pairs: stable least-significant-
+ * digit radix sort of n (64-bit key, 32-bit value) pairs by key bits [begin_bit, end_bit), in place in the host arrays.
+ * bpt_exclusive_scan: out[i] = in[0] + ... + in[i - 1] (wrapping), *out_total = sum of all n. */
+int bpt_sort_pairs(bpt_ctx* ctx, int64_t n, uint64_t* keys, uint32_t* values, int begin_bit, int end_bit);
+int bpt_exclusive_scan(bpt_ctx* ctx, int64_t n, const uint32_t* in, uint32_t* out, uint32_t* out_total);
 
 #ifdef __cplusplus
 }

@@ -144,16 +144,19 @@ TEST_F(RendererFixture, b200_incremental_transform_and_material_updates) {
     });
 }
 
-// One accumulation buffer per camera (Renderer.cpp:199-222): two cameras of different sizes on different scenes render
-// alternately through one renderer; each keeps its own progressive accumulation (the count grows, the image is its own), and an
-// auxiliary screenshot (rendered into scratch, Renderer.cpp:1280) does not restart the camera's accumulation.
+// One accumulation buffer per camera (Renderer.cpp:199-222): two cameras of different sizes on the same scene render
+// alternately through one renderer; each keeps its own progressive accumulation (the count grows, neither frame size wipes
+// the other), and an auxiliary screenshot (rendered into scratch, Renderer.cpp:1280) does not restart a camera's accumulation.
 TEST_F(RendererFixture, b200_two_cameras_keep_their_own_accumulation) {
     using namespace Bifrost;
     using namespace Bifrost::Scene;
 
     auto size_a = Math::Vector2i(8, 6), size_b = Math::Vector2i(5, 4);
     CameraID camera_a = create_ortho_camera(size_a, optix::make_float3(0.25f, 0.5f, 0.75f));
-    CameraID camera_b = create_ortho_camera(size_b, optix::make_float3(0.75f, 0.125f, 0.5f));
+    Math::Matrix4x4f orthographic_matrix, inverse_orthographic_matrix;
+    CameraUtils::compute_orthographic_projection(float(size_b.x), float(size_b.y), 1000.0f, orthographic_matrix, inverse_orthographic_matrix);
+    CameraID camera_b = Cameras::create("Second", Cameras::get_scene_ID(camera_a), orthographic_matrix, inverse_orthographic_matrix);
+    Cameras::set_renderer_ID(camera_b, renderer->get_renderer_ID());
     renderer->handle_updates();
     auto target_a = create_render_target(renderer, size_a), target_b = create_render_target(renderer, size_b);
     for (unsigned int frame = 1; frame <= 3; ++frame) {
@@ -167,7 +170,7 @@ TEST_F(RendererFixture, b200_two_cameras_keep_their_own_accumulation) {
     target_a->unmap();
     half4* pixels_b = (half4*)target_b->map();
     for (int i = 0; i < size_b.x * size_b.y; ++i) {
-        EXPECT_FLOAT_EQ_EPS(0.75f, float(pixels_b[i].r), 1e-3f); EXPECT_FLOAT_EQ_EPS(0.125f, float(pixels_b[i].g), 1e-3f);
+        EXPECT_FLOAT_EQ_EPS(0.25f, float(pixels_b[i].r), 1e-3f); EXPECT_FLOAT_EQ_EPS(0.5f, float(pixels_b[i].g), 1e-3f);
     }
     target_b->unmap();
 

@@ -108,14 +108,20 @@ def test_device_cdf_sampling_matches_infinite_area_light(bpt):
     print(f"direction: max abs err {d.max():.3e}, {(d > 1e-5).sum()}/{n} above 1e-5")
     assert (d <= 1e-5).mean() >= 0.9999
     ok = d <= 1e-5
+    # PDF = table / sin(theta) with sin(theta) = sqrt(1 - y^2): a direction that differs by one ulp in y (6e-8, measured above)
+    # moves 1 / sin(theta) by y * dy / sin^2(theta) relative, which exceeds 1e-5 within ~4 degrees of the poles. The bound
+    # therefore is 1e-5 + 2 ulp(y) / sin^2(theta); round 2 measured 104 / 65536 samples above a flat 1e-5, max 4.5e-5, all there.
+    sin2 = np.maximum(1.0 - want[ok, 5].astype(np.float64) ** 2, 1e-12)
+    bound = 1e-5 + 2 * 6e-8 / sin2
     rel_pdf = np.abs(samples["pdf"][ok] - want[ok, 3]) / np.maximum(np.abs(want[ok, 3]), 1e-12)
-    print(f"pdf: max rel err {rel_pdf.max():.3e}, {(rel_pdf > 1e-5).sum()} above 1e-5")
-    assert (rel_pdf <= 1e-5).mean() >= 0.999  # table lookup by (u, v): a sample on a texel border may read the neighbour's PDF
+    print(f"pdf: max rel err {rel_pdf.max():.3e}, {(rel_pdf > 1e-5).sum()} above a flat 1e-5, {(rel_pdf > bound).sum()} above the bound")
+    assert (rel_pdf <= bound).mean() >= 0.9999
     rel_rad = np.abs(samples["radiance"][ok] - want[ok, 0:3]) / np.maximum(np.abs(want[ok, 0:3]), 1e-3)
     print(f"radiance: max rel err {rel_rad.max():.3e}, {(rel_rad > 1e-4).sum()} above 1e-4")
     assert (rel_rad <= 1e-4).mean() >= 0.999  # bilinear weights in fp32 at 512 texels: 2^-24 * 512 relative in the weight
     # and the device PDF of the sampled direction (what MIS evaluates for BSDF-sampled rays) equals InfiniteAreaLight::PDF
     _, pdf, _ = bpt.light_sample_pdf_evaluate(light, zeros, pts, want[:, 4:7])
+    # same direction on both sides here, so the flat bound applies except where the direction sits on a texel border of the table
     rel = np.abs(pdf[ok] - ref["pdf_of_direction"][ok]) / np.maximum(np.abs(ref["pdf_of_direction"][ok]), 1e-12)
     print(f"pdf(direction): {(rel > 1e-5).sum()} above 1e-5")
     assert (rel <= 1e-5).mean() >= 0.99
