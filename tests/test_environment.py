@@ -97,7 +97,10 @@ def test_device_cdf_sampling_matches_infinite_area_light(bpt):
     pts = np.random.default_rng(7).random((n, 2)).astype(np.float32)
     ref = oracle_lib.reference_environment_sample(sky, pts)
     env = environment.build_environment(sky, sample_count=64)
-    bpt.set_environment((1.0, 1.0, 1.0), sky, env["per_pixel_pdf"], env["samples"])
+    # the per pixel PDF table from the SAME CDFs (a PDF is the difference of neighbouring CDF values: a table built from CDFs
+    # that differ in the last bit would be off by far more than 1e-5 in dark cells)
+    table = environment.solid_angle_pdf_sans_sin_theta(ref["marginal_cdf"], ref["conditional_cdf"])
+    bpt.set_environment((1.0, 1.0, 1.0), sky, table, env["samples"])
     bpt.set_environment_cdfs(ref["marginal_cdf"], ref["conditional_cdf"])
     light = np.zeros(1, capi.LIGHT_DTYPE); light["flags"] = capi.LIGHT_ENVIRONMENT
     zeros = np.zeros((n, 3), np.float32)
