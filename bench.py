@@ -154,6 +154,144 @@ def run_reference(args):
     return 0
 
 
+BSDF_TUPLES = 1 << 22          # BASELINE.json configs[0]
+BSDF_BYTES_PER_TUPLE = 104      # 60 B in (wo, wi, tint, {roughness, metallic, specularity}, u) + 44 B out
+BSDF_KINDS = {"DefaultShading": 0, "GGX_R": 1, "OrenNayar": 2, "Burley": 3}
+
+
+def bsdf_config(args):
+    return {"workload": f"bsdf: DefaultShading evaluate_with_PDF + sample over 2^22 random (wo, wi, tint, roughness, metallic, specularity, u) tuples per step and GPU, seed 1234",
+            "baseline_config": "configs[0] (BSDF evaluate + sample + PDF over 2^22 tuples)",
+            "l2_policy": "a 256 MB buffer is written between the timed steps (larger than L2): every step reads its inputs from HBM",
+            "parallelism": f"independent tuple batches x{args.gpus} (no collective)"}
+
+
+def run_bsdf_reference(args):
+    """--impl reference --workload bsdf: the reference's own host-compiled DefaultShading over a bounded sample of the tuples."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from tests import oracle_lib
+    from bifrost3d_b200.workloads import bsdf_tuples
+    ref = oracle_lib.load()
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n = 1 << 20
+    t = bsdf_tuples(n, seed=1234)
+    tuple_args = [t[k] for k in ("wo", "wi", "tint", "rms", "u")]
+    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 1))
+    times = []
+    for step in range(warmup + steps):
+        t0 = time.perf_counter(); ref.bsdf_eval_sample_pdf(0, *tuple_args, threads=threads); dt = time.perf_counter() - t0
+        if step >= warmup:
+            times.append(dt)
+    value = n * steps / sum(times) / 1e6
+    sample = f"the first 2^20 of the 2^22 tuples per step, {steps} steps"
+    print(json.dumps({"impl": "reference", "metric": "Mtuples/s", "value": value, "unit": "Mtuples/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+                      "ms_per_step": sum(times) / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": bsdf_config(args),
+                      "cpu_baseline": {"value": value, "unit": "Mtuples/s", "cores": threads, "kind": "reference", "sample": sample},
+                      "e2e": {"value": value, "unit": "Mtuples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "note": "the reference's own headers (DefaultShading.h, GGX.h, OrenNayar.h) compiled for the host, OpenMP over the tuples"}), flush=True)
+    return 0
+
+
+def run_bsdf(args):
+    """--workload bsdf = configs[0]: a step is one pass of DefaultShading evaluate + sample + PDF over 2^22 tuples resident in HBM."""
+    import torch
+    import bifrost3d_b200 as b
+    from bifrost3d_b200.workloads import bsdf_tuples
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    distributed = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the CUDA extension is the product and there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = b.Bpt(local_rank)
+    N, K, Wm = BSDF_TUPLES, args.steps, args.warmup
+    t = bsdf_tuples(N, seed=1234 + rank)
+    names_in, names_out = ("wo", "wi", "tint", "rms", "u"), {"eval_f": 3, "eval_pdf": 1, "sample_f": 3, "sample_pdf": 1, "sample_dir": 3}
+    dev = {k: torch.from_numpy(t[k]).cuda().contiguous() for k in names_in}
+    out = {k: torch.empty((N, c) if c > 1 else (N,), device="cuda") for k, c in names_out.items()}
+    ptrs = {k: v.data_ptr() for k, v in {**dev, **out}.items()}
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        ctx.synchronize(); torch.cuda.synchronize()
+        if distributed:
+            dist.barrier(); torch.cuda.synchronize()
+
+    def timed(kind, steps):
+        total = 0.0
+        for _ in range(steps):
+            flush.zero_(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream); ctx.bsdf_eval_sample_pdf_device(kind, N, ptrs); e1.record(stream)
+            ctx.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    for _ in range(Wm):
+        ctx.bsdf_eval_sample_pdf_device(0, N, ptrs)
+    barrier()
+    ctx.counters(reset=True)
+    sampler = ClockSampler(local_rank); sampler.start()
+    device_ms = timed(0, K)
+    barrier()
+    clocks = sampler.summary()
+    launches = ctx.counters()["kernel_launches"]
+    tm = torch.tensor([device_ms], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    device_ms = float(tm.item())
+    value = N * K * world / (device_ms * 1e-3) / 1e6
+    others = {name: N / (timed(kind, 5) / 5) / 1e3 for name, kind in BSDF_KINDS.items() if kind != 0}  # Mtuples/s of the single-lobe BSDFs
+
+    # end to end: host arrays in, host arrays out through the C ABI (bpt_bsdf_eval_sample_pdf with on_device = 0)
+    host_in = [t[k] for k in names_in]
+    ctx.bsdf_eval_sample_pdf(0, *host_in)
+    barrier()
+    e2e_steps = min(K, 4)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        result = ctx.bsdf_eval_sample_pdf(0, *host_in)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if distributed:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = N * e2e_steps * world / float(te.item()) / 1e6
+
+    if rank == 0:
+        peak, peak_kind = measured_peak()
+        achieved = N * BSDF_BYTES_PER_TUPLE / (device_ms / K * 1e-3) / 1e9 * 1.0
+        line = {"metric": "Mtuples/s", "value": value, "unit": "Mtuples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": device_ms / K,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": bsdf_config(args),
+                "e2e": {"value": e2e_value, "unit": "Mtuples/s", "h2d_bytes_per_step": int(N * 60), "d2h_bytes_per_step": int(N * 44), "steps": e2e_steps},
+                "gpu_launches": int(launches), "gpu_launches_per_step": launches / max(K, 1),
+                "roofline": {"bound": "hbm", "kernel": "bsdf_batch_kernel<DefaultShading>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": N * BSDF_BYTES_PER_TUPLE,
+                             "algorithmic_bytes_per_tuple": BSDF_BYTES_PER_TUPLE, "avg_launch_ms": device_ms / K,
+                             "note": "ALU bound, not HBM bound (IEEE division / square root and fp64 sin / cos / pow for parity with the host build)"},
+                "other_bsdfs_mtuples_per_s": others, "clocks": clocks,
+                "finite_fraction_of_outputs": float(np.isfinite(result["eval_f"]).mean())}
+        if not args.no_cpu_baseline and world == 1 and cpu_baseline_available():
+            from tests import oracle_lib
+            ref = oracle_lib.load()
+            n_cpu = 1 << 20
+            cpu_args = [t[k][:n_cpu] for k in names_in]
+            ref.bsdf_eval_sample_pdf(0, *[a[:4096] for a in cpu_args])
+            t0 = time.perf_counter(); ref.bsdf_eval_sample_pdf(0, *cpu_args); dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": n_cpu / dt / 1e6, "unit": "Mtuples/s", "cores": int(ref.max_threads()), "kind": "reference",
+                                    "sample": "the first 2^20 of the 2^22 tuples, one pass"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if distributed:
+        dist.destroy_process_group()
+    return 0
+
+
 def workload_config(args, scene, settings):
     from bifrost3d_b200 import scenes
     return {"workload": f"{scene['name']}: {scene['width']}x{scene['height']}, {scenes.triangle_count(scene)} triangles, {len(scene['lights'])} light(s), "
@@ -170,13 +308,17 @@ def main():
     ap.add_argument("--steps", type=int, default=64)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="materials", help="materials = BASELINE.json configs[2] (1080p, 4 bounces: the configuration the metric is quoted on); cornell = configs[1]; terrain = configs[3]")
+    ap.add_argument("--workload", default="materials", help="materials = BASELINE.json configs[2] (1080p, 4 bounces: the configuration the metric is quoted on); cornell = configs[1]; terrain = configs[3]; bsdf = configs[0] (2^22 BSDF tuples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sort-hits", type=int, default=None, metavar="K",
+                    help="sort the surface hits by (shading class, hit cell) before shading from wavefront iteration K on (bpt_set_hit_sorting); -1 = never; default: the library's")
     ap.add_argument("--russian-roulette", type=int, default=0, metavar="N",
                     help="opt-in Russian roulette from the N-th surface interaction on (configs[3] names it; 0 = off = the reference's behaviour)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.workload == "bsdf":
+        return run_bsdf_reference(args) if args.impl == "reference" else run_bsdf(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -198,6 +340,8 @@ def main():
         settings["russian_roulette_start"] = args.russian_roulette
     W, H = scene["width"], scene["height"]
     ctx = b.Bpt(local_rank)
+    if args.sort_hits is not None:
+        ctx.set_hit_sorting(args.sort_hits)
     scenes.upload(ctx, scene)
     ctx.build_accel()  # second build: the reported build time excludes one-off module loading and allocator warm-up
     info = ctx.accel_info()

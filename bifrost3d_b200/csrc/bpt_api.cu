@@ -344,6 +344,7 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     ctx->device = cuda_device;
     if (const char* bvh = getenv("BPT_BVH")) ctx->use_ploc = strcmp(bvh, "lbvh") != 0;
     if (const char* wide = getenv("BPT_WIDE")) ctx->use_wide = strcmp(wide, "0") != 0;
+    if (const char* sort_hits = getenv("BPT_SORT_HITS")) ctx->sort_hits_from_iteration = atoi(sort_hits);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return BPT_ERROR_CUDA; }
@@ -385,7 +386,7 @@ void bpt_destroy(bpt_ctx* c) {
     for (auto& kv : ctx->meshes) kv.second.release();
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release(); ctx->accel.shade_emission.release();
-    ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
+    ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.slot_of_primitive.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release();
     for (auto& target : ctx->parked_targets) target.second.buffer.release();
     if (ctx->copy_stream) {
@@ -705,6 +706,11 @@ int bpt_set_environment_sampling(bpt_ctx* c, int mode) {
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment_sampling: unknown mode");
     if (ctx->env_nee_mode != mode) ctx->env_light_uploaded = false;
     ctx->env_nee_mode = mode;
+    return BPT_OK;
+}
+
+int bpt_set_hit_sorting(bpt_ctx* c, int from_iteration) {
+    as_context(c)->sort_hits_from_iteration = from_iteration < 0 ? -1 : from_iteration;
     return BPT_OK;
 }
 

@@ -205,12 +205,14 @@ __device__ __forceinline__ Aabb load_box_cg(const Aabb* p) {
 // internal node merges its children's boxes (classic atomic-counter refit).
 __global__ void fit_kernel(int n, const uint32_t* __restrict__ sorted_prims, const float4* __restrict__ world_vertices,
                            const ShadeTriangle* __restrict__ shade,
-                           TraceTriangle* __restrict__ triangles, Aabb* __restrict__ leaf_boxes, Aabb* __restrict__ node_boxes,
+                           TraceTriangle* __restrict__ triangles, uint32_t* __restrict__ slot_of_primitive, Aabb* __restrict__ leaf_boxes,
+                           Aabb* __restrict__ node_boxes,
                            const TreeNode* __restrict__ tree, const int* __restrict__ parent_of_internal, const int* __restrict__ parent_of_leaf,
                            int* __restrict__ arrival) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     uint32_t gp = sorted_prims[p];
+    slot_of_primitive[gp] = (uint32_t)p;
     float4 v0 = world_vertices[3ll * gp], v1 = world_vertices[3ll * gp + 1], v2 = world_vertices[3ll * gp + 2];
     int material = shade[gp].material_index;
     TraceTriangle t;
@@ -623,6 +625,7 @@ int build_accel(Context* ctx) {
     A.has_emission = any_emission && n > 0;
     if (A.has_emission) BUILD_CHECK(A.shade_emission.resize(9ull * n)); else A.shade_emission.release();
     BUILD_CHECK(A.triangles.resize(std::max<size_t>(n, 1)));
+    BUILD_CHECK(A.slot_of_primitive.resize(std::max<size_t>(n, 1)));
     BUILD_CHECK(A.nodes.resize((size_t)n + 1));
     // PLOC scratch is sized for the worst case of one cluster per triangle and allocated outside the timed region.
     const bool try_ploc = ctx->use_ploc && n > LEAF_MAX;
@@ -667,7 +670,7 @@ int build_accel(Context* ctx) {
             hierarchy_kernel<<<full_grid(n - 1), block, 0, st>>>(n, sorted_keys, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr);
             ctx->counters.kernel_launches++;
         }
-        fit_kernel<<<full_grid(n), block, 0, st>>>(n, sorted_vals, A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr,
+        fit_kernel<<<full_grid(n), block, 0, st>>>(n, sorted_vals, A.world_vertices.ptr, A.shade.ptr, A.triangles.ptr, A.slot_of_primitive.ptr,
                                                    d_leaf_boxes.ptr, d_node_boxes.ptr, d_tree.ptr, d_parent_internal.ptr, d_parent_leaf.ptr, d_arrival.ptr);
         ctx->counters.kernel_launches++;
         // ---- upper hierarchy: PLOC over the leaf clusters; the plain LBVH emit is the fallback ----

@@ -104,6 +104,8 @@ struct Accel {
     bool has_uv = false;
     DeviceBuffer<float> shade_emission;         // 9 floats per primitive (per-vertex emission scale); only when a mesh has emission
     bool has_emission = false;
+    DeviceBuffer<uint32_t> slot_of_primitive;   // global primitive index -> position in `triangles` (Morton order): the spatial
+                                                // part of the key the surface hits are sorted by before shading
     DeviceBuffer<float> normal_matrices;        // 9 floats per instance record: inverse transpose of the upper 3x3
     int64_t triangle_count = 0;
     int64_t node_count = 0;
@@ -128,6 +130,9 @@ struct Context {
     bool has_transmissive_materials = false;
     bool use_wide = true; // BPT_WIDE=0 in the environment traverses the binary nodes (for A/B measurements)
     bool use_ploc = true; // BPT_BVH=lbvh in the environment selects the plain Morton hierarchy (for A/B measurements)
+    // Surface hits are sorted by (shading class, hit cell) before shading from this wavefront iteration on; -1 = never.
+    // bpt_set_hit_sorting; BPT_SORT_HITS in the environment sets the initial value.
+    int sort_hits_from_iteration = -1;
     DeviceBuffer<float4> nee_offsets; // 256 ReverseHalton toroidal shifts (Renderer.cpp:323-336)
 
     std::map<int, DeviceMesh> meshes;

@@ -73,6 +73,11 @@ struct Wavefront {
     DeviceBuffer<float4> sh_o, sh_d, sh_rad;
     DeviceBuffer<unsigned int> queue_a, queue_b;
     DeviceBuffer<unsigned int> queue_surface, queue_escaped; // extend sorts its results by what shading they need
+    // Sorting of the surface hits by (shading class, hit cell): keys beside queue_surface, the sorted queue, 2 x SORT_BINS
+    // counters (histogram, then running cursors) and the per-material shading class.
+    DeviceBuffer<unsigned short> surface_key;
+    DeviceBuffer<unsigned int> queue_surface_sorted, sort_bins;
+    DeviceBuffer<unsigned char> material_class;
     DeviceBuffer<QueueCounters> counters;
     DeviceBuffer<FrameState> frame_state;
     DeviceBuffer<float> coverage; // per material
@@ -92,6 +97,9 @@ struct WavefrontView {
                                      // parameter would make the compiler copy the whole struct to local memory
     unsigned int *queue_surface, *queue_escaped;
     unsigned int queue_capacity;      // entries per queue; the transmissive queue grows down from the end of queue_surface
+    unsigned short* surface_key;      // sort key of queue_surface[i]
+    unsigned int* queue_surface_sorted;
+    unsigned int* sort_bins;          // [0, SORT_BINS): histogram of the keys; [SORT_BINS, 2 SORT_BINS): scatter cursors
     QueueCounters* counters;
     const FrameState* frame;
     unsigned long long* ray_counters; // [0] extend, [1] shadow, [6] dropped non-finite samples, [7] iterations
@@ -113,6 +121,10 @@ struct SceneView {
     const float2* __restrict__ dielectric_tables;
     const float4* __restrict__ nee_offsets;
     bool split_by_shading_model; // the scene has Transmissive materials: extend keys surface hits by shading model
+    // Sorting of the surface hits before shading (north star (3): material-keyed sorting before shading)
+    const uint32_t* __restrict__ slot_of_primitive; // position of a primitive in the Morton-ordered triangle array
+    const unsigned char* __restrict__ material_class;
+    int sort_cell_shift;                          // hit cell = Morton slot >> shift, below SORT_CELLS
 };
 
 // Per-configuration constants (kernel parameters, baked into the graph).
@@ -121,7 +133,17 @@ struct FrameParams {
     unsigned int max_bounce_count;
     int next_event_sample_count;
     unsigned int russian_roulette_start_bounce; // 0 = off (the reference has no Russian roulette)
+    unsigned int sort_hits_from_iteration;      // surface hits are sorted from this iteration of a sample on; 0xffffffff = never
 };
+
+// Key of a surface hit: [shading class : 2][hit cell : 10]. The class separates what makes the shading code branch (Diffuse
+// versus Default shading model, coat or none); the cell is the top of the hit triangle's position in the Morton-ordered triangle
+// array, i.e. WHERE the path is. Sorting by it gives the shade kernel warps that read neighbouring triangles and materials
+// and take the same branches - and, because shading appends its rays in queue order, gives the next closest-hit launch and
+// the shadow launch warps whose rays start next to each other.
+constexpr unsigned int SORT_CELLS = 1024, SORT_CLASSES = 4, SORT_BINS = SORT_CELLS * SORT_CLASSES;
+__device__ __forceinline__ bool sorting_now(const QueueCounters* c, unsigned int from_iteration) { return c->iteration >= from_iteration; }
+
 
 // Appends `value` to a queue for every lane with `pred` set: one atomicAdd per warp.
 __device__ __forceinline__ void warp_append(bool pred, unsigned int* queue, unsigned int* counter, unsigned int value) {
@@ -191,6 +213,7 @@ __global__ void generate_kernel(WavefrontView w, FrameParams f) {
 
 // ---- extend: closest hit over triangles and analytic lights -------------------------------------------------
 
+template <bool SORT_HITS>
 struct ExtendSource {
     WavefrontView w;
     const unsigned int* __restrict__ queue_in;
@@ -199,6 +222,12 @@ struct ExtendSource {
     // Set when the scene has Transmissive materials: surface hits are then keyed by shading model.
     const ShadeTriangle* __restrict__ shade;
     const Material* __restrict__ materials;
+    // Read when the surface hits of this iteration are sorted before shading (SORT_HITS instantiation only).
+    bool sort_hits;
+    const ShadeTriangle* __restrict__ shade_all;
+    const uint32_t* __restrict__ slot_of_primitive;
+    const unsigned char* __restrict__ material_class;
+    int sort_cell_shift;
     __device__ void load(unsigned int i, Ray& ray, int& skip) const {
         unsigned int pixel = queue_in[i];
         float4 o = w.ray_o[pixel], d = w.ray_d[pixel];
@@ -232,7 +261,16 @@ struct ExtendSource {
         if (h.primitive >= 0 && !(h.primitive & LIGHT_HIT_FLAG)) {
             bool transmissive = shade != nullptr && materials[shade[h.primitive].material_index].shading_model == SHADING_TRANSMISSIVE;
             if (transmissive) w.queue_surface[w.queue_capacity - 1u - atomicAdd(&w.counters->transmissive, 1u)] = pixel;
-            else w.queue_surface[atomicAdd(&w.counters->surface, 1u)] = pixel;
+            else {
+                const unsigned int slot = atomicAdd(&w.counters->surface, 1u);
+                w.queue_surface[slot] = pixel;
+                if (SORT_HITS && sort_hits) {
+                    const unsigned int cell = min(slot_of_primitive[h.primitive] >> sort_cell_shift, SORT_CELLS - 1u);
+                    const unsigned int key = (unsigned int)material_class[shade_all[h.primitive].material_index] * SORT_CELLS + cell;
+                    w.surface_key[slot] = (unsigned short)key;
+                    atomicAdd(w.sort_bins + key, 1u);
+                }
+            }
         } else
             w.queue_escaped[atomicAdd(&w.counters->escaped, 1u)] = pixel;
 #ifdef BPT_TRAVERSAL_STATS
@@ -242,10 +280,14 @@ struct ExtendSource {
     }
 };
 
-__global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s) {
+// SORT_HITS: the instantiation that also writes the sort keys of the surface hits (bpt_set_hit_sorting); the default one
+// carries none of that state.
+template <bool SORT_HITS>
+__global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s, FrameParams f) {
     __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
-    ExtendSource source = { w, w.counters->parity ? w.queue_b : w.queue_a, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials };
+    ExtendSource<SORT_HITS> source = { w, w.counters->parity ? w.queue_b : w.queue_a, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials,
+                            SORT_HITS && sorting_now(w.counters, f.sort_hits_from_iteration), s.shade, s.slot_of_primitive, s.material_class, s.sort_cell_shift };
     traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
@@ -277,6 +319,42 @@ __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kern
     ShadowSource source = { w };
     traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
+}
+
+// Counting sort of the surface queue by key, two small kernels between the traversal and the shading of an iteration. The
+// histogram was filled by extend_kernel's atomics; one CTA turns it into running cursors (and clears it for the next
+// iteration), then every hit takes the next free position of its bin. The order inside a bin is whatever the atomics
+// make it - results do not depend on it, path state is indexed by pixel.
+__global__ void __launch_bounds__(1024) sort_scan_kernel(WavefrontView w, FrameParams f) {
+    if (!sorting_now(w.counters, f.sort_hits_from_iteration)) return;
+    __shared__ unsigned int warp_sums[32];
+    constexpr unsigned int PER_THREAD = SORT_BINS / 1024;
+    unsigned int v[PER_THREAD], sum = 0;
+#pragma unroll
+    for (unsigned int k = 0; k < PER_THREAD; ++k) { v[k] = w.sort_bins[threadIdx.x * PER_THREAD + k]; sum += v[k]; w.sort_bins[threadIdx.x * PER_THREAD + k] = 0; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned int inclusive = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, inclusive, o); if (lane >= o) inclusive += t; }
+    if (lane == 31) warp_sums[warp] = inclusive;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned int t2 = warp_sums[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned int t = __shfl_up_sync(0xffffffffu, t2, o); if (lane >= o) t2 += t; }
+        warp_sums[lane] = t2;
+    }
+    __syncthreads();
+    unsigned int running = (warp ? warp_sums[warp - 1] : 0u) + inclusive - sum;
+#pragma unroll
+    for (unsigned int k = 0; k < PER_THREAD; ++k) { w.sort_bins[SORT_BINS + threadIdx.x * PER_THREAD + k] = running; running += v[k]; }
+}
+
+__global__ void __launch_bounds__(256) sort_scatter_kernel(WavefrontView w, FrameParams f) {
+    if (!sorting_now(w.counters, f.sort_hits_from_iteration)) return;
+    const unsigned int count = w.counters->surface;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        w.queue_surface_sorted[atomicAdd(w.sort_bins + SORT_BINS + w.surface_key[i], 1u)] = w.queue_surface[i];
 }
 
 // Ends an iteration: the appended paths become the active queue, the queue roles flip, and the graph's WHILE node is told
@@ -382,7 +460,9 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     unsigned int* __restrict__ queue_out = parity ? w.queue_a : w.queue_b;
     unsigned int* shadow_counter = w.counters->shadow + parity;
     const unsigned int count = SURFACE ? (TRANSMISSIVE ? w.counters->transmissive : w.counters->surface) : w.counters->escaped;
-    const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count) : w.queue_surface) : w.queue_escaped;
+    const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count)
+                                                                     : (sorting_now(w.counters, f.sort_hits_from_iteration) ? w.queue_surface_sorted : w.queue_surface))
+                                                     : w.queue_escaped;
     const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
         bool valid = i < count;
@@ -656,6 +736,7 @@ struct SampleLaunch {
     int64_t pixels;
     int trace_grid, shade_grid, stream_grid, escaped_grid;
     int transmissive; // the scene holds Transmissive materials: a third shade kernel per iteration
+    int sort_hits;    // two more kernels per iteration: the counting sort of the surface queue
 };
 
 void destroy_graph(Wavefront* wf) {
@@ -700,12 +781,20 @@ cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L, double** accumula
 
     cudaGraphNode_t traced[2], shaded[3], advance;
     void* trace_args[] = { &L.w, &L.s };
-    GRAPH_CHECK(add_kernel(&traced[0], body, nullptr, 0, (const void*)extend_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
-    GRAPH_CHECK(add_kernel(&traced[1], body, nullptr, 0, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
     void* shade_args[] = { &L.w, &L.s, &L.f };
+    GRAPH_CHECK(add_kernel(&traced[0], body, nullptr, 0, L.sort_hits ? (const void*)extend_kernel<true> : (const void*)extend_kernel<false>, L.trace_grid, TRACE_BLOCK, shade_args));
+    GRAPH_CHECK(add_kernel(&traced[1], body, nullptr, 0, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
     size_t shade_count = 0;
     GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<false, false>, L.escaped_grid, SHADE_BLOCK, shade_args));
-    GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<true, false>, L.shade_grid, SHADE_BLOCK, shade_args));
+    if (L.sort_hits) { // the surface shading waits for the sorted queue; escaped paths are shaded beside the sort
+        cudaGraphNode_t scan, scatter, surface_inputs[2];
+        void* sort_args[] = { &L.w, &L.f };
+        GRAPH_CHECK(add_kernel(&scan, body, &traced[0], 1, (const void*)sort_scan_kernel, 1, 1024, sort_args));
+        GRAPH_CHECK(add_kernel(&scatter, body, &scan, 1, (const void*)sort_scatter_kernel, L.stream_grid, 256, sort_args));
+        surface_inputs[0] = scatter; surface_inputs[1] = traced[1]; // the shadow kernel adds to the radiance shading reads
+        GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, surface_inputs, 2, (const void*)shade_kernel<true, false>, L.shade_grid, SHADE_BLOCK, shade_args));
+    } else
+        GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<true, false>, L.shade_grid, SHADE_BLOCK, shade_args));
     if (L.transmissive)
         GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<true, true>, L.shade_grid, SHADE_BLOCK, shade_args));
     QueueCounters* counters = L.w.counters;
@@ -738,10 +827,15 @@ int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
     while (true) {
         for (uint32_t it = 0; it < planned; ++it) {
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 0)], st);
-            extend_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
+            if (L.sort_hits) extend_kernel<true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            else extend_kernel<false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
             shadow_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
+            if (L.sort_hits) { // timed with the shading it serves
+                sort_scan_kernel<<<1, 1024, 0, st>>>(L.w, L.f);
+                sort_scatter_kernel<<<L.stream_grid, 256, 0, st>>>(L.w, L.f);
+            }
             shade_kernel<false, false><<<L.escaped_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
             shade_kernel<true, false><<<L.shade_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
             if (L.transmissive) shade_kernel<true, true><<<L.shade_grid, SHADE_BLOCK, 0, st>>>(L.w, L.s, L.f);
@@ -785,6 +879,7 @@ void release_wavefront(Context* ctx) {
     wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
     wf->queue_surface.release(); wf->queue_escaped.release();
     wf->counters.release(); wf->frame_state.release(); wf->coverage.release();
+    wf->surface_key.release(); wf->queue_surface_sorted.release(); wf->sort_bins.release(); wf->material_class.release();
     delete wf;
     ctx->wavefront = nullptr;
 }
@@ -813,14 +908,25 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_a.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_b.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->queue_surface.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_escaped.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->surface_key.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->queue_surface_sorted.resize(pixels));
+        BPT_CUDA_CHECK(ctx, wf->sort_bins.resize(2 * SORT_BINS));
+        BPT_CUDA_CHECK(ctx, cudaMemsetAsync(wf->sort_bins.ptr, 0, 2 * SORT_BINS * sizeof(unsigned int), st));
         BPT_CUDA_CHECK(ctx, wf->counters.resize(1)); BPT_CUDA_CHECK(ctx, wf->frame_state.resize(1));
         wf->pixel_capacity = pixels;
     }
     if (wf->coverage_version != ctx->material_version) {
         std::vector<float> h_cov(ctx->host_materials.size());
-        for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
+        std::vector<unsigned char> h_class(std::max<size_t>(ctx->host_materials.size(), 1), 0);
+        for (size_t i = 0; i < h_cov.size(); ++i) {
+            const Material& m = ctx->host_materials[i];
+            h_cov[i] = material_coverage_table_entry(m);
+            // what the surface shading branches on: the shading model (DefaultShading.h vs DiffuseShading.h) and the coat lobe
+            h_class[i] = (unsigned char)((m.shading_model == SHADING_DIFFUSE ? 1u : 0u) | (m.coat != 0 ? 2u : 0u));
+        }
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // as above when the table has to grow
         BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
+        BPT_CUDA_CHECK(ctx, wf->material_class.resize(h_class.size()));
+        BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->material_class.ptr, h_class.data(), h_class.size(), cudaMemcpyHostToDevice, st));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->coverage.ptr, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // h_cov goes out of scope
         wf->coverage_version = ctx->material_version;
@@ -868,6 +974,10 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     s.dielectric_tables = ctx->dielectric_tables.ptr;
     s.split_by_shading_model = ctx->has_transmissive_materials;
     s.nee_offsets = ctx->nee_offsets.ptr;
+    s.slot_of_primitive = ctx->accel.slot_of_primitive.ptr;
+    s.material_class = wf->material_class.ptr;
+    s.sort_cell_shift = 0;
+    while ((ctx->accel.triangle_count >> s.sort_cell_shift) > (int64_t)SORT_CELLS) ++s.sort_cell_shift;
 
     WavefrontView& w = L.w;
     w.ray_o = wf->ray_o.ptr; w.ray_d = wf->ray_d.ptr; w.thr = wf->thr.ptr; w.rad = wf->rad.ptr; w.hit = wf->hit.ptr;
@@ -875,6 +985,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     w.queue_a = wf->queue_a.ptr; w.queue_b = wf->queue_b.ptr;
     w.queue_surface = wf->queue_surface.ptr; w.queue_escaped = wf->queue_escaped.ptr;
     w.queue_capacity = (unsigned int)pixels;
+    w.surface_key = wf->surface_key.ptr; w.queue_surface_sorted = wf->queue_surface_sorted.ptr; w.sort_bins = wf->sort_bins.ptr;
     w.counters = wf->counters.ptr;
     w.frame = wf->frame_state.ptr;
     w.ray_counters = reinterpret_cast<unsigned long long*>(ctx->device_counters);
@@ -884,6 +995,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     f.max_bounce_count = settings->max_bounce_count;
     f.next_event_sample_count = settings->next_event_sample_count;
     f.russian_roulette_start_bounce = settings->russian_roulette_start_bounce;
+    f.sort_hits_from_iteration = ctx->sort_hits_from_iteration < 0 ? 0xffffffffu : (unsigned int)ctx->sort_hits_from_iteration;
 
     // Persistent grids: a whole number of CTAs per SM.
     L.pixels = pixels;
@@ -892,7 +1004,8 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     L.stream_grid = ctx->sm_count * 8;
     L.escaped_grid = ctx->sm_count * 4;
     L.transmissive = ctx->has_transmissive_materials ? 1 : 0;
-    ctx->launches_per_iteration = 5 + L.transmissive;
+    L.sort_hits = ctx->sort_hits_from_iteration >= 0 ? 1 : 0;
+    ctx->launches_per_iteration = 5 + L.transmissive + 2 * L.sort_hits;
 
     // What changes per call travels through device memory, as the by-value argument of a one-thread kernel: fully
     // asynchronous, no staging buffer whose lifetime the host would have to track.

@@ -200,6 +200,12 @@ int bpt_set_environment_cdfs(bpt_ctx* ctx, const float* marginal_cdf, const floa
  * (texel + per pixel PDF) in both modes. */
 enum { BPT_ENVIRONMENT_NEE_PRESAMPLED = 0, BPT_ENVIRONMENT_NEE_CDF = 1 };
 int bpt_set_environment_sampling(bpt_ctx* ctx, int mode);
+/* Sorting of the surface hits before shading. From wavefront iteration `from_iteration` of a sample on (0 = from the camera rays'
+ * hits on, 1 = from the first bounce on, < 0 = never) the hits are put in the order of a 12-bit key - the material's shading
+ * class (shading model, coat) and the cell of the hit triangle in the Morton order of the acceleration structure - by a
+ * counting sort on the device. Results do not depend on it (path state is indexed by pixel); it only changes which paths
+ * share a warp in the shading kernel and, through the order the new rays are queued in, in the following traversal kernels. */
+int bpt_set_hit_sorting(bpt_ctx* ctx, int from_iteration);
 /* Acceleration structure build; replaces OptiX Trbvh (Renderer.cpp:161-182,470-477). Flattens the
  * instances to world space, builds the LBVH on the device. Must be called after meshes/instances change. */
 int bpt_build_accel(bpt_ctx* ctx);

@@ -415,3 +415,29 @@ def test_environment_cdf_next_event_estimation(bpt):
     bpt.render(scene["camera"], 96, 54, 0, 256, reset=True)
     presampled = bpt.resolve_float4()[..., :3]
     assert abs(by_cdf.mean() - presampled.mean()) < 0.03 * presampled.mean(), (by_cdf.mean(), presampled.mean())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("from_iteration", [0, 1])
+def test_hit_sorting_does_not_change_the_image(bpt, from_iteration):
+    """Sorting the surface hits by (shading class, hit cell) before shading only changes which paths share a warp: the
+    accumulated image is bit for bit the unsorted one, with mixed shading classes (Default, Diffuse, coat) in the scene."""
+    scene = scenes.cornell_box(sphere_quads=(32, 16))
+    mats = scene["materials"].copy()
+    mats[5]["coat"] = 65535; mats[5]["coat_roughness"] = 20000
+    mats[2]["shading_model"] = 1  # Diffuse
+    scene["materials"] = mats
+    scenes.upload(bpt, scene)
+    try:
+        bpt.set_hit_sorting(-1)
+        bpt.counters(reset=True)
+        bpt.render(scene["camera"], 160, 120, 0, 4, reset=True)
+        plain = bpt.resolve_float4(); plain_counters = bpt.counters()
+        bpt.set_hit_sorting(from_iteration)
+        bpt.counters(reset=True)
+        bpt.render(scene["camera"], 160, 120, 0, 4, reset=True)
+        ordered = bpt.resolve_float4(); ordered_counters = bpt.counters()
+    finally:
+        bpt.set_hit_sorting(-1)
+    assert np.array_equal(plain, ordered)
+    assert plain_counters["extend_rays"] == ordered_counters["extend_rays"] and plain_counters["shadow_rays"] == ordered_counters["shadow_rays"]
