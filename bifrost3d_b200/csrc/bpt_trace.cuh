@@ -263,6 +263,9 @@ struct Traversal {
 
     // One visit of a four-wide node: tests the four children, continues with the nearest one that is hit and defers the
     // others, farthest first, so that they come off the stack nearest first.
+    // (Measured in round 2 and dropped: letting the ray pick the entry / exit plane float4 of each axis by the sign of its
+    // direction removes the 24 per-axis min / max of the four slab tests, but the six loads then need computed addresses
+    // instead of [node + immediate]: extend +4 % SLOWER on the 1 M and 20 k triangle scenes, +7 % on the 50 M one.)
     BPT_D void wide_step(const AccelView& a) {
 #ifdef BPT_TRAVERSAL_STATS
         ++stat_nodes;

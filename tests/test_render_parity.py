@@ -44,10 +44,12 @@ def test_cornell_box_matches_oracle_sample_for_sample(bpt):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    # FP-order differences only: nearly all pixels agree to 1e-4, the rest took a different discrete decision in one sample
-    assert close.mean() > 0.98
-    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.002 * int(oc[0])
-    assert abs(int(counters["shadow_rays"]) - int(oc[1])) <= 0.002 * int(oc[1])
+    # FP-order differences only. Measured on B200 (round 2): every pixel of every scene of this file within 1e-4 and the ray
+    # counts identical to the oracle's, at 96 x 54 as well as at 1920 x 1080; the bound leaves room for one pixel in a thousand
+    # to take a different discrete decision (lobe choice, light choice, coverage test) on a last-bit difference.
+    assert close.mean() > 0.999
+    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 1e-4 * int(oc[0])
+    assert abs(int(counters["shadow_rays"]) - int(oc[1])) <= 1e-4 * int(oc[1])
 
 
 @pytest.mark.gpu
@@ -107,7 +109,7 @@ def test_vertex_tints_coverage_and_light_types(bpt):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
+    assert close.mean() > 0.999
 
 
 @pytest.mark.gpu
@@ -122,7 +124,7 @@ def test_environment_map_importance_sampling_and_mis(bpt):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
+    assert close.mean() > 0.999
 
 
 @pytest.mark.gpu
@@ -137,7 +139,7 @@ def test_instanced_terrain_small(bpt):
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert cpu.mean() > 0.005
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
+    assert close.mean() > 0.999
 
 
 @pytest.mark.gpu
@@ -209,7 +211,7 @@ def test_transmissive_shading_model_matches_oracle(bpt):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
+    assert close.mean() > 0.999
     assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.003 * int(oc[0])
     # the glass spheres transmit: with the same spheres opaque (Default model) the image differs visibly
     opaque = scene["materials"].copy()
@@ -369,7 +371,7 @@ def test_material_grid_full_res_finite(bpt):
             close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
             print(f"sample {sample} row {y}: pixel ({x},{y}) gpu {gpu[y, x, :3]} cpu {cpu[x]}; within 1e-4: {close.mean():.4f}")
             assert close[x], "the formerly NaN pixel matches the oracle"
-            assert close.mean() > 0.97
+            assert close.mean() > 0.999
     finally:
         sc.close()
 
@@ -389,9 +391,9 @@ def test_full_resolution_one_sample_image_parity(bpt, workload):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"{workload} {W}x{H}: relMSE {e:.3e}; pixels within 1e-4: {close.mean():.5f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
-    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 0.002 * int(oc[0])
-    assert abs(int(counters["shadow_rays"]) - int(oc[1])) <= 0.002 * int(oc[1])
+    assert close.mean() > 0.999
+    assert abs(int(counters["extend_rays"]) - int(oc[0])) <= 1e-4 * int(oc[0])
+    assert abs(int(counters["shadow_rays"]) - int(oc[1])) <= 1e-4 * int(oc[1])
 
 
 @pytest.mark.gpu
@@ -407,7 +409,7 @@ def test_environment_cdf_next_event_estimation(bpt):
     close = diff <= 1e-4 * (1 + np.abs(cpu).max(axis=-1))
     print(f"cdf NEE: relMSE {e:.3e}; pixels within 1e-4: {close.mean():.4f}; rays gpu {counters['extend_rays']}+{counters['shadow_rays']} cpu {oc[0]}+{oc[1]}")
     assert e <= REL_MSE_BOUND
-    assert close.mean() > 0.97
+    assert close.mean() > 0.999
     # expectation: 256 spp with either estimator
     bpt.render(scene["camera"], 96, 54, 0, 256, reset=True)
     by_cdf = bpt.resolve_float4()[..., :3]

@@ -13,15 +13,21 @@ pytestmark = pytest.mark.gpu
 
 KINDS = {"default": 0, "ggx_r": 1, "oren_nayar": 2, "burley": 3}
 
-# Fraction of tuples allowed to exceed the 1e-5 relative bound. These are ill-conditioned tuples
-# (sqrt(1 - x*x - y*y) near the horizon, rescaled lobe-selection numbers) where the rare 1 ulp difference in sin/cos/pow
-# between glibc and CUDA's libdevice is amplified; see DESIGN.md "FP contract".
-ALLOWED_OUTLIER_FRACTION = 5e-5
-OUTLIER_REL_TOL = 2e-3
+# The north star's bound is 1e-5 relative. What B200 measures against the host-compiled reference headers (round 2, 262 144
+# tuples per BSDF, printed by every run of these tests):
+#   evaluate_with_PDF (f and PDF): every element within 1e-5 (max 5e-7; bit-exact for GGX_R, Oren-Nayar, Burley) -> NO allowance.
+#   sample (f, PDF, direction): at most 6 of 786 432 elements above 1e-5, the largest 1.3e-4 (Oren-Nayar PDF). All of them are
+#     tuples where the sampled direction lies within ~1e-3 of the horizon: the samplers end in sqrt(1 - x^2 - y^2) (clipped LTC,
+#     Distributions.h:214-216; bounded VNDF, :411-414) whose relative condition number is 1 / (1 - x^2 - y^2), and x, y carry the
+#     1 ulp by which glibc's sinf / cosf (not correctly rounded in ~1e-3 of the arguments) differ from the correctly rounded
+#     values the device computes. The allowance below is sized to that: 2e-5 of the elements, none above 5e-4; the offending
+#     tuples are printed so that a change in their number or kind shows up in the log.
+SAMPLE_OUTLIER_FRACTION = 2e-5
+SAMPLE_OUTLIER_REL_TOL = 5e-4
 
 
 def allowed_outliers(n):
-    return max(2, int(np.ceil(ALLOWED_OUTLIER_FRACTION * n)))
+    return max(2, int(np.ceil(SAMPLE_OUTLIER_FRACTION * n)))
 
 
 def compare_bsdf(got, want, what):
@@ -31,21 +37,30 @@ def compare_bsdf(got, want, what):
         mismatch = cg != cw
         # a PDF straddling the 1e-6 validity threshold by rounding is a legitimate class flip
         near_threshold = np.abs(np.abs(want[key]) - 1e-6) < 1e-9
-        count = np.sum(mismatch & ~near_threshold)
-        assert count <= allowed_outliers(mismatch.size), f"{what}.{key}: {count} PDF class mismatches"
+        count = int(np.sum(mismatch & ~near_threshold))
+        limit = 0 if key == "eval_pdf" else allowed_outliers(mismatch.size)
+        assert count <= limit, f"{what}.{key}: {count} PDF class mismatches"
     for key, floor in (("eval_f", 1e-6), ("eval_pdf", 1e-6), ("sample_f", 1e-6), ("sample_pdf", 1e-6)):
         # Compare samples only where both agree the sample is usable (the reflectance of an invalid sample is unspecified).
         e = rel_err(got[key], want[key], floor)
+        rows = np.arange(e.shape[0])
         if key.startswith("sample"):
             valid = pdf_class(want["sample_pdf"]) == pdf_class(got["sample_pdf"])
-            e = e[valid]
+            e = e[valid]; rows = rows[valid]
         msgs.append(report(f"{what}.{key}", e, REL_TOL))
-        assert np.sum(e > REL_TOL) <= allowed_outliers(e.size), msgs[-1]
-        assert np.all(e[np.isfinite(e)] <= OUTLIER_REL_TOL) or np.mean(e > OUTLIER_REL_TOL) < 2e-5, msgs[-1]
+        bad = np.argwhere(e > REL_TOL)
+        for index in bad[:8]:
+            row = rows[index[0]]
+            msgs.append(f"    tuple {row}: got {np.atleast_1d(got[key][row])} want {np.atleast_1d(want[key][row])} sampled direction z {want['sample_dir'][row][2]:.3e}")
+        if key.startswith("eval"):
+            assert bad.shape[0] == 0, "\n".join(msgs[-9:])
+        else:
+            assert bad.shape[0] <= allowed_outliers(e.size), "\n".join(msgs[-9:])
+            assert np.all(e[np.isfinite(e)] <= SAMPLE_OUTLIER_REL_TOL), "\n".join(msgs[-9:])
     valid = (pdf_class(want["sample_pdf"]) == 3) & (pdf_class(got["sample_pdf"]) == 3)
     d = np.abs(got["sample_dir"][valid].astype(np.float64) - want["sample_dir"][valid])
     msgs.append(f"{what}.sample_dir: max abs err {d.max() if d.size else 0:.3e}, {int(np.sum(d > 1e-5))}/{d.size} above 1e-5")
-    assert np.sum(d > 1e-5) <= allowed_outliers(d.size), msgs[-1]
+    assert np.sum(d > 1e-5) == 0, msgs[-1]
     return msgs
 
 
@@ -200,16 +215,21 @@ def test_lights_match_reference(bpt, ref):
     gs, gp, gr = bpt.light_sample_pdf_evaluate(lights, position, u2, q)
     g = np.concatenate([gs["radiance"], gs["pdf"][:, None], gs["direction_to_light"], gs["distance"][:, None]], axis=1)
 
-    assert np.mean(pdf_class(g[:, 3]) != pdf_class(rs[:, 3])) < 1e-4
+    # Measured on B200 (round 2): every one of the 65 536 sphere / spot / directional elements within 1e-5 (sample radiance and
+    # PDF max 3e-7, direction 1.2e-7 absolute, distance 2.5e-7, pdf() and evaluate() bit-exact), so there is NO allowance; a PDF
+    # within rounding of the 1e-6 validity threshold may change class.
+    def class_mismatches(a, b):
+        mismatch = pdf_class(a) != pdf_class(b)
+        return int(np.sum(mismatch & ~(np.abs(np.abs(b) - 1e-6) < 1e-9)))
+    assert class_mismatches(g[:, 3], rs[:, 3]) == 0
     e = rel_err(g[:, 0:4], rs[:, 0:4], 1e-6)
-    print(report("light.sample radiance/pdf", e, REL_TOL)); assert np.mean(e > REL_TOL) < 5e-4
+    print(report("light.sample radiance/pdf", e, REL_TOL)); assert np.all(e <= REL_TOL)
     d = np.abs(g[:, 4:7].astype(np.float64) - rs[:, 4:7]); d = d[np.isfinite(d)]
-    print("light.sample direction max abs", d.max()); assert np.mean(d > 1e-5) < 5e-4
+    print("light.sample direction max abs", d.max()); assert np.all(d <= 1e-5)
     e = rel_err(g[:, 7], rs[:, 7], 1e-6)
-    print(report("light.sample distance", e, REL_TOL)); assert np.mean(e > 1e-4) < 1e-3
-    assert np.mean(pdf_class(gp) != pdf_class(rp)) < 2e-3
-    same = pdf_class(gp) == pdf_class(rp)
-    e = rel_err(gp[same], rp[same], 1e-6)
-    print(report("light.pdf", e, REL_TOL)); assert np.mean(e > REL_TOL) < 1e-3
+    print(report("light.sample distance", e, REL_TOL)); assert np.all(e <= REL_TOL)
+    assert class_mismatches(gp, rp) == 0
+    e = rel_err(gp, rp, 1e-6)
+    print(report("light.pdf", e, REL_TOL)); assert np.all(e <= REL_TOL)
     e = rel_err(gr, rr, 1e-6)
-    print(report("light.evaluate", e, REL_TOL)); assert np.mean(e > REL_TOL) < 2e-3
+    print(report("light.evaluate", e, REL_TOL)); assert np.all(e <= REL_TOL)
