@@ -310,6 +310,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="materials", help="materials = BASELINE.json configs[2] (1080p, 4 bounces: the configuration the metric is quoted on); cornell = configs[1]; terrain = configs[3]; bsdf = configs[0] (2^22 BSDF tuples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--spp-total", type=int, default=0, metavar="T",
+                    help="configs[4]: render T samples per pixel in total, T / N on each of the N GPUs (strong scaling; overrides --steps)")
     ap.add_argument("--sort-hits", type=int, default=None, metavar="K",
                     help="sort the surface hits by (shading class, hit cell) before shading from wavefront iteration K on (bpt_set_hit_sorting); -1 = never; default: the library's")
     ap.add_argument("--russian-roulette", type=int, default=0, metavar="N",
@@ -347,6 +349,10 @@ def main():
     info = ctx.accel_info()
     stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     cam = capi.make_camera(*scene["camera"])
+    if args.spp_total:
+        if args.spp_total % world:
+            raise SystemExit(f"--spp-total {args.spp_total} is not a multiple of the {world} GPUs")
+        args.steps = args.spp_total // world  # sample ranges [g T / N, (g + 1) T / N), SURVEY.md 8(d) C5
     K, Wm = args.steps, args.warmup
 
     def barrier():
@@ -382,12 +388,12 @@ def main():
     device_ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     counters = ctx.counters()
-    t = torch.tensor([device_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([device_ms, info["build_ms"]], dtype=torch.float64, device="cuda")
     rays = torch.tensor([float(counters["extend_rays"]), float(counters["shadow_rays"])], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
-    device_ms = float(t.item())
+    device_ms = float(t[0].item()); slowest_build_ms = float(t[1].item())
     total_samples = W * H * K * world
     value = total_samples / (device_ms * 1e-3) / 1e6
     mrays = float(rays.sum().item()) / (device_ms * 1e-3) / 1e6
@@ -458,11 +464,12 @@ def main():
 
     if rank == 0:
         line = {"metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": device_ms / K,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "higher_is_better": True, "scaling": "strong" if args.spp_total else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "iterations_per_step": counters["iterations"] / K,
                 "mrays_per_s": mrays, "extend_rays_per_step": counters["extend_rays"] / K, "shadow_rays_per_step": counters["shadow_rays"] / K,
                 "config": workload_config(args, scene, settings),
-                "bvh": {"triangles": info["triangles"], "nodes": info["nodes"], "build_ms": info["build_ms"], "mtris_per_s": info["triangles"] / max(info["build_ms"], 1e-6) / 1e3},
+                "bvh": {"triangles": info["triangles"], "nodes": info["nodes"], "build_ms": info["build_ms"], "mtris_per_s": info["triangles"] / max(info["build_ms"], 1e-6) / 1e3,
+                        "slowest_rank_build_ms": slowest_build_ms, "note": "every rank builds the same hierarchy over the replicated scene, outside the timed region"},
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.Settings)),
                         "d2h_bytes_per_step": int(frame.nbytes), "steps": e2e_steps},
                 "gpu_launches": int(counters["kernel_launches"]), "gpu_launches_per_step": launches_per_step,

@@ -48,7 +48,7 @@ class Settings(C.Structure):
 class Counters(C.Structure):
     _fields_ = [("extend_rays", C.c_uint64), ("shadow_rays", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("extend_ms", C.c_float), ("shadow_ms", C.c_float), ("shade_ms", C.c_float), ("other_ms", C.c_float),
-                ("extend_node_visits", C.c_uint64), ("extend_triangle_tests", C.c_uint64), ("nonfinite_samples", C.c_uint64), ("iterations", C.c_uint64)]
+                ("extend_node_visits", C.c_uint64), ("extend_triangle_tests", C.c_uint64), ("nonfinite_samples", C.c_uint64), ("traversal_stack_overflows", C.c_uint64), ("iterations", C.c_uint64)]
 
 
 assert C.sizeof(Material) == 64 and C.sizeof(Light) == 48 and C.sizeof(LightSample) == 32

@@ -798,6 +798,7 @@ int bpt_get_counters(bpt_ctx* c, bpt_counters* out, int reset) {
     ctx->counters.shadow_rays = host[1];
     ctx->counters.extend_node_visits = host[2];   // only counted by builds with -DBPT_TRAVERSAL_STATS
     ctx->counters.extend_triangle_tests = host[3];
+    ctx->counters.traversal_stack_overflows = host[5];
     ctx->counters.nonfinite_samples = host[6];
     ctx->counters.iterations = host[7];
     if (out) {

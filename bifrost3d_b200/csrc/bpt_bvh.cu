@@ -529,6 +529,7 @@ struct BatchSource {
         ray.tmin = tmin[i]; ray.tmax = tmax[i];
         skip = -1;
     }
+    __device__ float termination_weight(unsigned int) const { return 1.0f; }
     __device__ void store(unsigned int i, const Traversal<false>& tr) const {
         Hit h = tr.result();
         if (out_primitive) out_primitive[i] = h.primitive;

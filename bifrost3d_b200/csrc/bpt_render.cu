@@ -236,6 +236,7 @@ struct ExtendSource {
         // concurrently adds to the xyz lanes of the same record.
         skip = __float_as_int(reinterpret_cast<const float*>(w.rad + pixel)[3]);
     }
+    __device__ float termination_weight(unsigned int) const { return 1.0f; }
     __device__ void store(unsigned int i, const Traversal<false>& tr) const {
         Hit h = tr.result();
         float t_closest = h.primitive >= 0 ? h.t : RT_DEFAULT_MAX;
@@ -301,6 +302,7 @@ struct ShadowSource {
         ray.origin = f3(o); ray.tmin = 0.0f; ray.direction = f3(d); ray.tmax = o.w;
         skip = -1;
     }
+    __device__ float termination_weight(unsigned int i) const { return w.sh_rad[i].w; } // max(r, g, b), stored by the shade kernel
     __device__ void store(unsigned int i, const Traversal<true>& tr) const {
         if (tr.transmission > 0.0f) {
             unsigned int pixel = __float_as_uint(w.sh_d[i].w);
@@ -646,7 +648,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                         cast_shadow = true;
                         shadow_o = f4(light_sample_origin, light_sample.distance);
                         shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
-                        shadow_rad = f4(light_sample.radiance, 0.0f);
+                        shadow_rad = f4(light_sample.radiance, fmaxf(fmaxf(light_sample.radiance.x, light_sample.radiance.y), light_sample.radiance.z));
                     }
                 }
             }

@@ -138,9 +138,13 @@ struct TraversalStack {
     int* smem;                // [STACK_SMEM][TRACE_BLOCK], this thread's column
     int* spill;               // [STACK_LOCAL]
     int sp;
-    BPT_D void push(int link) {
+    // The build only hands out hierarchies whose depth fits (bpt_bvh.cu: 3 x wide levels + 1 <= STACK_SMEM + STACK_LOCAL, binary
+    // depth <= 96, else it falls back), so the last branch is unreachable by construction; if it ever ran, the dropped subtree
+    // would be a wrong image, so it is counted (bpt_counters.traversal_stack_overflows) instead of passing silently.
+    BPT_D void push(int link, unsigned long long* overflow_counter) {
         if (sp < STACK_SMEM) smem[sp * TRACE_BLOCK] = link;
         else if (sp - STACK_SMEM < STACK_LOCAL) spill[sp - STACK_SMEM] = link;
+        else atomicAdd(overflow_counter, 1ull);
         ++sp;
     }
     BPT_D int pop() {
@@ -156,6 +160,7 @@ struct AccelView {
     const TraceTriangle* __restrict__ triangles;
     const Material* __restrict__ materials; // with `textures`: only read by any-hit rays that meet a coverage-textured material
     TextureView textures;
+    unsigned long long* overflow_counter; // pushes beyond the traversal stack (never, see TraversalStack::push)
     int min_active; // see traversal_min_active_for
     int budget; // upper bound on the node visits between two refills of a warp's idle lanes
 };
@@ -181,6 +186,7 @@ inline AccelView accel_view(const Context* ctx) {
     a.materials = ctx->materials.ptr;
     a.textures.objects = ctx->texture_objects.ptr;
     a.textures.uv = ctx->accel.has_uv ? ctx->accel.shade_uv.ptr : nullptr;
+    a.overflow_counter = reinterpret_cast<unsigned long long*>(ctx->device_counters) + 5;
     a.min_active = traversal_min_active_for(ctx->accel.triangle_count);
     a.budget = traversal_budget_for(ctx->accel.triangle_count);
     return a;
@@ -214,6 +220,7 @@ struct Traversal {
     float tmax;          // closest hit: shrinks to the best t; any hit: < 0 once the ray is blocked
     Hit hit;
     float transmission;
+    float termination_weight; // any hit: the largest channel of the radiance the ray carries (1 for plain occlusion queries)
     int skip_primitive;
     int node;
     int postponed;       // a leaf found while other lanes were still descending; NODE_EMPTY when none
@@ -229,6 +236,7 @@ struct Traversal {
         tmax = r.tmax;
         hit.t = r.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
         transmission = 1.0f;
+        termination_weight = 1.0f;
         skip_primitive = skip;
         stack.sp = 0;
         node = 0; // root
@@ -252,7 +260,7 @@ struct Traversal {
         if (hit_l && hit_r) {
             bool left_first = tn_l <= tn_r;
             node = left_first ? links.x : links.y;
-            stack.push(left_first ? links.y : links.x);
+            stack.push(left_first ? links.y : links.x, a.overflow_counter);
         } else if (hit_l)
             node = links.x;
         else if (hit_r)
@@ -287,9 +295,9 @@ struct Traversal {
 #define BPT_CSWAP(ta, la, tb, lb) { bool s = tb < ta; float tt = s ? tb : ta; tb = s ? ta : tb; ta = tt; int ll = s ? lb : la; lb = s ? la : lb; la = ll; }
             BPT_CSWAP(t0, l0, t1, l1) BPT_CSWAP(t2, l2, t3, l3) BPT_CSWAP(t0, l0, t2, l2) BPT_CSWAP(t1, l1, t3, l3) BPT_CSWAP(t1, l1, t2, l2)
 #undef BPT_CSWAP
-            if (hits > 3) stack.push(l3);
-            if (hits > 2) stack.push(l2);
-            stack.push(l1);
+            if (hits > 3) stack.push(l3, a.overflow_counter);
+            if (hits > 2) stack.push(l2, a.overflow_counter);
+            stack.push(l1, a.overflow_counter);
             node = l0;
         } else
             node = h0 ? l0 : (h1 ? l1 : (h2 ? l2 : l3));
@@ -309,12 +317,13 @@ struct Traversal {
             bool candidate = watertight_triangle(shear, ray.origin, f3(v0), f3(v1), f3(v2), t, u, v) && primitive != skip_primitive;
             if (ANY_HIT) {
                 if (candidate && t > ray.tmin && t < ray.tmax) {
-                    // shadow_any_hit, MonteCarlo.cu:278-285: attenuate by (1 - coverage); opaque surfaces terminate.
+                    // shadow_any_hit, MonteCarlo.cu:278-285: the payload radiance is attenuated by (1 - coverage) and the ray ends
+                    // once all its channels are below 1e-7, i.e. once largest channel x transmission is; opaque surfaces end it.
                     float coverage = coverage_by_material[__float_as_int(v1.w)];
                     if (coverage < 0.0f) // coverage texture: Material::get_coverage(texcoord), Types.h:405-414
                         coverage = material_coverage(a.materials[__float_as_int(v1.w)], a.textures, interpolate_texcoord(a.textures, primitive, u, v));
                     transmission *= 1.0f - coverage;
-                    if (transmission < 0.0000001f) { transmission = 0.0f; return false; }
+                    if (transmission * termination_weight < 0.0000001f) { transmission = 0.0f; return false; }
                 }
             } else if (candidate && t > ray.tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
                 // hit.t starts at ray.tmax and hit.primitive at INT_MAX, so a first hit needs t < tmax.
@@ -365,7 +374,8 @@ struct Traversal {
 };
 
 // Persistent-thread driver. `Source` supplies rays and consumes results:
-//   bool load(unsigned int index, Ray& ray, int& skip_primitive)
+//   void load(unsigned int index, Ray& ray, int& skip_primitive)
+//   float termination_weight(unsigned int index)        (any hit only: the largest radiance channel the ray carries)
 //   void store(unsigned int index, const Traversal<ANY_HIT>& traversal)
 // `fetch_counter` is a zero-initialised global counter shared by all CTAs of the launch. Must be called by whole warps.
 template <bool ANY_HIT, class Source>
@@ -397,6 +407,7 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
                     Ray ray; int skip;
                     source.load(index, ray, skip);
                     tr.begin(ray, skip);
+                    if (ANY_HIT) tr.termination_weight = source.termination_weight(index);
                     has_ray = true;
                 } else
                     exhausted = true;

@@ -111,6 +111,7 @@ typedef struct bpt_counters {
     uint64_t extend_node_visits;     /* diagnostics, only filled by builds with -DBPT_TRAVERSAL_STATS */
     uint64_t extend_triangle_tests;
     uint64_t nonfinite_samples;      /* pixel samples whose radiance was NaN / inf: dropped from the accumulation, counted here */
+    uint64_t traversal_stack_overflows; /* pushes beyond the traversal stack: the build guarantees 0; anything else is a wrong image */
     uint64_t iterations;             /* wavefront iterations (one closest-hit + one shadow traversal launch each), counted on the device */
 } bpt_counters;
 

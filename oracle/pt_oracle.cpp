@@ -295,9 +295,10 @@ HitRecord closest_bvh(const Scene& sc, float3 o, float3 d, float tmin, float tma
     return hit;
 }
 
-// Product of (1 - coverage) over every triangle hit in (tmin, tmax); 0 as soon as it drops below 1e-7
-// (shadow_any_hit, MonteCarlo.cu:278-285).
-float transmission_bvh(const Scene& sc, float3 o, float3 d, float tmin, float tmax, bool brute) {
+// Product of (1 - coverage) over every triangle hit in (tmin, tmax). shadow_any_hit (MonteCarlo.cu:278-285) multiplies the
+// light sample's radiance by (1 - coverage) per surface and terminates the ray once every channel is below 1e-7;
+// `largest_radiance_channel` is max(r, g, b) of that radiance, so the rule here is the same up to rounding.
+float transmission_bvh(const Scene& sc, float3 o, float3 d, float tmin, float tmax, bool brute, float largest_radiance_channel = 1.0f) {
     Shear sh = make_shear(d);
     float transmission = 1.0f;
     auto visit = [&](int gp) -> bool {
@@ -308,7 +309,7 @@ float transmission_bvh(const Scene& sc, float3 o, float3 d, float tmin, float tm
         const Material& m = sc.materials[tri.material];
         float coverage = material_coverage(sc, m, interpolate_texcoord(tri, u, v));
         transmission *= 1.0f - coverage;
-        if (transmission < 0.0000001f) { transmission = 0.0f; return true; }
+        if (transmission * largest_radiance_channel < 0.0000001f) { transmission = 0.0f; return true; }
         return false;
     };
     if (brute) {
@@ -873,7 +874,8 @@ float3 trace_path(const Scene& sc, const CameraIn& cam, const SettingsIn& settin
         const LightSample& light_sample = payload.light_sample;
         if (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0) {
             counters.shadow_rays++;
-            float transmission = transmission_bvh(sc, payload.light_sample_origin, light_sample.direction_to_light, 0.0f, light_sample.distance, false);
+            float transmission = transmission_bvh(sc, payload.light_sample_origin, light_sample.direction_to_light, 0.0f, light_sample.distance, false,
+                                                  fmaxf(fmaxf(light_sample.radiance.x, light_sample.radiance.y), light_sample.radiance.z));
             payload.radiance += light_sample.radiance * transmission;
         }
         payload.light_sample = LightSample::none();

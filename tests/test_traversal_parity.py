@@ -205,3 +205,113 @@ def test_odd_frame_sizes_and_dark_scene(bpt):
     scenes.upload(bpt, dark)
     bpt.render(dark["camera"], 33, 17, 0, 2, reset=True)
     assert np.all(bpt.resolve_float4()[..., :3] == 0.0)
+
+
+# ---- the sizes that are benchmarked ("parity at the sizes you benchmark") ---------------------------------
+
+def camera_and_bounce_rays(scene, n, seed):
+    """Half camera-like rays towards the scene, half incoherent rays that start near the geometry."""
+    rng = np.random.default_rng(seed)
+    wv = None
+    o = np.empty((n, 3), np.float32); d = np.empty((n, 3), np.float32)
+    half = n // 2
+    lo, hi = scene["bounds"]
+    centre, extent = (lo + hi) / 2, (hi - lo)
+    o[:half] = (centre + np.float32([0, 1.5, -2.0]) * np.linalg.norm(extent) * 0.5).astype(np.float32)
+    target = rng.uniform(lo, hi, (half, 3))
+    d[:half] = (target - o[:half]).astype(np.float32)
+    o[half:] = rng.uniform(lo - 0.05 * extent, hi + 0.05 * extent, (n - half, 3)).astype(np.float32)
+    d[half:] = rng.normal(size=(n - half, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    return o, d.astype(np.float32)
+
+
+def scene_bounds(sc):
+    wv = sc.world_vertices().reshape(-1, 3)
+    return wv.min(axis=0).astype(np.float64), wv.max(axis=0).astype(np.float64)
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_material_grid_980k_triangles_bit_exact(bpt):
+    """configs[2]'s geometry at full size (980 002 triangles): 2^20 rays against the oracle's BVH, which
+    test_oracle_bvh_equals_brute_force proves equal to the brute-force loop."""
+    scene = scenes.material_grid()
+    scenes.upload(bpt, scene)
+    sc = oracle_lib.OracleScene(scene)
+    assert bpt.accel_info()["triangles"] == sc.triangle_count() == 980002
+    scene["bounds"] = scene_bounds(sc)
+    o, d = camera_and_bounce_rays(scene, 1 << 20, 21)
+    gp, gt, guv, gocc = bpt.intersect(o, d)
+    rp, rt, ruv, rocc = sc.intersect(o, d, brute=False)
+    assert np.array_equal(gp, rp), f"{(gp != rp).sum()} primitive ids differ"
+    hit = rp >= 0
+    assert np.array_equal(gt[hit], rt[hit]) and np.array_equal(guv[hit], ruv[hit]) and np.array_equal(gocc, rocc)
+    assert hit.mean() > 0.2
+    assert bpt.counters()["traversal_stack_overflows"] == 0
+    sc.close()
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_terrain_above_8m_triangles_bit_exact(bpt):
+    """A subset of configs[3] with more than 8 000 000 triangles, so that the large-scene traversal parameters
+    (traversal_budget_for / traversal_min_active_for in bpt_trace.cuh) are the ones that run: 2^19 rays, bit exact."""
+    scene = scenes.instanced_terrain(480, 270, (12, 7), 224, 8)  # 84 instances x 100 352 triangles = 8.43 M
+    scenes.upload(bpt, scene)
+    sc = oracle_lib.OracleScene(scene)
+    n_tris = sc.triangle_count()
+    assert bpt.accel_info()["triangles"] == n_tris and n_tris > 8_000_000
+    scene["bounds"] = scene_bounds(sc)
+    o, d = camera_and_bounce_rays(scene, 1 << 19, 22)
+    gp, gt, guv, gocc = bpt.intersect(o, d)
+    rp, rt, ruv, rocc = sc.intersect(o, d, brute=False)
+    assert np.array_equal(gp, rp), f"{(gp != rp).sum()} primitive ids differ"
+    hit = rp >= 0
+    assert np.array_equal(gt[hit], rt[hit]) and np.array_equal(guv[hit], ruv[hit]) and np.array_equal(gocc, rocc)
+    assert hit.mean() > 0.2
+    assert bpt.counters()["traversal_stack_overflows"] == 0
+    sc.close()
+
+
+def nested_slivers(count=80, growth=1.35):
+    """Triangles of geometrically growing size stacked a hair apart around one axis: every agglomerative build turns them
+    into a chain (each merge joins one more triangle to the cluster of all smaller ones), i.e. a hierarchy about as deep as
+    it has leaves. A ray down the axis meets every box, and going near to far it defers up to three siblings per level."""
+    positions, size = [], 0.01
+    for k in range(count):
+        z = 1e-4 * k
+        positions += [(-size, -size, z), (size, -size, z), (0.0, 1.5 * size, z)]
+        size *= growth
+    p = np.array(positions, np.float32)
+    return {"indices": np.arange(3 * count, dtype=np.uint32).reshape(count, 3), "positions": p}
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_deep_hierarchy_uses_the_spill_stack(bpt):
+    """Forces traversal stacks deeper than the 32 shared-memory entries (the local-memory spill part) and checks the result
+    against brute force, for closest-hit and for any-hit rays through partially covering surfaces (which never terminate
+    early and therefore walk the whole chain)."""
+    mesh = nested_slivers()
+    mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
+    mats[1]["coverage"] = 0.01
+    scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
+             "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
+    scenes.upload(bpt, scene)
+    sc = oracle_lib.OracleScene(scene)
+    rng = np.random.default_rng(31)
+    n = 20000
+    o = np.concatenate([rng.normal(scale=0.004, size=(n, 2)), np.full((n, 1), -1.0)], axis=1).astype(np.float32)
+    o[n // 2:, 2] = 1.0  # half of the rays come from the far side: the nearest triangle is the largest one
+    d = np.tile(np.float32([0, 0, 1]), (n, 1)); d[n // 2:, 2] = -1.0
+    d[:, :2] += rng.normal(scale=1e-3, size=(n, 2)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    bpt.counters(reset=True)
+    gp, gt, guv, gocc = bpt.intersect(o, d)
+    rp, rt, ruv, rocc = sc.intersect(o, d, brute=True)
+    assert np.array_equal(gp, rp) and np.array_equal(gocc, rocc)
+    hit = rp >= 0
+    assert hit.mean() > 0.9 and np.array_equal(gt[hit], rt[hit]) and np.array_equal(guv[hit], ruv[hit])
+    assert bpt.counters()["traversal_stack_overflows"] == 0
+    sc.close()
