@@ -634,8 +634,9 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     ctx->has_textured_materials = any_textured;
     ctx->material_version++;
     // Materials are read at shading time: the acceleration structure stays valid, unless the scene now needs the
-    // per-primitive texcoords that an untextured build left out.
-    if (any_textured && !ctx->accel.has_uv) ctx->accel.valid = false;
+    // per-primitive texcoords that a build made without textured materials in view left out. (A build made WITH them in view
+    // that found no mesh with texcoords has nothing to add: later material edits keep it.)
+    if (any_textured && !ctx->accel.built_for_textures) ctx->accel.valid = false;
     for (const bpt_instance& inst : ctx->instances)
         if (inst.material_id >= count) ctx->accel.valid = false; // bpt_build_accel will report the dangling material id
     return BPT_OK;

@@ -622,6 +622,7 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(A.world_vertices.resize(std::max<size_t>(3ull * n, 1)));
     BUILD_CHECK(A.shade.resize(std::max<size_t>(n, 1)));
     A.has_uv = any_texcoords && n > 0;
+    A.built_for_textures = ctx->has_textured_materials;
     if (A.has_uv) BUILD_CHECK(A.shade_uv.resize(3ull * n)); else A.shade_uv.release();
     A.has_emission = any_emission && n > 0;
     if (A.has_emission) BUILD_CHECK(A.shade_emission.resize(9ull * n)); else A.shade_emission.release();

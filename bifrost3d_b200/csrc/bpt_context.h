@@ -102,6 +102,7 @@ struct Accel {
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
     DeviceBuffer<float2> shade_uv;              // 3 texcoords per primitive, instance-major order; only when a mesh has texcoords
     bool has_uv = false;
+    bool built_for_textures = false;            // the last build saw textured materials (and kept whatever texcoords the meshes have)
     DeviceBuffer<float> shade_emission;         // 9 floats per primitive (per-vertex emission scale); only when a mesh has emission
     bool has_emission = false;
     DeviceBuffer<uint32_t> slot_of_primitive;   // global primitive index -> position in `triangles` (Morton order): the spatial

@@ -136,15 +136,17 @@ constexpr int MAX_TRIANGLES = 0x0fffffff;
 // (a struct that contains a dynamically indexed array is placed in local memory as a whole).
 struct TraversalStack {
     int* smem;                // [STACK_SMEM][TRACE_BLOCK], this thread's column
-    int* spill;               // [STACK_LOCAL]
+    int* spill;               // [STACK_LOCAL + 1]: the last slot is the "a push was dropped" flag
     int sp;
     // The build only hands out hierarchies whose depth fits (bpt_bvh.cu: 3 x wide levels + 1 <= STACK_SMEM + STACK_LOCAL, binary
     // depth <= 96, else it falls back), so the last branch is unreachable by construction; if it ever ran, the dropped subtree
     // would be a wrong image, so it is counted (bpt_counters.traversal_stack_overflows) instead of passing silently.
-    BPT_D void push(int link, unsigned long long* overflow_counter) {
+    // (The overflow is recorded in one extra slot of the spill array and counted when the ray retires: an atomic on a global
+    // counter right here cost 17 % of the closest-hit kernel - measured - although it never executes.)
+    BPT_D void push(int link) {
         if (sp < STACK_SMEM) smem[sp * TRACE_BLOCK] = link;
         else if (sp - STACK_SMEM < STACK_LOCAL) spill[sp - STACK_SMEM] = link;
-        else atomicAdd(overflow_counter, 1ull);
+        else spill[STACK_LOCAL] = 1;
         ++sp;
     }
     BPT_D int pop() {
@@ -260,7 +262,7 @@ struct Traversal {
         if (hit_l && hit_r) {
             bool left_first = tn_l <= tn_r;
             node = left_first ? links.x : links.y;
-            stack.push(left_first ? links.y : links.x, a.overflow_counter);
+            stack.push(left_first ? links.y : links.x);
         } else if (hit_l)
             node = links.x;
         else if (hit_r)
@@ -295,9 +297,9 @@ struct Traversal {
 #define BPT_CSWAP(ta, la, tb, lb) { bool s = tb < ta; float tt = s ? tb : ta; tb = s ? ta : tb; ta = tt; int ll = s ? lb : la; lb = s ? la : lb; la = ll; }
             BPT_CSWAP(t0, l0, t1, l1) BPT_CSWAP(t2, l2, t3, l3) BPT_CSWAP(t0, l0, t2, l2) BPT_CSWAP(t1, l1, t3, l3) BPT_CSWAP(t1, l1, t2, l2)
 #undef BPT_CSWAP
-            if (hits > 3) stack.push(l3, a.overflow_counter);
-            if (hits > 2) stack.push(l2, a.overflow_counter);
-            stack.push(l1, a.overflow_counter);
+            if (hits > 3) stack.push(l3);
+            if (hits > 2) stack.push(l2);
+            stack.push(l1);
             node = l0;
         } else
             node = h0 ? l0 : (h1 ? l1 : (h2 ? l2 : l3));
@@ -381,7 +383,8 @@ struct Traversal {
 template <bool ANY_HIT, class Source>
 BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
                           unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
-    int spill[STACK_LOCAL];
+    int spill[STACK_LOCAL + 1];
+    spill[STACK_LOCAL] = 0;
     Traversal<ANY_HIT> tr;
     tr.stack.smem = stack_smem;
     tr.stack.spill = spill;
@@ -394,7 +397,10 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
 
     while (true) {
         // Retire finished rays and refill idle lanes: one atomic per warp.
-        if (has_ray && tr.finished()) { source.store(index, tr); has_ray = false; }
+        if (has_ray && tr.finished()) {
+            source.store(index, tr); has_ray = false;
+            if (spill[STACK_LOCAL] != 0) { spill[STACK_LOCAL] = 0; atomicAdd(a.overflow_counter, 1ull); }
+        }
         unsigned int idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
         if (idle) {
             int leader = __ffs(idle) - 1;

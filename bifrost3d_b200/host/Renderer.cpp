@@ -183,16 +183,31 @@ struct Renderer::Implementation {
     // Images and textures, Renderer.cpp:650-751: every 2D texture becomes a texture object keyed by its TextureID.
     // Returns true when something changed.
     std::map<unsigned int, bool> uploaded_textures;
+    // Images and textures, Renderer.cpp:650-751. A texture travels when it is created, and again when the pixels of its image
+    // change (Images::Change::PixelsUpdated, :657-669); destroyed textures are collected here and released on the device once
+    // the materials that referenced them have been re-uploaded (release_destroyed_textures).
+    std::map<unsigned int, int> uploaded_texture_channels; // channel count of the device texture by TextureID index
+    std::vector<unsigned int> destroyed_textures;
     bool upload_textures() {
         bool changed = false;
+        for (TextureID texture_ID : Textures::get_changed_textures())
+            if (Textures::get_changes(texture_ID).contains(Textures::Change::Destroyed) && uploaded_textures[texture_ID]) {
+                uploaded_textures[texture_ID] = false;
+                uploaded_texture_channels.erase(texture_ID.get_index());
+                destroyed_textures.push_back(texture_ID.get_index());
+                changed = true; // materials are re-uploaded without it
+            }
         for (TextureID texture_ID : Textures::get_iterable()) {
-            if (uploaded_textures[texture_ID] && !Textures::get_changes(texture_ID).contains(Textures::Change::Created)) continue;
             Image image = Textures::get_image_ID(texture_ID);
+            bool created = Textures::get_changes(texture_ID).contains(Textures::Change::Created);
+            bool pixels_updated = image.exists() && Images::get_changes(image.get_ID()).contains(Images::Change::PixelsUpdated);
+            if (uploaded_textures[texture_ID] && !created && !pixels_updated) continue;
             if (!image.exists() || image.get_depth() > 1) continue;
             bpt_texture_desc desc = {};
             desc.width = int(image.get_width()); desc.height = int(image.get_height());
+            int channels = 4;
             switch (image.get_pixel_format()) {
-            case PixelFormat::Alpha8: desc.pixel_format = BPT_PIXEL_ALPHA8; break;
+            case PixelFormat::Alpha8: desc.pixel_format = BPT_PIXEL_ALPHA8; channels = 1; break;
             case PixelFormat::RGB24: desc.pixel_format = BPT_PIXEL_RGB24; break;
             case PixelFormat::RGBA32: desc.pixel_format = BPT_PIXEL_RGBA32; break;
             case PixelFormat::RGB_Float: desc.pixel_format = BPT_PIXEL_RGB_FLOAT; break;
@@ -209,16 +224,33 @@ struct Renderer::Implementation {
             int status = bpt_upload_texture(ctx, int(texture_ID.get_index()), &desc, image.get_pixels());
             check(ctx, status, "bpt_upload_texture");
             uploaded_textures[texture_ID] = status == BPT_OK;
+            if (status == BPT_OK) uploaded_texture_channels[texture_ID.get_index()] = channels;
             changed = true;
         }
         return changed;
     }
 
+    // After the materials were re-uploaded no device material references a destroyed texture any more.
+    void release_destroyed_textures() {
+        for (unsigned int texture_index : destroyed_textures)
+            check(ctx, bpt_destroy_texture(ctx, int(texture_index)), "bpt_destroy_texture");
+        destroyed_textures.clear();
+    }
+
     // A material's texture id if the texture made it to the device, else 0 (untextured).
-    int device_texture_id(TextureID texture_ID) {
+    // `required_channels`: the tint / roughness texture is sampled as RGBA, the roughness, metallic and coverage textures as
+    // one channel (Types.h:388-414). A texture of the wrong kind is dropped from THIS material with a warning instead of
+    // making bpt_set_materials refuse the whole array.
+    int device_texture_id(TextureID texture_ID, int required_channels, const char* what, const std::string& material_name) {
         if (texture_ID == TextureID::invalid_UID()) return 0;
         auto it = uploaded_textures.find(texture_ID);
-        return (it != uploaded_textures.end() && it->second) ? int(texture_ID.get_index()) : 0;
+        if (it == uploaded_textures.end() || !it->second) return 0;
+        if (uploaded_texture_channels[texture_ID.get_index()] != required_channels) {
+            printf("OptiXRenderer(B200) warning: the %s texture of material '%s' has %d channel(s), %d needed; rendering the material without it.\n",
+                   what, material_name.c_str(), uploaded_texture_channels[texture_ID.get_index()], required_channels);
+            return 0;
+        }
+        return int(texture_ID.get_index());
     }
 
     // load_mesh, Renderer.cpp:92-136 / mesh updates :621-648: a mesh is uploaded once and stays on the device; only created
@@ -290,12 +322,13 @@ struct Renderer::Implementation {
             RGB emission = host.get_emission();
             d.emission[0] = emission.r; d.emission[1] = emission.g; d.emission[2] = emission.b;
             // Renderer.cpp:760-806: one texture carries tint (rgb) and roughness (a), or roughness alone.
+            const std::string name = host.get_name();
             if (host.has_tint_texture())
-                d.tint_roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID());
+                d.tint_roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID(), 4, "tint / roughness", name);
             else if (host.has_roughness_texture())
-                d.roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID());
-            d.metallic_texture_id = device_texture_id(host.get_metallic_texture_ID());
-            d.coverage_texture_id = device_texture_id(host.get_coverage_texture_ID());
+                d.roughness_texture_id = device_texture_id(host.get_tint_roughness_texture_ID(), 1, "roughness", name);
+            d.metallic_texture_id = device_texture_id(host.get_metallic_texture_ID(), 1, "metallic", name);
+            d.coverage_texture_id = device_texture_id(host.get_coverage_texture_ID(), 1, "coverage", name);
         }
         check(ctx, bpt_set_materials(ctx, materials.data(), int(materials.size())), "bpt_set_materials");
     }
@@ -414,6 +447,7 @@ struct Renderer::Implementation {
         bool meshes_changed = upload_meshes();
         bool materials_changed = !scene_uploaded || textures_changed || !Materials::get_changed_materials().is_empty();
         if (materials_changed) upload_materials();
+        release_destroyed_textures();
         bool instances_changed = !scene_uploaded || meshes_changed || !Meshes::get_changed_meshes().is_empty();
         instances_changed |= !MeshModels::get_changed_models().is_empty();
         for (SceneNodeID node_ID : SceneNodes::get_changed_nodes())

@@ -165,3 +165,18 @@ def test_first_textured_material_asks_for_a_rebuild(bpt):
     fresh.render(scene["camera"], 48, 48, 0, 2, reset=True)
     assert np.array_equal(edited, fresh.resolve_float4())
     fresh.close()
+
+
+@pytest.mark.gpu
+def test_material_edits_keep_an_acceleration_structure_built_without_texcoords(bpt):
+    """Textured materials over meshes that carry no texcoords: the build has nothing to add for them, so a later material
+    edit must not invalidate the acceleration structure (it did before round 2: every edit forced a full rebuild)."""
+    scene = textured_cornell()
+    scene["meshes"] = {k: {name: value for name, value in m.items() if name != "texcoords"} for k, m in scene["meshes"].items()}
+    scenes.upload(bpt, scene)
+    bpt.render(scene["camera"], 32, 32, 0, 1, reset=True)
+    mats = scene["materials"].copy()
+    mats["roughness"] = np.clip(mats["roughness"] * 0.5, 0, 1)
+    bpt.set_materials(mats)
+    bpt.render(scene["camera"], 32, 32, 0, 1, reset=True)  # no bpt_build_accel in between
+    assert np.isfinite(bpt.resolve_float4()).all()
