@@ -69,7 +69,7 @@ EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_set_hit_sorting", "bpt_build_accel", "bpt_accel_info", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
-           "bpt_intersect", "bpt_sort_pairs", "bpt_exclusive_scan"]
+           "bpt_intersect", "bpt_sort_pairs", "bpt_exclusive_scan", "bpt_compare_images"]
 
 
 class TonemapSettings(C.Structure):
@@ -147,6 +147,7 @@ def load_library():
     lib.bpt_comm_init.argtypes = [vp, vp, i32, i32]
     lib.bpt_comm_destroy.argtypes = [vp]
     lib.bpt_reduce_accumulation.argtypes = [vp, i32]
+    lib.bpt_compare_images.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.bpt_sort_pairs.argtypes = [vp, i64, vp, vp, i32, i32]
     lib.bpt_exclusive_scan.argtypes = [vp, i64, vp, vp, vp]
     lib.bpt_select_accumulation.argtypes = [vp, i32]
@@ -455,6 +456,28 @@ class Bpt:
         self._check(self.lib.bpt_light_sample_pdf_evaluate(self.h, n, _ptr(l), stride, _ptr(position), _ptr(u2), _ptr(query_direction),
                                                            _ptr(samples), _ptr(pdf), _ptr(rad)))
         return samples, pdf, rad
+
+    def compare_images(self, reference, target, mssim_support=0, diff_images=False):
+        """ImageOperations::Compare rms / ssim / mssim (mssim only with a support > 0) of two (H, W, 3 or 4) float images."""
+        def rgba(image):
+            image = np.asarray(image, np.float32)
+            if image.shape[-1] == 3:
+                image = np.concatenate([image, np.ones(image.shape[:-1] + (1,), np.float32)], axis=-1)
+            return np.ascontiguousarray(image)
+        a, b = rgba(reference), rgba(target)
+        assert a.shape == b.shape and a.ndim == 3
+        h, w = a.shape[:2]
+        rms, ssim, mssim = C.c_float(), C.c_float(), C.c_float()
+        rms_diff = np.empty_like(a) if diff_images else None
+        mssim_diff = np.empty_like(a) if diff_images and mssim_support > 0 else None
+        self._check(self.lib.bpt_compare_images(self.h, w, h, _ptr(a), _ptr(b), int(mssim_support), C.byref(rms), C.byref(ssim),
+                                                C.byref(mssim) if mssim_support > 0 else None, _ptr(rms_diff), _ptr(mssim_diff)))
+        out = {"rms": rms.value, "ssim": ssim.value}
+        if mssim_support > 0:
+            out["mssim"] = mssim.value
+        if diff_images:
+            out["rms_diff"] = rms_diff; out["mssim_diff"] = mssim_diff
+        return out
 
     def sort_pairs(self, keys, values, begin_bit=0, end_bit=64):
         """Stable radix sort of (uint64 key, uint32 value) pairs by key bits [begin_bit, end_bit): the sort of the BVH build."""

@@ -448,6 +448,9 @@ __device__ LightSample sample_single_light(const SceneView& s, const Bsdf& mater
 #ifndef BPT_SHADE_MIN_BLOCKS
 #define BPT_SHADE_MIN_BLOCKS 8
 #endif
+#ifndef BPT_SHADE_SYNC
+#define BPT_SHADE_SYNC 0
+#endif
 // SURFACE, !TRANSMISSIVE: default_closest_hit / diffuse_closest_hit (MonteCarlo.cu:246-257); SURFACE, TRANSMISSIVE:
 // transmissive_closest_hit (:259-268), launched only for scenes that hold such materials; !SURFACE: miss and light hits.
 template <bool SURFACE, bool TRANSMISSIVE>
@@ -465,8 +468,17 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count)
                                                                      : (sorting_now(w.counters, f.sort_hits_from_iteration) ? w.queue_surface_sorted : w.queue_surface))
                                                      : w.queue_escaped;
+#if BPT_SHADE_SYNC
+    // whole CTAs take part in every iteration and start it together: the warps of a CTA then walk the kernel's ~100 KB of
+    // straight-line code side by side and share its instruction fetches
+    const unsigned int rounded = ((count + SHADE_BLOCK - 1u) / SHADE_BLOCK) * SHADE_BLOCK;
+#else
     const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
+#endif
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
+#if BPT_SHADE_SYNC
+        __syncthreads();
+#endif
         bool valid = i < count;
         bool continue_path = false, cast_shadow = false;
         unsigned int pixel = 0;

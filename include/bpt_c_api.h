@@ -281,6 +281,13 @@ typedef struct bpt_tonemap_settings {
 int bpt_resolve_tonemapped(bpt_ctx* ctx, const bpt_tonemap_settings* settings, void* out, int output_format);
 /* the operator alone for n colours (rgb_in, rgb_out: 3n floats): unit entry point for the parity test */
 int bpt_tonemap_colors(bpt_ctx* ctx, const bpt_tonemap_settings* settings, int64_t n, const float* rgb_in, float* rgb_out);
+/* Image comparison, extensions/ImageOperations/ImageOperations/Compare.h: rms (:23-44: root mean square of the luminance of the
+ * per channel absolute difference), ssim (:88-118: structural similarity of the whole images, luminance of the per channel
+ * index) and mssim (:123-180: mean of the SSIM of the weighted window [p - support, p + support) around every pixel).
+ * reference_rgba / target_rgba: width*height float4 on the HOST. Nullable outputs are skipped; out_rms_diff_rgba receives the
+ * per channel absolute difference (the `diff` image of rms), out_mssim_diff_rgba 1 - SSIM per channel (the one of mssim). */
+int bpt_compare_images(bpt_ctx* ctx, int width, int height, const float* reference_rgba, const float* target_rgba, int mssim_support,
+                       float* out_rms, float* out_ssim, float* out_mssim, float* out_rms_diff_rgba, float* out_mssim_diff_rgba);
 int bpt_synchronize(bpt_ctx* ctx);
 /* enabled != 0: bpt_render brackets its stage kernels with CUDA events on the context's stream and accumulates their
  * durations into bpt_counters.{extend,shade,shadow}_ms (used by bench.py for the roofline figures). */

@@ -45,6 +45,7 @@
 #include <Bifrost/Math/CameraEffects.h>
 #include <Bifrost/Math/OctahedralNormal.h>
 #include <Bifrost/Math/RNG.h>
+#include <ImageOperations/Compare.h>
 
 #include <omp.h>
 #include <cstdint>
@@ -79,6 +80,12 @@ inline Material make_material(const float* tint, const float* rms, const float* 
 }
 
 } // namespace
+
+// The core's image / texture managers are process-wide singletons: allocated once, shared by every entry point below.
+static void ensure_image_managers() {
+    static bool allocated = false;
+    if (!allocated) { Bifrost::Assets::Images::allocate(8u); Bifrost::Assets::Textures::allocate(4u); allocated = true; }
+}
 
 extern "C" {
 
@@ -338,8 +345,7 @@ int ref_environment_build(const float* texels, int width, int height, int reques
                           int* pdf_width, int* pdf_height, float* per_pixel_pdf, float* out_samples /*8 floats each*/, float* image_integral) {
     using namespace Bifrost;
     using namespace Bifrost::Assets;
-    static bool allocated = false;
-    if (!allocated) { Images::allocate(4u); Textures::allocate(4u); allocated = true; }
+    ensure_image_managers();
     Image image = Image::create2D("environment", PixelFormat::RGBA_Float, false, Math::Vector2ui(width, height));
     memcpy(image.get_pixels(), texels, sizeof(float) * 4 * size_t(width) * height);
     // Latlong sampler as SimpleViewer creates it: linear filtering, repeat in u, clamp in v.
@@ -385,8 +391,7 @@ int ref_environment_sample(const float* texels, int width, int height, int64_t n
                            float* out_pdf_of_direction /*n*/, float* marginal_cdf, float* conditional_cdf) {
     using namespace Bifrost;
     using namespace Bifrost::Assets;
-    static bool allocated = false;
-    if (!allocated) { Images::allocate(4u); Textures::allocate(4u); allocated = true; }
+    ensure_image_managers();
     Image image = Image::create2D("environment", PixelFormat::RGBA_Float, false, Math::Vector2ui(width, height));
     memcpy(image.get_pixels(), texels, sizeof(float) * 4 * size_t(width) * height);
     Texture latlong = Textures::create2D(image.get_ID(), MagnificationFilter::Linear, MinificationFilter::Linear, WrapMode::Repeat, WrapMode::Clamp);
@@ -406,6 +411,28 @@ int ref_environment_sample(const float* texels, int width, int height, int64_t n
     }
     Textures::destroy(latlong.get_ID());
     Images::destroy(image.get_ID());
+    return 0;
+}
+
+// The reference's own image comparison (extensions/ImageOperations/ImageOperations/Compare.h) on two RGBA float images.
+int ref_compare_images(int width, int height, const float* reference_rgba, const float* target_rgba, int mssim_support,
+                       float* out_rms, float* out_ssim, float* out_mssim, float* out_rms_diff /*nullable*/, float* out_mssim_diff /*nullable*/) {
+    using namespace Bifrost;
+    using namespace Bifrost::Assets;
+    ensure_image_managers();
+    auto make = [&](const char* name, const float* pixels) {
+        Image image = Image::create2D(name, PixelFormat::RGBA_Float, false, Math::Vector2ui(width, height));
+        if (pixels) memcpy(image.get_pixels(), pixels, sizeof(float) * 4 * size_t(width) * height);
+        return image;
+    };
+    Image reference = make("reference", reference_rgba), target = make("target", target_rgba);
+    Image rms_diff = out_rms_diff ? make("rms diff", nullptr) : Image(), mssim_diff = out_mssim_diff ? make("mssim diff", nullptr) : Image();
+    if (out_rms) *out_rms = ImageOperations::Compare::rms(reference, target, rms_diff);
+    if (out_ssim) *out_ssim = ImageOperations::Compare::ssim(reference, target);
+    if (out_mssim && mssim_support > 0) *out_mssim = ImageOperations::Compare::mssim(reference, target, mssim_support, mssim_diff);
+    if (out_rms_diff) memcpy(out_rms_diff, rms_diff.get_pixels(), sizeof(float) * 4 * size_t(width) * height);
+    if (out_mssim_diff) memcpy(out_mssim_diff, mssim_diff.get_pixels(), sizeof(float) * 4 * size_t(width) * height);
+    for (Image image : { reference, target, rms_diff, mssim_diff }) if (image.exists()) Images::destroy(image.get_ID());
     return 0;
 }
 

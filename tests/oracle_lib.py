@@ -267,3 +267,20 @@ def reference_environment_sample(texels, points):
     marginal = np.zeros(h + 1, np.float32); conditional = np.zeros((h, w + 1), np.float32)
     lib.ref_environment_sample(_p(tex), w, h, n, _p(pts), _p(samples), _p(pdf), _p(marginal), _p(conditional))
     return {"samples": samples, "pdf_of_direction": pdf, "marginal_cdf": marginal, "conditional_cdf": conditional}
+
+
+def reference_compare_images(reference, target, mssim_support, diff_images=False):
+    """ImageOperations::Compare::{rms, ssim, mssim} of the reference (oracle/ref_api.cpp: ref_compare_images) on (H, W, 4) floats."""
+    lib = load().lib
+    lib.ref_compare_images.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
+    lib.ref_compare_images.restype = C.c_int
+    a, b = _f32(reference), _f32(target)
+    h, w = a.shape[:2]
+    rms, ssim, mssim = C.c_float(), C.c_float(), C.c_float()
+    rms_diff = np.zeros_like(a) if diff_images else None
+    mssim_diff = np.zeros_like(a) if diff_images else None
+    lib.ref_compare_images(w, h, _p(a), _p(b), int(mssim_support), C.byref(rms), C.byref(ssim), C.byref(mssim), _p(rms_diff), _p(mssim_diff))
+    out = {"rms": rms.value, "ssim": ssim.value, "mssim": mssim.value}
+    if diff_images:
+        out["rms_diff"] = rms_diff; out["mssim_diff"] = mssim_diff
+    return out
