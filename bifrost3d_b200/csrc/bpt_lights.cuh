@@ -31,6 +31,7 @@ BPT_D LightSample light_sample_none() {
 // Orthonormal basis (Duff et al.), Utils.h:347-356.
 struct Tbn {
     float3 tangent, bitangent, normal;
+    BPT_D Tbn() {}
     BPT_D explicit Tbn(float3 n) : normal(n) {
         float sign = copysignf(1.0f, n.z);
         const float a = fdiv(-1.0f, sign + n.z);

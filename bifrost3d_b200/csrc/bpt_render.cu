@@ -21,6 +21,7 @@
 
 #include <cuda_fp16.h>
 #include <algorithm>
+#include <type_traits>
 #include <stdlib.h>
 #include <string.h>
 
@@ -33,7 +34,7 @@ namespace bpt {
 namespace {
 
 #ifndef BPT_SHADE_BLOCK
-#define BPT_SHADE_BLOCK 128
+#define BPT_SHADE_BLOCK 512
 #endif
 constexpr int SHADE_BLOCK = BPT_SHADE_BLOCK; // threads per CTA of the shade kernels (with BPT_SHADE_MIN_BLOCKS CTAs per SM)
 constexpr int LIGHT_HIT_FLAG = 0x40000000; // hit.primitive = LIGHT_HIT_FLAG | light index
@@ -446,10 +447,20 @@ __device__ LightSample sample_single_light(const SceneView& s, const Bsdf& mater
 }
 
 #ifndef BPT_SHADE_MIN_BLOCKS
-#define BPT_SHADE_MIN_BLOCKS 8
+#define BPT_SHADE_MIN_BLOCKS 2
 #endif
 #ifndef BPT_SHADE_SYNC
-#define BPT_SHADE_SYNC 0
+#define BPT_SHADE_SYNC 2 // 0: no barriers; 1: one at the top of every path; 2: also between the phases of the surface shading
+#endif
+#if BPT_SHADE_SYNC >= 1
+#define SHADE_TOP_BARRIER() __syncthreads()
+#else
+#define SHADE_TOP_BARRIER() do { } while (0)
+#endif
+#if BPT_SHADE_SYNC >= 2
+#define SHADE_PHASE_BARRIER() __syncthreads()
+#else
+#define SHADE_PHASE_BARRIER() do { } while (0)
 #endif
 // SURFACE, !TRANSMISSIVE: default_closest_hit / diffuse_closest_hit (MonteCarlo.cu:246-257); SURFACE, TRANSMISSIVE:
 // transmissive_closest_hit (:259-268), launched only for scenes that hold such materials; !SURFACE: miss and light hits.
@@ -468,40 +479,44 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
     const unsigned int* __restrict__ queue = SURFACE ? (TRANSMISSIVE ? w.queue_surface + (w.queue_capacity - count)
                                                                      : (sorting_now(w.counters, f.sort_hits_from_iteration) ? w.queue_surface_sorted : w.queue_surface))
                                                      : w.queue_escaped;
-#if BPT_SHADE_SYNC
-    // whole CTAs take part in every iteration and start it together: the warps of a CTA then walk the kernel's ~100 KB of
-    // straight-line code side by side and share its instruction fetches
+    // whole CTAs take part in every iteration (the barriers below), whole warps in the ballots of the queue compaction
     const unsigned int rounded = ((count + SHADE_BLOCK - 1u) / SHADE_BLOCK) * SHADE_BLOCK;
-#else
-    const unsigned int rounded = (count + 31u) & ~31u; // whole warps take part in the ballots
-#endif
+    // The surface shading of one path is ~4 500 executed instructions of straight-line code out of a ~100 KB kernel: every warp
+    // streams the whole kernel through the instruction caches once per path, and with the warps of an SM at unrelated places
+    // the top stall reason is instruction fetch (ncu round 2: no_instruction 5.7 warps per issue, 50 % of the issue slots).
+    // So the warps of a CTA are kept side by side: a CTA-wide barrier at the top of every path and between the phases of the
+    // shading (set-up | each next-event candidate | BSDF sampling) lets one fetched line serve all of them. Measured on B200:
+    // barrier at the top only, 512-thread CTAs: shade -7 % (1 M triangle scene) / -17 % (Cornell box); see DESIGN.md 6 for the
+    // phase barriers. The arithmetic and its order per path are untouched.
     for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < rounded; i += gridDim.x * blockDim.x) {
-#if BPT_SHADE_SYNC
-        __syncthreads();
-#endif
-        bool valid = i < count;
+        SHADE_TOP_BARRIER();
+        // Barriers must be reached by every thread of the CTA, and hoisting the shading state out of a conditional costs
+        // registers (measured: +6 % on the kernel). So the shading below is unconditional straight-line code: a thread past
+        // the end of the queue shades the queue's last path once more, a thread whose hit is rejected (back face, coverage)
+        // shades it anyway, and both drop the result. Lanes that would otherwise sit masked do the work, so it costs nothing
+        // unless a whole warp is rejected.
+        const bool valid = i < count;
         bool continue_path = false, cast_shadow = false;
-        unsigned int pixel = 0;
+        const unsigned int pixel = queue[valid ? i : count - 1u];
         float4 shadow_o = make_float4(0, 0, 0, 0), shadow_d = make_float4(0, 0, 0, 0), shadow_rad = make_float4(0, 0, 0, 0);
 
-        if (valid) {
-            pixel = queue[i];
-            const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
-            float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
-            const float4 hit4 = w.hit[pixel];
-            const float3 ray_origin = f3(ro), ray_direction = f3(rd);
-            Pdf bsdf_pdf(rd.w);
-            float3 throughput = f3(thr4), radiance = f3(rad4);
-            unsigned int bounces = __float_as_uint(thr4.w);
-            int previous_primitive = __float_as_int(rad4.w);
-            const float t_hit = hit4.x;
-            const int primitive = __float_as_int(hit4.y);
-            const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
+        const float4 ro = w.ray_o[pixel], rd = w.ray_d[pixel];
+        float4 thr4 = w.thr[pixel], rad4 = w.rad[pixel];
+        const float4 hit4 = w.hit[pixel];
+        const float3 ray_origin = f3(ro), ray_direction = f3(rd);
+        Pdf bsdf_pdf(rd.w);
+        float3 throughput = f3(thr4), radiance = f3(rad4);
+        unsigned int bounces = __float_as_uint(thr4.w);
+        int previous_primitive = __float_as_int(rad4.w);
+        const float t_hit = hit4.x;
+        const int primitive = __float_as_int(hit4.y);
+        const unsigned int pixel_hash = pcg2d(pixel % (unsigned int)f.width, pixel / (unsigned int)f.width).x;
 
-            float3 next_origin = ray_origin, next_direction = ray_direction;
-            float next_tmin = ro.w;
+        float3 next_origin = ray_origin, next_direction = ray_direction;
+        float next_tmin = ro.w;
 
-            if (!SURFACE && primitive < 0) {
+        if constexpr (!SURFACE) {
+            if (primitive < 0) {
                 // miss, SimpleRGPs.cu:349-362
                 float3 environment_radiance = s.env.tint;
                 if (s.env.texels != nullptr) {
@@ -511,7 +526,7 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 }
                 radiance += throughput * environment_radiance;
                 throughput = f3(0.0f);
-            } else if (!SURFACE) {
+            } else {
                 // light_closest_hit, MonteCarlo.cu:291-302; evaluate_intersection, LightImpl.h:86-108
                 Light light = s.lights[primitive & ~LIGHT_HIT_FLAG];
                 float3 light_radiance = light_evaluate(light, s.env, ray_origin, ray_direction);
@@ -520,151 +535,157 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
                 throughput = min3(throughput, f3(4.0f));
                 radiance += throughput * light_radiance;
                 throughput = f3(0.0f);
-            } else if (SURFACE) {
-                // interpolate_attributes, TriangleAttributes.cu:35-84 (geometry is pre-transformed to world space)
-                const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
-                             p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
-                const int4* shade_raw = reinterpret_cast<const int4*>(s.shade + primitive);
-                int4 sr0 = __ldg(shade_raw), sr1 = __ldg(shade_raw + 1);
-                ShadeTriangle st;
-                memcpy(&st, &sr0, 16); memcpy(reinterpret_cast<char*>(&st) + 16, &sr1, 16);
+            }
+        } else {
+            // ---- phase 0: hit attributes, reject rules, frame and material set-up ----
+            // interpolate_attributes, TriangleAttributes.cu:35-84 (geometry is pre-transformed to world space)
+            const float3 p0 = f3(__ldg(s.world_vertices + 3ll * primitive)), p1 = f3(__ldg(s.world_vertices + 3ll * primitive + 1)),
+                         p2 = f3(__ldg(s.world_vertices + 3ll * primitive + 2));
+            const int4* shade_raw = reinterpret_cast<const int4*>(s.shade + primitive);
+            int4 sr0 = __ldg(shade_raw), sr1 = __ldg(shade_raw + 1);
+            ShadeTriangle st;
+            memcpy(&st, &sr0, 16); memcpy(reinterpret_cast<char*>(&st) + 16, &sr1, 16);
 
-                float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
-                const float bx = hit4.z, by = hit4.w;
-                const float bz = 1.0f - bx - by;
-                const float3 intersection_point = p1 * bx + p2 * by + p0 * bz;
-                const bool has_normals = st.flags & 1u, has_tints = st.flags & 2u;
-                float3 shading_normal;
-                if (has_normals) {
-                    shading_normal = oct_decode(st.n1) * bx + oct_decode(st.n2) * by + oct_decode(st.n0) * bz;
-                    shading_normal = normalize(shading_normal);
-                } else
-                    shading_normal = geometric_normal;
-                float4 tint_and_roughness_scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-                if (has_tints) {
-                    const float n255 = 1.0f / 255.0f;
-                    tint_and_roughness_scale.x = (st.t1[0] * bx + st.t2[0] * by + st.t0[0] * bz) * n255;
-                    tint_and_roughness_scale.y = (st.t1[1] * bx + st.t2[1] * by + st.t0[1] * bz) * n255;
-                    tint_and_roughness_scale.z = (st.t1[2] * bx + st.t2[2] * by + st.t0[2] * bz) * n255;
-                    tint_and_roughness_scale.w = (st.t1[3] * bx + st.t2[3] * by + st.t0[3] * bz) * n255;
-                }
-
-                // path_tracing_closest_hit, MonteCarlo.cu:129-233. The same-primitive test (:137-142) already
-                // happened inside the traversal, which skips `previous_primitive`.
-                const float2 texcoord = interpolate_texcoord(s.accel.textures, primitive, bx, by);
-                const Material material_parameter = material_at(s.materials[st.material_index], s.accel.textures, texcoord);
-                float3 world_geometric_normal = geometric_normal;
-                bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
-                bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
-                backside_cull &= !material_is_transmissive(material_parameter);
-
-                float4 bsdf_coverage_random = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_BSDF);
-                float coverage_cutoff = bsdf_coverage_random.w;
-                float3 bsdf_random_uvs = f3(bsdf_coverage_random);
-                float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
-                bool discard_from_coverage = coverage < coverage_cutoff;
-
-                if (backside_cull || discard_from_coverage) {
-                    next_tmin = nextafterf(t_hit, INFINITY); // same ray, advanced past this surface
-                } else {
-                    previous_primitive = primitive;
-                    world_geometric_normal = hit_from_front ? world_geometric_normal : -world_geometric_normal;
-                    float3 world_shading_normal = shading_normal;
-                    if (has_normals) {
-                        const float* nm = s.normal_matrices + 9 * (st.flags >> 2);
-                        world_shading_normal = normalize(f3(nm[0] * shading_normal.x + nm[1] * shading_normal.y + nm[2] * shading_normal.z,
-                                                            nm[3] * shading_normal.x + nm[4] * shading_normal.y + nm[5] * shading_normal.z,
-                                                            nm[6] * shading_normal.x + nm[7] * shading_normal.y + nm[8] * shading_normal.z));
-                    }
-                    world_shading_normal = hit_from_front ? world_shading_normal : -world_shading_normal;
-                    world_shading_normal = fix_backfacing_shading_normal(-ray_direction, world_shading_normal, 0.002f);
-                    const Tbn tbn(world_shading_normal);
-
-                    const float3 world_intersection_point = intersection_point;
-                    const float3 wo = tbn.to_local(-ray_direction);
-                    float cos_theta = hit_from_front || material_is_thin_walled(material_parameter) ? wo.z : -wo.z;
-
-                    // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
-                    // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
-                    Pdf max_pdf_hint(bsdf_pdf.v * path_regularization_pdf_scale);
-                    const auto material = [&]() {
-                        if constexpr (TRANSMISSIVE)
-                            return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
-                                                                           cos_theta, max_pdf_hint);
-                        else
-                            return material_parameter.shading_model == SHADING_DIFFUSE
-                                ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
-                                : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
-                    }();
-
-                    float3 emission = f3(1.0f); // multiplicative identity, TriangleAttributes.cu:83
-                    if (s.shade_emission != nullptr) { // per-vertex emission scale, TriangleAttributes.cu:78-81
-                        const float* e = s.shade_emission + 9ll * primitive;
-                        emission = f3(e[3], e[4], e[5]) * bx + f3(e[6], e[7], e[8]) * by + f3(e[0], e[1], e[2]) * bz;
-                    }
-                    radiance += throughput * emission * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
-
-                    // reestimated_light_samples, MonteCarlo.cu:91-123
-                    LightSample light_sample = light_sample_none();
-                    if (s.light_count != 0) {
-                        float4 light_random_base = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_NEE);
-                        for (int k = 0; k < f.next_event_sample_count; ++k) {
-                            float4 shift = __ldg(s.nee_offsets + k);
-                            float4 r = light_random_base + shift; // toroidal_shift, Utils.h:46-49
-                            r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
-                            LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
-                            float light_weight = sum(light_sample.radiance);
-                            float new_light_weight = sum(candidate.radiance);
-                            float new_light_probability = fdiv(new_light_weight, light_weight + new_light_weight);
-                            if (r.w < new_light_probability) {
-                                light_sample = candidate;
-                                light_sample.radiance /= new_light_probability;
-                            } else
-                                light_sample.radiance /= 1.0f - new_light_probability;
-                        }
-                        light_sample.radiance /= float(f.next_event_sample_count);
-                    }
-                    float3 light_sample_origin = offset_ray_origin(world_intersection_point, light_sample.direction_to_light, world_geometric_normal);
-                    light_sample.radiance *= throughput;
-
-                    // BSDF sampling
-                    BsdfSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
-                    bool is_reflection = bsdf_sample.direction.z >= 0;
-                    next_direction = tbn.to_world(bsdf_sample.direction);
-                    bsdf_pdf = bsdf_sample.pdf;
-                    if (bsdf_sample.pdf.is_valid())
-                        throughput *= bsdf_sample.reflectance * fabsf(bsdf_sample.direction.z) / bsdf_sample.pdf.value();
-                    else
-                        throughput = f3(0.0f);
-
-                    float cos_geometric_theta_i = dot(next_direction, world_geometric_normal);
-                    if (is_reflection ? cos_geometric_theta_i < 0.0f : cos_geometric_theta_i >= 0.0f)
-                        next_direction = reflect(next_direction, world_geometric_normal);
-
-                    next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
-                    next_tmin = 0.0f;
-                    // Russian roulette, opt-in (bpt_settings.russian_roulette_start_bounce): survival probability =
-                    // the largest throughput component, decided by the otherwise unused RNG dimension 3 of this bounce.
-                    if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
-                        float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
-                        float u = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
-                        if (u < survival) throughput = throughput / survival;
-                        else throughput = f3(0.0f);
-                    }
-                    bounces += 1u;
-                    if (!light_sample.pdf.is_valid())
-                        bsdf_pdf.disable_MIS();
-
-                    // path_trace_single_bounce, SimpleRGPs.cu:117-125
-                    if (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0) {
-                        cast_shadow = true;
-                        shadow_o = f4(light_sample_origin, light_sample.distance);
-                        shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
-                        shadow_rad = f4(light_sample.radiance, fmaxf(fmaxf(light_sample.radiance.x, light_sample.radiance.y), light_sample.radiance.z));
-                    }
-                }
+            float3 geometric_normal = normalize(cross(p1 - p0, p2 - p0));
+            const float bx = hit4.z, by = hit4.w;
+            const float bz = 1.0f - bx - by;
+            const float3 intersection_point = p1 * bx + p2 * by + p0 * bz;
+            const bool has_normals = st.flags & 1u, has_tints = st.flags & 2u;
+            float3 shading_normal;
+            if (has_normals) {
+                shading_normal = oct_decode(st.n1) * bx + oct_decode(st.n2) * by + oct_decode(st.n0) * bz;
+                shading_normal = normalize(shading_normal);
+            } else
+                shading_normal = geometric_normal;
+            float4 tint_and_roughness_scale = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+            if (has_tints) {
+                const float n255 = 1.0f / 255.0f;
+                tint_and_roughness_scale.x = (st.t1[0] * bx + st.t2[0] * by + st.t0[0] * bz) * n255;
+                tint_and_roughness_scale.y = (st.t1[1] * bx + st.t2[1] * by + st.t0[1] * bz) * n255;
+                tint_and_roughness_scale.z = (st.t1[2] * bx + st.t2[2] * by + st.t0[2] * bz) * n255;
+                tint_and_roughness_scale.w = (st.t1[3] * bx + st.t2[3] * by + st.t0[3] * bz) * n255;
             }
 
+            // path_tracing_closest_hit, MonteCarlo.cu:129-233. The same-primitive test (:137-142) already
+            // happened inside the traversal, which skips `previous_primitive`.
+            const float2 texcoord = interpolate_texcoord(s.accel.textures, primitive, bx, by);
+            const Material material_parameter = material_at(s.materials[st.material_index], s.accel.textures, texcoord);
+            float3 world_geometric_normal = geometric_normal;
+            bool hit_from_front = dot(world_geometric_normal, ray_direction) < 0.0f;
+            bool backside_cull = !hit_from_front && !material_is_thin_walled(material_parameter);
+            backside_cull &= !material_is_transmissive(material_parameter);
+
+            float4 bsdf_coverage_random = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_BSDF);
+            float coverage_cutoff = bsdf_coverage_random.w;
+            float3 bsdf_random_uvs = f3(bsdf_coverage_random);
+            float coverage = material_coverage(material_parameter, s.accel.textures, texcoord);
+            bool discard_from_coverage = coverage < coverage_cutoff;
+            const bool rejected = backside_cull || discard_from_coverage; // the ray goes on past this surface (:146-164)
+
+            world_geometric_normal = hit_from_front ? world_geometric_normal : -world_geometric_normal;
+            float3 world_shading_normal = shading_normal;
+            if (has_normals) {
+                const float* nm = s.normal_matrices + 9 * (st.flags >> 2);
+                world_shading_normal = normalize(f3(nm[0] * shading_normal.x + nm[1] * shading_normal.y + nm[2] * shading_normal.z,
+                                                    nm[3] * shading_normal.x + nm[4] * shading_normal.y + nm[5] * shading_normal.z,
+                                                    nm[6] * shading_normal.x + nm[7] * shading_normal.y + nm[8] * shading_normal.z));
+            }
+            world_shading_normal = hit_from_front ? world_shading_normal : -world_shading_normal;
+            world_shading_normal = fix_backfacing_shading_normal(-ray_direction, world_shading_normal, 0.002f);
+            const Tbn tbn(world_shading_normal);
+
+            const float3 world_intersection_point = intersection_point;
+            const float3 wo = tbn.to_local(-ray_direction);
+            float cos_theta = hit_from_front || material_is_thin_walled(material_parameter) ? wo.z : -wo.z;
+
+            // DefaultMaterialCreator::create, MonteCarlo.cu:239-244. The per-vertex scale goes through the
+            // payload as unorm8 only for the AOV backends; shading uses the interpolated floats.
+            Pdf max_pdf_hint(bsdf_pdf.v * path_regularization_pdf_scale);
+            const auto material = [&]() {
+                if constexpr (TRANSMISSIVE)
+                    return TransmissiveShading::create_regularized(tables, s.dielectric_tables, material_parameter, tint_and_roughness_scale,
+                                                                   cos_theta, max_pdf_hint);
+                else
+                    return material_parameter.shading_model == SHADING_DIFFUSE
+                        ? DefaultShading::create_diffuse(material_parameter, tint_and_roughness_scale)
+                        : DefaultShading::create_regularized(tables, material_parameter, tint_and_roughness_scale, cos_theta, max_pdf_hint);
+            }();
+
+            float3 emission = f3(1.0f); // multiplicative identity, TriangleAttributes.cu:83
+            if (s.shade_emission != nullptr) { // per-vertex emission scale, TriangleAttributes.cu:78-81
+                const float* e = s.shade_emission + 9ll * primitive;
+                emission = f3(e[3], e[4], e[5]) * bx + f3(e[6], e[7], e[8]) * by + f3(e[0], e[1], e[2]) * bz;
+            }
+            if (!rejected) radiance += throughput * emission * f3(material_parameter.emission[0], material_parameter.emission[1], material_parameter.emission[2]);
+
+            // ---- phases 1 .. N: reestimated_light_samples, MonteCarlo.cu:91-123, one candidate per phase ----
+            LightSample light_sample = light_sample_none();
+            if (s.light_count != 0) {
+                float4 light_random_base = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_NEE);
+                for (int k = 0; k < f.next_event_sample_count; ++k) {
+                    SHADE_PHASE_BARRIER();
+                    float4 shift = __ldg(s.nee_offsets + k);
+                    float4 r = light_random_base + shift; // toroidal_shift, Utils.h:46-49
+                    r = make_float4(r.x - floorf(r.x), r.y - floorf(r.y), r.z - floorf(r.z), r.w - floorf(r.w));
+                    LightSample candidate = sample_single_light(s, material, world_intersection_point, wo, tbn, f3(r));
+                    float light_weight = sum(light_sample.radiance);
+                    float new_light_weight = sum(candidate.radiance);
+                    float new_light_probability = fdiv(new_light_weight, light_weight + new_light_weight);
+                    if (r.w < new_light_probability) {
+                        light_sample = candidate;
+                        light_sample.radiance /= new_light_probability;
+                    } else
+                        light_sample.radiance /= 1.0f - new_light_probability;
+                }
+                light_sample.radiance /= float(f.next_event_sample_count);
+            }
+            float3 light_sample_origin = offset_ray_origin(world_intersection_point, light_sample.direction_to_light, world_geometric_normal);
+            light_sample.radiance *= throughput;
+
+            // ---- last phase: BSDF sampling, throughput, the next ray ----
+            SHADE_PHASE_BARRIER();
+            BsdfSample bsdf_sample = material.sample(wo, bsdf_random_uvs);
+            if (rejected) {
+                next_tmin = nextafterf(t_hit, INFINITY); // same ray, advanced past this surface
+            } else {
+                previous_primitive = primitive;
+                bool is_reflection = bsdf_sample.direction.z >= 0;
+                next_direction = tbn.to_world(bsdf_sample.direction);
+                bsdf_pdf = bsdf_sample.pdf;
+                if (bsdf_sample.pdf.is_valid())
+                    throughput *= bsdf_sample.reflectance * fabsf(bsdf_sample.direction.z) / bsdf_sample.pdf.value();
+                else
+                    throughput = f3(0.0f);
+
+                float cos_geometric_theta_i = dot(next_direction, world_geometric_normal);
+                if (is_reflection ? cos_geometric_theta_i < 0.0f : cos_geometric_theta_i >= 0.0f)
+                    next_direction = reflect(next_direction, world_geometric_normal);
+
+                next_origin = offset_ray_origin(world_intersection_point, next_direction, world_geometric_normal);
+                next_tmin = 0.0f;
+                // Russian roulette, opt-in (bpt_settings.russian_roulette_start_bounce): survival probability =
+                // the largest throughput component, decided by the otherwise unused RNG dimension 3 of this bounce.
+                if (f.russian_roulette_start_bounce != 0u && bounces + 1u >= f.russian_roulette_start_bounce && !is_black(throughput)) {
+                    float survival = clampf(fmaxf(fmaxf(throughput.x, throughput.y), throughput.z), 0.05f, 1.0f);
+                    float u = path_rng_sample4f(accumulation_count, pixel_hash, bounces, DIM_ROULETTE).x;
+                    if (u < survival) throughput = throughput / survival;
+                    else throughput = f3(0.0f);
+                }
+                bounces += 1u;
+                if (!light_sample.pdf.is_valid())
+                    bsdf_pdf.disable_MIS();
+
+                // path_trace_single_bounce, SimpleRGPs.cu:117-125
+                if (valid && (light_sample.radiance.x > 0 || light_sample.radiance.y > 0 || light_sample.radiance.z > 0)) {
+                    cast_shadow = true;
+                    shadow_o = f4(light_sample_origin, light_sample.distance);
+                    shadow_d = f4(light_sample.direction_to_light, __uint_as_float(pixel));
+                    shadow_rad = f4(light_sample.radiance, fmaxf(fmaxf(light_sample.radiance.x, light_sample.radiance.y), light_sample.radiance.z));
+                }
+            }
+        }
+
+        if (valid) {
             continue_path = bounces <= f.max_bounce_count && !is_black(throughput); // SimpleRGPs.cu:136
             w.rad[pixel] = f4(radiance, __int_as_float(previous_primitive));
             if (continue_path) {

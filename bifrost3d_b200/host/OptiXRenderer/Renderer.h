@@ -71,6 +71,15 @@ public:
     // ---- addition: sample-sharded multi-GPU rendering ------------------------------------------------------------------
     // This renderer's accumulation indices start at `first_sample` (rank r of R renders [r * spp / R, (r + 1) * spp / R)).
     void set_sample_range(unsigned int first_sample) { m_first_sample = first_sample; }
+    // The collective that combines the ranks' accumulation buffers (bpt_comm_* / bpt_reduce_accumulation of the C ABI, NCCL
+    // underneath). Rank 0 creates the 128-byte id and hands it to the other ranks by whatever means the host has; every rank
+    // joins; after the last sample every rank calls reduce_accumulation, and `root` then resolves the mean of all samples
+    // with the next render-less resolve (resolve_accumulation).
+    static bool create_communicator_id(char id[128]);
+    bool join_communicator(const char id[128], int rank_count, int rank);
+    bool reduce_accumulation(CameraID camera, int root);
+    // Writes the current mean of `camera`'s accumulation to `target` without rendering another sample.
+    bool resolve_accumulation(CameraID camera, optix::Buffer target);
 
 private:
     Renderer(int cuda_device_ID, const std::filesystem::path& data_directory);

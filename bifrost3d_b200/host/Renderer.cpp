@@ -586,4 +586,24 @@ std::vector<Screenshot> Renderer::request_auxiliary_buffers(CameraID camera_ID, 
 }
 optix::Context& Renderer::get_context() { return m_impl->context; }
 
+bool Renderer::create_communicator_id(char id[128]) { return bpt_comm_unique_id(id) == BPT_OK; }
+bool Renderer::join_communicator(const char id[128], int rank_count, int rank) {
+    int status = bpt_comm_init(m_impl->ctx, id, rank_count, rank);
+    Implementation::check(m_impl->ctx, status, "bpt_comm_init");
+    return status == BPT_OK;
+}
+bool Renderer::reduce_accumulation(CameraID camera_ID, int root) {
+    Implementation::check(m_impl->ctx, bpt_select_accumulation(m_impl->ctx, int((unsigned int)camera_ID)), "bpt_select_accumulation");
+    int status = bpt_reduce_accumulation(m_impl->ctx, root);
+    Implementation::check(m_impl->ctx, status, "bpt_reduce_accumulation");
+    return status == BPT_OK;
+}
+bool Renderer::resolve_accumulation(CameraID camera_ID, optix::Buffer target) {
+    Implementation::check(m_impl->ctx, bpt_select_accumulation(m_impl->ctx, int((unsigned int)camera_ID)), "bpt_select_accumulation");
+    int status = bpt_resolve_half4(m_impl->ctx, (uint16_t*)target->getDevicePointer(0), 1);
+    Implementation::check(m_impl->ctx, status, "bpt_resolve_half4");
+    if (status == BPT_OK) status = bpt_synchronize(m_impl->ctx);
+    return status == BPT_OK;
+}
+
 } // namespace OptiXRenderer

@@ -18,7 +18,9 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"]
+        "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_active",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_sector_pipe_lsu_mem_local_op_ld_hit_rate.pct"]
 
 
 def launches(csv_path, out_path):
@@ -76,6 +78,20 @@ def kernel(rep_path, out_path, traffic_key=None, top=0):
         d = json.loads(p.read_text()) if p.exists() else {}
         d.setdefault(traffic_key, {})["extend_kernel_dram_bytes_per_launch"] = per_launch
         d[traffic_key]["source"] = Path(out_path).name
+        d[traffic_key]["launches_averaged"] = len(data)
+        # the rooflines the kernel actually sits under (weighted by launch duration): issue slots, the L1 load/store data pipe, L2
+        ti = hdr.index("gpu__time_duration.sum")
+        weights = [float(r[ti]) for r in data]
+        def weighted(key):
+            if key not in hdr:
+                return None
+            i = hdr.index(key)
+            return sum(float(r[i].replace(",", "")) * wt for r, wt in zip(data, weights)) / sum(weights)
+        d[traffic_key]["issue_slots_active_pct"] = weighted("smsp__issue_active.avg.pct_of_peak_sustained_active")
+        d[traffic_key]["active_lanes_per_instruction"] = weighted("smsp__thread_inst_executed_per_inst_executed.ratio")
+        d[traffic_key]["l1_lsu_data_pipe_pct"] = weighted("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed")
+        d[traffic_key]["l2_throughput_pct"] = weighted("lts__throughput.avg.pct_of_peak_sustained_elapsed")
+        d[traffic_key]["dram_throughput_pct"] = weighted("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
         p.write_text(json.dumps(d, indent=1) + "\n")
 
 
