@@ -296,7 +296,8 @@ def workload_config(args, scene, settings):
     from bifrost3d_b200 import scenes
     return {"workload": f"{scene['name']}: {scene['width']}x{scene['height']}, {scenes.triangle_count(scene)} triangles, {len(scene['lights'])} light(s), "
                         f"max_bounce_count {settings['max_bounces']}, next_event_sample_count {settings['nee_samples']}, 1 sample per pixel per step"
-                        + (f", Russian roulette from bounce {settings['russian_roulette_start']} (extension, not in the reference)" if settings.get("russian_roulette_start") else ""),
+                        + (f", Russian roulette from bounce {settings['russian_roulette_start']} (extension, not in the reference)" if settings.get("russian_roulette_start") else "")
+                        + (", environment next event estimation by CDF inversion on the device" if scene.get("environment", {}).get("nee") == "cdf" else ""),
             "baseline_config": {"cornell": "configs[1] (SmallPT-style Cornell box)", "materials": "configs[2] (material grid + HDR environment, 1080p)", "terrain": "configs[3] (50M-triangle instanced scene, 4K, 8 bounces)"}.get(args.workload, args.workload),
             "l2_policy": "per-step working set (path state + frame buffers) exceeds L2; no explicit flush",
             "parallelism": f"sample-index sharding x{args.gpus}, replicated BVH"}
@@ -312,6 +313,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--spp-total", type=int, default=0, metavar="T",
                     help="configs[4]: render T samples per pixel in total, T / N on each of the N GPUs (strong scaling; overrides --steps)")
+    ap.add_argument("--environment-nee", default=None, choices=["presampled", "cdf"],
+                    help="how next event estimation samples the environment map: presampled lights (the reference renderer's way, default) or CDF inversion on the device (SURVEY.md 8(d) C3: report both)")
     ap.add_argument("--sort-hits", type=int, default=None, metavar="K",
                     help="sort the surface hits by (shading class, hit cell) before shading from wavefront iteration K on (bpt_set_hit_sorting); -1 = never; default: the library's")
     ap.add_argument("--russian-roulette", type=int, default=0, metavar="N",
@@ -340,6 +343,8 @@ def main():
     scene, settings = build_scene(args.workload)
     if args.russian_roulette:
         settings["russian_roulette_start"] = args.russian_roulette
+    if args.environment_nee and scene.get("environment", {}).get("texels") is not None:
+        scene["environment"]["nee"] = args.environment_nee
     W, H = scene["width"], scene["height"]
     ctx = b.Bpt(local_rank)
     if args.sort_hits is not None:
@@ -416,6 +421,7 @@ def main():
     prof_ms = p0.elapsed_time(p1)
     ctx.set_profiling(False)
     peak, peak_kind = measured_peak()
+    capture = ncu_capture(args.workload)
     bpr = bytes_per_ray(info["triangles"])
     extend_s = prof["extend_ms"] * 1e-3
     shadow_s = prof["shadow_ms"] * 1e-3
@@ -429,6 +435,10 @@ def main():
                 "measured_in": f"instrumented pass of {Kp} steps behind the timed region (stream launches + CUDA events between the stages), {prof_ms / Kp:.3f} ms/step against {device_ms / K:.3f} ms/step for the graph launches of the timed region",
                 "share_of_step": {"extend": prof["extend_ms"] / prof_ms, "shade": prof["shade_ms"] / prof_ms, "shadow": prof["shadow_ms"] / prof_ms},
                 "ms_per_step": {"extend": prof["extend_ms"] / Kp, "shade": prof["shade_ms"] / Kp, "shadow": prof["shadow_ms"] / Kp, "instrumented_total": prof_ms / Kp},
+                # The HBM figure above is the model SURVEY.md 8(d) prescribes; the scene's hierarchy is served by L1 / L2, and what the
+                # kernel is limited by are the issue slots (at the SIMT width below) and the L1 load/store data pipe: from the ncu capture.
+                "measured_limits_from_ncu": {k: capture.get(k) for k in ("issue_slots_active_pct", "active_lanes_per_instruction", "l1_lsu_data_pipe_pct",
+                                                                         "l2_throughput_pct", "dram_throughput_pct", "launches_averaged", "source")},
                 "shadow_kernel_achieved": prof["shadow_rays"] * bpr / max(shadow_s, 1e-12) / 1e9,
                 "grays_per_s_extend": prof["extend_rays"] / max(extend_s, 1e-12) / 1e9}
 
@@ -486,16 +496,21 @@ def main():
     return 0
 
 
-def ncu_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of extend_kernel per launch, from the committed `ncu --set full` capture
-    of this workload (profiles/traffic.json, written by tools/summarize_ncu.py); None when there is no capture."""
+def ncu_capture(workload):
+    """What the committed `ncu --set full` capture of this workload says about extend_kernel (profiles/traffic.json, written by
+    tools/summarize_ncu.py from every launch of one sample): DRAM bytes per launch and the utilisation of the units the kernel
+    actually sits under. {} when there is no capture."""
     p = REPO / "profiles" / "traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get(workload, {}).get("extend_kernel_dram_bytes_per_launch")
+            return json.loads(p.read_text()).get(workload, {})
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
+
+
+def ncu_traffic(workload):
+    return ncu_capture(workload).get("extend_kernel_dram_bytes_per_launch")
 
 
 def cpu_baseline_available():

@@ -18,7 +18,13 @@ namespace {
 // xyz triples; each warp stages its 32 tuples through shared memory so that global loads and stores
 // are fully coalesced 128-bit transactions instead of stride-12 scalar accesses.
 // ------------------------------------------------------------------------------------------------
-constexpr int BSDF_BLOCK = 256;
+#ifndef BPT_BSDF_BLOCK
+#define BPT_BSDF_BLOCK 256
+#endif
+#ifndef BPT_BSDF_MIN_BLOCKS
+#define BPT_BSDF_MIN_BLOCKS 4 // 64 registers, 4 x 256 threads per SM: +9 % over 78 registers x 3 CTAs (measured round 2)
+#endif
+constexpr int BSDF_BLOCK = BPT_BSDF_BLOCK;
 
 template <int FLOATS_PER_ITEM>
 __device__ __forceinline__ void stage_in(float* smem, const float* __restrict__ g, int64_t block_first, int64_t n, int block_items) {
@@ -62,7 +68,7 @@ struct BsdfBatchArgs {
 };
 
 template <int KIND>
-__global__ void __launch_bounds__(BSDF_BLOCK) bsdf_batch_kernel(BsdfBatchArgs a) {
+__global__ void __launch_bounds__(BSDF_BLOCK, BPT_BSDF_MIN_BLOCKS) bsdf_batch_kernel(BsdfBatchArgs a) {
     // 3 tables (12 KB) + staging: 5 x 3 floats in, 2 floats coat, 11 floats out -> reuse the input area for output.
     __shared__ __align__(16) float s_tables[3 * TABLE_FLOATS];
     __shared__ __align__(16) float s_wo[BSDF_BLOCK * 3];

@@ -1,21 +1,23 @@
 #!/bin/bash
-# Round measurements on one B200 (run through gpurun): bench lines, the ncu launch list and `ncu --set full` captures.
-# Everything lands in gpurun_out/; tools/summarize_ncu.py turns the captures into the summaries under profiles/.
-R=${1:-r01}
-O=gpurun_out
-mkdir -p $O
-python bench.py --steps 64 --warmup 3 2>$O/bench_materials.err | tail -1 > $O/${R}_bench_materials.json
-python bench.py --steps 64 --warmup 3 --workload cornell --no-cpu-baseline 2>/dev/null | tail -1 > $O/${R}_bench_cornell.json
-python bench.py --steps 16 --warmup 3 --workload terrain --no-cpu-baseline 2>/dev/null | tail -1 > $O/${R}_bench_terrain.json
-python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 > $O/${R}_bench_reference.json
-python tools/bench_bsdf.py 2>/dev/null | tail -1 > $O/${R}_bench_bsdf_tuples.json
-BPT_BVH=lbvh python bench.py --steps 32 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > $O/${R}_bench_materials_lbvh.json
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"generate_kernel|extend_kernel|shade_kernel|shadow_kernel|advance_kernel|accumulate_kernel" -c 600 --csv --log-file $O/${R}_launches_materials.csv python bench.py --steps 4 --warmup 3 --no-cpu-baseline > $O/ncu_a.log 2>&1
-NCU="ncu --set full --clock-control none --import-source on -f"
-$NCU -k regex:extend_kernel -s 6 -c 3 -o $O/prof_${R}_extend_materials python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_c.log 2>&1
-$NCU -k regex:shade_kernel -s 12 -c 4 -o $O/prof_${R}_shade_materials python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_d.log 2>&1
-$NCU -k regex:shadow_kernel -s 6 -c 2 -o $O/prof_${R}_shadow_materials python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_f.log 2>&1
-$NCU -k regex:extend_kernel -s 10 -c 12 -o $O/prof_${R}_extend_terrain python bench.py --workload terrain --steps 2 --warmup 3 --no-cpu-baseline > $O/ncu_g.log 2>&1
-$NCU -k regex:ploc_nearest_kernel -c 2 -o $O/prof_${R}_ploc_nearest python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $O/ncu_h.log 2>&1
-ls -la $O/*.ncu-rep
-for f in materials cornell terrain reference bsdf_tuples materials_lbvh; do echo $f; cut -c1-300 $O/${R}_bench_$f.json; done
+# Round measurements on one B200 (run through gpurun): the GPU test-suite and one bench line per workload, each with its exit
+# code and stderr kept (gpurun_out/<tag>_*.json, .err). tools/profile_round.sh takes the ncu captures, tools/scale_round.sh
+# the multi-GPU lines.
+R=${1:-r02}
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -q -rA > $O/${R}_pytest_gpu_full.log 2>&1; echo "pytest rc=$?" > $O/${R}_pytest_gpu.log; grep -E "^(FAILED|ERROR)|passed|failed" $O/${R}_pytest_gpu_full.log >> $O/${R}_pytest_gpu.log
+run() { # <name> <bench.py arguments...>
+  local name=$1; shift
+  python bench.py "$@" > $O/${R}_bench_$name.all 2> $O/${R}_bench_$name.err; local rc=$?
+  grep '^{' $O/${R}_bench_$name.all | tail -1 > $O/${R}_bench_$name.json; rm -f $O/${R}_bench_$name.all
+  echo "$name rc=$rc $(cut -c1-160 $O/${R}_bench_$name.json)"
+}
+run materials --steps 64 --warmup 3
+run materials_cdf_nee --steps 64 --warmup 3 --no-cpu-baseline --environment-nee cdf
+run cornell --steps 64 --warmup 3 --workload cornell
+run terrain --steps 16 --warmup 3 --workload terrain --no-cpu-baseline
+run terrain_rr3 --steps 16 --warmup 3 --workload terrain --no-cpu-baseline --russian-roulette 3
+run bsdf --steps 20 --warmup 3 --workload bsdf
+run reference --impl reference --steps 3 --warmup 1
+run reference_bsdf --impl reference --steps 3 --warmup 1 --workload bsdf
+BPT_GRAPH=0 run materials_stream_launches --steps 32 --warmup 3 --no-cpu-baseline
+cat $O/${R}_pytest_gpu.log

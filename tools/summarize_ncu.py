@@ -62,10 +62,11 @@ def kernel(rep_path, out_path, traffic_key=None, top=0):
     for i, h in enumerate(hdr):
         if "issue_stalled" in h and h.endswith("per_issue_active.ratio"):
             try:
-                stalls.append((sum(float(r[i]) for r in data) / len(data), h))
+                wts = [float(r[hdr.index("gpu__time_duration.sum")]) for r in data]  # weighted by launch duration
+                stalls.append((sum(float(r[i]) * wt for r, wt in zip(data, wts)) / sum(wts), h))
             except ValueError:
                 pass
-    lines += ["", "Top stall reasons (average warps stalled per issued instruction):", ""]
+    lines += ["", "Top stall reasons (warps stalled per issued instruction, averaged over the launches by duration):", ""]
     for v, h in sorted(stalls, reverse=True)[:6]:
         lines.append(f"* {h.split('issue_stalled_')[1].split('_per_issue')[0]}: {v:.2f}")
     Path(out_path).write_text("\n".join(lines) + "\n")
