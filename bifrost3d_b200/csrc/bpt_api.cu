@@ -393,7 +393,7 @@ void bpt_destroy(bpt_ctx* c) {
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release(); ctx->accel.shade_emission.release();
     ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.slot_of_primitive.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
-    ctx->accumulation.release(); ctx->output_half4.release();
+    ctx->accumulation.release(); ctx->output_half4.release(); ctx->output_float4.release(); ctx->query_scratch.release();
     for (auto& target : ctx->parked_targets) target.second.buffer.release();
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);

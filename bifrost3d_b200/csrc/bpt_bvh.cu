@@ -794,22 +794,25 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     std::vector<float> h_cov(ctx->host_materials.size());
     for (size_t i = 0; i < h_cov.size(); ++i) h_cov[i] = material_coverage_table_entry(ctx->host_materials[i]);
 
-    float *d_o = nullptr, *d_d = nullptr, *d_tmin = nullptr, *d_tmax = nullptr, *d_cov = nullptr, *d_t = nullptr, *d_uv = nullptr;
-    int32_t* d_prim = nullptr; uint8_t* d_occ = nullptr;
-    auto cleanup = [&]() { for (void* p : { (void*)d_o, (void*)d_d, (void*)d_tmin, (void*)d_tmax, (void*)d_cov, (void*)d_t, (void*)d_uv, (void*)d_prim, (void*)d_occ }) if (p) cudaFree(p); };
-#define Q_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); return ctx->cuda_fail(_e, #expr); } } while (0)
-    Q_CHECK(cudaMalloc((void**)&d_o, 3 * n * sizeof(float))); Q_CHECK(cudaMalloc((void**)&d_d, 3 * n * sizeof(float)));
-    Q_CHECK(cudaMalloc((void**)&d_tmin, n * sizeof(float))); Q_CHECK(cudaMalloc((void**)&d_tmax, n * sizeof(float)));
-    Q_CHECK(cudaMalloc((void**)&d_cov, h_cov.size() * sizeof(float)));
+    // One context-owned scratch block that only grows (no allocation on a repeated query), carved into 256-byte aligned parts.
+    size_t offset = 0;
+    auto carve = [&](size_t bytes) { size_t at = offset; offset = (offset + bytes + 255) & ~size_t(255); return at; };
+    const size_t at_o = carve(3 * n * sizeof(float)), at_d = carve(3 * n * sizeof(float)), at_tmin = carve(n * sizeof(float)), at_tmax = carve(n * sizeof(float));
+    const size_t at_cov = carve(std::max<size_t>(h_cov.size(), 1) * sizeof(float));
+    const size_t at_prim = carve(n * sizeof(int32_t)), at_t = carve(n * sizeof(float)), at_uv = carve(2 * n * sizeof(float)), at_occ = carve(n);
+#define Q_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return ctx->cuda_fail(_e, #expr); } while (0)
+    if (ctx->query_scratch.capacity < offset) Q_CHECK(cudaStreamSynchronize(st));
+    Q_CHECK(ctx->query_scratch.resize(offset));
+    unsigned char* base = ctx->query_scratch.ptr;
+    float *d_o = (float*)(base + at_o), *d_d = (float*)(base + at_d), *d_tmin = (float*)(base + at_tmin), *d_tmax = (float*)(base + at_tmax), *d_cov = (float*)(base + at_cov);
+    int32_t* d_prim = out_primitive ? (int32_t*)(base + at_prim) : nullptr;
+    float *d_t = out_t ? (float*)(base + at_t) : nullptr, *d_uv = out_uv ? (float*)(base + at_uv) : nullptr;
+    uint8_t* d_occ = out_occluded ? base + at_occ : nullptr;
     Q_CHECK(cudaMemcpyAsync(d_o, origins, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     Q_CHECK(cudaMemcpyAsync(d_d, directions, 3 * n * sizeof(float), cudaMemcpyHostToDevice, st));
     Q_CHECK(cudaMemcpyAsync(d_tmin, tmin, n * sizeof(float), cudaMemcpyHostToDevice, st));
     Q_CHECK(cudaMemcpyAsync(d_tmax, tmax, n * sizeof(float), cudaMemcpyHostToDevice, st));
-    Q_CHECK(cudaMemcpyAsync(d_cov, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (out_primitive) Q_CHECK(cudaMalloc((void**)&d_prim, n * sizeof(int32_t)));
-    if (out_t) Q_CHECK(cudaMalloc((void**)&d_t, n * sizeof(float)));
-    if (out_uv) Q_CHECK(cudaMalloc((void**)&d_uv, 2 * n * sizeof(float)));
-    if (out_occluded) Q_CHECK(cudaMalloc((void**)&d_occ, n));
+    if (!h_cov.empty()) Q_CHECK(cudaMemcpyAsync(d_cov, h_cov.data(), h_cov.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     AccelView view = accel_view(ctx);
     int grid = (int)std::min<int64_t>((n + TRACE_BLOCK - 1) / TRACE_BLOCK, (int64_t)ctx->sm_count * 8);
     BatchSource source = { d_o, d_d, d_tmin, d_tmax, d_prim, d_t, d_uv, d_occ };
@@ -830,7 +833,6 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     if (out_occluded) Q_CHECK(cudaMemcpyAsync(out_occluded, d_occ, n, cudaMemcpyDeviceToHost, st));
     Q_CHECK(cudaStreamSynchronize(st));
 #undef Q_CHECK
-    cleanup();
     return BPT_OK;
 }
 

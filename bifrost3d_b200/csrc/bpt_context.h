@@ -167,6 +167,8 @@ struct Context {
     int width = 0, height = 0;
     DeviceBuffer<double> accumulation; // double4 per pixel: radiance sum xyz, sample count w
     DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
+    DeviceBuffer<float> output_float4;   // the same for bpt_resolve_float4
+    DeviceBuffer<unsigned char> query_scratch; // rays in, hits out of bpt_intersect; grows, never shrinks
     // Pipelined frame read-back (bpt_resolve_half4_async): two staging frames, a copy stream and per-slot events, so the
     // device -> host copy of frame k overlaps the rendering of frame k + 1.
     DeviceBuffer<uint16_t> frame_staging[2];

@@ -1144,12 +1144,13 @@ int resolve_float4(Context* ctx, float* out) {
     if (!out || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_float4: nothing rendered");
     int64_t pixels = (int64_t)ctx->width * ctx->height;
     cudaStream_t st = ctx->stream;
-    float4* d = nullptr;
-    BPT_CUDA_CHECK(ctx, cudaMallocAsync((void**)&d, pixels * sizeof(float4), st));
+    // context-owned staging frame: no allocation on the per-frame path
+    if (ctx->output_float4.capacity < (size_t)(4 * pixels)) BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+    BPT_CUDA_CHECK(ctx, ctx->output_float4.resize(4 * pixels));
+    float4* d = reinterpret_cast<float4*>(ctx->output_float4.ptr);
     resolve_float4_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->accumulation.ptr, d, pixels);
     ctx->counters.kernel_launches++;
     BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(out, d, pixels * sizeof(float4), cudaMemcpyDeviceToHost, st));
-    BPT_CUDA_CHECK(ctx, cudaFreeAsync(d, st));
     BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
     BPT_CUDA_CHECK(ctx, cudaGetLastError());
     return BPT_OK;
