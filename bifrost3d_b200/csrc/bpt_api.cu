@@ -423,6 +423,7 @@ int bpt_synchronize(bpt_ctx* c) {
 
 int bpt_set_tables(bpt_ctx* c, const float* ggx_with_fresnel_rho, const float* ggx_rho, const float* estimate_ggx_alpha) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (!ggx_with_fresnel_rho || !ggx_rho || !estimate_ggx_alpha) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_tables: null table");
     cudaSetDevice(ctx->device);
     std::vector<float> all(3 * TABLE_FLOATS);
@@ -437,6 +438,7 @@ int bpt_set_tables(bpt_ctx* c, const float* ggx_with_fresnel_rho, const float* g
 
 int bpt_set_dielectric_tables(bpt_ctx* c, const float* into_light_medium, const float* into_dense_medium) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (!into_light_medium || !into_dense_medium) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_dielectric_tables: null table");
     cudaSetDevice(ctx->device);
     std::vector<float2> all(2 * DIELECTRIC_TABLE_FLOAT2S);
@@ -451,6 +453,7 @@ int bpt_set_dielectric_tables(bpt_ctx* c, const float* into_light_medium, const 
 // Image + sampler creation, Renderer.cpp:650-751.
 int bpt_upload_texture(bpt_ctx* c, int texture_id, const bpt_texture_desc* desc, const void* pixels) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (texture_id < 1 || texture_id > (1 << 20) || !desc || !pixels || desc->width <= 0 || desc->height <= 0)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_texture: bad arguments (texture ids start at 1)");
     if (desc->wrap_u < BPT_WRAP_CLAMP || desc->wrap_u > BPT_WRAP_REPEAT || desc->wrap_v < BPT_WRAP_CLAMP || desc->wrap_v > BPT_WRAP_REPEAT)
@@ -514,6 +517,7 @@ int bpt_upload_texture(bpt_ctx* c, int texture_id, const bpt_texture_desc* desc,
 
 int bpt_destroy_texture(bpt_ctx* c, int texture_id) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     auto it = ctx->textures.find(texture_id);
     if (it == ctx->textures.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_destroy_texture: unknown texture id");
     for (const Material& m : ctx->host_materials)
@@ -549,6 +553,7 @@ int bpt_texture_sample(bpt_ctx* c, int texture_id, int64_t n, const float* uv, f
 int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primitive_count, const float* positions, const float* normals,
                     const float* texcoords, const uint8_t* tint_roughness, int vertex_count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (!indices || !positions || primitive_count < 0 || vertex_count < 0)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_upload_mesh: null indices/positions or negative counts");
     for (int64_t i = 0; i < 3ll * primitive_count; ++i)
@@ -575,6 +580,7 @@ int bpt_upload_mesh(bpt_ctx* c, int mesh_id, const uint32_t* indices, int primit
 
 int bpt_set_mesh_emission(bpt_ctx* c, int mesh_id, const float* emission, int vertex_count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     auto it = ctx->meshes.find(mesh_id);
     if (it == ctx->meshes.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_mesh_emission: unknown mesh id");
     if (emission && vertex_count != it->second.vertex_count)
@@ -591,6 +597,7 @@ int bpt_set_mesh_emission(bpt_ctx* c, int mesh_id, const float* emission, int ve
 
 int bpt_remove_mesh(bpt_ctx* c, int mesh_id) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     auto it = ctx->meshes.find(mesh_id);
     if (it == ctx->meshes.end()) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_remove_mesh: unknown mesh id");
     for (const bpt_instance& inst : ctx->instances)
@@ -604,6 +611,7 @@ int bpt_remove_mesh(bpt_ctx* c, int mesh_id) {
 
 int bpt_set_instances(bpt_ctx* c, const bpt_instance* instances, int count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (count < 0 || (count > 0 && !instances)) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_instances: bad arguments");
     for (int i = 0; i < count; ++i)
         if (ctx->meshes.find(instances[i].mesh_id) == ctx->meshes.end())
@@ -615,6 +623,7 @@ int bpt_set_instances(bpt_ctx* c, const bpt_instance* instances, int count) {
 
 int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (count <= 0 || !materials) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_materials: need at least material 0");
     bool any_transmissive = false, any_textured = false;
     for (int i = 0; i < count; ++i) {
@@ -650,6 +659,7 @@ int bpt_set_materials(bpt_ctx* c, const bpt_material* materials, int count) {
 
 int bpt_set_lights(bpt_ctx* c, const bpt_light* lights, int count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (count < 0 || (count > 0 && !lights)) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_lights: bad arguments");
     for (int i = 0; i < count; ++i) {
         uint32_t t = lights[i].flags & BPT_LIGHT_TYPE_MASK;
@@ -671,6 +681,7 @@ int bpt_set_lights(bpt_ctx* c, const bpt_light* lights, int count) {
 int bpt_set_environment(bpt_ctx* c, const float tint[3], const float* texels, int width, int height, const float* per_pixel_pdf,
                         int pdf_width, int pdf_height, const bpt_light_sample* samples, int sample_count) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (!tint) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment: null tint");
     cudaSetDevice(ctx->device);
     memcpy(ctx->env_tint, tint, 3 * sizeof(float));
@@ -693,6 +704,7 @@ int bpt_set_environment(bpt_ctx* c, const float tint[3], const float* texels, in
 
 int bpt_set_environment_cdfs(bpt_ctx* c, const float* marginal_cdf, const float* conditional_cdf, int pdf_width, int pdf_height) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     cudaSetDevice(ctx->device);
     ctx->env_light_uploaded = false;
     if (!marginal_cdf && !conditional_cdf) { ctx->env_has_cdfs = false; return BPT_OK; }
@@ -709,6 +721,7 @@ int bpt_set_environment_cdfs(bpt_ctx* c, const float* marginal_cdf, const float*
 
 int bpt_set_environment_sampling(bpt_ctx* c, int mode) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     if (mode != BPT_ENVIRONMENT_NEE_PRESAMPLED && mode != BPT_ENVIRONMENT_NEE_CDF)
         return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_set_environment_sampling: unknown mode");
     if (ctx->env_nee_mode != mode) ctx->env_light_uploaded = false;
@@ -717,12 +730,14 @@ int bpt_set_environment_sampling(bpt_ctx* c, int mode) {
 }
 
 int bpt_set_hit_sorting(bpt_ctx* c, int from_iteration) {
+    as_context(c)->scene_epoch++;
     as_context(c)->sort_hits_from_iteration = from_iteration < 0 ? -1 : from_iteration;
     return BPT_OK;
 }
 
 int bpt_build_accel(bpt_ctx* c) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     cudaSetDevice(ctx->device);
     return build_accel(ctx);
 }
@@ -745,6 +760,7 @@ int bpt_render(bpt_ctx* c, const bpt_camera* camera, const bpt_settings* setting
 
 int bpt_render_aov(bpt_ctx* c, const bpt_camera* camera, int aov_kind, int width, int height, uint32_t first_sample, uint32_t sample_count, int reset_accumulation) {
     Context* ctx = as_context(c);
+    ctx->scene_epoch++;
     cudaSetDevice(ctx->device);
     return render_aov(ctx, camera, aov_kind, width, height, first_sample, sample_count, reset_accumulation);
 }

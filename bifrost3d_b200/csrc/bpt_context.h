@@ -179,6 +179,7 @@ struct Context {
     uint64_t material_version = 0;
     bool env_light_uploaded = false;
     void* wavefront = nullptr;         // integrator-owned state (bpt_render.cu)
+    uint64_t scene_epoch = 0;          // bumped by every call that uploads or rebuilds scene data on the main stream
 
     // Multi-GPU (bpt_comm.cu): ncclComm_t of this rank, bound at run time.
     void* comm = nullptr;

@@ -57,12 +57,12 @@ struct QueueCounters {
 };
 
 // What changes from frame to frame lives in device memory, so that one instantiated graph serves every bpt_render call of a
-// scene: the host copies this small record in front of the launches, accumulate_kernel advances sample_index.
+// scene: the host copies this small record in front of the launches, finish_sample_kernel advances sample_index.
 struct FrameState {
     bpt_camera camera;
     float path_regularization_pdf_scale;
     unsigned int sample_index; // accumulation index of the sample being rendered (Types.h:486-501 `accumulations`)
-    double* accumulation;      // the selected accumulation target (one per camera): double4 per pixel
+    unsigned int sample_stride; // what finish_sample_kernel adds to it: 1, or 2 when two samples are in flight (even / odd lanes)
 };
 
 struct Wavefront {
@@ -375,7 +375,7 @@ __global__ void advance_kernel(QueueCounters* c, unsigned long long* ray_counter
     c->transmissive = 0;
     c->parity = parity ^ 1u;
     c->iteration += 1u;
-    ray_counters[7] += 1ull;
+    atomicAdd(ray_counters + 7, 1ull); // two samples may be in flight
     if (c->iteration >= MAX_ITERATIONS_PER_SAMPLE) c->active = 0; // the leftover paths are dropped; never observed
     if (has_handle) cudaGraphSetConditional(loop_handle, c->active != 0u ? 1u : 0u);
 }
@@ -715,6 +715,8 @@ __global__ void __launch_bounds__(SHADE_BLOCK, BPT_SHADE_MIN_BLOCKS) shade_kerne
 
 
 __global__ void set_frame_state_kernel(FrameState* destination, FrameState value) { *destination = value; }
+// Last node of a sample: the lane's next sample (no kernel of this sample reads the index any more).
+__global__ void finish_sample_kernel(FrameState* frame) { frame->sample_index += frame->sample_stride; }
 
 // ---- accumulate / resolve --------------------------------------------------------------------------------
 
@@ -723,10 +725,7 @@ __global__ void set_frame_state_kernel(FrameState* destination, FrameState value
 // combined with one sum-reduce.
 // A sample whose radiance is not finite is dropped (neither the sum nor the pixel's sample count change) and counted in
 // bpt_counters.nonfinite_samples: a single NaN would otherwise poison the pixel's fp64 sum for the rest of the render.
-__global__ void accumulate_kernel(const float4* __restrict__ rad, int64_t pixel_count, unsigned long long* __restrict__ nonfinite, FrameState* frame) {
-    double* __restrict__ accum = frame->accumulation;
-    // the next sample of this bpt_render call (no kernel of this sample reads the index any more)
-    if (blockIdx.x == 0 && threadIdx.x == 0) frame->sample_index += 1u;
+__global__ void accumulate_kernel(const float4* __restrict__ rad, double* __restrict__ accum, int64_t pixel_count, unsigned long long* __restrict__ nonfinite) {
     unsigned int dropped = 0;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
         float4 r = rad[p];
@@ -761,7 +760,23 @@ __global__ void resolve_float4_kernel(const double* __restrict__ accum, float4* 
     }
 }
 
-Wavefront* wavefront(Context* ctx) { return static_cast<Wavefront*>(ctx->wavefront); }
+// Two samples in flight. A sample is a chain of dependent kernels whose late iterations hold few paths, and every link of
+// the chain ends in a tail where the SMs drain; a second, independent chain fills those gaps. Samples with an even
+// accumulation index run on lane 0, odd ones on lane 1: own path state, own graph, own stream. The radiance of a finished
+// sample is added to the accumulation target by a launch on the context's MAIN stream that waits for the lane, so
+// the sums happen in index order whatever the lanes do (results are bit for bit those of a single lane), and everything else
+// the caller enqueues on the main stream - resolves, uploads, the NCCL reduce - stays ordered behind the samples it follows.
+// A lane waits for the main stream only after the scene changed (ctx->scene_epoch), and for the accumulation of its own
+// previous sample (which reads the radiance buffer the next sample overwrites).
+struct Integrator {
+    Wavefront lane[2];
+    cudaStream_t stream[2] = { nullptr, nullptr };
+    cudaEvent_t sample_done[2] = { nullptr, nullptr }, accumulated[2] = { nullptr, nullptr }, scene_ready = nullptr;
+    bool accumulated_recorded[2] = { false, false };
+    uint64_t scene_epoch_seen = ~0ull;
+};
+
+Integrator* integrator(Context* ctx) { return static_cast<Integrator*>(ctx->wavefront); }
 
 // Everything the kernels of one sample are launched with. Its bytes are the signature the instantiated graph is keyed by.
 struct SampleLaunch {
@@ -791,16 +806,16 @@ cudaError_t add_kernel(cudaGraphNode_t* node, cudaGraph_t graph, const cudaGraph
 
 // One sample as a graph:
 //   generate -> WHILE(paths alive) { extend || shadow -> shade_escaped || shade_surface [|| shade_transmissive] -> advance }
-//            -> shadow (the rays of the last shade) -> accumulate
+//            -> shadow (the rays of the last shade) -> finish (the lane's next sample index)
+// The accumulation of the sample's radiance is a separate launch on the context's main stream (see render()).
 // The WHILE handle starts every launch at 1 (cudaGraphCondAssignDefault); advance_kernel sets it from the queue length.
-cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L, double** accumulation_slot_unused = nullptr) {
-    (void)accumulation_slot_unused;
+cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L) {
     destroy_graph(wf);
 #define GRAPH_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { destroy_graph(wf); return _e; } } while (0)
     GRAPH_CHECK(cudaGraphCreate(&wf->graph, 0));
     cudaGraph_t graph = wf->graph;
 
-    cudaGraphNode_t generate, loop, final_shadow, accumulate;
+    cudaGraphNode_t generate, loop, final_shadow, finish;
     void* generate_args[] = { &L.w, &L.f };
     GRAPH_CHECK(add_kernel(&generate, graph, nullptr, 0, (const void*)generate_kernel, L.stream_grid, 256, generate_args));
 
@@ -839,11 +854,9 @@ cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L, double** accumula
     GRAPH_CHECK(add_kernel(&advance, body, shaded, shade_count, (const void*)advance_kernel, 1, 1, advance_args));
 
     GRAPH_CHECK(add_kernel(&final_shadow, graph, &loop, 1, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
-    const float4* rad = L.w.rad;
-    unsigned long long* nonfinite = L.w.ray_counters + 6;
     FrameState* frame = const_cast<FrameState*>(L.w.frame);
-    void* accumulate_args[] = { &rad, &L.pixels, &nonfinite, &frame };
-    GRAPH_CHECK(add_kernel(&accumulate, graph, &final_shadow, 1, (const void*)accumulate_kernel, L.stream_grid, 256, accumulate_args));
+    void* finish_args[] = { &frame };
+    GRAPH_CHECK(add_kernel(&finish, graph, &final_shadow, 1, (const void*)finish_sample_kernel, 1, 1, finish_args));
 
     GRAPH_CHECK(cudaGraphInstantiate(&wf->graph_exec, graph, 0));
 #undef GRAPH_CHECK
@@ -900,44 +913,41 @@ int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, ctx->stage_events[0], ctx->stage_events[1]); ctx->counters.shadow_ms += ms;
     }
-    accumulate_kernel<<<L.stream_grid, 256, 0, st>>>(L.w.rad, L.pixels, L.w.ray_counters + 6, const_cast<FrameState*>(L.w.frame));
+    finish_sample_kernel<<<1, 1, 0, st>>>(const_cast<FrameState*>(L.w.frame));
     return BPT_OK;
 }
 
 } // namespace
 
 void release_wavefront(Context* ctx) {
-    Wavefront* wf = wavefront(ctx);
-    if (!wf) return;
-    destroy_graph(wf);
-    wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
-    wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
-    wf->queue_surface.release(); wf->queue_escaped.release();
-    wf->counters.release(); wf->frame_state.release(); wf->coverage.release();
-    wf->surface_key.release(); wf->queue_surface_sorted.release(); wf->sort_bins.release(); wf->material_class.release();
-    delete wf;
+    Integrator* in = integrator(ctx);
+    if (!in) return;
+    for (int l = 0; l < 2; ++l) {
+        if (in->stream[l]) cudaStreamSynchronize(in->stream[l]);
+        Wavefront* wf = &in->lane[l];
+        destroy_graph(wf);
+        wf->ray_o.release(); wf->ray_d.release(); wf->thr.release(); wf->rad.release(); wf->hit.release();
+        wf->sh_o.release(); wf->sh_d.release(); wf->sh_rad.release(); wf->queue_a.release(); wf->queue_b.release();
+        wf->queue_surface.release(); wf->queue_escaped.release();
+        wf->counters.release(); wf->frame_state.release(); wf->coverage.release();
+        wf->surface_key.release(); wf->queue_surface_sorted.release(); wf->sort_bins.release(); wf->material_class.release();
+        if (in->stream[l]) cudaStreamDestroy(in->stream[l]);
+        if (in->sample_done[l]) cudaEventDestroy(in->sample_done[l]);
+        if (in->accumulated[l]) cudaEventDestroy(in->accumulated[l]);
+    }
+    if (in->scene_ready) cudaEventDestroy(in->scene_ready);
+    delete in;
     ctx->wavefront = nullptr;
 }
 
-int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
-           uint32_t first_sample, uint32_t sample_count, int reset_accumulation) {
-    if (!camera || !settings || width <= 0 || height <= 0) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: bad arguments");
-    if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_build_accel first");
-    if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_set_tables first");
-    if (ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
-        return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: transmissive materials need bpt_set_dielectric_tables");
-    if (int status = sync_texture_table(ctx)) return status;
-    if (settings->next_event_sample_count < 0 || settings->next_event_sample_count > 256)
-        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: next_event_sample_count must be in [0, 256]");
+namespace {
+
+// Buffers, per-material tables and the launch description of one lane for this call.
+int prepare_lane(Context* ctx, Wavefront* wf, const bpt_settings* settings, int width, int height, SampleLaunch& L) {
     cudaStream_t st = ctx->stream;
     const int64_t pixels = (int64_t)width * height;
-    if (pixels > 0x7fffffffll) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: frame too large");
-
-    ctx->half4_scale = 1.0f;
-    if (!ctx->wavefront) ctx->wavefront = new Wavefront();
-    Wavefront* wf = wavefront(ctx);
     if (wf->pixel_capacity < pixels) {
-        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // launches in flight still use the old buffers
+        BPT_CUDA_CHECK(ctx, cudaDeviceSynchronize()); // launches in flight (on any lane) still use the old buffers
         BPT_CUDA_CHECK(ctx, wf->ray_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->ray_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->thr.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->rad.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->hit.resize(pixels));
         BPT_CUDA_CHECK(ctx, wf->sh_o.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_d.resize(pixels)); BPT_CUDA_CHECK(ctx, wf->sh_rad.resize(pixels));
@@ -947,6 +957,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         BPT_CUDA_CHECK(ctx, wf->sort_bins.resize(2 * SORT_BINS));
         BPT_CUDA_CHECK(ctx, cudaMemsetAsync(wf->sort_bins.ptr, 0, 2 * SORT_BINS * sizeof(unsigned int), st));
         BPT_CUDA_CHECK(ctx, wf->counters.resize(1)); BPT_CUDA_CHECK(ctx, wf->frame_state.resize(1));
+        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
         wf->pixel_capacity = pixels;
     }
     if (wf->coverage_version != ctx->material_version) {
@@ -958,7 +969,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
             // what the surface shading branches on: the shading model (DefaultShading.h vs DiffuseShading.h) and the coat lobe
             h_class[i] = (unsigned char)((m.shading_model == SHADING_DIFFUSE ? 1u : 0u) | (m.coat != 0 ? 2u : 0u));
         }
-        BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st)); // as above when the table has to grow
+        BPT_CUDA_CHECK(ctx, cudaDeviceSynchronize()); // as above when the tables have to grow
         BPT_CUDA_CHECK(ctx, wf->coverage.resize(h_cov.size()));
         BPT_CUDA_CHECK(ctx, wf->material_class.resize(h_class.size()));
         BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(wf->material_class.ptr, h_class.data(), h_class.size(), cudaMemcpyHostToDevice, st));
@@ -967,16 +978,6 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         wf->coverage_version = ctx->material_version;
     }
 
-    bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
-    if (size_changed) {
-        if (ctx->accumulation.capacity < (size_t)(4 * pixels)) BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
-        BPT_CUDA_CHECK(ctx, ctx->accumulation.resize(4 * pixels));
-        ctx->width = width; ctx->height = height;
-    }
-    if (size_changed || reset_accumulation)
-        BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
-
-    SampleLaunch L;
     memset(&L, 0, sizeof(L)); // padding included: the bytes are compared
     SceneView& s = L.s;
     s.accel = accel_view(ctx);
@@ -998,6 +999,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         if (!ctx->env_light_uploaded) {
             Light env_light = {};
             env_light.flags = env_by_cdf ? BPT_LIGHT_ENVIRONMENT : BPT_LIGHT_PRESAMPLED_ENVIRONMENT;
+            BPT_CUDA_CHECK(ctx, cudaDeviceSynchronize());
             BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->lights.ptr + ctx->light_count, &env_light, sizeof(Light), cudaMemcpyHostToDevice, st));
             BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
             ctx->env_light_uploaded = true;
@@ -1041,6 +1043,63 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     L.transmissive = ctx->has_transmissive_materials ? 1 : 0;
     L.sort_hits = ctx->sort_hits_from_iteration >= 0 ? 1 : 0;
     ctx->launches_per_iteration = 5 + L.transmissive + 2 * L.sort_hits;
+    return BPT_OK;
+}
+
+} // namespace
+
+int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings, int width, int height,
+           uint32_t first_sample, uint32_t sample_count, int reset_accumulation) {
+    if (!camera || !settings || width <= 0 || height <= 0) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: bad arguments");
+    if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_build_accel first");
+    if (!ctx->has_tables) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: call bpt_set_tables first");
+    if (ctx->has_transmissive_materials && !ctx->has_dielectric_tables)
+        return ctx->fail(BPT_ERROR_NOT_READY, "bpt_render: transmissive materials need bpt_set_dielectric_tables");
+    if (int status = sync_texture_table(ctx)) return status;
+    if (settings->next_event_sample_count < 0 || settings->next_event_sample_count > 256)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: next_event_sample_count must be in [0, 256]");
+    cudaStream_t st = ctx->stream;
+    const int64_t pixels = (int64_t)width * height;
+    if (pixels > 0x7fffffffll) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_render: frame too large");
+
+    ctx->half4_scale = 1.0f;
+    if (!ctx->wavefront) ctx->wavefront = new Integrator();
+    Integrator* in = integrator(ctx);
+
+    static const bool graphs_disabled = [] { const char* e = getenv("BPT_GRAPH"); return e && e[0] == '0'; }();
+    static const bool single_lane = [] { const char* e = getenv("BPT_LANES"); return e && e[0] == '1'; }();
+    bool use_graph = !ctx->profiling && !graphs_disabled && !in->lane[0].graph_unavailable;
+    int lanes = (use_graph && !single_lane) ? 2 : 1;
+
+    SampleLaunch L[2];
+    for (int l = 0; l < lanes; ++l)
+        if (int status = prepare_lane(ctx, &in->lane[l], settings, width, height, L[l])) return status;
+
+    bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
+    if (size_changed) {
+        if (ctx->accumulation.capacity < (size_t)(4 * pixels)) BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+        BPT_CUDA_CHECK(ctx, ctx->accumulation.resize(4 * pixels));
+        ctx->width = width; ctx->height = height;
+    }
+    if (size_changed || reset_accumulation)
+        BPT_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->accumulation.ptr, 0, sizeof(double) * 4 * pixels, st));
+
+    if (use_graph)
+        for (int l = 0; l < lanes; ++l) {
+            Wavefront* wf = &in->lane[l];
+            const bool current = wf->graph_exec && wf->graph_signature.size() == sizeof(SampleLaunch) && memcmp(wf->graph_signature.data(), &L[l], sizeof(SampleLaunch)) == 0;
+            if (current) continue;
+            cudaError_t e = build_sample_graph(wf, L[l]);
+            if (e != cudaSuccess) {
+                // e.g. a driver without conditional nodes: remember it, say so once, and take the stream path
+                in->lane[0].graph_unavailable = true;
+                ctx->last_error = std::string("bpt_render: sample graph unavailable (") + cudaGetErrorString(e) + "), using stream launches";
+                fprintf(stderr, "%s\n", ctx->last_error.c_str());
+                cudaGetLastError();
+                use_graph = false; lanes = 1;
+                break;
+            }
+        }
 
     // What changes per call travels through device memory, as the by-value argument of a one-thread kernel: fully
     // asynchronous, no staging buffer whose lifetime the host would have to track.
@@ -1048,32 +1107,54 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     memset(&frame_state, 0, sizeof(frame_state));
     frame_state.camera = *camera;
     frame_state.path_regularization_pdf_scale = settings->path_regularization_pdf_scale;
-    frame_state.sample_index = first_sample;
-    frame_state.accumulation = ctx->accumulation.ptr;
-    set_frame_state_kernel<<<1, 1, 0, st>>>(wf->frame_state.ptr, frame_state);
+    frame_state.sample_stride = (unsigned int)lanes;
+    unsigned long long* nonfinite = reinterpret_cast<unsigned long long*>(ctx->device_counters) + 6;
 
-    static const bool graphs_disabled = [] { const char* e = getenv("BPT_GRAPH"); return e && e[0] == '0'; }();
-    const bool use_graph = !ctx->profiling && !graphs_disabled && !wf->graph_unavailable;
-    if (use_graph) {
-        const bool current = wf->graph_exec && wf->graph_signature.size() == sizeof(L) && memcmp(wf->graph_signature.data(), &L, sizeof(L)) == 0;
-        if (!current) {
-            cudaError_t e = build_sample_graph(wf, L);
-            if (e != cudaSuccess) {
-                // e.g. a driver without conditional nodes: remember it, say so once, and take the stream path
-                wf->graph_unavailable = true;
-                ctx->last_error = std::string("bpt_render: sample graph unavailable (") + cudaGetErrorString(e) + "), using stream launches";
-                fprintf(stderr, "%s\n", ctx->last_error.c_str());
-                cudaGetLastError();
+    if (lanes == 2) {
+        for (int l = 0; l < 2; ++l)
+            if (!in->stream[l]) {
+                BPT_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&in->stream[l], cudaStreamNonBlocking));
+                BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in->sample_done[l], cudaEventDisableTiming));
+                BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in->accumulated[l], cudaEventDisableTiming));
             }
+        if (!in->scene_ready) BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in->scene_ready, cudaEventDisableTiming));
+        if (in->scene_epoch_seen != ctx->scene_epoch) { // uploads / builds since the last render: the lanes start behind them
+            BPT_CUDA_CHECK(ctx, cudaEventRecord(in->scene_ready, st));
+            for (int l = 0; l < 2; ++l) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(in->stream[l], in->scene_ready, 0));
+            in->scene_epoch_seen = ctx->scene_epoch;
         }
-    }
-    if (use_graph && wf->graph_exec) {
-        for (uint32_t k = 0; k < sample_count; ++k) BPT_CUDA_CHECK(ctx, cudaGraphLaunch(wf->graph_exec, st));
+        bool lane_started[2] = { false, false };
+        for (uint32_t k = 0; k < sample_count; ++k) {
+            const int l = int((first_sample + k) & 1u);
+            cudaStream_t lane_stream = in->stream[l];
+            if (in->accumulated_recorded[l]) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(lane_stream, in->accumulated[l], 0)); // its radiance buffer is free again
+            if (!lane_started[l]) {
+                frame_state.sample_index = first_sample + k;
+                set_frame_state_kernel<<<1, 1, 0, lane_stream>>>(in->lane[l].frame_state.ptr, frame_state);
+                lane_started[l] = true;
+            }
+            BPT_CUDA_CHECK(ctx, cudaGraphLaunch(in->lane[l].graph_exec, lane_stream));
+            BPT_CUDA_CHECK(ctx, cudaEventRecord(in->sample_done[l], lane_stream));
+            BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, in->sample_done[l], 0));
+            accumulate_kernel<<<L[l].stream_grid, 256, 0, st>>>(L[l].w.rad, ctx->accumulation.ptr, pixels, nonfinite);
+            BPT_CUDA_CHECK(ctx, cudaEventRecord(in->accumulated[l], st));
+            in->accumulated_recorded[l] = true;
+        }
+        ctx->counters.kernel_launches += (lane_started[0] ? 1ull : 0ull) + (lane_started[1] ? 1ull : 0ull);
     } else {
-        for (uint32_t k = 0; k < sample_count; ++k)
-            if (int status = launch_sample_serial(ctx, L, st)) return status;
+        // One lane on the main stream. The other lane may hold a sample of an earlier two-lane call: the main stream already
+        // waits for it through that sample's accumulation.
+        frame_state.sample_index = first_sample;
+        set_frame_state_kernel<<<1, 1, 0, st>>>(in->lane[0].frame_state.ptr, frame_state);
+        ctx->counters.kernel_launches += 1;
+        for (uint32_t k = 0; k < sample_count; ++k) {
+            if (use_graph) BPT_CUDA_CHECK(ctx, cudaGraphLaunch(in->lane[0].graph_exec, st));
+            else if (int status = launch_sample_serial(ctx, L[0], st)) return status;
+            accumulate_kernel<<<L[0].stream_grid, 256, 0, st>>>(L[0].w.rad, ctx->accumulation.ptr, pixels, nonfinite);
+        }
+        in->scene_epoch_seen = ~0ull; // the lanes have not seen what the main stream did meanwhile
     }
-    ctx->counters.kernel_launches += 1ull + 3ull * sample_count; // the frame state; per sample: generate, the last shadow, accumulate; the iterations are counted on the device
+    ctx->counters.kernel_launches += 4ull * sample_count; // per sample: generate, the last shadow, finish, accumulate; the iterations are counted on the device
     ctx->counters.samples += (uint64_t)pixels * sample_count;
     BPT_CUDA_CHECK(ctx, cudaGetLastError());
     return BPT_OK;

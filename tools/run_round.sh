@@ -1,10 +1,9 @@
 O=gpurun_out; mkdir -p $O; : > $O/bench_lines.log
-for lib in "" bifrost3d_b200/variants/*.so; do
-  [ -n "$lib" ] && export BPT_LIB=$PWD/$lib || unset BPT_LIB
-  name=$(basename "${lib:-default}" .so)
-  python bench.py --workload bsdf --steps 10 --warmup 3 --no-cpu-baseline > $O/line_bsdf_$name.json 2> $O/line_bsdf_$name.err; echo "bsdf $name rc=$?" | tee -a $O/bench_lines.log
-  tail -1 $O/line_bsdf_$name.json | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); print('   ', round(d['value'],1), d['unit'], round(d['ms_per_step'],4), 'ms  frac', round(d['roofline']['frac'],4), 'others', {k: round(v) for k, v in d['other_bsdfs_mtuples_per_s'].items()})" | tee -a $O/bench_lines.log
+python -m pytest tests -m gpu -q -rA > $O/pytest_gpu_full.log 2>&1; echo "pytest rc=$?" > $O/pytest_gpu.log; grep -E "^(FAILED|ERROR)|passed|failed" $O/pytest_gpu_full.log >> $O/pytest_gpu.log
+for w in materials cornell; do
+  tools/bench_line.sh ${w}_lanes2 --steps 64 --warmup 3 --no-cpu-baseline --workload $w
+  BPT_LANES=1 tools/bench_line.sh ${w}_lanes1 --steps 64 --warmup 3 --no-cpu-baseline --workload $w
 done
-unset BPT_LIB
-cat $O/bench_lines.log
+tools/bench_line.sh terrain_lanes2 --steps 16 --warmup 3 --no-cpu-baseline --workload terrain
+BPT_LANES=1 tools/bench_line.sh terrain_lanes1 --steps 16 --warmup 3 --no-cpu-baseline --workload terrain
+cat $O/pytest_gpu.log; cat $O/bench_lines.log
