@@ -444,25 +444,28 @@ def main():
 
     # ---- end-to-end through the C ABI with host buffers ---------------------------------------------
     barrier()
-    # Two pinned host frames, as a display path would use: the read-back of frame k (bpt_resolve_half4_async) overlaps the
-    # rendering of frame k + 1; every frame is complete in host memory before the timed region ends.
-    frames_t = [torch.empty((H, W, 4), dtype=torch.int16).pin_memory() for _ in range(2)]
+    # A ring of pinned host frames (bpt_resolve_half4_async has BPT_FRAME_SLOTS = 4 slots): the read-back of frame k overlaps
+    # the rendering of the following frames; every frame is complete in host memory before the timed region ends.
+    SLOTS = 4
+    frames_t = [torch.empty((H, W, 4), dtype=torch.int16).pin_memory() for _ in range(SLOTS)]
     frames = [f.numpy().view(np.uint16) for f in frames_t]
-    for k in range(2):
-        ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.resolve_half4_async(frames[k & 1], k & 1)
-    ctx.wait_frame(0); ctx.wait_frame(1)
+    for k in range(SLOTS):
+        ctx.render(cam, W, H, first + k, 1, reset=(k == 0), **settings); ctx.resolve_half4_async(frames[k % SLOTS], k % SLOTS)
+    for slot in range(SLOTS):
+        ctx.wait_frame(slot)
     barrier()
     t0 = time.perf_counter()
     e2e_steps = min(K, 32)
     for k in range(e2e_steps):
         cam_k = capi.make_camera(*scene["camera"])  # host-side camera state is rebuilt and uploaded every step
         ctx.render(cam_k, W, H, first + k, 1, reset=(k == 0), **settings)
-        ctx.wait_frame(k & 1)                         # the frame this slot delivered two steps ago has been consumed
-        ctx.resolve_half4_async(frames[k & 1], k & 1)  # device -> host read of the displayed frame
-    ctx.wait_frame(0); ctx.wait_frame(1)
+        ctx.wait_frame(k % SLOTS)                              # the frame this slot delivered SLOTS steps ago has been consumed
+        ctx.resolve_half4_async(frames[k % SLOTS], k % SLOTS)  # device -> host read of the frame
+    for slot in range(SLOTS):
+        ctx.wait_frame(slot)
     barrier()
     e2e_s = time.perf_counter() - t0
-    frame = frames[(e2e_steps - 1) & 1]
+    frame = frames[(e2e_steps - 1) % SLOTS]
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if distributed:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

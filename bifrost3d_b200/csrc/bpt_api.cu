@@ -397,7 +397,7 @@ void bpt_destroy(bpt_ctx* c) {
     for (auto& target : ctx->parked_targets) target.second.buffer.release();
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
-        for (int i = 0; i < 2; ++i) { cudaEventDestroy(ctx->frame_resolved[i]); cudaEventDestroy(ctx->frame_copied[i]); ctx->frame_staging[i].release(); }
+        for (int i = 0; i < BPT_FRAME_SLOTS; ++i) { cudaEventDestroy(ctx->frame_resolved[i]); cudaEventDestroy(ctx->frame_copied[i]); ctx->frame_staging[i].release(); }
         cudaStreamDestroy(ctx->copy_stream);
     }
     if (ctx->device_counters) cudaFree(ctx->device_counters);

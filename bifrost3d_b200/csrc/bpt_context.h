@@ -169,12 +169,12 @@ struct Context {
     DeviceBuffer<uint16_t> output_half4; // staging frame for bpt_resolve_half4 to host memory
     DeviceBuffer<float> output_float4;   // the same for bpt_resolve_float4
     DeviceBuffer<unsigned char> query_scratch; // rays in, hits out of bpt_intersect; grows, never shrinks
-    // Pipelined frame read-back (bpt_resolve_half4_async): two staging frames, a copy stream and per-slot events, so the
+    // Pipelined frame read-back (bpt_resolve_half4_async): BPT_FRAME_SLOTS staging frames, a copy stream and per-slot events, so the
     // device -> host copy of frame k overlaps the rendering of frame k + 1.
-    DeviceBuffer<uint16_t> frame_staging[2];
+    DeviceBuffer<uint16_t> frame_staging[BPT_FRAME_SLOTS];
     cudaStream_t copy_stream = nullptr;
-    cudaEvent_t frame_resolved[2] = {}, frame_copied[2] = {};
-    bool frame_in_flight[2] = { false, false };
+    cudaEvent_t frame_resolved[BPT_FRAME_SLOTS] = {}, frame_copied[BPT_FRAME_SLOTS] = {};
+    bool frame_in_flight[BPT_FRAME_SLOTS] = {};
     float half4_scale = 1.0f; // depth backend: the displayed value is depth / (far - near), SimpleRGPs.cu:247-258
     uint64_t material_version = 0;
     bool env_light_uploaded = false;

@@ -25,6 +25,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifndef BPT_DEFAULT_LANES
+#define BPT_DEFAULT_LANES 4 // samples in flight (BPT_LANES in the environment overrides; 1 = a single chain of kernels)
+#endif
+#ifndef BPT_TRACE_GRID_CTAS_SHARED
+#define BPT_TRACE_GRID_CTAS_SHARED 4 // CTAs per SM of a traversal kernel's persistent grid when several samples are in flight
+#endif
 #ifndef BPT_TILED_QUEUE
 #define BPT_TILED_QUEUE 1
 #endif
@@ -62,7 +68,7 @@ struct FrameState {
     bpt_camera camera;
     float path_regularization_pdf_scale;
     unsigned int sample_index; // accumulation index of the sample being rendered (Types.h:486-501 `accumulations`)
-    unsigned int sample_stride; // what finish_sample_kernel adds to it: 1, or 2 when two samples are in flight (even / odd lanes)
+    unsigned int sample_stride; // what finish_sample_kernel adds to it: the number of lanes (samples in flight)
 };
 
 struct Wavefront {
@@ -375,7 +381,7 @@ __global__ void advance_kernel(QueueCounters* c, unsigned long long* ray_counter
     c->transmissive = 0;
     c->parity = parity ^ 1u;
     c->iteration += 1u;
-    atomicAdd(ray_counters + 7, 1ull); // two samples may be in flight
+    atomicAdd(ray_counters + 7, 1ull); // several samples may be in flight
     if (c->iteration >= MAX_ITERATIONS_PER_SAMPLE) c->active = 0; // the leftover paths are dropped; never observed
     if (has_handle) cudaGraphSetConditional(loop_handle, c->active != 0u ? 1u : 0u);
 }
@@ -760,19 +766,21 @@ __global__ void resolve_float4_kernel(const double* __restrict__ accum, float4* 
     }
 }
 
-// Two samples in flight. A sample is a chain of dependent kernels whose late iterations hold few paths, and every link of
-// the chain ends in a tail where the SMs drain; a second, independent chain fills those gaps. Samples with an even
-// accumulation index run on lane 0, odd ones on lane 1: own path state, own graph, own stream. The radiance of a finished
+// Several samples in flight. A sample is a chain of dependent kernels whose late iterations hold few paths, and every link of
+// the chain ends in a tail where the SMs drain; other, independent chains fill those gaps. The sample with accumulation
+// index i runs on lane i mod L (L = BPT_DEFAULT_LANES; measured 1 / 2 / 3 / 4 lanes: 572 / 657 / 669 / 672 Msamples/s on
+// configs[2], 506 / 550 / 563 / 570 on configs[3]): own path state, own graph, own stream. The radiance of a finished
 // sample is added to the accumulation target by a launch on the context's MAIN stream that waits for the lane, so
 // the sums happen in index order whatever the lanes do (results are bit for bit those of a single lane), and everything else
 // the caller enqueues on the main stream - resolves, uploads, the NCCL reduce - stays ordered behind the samples it follows.
 // A lane waits for the main stream only after the scene changed (ctx->scene_epoch), and for the accumulation of its own
 // previous sample (which reads the radiance buffer the next sample overwrites).
+constexpr int MAX_LANES = 8;
 struct Integrator {
-    Wavefront lane[2];
-    cudaStream_t stream[2] = { nullptr, nullptr };
-    cudaEvent_t sample_done[2] = { nullptr, nullptr }, accumulated[2] = { nullptr, nullptr }, scene_ready = nullptr;
-    bool accumulated_recorded[2] = { false, false };
+    Wavefront lane[MAX_LANES];
+    cudaStream_t stream[MAX_LANES] = {};
+    cudaEvent_t sample_done[MAX_LANES] = {}, accumulated[MAX_LANES] = {}, scene_ready = nullptr;
+    bool accumulated_recorded[MAX_LANES] = {};
     uint64_t scene_epoch_seen = ~0ull;
 };
 
@@ -922,7 +930,7 @@ int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
 void release_wavefront(Context* ctx) {
     Integrator* in = integrator(ctx);
     if (!in) return;
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < MAX_LANES; ++l) {
         if (in->stream[l]) cudaStreamSynchronize(in->stream[l]);
         Wavefront* wf = &in->lane[l];
         destroy_graph(wf);
@@ -943,7 +951,7 @@ void release_wavefront(Context* ctx) {
 namespace {
 
 // Buffers, per-material tables and the launch description of one lane for this call.
-int prepare_lane(Context* ctx, Wavefront* wf, const bpt_settings* settings, int width, int height, SampleLaunch& L) {
+int prepare_lane(Context* ctx, Wavefront* wf, const bpt_settings* settings, int width, int height, int lanes, SampleLaunch& L) {
     cudaStream_t st = ctx->stream;
     const int64_t pixels = (int64_t)width * height;
     if (wf->pixel_capacity < pixels) {
@@ -1036,8 +1044,16 @@ int prepare_lane(Context* ctx, Wavefront* wf, const bpt_settings* settings, int 
 
     // Persistent grids: a whole number of CTAs per SM.
     L.pixels = pixels;
-    L.trace_grid = ctx->sm_count * BPT_TRACE_MIN_BLOCKS;
-    L.shade_grid = ctx->sm_count * BPT_SHADE_MIN_BLOCKS;
+    // With several samples in flight a traversal kernel does not need the whole GPU to itself: 4 CTAs per SM instead of the 8
+    // that fit let kernels of different lanes share an SM instead of queueing behind each other's CTAs (measured with 4 lanes,
+    // 8 / 6 / 5 / 4 / 2 CTAs per SM: 671 / 679 / 678 / 685 / 693 Msamples/s on configs[2], 499 / 508 / 511 / 513 / 520 on
+    // configs[1], 569 / 558 / - / 567 / - on configs[3]). A single chain (profiling, BPT_LANES=1) keeps the full grid.
+    // BPT_TRACE_CTAS / BPT_SHADE_CTAS in the environment override both for tuning runs.
+    static const int trace_ctas_env = [] { const char* e = getenv("BPT_TRACE_CTAS"); return e ? atoi(e) : 0; }();
+    static const int shade_ctas_env = [] { const char* e = getenv("BPT_SHADE_CTAS"); return e ? atoi(e) : 0; }();
+    const int trace_ctas = trace_ctas_env > 0 ? trace_ctas_env : (lanes > 1 ? BPT_TRACE_GRID_CTAS_SHARED : BPT_TRACE_MIN_BLOCKS);
+    L.trace_grid = ctx->sm_count * trace_ctas;
+    L.shade_grid = ctx->sm_count * (shade_ctas_env > 0 ? shade_ctas_env : BPT_SHADE_MIN_BLOCKS);
     L.stream_grid = ctx->sm_count * 8;
     L.escaped_grid = ctx->sm_count * 4;
     L.transmissive = ctx->has_transmissive_materials ? 1 : 0;
@@ -1067,13 +1083,13 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     Integrator* in = integrator(ctx);
 
     static const bool graphs_disabled = [] { const char* e = getenv("BPT_GRAPH"); return e && e[0] == '0'; }();
-    static const bool single_lane = [] { const char* e = getenv("BPT_LANES"); return e && e[0] == '1'; }();
+    static const int lane_setting = [] { const char* e = getenv("BPT_LANES"); int n = e ? atoi(e) : BPT_DEFAULT_LANES; return n < 1 ? 1 : (n > MAX_LANES ? MAX_LANES : n); }();
     bool use_graph = !ctx->profiling && !graphs_disabled && !in->lane[0].graph_unavailable;
-    int lanes = (use_graph && !single_lane) ? 2 : 1;
+    int lanes = use_graph ? lane_setting : 1;
 
-    SampleLaunch L[2];
+    SampleLaunch L[MAX_LANES];
     for (int l = 0; l < lanes; ++l)
-        if (int status = prepare_lane(ctx, &in->lane[l], settings, width, height, L[l])) return status;
+        if (int status = prepare_lane(ctx, &in->lane[l], settings, width, height, lanes, L[l])) return status;
 
     bool size_changed = ctx->width != width || ctx->height != height || ctx->accumulation.size != (size_t)(4 * pixels);
     if (size_changed) {
@@ -1110,8 +1126,8 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
     frame_state.sample_stride = (unsigned int)lanes;
     unsigned long long* nonfinite = reinterpret_cast<unsigned long long*>(ctx->device_counters) + 6;
 
-    if (lanes == 2) {
-        for (int l = 0; l < 2; ++l)
+    if (lanes > 1) {
+        for (int l = 0; l < lanes; ++l)
             if (!in->stream[l]) {
                 BPT_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&in->stream[l], cudaStreamNonBlocking));
                 BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in->sample_done[l], cudaEventDisableTiming));
@@ -1120,12 +1136,12 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
         if (!in->scene_ready) BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&in->scene_ready, cudaEventDisableTiming));
         if (in->scene_epoch_seen != ctx->scene_epoch) { // uploads / builds since the last render: the lanes start behind them
             BPT_CUDA_CHECK(ctx, cudaEventRecord(in->scene_ready, st));
-            for (int l = 0; l < 2; ++l) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(in->stream[l], in->scene_ready, 0));
+            for (int l = 0; l < lanes; ++l) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(in->stream[l], in->scene_ready, 0));
             in->scene_epoch_seen = ctx->scene_epoch;
         }
-        bool lane_started[2] = { false, false };
+        bool lane_started[MAX_LANES] = {};
         for (uint32_t k = 0; k < sample_count; ++k) {
-            const int l = int((first_sample + k) & 1u);
+            const int l = int((first_sample + k) % (uint32_t)lanes);
             cudaStream_t lane_stream = in->stream[l];
             if (in->accumulated_recorded[l]) BPT_CUDA_CHECK(ctx, cudaStreamWaitEvent(lane_stream, in->accumulated[l], 0)); // its radiance buffer is free again
             if (!lane_started[l]) {
@@ -1140,7 +1156,7 @@ int render(Context* ctx, const bpt_camera* camera, const bpt_settings* settings,
             BPT_CUDA_CHECK(ctx, cudaEventRecord(in->accumulated[l], st));
             in->accumulated_recorded[l] = true;
         }
-        ctx->counters.kernel_launches += (lane_started[0] ? 1ull : 0ull) + (lane_started[1] ? 1ull : 0ull);
+        for (int l = 0; l < lanes; ++l) ctx->counters.kernel_launches += lane_started[l] ? 1ull : 0ull;
     } else {
         // One lane on the main stream. The other lane may hold a sample of an earlier two-lane call: the main stream already
         // waits for it through that sample's accumulation.
@@ -1184,12 +1200,12 @@ int resolve_half4(Context* ctx, uint16_t* out, int on_device) {
 // stream, and returns without waiting: the next bpt_render overlaps the copy. `out_host` should be pinned memory.
 int resolve_half4_async(Context* ctx, uint16_t* out_host, int slot) {
     if (!out_host || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_resolve_half4_async: nothing rendered");
-    if (slot < 0 || slot > 1) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_resolve_half4_async: slot must be 0 or 1");
+    if (slot < 0 || slot >= BPT_FRAME_SLOTS) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_resolve_half4_async: slot must be in [0, BPT_FRAME_SLOTS)");
     const int64_t pixels = (int64_t)ctx->width * ctx->height;
     cudaStream_t st = ctx->stream;
     if (!ctx->copy_stream) {
         BPT_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < BPT_FRAME_SLOTS; ++i) {
             BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->frame_resolved[i], cudaEventDisableTiming));
             BPT_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->frame_copied[i], cudaEventDisableTiming));
         }
@@ -1213,7 +1229,7 @@ int resolve_half4_async(Context* ctx, uint16_t* out_host, int slot) {
 }
 
 int wait_frame(Context* ctx, int slot) {
-    if (slot < 0 || slot > 1) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_wait_frame: slot must be 0 or 1");
+    if (slot < 0 || slot >= BPT_FRAME_SLOTS) return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_wait_frame: slot must be in [0, BPT_FRAME_SLOTS)");
     if (ctx->frame_in_flight[slot]) {
         BPT_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->frame_copied[slot]));
         ctx->frame_in_flight[slot] = false;

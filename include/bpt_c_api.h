@@ -258,8 +258,10 @@ int bpt_reduce_accumulation(bpt_ctx* ctx, int root);
 int bpt_resolve_half4(bpt_ctx* ctx, uint16_t* out, int on_device);
 /* Pipelined read-back for progressive display: enqueues the half4 resolve on the render stream and its device -> host copy
  * on a second stream, then returns; the copy of frame k overlaps the rendering of frame k + 1. `out_host` (width*height*4
- * uint16, ideally pinned) is complete after bpt_wait_frame(ctx, slot). Two slots (0, 1) alternate; re-using a slot waits for
- * its previous copy on the device, not on the host. */
+ * uint16, ideally pinned) is complete after bpt_wait_frame(ctx, slot). BPT_FRAME_SLOTS slots rotate (as many frames can be on
+ * their way to the host as samples can be in flight on the device); re-using a slot waits for its previous copy on the device,
+ * not on the host. */
+enum { BPT_FRAME_SLOTS = 4 };
 int bpt_resolve_half4_async(bpt_ctx* ctx, uint16_t* out_host, int slot);
 int bpt_wait_frame(bpt_ctx* ctx, int slot);
 /* mean as float4 to a HOST buffer of width*height*4 floats. */

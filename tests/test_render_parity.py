@@ -318,7 +318,7 @@ def test_pipelined_frame_readback_equals_the_synchronous_one(bpt):
     bpt.wait_frame(0); bpt.wait_frame(1)
     assert np.array_equal(frames[0], expected[2]) and np.array_equal(frames[1], expected[3])
     with pytest.raises(capi.BptError, match="slot"):
-        bpt.resolve_half4_async(frames[0], 2)
+        bpt.resolve_half4_async(frames[0], 4)  # BPT_FRAME_SLOTS = 4
 
 
 @pytest.mark.gpu

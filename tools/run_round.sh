@@ -1,9 +1,10 @@
 O=gpurun_out; mkdir -p $O; : > $O/bench_lines.log
-python -m pytest tests -m gpu -q -rA > $O/pytest_gpu_full.log 2>&1; echo "pytest rc=$?" > $O/pytest_gpu.log; grep -E "^(FAILED|ERROR)|passed|failed" $O/pytest_gpu_full.log >> $O/pytest_gpu.log
 for w in materials cornell; do
-  tools/bench_line.sh ${w}_lanes2 --steps 64 --warmup 3 --no-cpu-baseline --workload $w
-  BPT_LANES=1 tools/bench_line.sh ${w}_lanes1 --steps 64 --warmup 3 --no-cpu-baseline --workload $w
+  for cfg in "4 3" "4 5" "6 4" "8 4" "6 3" "3 4" "4 2"; do set -- $cfg
+    BPT_LANES=$1 BPT_TRACE_CTAS=$2 tools/bench_line.sh ${w}_lanes$1_trace$2 --steps 64 --warmup 8 --no-cpu-baseline --workload $w
+  done
 done
-tools/bench_line.sh terrain_lanes2 --steps 16 --warmup 3 --no-cpu-baseline --workload terrain
-BPT_LANES=1 tools/bench_line.sh terrain_lanes1 --steps 16 --warmup 3 --no-cpu-baseline --workload terrain
-cat $O/pytest_gpu.log; cat $O/bench_lines.log
+for cfg in "4 6" "6 8" "8 8" "6 6"; do set -- $cfg
+  BPT_LANES=$1 BPT_TRACE_CTAS=$2 tools/bench_line.sh terrain_lanes$1_trace$2 --steps 16 --warmup 8 --no-cpu-baseline --workload terrain
+done
+cat $O/bench_lines.log
