@@ -482,6 +482,7 @@ def main():
                 "mrays_per_s": mrays, "extend_rays_per_step": counters["extend_rays"] / K, "shadow_rays_per_step": counters["shadow_rays"] / K,
                 "config": workload_config(args, scene, settings),
                 "bvh": {"triangles": info["triangles"], "nodes": info["nodes"], "build_ms": info["build_ms"], "mtris_per_s": info["triangles"] / max(info["build_ms"], 1e-6) / 1e3,
+                        "node_width": info["node_width"], "traversed_nodes": info["traversed_nodes"], "levels": info["levels"],
                         "slowest_rank_build_ms": slowest_build_ms, "note": "every rank builds the same hierarchy over the replicated scene, outside the timed region"},
                 "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(capi.C.sizeof(capi.Camera) + capi.C.sizeof(capi.Settings)),
                         "d2h_bytes_per_step": int(frame.nbytes), "steps": e2e_steps},

@@ -8,6 +8,7 @@
 #include "bpt_lights.cuh"
 #include "bpt_rng.cuh"
 #include "bpt_trace.cuh"
+#include <type_traits>
 
 namespace bpt {
 
@@ -43,12 +44,14 @@ __device__ __forceinline__ unsigned int compact_by_2(unsigned int v) {
     return v;
 }
 
+template <bool COMPRESSED>
 __global__ void __launch_bounds__(TRACE_BLOCK) aov_kernel(AccelView accel, const float4* __restrict__ world_vertices, const ShadeTriangle* __restrict__ shade,
                                                           const float* __restrict__ normal_matrices, const Material* __restrict__ materials,
                                                           const float* __restrict__ coverage, const Light* __restrict__ lights, int analytic_light_count,
                                                           const float* __restrict__ tables_, const float2* __restrict__ dielectric_tables, AovParams f, float4* __restrict__ out) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    int spill[STACK_LOCAL];
+    __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
+    typedef typename std::conditional<COMPRESSED, TraversalCW<false>, Traversal<false>>::type Trav;
+    typename Trav::Spill spill;
     const ShadingTables tables = { tables_, tables_ + TABLE_FLOATS, tables_ + 2 * TABLE_FLOATS };
     int64_t pixel_count = (int64_t)f.width * f.height;
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < pixel_count; p += (int64_t)gridDim.x * blockDim.x) {
@@ -71,9 +74,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK) aov_kernel(AccelView accel, const
         // process_material_intersection, SimpleRGPs.cu:265-280: trace until a surface is accepted or the ray leaves the scene.
         for (int guard = 0; guard < 4096; ++guard) {
             Ray ray; ray.origin = origin; ray.direction = direction; ray.tmin = tmin; ray.tmax = 1e27f;
-            Traversal<false> tr;
-            tr.stack.smem = s_stack + threadIdx.x; tr.stack.spill = spill;
-            tr.begin(ray, -1);
+            Trav tr;
+            tr.attach(s_stack + threadIdx.x, spill);
+            tr.begin(accel, ray, -1);
             tr.run(accel, coverage, 0x7fffffff);
             Hit h = tr.result();
             float t_closest = h.primitive >= 0 ? h.t : 1e27f;
@@ -198,8 +201,12 @@ int render_aov(Context* ctx, const bpt_camera* camera, int kind, int width, int 
     const int grid = ctx->sm_count * 8;
     for (uint32_t k = 0; k < sample_count; ++k) {
         f.accumulation_count = first_sample + k;
-        aov_kernel<<<grid, TRACE_BLOCK, 0, st>>>(accel, ctx->accel.world_vertices.ptr, ctx->accel.shade.ptr, ctx->accel.normal_matrices.ptr, ctx->materials.ptr,
-                                                  d_cov, ctx->lights.ptr, ctx->light_count, ctx->tables.ptr, ctx->dielectric_tables.ptr, f, d_out);
+        if (accel.cw)
+            aov_kernel<true><<<grid, TRACE_BLOCK, 0, st>>>(accel, ctx->accel.world_vertices.ptr, ctx->accel.shade.ptr, ctx->accel.normal_matrices.ptr, ctx->materials.ptr,
+                                                            d_cov, ctx->lights.ptr, ctx->light_count, ctx->tables.ptr, ctx->dielectric_tables.ptr, f, d_out);
+        else
+            aov_kernel<false><<<grid, TRACE_BLOCK, 0, st>>>(accel, ctx->accel.world_vertices.ptr, ctx->accel.shade.ptr, ctx->accel.normal_matrices.ptr, ctx->materials.ptr,
+                                                             d_cov, ctx->lights.ptr, ctx->light_count, ctx->tables.ptr, ctx->dielectric_tables.ptr, f, d_out);
         accumulate_kernel_aov<<<grid, 256, 0, st>>>(d_out, ctx->accumulation.ptr, pixels);
         ctx->counters.kernel_launches += 2;
     }

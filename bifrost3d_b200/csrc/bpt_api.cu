@@ -350,6 +350,7 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     ctx->device = cuda_device;
     if (const char* bvh = getenv("BPT_BVH")) ctx->use_ploc = strcmp(bvh, "lbvh") != 0;
     if (const char* wide = getenv("BPT_WIDE")) ctx->use_wide = strcmp(wide, "0") != 0;
+    if (const char* cw = getenv("BPT_CW")) ctx->use_cw = strcmp(cw, "0") != 0;
     if (const char* sort_hits = getenv("BPT_SORT_HITS")) ctx->sort_hits_from_iteration = atoi(sort_hits);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
@@ -392,7 +393,7 @@ void bpt_destroy(bpt_ctx* c) {
     for (auto& kv : ctx->meshes) kv.second.release();
     for (auto& kv : ctx->textures) destroy_texture(kv.second);
     ctx->textures.clear(); ctx->texture_objects.release(); ctx->accel.shade_uv.release(); ctx->accel.shade_emission.release();
-    ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.triangles.release(); ctx->accel.slot_of_primitive.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
+    ctx->accel.nodes.release(); ctx->accel.wide_nodes.release(); ctx->accel.cw_nodes.release(); ctx->accel.triangles.release(); ctx->accel.slot_of_primitive.release(); ctx->accel.world_vertices.release(); ctx->accel.shade.release(); ctx->accel.normal_matrices.release();
     ctx->accumulation.release(); ctx->output_half4.release(); ctx->output_float4.release(); ctx->query_scratch.release();
     for (auto& target : ctx->parked_targets) target.second.buffer.release();
     if (ctx->copy_stream) {
@@ -748,6 +749,16 @@ int bpt_accel_info(bpt_ctx* c, int64_t* triangle_count, int64_t* node_count, flo
     if (triangle_count) *triangle_count = ctx->accel.triangle_count;
     if (node_count) *node_count = ctx->accel.node_count;
     if (build_ms) *build_ms = ctx->accel.build_ms;
+    return BPT_OK;
+}
+
+int bpt_accel_hierarchy(bpt_ctx* c, int* kind, int64_t* node_count, int* levels) {
+    Context* ctx = as_context(c);
+    if (!ctx->accel.valid) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_accel_hierarchy: no acceleration structure built");
+    const Accel& A = ctx->accel;
+    if (kind) *kind = A.cw_levels > 0 ? 8 : (A.wide_levels > 0 ? 4 : 2);
+    if (node_count) *node_count = A.cw_levels > 0 ? A.cw_node_count : (A.wide_levels > 0 ? A.wide_node_count : A.node_count);
+    if (levels) *levels = A.cw_levels > 0 ? A.cw_levels : (A.wide_levels > 0 ? A.wide_levels : A.ploc_depth);
     return BPT_OK;
 }
 

@@ -6,6 +6,7 @@
 // of <= LEAF_MAX triangles collapsed into leaves, and the Morton-ordered 48-byte triangle array.
 #include "bpt_context.h"
 #include "bpt_trace.cuh"
+#include <type_traits>
 
 #include "bpt_sort.cuh"
 
@@ -518,6 +519,51 @@ __global__ void tiny_root_kernel(int n, const Aabb* __restrict__ leaf_boxes, Bvh
     nodes[0] = out;
 }
 
+// ---- compressed eight-wide collapse ------------------------------------------------------------------------------------
+// Top down like the four-wide collapse, but a node keeps opening its inner child with the largest surface area until it has
+// eight children (or only leaves). bpt_cw.cuh encodes the node (octant slots, quantised boxes); here the node's inner
+// children get consecutive node indices and the triangles of its leaf children consecutive places in a second triangle
+// array, both in slot order, which is what lets the node address them with two base indices and a few bits per child.
+// The tasks of the next level sit at (node index - first node index of that level).
+__global__ void cw_collapse_kernel(int count, int next_level_base, const WideTask* __restrict__ tasks, WideTask* __restrict__ next_tasks,
+                                   int* __restrict__ counters /*[0] nodes allocated, [1] triangles placed*/, const BvhNode* __restrict__ nodes,
+                                   CwNode* __restrict__ cw, const TraceTriangle* __restrict__ triangles_in, TraceTriangle* __restrict__ triangles_out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const WideTask task = tasks[i];
+    int link[CW_WIDTH]; float3 lo[CW_WIDTH], hi[CW_WIDTH];
+    int k = 0;
+    auto open = [&](int binary_index, int a, int b) {
+        const BvhNode n = nodes[binary_index];
+        lo[a] = f3(n.lo_l_hi_l_x.x, n.lo_l_hi_l_x.y, n.lo_l_hi_l_x.z); hi[a] = f3(n.lo_l_hi_l_x.w, n.hi_l_lo_r.x, n.hi_l_lo_r.y); link[a] = n.left;
+        lo[b] = f3(n.hi_l_lo_r.z, n.hi_l_lo_r.w, n.lo_r_hi_r.x); hi[b] = f3(n.lo_r_hi_r.y, n.lo_r_hi_r.z, n.lo_r_hi_r.w); link[b] = n.right;
+    };
+    open(task.binary_index, 0, 1); k = 2;
+    while (k < CW_WIDTH) {
+        int best = -1; float best_area = -1.0f;
+        for (int c = 0; c < k; ++c)
+            if (link[c] >= 0) { float area = box_area(lo[c], hi[c]); if (area > best_area) { best_area = area; best = c; } }
+        if (best < 0) break;
+        open(link[best], best, k); ++k;
+    }
+    int triangle_counts[CW_WIDTH];
+    for (int c = 0; c < k; ++c) triangle_counts[c] = link[c] >= 0 ? 0 : leaf_count(link[c]);
+    CwNode node; CwPlacement place;
+    cw_encode(k, lo, hi, triangle_counts, node, place);
+    node.child_base = place.inner_count ? (uint32_t)atomicAdd(counters, place.inner_count) : 0u;
+    node.triangle_base = place.triangle_count ? (uint32_t)atomicAdd(counters + 1, place.triangle_count) : 0u;
+    for (int c = 0; c < k; ++c) {
+        if (link[c] >= 0) {
+            const int child = (int)node.child_base + place.offset[c];
+            next_tasks[child - next_level_base] = { child, link[c] };
+        } else {
+            const int first = leaf_first(link[c]);
+            for (int t = 0; t < triangle_counts[c]; ++t) triangles_out[node.triangle_base + place.offset[c] + t] = triangles_in[first + t];
+        }
+    }
+    cw[task.wide_index] = node;
+}
+
 // ---- batched queries -----------------------------------------------------------------------------
 
 struct BatchSource {
@@ -530,20 +576,25 @@ struct BatchSource {
         skip = -1;
     }
     __device__ float termination_weight(unsigned int) const { return 1.0f; }
-    __device__ void store(unsigned int i, const Traversal<false>& tr) const {
+    template <class Trav>
+    __device__ void store_closest(unsigned int i, const Trav& tr) const {
         Hit h = tr.result();
         if (out_primitive) out_primitive[i] = h.primitive;
         if (out_t) out_t[i] = h.primitive >= 0 ? h.t : INFINITY;
         if (out_uv) { out_uv[2ll * i] = h.u; out_uv[2ll * i + 1] = h.v; }
     }
+    __device__ void store(unsigned int i, const Traversal<false>& tr) const { store_closest(i, tr); }
+    __device__ void store(unsigned int i, const TraversalCW<false>& tr) const { store_closest(i, tr); }
     __device__ void store(unsigned int i, const Traversal<true>& tr) const { out_occluded[i] = tr.transmission < 1.0f ? 1 : 0; }
+    __device__ void store(unsigned int i, const TraversalCW<true>& tr) const { out_occluded[i] = tr.transmission < 1.0f ? 1 : 0; }
 };
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool COMPRESSED>
 __global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel, unsigned int n, BatchSource source, const float* __restrict__ coverage,
                                                                 unsigned int* fetch_counter) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
-    traverse_queue<ANY_HIT>(accel, coverage, source, n, fetch_counter, s_stack + threadIdx.x, accel.budget);
+    __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
+    typedef typename std::conditional<COMPRESSED, TraversalCW<ANY_HIT>, Traversal<ANY_HIT>>::type Trav;
+    traverse_queue_with<ANY_HIT, Trav>(accel, coverage, source, n, fetch_counter, s_stack + threadIdx.x, accel.budget);
 }
 
 } // namespace
@@ -597,9 +648,11 @@ int build_accel(Context* ctx) {
     // PLOC scratch
     DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
     DeviceBuffer<uint32_t> d_scan_temp, d_scan_total;
-    DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four-wide collapse
+    DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four- and eight-wide collapse
+    DeviceBuffer<TraceTriangle> d_triangles_by_node;                 // the triangle array in the order of the eight-wide nodes
+    const bool try_cw = ctx->use_cw && LEAF_MAX <= CW_MAX_LEAF_TRIANGLES;
     auto release_all = [&]() {
-        d_tasks[0].release(); d_tasks[1].release(); d_counters.release();
+        d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); d_triangles_by_node.release();
         d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release();
         for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); }
         d_records.release(); d_bounds.release();
@@ -644,10 +697,14 @@ int build_accel(Context* ctx) {
         BUILD_CHECK(d_tree.resize(std::max(n - 1, 1))); BUILD_CHECK(d_parent_internal.resize(std::max(n - 1, 1)));
         BUILD_CHECK(d_parent_leaf.resize(n)); BUILD_CHECK(d_arrival.resize(std::max(n - 1, 1))); BUILD_CHECK(d_node_boxes.resize(std::max(n - 1, 1)));
     }
-    if (ctx->use_wide) { // worst case: as many wide nodes and tasks as binary nodes; trimmed after the build
-        BUILD_CHECK(A.wide_nodes.resize((size_t)n + 1)); BUILD_CHECK(d_tasks[0].resize((size_t)n + 1)); BUILD_CHECK(d_tasks[1].resize((size_t)n + 1));
+    if (ctx->use_wide || try_cw) { // worst case: as many wide nodes and tasks as binary nodes; trimmed after the build
+        BUILD_CHECK(d_tasks[0].resize((size_t)n + 1)); BUILD_CHECK(d_tasks[1].resize((size_t)n + 1));
         BUILD_CHECK(d_counters.resize(2));
     }
+    if (try_cw && n >= 2) { BUILD_CHECK(A.cw_nodes.resize((size_t)n + 1)); BUILD_CHECK(d_triangles_by_node.resize(n)); }
+    // The four-wide nodes are the fallback of the eight-wide ones: their worst-case array is only allocated up front when
+    // they are the first choice, so that the usual build does not reserve 128 bytes per triangle it never touches.
+    if (ctx->use_wide && !(try_cw && n >= 2)) BUILD_CHECK(A.wide_nodes.resize((size_t)n + 1));
 
     BUILD_CHECK(cudaEventRecord(ctx->ev[0], st));
     const int block = 256;
@@ -736,10 +793,33 @@ int build_accel(Context* ctx) {
         ctx->counters.kernel_launches++;
         A.node_count = 1; A.ploc_passes = 0; A.ploc_depth = 0;
     }
-    // ---- four-wide collapse of whichever binary hierarchy was built ----
+    // ---- compressed eight-wide collapse of whichever binary hierarchy was built ----
+    A.cw_levels = 0; A.cw_node_count = 0;
+    if (try_cw && n >= 2) {
+        WideTask root = { 0, 0 };
+        BUILD_CHECK(cudaMemcpyAsync(d_tasks[0].ptr, &root, sizeof(root), cudaMemcpyHostToDevice, st));
+        int h_counters[2] = { 1, 0 }; // nodes allocated (the root is node 0), triangles placed
+        BUILD_CHECK(cudaMemcpyAsync(d_counters.ptr, h_counters, sizeof(h_counters), cudaMemcpyHostToDevice, st));
+        int count = 1, cur = 0, levels = 0, next_level_base = 1;
+        while (count > 0) {
+            cw_collapse_kernel<<<full_grid(count), block, 0, st>>>(count, next_level_base, d_tasks[cur].ptr, d_tasks[cur ^ 1].ptr, d_counters.ptr, A.nodes.ptr,
+                                                                  A.cw_nodes.ptr, A.triangles.ptr, d_triangles_by_node.ptr);
+            ctx->counters.kernel_launches++;
+            BUILD_CHECK(cudaMemcpyAsync(h_counters, d_counters.ptr, sizeof(h_counters), cudaMemcpyDeviceToHost, st));
+            BUILD_CHECK(cudaStreamSynchronize(st));
+            count = h_counters[0] - next_level_base; next_level_base = h_counters[0]; cur ^= 1; ++levels;
+        }
+        // a node visit leaves at most two groups on the stack: fall back to the four-wide nodes if that could overflow it
+        if (h_counters[1] == n && 2 * levels + 2 <= CW_STACK_SMEM + CW_STACK_LOCAL) {
+            A.cw_levels = levels; A.cw_node_count = h_counters[0];
+            std::swap(A.triangles.ptr, d_triangles_by_node.ptr); std::swap(A.triangles.capacity, d_triangles_by_node.capacity); std::swap(A.triangles.size, d_triangles_by_node.size);
+        }
+    }
+    // ---- four-wide collapse: the fallback of the eight-wide nodes, or the first choice with BPT_CW=0 ----
     A.wide_levels = 0; A.wide_node_count = 0;
-    if (ctx->use_wide) {
+    if (ctx->use_wide && A.cw_levels == 0) {
 #define WIDE_CHECK(expr) BUILD_CHECK(expr)
+        WIDE_CHECK(A.wide_nodes.resize((size_t)n + 1));
         WideTask root = { 0, 0 };
         WIDE_CHECK(cudaMemcpyAsync(d_tasks[0].ptr, &root, sizeof(root), cudaMemcpyHostToDevice, st));
         int h_counters[2] = { 0, 1 }; // tasks of the next level, wide nodes allocated (the root is node 0)
@@ -777,6 +857,8 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(trim(A.nodes, (size_t)A.node_count + 1));
     if (A.wide_levels > 0) BUILD_CHECK(trim(A.wide_nodes, (size_t)A.wide_node_count));
     else A.wide_nodes.release();
+    if (A.cw_levels > 0) BUILD_CHECK(trim(A.cw_nodes, (size_t)A.cw_node_count));
+    else A.cw_nodes.release();
 #undef BUILD_CHECK
 
     A.triangle_count = n;
@@ -819,11 +901,13 @@ int intersect_batch(Context* ctx, int64_t n, const float* origins, const float* 
     unsigned int* d_fetch = reinterpret_cast<unsigned int*>(ctx->device_counters + 4); // two scratch fetch counters
     Q_CHECK(cudaMemsetAsync(d_fetch, 0, 2 * sizeof(unsigned int), st));
     if (out_primitive || out_t || out_uv) {
-        intersect_kernel<false><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch);
+        if (view.cw) intersect_kernel<false, true><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch);
+        else intersect_kernel<false, false><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch);
         ctx->counters.kernel_launches++;
     }
     if (out_occluded) {
-        intersect_kernel<true><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch + 1);
+        if (view.cw) intersect_kernel<true, true><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch + 1);
+        else intersect_kernel<true, false><<<grid, TRACE_BLOCK, 0, st>>>(view, (unsigned int)n, source, d_cov, d_fetch + 1);
         ctx->counters.kernel_launches++;
     }
     Q_CHECK(cudaGetLastError());

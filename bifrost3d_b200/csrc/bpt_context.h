@@ -9,6 +9,7 @@
 #include <map>
 
 #include "bpt_types.h"
+#include "bpt_cw.cuh"
 
 namespace bpt {
 
@@ -97,7 +98,10 @@ struct Accel {
     DeviceBuffer<WideNode> wide_nodes;           // four-wide collapse of `nodes`; used by traversal when wide_levels > 0
     int64_t wide_node_count = 0;
     int wide_levels = 0;                          // depth of the four-wide tree; 0 = traverse the binary nodes
-    DeviceBuffer<TraceTriangle> triangles;      // traversal order (Morton sorted)
+    DeviceBuffer<CwNode> cw_nodes;               // compressed eight-wide collapse of `nodes` (bpt_cw.cuh); used when cw_levels > 0
+    int64_t cw_node_count = 0;
+    int cw_levels = 0;                            // depth of the eight-wide tree; 0 = not built / too deep for its stack
+    DeviceBuffer<TraceTriangle> triangles;      // traversal order: Morton sorted, or grouped per eight-wide node when cw_levels > 0
     DeviceBuffer<float4> world_vertices;        // 3 per primitive, instance-major order: position.xyz, w unused
     DeviceBuffer<ShadeTriangle> shade;          // instance-major order
     DeviceBuffer<float2> shade_uv;              // 3 texcoords per primitive, instance-major order; only when a mesh has texcoords
@@ -130,6 +134,7 @@ struct Context {
     bool has_dielectric_tables = false;
     bool has_transmissive_materials = false;
     bool use_wide = true; // BPT_WIDE=0 in the environment traverses the binary nodes (for A/B measurements)
+    bool use_cw = true;   // BPT_CW=0 in the environment keeps the uncompressed four-wide nodes (for A/B measurements)
     bool use_ploc = true; // BPT_BVH=lbvh in the environment selects the plain Morton hierarchy (for A/B measurements)
     // Surface hits are sorted by (shading class, hit cell) before shading from this wavefront iteration on; -1 = never.
     // bpt_set_hit_sorting; BPT_SORT_HITS in the environment sets the initial value.

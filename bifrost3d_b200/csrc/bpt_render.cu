@@ -244,23 +244,29 @@ struct ExtendSource {
         skip = __float_as_int(reinterpret_cast<const float*>(w.rad + pixel)[3]);
     }
     __device__ float termination_weight(unsigned int) const { return 1.0f; }
-    __device__ void store(unsigned int i, const Traversal<false>& tr) const {
+    template <class Trav>
+    __device__ void store(unsigned int i, const Trav& tr) const {
         Hit h = tr.result();
         float t_closest = h.primitive >= 0 ? h.t : RT_DEFAULT_MAX;
+        const unsigned int pixel = queue_in[i];
+        // The eight-wide traversal does not keep the direction (it carries the reciprocal): read the ray again when a light needs it.
+        float3 ray_origin, ray_direction; float ray_tmin;
+        if constexpr (Trav::COMPRESSED) {
+            if (analytic_light_count > 0) { const float4 o = w.ray_o[pixel], d = w.ray_d[pixel]; ray_origin = f3(o); ray_tmin = o.w; ray_direction = f3(d); }
+        } else { ray_origin = tr.ray.origin; ray_direction = tr.ray.direction; ray_tmin = tr.ray.tmin; }
         // Analytic sphere / disk lights (LightSources.cu:31-70): intersectable by MonteCarlo rays only.
         for (int l = 0; l < analytic_light_count; ++l) {
             Light light = lights[l];
             float t = -1e30f, radius = 0.0f;
             if (light_type(light) == BPT_LIGHT_SPHERE) {
                 SphereLight sl = as_sphere(light); radius = sl.radius;
-                t = isect::ray_sphere(tr.ray.origin, tr.ray.direction, sl.position, sl.radius);
+                t = isect::ray_sphere(ray_origin, ray_direction, sl.position, sl.radius);
             } else if (light_type(light) == BPT_LIGHT_SPOT) {
                 SpotLight sp = as_spot(light); radius = sp.radius;
-                t = isect::ray_disk(tr.ray.origin, tr.ray.direction, sp.position, sp.direction, sp.radius);
+                t = isect::ray_disk(ray_origin, ray_direction, sp.position, sp.direction, sp.radius);
             }
-            if (radius > 0.0f && t > tr.ray.tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
+            if (radius > 0.0f && t > ray_tmin && t < t_closest) { t_closest = t; h.t = t; h.primitive = LIGHT_HIT_FLAG | l; }
         }
-        unsigned int pixel = queue_in[i];
         w.hit[pixel] = make_float4(h.t, __int_as_float(h.primitive), h.u, h.v);
         // Sort the paths by the shading they need: surface hits go to the (large) surface shading kernels - keyed by the
         // material's shading model when the scene mixes them - and escaped rays and light hits to a small one, so none runs
@@ -290,13 +296,15 @@ struct ExtendSource {
 
 // SORT_HITS: the instantiation that also writes the sort keys of the surface hits (bpt_set_hit_sorting); the default one
 // carries none of that state.
-template <bool SORT_HITS>
+// COMPRESSED: the instantiation that traverses the compressed eight-wide nodes (s.accel.cw).
+template <bool SORT_HITS, bool COMPRESSED>
 __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kernel(WavefrontView w, SceneView s, FrameParams f) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->active;
     ExtendSource<SORT_HITS> source = { w, w.counters->parity ? w.queue_b : w.queue_a, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials,
                             SORT_HITS && sorting_now(w.counters, f.sort_hits_from_iteration), s.shade, s.slot_of_primitive, s.material_class, s.sort_cell_shift };
-    traverse_queue<false>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
+    typedef typename std::conditional<COMPRESSED, TraversalCW<false>, Traversal<false>>::type Trav;
+    traverse_queue_with<false, Trav>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
 
@@ -310,7 +318,8 @@ struct ShadowSource {
         skip = -1;
     }
     __device__ float termination_weight(unsigned int i) const { return w.sh_rad[i].w; } // max(r, g, b), stored by the shade kernel
-    __device__ void store(unsigned int i, const Traversal<true>& tr) const {
+    template <class Trav>
+    __device__ void store(unsigned int i, const Trav& tr) const {
         if (tr.transmission > 0.0f) {
             unsigned int pixel = __float_as_uint(w.sh_d[i].w);
             float4 l = w.sh_rad[i];
@@ -322,11 +331,13 @@ struct ShadowSource {
     }
 };
 
+template <bool COMPRESSED>
 __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kernel(WavefrontView w, SceneView s) {
-    __shared__ int s_stack[STACK_SMEM * TRACE_BLOCK];
+    __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->shadow[w.counters->parity ^ 1u]; // filled by the previous iteration's shade kernels
     ShadowSource source = { w };
-    traverse_queue<true>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
+    typedef typename std::conditional<COMPRESSED, TraversalCW<true>, Traversal<true>>::type Trav;
+    traverse_queue_with<true, Trav>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
 }
 
@@ -840,8 +851,12 @@ cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L) {
     cudaGraphNode_t traced[2], shaded[3], advance;
     void* trace_args[] = { &L.w, &L.s };
     void* shade_args[] = { &L.w, &L.s, &L.f };
-    GRAPH_CHECK(add_kernel(&traced[0], body, nullptr, 0, L.sort_hits ? (const void*)extend_kernel<true> : (const void*)extend_kernel<false>, L.trace_grid, TRACE_BLOCK, shade_args));
-    GRAPH_CHECK(add_kernel(&traced[1], body, nullptr, 0, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
+    const bool compressed = L.s.accel.cw != nullptr;
+    const void* extend_function = L.sort_hits ? (compressed ? (const void*)extend_kernel<true, true> : (const void*)extend_kernel<true, false>)
+                                              : (compressed ? (const void*)extend_kernel<false, true> : (const void*)extend_kernel<false, false>);
+    const void* shadow_function = compressed ? (const void*)shadow_kernel<true> : (const void*)shadow_kernel<false>;
+    GRAPH_CHECK(add_kernel(&traced[0], body, nullptr, 0, extend_function, L.trace_grid, TRACE_BLOCK, shade_args));
+    GRAPH_CHECK(add_kernel(&traced[1], body, nullptr, 0, shadow_function, L.trace_grid, TRACE_BLOCK, trace_args));
     size_t shade_count = 0;
     GRAPH_CHECK(add_kernel(&shaded[shade_count++], body, traced, 2, (const void*)shade_kernel<false, false>, L.escaped_grid, SHADE_BLOCK, shade_args));
     if (L.sort_hits) { // the surface shading waits for the sorted queue; escaped paths are shaded beside the sort
@@ -861,7 +876,7 @@ cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L) {
     void* advance_args[] = { &counters, &ray_counters, &handle, &has_handle };
     GRAPH_CHECK(add_kernel(&advance, body, shaded, shade_count, (const void*)advance_kernel, 1, 1, advance_args));
 
-    GRAPH_CHECK(add_kernel(&final_shadow, graph, &loop, 1, (const void*)shadow_kernel, L.trace_grid, TRACE_BLOCK, trace_args));
+    GRAPH_CHECK(add_kernel(&final_shadow, graph, &loop, 1, shadow_function, L.trace_grid, TRACE_BLOCK, trace_args));
     FrameState* frame = const_cast<FrameState*>(L.w.frame);
     void* finish_args[] = { &frame };
     GRAPH_CHECK(add_kernel(&finish, graph, &final_shadow, 1, (const void*)finish_sample_kernel, 1, 1, finish_args));
@@ -876,6 +891,7 @@ cudaError_t build_sample_graph(Wavefront* wf, SampleLaunch& L) {
 // per-stage timing is on (bpt_set_profiling: CUDA events between the stages), with BPT_GRAPH=0, or when the driver refuses
 // conditional graph nodes.
 int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
+    const bool compressed = L.s.accel.cw != nullptr;
     generate_kernel<<<L.stream_grid, 256, 0, st>>>(L.w, L.f);
     // A path shades at most max_bounce_count + 1 surfaces; rejected hits (back faces, coverage) re-trace the same ray
     // without consuming a bounce, so a few extra iterations run before the queue length is checked on the host.
@@ -883,10 +899,16 @@ int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
     while (true) {
         for (uint32_t it = 0; it < planned; ++it) {
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 0)], st);
-            if (L.sort_hits) extend_kernel<true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
-            else extend_kernel<false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            if (compressed) {
+                if (L.sort_hits) extend_kernel<true, true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+                else extend_kernel<false, true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            } else {
+                if (L.sort_hits) extend_kernel<true, false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+                else extend_kernel<false, false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s, L.f);
+            }
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 1)], st);
-            shadow_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
+            if (compressed) shadow_kernel<true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
+            else shadow_kernel<false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
             if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(it * 4 + 2)], st);
             if (L.sort_hits) { // timed with the shading it serves
                 sort_scan_kernel<<<1, 1024, 0, st>>>(L.w, L.f);
@@ -914,7 +936,8 @@ int launch_sample_serial(Context* ctx, SampleLaunch& L, cudaStream_t st) {
         planned = 2;
     }
     if (ctx->profiling) cudaEventRecord(ctx->stage_events[ctx->stage_event(0)], st);
-    shadow_kernel<<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s); // the shadow rays of the last shade
+    if (compressed) shadow_kernel<true><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s); // the shadow rays of the last shade
+    else shadow_kernel<false><<<L.trace_grid, TRACE_BLOCK, 0, st>>>(L.w, L.s);
     if (ctx->profiling) {
         cudaEventRecord(ctx->stage_events[ctx->stage_event(1)], st);
         cudaEventSynchronize(ctx->stage_events[1]);

@@ -22,6 +22,7 @@
 #include <cfloat>
 #include "bpt_context.h"
 #include "bpt_math.cuh"
+#include "bpt_cw.cuh"
 
 namespace bpt {
 
@@ -159,7 +160,9 @@ struct TraversalStack {
 struct AccelView {
     const BvhNode* __restrict__ nodes;
     const WideNode* __restrict__ wide; // four-wide nodes; nullptr = traverse the binary nodes
-    const TraceTriangle* __restrict__ triangles;
+    const CwNode* __restrict__ cw;     // compressed eight-wide nodes (bpt_cw.cuh); when set, the kernels instantiated for them run
+    uint32_t cw_exponent_word;         // CW_EXPONENT_WORD as a run-time value (bpt_cw.cuh: cw_plane_float)
+    const TraceTriangle* __restrict__ triangles; // in the order of the hierarchy in use (Morton order, or per node for `cw`)
     const Material* __restrict__ materials; // with `textures`: only read by any-hit rays that meet a coverage-textured material
     TextureView textures;
     unsigned long long* overflow_counter; // pushes beyond the traversal stack (never, see TraversalStack::push)
@@ -185,6 +188,8 @@ inline AccelView accel_view(const Context* ctx) {
     AccelView a;
     a.nodes = ctx->accel.nodes.ptr; a.triangles = ctx->accel.triangles.ptr;
     a.wide = ctx->accel.wide_levels > 0 ? ctx->accel.wide_nodes.ptr : nullptr;
+    a.cw = ctx->accel.cw_levels > 0 ? ctx->accel.cw_nodes.ptr : nullptr;
+    a.cw_exponent_word = CW_EXPONENT_WORD;
     a.materials = ctx->materials.ptr;
     a.textures.objects = ctx->texture_objects.ptr;
     a.textures.uv = ctx->accel.has_uv ? ctx->accel.shade_uv.ptr : nullptr;
@@ -230,8 +235,24 @@ struct Traversal {
 #ifdef BPT_TRAVERSAL_STATS
     unsigned int stat_nodes, stat_triangles;
 #endif
+    static constexpr bool COMPRESSED = false;
 
-    BPT_D void begin(const Ray& r, int skip) {
+    // The part of the stack that does not fit in shared memory, declared by whoever drives the traversal.
+    struct Spill { int slots[STACK_LOCAL + 1]; };
+    // `smem_column`: this thread's column of the CTA's [STACK_SMEM][TRACE_BLOCK] array.
+    BPT_D void attach(int* smem_column, Spill& spill) {
+        stack.smem = smem_column; stack.spill = spill.slots; stack.sp = 0;
+        spill.slots[STACK_LOCAL] = 0;
+        node = NODE_EMPTY; postponed = NODE_EMPTY;
+    }
+    BPT_D bool take_overflow() {
+        if (stack.spill[STACK_LOCAL] == 0) return false;
+        stack.spill[STACK_LOCAL] = 0;
+        return true;
+    }
+    BPT_D float3 ray_origin() const { return ray.origin; }
+
+    BPT_D void begin(const AccelView&, const Ray& r, int skip) {
         ray = r;
         shear = make_ray_shear(r.direction);
         inv_d = f3(__fdiv_rn(1.0f, r.direction.x), __fdiv_rn(1.0f, r.direction.y), __fdiv_rn(1.0f, r.direction.z)); // IEEE whatever -prec-div says
@@ -375,22 +396,177 @@ struct Traversal {
     }
 };
 
-// Persistent-thread driver. `Source` supplies rays and consumes results:
+// ---- compressed eight-wide nodes -----------------------------------------------------------------------------------
+// The node format and the ray / node test are in bpt_cw.cuh; this is the per-lane state and the warp-level loop.
+// * The stack holds 64-bit groups: (first child node, hit children by priority | the parent's imask) or (first triangle,
+//   hit triangles). A node visit pushes at most one entry - the rest of the group the visited child came from - and
+//   needs no sorting: the octant slots of the encoder already are a front-to-back order.
+// * Control flow is the same "while-while" with one parked triangle group per lane as in Traversal: a lane that has found
+//   triangles keeps visiting nodes while other lanes of its warp are still searching, and all lanes then test their
+//   triangles together.
+#ifndef BPT_CW_SPECULATE
+#define BPT_CW_SPECULATE 1
+#endif
+constexpr int CW_STACK_SMEM = STACK_SMEM / 2;  // 8-byte entries in the same shared memory as Traversal's 4-byte ones
+constexpr int CW_STACK_LOCAL = 48;             // bpt_bvh.cu only hands out trees with 2 * levels + 2 <= CW_STACK_SMEM + CW_STACK_LOCAL
+
+struct CwStack {
+    uint2* smem;   // [CW_STACK_SMEM][TRACE_BLOCK], this thread's column
+    uint2* spill;  // [CW_STACK_LOCAL + 1]: the last slot is the "a push was dropped" flag (see TraversalStack)
+    int sp;
+    BPT_D void push(uint2 group) {
+        if (sp < CW_STACK_SMEM) smem[sp * TRACE_BLOCK] = group;
+        else if (sp - CW_STACK_SMEM < CW_STACK_LOCAL) spill[sp - CW_STACK_SMEM] = group;
+        else spill[CW_STACK_LOCAL].x = 1u;
+        ++sp;
+    }
+    BPT_D uint2 pop() {
+        if (sp == 0) return make_uint2(0u, 0u);
+        --sp;
+        return sp < CW_STACK_SMEM ? smem[sp * TRACE_BLOCK] : spill[min(sp - CW_STACK_SMEM, CW_STACK_LOCAL - 1)];
+    }
+};
+
+template <bool ANY_HIT>
+struct TraversalCW {
+    static constexpr bool COMPRESSED = true;
+    CwRay cw;            // origin, reciprocal direction, octant
+    float tmin, ray_tmax;
+    RayShear shear;
+    float tmax;          // closest hit: shrinks to the best t; any hit: the ray's tmax
+    Hit hit;
+    float transmission;
+    float termination_weight;
+    int skip_primitive;
+    uint2 ngroup;        // node group being worked on (y == 0: none; no bits in 24..31: a triangle group that came off the stack)
+    uint2 tgroup;        // triangles found and not tested yet
+    CwStack stack;
+#ifdef BPT_TRAVERSAL_STATS
+    unsigned int stat_nodes, stat_triangles;
+#endif
+
+    struct Spill { uint2 slots[CW_STACK_LOCAL + 1]; };
+    BPT_D void attach(int* smem_column, Spill& spill) {
+        stack.smem = reinterpret_cast<uint2*>(smem_column - threadIdx.x) + threadIdx.x;
+        stack.spill = spill.slots; stack.sp = 0;
+        spill.slots[CW_STACK_LOCAL].x = 0u;
+        ngroup = make_uint2(0u, 0u); tgroup = make_uint2(0u, 0u);
+    }
+    BPT_D bool take_overflow() {
+        if (stack.spill[CW_STACK_LOCAL].x == 0u) return false;
+        stack.spill[CW_STACK_LOCAL].x = 0u;
+        return true;
+    }
+    BPT_D float3 ray_origin() const { return cw.origin; }
+
+    BPT_D void begin(const AccelView& a, const Ray& r, int skip) {
+        cw = cw_make_ray(r.origin, r.direction);
+        shear = make_ray_shear(r.direction);
+        tmin = r.tmin; ray_tmax = r.tmax; tmax = r.tmax;
+        hit.t = r.tmax; hit.primitive = 0x7fffffff; hit.u = hit.v = 0.0f;
+        transmission = 1.0f;
+        termination_weight = 1.0f;
+        skip_primitive = skip;
+        stack.sp = 0;
+        ngroup = make_uint2(0u, 0x80000000u); // the root: "child 7 ^ octant of a group whose imask is empty" = node 0
+        tgroup = make_uint2(0u, 0u);
+#ifdef BPT_TRAVERSAL_STATS
+        stat_nodes = stat_triangles = 0;
+#endif
+    }
+
+    // Visits the nearest unvisited child of `ngroup`: the rest of the group goes to the stack, `ngroup` becomes the group
+    // of that child's own inner children and `found` the triangles of its leaf children.
+    BPT_D void node_step(const AccelView& a, uint2& found) {
+#ifdef BPT_TRAVERSAL_STATS
+        ++stat_nodes;
+#endif
+        const uint32_t index = cw_next_child(ngroup, cw);
+        if (cw_is_node_group(ngroup)) stack.push(ngroup);
+        const uint4* n = reinterpret_cast<const uint4*>(a.cw + index);
+        const uint4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3), n4 = __ldg(n + 4);
+        const uint32_t hits = cw_intersect_children(n0, n1, n2, n3, n4, cw, tmin, tmax, a.cw_exponent_word);
+        ngroup = make_uint2(n1.x, (hits & 0xff000000u) ? ((hits & 0xff000000u) | (n0.w >> 24)) : 0u);
+        found = make_uint2(n1.y, hits & 0x00ffffffu);
+    }
+
+    // Tests one triangle (Traversal::intersect_leaf has the same body). Returns false when an any-hit ray got blocked.
+    BPT_D bool test_triangle(const AccelView& a, const float* __restrict__ coverage_by_material, uint32_t index) {
+        const float4* tri = reinterpret_cast<const float4*>(a.triangles + index);
+        const float4 v0 = ldg4(tri), v1 = ldg4(tri + 1), v2 = ldg4(tri + 2);
+        const int primitive = __float_as_int(v0.w);
+#ifdef BPT_TRAVERSAL_STATS
+        ++stat_triangles;
+#endif
+        float t, u, v;
+        const bool candidate = watertight_triangle(shear, cw.origin, f3(v0), f3(v1), f3(v2), t, u, v) && primitive != skip_primitive;
+        if (ANY_HIT) {
+            if (candidate && t > tmin && t < ray_tmax) { // shadow_any_hit, MonteCarlo.cu:278-285
+                float coverage = coverage_by_material[__float_as_int(v1.w)];
+                if (coverage < 0.0f)
+                    coverage = material_coverage(a.materials[__float_as_int(v1.w)], a.textures, interpolate_texcoord(a.textures, primitive, u, v));
+                transmission *= 1.0f - coverage;
+                if (transmission * termination_weight < 0.0000001f) { transmission = 0.0f; return false; }
+            }
+        } else if (candidate && t > tmin && (t < hit.t || (t == hit.t && primitive < hit.primitive))) {
+            hit.t = t; hit.primitive = primitive; hit.u = u; hit.v = v;
+            tmax = t;
+        }
+        return true;
+    }
+
+    BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget, int min_active = 0) {
+        while ((ngroup.y | tgroup.y) != 0u && budget > 0) {
+            while (cw_is_node_group(ngroup) && (BPT_CW_SPECULATE || tgroup.y == 0u) && budget > 0) {
+                uint2 found;
+                node_step(a, found);
+                --budget;
+                if (found.y != 0u) {
+                    if (tgroup.y == 0u) tgroup = found;
+                    else { // a second batch of triangles: it waits in `ngroup`, in front of the child's own group
+                        if (ngroup.y != 0u) stack.push(ngroup);
+                        ngroup = found;
+                    }
+                }
+                if (ngroup.y == 0u) ngroup = stack.pop();
+                const unsigned int active = __activemask();
+                if (__popc(active) < min_active) budget = 0;
+                if (!__any_sync(active, tgroup.y == 0u && cw_is_node_group(ngroup)))
+                    break;
+            }
+            // One triangle loop for the parked triangles and for triangle groups that came off the stack.
+            while (true) {
+                if (tgroup.y == 0u) {
+                    if (ngroup.y == 0u || cw_is_node_group(ngroup)) break;
+                    tgroup = ngroup; ngroup = stack.pop();
+                }
+                const int bit = 31 - __clz((int)tgroup.y);
+                tgroup.y &= ~(1u << bit);
+                if (!test_triangle(a, coverage_by_material, tgroup.x + (uint32_t)bit)) { ngroup.y = 0u; tgroup.y = 0u; stack.sp = 0; break; }
+            }
+        }
+    }
+
+    BPT_D bool finished() const { return (ngroup.y | tgroup.y) == 0u; }
+
+    BPT_D Hit result() const {
+        Hit h = hit;
+        if (!ANY_HIT && h.primitive == 0x7fffffff) h.primitive = -1;
+        return h;
+    }
+};
+
+// Persistent-thread driver. `Trav` is Traversal<ANY_HIT> or TraversalCW<ANY_HIT>. `Source` supplies rays and consumes results:
 //   void load(unsigned int index, Ray& ray, int& skip_primitive)
 //   float termination_weight(unsigned int index)        (any hit only: the largest radiance channel the ray carries)
-//   void store(unsigned int index, const Traversal<ANY_HIT>& traversal)
+//   void store(unsigned int index, const Trav& traversal)
 // `fetch_counter` is a zero-initialised global counter shared by all CTAs of the launch. Must be called by whole warps.
-template <bool ANY_HIT, class Source>
-BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
-                          unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
-    int spill[STACK_LOCAL + 1];
-    spill[STACK_LOCAL] = 0;
-    Traversal<ANY_HIT> tr;
-    tr.stack.smem = stack_smem;
-    tr.stack.spill = spill;
-    tr.stack.sp = 0;
-    tr.node = NODE_EMPTY;
-    tr.postponed = NODE_EMPTY;
+template <bool ANY_HIT, class Trav, class Source>
+BPT_D void traverse_queue_with(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
+                               unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
+    typename Trav::Spill spill;
+    Trav tr;
+    tr.attach(stack_smem, spill);
     unsigned int index = 0;
     bool has_ray = false, exhausted = false;
     const int lane = threadIdx.x & 31;
@@ -399,7 +575,7 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
         // Retire finished rays and refill idle lanes: one atomic per warp.
         if (has_ray && tr.finished()) {
             source.store(index, tr); has_ray = false;
-            if (spill[STACK_LOCAL] != 0) { spill[STACK_LOCAL] = 0; atomicAdd(a.overflow_counter, 1ull); }
+            if (tr.take_overflow()) atomicAdd(a.overflow_counter, 1ull);
         }
         unsigned int idle = __ballot_sync(0xffffffffu, !has_ray && !exhausted);
         if (idle) {
@@ -412,7 +588,7 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
                 if (index < count) {
                     Ray ray; int skip;
                     source.load(index, ray, skip);
-                    tr.begin(ray, skip);
+                    tr.begin(a, ray, skip);
                     if (ANY_HIT) tr.termination_weight = source.termination_weight(index);
                     has_ray = true;
                 } else
@@ -425,6 +601,12 @@ BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage
         if (has_ray)
             tr.run(a, coverage_by_material, budget, exhausted_warp ? 0 : a.min_active);
     }
+}
+
+template <bool ANY_HIT, class Source>
+BPT_D void traverse_queue(const AccelView& a, const float* __restrict__ coverage_by_material, Source& source, unsigned int count,
+                          unsigned int* fetch_counter, int* stack_smem, int budget = TRAVERSAL_BUDGET) {
+    traverse_queue_with<ANY_HIT, Traversal<ANY_HIT>>(a, coverage_by_material, source, count, fetch_counter, stack_smem, budget);
 }
 
 } // namespace bpt

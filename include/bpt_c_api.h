@@ -212,6 +212,12 @@ int bpt_set_hit_sorting(bpt_ctx* ctx, int from_iteration);
 int bpt_build_accel(bpt_ctx* ctx);
 /* Number of triangles / BVH nodes of the last build and its device time in ms. */
 int bpt_accel_info(bpt_ctx* ctx, int64_t* triangle_count, int64_t* node_count, float* build_ms);
+/* Which node format the rays of the last build traverse: *kind = 8 compressed eight-wide nodes (80 bytes, quantised child
+ * boxes), 4 = four-wide nodes (128 bytes), 2 = the binary nodes (64 bytes); their number and the depth of that tree. The
+ * build picks the widest format whose traversal stack the tree's depth fits; BPT_CW=0 / BPT_WIDE=0 in the environment
+ * rule the first two out (A/B measurements). OptiX keeps this choice to itself (rtAccelerationSetBuilder "Trbvh",
+ * Renderer.cpp:161-182), so there is no reference counterpart. */
+int bpt_accel_hierarchy(bpt_ctx* ctx, int* kind, int64_t* node_count, int* levels);
 
 /* ---- rendering (Renderer::render, Renderer.cpp:1250-1265; SimpleRGPs.cu:74-140) ----------------- */
 

@@ -141,18 +141,23 @@ def test_empty_scene_misses_everything(bpt):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variable,value", [("BPT_WIDE", "0"), ("BPT_BVH", "lbvh")])
-def test_every_hierarchy_returns_the_same_hits(bpt, variable, value, monkeypatch):
-    """The four-wide PLOC hierarchy (default), its binary form (BPT_WIDE=0: the fallback for trees too deep for the stack)
-    and the plain Morton hierarchy (BPT_BVH=lbvh: the fallback when PLOC gives up) must return identical hits: the result
-    is defined by min (t, primitive id), not by the traversal order."""
+@pytest.mark.parametrize("environment,node_width", [({"BPT_CW": "0"}, 4), ({"BPT_CW": "0", "BPT_WIDE": "0"}, 2), ({"BPT_BVH": "lbvh"}, 8),
+                                                    ({"BPT_BVH": "lbvh", "BPT_CW": "0"}, 4)])
+def test_every_hierarchy_returns_the_same_hits(bpt, environment, node_width, monkeypatch):
+    """The compressed eight-wide PLOC hierarchy (default), the four-wide nodes (BPT_CW=0: the fallback for trees too deep for
+    the eight-wide stack), the binary nodes (BPT_WIDE=0 as well: the fallback of that) and the plain Morton hierarchy
+    (BPT_BVH=lbvh: the fallback when PLOC gives up) must return identical hits: the result is defined by
+    min (t, primitive id), not by the traversal order."""
     scene = soup_scene(20000, 11, size=0.08)
     o, d = random_rays(60000, 12)
     scenes.upload(bpt, scene)
+    assert bpt.accel_info()["node_width"] == 8
     want = bpt.intersect(o, d)
-    monkeypatch.setenv(variable, value)
+    for variable, value in environment.items():
+        monkeypatch.setenv(variable, value)
     other = capi.Bpt(0)
     scenes.upload(other, scene)
+    assert other.accel_info()["node_width"] == node_width
     got = other.intersect(o, d)
     other.close()
     for a, b in zip(got, want):
@@ -287,26 +292,76 @@ def nested_slivers(count=80, growth=1.35):
     return {"indices": np.arange(3 * count, dtype=np.uint32).reshape(count, 3), "positions": p}
 
 
+def deep_hierarchy_rays(n, seed):
+    rng = np.random.default_rng(seed)
+    o = np.concatenate([rng.normal(scale=0.004, size=(n, 2)), np.full((n, 1), -1.0)], axis=1).astype(np.float32)
+    o[n // 2:, 2] = 1.0  # half of the rays come from the far side: the nearest triangle is the largest one
+    d = np.tile(np.float32([0, 0, 1]), (n, 1)); d[n // 2:, 2] = -1.0
+    d[:, :2] += rng.normal(scale=1e-3, size=(n, 2)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    return o, d.astype(np.float32)
+
+
 @pytest.mark.gpu
 @needs_oracle
-def test_deep_hierarchy_uses_the_spill_stack(bpt):
-    """Forces traversal stacks deeper than the 32 shared-memory entries (the local-memory spill part) and checks the result
-    against brute force, for closest-hit and for any-hit rays through partially covering surfaces (which never terminate
-    early and therefore walk the whole chain)."""
+@pytest.mark.parametrize("environment", [{}, {"BPT_CW": "0"}])
+def test_deep_hierarchy_uses_the_spill_stack(environment, monkeypatch):
+    """Forces traversal stacks deeper than the 32 shared-memory entries of the four-wide traversal (the local-memory spill
+    part; BPT_CW=0) and checks the result against brute force, for closest-hit and for any-hit rays through partially
+    covering surfaces (which never terminate early and therefore walk the whole chain). The eight-wide nodes swallow seven
+    links of such a chain per node: the same scene through them is the other case."""
+    for variable, value in environment.items():
+        monkeypatch.setenv(variable, value)
+    bpt = capi.Bpt(0)
     mesh = nested_slivers()
     mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
     mats[1]["coverage"] = 0.01
     scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
              "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
     scenes.upload(bpt, scene)
+    assert bpt.accel_info()["node_width"] == (4 if environment else 8)
     sc = oracle_lib.OracleScene(scene)
-    rng = np.random.default_rng(31)
-    n = 20000
-    o = np.concatenate([rng.normal(scale=0.004, size=(n, 2)), np.full((n, 1), -1.0)], axis=1).astype(np.float32)
-    o[n // 2:, 2] = 1.0  # half of the rays come from the far side: the nearest triangle is the largest one
-    d = np.tile(np.float32([0, 0, 1]), (n, 1)); d[n // 2:, 2] = -1.0
-    d[:, :2] += rng.normal(scale=1e-3, size=(n, 2)).astype(np.float32)
-    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    o, d = deep_hierarchy_rays(20000, 31)
+    bpt.counters(reset=True)
+    gp, gt, guv, gocc = bpt.intersect(o, d)
+    rp, rt, ruv, rocc = sc.intersect(o, d, brute=True)
+    assert np.array_equal(gp, rp) and np.array_equal(gocc, rocc)
+    hit = rp >= 0
+    assert hit.mean() > 0.9 and np.array_equal(gt[hit], rt[hit]) and np.array_equal(guv[hit], ruv[hit])
+    assert bpt.counters()["traversal_stack_overflows"] == 0
+    sc.close(); bpt.close()
+
+
+def nested_clusters(count=150, growth=1.15, per_cluster=5):
+    """Like nested_slivers, but every link of the chain is a small fan of triangles, i.e. an inner node: an eight-wide node
+    over such a chain holds up to seven inner children plus the rest of the chain, a ray down the axis hits them all and
+    leaves the unvisited ones on the stack at every level."""
+    positions, size = [], 0.01
+    for k in range(count):
+        z = 1e-4 * k
+        for f in range(per_cluster):
+            a0, a1 = 2 * np.pi * f / per_cluster, 2 * np.pi * (f + 1) / per_cluster
+            positions += [(0.0, 0.0, z), (size * np.cos(a0), size * np.sin(a0), z), (size * np.cos(a1), size * np.sin(a1), z)]
+        size *= growth
+    p = np.array(positions, np.float32)
+    return {"indices": np.arange(p.shape[0], dtype=np.uint32).reshape(-1, 3), "positions": p}
+
+
+@pytest.mark.gpu
+@needs_oracle
+def test_deep_hierarchy_of_inner_nodes(bpt):
+    """A chain whose links are inner nodes (see nested_clusters): whichever node format the build settles on for its depth,
+    closest hits and transmissions equal brute force and no push is dropped."""
+    mesh = nested_clusters()
+    mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
+    mats[1]["coverage"] = 0.01
+    scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
+             "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
+    scenes.upload(bpt, scene)
+    info = bpt.accel_info()
+    print("nested clusters:", info)
+    sc = oracle_lib.OracleScene(scene)
+    o, d = deep_hierarchy_rays(20000, 37)
     bpt.counters(reset=True)
     gp, gt, guv, gocc = bpt.intersect(o, d)
     rp, rt, ruv, rocc = sc.intersect(o, d, brute=True)
