@@ -399,14 +399,13 @@ struct Traversal {
 // ---- compressed eight-wide nodes -----------------------------------------------------------------------------------
 // The node format and the ray / node test are in bpt_cw.cuh; this is the per-lane state and the warp-level loop.
 // * The stack holds 64-bit groups: (first child node, hit children by priority | the parent's imask) or (first triangle,
-//   hit triangles). A node visit pushes at most one entry - the rest of the group the visited child came from - and
+//   hit triangles). A node visit pushes at most one node group - the rest of the group the visited child came from - and
 //   needs no sorting: the octant slots of the encoder already are a front-to-back order.
-// * Control flow is the same "while-while" with one parked triangle group per lane as in Traversal: a lane that has found
-//   triangles keeps visiting nodes while other lanes of its warp are still searching, and all lanes then test their
-//   triangles together.
-#ifndef BPT_CW_SPECULATE
-#define BPT_CW_SPECULATE 1
-#endif
+// * Control flow is "while-while" with speculation, as in Traversal: a lane that has found triangles keeps visiting nodes
+//   while other lanes of its warp are still searching for theirs (further triangles it meets wait on its stack), and all
+//   lanes then test their triangles together. Measured on B200 (configs[2] / configs[1], Msamples/s): no speculation
+//   603 / 479, one parked group and then wait 691 / 500, unbounded (this) 703 / 504; ending the node loop while 3 / 6 / 10
+//   lanes are still searching 698 / 696 / 690 on configs[2].
 constexpr int CW_STACK_SMEM = STACK_SMEM / 2;  // 8-byte entries in the same shared memory as Traversal's 4-byte ones
 constexpr int CW_STACK_LOCAL = 48;             // bpt_bvh.cu only hands out trees with 2 * levels + 2 <= CW_STACK_SMEM + CW_STACK_LOCAL
 
@@ -438,7 +437,7 @@ struct TraversalCW {
     float transmission;
     float termination_weight;
     int skip_primitive;
-    uint2 ngroup;        // node group being worked on (y == 0: none; no bits in 24..31: a triangle group that came off the stack)
+    uint2 ngroup;        // group being worked on (y == 0: none; no bits in 24..31: a triangle group that came off the stack)
     uint2 tgroup;        // triangles found and not tested yet
     CwStack stack;
 #ifdef BPT_TRAVERSAL_STATS
@@ -517,16 +516,13 @@ struct TraversalCW {
 
     BPT_D void run(const AccelView& a, const float* __restrict__ coverage_by_material, int budget, int min_active = 0) {
         while ((ngroup.y | tgroup.y) != 0u && budget > 0) {
-            while (cw_is_node_group(ngroup) && (BPT_CW_SPECULATE || tgroup.y == 0u) && budget > 0) {
+            while (cw_is_node_group(ngroup) && budget > 0) {
                 uint2 found;
                 node_step(a, found);
                 --budget;
                 if (found.y != 0u) {
                     if (tgroup.y == 0u) tgroup = found;
-                    else { // a second batch of triangles: it waits in `ngroup`, in front of the child's own group
-                        if (ngroup.y != 0u) stack.push(ngroup);
-                        ngroup = found;
-                    }
+                    else stack.push(found); // further triangles wait on the stack while the lane keeps visiting nodes
                 }
                 if (ngroup.y == 0u) ngroup = stack.pop();
                 const unsigned int active = __activemask();
