@@ -281,6 +281,7 @@ __global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb
 #endif
 constexpr int PLOC_RADIUS = BPT_PLOC_RADIUS;
 constexpr int PLOC_MAX_DEPTH = 96; // the traversal stack holds STACK_SMEM + STACK_LOCAL = 104 entries
+constexpr int PLOC_TAIL = 1024;    // the last clusters finish inside one block (ploc_tail_kernel)
 
 __device__ __forceinline__ bool is_leaf_cluster_child(const TreeNode* __restrict__ tree, int child, int& first, int& size) {
     if (child < 0) { first = ~child; size = 1; return true; }
@@ -322,64 +323,88 @@ __device__ __forceinline__ float union_area(const Aabb& a, const Aabb& b) {
     return d.x * d.y + d.y * d.z + d.z * d.x;
 }
 
-__global__ void ploc_nearest_kernel(int m, const Aabb* __restrict__ cl_box, int* __restrict__ nearest) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const Aabb mine = cl_box[i];
-    float best = FLT_MAX; int best_j = -1, best_rank = 0x7fffffff;
-    const int lo = max(0, i - PLOC_RADIUS), hi = min(m - 1, i + PLOC_RADIUS);
-    for (int j = lo; j <= hi; ++j) {
-        if (j == i) continue;
-        float a = union_area(mine, cl_box[j]);
-        // exact ties (regular or coincident geometry): prefer the aligned partner i ^ 1, then the closer position, then the
-        // lower one, so that equal boxes still pair up instead of forming a chain that merges one pair per pass
-        int rank = (j == (i ^ 1)) ? 0 : 2 * abs(j - i) + (j > i ? 1 : 0);
-        if (a < best || (a == best && rank < best_rank)) { best = a; best_j = j; best_rank = rank; }
+// What a PLOC pass needs to know, kept in device memory so that the passes can follow each other without the host: the
+// number of clusters, which of the two cluster lists is current, and how it went.
+struct PlocState { uint32_t m; int cur; int passes; int failed; };
+struct PlocLists { int* link[2]; Aabb* box[2]; int* depth[2]; };
+
+__global__ void ploc_nearest_kernel(const PlocState* __restrict__ state, PlocLists lists, int* __restrict__ nearest) {
+    const int m = (int)state->m;
+    const Aabb* __restrict__ cl_box = lists.box[state->cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const Aabb mine = cl_box[i];
+        float best = FLT_MAX; int best_j = -1, best_rank = 0x7fffffff;
+        const int lo = max(0, i - PLOC_RADIUS), hi = min(m - 1, i + PLOC_RADIUS);
+        for (int j = lo; j <= hi; ++j) {
+            if (j == i) continue;
+            float a = union_area(mine, cl_box[j]);
+            // exact ties (regular or coincident geometry): prefer the aligned partner i ^ 1, then the closer position, then the
+            // lower one, so that equal boxes still pair up instead of forming a chain that merges one pair per pass
+            int rank = (j == (i ^ 1)) ? 0 : 2 * abs(j - i) + (j > i ? 1 : 0);
+            if (a < best || (a == best && rank < best_rank)) { best = a; best_j = j; best_rank = rank; }
+        }
+        nearest[i] = best_j;
     }
-    nearest[i] = best_j;
 }
 
 // Mutual nearest neighbours merge: the lower position keeps the new node, the higher one is dropped.
-__global__ void ploc_merge_kernel(int m, const int* __restrict__ nearest, int* __restrict__ cl_link, Aabb* __restrict__ cl_box, int* __restrict__ cl_depth,
-                                  uint32_t* __restrict__ keep, BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    int j = nearest[i];
-    bool mutual = j >= 0 && nearest[j] == i;
-    if (!mutual) { keep[i] = 1u; return; }
-    if (i > j) { keep[i] = 0u; return; }
-    Aabb a = cl_box[i], b = cl_box[j];
-    int index = atomicAdd(node_counter, 1);
-    BvhNode out;
-    out.lo_l_hi_l_x = make_float4(a.lo.x, a.lo.y, a.lo.z, a.hi.x);
-    out.hi_l_lo_r = make_float4(a.hi.y, a.hi.z, b.lo.x, b.lo.y);
-    out.lo_r_hi_r = make_float4(b.lo.z, b.hi.x, b.hi.y, b.hi.z);
-    out.left = cl_link[i]; out.right = cl_link[j]; out.pad0 = 0; out.pad1 = 0;
-    nodes[index] = out;
-    Aabb merged; merged.lo = min3(a.lo, b.lo); merged.hi = max3(a.hi, b.hi);
-    int depth = max(cl_depth[i], cl_depth[j]) + 1;
-    // cluster j is only read by this thread (its own thread returned above), so updating slot i in place is race free:
-    // no other cluster has i or j as a MUTUAL partner, and non-mutual clusters only read `nearest`.
-    cl_box[i] = merged; cl_link[i] = index; cl_depth[i] = depth;
-    keep[i] = 1u;
-    atomicMax(max_depth, depth);
+__global__ void ploc_merge_kernel(const PlocState* __restrict__ state, PlocLists lists, const int* __restrict__ nearest, uint32_t* __restrict__ keep,
+                                  BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
+    const int m = (int)state->m;
+    int* __restrict__ cl_link = lists.link[state->cur]; Aabb* __restrict__ cl_box = lists.box[state->cur]; int* __restrict__ cl_depth = lists.depth[state->cur];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        int j = nearest[i];
+        bool mutual = j >= 0 && nearest[j] == i;
+        if (!mutual) { keep[i] = 1u; continue; }
+        if (i > j) { keep[i] = 0u; continue; }
+        Aabb a = cl_box[i], b = cl_box[j];
+        int index = atomicAdd(node_counter, 1);
+        BvhNode out;
+        out.lo_l_hi_l_x = make_float4(a.lo.x, a.lo.y, a.lo.z, a.hi.x);
+        out.hi_l_lo_r = make_float4(a.hi.y, a.hi.z, b.lo.x, b.lo.y);
+        out.lo_r_hi_r = make_float4(b.lo.z, b.hi.x, b.hi.y, b.hi.z);
+        out.left = cl_link[i]; out.right = cl_link[j]; out.pad0 = 0; out.pad1 = 0;
+        nodes[index] = out;
+        Aabb merged; merged.lo = min3(a.lo, b.lo); merged.hi = max3(a.hi, b.hi);
+        int depth = max(cl_depth[i], cl_depth[j]) + 1;
+        // cluster j is only read by this thread (its own thread took the branch above), so updating slot i in place is race
+        // free: no other cluster has i or j as a MUTUAL partner, and non-mutual clusters only read `nearest`.
+        cl_box[i] = merged; cl_link[i] = index; cl_depth[i] = depth;
+        keep[i] = 1u;
+        atomicMax(max_depth, depth);
+    }
 }
 
-__global__ void ploc_compact_kernel(int m, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ position, const int* __restrict__ link_in,
-                                    const Aabb* __restrict__ box_in, const int* __restrict__ depth_in, int* __restrict__ link_out,
-                                    Aabb* __restrict__ box_out, int* __restrict__ depth_out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m || !keep[i]) return;
-    uint32_t c = position[i];
-    link_out[c] = link_in[i]; box_out[c] = box_in[i]; depth_out[c] = depth_in[i];
+__global__ void ploc_compact_kernel(const PlocState* __restrict__ state, PlocLists lists, const uint32_t* __restrict__ keep, const uint32_t* __restrict__ position) {
+    const int m = (int)state->m, cur = state->cur;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        if (!keep[i]) continue;
+        uint32_t c = position[i];
+        lists.link[cur ^ 1][c] = lists.link[cur][i]; lists.box[cur ^ 1][c] = lists.box[cur][i]; lists.depth[cur ^ 1][c] = lists.depth[cur][i];
+    }
+}
+
+// Ends a pass: the compacted list becomes the current one, and the loop goes on while more than PLOC_TAIL clusters are left.
+// `loop_handle`: the WHILE node of the build's graph when the passes run as one (has_handle), else the host reads the state.
+__global__ void ploc_advance_kernel(PlocState* __restrict__ state, const uint32_t* __restrict__ kept, cudaGraphConditionalHandle loop_handle, int has_handle) {
+    const uint32_t next_m = *kept;
+    if (next_m >= state->m || state->passes >= 4096) state->failed = 1; // cannot happen: the globally closest pair is always mutual
+    else { state->m = next_m; state->cur ^= 1; state->passes += 1; }
+    if (has_handle) cudaGraphSetConditional(loop_handle, (!state->failed && state->m > (uint32_t)PLOC_TAIL) ? 1u : 0u);
+}
+
+__global__ void ploc_begin_kernel(PlocState* __restrict__ state, uint32_t m, cudaGraphConditionalHandle loop_handle, int has_handle) {
+    state->m = m; state->cur = 0; state->passes = 0; state->failed = 0;
+    if (has_handle) cudaGraphSetConditional(loop_handle, m > (uint32_t)PLOC_TAIL ? 1u : 0u);
 }
 
 // The last PLOC_TAIL clusters finish inside one block: the same search / merge / compact passes as above on shared memory,
-// without a kernel launch and a host round trip per pass (the top of the tree takes ~50 passes that merge a few pairs each).
-constexpr int PLOC_TAIL = 1024;
-
-__global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int m, const int* __restrict__ cl_link, const Aabb* __restrict__ cl_box, const int* __restrict__ cl_depth,
+// without a kernel launch per pass (the top of the tree takes ~50 passes that merge a few pairs each).
+__global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(const PlocState* __restrict__ state, PlocLists lists,
                                                               BvhNode* __restrict__ nodes, int* __restrict__ node_counter, int* __restrict__ max_depth) {
+    const int m = (int)state->m;
+    if (state->failed || m > PLOC_TAIL) return;
+    const int* __restrict__ cl_link = lists.link[state->cur]; const Aabb* __restrict__ cl_box = lists.box[state->cur]; const int* __restrict__ cl_depth = lists.depth[state->cur];
     __shared__ Aabb s_box[PLOC_TAIL];
     __shared__ int s_link[PLOC_TAIL], s_depth[PLOC_TAIL], s_nearest[PLOC_TAIL];
     __shared__ int s_warp_sums[32];
@@ -647,13 +672,13 @@ int build_accel(Context* ctx) {
     DeviceBuffer<TreeNode> d_tree; DeviceBuffer<int> d_parent_internal, d_parent_leaf, d_arrival; DeviceBuffer<Aabb> d_leaf_boxes, d_node_boxes;
     // PLOC scratch
     DeviceBuffer<uint32_t> d_flag, d_pos; DeviceBuffer<int> d_link[2], d_depth[2], d_nearest, d_scalars; DeviceBuffer<Aabb> d_box[2];
-    DeviceBuffer<uint32_t> d_scan_temp, d_scan_total;
+    DeviceBuffer<uint32_t> d_scan_temp, d_scan_total; DeviceBuffer<PlocState> d_ploc_state;
     DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four- and eight-wide collapse
     DeviceBuffer<TraceTriangle> d_triangles_by_node;                 // the triangle array in the order of the eight-wide nodes
     const bool try_cw = ctx->use_cw && LEAF_MAX <= CW_MAX_LEAF_TRIANGLES;
     auto release_all = [&]() {
         d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); d_triangles_by_node.release();
-        d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release();
+        d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release(); d_ploc_state.release();
         for (int k = 0; k < 2; ++k) { d_link[k].release(); d_depth[k].release(); d_box[k].release(); }
         d_records.release(); d_bounds.release();
         d_keys.release(); d_keys_alt.release(); d_vals.release(); d_vals_alt.release(); d_temp.release();
@@ -687,7 +712,7 @@ int build_accel(Context* ctx) {
     if (try_ploc) {
         BUILD_CHECK(d_flag.resize(n)); BUILD_CHECK(d_pos.resize(n)); BUILD_CHECK(d_scalars.resize(2)); BUILD_CHECK(d_nearest.resize(n));
         for (int k = 0; k < 2; ++k) { BUILD_CHECK(d_link[k].resize(n)); BUILD_CHECK(d_depth[k].resize(n)); BUILD_CHECK(d_box[k].resize(n)); }
-        BUILD_CHECK(d_scan_temp.resize(sort::scan_scratch_words(n))); BUILD_CHECK(d_scan_total.resize(1));
+        BUILD_CHECK(d_scan_temp.resize(sort::scan_scratch_words(n))); BUILD_CHECK(d_scan_total.resize(1)); BUILD_CHECK(d_ploc_state.resize(1));
     }
     BUILD_CHECK(d_leaf_boxes.resize(std::max<size_t>(n, 1)));
     // every scratch buffer is allocated here, outside the timed region (cudaMalloc / cudaFree of gigabytes take tens of ms)
@@ -751,32 +776,83 @@ int build_accel(Context* ctx) {
                 int h_scalars[2] = { 1, 0 }; // next node index, deepest cluster
                 PLOC_CHECK(cudaMemcpyAsync(d_scalars.ptr, h_scalars, sizeof(h_scalars), cudaMemcpyHostToDevice, st));
                 ctx->counters.kernel_launches++;
-                int cur = 0, passes = 0;
-                bool failed = false;
-                while (m > PLOC_TAIL) {
-                    ploc_nearest_kernel<<<full_grid(m), block, 0, st>>>(m, d_box[cur].ptr, d_nearest.ptr);
-                    ploc_merge_kernel<<<full_grid(m), block, 0, st>>>(m, d_nearest.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, d_flag.ptr, A.nodes.ptr,
-                                                                     d_scalars.ptr, d_scalars.ptr + 1);
-                    sort::exclusive_scan(d_flag.ptr, d_pos.ptr, (uint32_t)m, nullptr, d_scan_temp.ptr, d_scan_total.ptr, ctx->sm_count, st);
-                    ploc_compact_kernel<<<full_grid(m), block, 0, st>>>(m, d_flag.ptr, d_pos.ptr, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr,
-                                                                       d_link[cur ^ 1].ptr, d_box[cur ^ 1].ptr, d_depth[cur ^ 1].ptr);
-                    PLOC_CHECK(cudaMemcpyAsync(&kept, d_scan_total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-                    PLOC_CHECK(cudaStreamSynchronize(st));
-                    ctx->counters.kernel_launches += 3 + sort::SCAN_LAUNCHES;
-                    int next_m = int(kept);
-                    if (next_m >= m || ++passes > 4096) { failed = true; break; } // cannot happen: the globally closest pair is always mutual
-                    if (getenv("BPT_PLOC_DEBUG")) fprintf(stderr, "ploc pass %d: %d -> %d clusters\n", passes, m, next_m);
-                    m = next_m; cur ^= 1;
+                // The passes follow each other on the device: one graph = begin -> WHILE (more than PLOC_TAIL clusters) { nearest,
+                // merge, scan, compact, advance }, the loop condition set by ploc_advance_kernel from the scan's grand total. (Round 1
+                // read that total back and synchronised once per pass: about half of the build time at 1 M triangles.) If the driver
+                // refuses the graph the same kernels run as stream launches with the host reading the state after every pass.
+                PlocLists lists = { { d_link[0].ptr, d_link[1].ptr }, { d_box[0].ptr, d_box[1].ptr }, { d_depth[0].ptr, d_depth[1].ptr } };
+                PlocState* state = d_ploc_state.ptr;
+                const int pass_grid = (int)std::min<int64_t>(full_grid(m), (int64_t)ctx->sm_count * 16);
+                auto enqueue_pass = [&](cudaStream_t stream, cudaGraphConditionalHandle handle, int has_handle) {
+                    ploc_nearest_kernel<<<pass_grid, block, 0, stream>>>(state, lists, d_nearest.ptr);
+                    ploc_merge_kernel<<<pass_grid, block, 0, stream>>>(state, lists, d_nearest.ptr, d_flag.ptr, A.nodes.ptr, d_scalars.ptr, d_scalars.ptr + 1);
+                    sort::exclusive_scan(d_flag.ptr, d_pos.ptr, (uint32_t)m, &state->m, d_scan_temp.ptr, d_scan_total.ptr, ctx->sm_count, stream);
+                    ploc_compact_kernel<<<pass_grid, block, 0, stream>>>(state, lists, d_flag.ptr, d_pos.ptr);
+                    ploc_advance_kernel<<<1, 1, 0, stream>>>(state, d_scan_total.ptr, handle, has_handle);
+                };
+                static const bool graphs_disabled = [] { const char* e = getenv("BPT_GRAPH"); return e && e[0] == '0'; }();
+                bool looped_on_device = false;
+                if (m > PLOC_TAIL && !graphs_disabled) {
+                    cudaGraph_t graph = nullptr; cudaGraphExec_t exec = nullptr;
+                    bool ok = cudaGraphCreate(&graph, 0) == cudaSuccess;
+                    cudaGraphConditionalHandle handle = 0;
+                    ok = ok && cudaGraphConditionalHandleCreate(&handle, graph, 1, cudaGraphCondAssignDefault) == cudaSuccess;
+                    cudaGraphNode_t begin = nullptr, loop = nullptr;
+                    if (ok) {
+                        uint32_t m0 = (uint32_t)m; int has_handle = 1;
+                        void* begin_args[] = { &state, &m0, &handle, &has_handle };
+                        cudaKernelNodeParams kp = {};
+                        kp.func = (void*)ploc_begin_kernel; kp.gridDim = dim3(1); kp.blockDim = dim3(1); kp.kernelParams = begin_args;
+                        ok = cudaGraphAddKernelNode(&begin, graph, nullptr, 0, &kp) == cudaSuccess;
+                    }
+                    if (ok) {
+                        cudaGraphNodeParams lp = {};
+                        lp.type = cudaGraphNodeTypeConditional;
+                        lp.conditional.handle = handle; lp.conditional.type = cudaGraphCondTypeWhile; lp.conditional.size = 1;
+                        ok = cudaGraphAddNode(&loop, graph, &begin, 1, &lp) == cudaSuccess;
+                        if (ok) { // the body: the launches of one pass, captured from a side stream into the loop's graph
+                            cudaGraph_t body = lp.conditional.phGraph_out[0];
+                            cudaStream_t capture = nullptr;
+                            ok = cudaStreamCreateWithFlags(&capture, cudaStreamNonBlocking) == cudaSuccess;
+                            if (ok) {
+                                ok = cudaStreamBeginCaptureToGraph(capture, body, nullptr, nullptr, 0, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                                if (ok) {
+                                    enqueue_pass(capture, handle, 1);
+                                    cudaGraph_t captured = nullptr;
+                                    ok = cudaStreamEndCapture(capture, &captured) == cudaSuccess;
+                                }
+                                cudaStreamDestroy(capture);
+                            }
+                        }
+                    }
+                    ok = ok && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+                    ok = ok && cudaGraphLaunch(exec, st) == cudaSuccess;
+                    if (ok) { looped_on_device = true; ctx->counters.kernel_launches += 1; }
+                    else cudaGetLastError(); // the stream launches below take over
+                    if (exec) { if (ok) cudaStreamSynchronize(st); cudaGraphExecDestroy(exec); }
+                    if (graph) cudaGraphDestroy(graph);
                 }
-                if (!failed) {
-                    ploc_tail_kernel<<<1, PLOC_TAIL, 0, st>>>(m, d_link[cur].ptr, d_box[cur].ptr, d_depth[cur].ptr, A.nodes.ptr, d_scalars.ptr, d_scalars.ptr + 1);
-                    ctx->counters.kernel_launches++;
+                PlocState h_state = { (uint32_t)m, 0, 0, 0 };
+                if (!looped_on_device) {
+                    ploc_begin_kernel<<<1, 1, 0, st>>>(state, (uint32_t)m, 0ull, 0);
+                    while (h_state.m > (uint32_t)PLOC_TAIL && !h_state.failed) {
+                        enqueue_pass(st, 0ull, 0);
+                        PLOC_CHECK(cudaMemcpyAsync(&h_state, state, sizeof(h_state), cudaMemcpyDeviceToHost, st));
+                        PLOC_CHECK(cudaStreamSynchronize(st));
+                        ctx->counters.kernel_launches += 4 + sort::SCAN_LAUNCHES;
+                        if (getenv("BPT_PLOC_DEBUG")) fprintf(stderr, "ploc pass %d: %u clusters\n", h_state.passes, h_state.m);
+                    }
                 }
+                ploc_tail_kernel<<<1, PLOC_TAIL, 0, st>>>(state, lists, A.nodes.ptr, d_scalars.ptr, d_scalars.ptr + 1);
+                ctx->counters.kernel_launches++;
+                PLOC_CHECK(cudaMemcpyAsync(&h_state, state, sizeof(h_state), cudaMemcpyDeviceToHost, st));
                 PLOC_CHECK(cudaMemcpyAsync(h_scalars, d_scalars.ptr, sizeof(h_scalars), cudaMemcpyDeviceToHost, st));
                 PLOC_CHECK(cudaStreamSynchronize(st));
-                if (!failed && h_scalars[1] <= PLOC_MAX_DEPTH) {
+                if (!h_state.failed && h_state.m <= (uint32_t)PLOC_TAIL && h_scalars[1] <= PLOC_MAX_DEPTH) {
                     A.node_count = h_scalars[0];
-                    A.ploc_passes = passes; A.ploc_depth = h_scalars[1];
+                    A.ploc_passes = h_state.passes; A.ploc_depth = h_scalars[1];
+                    A.ploc_on_device = looped_on_device;
+                    if (looped_on_device) ctx->counters.kernel_launches += (uint64_t)h_state.passes * (4 + sort::SCAN_LAUNCHES);
                     ploc_done = true;
                 }
             }

@@ -52,6 +52,7 @@ static __global__ void __launch_bounds__(BLOCK) scan_reduce_kernel(const uint32_
                                                             uint32_t* __restrict__ tile_sums, uint32_t tiles) {
     __shared__ uint32_t warp_sums[32];
     n = element_count(n, count_ptr);
+    tiles = min(tiles, (n + SCAN_TILE - 1) / SCAN_TILE); // a count from device memory can be far below the capacity the launch is sized for
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
         uint32_t sum = 0;
@@ -64,8 +65,10 @@ static __global__ void __launch_bounds__(BLOCK) scan_reduce_kernel(const uint32_
 }
 
 // One CTA: exclusive scan of the tile sums in place; the grand total goes to total_out (if given).
-static __global__ void __launch_bounds__(BLOCK) scan_spine_kernel(uint32_t* __restrict__ tile_sums, uint32_t tiles, uint32_t* __restrict__ total_out) {
+static __global__ void __launch_bounds__(BLOCK) scan_spine_kernel(uint32_t* __restrict__ tile_sums, uint32_t tiles, uint32_t* __restrict__ total_out,
+                                                                  uint32_t n, const uint32_t* __restrict__ count_ptr) {
     __shared__ uint32_t warp_sums[32];
+    tiles = min(tiles, (element_count(n, count_ptr) + SCAN_TILE - 1) / SCAN_TILE);
     uint32_t carry = 0;
     for (uint32_t base = 0; base < tiles; base += BLOCK) {
         const uint32_t i = base + threadIdx.x;
@@ -82,6 +85,7 @@ static __global__ void __launch_bounds__(BLOCK) scan_apply_kernel(const uint32_t
                                                            const uint32_t* __restrict__ count_ptr, const uint32_t* __restrict__ tile_offsets, uint32_t tiles) {
     __shared__ uint32_t warp_sums[32];
     n = element_count(n, count_ptr);
+    tiles = min(tiles, (n + SCAN_TILE - 1) / SCAN_TILE);
     for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         const uint32_t base = tile * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
         uint32_t v[SCAN_ITEMS];
@@ -107,7 +111,7 @@ inline void exclusive_scan(const uint32_t* in, uint32_t* out, uint32_t n, const 
     if (tiles == 0) { if (total_out) cudaMemsetAsync(total_out, 0, sizeof(uint32_t), stream); return; }
     const int grid = (int)(tiles < (uint32_t)sm_count * 8u ? tiles : (uint32_t)sm_count * 8u);
     scan_reduce_kernel<<<grid, BLOCK, 0, stream>>>(in, n, count_ptr, scratch, tiles);
-    scan_spine_kernel<<<1, BLOCK, 0, stream>>>(scratch, tiles, total_out);
+    scan_spine_kernel<<<1, BLOCK, 0, stream>>>(scratch, tiles, total_out, n, count_ptr);
     scan_apply_kernel<<<grid, BLOCK, 0, stream>>>(in, out, n, count_ptr, scratch, tiles);
 }
 constexpr int SCAN_LAUNCHES = 3;
