@@ -350,7 +350,7 @@ int bpt_create(int cuda_device, bpt_ctx** out_ctx) {
     ctx->device = cuda_device;
     if (const char* bvh = getenv("BPT_BVH")) ctx->use_ploc = strcmp(bvh, "lbvh") != 0;
     if (const char* wide = getenv("BPT_WIDE")) ctx->use_wide = strcmp(wide, "0") != 0;
-    if (const char* cw = getenv("BPT_CW")) ctx->use_cw = strcmp(cw, "0") != 0;
+    if (const char* cw = getenv("BPT_CW")) ctx->cw_min_triangles = strcmp(cw, "0") != 0 ? 0 : INT64_MAX;
     if (const char* sort_hits = getenv("BPT_SORT_HITS")) ctx->sort_hits_from_iteration = atoi(sort_hits);
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cuda_device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;

@@ -675,7 +675,7 @@ int build_accel(Context* ctx) {
     DeviceBuffer<uint32_t> d_scan_temp, d_scan_total; DeviceBuffer<PlocState> d_ploc_state;
     DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four- and eight-wide collapse
     DeviceBuffer<TraceTriangle> d_triangles_by_node;                 // the triangle array in the order of the eight-wide nodes
-    const bool try_cw = ctx->use_cw && LEAF_MAX <= CW_MAX_LEAF_TRIANGLES;
+    const bool try_cw = prim_total >= ctx->cw_min_triangles && LEAF_MAX <= CW_MAX_LEAF_TRIANGLES;
     auto release_all = [&]() {
         d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); d_triangles_by_node.release();
         d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release(); d_ploc_state.release();

@@ -214,8 +214,9 @@ int bpt_build_accel(bpt_ctx* ctx);
 int bpt_accel_info(bpt_ctx* ctx, int64_t* triangle_count, int64_t* node_count, float* build_ms);
 /* Which node format the rays of the last build traverse: *kind = 8 compressed eight-wide nodes (80 bytes, quantised child
  * boxes), 4 = four-wide nodes (128 bytes), 2 = the binary nodes (64 bytes); their number and the depth of that tree. The
- * build picks the widest format whose traversal stack the tree's depth fits; BPT_CW=0 / BPT_WIDE=0 in the environment
- * rule the first two out (A/B measurements). OptiX keeps this choice to itself (rtAccelerationSetBuilder "Trbvh",
+ * build takes the eight-wide nodes from 131 072 triangles on (below that the four-wide ones measure faster) and falls back
+ * to the next narrower format when the tree is too deep for a format's traversal stack; BPT_CW=1 / BPT_CW=0 / BPT_WIDE=0 in
+ * the environment force or rule out formats (A/B measurements, tests). OptiX keeps this choice to itself (rtAccelerationSetBuilder "Trbvh",
  * Renderer.cpp:161-182), so there is no reference counterpart. */
 int bpt_accel_hierarchy(bpt_ctx* ctx, int* kind, int64_t* node_count, int* levels);
 

@@ -33,7 +33,8 @@ def render_both(bpt, scene, width, height, spp, first=0, **settings):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_cornell_box_matches_oracle_sample_for_sample(bpt):
+def test_cornell_box_matches_oracle_sample_for_sample(tracer):
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(32, 16))
     w = h = 96
     gpu, cpu, counters, oc = render_both(bpt, scene, w, h, 6)
@@ -85,8 +86,9 @@ def test_background_color_only(bpt):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_vertex_tints_coverage_and_light_types(bpt):
+def test_vertex_tints_coverage_and_light_types(tracer):
     """Per-vertex tint/roughness, stochastic coverage, emission, spot + directional lights and instance rotation."""
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(16, 8))
     rng = np.random.default_rng(3)
     sphere = scene["meshes"][1]

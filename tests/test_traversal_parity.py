@@ -60,7 +60,8 @@ def test_oracle_flatten_matches_numpy():
 @pytest.mark.gpu
 @needs_oracle
 @pytest.mark.parametrize("n_tris,seed", [(1, 3), (2, 4), (5, 5), (4000, 6), (50000, 7)])
-def test_closest_hit_bit_exact_vs_brute_force(bpt, n_tris, seed):
+def test_closest_hit_bit_exact_vs_brute_force(tracer, n_tris, seed):
+    bpt = tracer
     scene = soup_scene(n_tris, seed)
     scenes.upload(bpt, scene)
     info = bpt.accel_info()
@@ -90,7 +91,8 @@ def test_closest_hit_bit_exact_vs_brute_force(bpt, n_tris, seed):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_interval_and_occlusion_semantics(bpt):
+def test_interval_and_occlusion_semantics(tracer):
+    bpt = tracer
     scene = soup_scene(2000, 11)
     scenes.upload(bpt, scene)
     sc = oracle_lib.OracleScene(scene)
@@ -112,7 +114,8 @@ def test_interval_and_occlusion_semantics(bpt):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_cornell_box_instances_and_flattening(bpt):
+def test_cornell_box_instances_and_flattening(tracer):
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(40, 20))
     scenes.upload(bpt, scene)
     sc = oracle_lib.OracleScene(scene)
@@ -141,17 +144,17 @@ def test_empty_scene_misses_everything(bpt):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("environment,node_width", [({"BPT_CW": "0"}, 4), ({"BPT_CW": "0", "BPT_WIDE": "0"}, 2), ({"BPT_BVH": "lbvh"}, 8),
-                                                    ({"BPT_BVH": "lbvh", "BPT_CW": "0"}, 4)])
+@pytest.mark.parametrize("environment,node_width", [({"BPT_CW": "1"}, 8), ({"BPT_CW": "0", "BPT_WIDE": "0"}, 2), ({"BPT_BVH": "lbvh"}, 4),
+                                                    ({"BPT_BVH": "lbvh", "BPT_CW": "1"}, 8)])
 def test_every_hierarchy_returns_the_same_hits(bpt, environment, node_width, monkeypatch):
-    """The compressed eight-wide PLOC hierarchy (default), the four-wide nodes (BPT_CW=0: the fallback for trees too deep for
-    the eight-wide stack), the binary nodes (BPT_WIDE=0 as well: the fallback of that) and the plain Morton hierarchy
-    (BPT_BVH=lbvh: the fallback when PLOC gives up) must return identical hits: the result is defined by
+    """The four-wide PLOC hierarchy (what a scene of this size gets), the compressed eight-wide nodes (BPT_CW=1: what scenes
+    from 131 072 triangles on get), the binary nodes (the fallback for trees too deep for either stack) and the plain Morton
+    hierarchy (BPT_BVH=lbvh: the fallback when PLOC gives up) must return identical hits: the result is defined by
     min (t, primitive id), not by the traversal order."""
     scene = soup_scene(20000, 11, size=0.08)
     o, d = random_rays(60000, 12)
     scenes.upload(bpt, scene)
-    assert bpt.accel_info()["node_width"] == 8
+    assert bpt.accel_info()["node_width"] == 4
     want = bpt.intersect(o, d)
     for variable, value in environment.items():
         monkeypatch.setenv(variable, value)
@@ -167,7 +170,7 @@ def test_every_hierarchy_returns_the_same_hits(bpt, environment, node_width, mon
 
 @pytest.mark.gpu
 @needs_oracle
-def test_degenerate_geometry_ties_and_large_coordinates(bpt):
+def test_degenerate_geometry_ties_and_large_coordinates(tracer):
     """Coincident triangles (exact ties in t resolve to the lower primitive id), zero-area triangles (never hit, must not
     break the build), identical centroids (equal Morton codes) and a scene 10 km from the origin, bit exact vs brute force."""
     rng = np.random.default_rng(31)
@@ -182,6 +185,7 @@ def test_degenerate_geometry_ties_and_large_coordinates(bpt):
     mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
     scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
              "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
+    bpt = tracer
     scenes.upload(bpt, scene)
     sc = oracle_lib.OracleScene(scene)
     o, d = random_rays(60000, 33)
@@ -244,7 +248,7 @@ def test_material_grid_980k_triangles_bit_exact(bpt):
     scene = scenes.material_grid()
     scenes.upload(bpt, scene)
     sc = oracle_lib.OracleScene(scene)
-    assert bpt.accel_info()["triangles"] == sc.triangle_count() == 980002
+    assert bpt.accel_info()["triangles"] == sc.triangle_count() == 980002 and bpt.accel_info()["node_width"] == 8
     scene["bounds"] = scene_bounds(sc)
     o, d = camera_and_bounce_rays(scene, 1 << 20, 21)
     gp, gt, guv, gocc = bpt.intersect(o, d)
@@ -304,7 +308,7 @@ def deep_hierarchy_rays(n, seed):
 
 @pytest.mark.gpu
 @needs_oracle
-@pytest.mark.parametrize("environment", [{}, {"BPT_CW": "0"}])
+@pytest.mark.parametrize("environment", [{"BPT_CW": "1"}, {"BPT_CW": "0"}])
 def test_deep_hierarchy_uses_the_spill_stack(environment, monkeypatch):
     """Forces traversal stacks deeper than the 32 shared-memory entries of the four-wide traversal (the local-memory spill
     part; BPT_CW=0) and checks the result against brute force, for closest-hit and for any-hit rays through partially
@@ -319,7 +323,7 @@ def test_deep_hierarchy_uses_the_spill_stack(environment, monkeypatch):
     scene = {"meshes": {0: mesh}, "materials": mats, "instances": np.array([scenes._instance(0, 1, scenes.affine())], capi.INSTANCE_DTYPE),
              "lights": np.zeros(0, capi.LIGHT_DTYPE), "environment": {"tint": (0, 0, 0)}}
     scenes.upload(bpt, scene)
-    assert bpt.accel_info()["node_width"] == (4 if environment else 8)
+    assert bpt.accel_info()["node_width"] == (8 if environment["BPT_CW"] == "1" else 4)
     sc = oracle_lib.OracleScene(scene)
     o, d = deep_hierarchy_rays(20000, 31)
     bpt.counters(reset=True)
@@ -349,9 +353,10 @@ def nested_clusters(count=150, growth=1.15, per_cluster=5):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_deep_hierarchy_of_inner_nodes(bpt):
+def test_deep_hierarchy_of_inner_nodes(bpt8):
     """A chain whose links are inner nodes (see nested_clusters): whichever node format the build settles on for its depth,
     closest hits and transmissions equal brute force and no push is dropped."""
+    bpt = bpt8
     mesh = nested_clusters()
     mats = np.array([scenes.material((0, 0, 0), 0.0), scenes.material((0.5, 0.5, 0.5), 0.5)], capi.MATERIAL_DTYPE)
     mats[1]["coverage"] = 0.01
