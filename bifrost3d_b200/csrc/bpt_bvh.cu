@@ -618,7 +618,7 @@ template <bool ANY_HIT, bool COMPRESSED>
 __global__ void __launch_bounds__(TRACE_BLOCK) intersect_kernel(AccelView accel, unsigned int n, BatchSource source, const float* __restrict__ coverage,
                                                                 unsigned int* fetch_counter) {
     __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
-    typedef typename std::conditional<COMPRESSED, TraversalCW<ANY_HIT>, Traversal<ANY_HIT>>::type Trav;
+    typedef typename TraversalFor<ANY_HIT, COMPRESSED>::type Trav;
     traverse_queue_with<ANY_HIT, Trav>(accel, coverage, source, n, fetch_counter, s_stack + threadIdx.x, accel.budget);
 }
 

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) extend_kern
     const unsigned int count = w.counters->active;
     ExtendSource<SORT_HITS> source = { w, w.counters->parity ? w.queue_b : w.queue_a, s.lights, s.analytic_light_count, s.split_by_shading_model ? s.shade : nullptr, s.materials,
                             SORT_HITS && sorting_now(w.counters, f.sort_hits_from_iteration), s.shade, s.slot_of_primitive, s.material_class, s.sort_cell_shift };
-    typedef typename std::conditional<COMPRESSED, TraversalCW<false>, Traversal<false>>::type Trav;
+    typedef typename TraversalFor<false, COMPRESSED>::type Trav;
     traverse_queue_with<false, Trav>(s.accel, s.coverage, source, count, &w.counters->fetch_extend, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters, (unsigned long long)count);
 }
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, BPT_TRACE_MIN_BLOCKS) shadow_kern
     __shared__ __align__(16) int s_stack[STACK_SMEM * TRACE_BLOCK];
     const unsigned int count = w.counters->shadow[w.counters->parity ^ 1u]; // filled by the previous iteration's shade kernels
     ShadowSource source = { w };
-    typedef typename std::conditional<COMPRESSED, TraversalCW<true>, Traversal<true>>::type Trav;
+    typedef typename TraversalFor<true, COMPRESSED>::type Trav;
     traverse_queue_with<true, Trav>(s.accel, s.coverage, source, count, &w.counters->fetch_shadow, s_stack + threadIdx.x, s.accel.budget);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(w.ray_counters + 1, (unsigned long long)count);
 }

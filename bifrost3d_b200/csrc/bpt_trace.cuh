@@ -406,6 +406,10 @@ struct Traversal {
 //   lanes then test their triangles together. Measured on B200 (configs[2] / configs[1], Msamples/s): no speculation
 //   603 / 479, one parked group and then wait 691 / 500, unbounded (this) 703 / 504; ending the node loop while 3 / 6 / 10
 //   lanes are still searching 698 / 696 / 690 on configs[2].
+// * Measured and dropped: triangle tests shared by the warp (the (ray, triangle) pairs of all lanes listed in shared memory and
+//   dealt out 32 at a time, also to lanes without a ray; owners fold the results in list order). Bit-exact, 60 parity tests
+//   green, and slower: configs[2] 704 -> 662, configs[3] 580 -> 542 Msamples/s (closest-hit kernel 1.78 -> 1.81 ms, any-hit
+//   0.92 -> 0.96): the prefix sum, the list, two barriers per round and the fold loop cost what the wider tests return.
 constexpr int CW_STACK_SMEM = STACK_SMEM / 2;  // 8-byte entries in the same shared memory as Traversal's 4-byte ones
 constexpr int CW_STACK_LOCAL = 48;             // bpt_bvh.cu only hands out trees with 2 * levels + 2 <= CW_STACK_SMEM + CW_STACK_LOCAL
 
@@ -551,6 +555,10 @@ struct TraversalCW {
         return h;
     }
 };
+
+// The traversal a kernel instantiated for a node format runs.
+template <bool ANY_HIT, bool COMPRESSED> struct TraversalFor { typedef Traversal<ANY_HIT> type; };
+template <bool ANY_HIT> struct TraversalFor<ANY_HIT, true> { typedef TraversalCW<ANY_HIT> type; };
 
 // Persistent-thread driver. `Trav` is Traversal<ANY_HIT> or TraversalCW<ANY_HIT>. `Source` supplies rays and consumes results:
 //   void load(unsigned int index, Ray& ray, int& skip_primitive)
