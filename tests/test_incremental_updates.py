@@ -19,7 +19,8 @@ def fresh_render(scene, size=(48, 40), spp=3):
     return img
 
 
-def test_material_edit_keeps_the_acceleration_structure(bpt):
+def test_material_edit_keeps_the_acceleration_structure(tracer):
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(16, 8))
     scenes.upload(bpt, scene)
     bpt.render(scene["camera"], 48, 40, 0, 3, reset=True)
@@ -36,7 +37,8 @@ def test_material_edit_keeps_the_acceleration_structure(bpt):
     assert np.array_equal(after, fresh_render(edited))
 
 
-def test_transform_edit_rebuilds_from_resident_meshes(bpt):
+def test_transform_edit_rebuilds_from_resident_meshes(tracer):
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(16, 8))
     scenes.upload(bpt, scene)
     inst = scene["instances"].copy()

@@ -116,8 +116,9 @@ def test_vertex_tints_coverage_and_light_types(tracer):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_environment_map_importance_sampling_and_mis(bpt):
+def test_environment_map_importance_sampling_and_mis(tracer):
     """configs[2] in small: material grid lit only by an HDR environment (presampled NEE + MIS on escaped rays)."""
+    bpt = tracer
     scene = scenes.material_grid(96, 54, grid=3, sphere_quads=(24, 12), env_size=(256, 128), env_samples=512)
     gpu, cpu, counters, oc = render_both(bpt, scene, 96, 54, 6)
     assert cpu.mean() > 0.01
@@ -145,9 +146,10 @@ def test_instanced_terrain_small(bpt):
 
 
 @pytest.mark.gpu
-def test_aov_backends_on_a_tinted_quad(bpt):
+def test_aov_backends_on_a_tinted_quad(tracer):
     """RendererTest.h:155-172 in Python: an orthographic view of a quad whose vertex tints encode the pixel position; plus
     roughness, shading normal and depth of the same quad."""
+    bpt = tracer
     w, h = 8, 6
     mesh = {"indices": np.array([[0, 1, 2], [1, 2, 3]], np.uint32),
             "positions": np.array([[-0.5 * w, -0.5 * h, 1], [-0.5 * w, 0.5 * h, 1], [0.5 * w, -0.5 * h, 1], [0.5 * w, 0.5 * h, 1]], np.float32),
@@ -198,9 +200,10 @@ def test_diffuse_shading_model_matches_oracle(bpt):
 
 @pytest.mark.gpu
 @needs_oracle
-def test_transmissive_shading_model_matches_oracle(bpt):
+def test_transmissive_shading_model_matches_oracle(tracer):
     """ShadingModel::Transmissive (transmissive_closest_hit, MonteCarlo.cu:259-268): a frosted and a smooth glass sphere in
     the Cornell box; paths enter and leave the medium, refract through both interfaces and pick up the tinted transmission."""
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(24, 12))
     mats = scene["materials"].copy()
     mats[4] = scenes.material((0.95, 0.97, 0.95), 0.2, 0.04); mats[4]["shading_model"] = 2
@@ -423,9 +426,10 @@ def test_environment_cdf_next_event_estimation(bpt):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("from_iteration", [0, 1])
-def test_hit_sorting_does_not_change_the_image(bpt, from_iteration):
+def test_hit_sorting_does_not_change_the_image(tracer, from_iteration):
     """Sorting the surface hits by (shading class, hit cell) before shading only changes which paths share a warp: the
     accumulated image is bit for bit the unsorted one, with mixed shading classes (Default, Diffuse, coat) in the scene."""
+    bpt = tracer
     scene = scenes.cornell_box(sphere_quads=(32, 16))
     mats = scene["materials"].copy()
     mats[5]["coat"] = 65535; mats[5]["coat_roughness"] = 20000

@@ -101,9 +101,10 @@ def textured_cornell():
 
 @pytest.mark.gpu
 @needs_oracle
-def test_textured_materials_match_oracle(bpt):
+def test_textured_materials_match_oracle(tracer):
     """Tint/roughness (sRGB RGBA8), roughness + metallic (Alpha8), partial coverage and cutout textures: closest hit,
     stochastic coverage and the shadow any-hit all read them (MonteCarlo.cu:152-164, 278-285)."""
+    bpt = tracer
     scene = textured_cornell()
     gpu, cpu, counters, oc = render_both(bpt, scene, 96, 96, 6)
     assert np.isfinite(gpu).all() and cpu.mean() > 0.01
