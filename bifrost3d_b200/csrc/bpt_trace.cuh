@@ -410,6 +410,8 @@ struct Traversal {
 //   dealt out 32 at a time, also to lanes without a ray; owners fold the results in list order). Bit-exact, 60 parity tests
 //   green, and slower: configs[2] 704 -> 662, configs[3] 580 -> 542 Msamples/s (closest-hit kernel 1.78 -> 1.81 ms, any-hit
 //   0.92 -> 0.96): the prefix sum, the list, two barriers per round and the fold loop cost what the wider tests return.
+//   Also dropped: prefetch.global.L2 of a found group's first (and last) triangle at the end of the node visit: configs[3]
+//   579 -> 574 (568), configs[2] 703 -> 696 (693).
 constexpr int CW_STACK_SMEM = STACK_SMEM / 2;  // 8-byte entries in the same shared memory as Traversal's 4-byte ones
 constexpr int CW_STACK_LOCAL = 48;             // bpt_bvh.cu only hands out trees with 2 * levels + 2 <= CW_STACK_SMEM + CW_STACK_LOCAL
 
