@@ -116,7 +116,7 @@ struct Accel {
     int64_t node_count = 0;
     float build_ms = 0.0f;
     int ploc_passes = 0, ploc_depth = 0;        // 0 when the plain LBVH hierarchy is in use
-    bool ploc_on_device = false;                // the PLOC passes ran as one graph with a device-side loop condition
+    bool ploc_on_device = false;                // the PLOC passes ran inside one cooperative launch
     float3 scene_lo, scene_hi;
     bool valid = false;
 };

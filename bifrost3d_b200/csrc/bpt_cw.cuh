@@ -138,27 +138,40 @@ BPT_HD void cw_encode(int count, const float3* lo, const float3* hi, const int* 
     for (int i = 1; i < count; ++i) { nlo = min3(nlo, lo[i]); nhi = max3(nhi, hi[i]); }
 
     // Octant slots: greedily hand the (child, slot) pair with the largest projection of the child's centre (relative to the
-    // node's) on the slot's diagonal its slot. Bit 4 / 2 / 1 of a slot = the +x / +y / +z side.
+    // node's) on the slot's diagonal its slot. Bit 4 / 2 / 1 of a slot = the +x / +y / +z side. (All loops run over the full
+    // width with masks, so that they unroll and the 8 x 8 projections stay in registers: with loops over `count` the build
+    // kernel kept them in local memory and spent 43 us per tree level on this function.)
     float cost[CW_WIDTH][CW_WIDTH];
-    for (int i = 0; i < count; ++i) {
-        const float cx = (lo[i].x + hi[i].x) - (nlo.x + nhi.x), cy = (lo[i].y + hi[i].y) - (nlo.y + nhi.y), cz = (lo[i].z + hi[i].z) - (nlo.z + nhi.z);
+#pragma unroll
+    for (int i = 0; i < CW_WIDTH; ++i) {
+        const int c = i < count ? i : 0;
+        const float cx = (lo[c].x + hi[c].x) - (nlo.x + nhi.x), cy = (lo[c].y + hi[c].y) - (nlo.y + nhi.y), cz = (lo[c].z + hi[c].z) - (nlo.z + nhi.z);
+#pragma unroll
         for (int s = 0; s < CW_WIDTH; ++s)
             cost[i][s] = ((s & 4) ? cx : -cx) + ((s & 2) ? cy : -cy) + ((s & 1) ? cz : -cz);
     }
     uint32_t child_free = (1u << count) - 1u, slot_free = 0xffu;
     int child_in_slot[CW_WIDTH];
+#pragma unroll
     for (int s = 0; s < CW_WIDTH; ++s) child_in_slot[s] = -1;
-    for (int round = 0; round < count; ++round) {
-        int best_child = -1, best_slot = -1; float best = 0.0f;
-        for (int i = 0; i < count; ++i) {
-            if (!(child_free >> i & 1u)) continue;
-            for (int s = 0; s < CW_WIDTH; ++s) {
-                if (!(slot_free >> s & 1u)) continue;
-                if (best_child < 0 || cost[i][s] > best) { best = cost[i][s]; best_child = i; best_slot = s; }
-            }
+#pragma unroll
+    for (int round = 0; round < CW_WIDTH; ++round) {
+        if (round < count) {
+            int best_pair = -1; float best = 0.0f; // pair = child * 8 + slot
+#pragma unroll
+            for (int i = 0; i < CW_WIDTH; ++i)
+#pragma unroll
+                for (int s = 0; s < CW_WIDTH; ++s) {
+                    const bool open = (child_free >> i & 1u) && (slot_free >> s & 1u);
+                    if (open && (best_pair < 0 || cost[i][s] > best)) { best = cost[i][s]; best_pair = i * CW_WIDTH + s; }
+                }
+            const int best_child = best_pair >> 3, best_slot = best_pair & 7;
+            child_free &= ~(1u << best_child); slot_free &= ~(1u << best_slot);
+#pragma unroll
+            for (int s = 0; s < CW_WIDTH; ++s) if (s == best_slot) child_in_slot[s] = best_child;
+#pragma unroll
+            for (int i = 0; i < CW_WIDTH; ++i) if (i == best_child) placement.slot[i] = best_slot;
         }
-        child_free &= ~(1u << best_child); slot_free &= ~(1u << best_slot);
-        child_in_slot[best_slot] = best_child; placement.slot[best_child] = best_slot;
     }
 
     const uint32_t bx = cw_scale_exponent(cw_sub_up(nhi.x, nlo.x)), by = cw_scale_exponent(cw_sub_up(nhi.y, nlo.y)), bz = cw_scale_exponent(cw_sub_up(nhi.z, nlo.z));
