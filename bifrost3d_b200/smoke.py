@@ -34,4 +34,23 @@ def run():
         assert frac < 1e-3
     else:
         print("smoke: oracle/_ref not available, rendered without comparison")
+    # 3. the same render through the compressed eight-wide nodes (what scenes from 131 072 triangles on get): closest hits are a
+    #    minimum over (t, primitive), so the image must not depend on the node format
+    import os
+    before = os.environ.get("BPT_CW")
+    os.environ["BPT_CW"] = "1"
+    try:
+        wide = b.Bpt(0)
+    finally:
+        if before is None:
+            del os.environ["BPT_CW"]
+        else:
+            os.environ["BPT_CW"] = before
+    scenes.upload(wide, scene)
+    assert wide.accel_info()["node_width"] == 8 and ctx.accel_info()["node_width"] == 4
+    wide.render(scene["camera"], 64, 64, 0, 4, reset=True)
+    same = np.array_equal(wide.resolve_float4()[..., :3], gpu)
+    print(f"smoke: eight-wide nodes render the same image as four-wide ones: {same}")
+    assert same
+    wide.close()
     ctx.close()
