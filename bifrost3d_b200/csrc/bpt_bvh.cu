@@ -20,6 +20,8 @@ namespace {
 
 #ifndef BPT_LEAF_MAX
 #define BPT_LEAF_MAX 2
+#else
+#define BPT_LEAF_MAX_FORCED 1
 #endif
 constexpr int LEAF_MAX = BPT_LEAF_MAX;
 
@@ -245,7 +247,7 @@ __global__ void fit_kernel(int n, const uint32_t* __restrict__ sorted_prims, con
     }
 }
 
-__global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
+__global__ void emit_kernel(int n, int leaf_max, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
                             BvhNode* __restrict__ nodes) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
@@ -260,7 +262,7 @@ __global__ void emit_kernel(int n, const TreeNode* __restrict__ tree, const Aabb
             TreeNode c = tree[child[k]];
             int size = c.last - c.first + 1;
             box[k] = node_boxes[child[k]];
-            link[k] = size <= LEAF_MAX ? pack_leaf(c.first, size) : child[k];
+            link[k] = size <= leaf_max ? pack_leaf(c.first, size) : child[k];
         }
     }
     BvhNode out;
@@ -284,34 +286,34 @@ constexpr int PLOC_RADIUS = BPT_PLOC_RADIUS;
 constexpr int PLOC_MAX_DEPTH = 96; // the traversal stack holds STACK_SMEM + STACK_LOCAL = 104 entries
 constexpr int PLOC_TAIL = 1024;    // the last clusters finish inside one block (ploc_tail_kernel)
 
-__device__ __forceinline__ bool is_leaf_cluster_child(const TreeNode* __restrict__ tree, int child, int& first, int& size) {
+__device__ __forceinline__ bool is_leaf_cluster_child(const TreeNode* __restrict__ tree, int child, int leaf_max, int& first, int& size) {
     if (child < 0) { first = ~child; size = 1; return true; }
     TreeNode c = tree[child];
     first = c.first; size = c.last - c.first + 1;
-    return size <= LEAF_MAX;
+    return size <= leaf_max;
 }
 
 // flag[p] = 1 where a leaf cluster starts (p = position in the sorted triangle array).
-__global__ void ploc_mark_kernel(int n, const TreeNode* __restrict__ tree, uint32_t* __restrict__ flag) {
+__global__ void ploc_mark_kernel(int n, int leaf_max, const TreeNode* __restrict__ tree, uint32_t* __restrict__ flag) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     TreeNode tn = tree[i];
-    if (i != 0 && tn.last - tn.first + 1 <= LEAF_MAX) return; // inside a leaf cluster
+    if (i != 0 && tn.last - tn.first + 1 <= leaf_max) return; // inside a leaf cluster
     int first, size;
-    if (is_leaf_cluster_child(tree, tn.left, first, size)) flag[first] = 1u;
-    if (is_leaf_cluster_child(tree, tn.right, first, size)) flag[first] = 1u;
+    if (is_leaf_cluster_child(tree, tn.left, leaf_max, first, size)) flag[first] = 1u;
+    if (is_leaf_cluster_child(tree, tn.right, leaf_max, first, size)) flag[first] = 1u;
 }
 
-__global__ void ploc_gather_kernel(int n, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
+__global__ void ploc_gather_kernel(int n, int leaf_max, const TreeNode* __restrict__ tree, const Aabb* __restrict__ leaf_boxes, const Aabb* __restrict__ node_boxes,
                                    const uint32_t* __restrict__ position, int* __restrict__ cl_link, Aabb* __restrict__ cl_box, int* __restrict__ cl_depth) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     TreeNode tn = tree[i];
-    if (i != 0 && tn.last - tn.first + 1 <= LEAF_MAX) return;
+    if (i != 0 && tn.last - tn.first + 1 <= leaf_max) return;
     int child[2] = { tn.left, tn.right };
     for (int k = 0; k < 2; ++k) {
         int first, size;
-        if (!is_leaf_cluster_child(tree, child[k], first, size)) continue;
+        if (!is_leaf_cluster_child(tree, child[k], leaf_max, first, size)) continue;
         uint32_t c = position[first];
         cl_link[c] = pack_leaf(first, size);
         cl_box[c] = child[k] < 0 ? leaf_boxes[~child[k]] : node_boxes[child[k]];
@@ -753,7 +755,15 @@ int build_accel(Context* ctx) {
     DeviceBuffer<uint32_t> d_scan_temp, d_scan_total, d_block_counts; DeviceBuffer<PlocState> d_ploc_state;
     DeviceBuffer<WideTask> d_tasks[2]; DeviceBuffer<int> d_counters; // four- and eight-wide collapse
     DeviceBuffer<TraceTriangle> d_triangles_by_node;                 // the triangle array in the order of the eight-wide nodes
-    const bool try_cw = prim_total >= ctx->cw_min_triangles && LEAF_MAX <= CW_MAX_LEAF_TRIANGLES;
+    // Leaf clusters: at most two triangles; one on the scenes of the large-scene regime (bpt_trace.cuh: more than 8 M triangles),
+    // where tighter leaves measure 2.8 % faster (50 M triangles: 596 against 580 Msamples/s) for 70 % more nodes and a 19 %
+    // longer build. BPT_LEAF_MAX at compile time overrides both.
+#ifdef BPT_LEAF_MAX_FORCED
+    const int leaf_max = LEAF_MAX;
+#else
+    const int leaf_max = prim_total > 8000000ll ? 1 : LEAF_MAX;
+#endif
+    const bool try_cw = prim_total >= ctx->cw_min_triangles && leaf_max <= CW_MAX_LEAF_TRIANGLES;
     auto release_all = [&]() {
         d_tasks[0].release(); d_tasks[1].release(); d_counters.release(); d_triangles_by_node.release();
         d_flag.release(); d_pos.release(); d_nearest.release(); d_scalars.release(); d_scan_temp.release(); d_scan_total.release(); d_block_counts.release(); d_ploc_state.release();
@@ -786,7 +796,7 @@ int build_accel(Context* ctx) {
     BUILD_CHECK(A.slot_of_primitive.resize(std::max<size_t>(n, 1)));
     BUILD_CHECK(A.nodes.resize((size_t)n + 1));
     // PLOC scratch is sized for the worst case of one cluster per triangle and allocated outside the timed region.
-    const bool try_ploc = ctx->use_ploc && n > LEAF_MAX;
+    const bool try_ploc = ctx->use_ploc && n > leaf_max;
     if (try_ploc) {
         BUILD_CHECK(d_flag.resize(n)); BUILD_CHECK(d_pos.resize(n)); BUILD_CHECK(d_scalars.resize(2)); BUILD_CHECK(d_nearest.resize(n));
         for (int k = 0; k < 2; ++k) { BUILD_CHECK(d_link[k].resize(n)); BUILD_CHECK(d_depth[k].resize(n)); BUILD_CHECK(d_box[k].resize(n)); }
@@ -841,7 +851,7 @@ int build_accel(Context* ctx) {
         if (try_ploc) {
 #define PLOC_CHECK(expr) BUILD_CHECK(expr)
             PLOC_CHECK(cudaMemsetAsync(d_flag.ptr, 0, sizeof(uint32_t) * n, st));
-            ploc_mark_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_flag.ptr);
+            ploc_mark_kernel<<<full_grid(n - 1), block, 0, st>>>(n, leaf_max, d_tree.ptr, d_flag.ptr);
             sort::exclusive_scan(d_flag.ptr, d_pos.ptr, (uint32_t)n, nullptr, d_scan_temp.ptr, d_scan_total.ptr, ctx->sm_count, st);
             uint32_t kept = 0; // number of flags set = the scan's grand total
             PLOC_CHECK(cudaMemcpyAsync(&kept, d_scan_total.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -850,7 +860,7 @@ int build_accel(Context* ctx) {
             ctx->counters.kernel_launches += 1 + sort::SCAN_LAUNCHES;
             if (m >= 2) {
                 // m - 1 nodes from index 1 on, the root is copied to index 0: A.nodes holds n + 1 entries
-                ploc_gather_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, d_pos.ptr, d_link[0].ptr, d_box[0].ptr,
+                ploc_gather_kernel<<<full_grid(n - 1), block, 0, st>>>(n, leaf_max, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, d_pos.ptr, d_link[0].ptr, d_box[0].ptr,
                                                                        d_depth[0].ptr);
                 int h_scalars[2] = { 1, 0 }; // next node index, deepest cluster
                 PLOC_CHECK(cudaMemcpyAsync(d_scalars.ptr, h_scalars, sizeof(h_scalars), cudaMemcpyHostToDevice, st));
@@ -908,7 +918,7 @@ int build_accel(Context* ctx) {
 #undef PLOC_CHECK
         }
         if (!ploc_done && n > 1) {
-            emit_kernel<<<full_grid(n - 1), block, 0, st>>>(n, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, A.nodes.ptr);
+            emit_kernel<<<full_grid(n - 1), block, 0, st>>>(n, leaf_max, d_tree.ptr, d_leaf_boxes.ptr, d_node_boxes.ptr, A.nodes.ptr);
             ctx->counters.kernel_launches++;
             A.node_count = n - 1; A.ploc_passes = 0; A.ploc_depth = 0;
         }
