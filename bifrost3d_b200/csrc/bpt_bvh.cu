@@ -2,8 +2,11 @@
 // batched intersection entry point.
 //
 // Build = flatten instances to world space -> centroid bounds -> 63-bit Morton codes -> radix sort ->
-// Karras' parallel radix tree (HPG 2012) -> bottom-up box fit -> emit 64-byte two-child nodes with subtrees
-// of <= LEAF_MAX triangles collapsed into leaves, and the Morton-ordered 48-byte triangle array.
+// Karras' parallel radix tree (HPG 2012) -> bottom-up box fit; its subtrees of at most two triangles (one on scenes above
+// 8 M triangles) are the leaf clusters -> PLOC (Meister and Bittner 2018) rebuilds the hierarchy above them, its passes
+// inside one cooperative launch -> 64-byte two-child nodes -> collapse to compressed eight-wide nodes (bpt_cw.cuh; the
+// triangle array is regrouped per node) for scenes from 131 072 triangles on, to 128-byte four-wide nodes below that.
+// Fallbacks: the plain Morton hierarchy when PLOC gives up, narrower nodes when a tree is too deep for a traversal stack.
 #include "bpt_context.h"
 #include "bpt_trace.cuh"
 #include <type_traits>
@@ -408,8 +411,8 @@ __global__ void ploc_begin_kernel(PlocState* __restrict__ state, uint32_t m) {
 // (nearest | merge + count | compact). Every block owns a contiguous chunk of the cluster list, so the order-preserving
 // compaction is a block-local scan plus the sum of the preceding blocks' counts, which every block adds up for itself -
 // as it does the grand total, so all blocks know the next pass's cluster count without reading it back from anywhere.
-// Measured on B200 at 1 M triangles (33 passes): 2.05 ms as a graph with a conditional WHILE node over the five stream
-// kernels (62 us per pass, mostly node-to-node latency), 2.4 ms as stream launches with a host read per pass.
+// Measured on B200 at 1 M triangles (33 passes): 1.26 ms; the five stream kernels of a pass as one graph with a conditional
+// WHILE node 2.05 ms (62 us per pass, mostly node-to-node latency), as stream launches with a host read per pass 2.4 ms.
 constexpr int PLOC_BLOCK = 512;
 
 __device__ __forceinline__ uint32_t ploc_block_exclusive_scan(uint32_t v, uint32_t* warp_sums /*[PLOC_BLOCK / 32]*/, uint32_t& total) {
