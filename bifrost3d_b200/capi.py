@@ -66,7 +66,7 @@ LIGHT_SPHERE, LIGHT_DIRECTIONAL, LIGHT_ENVIRONMENT, LIGHT_PRESAMPLED_ENVIRONMENT
 ENVIRONMENT_NEE_PRESAMPLED, ENVIRONMENT_NEE_CDF = 0, 1
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_mesh_emission", "bpt_remove_mesh", "bpt_set_instances",
-           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_set_hit_sorting", "bpt_build_accel", "bpt_accel_info", "bpt_accel_hierarchy", "bpt_render", "bpt_render_aov",
+           "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_set_hit_sorting", "bpt_build_accel", "bpt_accel_info", "bpt_accel_hierarchy", "bpt_read_accumulation", "bpt_write_accumulation", "bpt_render", "bpt_render_aov",
            "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect", "bpt_sort_pairs", "bpt_exclusive_scan", "bpt_compare_images"]
@@ -141,6 +141,8 @@ def load_library():
     lib.bpt_build_accel.argtypes = [vp]
     lib.bpt_accel_info.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(C.c_float)]
     lib.bpt_accel_hierarchy.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32)]
+    lib.bpt_read_accumulation.argtypes = [vp, vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.bpt_write_accumulation.argtypes = [vp, i32, i32, vp]
     lib.bpt_render.argtypes = [vp, C.POINTER(Camera), C.POINTER(Settings), i32, i32, u32, u32, i32]
     lib.bpt_render_aov.argtypes = [vp, C.POINTER(Camera), i32, i32, i32, u32, u32, i32]
     lib.bpt_accumulation_device_ptr.argtypes = [vp]; lib.bpt_accumulation_device_ptr.restype = vp
@@ -328,6 +330,20 @@ class Bpt:
         self._check(self.lib.bpt_accel_hierarchy(self.h, C.byref(kind), C.byref(wide_nodes), C.byref(levels)))
         return {"triangles": t.value, "nodes": n.value, "build_ms": ms.value,
                 "node_width": kind.value, "traversed_nodes": wide_nodes.value, "levels": levels.value}
+
+    # ---- checkpoint / resume ----
+    def read_accumulation(self):
+        """The selected target's state: float64 [height, width, 4] (radiance sums, sample count)."""
+        w, h = C.c_int32(), C.c_int32()
+        self._check(self.lib.bpt_read_accumulation(self.h, None, C.byref(w), C.byref(h)))
+        sums = np.empty((h.value, w.value, 4), np.float64)
+        self._check(self.lib.bpt_read_accumulation(self.h, _ptr(sums), C.byref(w), C.byref(h)))
+        return sums
+
+    def write_accumulation(self, sums):
+        sums = np.ascontiguousarray(sums, np.float64)
+        assert sums.ndim == 3 and sums.shape[2] == 4
+        self._check(self.lib.bpt_write_accumulation(self.h, sums.shape[1], sums.shape[0], _ptr(sums)))
 
     # ---- rendering ----
     def render(self, camera, width, height, first_sample, sample_count, max_bounces=4, nee_samples=3, pdf_scale=0.5, reset=False,

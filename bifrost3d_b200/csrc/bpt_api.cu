@@ -796,6 +796,34 @@ int bpt_select_accumulation(bpt_ctx* c, int slot) {
     return BPT_OK;
 }
 
+int bpt_read_accumulation(bpt_ctx* c, double* sums, int* out_width, int* out_height) {
+    Context* ctx = as_context(c);
+    if (out_width) *out_width = ctx->width;
+    if (out_height) *out_height = ctx->height;
+    if (!sums) return BPT_OK;
+    const size_t count = 4ull * (size_t)ctx->width * (size_t)ctx->height;
+    if (count == 0 || !ctx->accumulation.ptr) return ctx->fail(BPT_ERROR_NOT_READY, "bpt_read_accumulation: nothing rendered into the selected target");
+    cudaSetDevice(ctx->device);
+    // the main stream is ordered behind every sample's accumulation, whichever lane rendered it
+    BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(sums, ctx->accumulation.ptr, count * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return BPT_OK;
+}
+
+int bpt_write_accumulation(bpt_ctx* c, int width, int height, const double* sums) {
+    Context* ctx = as_context(c);
+    if (width <= 0 || height <= 0 || !sums || (int64_t)width * height > 0x7fffffffll)
+        return ctx->fail(BPT_ERROR_INVALID_ARGUMENT, "bpt_write_accumulation: bad arguments");
+    cudaSetDevice(ctx->device);
+    const size_t count = 4ull * (size_t)width * (size_t)height;
+    if (ctx->accumulation.capacity < count) BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // the old buffer may still be in use
+    BPT_CUDA_CHECK(ctx, ctx->accumulation.resize(count));
+    ctx->width = width; ctx->height = height; ctx->half4_scale = 1.0f;
+    BPT_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->accumulation.ptr, sums, count * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    BPT_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); // `sums` is the caller's memory
+    return BPT_OK;
+}
+
 int bpt_release_accumulation(bpt_ctx* c, int slot) {
     Context* ctx = as_context(c);
     cudaSetDevice(ctx->device);

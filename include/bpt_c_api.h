@@ -244,6 +244,15 @@ int bpt_select_accumulation(bpt_ctx* ctx, int slot);
 int bpt_release_accumulation(bpt_ctx* ctx, int slot);
 /* Device pointer to the double4[width*height] accumulation (sum) buffer, e.g. for an NCCL reduce. */
 void* bpt_accumulation_device_ptr(bpt_ctx* ctx);
+/* Checkpoint / resume of a progressive render. The resumable state of the reference is its accumulation buffer and the
+ * `accumulations` count (Renderer.cpp:200-205,1262); here it is the selected target's double4 sums (xyz = radiance sum,
+ * w = samples) and its size. A sample is a pure function of (pixel, accumulation index, scene) (Types.h:452-459), so a
+ * render resumed from a saved state with first_sample = the number of samples it holds continues bit for bit as if it had
+ * never stopped. bpt_read_accumulation waits for the rendering enqueued so far and copies 4 * width * height doubles to the
+ * host (out_width / out_height report the size; pass sums = NULL to query it); bpt_write_accumulation replaces the selected
+ * target with the given state. */
+int bpt_read_accumulation(bpt_ctx* ctx, double* sums, int* out_width, int* out_height);
+int bpt_write_accumulation(bpt_ctx* ctx, int width, int height, const double* sums);
 /* ---- multi-GPU: sample-index sharding -------------------------------------------------------------
  * The reference renders on one device (Renderer.cpp:289-291). Here every rank (one process per GPU) uploads the same scene,
  * renders a disjoint range of accumulation indices (`first_sample`) into its own fp64 sum buffer, and ONE collective adds the
