@@ -390,6 +390,8 @@ def main():
         ctx.reduce_accumulation(0)
     e1.record(stream)
     barrier()
+    if distributed:
+        ctx.comm_check()  # an asynchronous NCCL error (a lost peer, a link error) fails the run instead of a wrong image
     device_ms = e0.elapsed_time(e1)
     clocks = sampler.summary()
     counters = ctx.counters()

@@ -67,7 +67,7 @@ ENVIRONMENT_NEE_PRESAMPLED, ENVIRONMENT_NEE_CDF = 0, 1
 
 EXPORTS = ["bpt_create", "bpt_destroy", "bpt_last_error", "bpt_stream", "bpt_set_tables", "bpt_set_dielectric_tables", "bpt_upload_texture", "bpt_destroy_texture", "bpt_texture_sample", "bpt_upload_mesh", "bpt_set_mesh_emission", "bpt_remove_mesh", "bpt_set_instances",
            "bpt_set_materials", "bpt_set_lights", "bpt_set_environment", "bpt_set_environment_cdfs", "bpt_set_environment_sampling", "bpt_set_hit_sorting", "bpt_build_accel", "bpt_accel_info", "bpt_accel_hierarchy", "bpt_read_accumulation", "bpt_write_accumulation", "bpt_render", "bpt_render_aov",
-           "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
+           "bpt_accumulation_device_ptr", "bpt_select_accumulation", "bpt_release_accumulation", "bpt_comm_unique_id", "bpt_comm_init", "bpt_comm_destroy", "bpt_comm_check", "bpt_reduce_accumulation", "bpt_resolve_half4", "bpt_resolve_half4_async", "bpt_wait_frame", "bpt_resolve_float4", "bpt_resolve_tonemapped", "bpt_tonemap_colors", "bpt_synchronize", "bpt_set_profiling", "bpt_get_counters",
            "bpt_bsdf_eval_sample_pdf", "bpt_default_shading_regularized", "bpt_light_sample_pdf_evaluate", "bpt_rng_sample4",
            "bpt_intersect", "bpt_sort_pairs", "bpt_exclusive_scan", "bpt_compare_images"]
 
@@ -149,6 +149,7 @@ def load_library():
     lib.bpt_comm_unique_id.argtypes = [vp]
     lib.bpt_comm_init.argtypes = [vp, vp, i32, i32]
     lib.bpt_comm_destroy.argtypes = [vp]
+    lib.bpt_comm_check.argtypes = [vp]
     lib.bpt_reduce_accumulation.argtypes = [vp, i32]
     lib.bpt_compare_images.argtypes = [vp, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp]
     lib.bpt_sort_pairs.argtypes = [vp, i64, vp, vp, i32, i32]
@@ -378,6 +379,10 @@ class Bpt:
 
     def comm_destroy(self):
         self._check(self.lib.bpt_comm_destroy(self.h))
+
+    def comm_check(self):
+        """Raises if NCCL has recorded an asynchronous error on the communicator."""
+        self._check(self.lib.bpt_comm_check(self.h))
 
     def reduce_accumulation(self, root=0):
         """Sum of all ranks' selected accumulation targets into `root` (ncclReduce on the render stream); root < 0: all-reduce."""

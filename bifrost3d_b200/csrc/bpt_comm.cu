@@ -29,6 +29,7 @@ struct Nccl {
     int (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
+    int (*CommGetAsyncError)(ncclComm_t, int*) = nullptr; // optional: absent from very old NCCL builds
     std::string error;
 };
 
@@ -50,6 +51,7 @@ Nccl* nccl() {
     n.Reduce = reinterpret_cast<decltype(n.Reduce)>(sym("ncclReduce"));
     n.AllReduce = reinterpret_cast<decltype(n.AllReduce)>(sym("ncclAllReduce"));
     n.GetErrorString = reinterpret_cast<decltype(n.GetErrorString)>(sym("ncclGetErrorString"));
+    n.CommGetAsyncError = reinterpret_cast<decltype(n.CommGetAsyncError)>(dlsym(n.handle, "ncclCommGetAsyncError"));
     return &n;
 }
 
@@ -99,6 +101,18 @@ int bpt_comm_destroy(bpt_ctx* c) {
     int status = nccl()->CommDestroy(static_cast<ncclComm_t>(ctx->comm));
     ctx->comm = nullptr; ctx->comm_rank = 0; ctx->comm_rank_count = 1;
     return status == NCCL_SUCCESS ? BPT_OK : nccl_fail(ctx, "ncclCommDestroy", status);
+}
+
+int bpt_comm_check(bpt_ctx* c) {
+    Context* ctx = as_context(c);
+    if (!ctx->comm) return BPT_OK;
+    Nccl* n = nccl();
+    if (!n->CommGetAsyncError) return BPT_OK;
+    int async_status = NCCL_SUCCESS;
+    int status = n->CommGetAsyncError(static_cast<ncclComm_t>(ctx->comm), &async_status);
+    if (status != NCCL_SUCCESS) return nccl_fail(ctx, "ncclCommGetAsyncError", status);
+    if (async_status != NCCL_SUCCESS) return nccl_fail(ctx, "the communicator reports an asynchronous error", async_status);
+    return BPT_OK;
 }
 
 int bpt_reduce_accumulation(bpt_ctx* c, int root) {

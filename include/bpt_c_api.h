@@ -265,6 +265,10 @@ enum { BPT_COMM_ID_BYTES = 128 }; /* sizeof(ncclUniqueId) */
 int bpt_comm_unique_id(char out_id[BPT_COMM_ID_BYTES]);
 int bpt_comm_init(bpt_ctx* ctx, const char id[BPT_COMM_ID_BYTES], int rank_count, int rank);
 int bpt_comm_destroy(bpt_ctx* ctx);
+/* Failure detection: BPT_OK, or the asynchronous error NCCL has recorded on the communicator (a peer that died, a link error;
+ * ncclCommGetAsyncError). A collective is only enqueued by bpt_reduce_accumulation, so a host that wants to know whether the
+ * combine went through calls this after bpt_synchronize. BPT_OK without a communicator. */
+int bpt_comm_check(bpt_ctx* ctx);
 /* ncclReduce(sum, fp64) of the selected accumulation target into rank `root`'s, in place, enqueued on the context's stream
  * after the samples already enqueued (no host synchronisation); root < 0: ncclAllReduce, every rank gets the total.
  * All ranks must call it with the same frame size. Call it once per job: the root's buffer then already holds the total. */
