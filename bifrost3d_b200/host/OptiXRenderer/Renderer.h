@@ -81,6 +81,13 @@ public:
     // Writes the current mean of `camera`'s accumulation to `target` without rendering another sample.
     bool resolve_accumulation(CameraID camera, optix::Buffer target);
 
+    // ---- addition: checkpoint / resume ---------------------------------------------------------------------------------
+    // The reference's resumable state - a camera's accumulation buffer and its `accumulations` count (Renderer.cpp:200-205,
+    // 1262) - written to / restored from a file. A sample is a pure function of (pixel, accumulation index, scene), so the
+    // render continues after load_accumulation exactly as if it had never stopped (same scene and camera assumed).
+    bool save_accumulation(CameraID camera, const std::filesystem::path& file);
+    bool load_accumulation(CameraID camera, const std::filesystem::path& file);
+
 private:
     Renderer(int cuda_device_ID, const std::filesystem::path& data_directory);
 

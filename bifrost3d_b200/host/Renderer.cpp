@@ -606,4 +606,54 @@ bool Renderer::resolve_accumulation(CameraID camera_ID, optix::Buffer target) {
     return status == BPT_OK;
 }
 
+
+namespace {
+struct CheckpointHeader { char magic[8]; int32_t width, height; uint32_t accumulations; uint32_t reserved; };
+const char CHECKPOINT_MAGIC[8] = { 'B', 'P', 'T', 'A', 'C', 'C', '1', 0 };
+}
+
+bool Renderer::save_accumulation(CameraID camera_ID, const std::filesystem::path& file) {
+    m_impl->conditional_per_camera_state_resize(camera_ID);
+    const Implementation::CameraState& state = m_impl->per_camera_state[camera_ID];
+    Implementation::check(m_impl->ctx, bpt_select_accumulation(m_impl->ctx, int((unsigned int)camera_ID)), "bpt_select_accumulation");
+    CheckpointHeader header = {};
+    memcpy(header.magic, CHECKPOINT_MAGIC, sizeof(header.magic));
+    if (bpt_read_accumulation(m_impl->ctx, nullptr, &header.width, &header.height) != BPT_OK || header.width <= 0 || header.height <= 0) return false;
+    header.accumulations = state.accumulations;
+    std::vector<double> sums(4ull * header.width * header.height);
+    int status = bpt_read_accumulation(m_impl->ctx, sums.data(), nullptr, nullptr);
+    Implementation::check(m_impl->ctx, status, "bpt_read_accumulation");
+    if (status != BPT_OK) return false;
+    FILE* f = fopen(file.string().c_str(), "wb");
+    if (!f) return false;
+    bool ok = fwrite(&header, sizeof(header), 1, f) == 1 && fwrite(sums.data(), sizeof(double), sums.size(), f) == sums.size();
+    return fclose(f) == 0 && ok;
+}
+
+bool Renderer::load_accumulation(CameraID camera_ID, const std::filesystem::path& file) {
+    FILE* f = fopen(file.string().c_str(), "rb");
+    if (!f) return false;
+    CheckpointHeader header = {};
+    std::vector<double> sums;
+    bool ok = fread(&header, sizeof(header), 1, f) == 1 && memcmp(header.magic, CHECKPOINT_MAGIC, sizeof(header.magic)) == 0 &&
+              header.width > 0 && header.height > 0 && (int64_t)header.width * header.height <= 0x7fffffffll;
+    if (ok) {
+        sums.resize(4ull * header.width * header.height);
+        ok = fread(sums.data(), sizeof(double), sums.size(), f) == sums.size();
+    }
+    fclose(f);
+    if (!ok) return false;
+    Implementation::check(m_impl->ctx, bpt_select_accumulation(m_impl->ctx, int((unsigned int)camera_ID)), "bpt_select_accumulation");
+    int status = bpt_write_accumulation(m_impl->ctx, header.width, header.height, sums.data());
+    Implementation::check(m_impl->ctx, status, "bpt_write_accumulation");
+    if (status != BPT_OK) return false;
+    // the camera continues from the restored count: frame size and view as they are now, or render() would start over
+    m_impl->conditional_per_camera_state_resize(camera_ID);
+    Implementation::CameraState& state = m_impl->per_camera_state[camera_ID];
+    state.frame_size = Vector2i(header.width, header.height);
+    state.inverse_view_projection_matrix = Cameras::get_inverse_view_projection_matrix(camera_ID);
+    state.accumulations = header.accumulations;
+    return true;
+}
+
 } // namespace OptiXRenderer

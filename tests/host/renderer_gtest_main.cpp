@@ -180,6 +180,32 @@ TEST_F(RendererFixture, b200_two_cameras_keep_their_own_accumulation) {
     EXPECT_EQ(4u, renderer->render(camera_b, target_b, size_b));
 }
 
+// Checkpoint / resume: a render that is saved after three samples, carried on, rolled back to the saved state and carried on
+// again arrives at the same pixels (a sample is a pure function of pixel, accumulation index and scene).
+TEST_F(RendererFixture, b200_checkpoint_and_resume) {
+    using namespace Bifrost;
+    using namespace Bifrost::Scene;
+
+    auto size = Math::Vector2i(6, 5);
+    CameraID camera_ID = create_ortho_camera_with_quad_scene(size, optix::make_float3(0.25f, 0.5f, 0.75f));
+    renderer->handle_updates();
+    auto target = create_render_target(renderer, size);
+    for (unsigned int frame = 1; frame <= 3; ++frame) EXPECT_EQ(frame, renderer->render(camera_ID, target, size));
+    const std::filesystem::path file = std::filesystem::temp_directory_path() / "bpt_checkpoint_gtest.bin";
+    ASSERT_TRUE(renderer->save_accumulation(camera_ID, file));
+    EXPECT_EQ(4u, renderer->render(camera_ID, target, size));
+    EXPECT_EQ(5u, renderer->render(camera_ID, target, size));
+    std::vector<unsigned short> uninterrupted(4 * size.x * size.y);
+    memcpy(uninterrupted.data(), target->map(), uninterrupted.size() * sizeof(unsigned short)); target->unmap();
+
+    ASSERT_TRUE(renderer->load_accumulation(camera_ID, file)); // back to three samples
+    EXPECT_EQ(4u, renderer->render(camera_ID, target, size));
+    EXPECT_EQ(5u, renderer->render(camera_ID, target, size));
+    EXPECT_EQ(0, memcmp(uninterrupted.data(), target->map(), uninterrupted.size() * sizeof(unsigned short))); target->unmap();
+    EXPECT_FALSE(renderer->load_accumulation(camera_ID, file.string() + ".missing"));
+    std::filesystem::remove(file);
+}
+
 } // namespace OptiXRenderer
 
 // tests/OptiXRendererTests/Utils.cpp uses windows.h; the data directory is unused by this implementation.
