@@ -36,11 +36,12 @@ def test_textures_and_environment_maps_through_the_core_managers():
     """Cases added to the reference's fixture (tests/host/renderer_gtest_main.cpp): a tint texture created through
     Images / Textures / Materials shows up in the TintVisualization backend, and a SceneRoot environment map is presampled
     through the core's InfiniteAreaLight and lights the background; material and transform edits reach the next frame
-    through the incremental handle_updates; two cameras keep their own accumulation targets."""
+    through the incremental handle_updates; two cameras keep their own accumulation targets; a render rolled back to a saved
+    accumulation state (Renderer::save_accumulation / load_accumulation) arrives at the same pixels."""
     out = subprocess.run([str(BINARY), "--gtest_filter=*b200_*"], capture_output=True, text=True, timeout=300)
     print(out.stdout[-2500:])
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
-    assert "[  PASSED  ] 4 tests." in out.stdout
+    assert "[  PASSED  ] 5 tests." in out.stdout
 
 
 def test_host_shim_exports_the_reference_api():
