@@ -3,12 +3,13 @@
 Test infrastructure only: used as the checker, never as the thing measured or shipped.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 REPO = Path(__file__).resolve().parent.parent
-LIB_PATH = REPO / "oracle" / "_ref" / "libbifrost_ref.so"
+LIB_PATH = Path(os.environ["BPT_ORACLE_LIB"]) if os.environ.get("BPT_ORACLE_LIB") else REPO / "oracle" / "_ref" / "libbifrost_ref.so"  # the override: a sanitizer build
 
 _lib = None
 
