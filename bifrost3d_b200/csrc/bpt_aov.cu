@@ -4,6 +4,12 @@
 // (Renderer.cpp:1267-1358). Like the reference they follow the camera ray through rejected hits (back faces, stochastic
 // coverage: MonteCarlo.cu:146-164) until the first accepted surface, then accumulate the feature in the same fp64 buffer.
 // Not a hot path: one thread per pixel, the whole loop in one kernel.
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include "bpt_context.h"
 #include "bpt_lights.cuh"
 #include "bpt_rng.cuh"

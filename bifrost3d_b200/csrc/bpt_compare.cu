@@ -8,6 +8,12 @@
 // results agree to fp64 rounding (tests: 1e-6 relative), not bit for bit. Two properties of the header are kept as they are:
 // the window of mssim is [p - support, p + support) - exclusive at the upper end - and its Gaussian weight is
 // exp(+d^2 / (2 sigma^2)) / sqrt(2 pi sigma^2) with a POSITIVE exponent (:150-152).
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include "bpt_context.h"
 #include "bpt_math.cuh"
 #include "../../include/bpt_c_api.h"

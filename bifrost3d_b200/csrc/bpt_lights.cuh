@@ -6,6 +6,12 @@
 //   ray/sphere, ray/plane, ray/disk  .../Intersect.h:23-67
 //   TBN          .../TBN.h:27-58, compute_tangents Utils.h:347-356
 //   environment  .../PresampledEnvironmentLightImpl.h:17-55, latlong mapping Utils.h:288-301
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #pragma once
 #include "bpt_context.h"
 #include "bpt_shading.cuh"

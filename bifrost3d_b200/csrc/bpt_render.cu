@@ -14,6 +14,12 @@
 // never synchronises inside bpt_render, and the shadow rays of bounce k - 1 are traced concurrently with the closest-hit
 // rays of bounce k (both only depend on shade(k - 1)). Queues are compacted with warp ballot + one atomic per warp.
 // Path state is SoA, indexed by pixel, in 16-byte records so every access is a 128-bit transaction.
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include "bpt_context.h"
 #include "bpt_lights.cuh"
 #include "bpt_rng.cuh"

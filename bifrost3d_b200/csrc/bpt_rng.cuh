@@ -12,6 +12,12 @@
 //          warp-uniform, so every read is a constant-cache broadcast. The numbers are not copied from
 //          the reference: they are generated at compile time from the Joe-Kuo primitive polynomials
 //          (dim 2: x^2+x+1, m = {1,3}; dim 3: x^3+x+1, m = {1,3,1}) and checked against the oracle.
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #pragma once
 #include "bpt_math.cuh"
 

@@ -13,6 +13,12 @@
 //   fresnel / coat helpers .../Utils.h:129-190,363-367
 // The rho / alpha tables are sampled like the reference's HOST branch: float tables with the
 // software bilinear of core/Bifrost/Bifrost/Math/ImageSampling.h:18-41 (not unorm16 textures).
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #pragma once
 #include "bpt_math.cuh"
 #include "bpt_types.h"

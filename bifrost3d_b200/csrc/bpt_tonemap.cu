@@ -3,6 +3,12 @@
 // TonemappingMode :18, filmic :161-224, AgX :236-265, Khronos neutral :272-291), which the reference applies to the
 // renderer's output outside OptiXRenderer (DX11Renderer compositor). They are restated here for fp32 on the device; the
 // parity test drives the reference header itself on the same colours (tests/test_tonemap.py).
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include "bpt_context.h"
 #include "bpt_math.cuh"
 

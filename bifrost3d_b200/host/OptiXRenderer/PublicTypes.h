@@ -1,5 +1,11 @@
 // Public POD types of the renderer, API compatible with the reference's
 // extensions/OptiXRenderer/OptiXRenderer/PublicTypes.h:20-58 (same names, enumerators and members).
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #ifndef _OPTIXRENDERER_PUBLIC_TYPES_H_
 #define _OPTIXRENDERER_PUBLIC_TYPES_H_
 

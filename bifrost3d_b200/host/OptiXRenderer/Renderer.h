@@ -2,6 +2,12 @@
 // libbpt.so (include/bpt_c_api.h). Class name, method names, argument types and behaviour follow the reference so that code
 // written against it (DX11OptiXAdaptor, tests/OptiXRendererTests/RendererTest.h) compiles and links unchanged; there is no
 // OptiX underneath, `optix::Buffer` / `optix::Context` are the small facade types of host/optix_facade.
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #pragma once
 
 #include <OptiXRenderer/PublicTypes.h>

@@ -5,6 +5,12 @@
 // OptiX scene graph. Scene synchronisation is incremental at the granularity of the C ABI: meshes and textures are uploaded
 // once and stay resident, a material edit uploads the material records only, and a transform or model change re-flattens the
 // resident meshes and rebuilds the BVH on the device (the counterpart of the reference's acceleration refit).
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include <OptiXRenderer/Renderer.h>
 
 #include <optixu/optixpp_namespace.h>

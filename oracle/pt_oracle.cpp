@@ -12,6 +12,12 @@
 //                 Woop, Benthin, Wald (JCGT 2013) in plain IEEE fp32 and resolving the closest hit as
 //                 min (t, global primitive index).
 // Scenes are flattened to world space (instance-major primitive order) with the same rounding as the product.
+// ---------------------------------------------------------------------------
+// The arithmetic restated in this file follows Bifrost3D (https://github.com/papaboo/Bifrost3D), which carries this notice:
+//   Copyright (C) Bifrost. See AUTHORS.txt for authors.
+//   This program is open source and distributed under the New BSD License. See LICENSE.txt for more detail.
+// The notice and the licence terms are reproduced in NOTICE.md at the root of this repository.
+// ---------------------------------------------------------------------------
 #include <OptiXRenderer/MonteCarlo.h>
 #include <OptiXRenderer/RNG.h>
 #include <OptiXRenderer/Intersect.h>
