@@ -87,6 +87,18 @@ def test_bsdf_matches_reference(bpt, ref, name, n):
 
 
 @pytest.mark.skipif(not oracle_lib.available(), reason="oracle/_ref not built")
+def test_default_shading_matches_reference_at_the_full_c1_size(bpt, ref):
+    """BASELINE.json configs[0] at the size bench.py --workload bsdf runs it: 2^22 DefaultShading tuples (with coat) against the
+    reference's host-compiled headers, same tolerances as the smaller batches."""
+    n = 1 << 22
+    t = bsdf_tuples(n, seed=1234, with_coat=True)
+    got = bpt.bsdf_eval_sample_pdf(KINDS["default"], t["wo"], t["wi"], t["tint"], t["rms"], t["u"], coat=t["coat"])
+    want = ref.bsdf_eval_sample_pdf(KINDS["default"], t["wo"], t["wi"], t["tint"], t["rms"], t["u"], coat=t["coat"])
+    for m in compare_bsdf(got, want, f"default[n={n}]"):
+        print(m)
+
+
+@pytest.mark.skipif(not oracle_lib.available(), reason="oracle/_ref not built")
 def test_default_shading_regression_vectors_on_gpu(bpt, ref):
     """The reference's own golden vectors (DefaultShadingTest.h:410-447), 1e-4 relative as in the reference test."""
     from tests.test_oracle_reference import regression_inputs
