@@ -1,7 +1,10 @@
 #!/bin/bash
 # A/B of the compressed eight-wide nodes against the four-wide ones on one B200 (run through gpurun): the GPU tests first,
 # then one bench line per workload and node format, then the prepared build variants (bifrost3d_b200/variants/*.so, built
-# here with `make OUT=... BUILD=... EXTRA=...`). Every run keeps its exit code and stderr.
+# here with `make -C bifrost3d_b200/csrc OUT=../variants/libbpt_<name>.so BUILD=build_<name> EXTRA="-D..."`: nospec =
+# -DBPT_CW_SPECULATE=0 and the mbN = -DBPT_TRACE_MIN_BLOCKS=N variants of this script were measured in round 2 (profiles/
+# r02_ab_node_formats.txt) and their switches have since been removed from the source; tools/ab_variants.sh is the general form).
+# Every run keeps its exit code and stderr.
 R=${1:-r02cw}
 O=gpurun_out; mkdir -p $O
 python -m pytest tests -m gpu -q -rA -x > $O/${R}_pytest_gpu_full.log 2>&1; echo "pytest rc=$?" > $O/${R}_pytest_gpu.log
